@@ -1,0 +1,243 @@
+// a13 / config 2: the fused single-pass pipeline
+//     NV12/NV21 -> BGR (u8) -> resize INTER_LINEAR (u8) -> u8->fp32 -> normalize -> HWC->CHW
+// reference chain: cvt_color.cpp:39-135 -> resize_naive.cpp:10-68 -> tensor.cpp:459-502 ->
+// normalize_naive.cpp:74-90 -> tensor.cpp:160-170 (five passes over HBM); here: one read of the NV12 frame, one
+// write of the fp32 planes, every intermediate stays in registers / shared memory.
+//
+// Bit-exactness: each of the four taps is converted to BGR and clamped to u8 exactly as the unfused chain would
+// have stored it; the bilinear MAC is the reference's integer expression regrouped row-wise
+//     (p00*cx0 + p01*cx1)*cy0 + (p10*cx0 + p11*cx1)*cy1          (same integer, no overflow: < 2^31)
+// then >>22 gives the u8 the chain would have stored, and the final value is table[c][u8], the table holding the
+// reference's exact (float)((double)(x-mean)/((double)std+1e-6)) for the 256 possible inputs.
+//
+// Work decomposition: a CTA owns TH output rows x TW output columns of one frame.  It stages the source rows those
+// outputs touch (a contiguous band of the Y plane and of the interleaved chroma plane) in shared memory with
+// 128-bit loads, so every HBM sector is fetched once and the 2x2 gathers, the shared chroma and the row reuse
+// between consecutive output rows are served on chip.  Each thread owns output columns and walks down the rows,
+// carrying the horizontally interpolated row (3 ints) over when the next output row starts on it.
+// Stores: lanes = consecutive columns -> 128 B per warp per plane, streaming.
+#include "vacv_common.cuh"
+
+namespace vacv {
+
+struct FusedGeom {
+    int w, h, wo, ho;
+    int TW, TH;            // output tile
+    int ypitch, cpitch;    // shared-memory row pitch (bytes) of the Y / chroma bands
+    int yrows, crows;      // band capacity in rows
+    int vec;               // 1: 16-byte staging legal (w % 16 == 0, aligned base)
+};
+
+template <bool kVFirst>
+__device__ __forceinline__ void hrow(const uint8_t* __restrict__ yrow, const uint8_t* __restrict__ crow,
+                                     int yo, int ca, int cb, int cx0, int cx1, int (&H)[3]) {
+    const int Y0 = yrow[yo], Y1 = yrow[yo + 1];
+    const unsigned pa = *reinterpret_cast<const uint16_t*>(crow + ca);
+    const unsigned pb = *reinterpret_cast<const uint16_t*>(crow + cb);
+    const ChromaTerms ta = kVFirst ? chroma_terms(pa & 0xff, pa >> 8) : chroma_terms(pa >> 8, pa & 0xff);
+    const ChromaTerms tb = kVFirst ? chroma_terms(pb & 0xff, pb >> 8) : chroma_terms(pb >> 8, pb & 0xff);
+    H[0] = clamp255(Y0 + ta.ba) * cx0 + clamp255(Y1 + tb.ba) * cx1;
+    H[1] = clamp255(Y0 - ta.ga) * cx0 + clamp255(Y1 - tb.ga) * cx1;
+    H[2] = clamp255(Y0 + ta.ra) * cx0 + clamp255(Y1 + tb.ra) * cx1;
+}
+
+template <bool kVFirst>
+__global__ void __launch_bounds__(320) nv_resize_normalize_chw_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst,
+                                                                       FusedGeom g, const float* __restrict__ mean,
+                                                                       const float* __restrict__ stddev) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    float* lut = reinterpret_cast<float*>(smem);                       // [3][256]
+    int* s_sy = reinterpret_cast<int*>(smem + 3072);                   // [TH]
+    int* s_cy = s_sy + g.TH;                                           // [TH]  cy0 | cy1 << 16
+    int* s_misc = s_cy + g.TH;                                         // [4]   sx_first, sx_last
+    uint8_t* ybuf = smem + 3072 + ((8 * g.TH + 16 + 15) & ~15);
+    uint8_t* cbuf = ybuf + (size_t)g.yrows * g.ypitch;
+
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int tiles_x = (g.wo + g.TW - 1) / g.TW;
+    const int dx0 = (blockIdx.x % tiles_x) * g.TW, dy0 = (blockIdx.x / tiles_x) * g.TH;
+    const int tw = min(g.TW, g.wo - dx0), th = min(g.TH, g.ho - dy0);
+    const size_t frame = blockIdx.y;
+    const uint8_t* yplane = src + frame * ((size_t)g.w * g.h * 3 / 2);
+    const uint8_t* cplane = yplane + (size_t)g.w * g.h;
+
+    // ---- coefficients (resize_naive.cpp:17-53) + normalisation table
+    const double scale_x = (double)((float)g.w / (float)g.wo), scale_y = (double)((float)g.h / (float)g.ho);
+    if (tid < th) {
+        int s; float f;
+        linear_coord(dy0 + tid, scale_y, g.h, s, f);
+        s_sy[tid] = s;
+        s_cy[tid] = (sat_short((1.f - f) * 2048.f) & 0xffff) | (sat_short(2048.f * f) << 16);
+    } else if (tid == nthr - 1) {
+        int s; float f;
+        linear_coord(dx0, scale_x, g.w, s, f); s_misc[0] = s;
+        linear_coord(dx0 + tw - 1, scale_x, g.w, s, f); s_misc[1] = s;
+    }
+    for (int t = tid; t < 768; t += nthr)
+        lut[t] = normalize_one((float)(t & 255), __ldg(mean + (t >> 8)), (double)__ldg(stddev + (t >> 8)) + 1e-6);
+    __syncthreads();
+
+    // ---- stage the source band
+    const int y_first = s_sy[0], y_last = s_sy[th - 1] + 1;            // Y rows [y_first, y_last]
+    const int c_first = y_first >> 1, c_last = y_last >> 1;            // chroma rows
+    const int xb0 = s_misc[0] & ~15;                                   // Y byte columns [xb0, xb1)
+    const int xb1 = min((s_misc[1] + 2 + 15) & ~15, (g.w + 15) & ~15);
+    const int cb0 = xb0, cb1 = xb1;                                    // chroma bytes cover the same x range (2 bytes per 2 px)
+    const int ywidth = xb1 - xb0;
+    if (g.vec) {
+        const int cpr = ywidth >> 4;                                   // 16-byte chunks per row
+        const int ny = (y_last - y_first + 1) * cpr, nc = (c_last - c_first + 1) * cpr;
+        for (int i = tid; i < ny + nc; i += nthr) {
+            const bool isy = i < ny;
+            const int j = isy ? i : i - ny;
+            const int r = j / cpr, q = j - r * cpr;
+            const uint8_t* gp = (isy ? yplane + (size_t)(y_first + r) * g.w : cplane + (size_t)(c_first + r) * g.w) + xb0 + 16 * q;
+            uint8_t* sp = (isy ? ybuf + r * g.ypitch : cbuf + r * g.cpitch) + 16 * q;
+            *reinterpret_cast<uint4*>(sp) = ld_stream16(gp);
+        }
+    } else {
+        const int wy = min(xb1, g.w) - xb0;
+        const int ny = (y_last - y_first + 1) * wy, nc = (c_last - c_first + 1) * wy;
+        for (int i = tid; i < ny + nc; i += nthr) {
+            const bool isy = i < ny;
+            const int j = isy ? i : i - ny;
+            const int r = j / wy, q = j - r * wy;
+            if (isy) ybuf[r * g.ypitch + q] = __ldg(yplane + (size_t)(y_first + r) * g.w + xb0 + q);
+            else cbuf[r * g.cpitch + q] = __ldg(cplane + (size_t)(c_first + r) * g.w + cb0 + q);
+        }
+    }
+    (void)cb1;
+    __syncthreads();
+
+    // ---- compute: thread-owned columns, walk down the tile rows
+    const size_t plane = (size_t)g.wo * g.ho;
+    float* out = dst + frame * 3 * plane;
+    for (int col = tid; col < tw; col += nthr) {
+        const int dx = dx0 + col;
+        int sx; float fx;
+        linear_coord(dx, scale_x, g.w, sx, fx);
+        const int cx0 = sat_short((1.f - fx) * 2048.f), cx1 = sat_short(2048.f * fx);
+        const int yo = sx - xb0;
+        const int ca = (sx & ~1) - cb0, cb = ((sx + 1) & ~1) - cb0;
+        int H0[3], H1[3];
+        int have = -2;   // source row held in H1
+        for (int ty = 0; ty < th; ++ty) {
+            const int sy = s_sy[ty];
+            const int cy = s_cy[ty];
+            const int cy0 = (short)(cy & 0xffff), cy1 = cy >> 16;
+            if (sy == have) {   // the row below the previous output's pair is this output's top row
+                H0[0] = H1[0]; H0[1] = H1[1]; H0[2] = H1[2];
+            } else if (sy + 1 != have) {
+                hrow<kVFirst>(ybuf + (sy - y_first) * g.ypitch, cbuf + ((sy >> 1) - c_first) * g.cpitch, yo, ca, cb, cx0, cx1, H0);
+            }
+            if (sy + 1 != have) {
+                hrow<kVFirst>(ybuf + (sy + 1 - y_first) * g.ypitch, cbuf + (((sy + 1) >> 1) - c_first) * g.cpitch, yo, ca, cb, cx0, cx1, H1);
+                have = sy + 1;
+            }
+            const size_t o = (size_t)(dy0 + ty) * g.wo + dx;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int v = (H0[k] * cy0 + H1[k] * cy1) >> 22;
+                st_stream4f(out + k * plane + o, lut[k * 256 + (v & 0xff)]);
+            }
+        }
+    }
+}
+
+// ResizeNormalize::resize_normalize (resize_normalize.cpp:15-31): resize INTER_LINEAR u8 HWC -> fp32 normalised.
+// One CTA per (frame, band of output rows); exact table per CTA; taps through the read-only path.
+template <int C>
+__global__ void __launch_bounds__(256) resize_normalize_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst,
+                                                                int w, int h, int wo, int ho, int rows_per_cta,
+                                                                const float* __restrict__ mean, const float* __restrict__ stddev,
+                                                                int out_layout) {
+    __shared__ float lut[C][256];
+    for (int t = threadIdx.x; t < 256 * C; t += blockDim.x)
+        lut[t >> 8][t & 255] = normalize_one((float)(t & 255), __ldg(mean + (t >> 8)), (double)__ldg(stddev + (t >> 8)) + 1e-6);
+    __syncthreads();
+    const double scale_x = (double)((float)w / (float)wo), scale_y = (double)((float)h / (float)ho);
+    const uint8_t* img = src + (size_t)blockIdx.y * w * h * C;
+    const size_t plane = (size_t)wo * ho;
+    float* out = dst + (size_t)blockIdx.y * plane * C;
+    const int y0 = blockIdx.x * rows_per_cta, y1 = min(y0 + rows_per_cta, ho);
+    for (int i = y0 * wo + threadIdx.x; i < y1 * wo; i += blockDim.x) {
+        const int dy = i / wo, dx = i - dy * wo;
+        int sx, sy; float fx, fy;
+        linear_coord(dx, scale_x, w, sx, fx);
+        linear_coord(dy, scale_y, h, sy, fy);
+        const int cx0 = sat_short((1.f - fx) * 2048.f), cx1 = sat_short(2048.f * fx);
+        const int cy0 = sat_short((1.f - fy) * 2048.f), cy1 = sat_short(2048.f * fy);
+        const uint8_t* lt = img + ((size_t)sy * w + sx) * C;
+        const uint8_t* lb = lt + (size_t)w * C;
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            const int v = (__ldg(lt + k) * cx0 * cy0 + __ldg(lb + k) * cx0 * cy1 + __ldg(lt + C + k) * cx1 * cy0 +
+                           __ldg(lb + C + k) * cx1 * cy1) >> 22;
+            const float r = lut[k][v & 0xff];
+            if (out_layout == VACV_NHWC) out[(size_t)i * C + k] = r;
+            else st_stream4f(out + k * plane + i, r);
+        }
+    }
+}
+
+}  // namespace vacv
+
+using namespace vacv;
+
+extern "C" int vacv_cuda_nv_resize_normalize_chw(const uint8_t* src, float* dst, int batch, int w, int h, int v_first,
+                                                 int w_out, int h_out, const float* mean, const float* stddev, void* stream) {
+    VACV_REQUIRE(src && dst && mean && stddev, "nv_resize_normalize_chw: null pointer");
+    VACV_REQUIRE(batch > 0 && w >= 2 && h >= 2 && w_out > 0 && h_out > 0, "nv_resize_normalize_chw: bad size");
+    VACV_REQUIRE((w % 2) == 0 && (h % 2) == 0, "nv_resize_normalize_chw: w and h must be even (got %dx%d)", w, h);
+    VACV_REQUIRE(batch <= 65535, "nv_resize_normalize_chw: batch <= 65535 per call");
+    if (w_out == w && h_out == h)   // resize.cpp:58-61 memcpy shortcut == identity taps; not on the fused fast path
+        return set_error(VACV_ERR_UNSUPPORTED, "nv_resize_normalize_chw: same-size resize (compose cvt_nv2bgr + normalize + layout_change)");
+    FusedGeom g;
+    g.w = w; g.h = h; g.wo = w_out; g.ho = h_out;
+    g.vec = (w % 16) == 0 && (((uintptr_t)src) & 15) == 0;
+    const double sx = (double)w / w_out, sy = (double)h / h_out;
+    // tile: full output rows when the source span fits comfortably, else split in x
+    const int budget = 44 * 1024;   // ~4 CTAs / SM
+    int TW = w_out, TH = 8;
+    auto span = [](double scale, int n) { return (int)(scale * (n - 1)) + 4; };
+    auto bytes = [&](int tw, int th) {
+        const int yp = (span(sx, tw) + 32 + 15) & ~15;
+        const int yr = span(sy, th) + 1, cr = yr / 2 + 2;
+        return (size_t)yp * (yr + cr);
+    };
+    while (TH > 1 && bytes(TW, TH) > (size_t)budget) --TH;
+    while (TW > 32 && bytes(TW, TH) > (size_t)budget) TW = (TW + 1) / 2;
+    TW = (TW + 31) & ~31;
+    if (bytes(TW, TH) > 200 * 1024) return set_error(VACV_ERR_UNSUPPORTED, "nv_resize_normalize_chw: scale too large for the staged tile");
+    g.TW = TW; g.TH = TH;
+    g.ypitch = g.cpitch = (span(sx, TW) + 32 + 15) & ~15;
+    g.yrows = span(sy, TH) + 1; g.crows = g.yrows / 2 + 2;
+    const size_t smem = 3072 + ((8 * TH + 16 + 15) & ~15) + (size_t)g.ypitch * (g.yrows + g.crows);
+    int threads = 32 * max(1, min(10, (min(TW, w_out) + 63) / 64));   // ~2 columns per thread, <= 320
+    const int tiles = ceil_div(w_out, TW) * ceil_div(h_out, TH);
+    dim3 grid(tiles, batch);
+    cudaStream_t s = as_stream(stream);
+    auto kern = v_first ? nv_resize_normalize_chw_kernel<true> : nv_resize_normalize_chw_kernel<false>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return set_error(VACV_ERR_CUDA, "nv_resize_normalize_chw: %s", cudaGetErrorString(e));
+    }
+    kern<<<grid, threads, smem, s>>>(src, dst, g, mean, stddev);
+    return check_launch("nv_resize_normalize_chw");
+}
+
+extern "C" int vacv_cuda_resize_normalize(const uint8_t* src, float* dst, int batch, int w, int h, int c,
+                                          int w_out, int h_out, const float* mean, const float* stddev,
+                                          int out_layout, void* stream) {
+    VACV_REQUIRE(src && dst && mean && stddev, "resize_normalize: null pointer");
+    VACV_REQUIRE(batch > 0 && batch <= 65535 && w >= 2 && h >= 2 && w_out > 0 && h_out > 0, "resize_normalize: bad size");
+    if (c != 1 && c != 3) return set_error(VACV_ERR_UNSUPPORTED, "resize_normalize: c must be 1 or 3 (got %d)", c);
+    if (w_out == w && h_out == h)
+        return set_error(VACV_ERR_UNSUPPORTED, "resize_normalize: same-size resize (use vacv_cuda_normalize)");
+    const int rows_per_cta = max(1, min(h_out, (8192 + w_out - 1) / w_out));
+    dim3 grid(ceil_div(h_out, rows_per_cta), batch);
+    cudaStream_t s = as_stream(stream);
+    if (c == 3) resize_normalize_kernel<3><<<grid, 256, 0, s>>>(src, dst, w, h, w_out, h_out, rows_per_cta, mean, stddev, out_layout);
+    else resize_normalize_kernel<1><<<grid, 256, 0, s>>>(src, dst, w, h, w_out, h_out, rows_per_cta, mean, stddev, out_layout);
+    return check_launch("resize_normalize");
+}

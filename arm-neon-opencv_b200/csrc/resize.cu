@@ -1,0 +1,276 @@
+// a5-a9: resize INTER_LINEAR / INTER_CUBIC (reference: src/cv/resize.cpp:42-100, src/cv/resize_naive.cpp,
+// src/cv/resize_neon.cpp; u8 cubic = OpenCV 2.4.13 cv::resize, the reference's only path for it).
+//
+// Coefficients are rebuilt on the device with the reference's exact expression order (fp32 / fp64 mix,
+// --fmad=false), so the entry points are stateless like the reference's.  A CTA owns a 32x8 tile of output
+// pixels of one image; x-coefficients are computed once per column and y-coefficients once per row of the tile
+// into shared memory, then each thread gathers its taps through the read-only path.
+#include "vacv_common.cuh"
+
+namespace vacv {
+
+constexpr int kTileX = 32, kTileY = 8;
+
+struct ResizeGeom {
+    int w, h, c, wo, ho;
+    size_t src_image, dst_image;   // elements between consecutive images (frames for HWC, planes for CHW)
+};
+
+// ----------------------------------------------------------------------------------------------------
+// a5 bilinear u8, naive rule (resize_naive.cpp:10-68) / a7 NEON rule (resize_neon.cpp:12-347)
+template <bool kSigned, bool kNeonRule>
+__global__ void __launch_bounds__(kTileX * kTileY) resize_linear_u8_kernel(const uint8_t* __restrict__ src,
+                                                                            uint8_t* __restrict__ dst, ResizeGeom g) {
+    __shared__ int s_sx[kTileX], s_cx[kTileX], s_sy[kTileY], s_cy[kTileY];   // c = c0 | c1 << 16
+    const int dx0 = blockIdx.x * kTileX, dy0 = blockIdx.y * kTileY;
+    const int t = threadIdx.y * kTileX + threadIdx.x;
+    if (t < kTileX + kTileY) {
+        const bool isx = t < kTileX;
+        const int d = isx ? dx0 + t : dy0 + (t - kTileX);
+        const int n_in = isx ? g.w : g.h, n_out = isx ? g.wo : g.ho;
+        // naive: fp32 scale (resize_naive.cpp:17-18); NEON: fp64 scale (resize_neon.cpp:17-18)
+        const double scale = kNeonRule ? (double)n_in / (double)n_out : (double)((float)n_in / (float)n_out);
+        int s; float f;
+        linear_coord(min(d, n_out - 1), scale, n_in, s, f);
+        const int c0 = sat_short((1.f - f) * 2048.f), c1 = sat_short(f * 2048.f);
+        if (isx) { s_sx[t] = s; s_cx[t] = (c0 & 0xffff) | (c1 << 16); }
+        else { s_sy[t - kTileX] = s; s_cy[t - kTileX] = (c0 & 0xffff) | (c1 << 16); }
+    }
+    __syncthreads();
+    const int dx = dx0 + threadIdx.x, dy = dy0 + threadIdx.y;
+    if (dx >= g.wo || dy >= g.ho) return;
+    const int sx = s_sx[threadIdx.x], sy = s_sy[threadIdx.y];
+    const int cx0 = (short)(s_cx[threadIdx.x] & 0xffff), cx1 = s_cx[threadIdx.x] >> 16;
+    const int cy0 = (short)(s_cy[threadIdx.y] & 0xffff), cy1 = s_cy[threadIdx.y] >> 16;
+    const uint8_t* img = src + blockIdx.z * g.src_image;
+    const uint8_t* lt = img + ((size_t)sy * g.w + sx) * g.c;
+    const uint8_t* lb = lt + (size_t)g.w * g.c;
+    uint8_t* o = dst + blockIdx.z * g.dst_image + ((size_t)dy * g.wo + dx) * g.c;
+    for (int k = 0; k < g.c; ++k) {
+        const int p00 = pix<kSigned>(__ldg(lt + k)), p01 = pix<kSigned>(__ldg(lt + g.c + k));
+        const int p10 = pix<kSigned>(__ldg(lb + k)), p11 = pix<kSigned>(__ldg(lb + g.c + k));
+        int v;
+        if (kNeonRule) {
+            const int r0 = (short)((p00 * cx0 + p01 * cx1) >> 4), r1 = (short)((p10 * cx0 + p11 * cx1) >> 4);
+            v = clamp255(((short)((cy0 * r0) >> 16) + (short)((cy1 * r1) >> 16) + 2) >> 2);
+        } else {
+            v = (p00 * cx0 * cy0 + p10 * cx0 * cy1 + p01 * cx1 * cy0 + p11 * cx1 * cy1) >> 22;   // :60-65
+        }
+        o[k] = (uint8_t)v;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// a6 bilinear fp32 (resize_naive.cpp:70-128)
+__global__ void __launch_bounds__(kTileX * kTileY) resize_linear_f32_kernel(const float* __restrict__ src,
+                                                                             float* __restrict__ dst, ResizeGeom g) {
+    __shared__ int s_sx[kTileX], s_sy[kTileY];
+    __shared__ float s_fx[kTileX], s_fy[kTileY];
+    const int dx0 = blockIdx.x * kTileX, dy0 = blockIdx.y * kTileY;
+    const int t = threadIdx.y * kTileX + threadIdx.x;
+    if (t < kTileX + kTileY) {
+        const bool isx = t < kTileX;
+        const int d = isx ? dx0 + t : dy0 + (t - kTileX);
+        const int n_in = isx ? g.w : g.h, n_out = isx ? g.wo : g.ho;
+        int s; float f;
+        linear_coord(min(d, n_out - 1), (double)((float)n_in / (float)n_out), n_in, s, f);
+        if (isx) { s_sx[t] = s; s_fx[t] = f; } else { s_sy[t - kTileX] = s; s_fy[t - kTileX] = f; }
+    }
+    __syncthreads();
+    const int dx = dx0 + threadIdx.x, dy = dy0 + threadIdx.y;
+    if (dx >= g.wo || dy >= g.ho) return;
+    const int sx = s_sx[threadIdx.x], sy = s_sy[threadIdx.y];
+    const float fx = s_fx[threadIdx.x], fy = s_fy[threadIdx.y];
+    const float cx0 = 1.f - fx, cx1 = fx, cy0 = 1.f - fy, cy1 = fy;
+    const float* img = src + blockIdx.z * g.src_image;
+    const float* lt = img + ((size_t)sy * g.w + sx) * g.c;
+    const float* lb = lt + (size_t)g.w * g.c;
+    float* o = dst + blockIdx.z * g.dst_image + ((size_t)dy * g.wo + dx) * g.c;
+    for (int k = 0; k < g.c; ++k)   // :121-124 evaluation order
+        o[k] = __ldg(lt + k) * cx0 * cy0 + __ldg(lb + k) * cx0 * cy1 + __ldg(lt + g.c + k) * cx1 * cy0 +
+               __ldg(lb + g.c + k) * cx1 * cy1;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// a8 bicubic fp32 (resize_naive.cpp:130-185 coefficients with border folding; :230,:345 accumulation order)
+__device__ __forceinline__ void cubic_naive(int d, int n_in, int n_out, int& ofs, float (&a)[4]) {
+    const double scale = (double)n_in / (double)n_out;
+    float fx = (float)(((double)d + 0.5) * scale - 0.5);
+    int sx = (int)floorf(fx);
+    fx -= (float)sx;
+    const float A = -0.75f;
+    const float fx0 = fx + 1, fx1 = fx, fx2 = 1 - fx;
+    a[0] = A * fx0 * fx0 * fx0 - 5 * A * fx0 * fx0 + 8 * A * fx0 - 4 * A;
+    a[1] = (A + 2) * fx1 * fx1 * fx1 - (A + 3) * fx1 * fx1 + 1;
+    a[2] = (A + 2) * fx2 * fx2 * fx2 - (A + 3) * fx2 * fx2 + 1;
+    a[3] = 1.f - a[0] - a[1] - a[2];
+    if (sx <= -1) { sx = 1; a[0] = 1.f - a[3]; a[1] = a[3]; a[2] = 0.f; a[3] = 0.f; }
+    if (sx == 0) { sx = 1; a[0] = a[0] + a[1]; a[1] = a[2]; a[2] = a[3]; a[3] = 0.f; }
+    if (sx == n_in - 2) { sx = n_in - 3; a[3] = a[2] + a[3]; a[2] = a[1]; a[1] = a[0]; a[0] = 0.f; }
+    if (sx >= n_in - 1) { sx = n_in - 3; a[3] = 1.f - a[0]; a[2] = a[0]; a[1] = 0.f; a[0] = 0.f; }
+    ofs = sx;
+}
+
+__global__ void __launch_bounds__(kTileX * kTileY) resize_cubic_f32_kernel(const float* __restrict__ src,
+                                                                            float* __restrict__ dst, ResizeGeom g) {
+    __shared__ int s_sx[kTileX], s_sy[kTileY];
+    __shared__ float s_a[kTileX][4], s_b[kTileY][4];
+    const int dx0 = blockIdx.x * kTileX, dy0 = blockIdx.y * kTileY;
+    const int t = threadIdx.y * kTileX + threadIdx.x;
+    if (t < kTileX + kTileY) {
+        const bool isx = t < kTileX;
+        const int d = isx ? dx0 + t : dy0 + (t - kTileX);
+        int ofs; float a[4];
+        cubic_naive(min(d, (isx ? g.wo : g.ho) - 1), isx ? g.w : g.h, isx ? g.wo : g.ho, ofs, a);
+        if (isx) { s_sx[t] = ofs; for (int j = 0; j < 4; ++j) s_a[t][j] = a[j]; }
+        else { s_sy[t - kTileX] = ofs; for (int j = 0; j < 4; ++j) s_b[t - kTileX][j] = a[j]; }
+    }
+    __syncthreads();
+    const int dx = dx0 + threadIdx.x, dy = dy0 + threadIdx.y;
+    if (dx >= g.wo || dy >= g.ho) return;
+    const int sx = s_sx[threadIdx.x], sy = s_sy[threadIdx.y];
+    const float a0 = s_a[threadIdx.x][0], a1 = s_a[threadIdx.x][1], a2 = s_a[threadIdx.x][2], a3 = s_a[threadIdx.x][3];
+    const float b0 = s_b[threadIdx.y][0], b1 = s_b[threadIdx.y][1], b2 = s_b[threadIdx.y][2], b3 = s_b[threadIdx.y][3];
+    const float* img = src + blockIdx.z * g.src_image;
+    float* o = dst + blockIdx.z * g.dst_image + ((size_t)dy * g.wo + dx) * g.c;
+    const int c = g.c;
+    for (int k = 0; k < c; ++k) {
+        float r[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float* S = img + ((size_t)(sy - 1 + j) * g.w + sx) * c + k;
+            r[j] = __ldg(S - c) * a0 + __ldg(S) * a1 + __ldg(S + c) * a2 + __ldg(S + 2 * c) * a3;
+        }
+        o[k] = r[0] * b0 + r[1] * b1 + r[2] * b2 + r[3] * b3;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// a9 bicubic u8 = OpenCV 2.4.13 cv::resize(CV_8UCn, INTER_CUBIC): int32 horizontal pass with
+// 11-bit coefficients (round-half-even), fp32 vertical pass with round-half-even for the first (W*cn & ~7)
+// elements of a row (the SSE2 body) and an integer (+2^21)>>22 vertical pass for the <=7 tail elements.
+__device__ __forceinline__ void cubic_cv(float x, float (&k)[4]) {
+    const float A = -0.75f;
+    k[0] = ((A * (x + 1) - 5 * A) * (x + 1) + 8 * A) * (x + 1) - 4 * A;
+    k[1] = ((A + 2) * x - (A + 3)) * x * x + 1;
+    k[2] = ((A + 2) * (1 - x) - (A + 3)) * (1 - x) * (1 - x) + 1;
+    k[3] = 1.f - k[0] - k[1] - k[2];
+}
+__device__ __forceinline__ int sat_short_rhe(float v) { return max(min(__float2int_rn(v), 32767), -32768); }
+
+__global__ void __launch_bounds__(kTileX * kTileY) resize_cubic_u8_cv24_kernel(const uint8_t* __restrict__ src,
+                                                                                uint8_t* __restrict__ dst, ResizeGeom g) {
+    __shared__ int s_sx[kTileX], s_sy[kTileY];
+    __shared__ short s_a[kTileX][4], s_b[kTileY][4];
+    const int dx0 = blockIdx.x * kTileX, dy0 = blockIdx.y * kTileY;
+    const int t = threadIdx.y * kTileX + threadIdx.x;
+    if (t < kTileX + kTileY) {
+        const bool isx = t < kTileX;
+        const int n_in = isx ? g.w : g.h, n_out = isx ? g.wo : g.ho;
+        const int d = min(isx ? dx0 + t : dy0 + (t - kTileX), n_out - 1);
+        const double scale = 1. / ((double)n_out / (double)n_in);
+        float f = (float)(((double)d + 0.5) * scale - 0.5);
+        int s = (int)floorf(f);
+        f -= (float)s;
+        if (isx) {   // 2.4: the clamp is applied along x only
+            if (s < 0) { f = 0.f; s = 0; }
+            if (s >= n_in - 1) { f = 0.f; s = n_in - 1; }
+        }
+        float k[4];
+        cubic_cv(f, k);
+        for (int j = 0; j < 4; ++j) {
+            const short q = (short)sat_short_rhe(k[j] * 2048.f);
+            if (isx) s_a[t][j] = q; else s_b[t - kTileX][j] = q;
+        }
+        if (isx) s_sx[t] = s; else s_sy[t - kTileX] = s;
+    }
+    __syncthreads();
+    const int dx = dx0 + threadIdx.x, dy = dy0 + threadIdx.y;
+    if (dx >= g.wo || dy >= g.ho) return;
+    const int sx = s_sx[threadIdx.x], sy = s_sy[threadIdx.y];
+    int xi[4], a[4], b[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        xi[j] = min(max(sx - 1 + j, 0), g.w - 1) * g.c;
+        a[j] = s_a[threadIdx.x][j];
+        b[j] = s_b[threadIdx.y][j];
+    }
+    const uint8_t* img = src + blockIdx.z * g.src_image;
+    const uint8_t* rows[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) rows[j] = img + (size_t)min(max(sy - 1 + j, 0), g.h - 1) * g.w * g.c;
+    uint8_t* o = dst + blockIdx.z * g.dst_image + ((size_t)dy * g.wo + dx) * g.c;
+    const int vec_end = (g.wo * g.c) & ~7;
+    const float sc = 1.f / (2048 * 2048);
+    const float fb0 = (float)b[0] * sc, fb1 = (float)b[1] * sc, fb2 = (float)b[2] * sc, fb3 = (float)b[3] * sc;
+    for (int k = 0; k < g.c; ++k) {
+        int H[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            H[j] = __ldg(rows[j] + xi[0] + k) * a[0] + __ldg(rows[j] + xi[1] + k) * a[1] +
+                   __ldg(rows[j] + xi[2] + k) * a[2] + __ldg(rows[j] + xi[3] + k) * a[3];
+        int v;
+        if (dx * g.c + k < vec_end) {
+            float f = (float)H[0] * fb0;
+            f = f + (float)H[1] * fb1;
+            f = f + (float)H[2] * fb2;
+            f = f + (float)H[3] * fb3;
+            v = max(min(__float2int_rn(f), 32767), -32768);
+        } else {
+            v = (H[0] * b[0] + H[1] * b[1] + H[2] * b[2] + H[3] * b[3] + (1 << 21)) >> 22;
+        }
+        o[k] = (uint8_t)clamp255(v);
+    }
+}
+
+}  // namespace vacv
+
+using namespace vacv;
+
+extern "C" int vacv_cuda_resize(const void* src, void* dst, int batch, int w, int h, int c, int dtype, int layout,
+                                int w_out, int h_out, int interpolation, int flags, void* stream) {
+    VACV_REQUIRE(src && dst, "resize: null pointer");
+    VACV_REQUIRE(batch > 0 && w > 0 && h > 0 && c > 0 && w_out > 0 && h_out > 0, "resize: non-positive size");
+    if (interpolation != VACV_INTER_LINEAR && interpolation != VACV_INTER_CUBIC)
+        return set_error(VACV_ERR_UNSUPPORTED, "resize: interpolation %d (reference native paths: LINEAR, CUBIC)", interpolation);
+    if (dtype != VACV_INT8 && dtype != VACV_FP32) return set_error(VACV_ERR_UNSUPPORTED, "resize: dtype %d", dtype);
+    cudaStream_t s = as_stream(stream);
+    const size_t es = elem_size(dtype);
+    if (w_out == w && h_out == h) {   // resize.cpp:58-61 (intended: the whole buffer, App. C-7)
+        cudaError_t e = cudaMemcpyAsync(dst, src, (size_t)batch * w * h * c * es, cudaMemcpyDeviceToDevice, s);
+        if (e != cudaSuccess) return set_error(VACV_ERR_CUDA, "resize: %s", cudaGetErrorString(e));
+        return VACV_OK;
+    }
+    const bool cubic = interpolation == VACV_INTER_CUBIC;
+    if (cubic) VACV_REQUIRE(dtype == VACV_INT8 || (w >= 4 && h >= 4), "resize: fp32 cubic needs w,h >= 4");
+    else VACV_REQUIRE(w >= 2 && h >= 2, "resize: bilinear needs w,h >= 2");
+    if (cubic && dtype == VACV_INT8 && layout != VACV_NHWC && c != 1)
+        return set_error(VACV_ERR_UNSUPPORTED, "resize: u8 INTER_CUBIC is HWC only (cv::resize on a cv::Mat)");
+    ResizeGeom g;
+    g.w = w; g.h = h; g.wo = w_out; g.ho = h_out;
+    int images;
+    if (layout == VACV_NHWC) { g.c = c; images = batch; }
+    else { g.c = 1; images = batch * c; }   // resize.cpp:73-87: per-plane calls with c = 1
+    g.src_image = (size_t)w * h * g.c;
+    g.dst_image = (size_t)w_out * h_out * g.c;
+    dim3 block(kTileX, kTileY);
+    for (int i0 = 0; i0 < images; i0 += 65535) {
+        const int ni = min(images - i0, 65535);
+        dim3 grid(ceil_div(w_out, kTileX), ceil_div(h_out, kTileY), ni);
+        const uint8_t* sp = (const uint8_t*)src + (size_t)i0 * g.src_image * es;
+        uint8_t* dp = (uint8_t*)dst + (size_t)i0 * g.dst_image * es;
+        if (!cubic && dtype == VACV_INT8) {
+            const bool sc = flags & VACV_FLAG_SIGNED_CHAR;
+            if (flags & VACV_FLAG_NEON_RULE) resize_linear_u8_kernel<false, true><<<grid, block, 0, s>>>(sp, dp, g);
+            else if (sc) resize_linear_u8_kernel<true, false><<<grid, block, 0, s>>>(sp, dp, g);
+            else resize_linear_u8_kernel<false, false><<<grid, block, 0, s>>>(sp, dp, g);
+        } else if (!cubic) {
+            resize_linear_f32_kernel<<<grid, block, 0, s>>>((const float*)sp, (float*)dp, g);
+        } else if (dtype == VACV_FP32) {
+            resize_cubic_f32_kernel<<<grid, block, 0, s>>>((const float*)sp, (float*)dp, g);
+        } else {
+            resize_cubic_u8_cv24_kernel<<<grid, block, 0, s>>>(sp, dp, g);
+        }
+    }
+    return check_launch("resize");
+}

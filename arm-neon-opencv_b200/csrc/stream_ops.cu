@@ -1,0 +1,333 @@
+// a2 crop, a3 layout_change, a4 dtype_change, a12 normalize -- the pure streaming operators.
+// All are HBM-bound byte movers: the design rule is "every global access a warp issues is lane-contiguous and
+// as wide as the alignment allows (128-bit in the common shapes)".
+#include "vacv_common.cuh"
+
+namespace vacv {
+
+// =====================================================================================================
+// a2 crop (src/cv/crop.cpp:44-142).  Both layouts reduce to "copy R byte-rows of RB bytes": HWC rows are
+// cw*c*elem bytes, CHW rows are cw*elem bytes for each of c planes.  One warp per destination row.  The
+// destination is written in 16-byte aligned chunks; the (generally misaligned) source bytes for a chunk come
+// from five aligned 32-bit words merged with funnel shifts (L1 serves the overlap between neighbouring lanes).
+struct CropGeom {
+    int rows_per_frame;   // ch (HWC) or c*ch (CHW)
+    int ch;               // rows per plane
+    int RB;               // destination row bytes
+    size_t src_frame, src_plane, src_pitch, src_ofs;   // bytes
+};
+
+__global__ void __launch_bounds__(256) crop_rows_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+                                                         CropGeom g, size_t total_rows) {
+    const size_t row = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= total_rows) return;
+    const int lane = threadIdx.x & 31;
+    const size_t frame = row / g.rows_per_frame;
+    const int rr = (int)(row % g.rows_per_frame);
+    const int plane = rr / g.ch, y = rr % g.ch;
+    const uint8_t* s = src + frame * g.src_frame + plane * g.src_plane + (size_t)y * g.src_pitch + g.src_ofs;
+    uint8_t* d = dst + row * (size_t)g.RB;
+
+    const int head = min((int)((16 - ((uintptr_t)d & 15)) & 15), g.RB);
+    if (lane < head) d[lane] = __ldg(s + lane);
+    const int nchunks = (g.RB - head) >> 4;
+    const uint8_t* sb = s + head;
+    uint8_t* db = d + head;
+    const int m = (int)((uintptr_t)sb & 3);           // same for every chunk of this row
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(sb - m);
+    const int sh = 8 * m;
+    for (int q = lane; q < nchunks; q += 32) {
+        const uint32_t* p = sw + 4 * q;
+        uint4 o;
+        if (m == 0) {
+            o = make_uint4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
+        } else {
+            uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2), w3 = __ldg(p + 3), w4 = __ldg(p + 4);
+            o = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
+                           __funnelshift_r(w3, w4, sh));
+        }
+        st_stream16(db + 16 * q, o);
+    }
+    const int done = head + 16 * nchunks;
+    if (lane < g.RB - done) d[done + lane] = __ldg(s + done + lane);
+}
+
+// =====================================================================================================
+// a3 layout_change (src/common/tensor.cpp:160-182): chw[k*wh + j] = hwc[j*c + k].
+// c == 3 fast path: a thread moves V = 16/sizeof(T) pixels: 48 contiguous bytes on the interleaved side
+// (three 128-bit accesses; neighbouring lanes complete each other's sectors) and one 128-bit access per plane.
+template <typename T>
+__device__ __forceinline__ void deinterleave3(const uint4 (&in)[3], uint4 (&out)[3]) {
+    constexpr int V = 16 / sizeof(T);
+    const T* a = reinterpret_cast<const T*>(in);
+    T* o = reinterpret_cast<T*>(out);
+#pragma unroll
+    for (int i = 0; i < V; ++i)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) o[k * V + i] = a[3 * i + k];
+}
+template <typename T>
+__device__ __forceinline__ void interleave3(const uint4 (&in)[3], uint4 (&out)[3]) {
+    constexpr int V = 16 / sizeof(T);
+    const T* a = reinterpret_cast<const T*>(in);
+    T* o = reinterpret_cast<T*>(out);
+#pragma unroll
+    for (int i = 0; i < V; ++i)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) o[3 * i + k] = a[k * V + i];
+}
+
+// groups = batch * wh / V ; wh % V == 0
+template <typename T, bool kToCHW>
+__global__ void __launch_bounds__(256) layout_c3_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst,
+                                                         size_t groups, size_t groups_per_frame) {
+    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= groups) return;
+    const size_t frame = g / groups_per_frame, j = g % groups_per_frame;
+    const size_t inter = frame * groups_per_frame * 3 + j * 3;      // uint4 index on the HWC side
+    const size_t planar = frame * groups_per_frame * 3 + j;         // uint4 index of plane 0 on the CHW side
+    uint4 a[3], b[3];
+    if (kToCHW) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) a[k] = __ldg(src + inter + k);
+        deinterleave3<T>(a, b);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) st_stream16(dst + planar + k * groups_per_frame, b[k]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) a[k] = ld_stream16(src + planar + k * groups_per_frame);
+        interleave3<T>(a, b);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) st_stream16(dst + inter + k, b[k]);
+    }
+}
+
+template <typename T, bool kToCHW>
+__global__ void layout_generic_kernel(const T* __restrict__ src, T* __restrict__ dst, int wh, int c, size_t total) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // index on the destination side
+    if (i >= total) return;
+    const size_t per = (size_t)wh * c;
+    const size_t frame = i / per, r = i % per;
+    size_t s;
+    if (kToCHW) { size_t k = r / wh, j = r % wh; s = j * c + k; }
+    else        { size_t j = r / c, k = r % c;   s = k * wh + j; }
+    dst[i] = src[frame * per + s];
+}
+
+// =====================================================================================================
+// a4 dtype_change (src/common/tensor.cpp:459-502)
+__global__ void __launch_bounds__(256) u8_to_f32_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, size_t n4) {
+    // 4 elements per thread: 32-bit load (128 B / warp), 128-bit store (512 B / warp)
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n4; i += stride) {
+        uint32_t v = ld_stream4(src + 4 * i);
+        st_stream16f(dst + 4 * i, make_float4((float)(v & 0xff), (float)((v >> 8) & 0xff), (float)((v >> 16) & 0xff),
+                                              (float)(v >> 24)));
+    }
+}
+__global__ void __launch_bounds__(256) f32_to_u8_kernel(const float* __restrict__ src, uint8_t* __restrict__ dst, size_t n4) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n4; i += stride) {
+        uint4 r = ld_stream16(src + 4 * i);
+        // static_cast<char>(float) on x86 = cvttss2si then low byte (tensor.cpp:488-492)
+        uint32_t b0 = (uint32_t)(int)__uint_as_float(r.x) & 0xff, b1 = (uint32_t)(int)__uint_as_float(r.y) & 0xff;
+        uint32_t b2 = (uint32_t)(int)__uint_as_float(r.z) & 0xff, b3 = (uint32_t)(int)__uint_as_float(r.w) & 0xff;
+        st_stream4(dst + 4 * i, b0 | (b1 << 8) | (b2 << 16) | (b3 << 24));
+    }
+}
+__global__ void dtype_tail_kernel(const void* src, void* dst, size_t begin, size_t n, int to_f32) {
+    size_t i = begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (to_f32) ((float*)dst)[i] = (float)((const uint8_t*)src)[i];
+    else ((uint8_t*)dst)[i] = (uint8_t)(int)((const float*)src)[i];
+}
+
+// =====================================================================================================
+// a12 normalize (src/cv/normalize_naive.cpp:74-90): (float)((double)(x - mean) / ((double)std + 1e-6)).
+// fp32 input: exact double division per element.  u8 input: there are only 256 possible inputs per channel,
+// so each CTA builds the 256 x c table once with that exact expression and the stream becomes
+// 4-byte load -> 4 shared-memory lookups -> 16-byte store.
+constexpr int kNormMaxC = 4;
+
+struct NormGeom {
+    int c, layout;
+    unsigned wh;           // pixels per plane
+    size_t per_frame;      // wh * c
+    int stats_per_frame;
+};
+
+__device__ __forceinline__ int channel_of(const NormGeom& g, size_t r /* index within the frame */) {
+    return g.layout == VACV_NHWC ? (int)(r % g.c) : (int)(r / g.wh);
+}
+
+__global__ void __launch_bounds__(256) normalize_f32_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                             const float* __restrict__ mean, const float* __restrict__ stddev,
+                                                             NormGeom g, size_t n4, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n4; i += stride) {
+        const size_t e = 4 * i;
+        uint4 r = ld_stream16(src + e);
+        const float x[4] = {__uint_as_float(r.x), __uint_as_float(r.y), __uint_as_float(r.z), __uint_as_float(r.w)};
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const size_t frame = (e + j) / g.per_frame, rr = (e + j) % g.per_frame;
+            const int k = channel_of(g, rr) + (g.stats_per_frame ? (int)frame * g.c : 0);
+            o[j] = normalize_one(x[j], __ldg(mean + k), (double)__ldg(stddev + k) + 1e-6);
+        }
+        st_stream16f(dst + e, make_float4(o[0], o[1], o[2], o[3]));
+    }
+    // tail (< 4 elements)
+    if (blockIdx.x == 0 && threadIdx.x < n - 4 * n4) {
+        const size_t e = 4 * n4 + threadIdx.x;
+        const size_t frame = e / g.per_frame, rr = e % g.per_frame;
+        const int k = channel_of(g, rr) + (g.stats_per_frame ? (int)frame * g.c : 0);
+        dst[e] = normalize_one(src[e], mean[k], (double)stddev[k] + 1e-6);
+    }
+}
+
+// grid = (ctas_per_frame, frames_in_launch) so that a CTA's table belongs to one frame's statistics.
+__global__ void __launch_bounds__(256) normalize_u8_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst,
+                                                            const float* __restrict__ mean, const float* __restrict__ stddev,
+                                                            NormGeom g) {
+    __shared__ float lut[kNormMaxC][256];
+    const size_t frame = blockIdx.y;
+    const float* mu = mean + (g.stats_per_frame ? frame * g.c : 0);
+    const float* sd = stddev + (g.stats_per_frame ? frame * g.c : 0);
+    for (int t = threadIdx.x; t < 256 * g.c; t += blockDim.x) {
+        const int k = t >> 8, v = t & 255;
+        lut[k][v] = normalize_one((float)v, mu[k], (double)sd[k] + 1e-6);
+    }
+    __syncthreads();
+    const uint8_t* s = src + frame * g.per_frame;
+    float* d = dst + frame * g.per_frame;
+    const size_t n4 = g.per_frame >> 2;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t e = 4 * i;
+        const uint32_t v = ld_stream4(s + e);
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = lut[channel_of(g, e + j)][(v >> (8 * j)) & 0xff];
+        st_stream16f(d + e, make_float4(o[0], o[1], o[2], o[3]));
+    }
+    if (blockIdx.x == 0 && threadIdx.x < g.per_frame - 4 * n4) {
+        const size_t e = 4 * n4 + threadIdx.x;
+        d[e] = lut[channel_of(g, e)][s[e]];
+    }
+}
+
+}  // namespace vacv
+
+using namespace vacv;
+
+extern "C" int vacv_cuda_crop(const void* src, void* dst, int batch, int w, int h, int c, int dtype, int layout,
+                              int left, int top, int cw, int ch, void* stream) {
+    VACV_REQUIRE(src && dst, "crop: null pointer");
+    VACV_REQUIRE(batch > 0 && w > 0 && h > 0 && c > 0 && cw > 0 && ch > 0, "crop: non-positive size");
+    if (dtype != VACV_INT8 && dtype != VACV_FP32) return set_error(VACV_ERR_UNSUPPORTED, "crop: dtype %d (reference: INT8/FP32 only, crop.cpp:133)", dtype);
+    VACV_REQUIRE(left >= 0 && top >= 0 && left + cw <= w && top + ch <= h,
+                 "crop: rect (%d,%d %dx%d) outside %dx%d frame", left, top, cw, ch, w, h);
+    const size_t es = elem_size(dtype);
+    CropGeom g;
+    if (layout == VACV_NHWC) {
+        g.rows_per_frame = ch; g.ch = ch; g.RB = (int)(cw * c * es);
+        g.src_plane = 0; g.src_pitch = (size_t)w * c * es; g.src_ofs = ((size_t)top * w + left) * c * es;
+    } else {
+        g.rows_per_frame = c * ch; g.ch = ch; g.RB = (int)(cw * es);
+        g.src_plane = (size_t)w * h * es; g.src_pitch = (size_t)w * es; g.src_ofs = ((size_t)top * w + left) * es;
+    }
+    g.src_frame = (size_t)w * h * c * es;
+    const size_t rows = (size_t)batch * g.rows_per_frame;
+    crop_rows_kernel<<<ceil_div(rows * 32, 256), 256, 0, as_stream(stream)>>>((const uint8_t*)src, (uint8_t*)dst, g, rows);
+    return check_launch("crop");
+}
+
+template <typename T>
+static void launch_layout(const void* src, void* dst, int batch, int wh, int c, bool to_chw, cudaStream_t s) {
+    constexpr int V = 16 / sizeof(T);
+    const bool vec = c == 3 && (wh % V) == 0 && (((uintptr_t)src | (uintptr_t)dst) & 15) == 0;
+    if (vec) {
+        const size_t gpf = wh / V, groups = gpf * batch;
+        if (to_chw) layout_c3_kernel<T, true><<<ceil_div(groups, 256), 256, 0, s>>>((const uint4*)src, (uint4*)dst, groups, gpf);
+        else layout_c3_kernel<T, false><<<ceil_div(groups, 256), 256, 0, s>>>((const uint4*)src, (uint4*)dst, groups, gpf);
+    } else {
+        const size_t total = (size_t)batch * wh * c;
+        if (to_chw) layout_generic_kernel<T, true><<<ceil_div(total, 256), 256, 0, s>>>((const T*)src, (T*)dst, wh, c, total);
+        else layout_generic_kernel<T, false><<<ceil_div(total, 256), 256, 0, s>>>((const T*)src, (T*)dst, wh, c, total);
+    }
+}
+
+extern "C" int vacv_cuda_layout_change(const void* src, void* dst, int batch, int w, int h, int c, int dtype,
+                                       int from_layout, int to_layout, void* stream) {
+    VACV_REQUIRE(src && dst, "layout_change: null pointer");
+    VACV_REQUIRE(batch > 0 && w > 0 && h > 0 && c > 0, "layout_change: non-positive size");
+    const size_t es = elem_size(dtype);
+    if (es != 1 && es != 2 && es != 4) return set_error(VACV_ERR_UNSUPPORTED, "layout_change: dtype %d", dtype);
+    cudaStream_t s = as_stream(stream);
+    if (c == 1 || from_layout == to_layout) {   // tensor.cpp:398-400: clone
+        cudaError_t e = cudaMemcpyAsync(dst, src, (size_t)batch * w * h * c * es, cudaMemcpyDeviceToDevice, s);
+        if (e != cudaSuccess) return set_error(VACV_ERR_CUDA, "layout_change: %s", cudaGetErrorString(e));
+        return VACV_OK;
+    }
+    const bool to_chw = to_layout == VACV_NCHW;
+    if (es == 1) launch_layout<uint8_t>(src, dst, batch, w * h, c, to_chw, s);
+    else if (es == 2) launch_layout<uint16_t>(src, dst, batch, w * h, c, to_chw, s);
+    else launch_layout<uint32_t>(src, dst, batch, w * h, c, to_chw, s);
+    return check_launch("layout_change");
+}
+
+extern "C" int vacv_cuda_dtype_change(const void* src, void* dst, size_t n, int from_dtype, int to_dtype, void* stream) {
+    VACV_REQUIRE(src && dst, "dtype_change: null pointer");
+    VACV_REQUIRE(n > 0, "dtype_change: empty");
+    cudaStream_t s = as_stream(stream);
+    if (from_dtype == to_dtype) {   // tensor.cpp:464-466: clone
+        cudaError_t e = cudaMemcpyAsync(dst, src, n * elem_size(from_dtype), cudaMemcpyDeviceToDevice, s);
+        if (e != cudaSuccess) return set_error(VACV_ERR_CUDA, "dtype_change: %s", cudaGetErrorString(e));
+        return VACV_OK;
+    }
+    const bool to_f32 = from_dtype == VACV_INT8 && to_dtype == VACV_FP32;
+    const bool to_u8 = from_dtype == VACV_FP32 && to_dtype == VACV_INT8;
+    if (!to_f32 && !to_u8)   // the reference silently returns an uninitialised tensor here (tensor.cpp:494-499)
+        return set_error(VACV_ERR_UNSUPPORTED, "dtype_change: %d -> %d (reference: INT8<->FP32 only)", from_dtype, to_dtype);
+    const bool aligned = (((uintptr_t)src | (uintptr_t)dst) & 15) == 0;
+    const size_t n4 = aligned ? n / 4 : 0;
+    if (n4) {
+        const unsigned blocks = (unsigned)min((size_t)kNumSMs * 16, (size_t)ceil_div(n4, 256));
+        if (to_f32) u8_to_f32_kernel<<<blocks, 256, 0, s>>>((const uint8_t*)src, (float*)dst, n4);
+        else f32_to_u8_kernel<<<blocks, 256, 0, s>>>((const float*)src, (uint8_t*)dst, n4);
+    }
+    if (4 * n4 < n) dtype_tail_kernel<<<ceil_div(n - 4 * n4, 256), 256, 0, s>>>(src, dst, 4 * n4, n, to_f32 ? 1 : 0);
+    return check_launch("dtype_change");
+}
+
+extern "C" int vacv_cuda_normalize(const void* src, float* dst, int batch, int w, int h, int c, int src_dtype, int layout,
+                                   const float* mean, const float* stddev, int stats_per_frame, void* stream) {
+    VACV_REQUIRE(src && dst && mean && stddev, "normalize: null pointer");
+    VACV_REQUIRE(batch > 0 && w > 0 && h > 0 && c > 0, "normalize: non-positive size");
+    if (src_dtype != VACV_INT8 && src_dtype != VACV_FP32) return set_error(VACV_ERR_UNSUPPORTED, "normalize: src dtype %d", src_dtype);
+    VACV_REQUIRE((((uintptr_t)src | (uintptr_t)dst) & 15) == 0, "normalize: buffers must be 16-byte aligned");
+    cudaStream_t s = as_stream(stream);
+    NormGeom g;
+    g.c = c; g.layout = layout; g.wh = (unsigned)w * h; g.per_frame = (size_t)w * h * c; g.stats_per_frame = stats_per_frame;
+    const size_t n = g.per_frame * batch;
+    if (src_dtype == VACV_FP32) {
+        const size_t n4 = n / 4;
+        const unsigned blocks = (unsigned)max((size_t)1, min((size_t)kNumSMs * 16, (size_t)ceil_div(n4, 256)));
+        normalize_f32_kernel<<<blocks, 256, 0, s>>>((const float*)src, dst, mean, stddev, g, n4, n);
+    } else {
+        if (c > kNormMaxC) return set_error(VACV_ERR_UNSUPPORTED, "normalize: u8 input supports c <= %d", kNormMaxC);
+        VACV_REQUIRE((g.per_frame % 4) == 0 || batch == 1, "normalize: u8 batch needs w*h*c %% 4 == 0");
+        const unsigned per_frame_ctas = (unsigned)max((size_t)1, min((size_t)ceil_div(g.per_frame / 4, 256 * 8), (size_t)4096));
+        for (int f0 = 0; f0 < batch; f0 += 65535) {
+            const int nf = min(batch - f0, 65535);
+            dim3 grid(per_frame_ctas, nf);
+            normalize_u8_kernel<<<grid, 256, 0, s>>>((const uint8_t*)src + (size_t)f0 * g.per_frame, dst + (size_t)f0 * g.per_frame,
+                                                     mean + (stats_per_frame ? (size_t)f0 * c : 0),
+                                                     stddev + (stats_per_frame ? (size_t)f0 * c : 0), g);
+        }
+    }
+    return check_launch("normalize");
+}

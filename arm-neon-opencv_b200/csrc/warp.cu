@@ -1,0 +1,166 @@
+// a10: warp_affine (reference: src/cv/warp_affine.cpp:76-169, src/cv/warp_affine_naive.cpp:9-106) and the fused
+// warp_affine_normalize (API src/cv/warp_affine_normalize.cpp:13-45; semantics = composition).
+//
+// Matrix inversion / rotation-matrix construction stay on the host (vacv_host.cpp) with the reference's mixed
+// float/double arithmetic; the device evaluates fx = (m0*dx + m1*dy) + m2 in fp32 with no FMA contraction.
+// One launch covers a whole batch of crops; each crop reads its own frame of a device-resident frame pool.
+#include "vacv_common.cuh"
+
+namespace vacv {
+
+struct WarpGeom {
+    int w, h, c, wo, ho;
+    size_t frame_elems;   // w*h*c
+    int planar;           // 1: CHW (c planes, same geometry; warp_affine.cpp:152-168)
+};
+
+struct Taps { int ofs; int cx0, cx1, cy0, cy1; float fx, fy; bool in; };
+
+// warp_affine_naive.cpp:23-44
+__device__ __forceinline__ Taps warp_taps(const float* __restrict__ m, int dx, int dy, int w, int h) {
+    Taps t;
+    float fx = m[0] * (float)dx + m[1] * (float)dy + m[2];
+    float fy = m[3] * (float)dx + m[4] * (float)dy + m[5];
+    const int sy = (int)floorf(fy);
+    fy -= (float)sy;
+    const int sx = (int)floorf(fx);
+    fx -= (float)sx;
+    t.in = !(sy < 0 || sy >= h - 1 || sx < 0 || sx >= w - 1);
+    t.cy0 = sat_short((1.f - fy) * 2048.f);
+    t.cy1 = sat_short((float)(2048 - t.cy0));   // sums to exactly 2048 (:32)
+    t.cx0 = sat_short((1.f - fx) * 2048.f);
+    t.cx1 = sat_short((float)(2048 - t.cx0));
+    t.fx = fx; t.fy = fy;
+    t.ofs = sy * w + sx;
+    return t;
+}
+
+template <bool kSigned>
+__device__ __forceinline__ int warp_u8(const uint8_t* __restrict__ lt, int row, int c, const Taps& t) {
+    const int p00 = pix<kSigned>(__ldg(lt)), p01 = pix<kSigned>(__ldg(lt + c));
+    const int p10 = pix<kSigned>(__ldg(lt + row)), p11 = pix<kSigned>(__ldg(lt + row + c));
+    return (p00 * t.cx0 * t.cy0 + p10 * t.cx0 * t.cy1 + p01 * t.cx1 * t.cy0 + p11 * t.cx1 * t.cy1) >> 22;
+}
+
+// grid = (ceil(wo/32), ceil(ho/8), crops)
+template <typename T, bool kSigned>
+__global__ void __launch_bounds__(256) warp_affine_kernel(const T* __restrict__ frames, const int* __restrict__ frame_idx,
+                                                           const float* __restrict__ minv, T* __restrict__ dst,
+                                                           WarpGeom g, int crop0) {
+    __shared__ float m[6];
+    const int crop = crop0 + blockIdx.z;
+    if (threadIdx.y == 0 && threadIdx.x < 6) m[threadIdx.x] = __ldg(minv + 6 * (size_t)crop + threadIdx.x);
+    __syncthreads();
+    const int dx = blockIdx.x * 32 + threadIdx.x, dy = blockIdx.y * 8 + threadIdx.y;
+    if (dx >= g.wo || dy >= g.ho) return;
+    const size_t f = frame_idx ? (size_t)__ldg(frame_idx + crop) : (size_t)crop;
+    const T* img = frames + f * g.frame_elems;
+    T* out = dst + (size_t)crop * g.wo * g.ho * g.c;
+    const Taps t = warp_taps(m, dx, dy, g.w, g.h);
+    const int step = g.planar ? 1 : g.c;                          // element stride between x-neighbours
+    const size_t plane_in = g.planar ? (size_t)g.w * g.h : 1, plane_out = g.planar ? (size_t)g.wo * g.ho : 1;
+    const T* lt = img + (size_t)t.ofs * step;
+    T* o = out + ((size_t)dy * g.wo + dx) * step;
+    const int row = g.w * step;
+    for (int k = 0; k < g.c; ++k) {
+        T v;
+        if (!t.in) v = (T)0;   // reference leaves these untouched; defined as 0 (App. C-5)
+        else if (sizeof(T) == 1) v = (T)warp_u8<kSigned>((const uint8_t*)lt + k * plane_in, row, step, t);
+        else {
+            const float* p = (const float*)lt + k * plane_in;
+            const float cx0 = 1.f - t.fx, cx1 = t.fx, cy0 = 1.f - t.fy, cy1 = t.fy;
+            v = (T)(__ldg(p) * cx0 * cy0 + __ldg(p + row) * cx0 * cy1 + __ldg(p + step) * cx1 * cy0 +
+                    __ldg(p + row + step) * cx1 * cy1);
+        }
+        o[k * plane_out] = v;
+    }
+}
+
+// Fused: warp u8 HWC -> (u8 value) -> table[c][256] = normalised fp32.  One CTA per crop (grid.x) x row band
+// (grid.y); the exact 256 x c table is built once per CTA.  out_layout HWC (reference) or CHW planes.
+template <int C>
+__global__ void __launch_bounds__(256) warp_affine_normalize_kernel(const uint8_t* __restrict__ frames,
+                                                                     const int* __restrict__ frame_idx,
+                                                                     const float* __restrict__ minv,
+                                                                     float* __restrict__ dst, WarpGeom g,
+                                                                     const float* __restrict__ mean,
+                                                                     const float* __restrict__ stddev,
+                                                                     int out_layout, int rows_per_cta) {
+    __shared__ float lut[C][256];
+    __shared__ float m[6];
+    const int crop = blockIdx.x;
+    if (threadIdx.x < 6) m[threadIdx.x] = __ldg(minv + 6 * (size_t)crop + threadIdx.x);
+    for (int t = threadIdx.x; t < 256 * C; t += blockDim.x)
+        lut[t >> 8][t & 255] = normalize_one((float)(t & 255), __ldg(mean + (t >> 8)), (double)__ldg(stddev + (t >> 8)) + 1e-6);
+    __syncthreads();
+    const size_t f = frame_idx ? (size_t)__ldg(frame_idx + crop) : (size_t)crop;
+    const uint8_t* img = frames + f * g.frame_elems;
+    float* out = dst + (size_t)crop * g.wo * g.ho * C;
+    const int y0 = blockIdx.y * rows_per_cta, y1 = min(y0 + rows_per_cta, g.ho);
+    const int row = g.w * C;
+    const size_t plane = (size_t)g.wo * g.ho;
+    for (int i = y0 * g.wo + threadIdx.x; i < y1 * g.wo; i += blockDim.x) {
+        const int dy = i / g.wo, dx = i - dy * g.wo;
+        const Taps t = warp_taps(m, dx, dy, g.w, g.h);
+        const uint8_t* lt = img + (size_t)t.ofs * C;
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            const int v = t.in ? (warp_u8<false>(lt + k, row, C, t) & 0xff) : 0;
+            const float r = lut[k][v];
+            if (out_layout == VACV_NHWC) out[(size_t)i * C + k] = r;
+            else st_stream4f(out + k * plane + i, r);
+        }
+    }
+}
+
+}  // namespace vacv
+
+using namespace vacv;
+
+static int check_warp_args(const void* frames, const float* minv, const void* dst, int n_frames, int w, int h, int c,
+                           int n_crops, int w_out, int h_out) {
+    VACV_REQUIRE(frames && minv && dst, "warp_affine: null pointer");
+    VACV_REQUIRE(n_frames > 0 && n_crops > 0 && w > 1 && h > 1 && c > 0 && w_out > 0 && h_out > 0, "warp_affine: bad size");
+    return VACV_OK;
+}
+
+extern "C" int vacv_cuda_warp_affine(const void* frames, int n_frames, int w, int h, int c, int dtype, int layout,
+                                     const int* frame_idx, const float* minv, int n_crops,
+                                     void* dst, int w_out, int h_out, int flags, void* stream) {
+    if (int e = check_warp_args(frames, minv, dst, n_frames, w, h, c, n_crops, w_out, h_out)) return e;
+    if (dtype != VACV_INT8 && dtype != VACV_FP32) return set_error(VACV_ERR_UNSUPPORTED, "warp_affine: dtype %d", dtype);
+    VACV_REQUIRE(frame_idx || n_crops <= n_frames, "warp_affine: frame_idx == NULL needs n_crops <= n_frames");
+    WarpGeom g;
+    g.w = w; g.h = h; g.c = c; g.wo = w_out; g.ho = h_out; g.frame_elems = (size_t)w * h * c; g.planar = layout == VACV_NCHW;
+    cudaStream_t s = as_stream(stream);
+    dim3 block(32, 8);
+    for (int c0 = 0; c0 < n_crops; c0 += 65535) {
+        dim3 grid(ceil_div(w_out, 32), ceil_div(h_out, 8), min(n_crops - c0, 65535));
+        if (dtype == VACV_FP32)
+            warp_affine_kernel<float, false><<<grid, block, 0, s>>>((const float*)frames, frame_idx, minv, (float*)dst, g, c0);
+        else if (flags & VACV_FLAG_SIGNED_CHAR)
+            warp_affine_kernel<uint8_t, true><<<grid, block, 0, s>>>((const uint8_t*)frames, frame_idx, minv, (uint8_t*)dst, g, c0);
+        else
+            warp_affine_kernel<uint8_t, false><<<grid, block, 0, s>>>((const uint8_t*)frames, frame_idx, minv, (uint8_t*)dst, g, c0);
+    }
+    return check_launch("warp_affine");
+}
+
+extern "C" int vacv_cuda_warp_affine_normalize(const uint8_t* frames, int n_frames, int w, int h, int c,
+                                               const int* frame_idx, const float* minv, int n_crops,
+                                               float* dst, int w_out, int h_out, const float* mean, const float* stddev,
+                                               int out_layout, void* stream) {
+    if (int e = check_warp_args(frames, minv, dst, n_frames, w, h, c, n_crops, w_out, h_out)) return e;
+    VACV_REQUIRE(mean && stddev, "warp_affine_normalize: null statistics");
+    VACV_REQUIRE(frame_idx || n_crops <= n_frames, "warp_affine_normalize: frame_idx == NULL needs n_crops <= n_frames");
+    if (c != 1 && c != 3) return set_error(VACV_ERR_UNSUPPORTED, "warp_affine_normalize: c must be 1 or 3 (got %d)", c);
+    WarpGeom g;
+    g.w = w; g.h = h; g.c = c; g.wo = w_out; g.ho = h_out; g.frame_elems = (size_t)w * h * c; g.planar = 0;
+    // >= ~8k output pixels per CTA so the 256*c-entry table build is amortised
+    const int rows_per_cta = max(1, min(h_out, (8192 + w_out - 1) / w_out));
+    dim3 grid(n_crops, ceil_div(h_out, rows_per_cta));
+    cudaStream_t s = as_stream(stream);
+    if (c == 3) warp_affine_normalize_kernel<3><<<grid, 256, 0, s>>>(frames, frame_idx, minv, dst, g, mean, stddev, out_layout, rows_per_cta);
+    else warp_affine_normalize_kernel<1><<<grid, 256, 0, s>>>(frames, frame_idx, minv, dst, g, mean, stddev, out_layout, rows_per_cta);
+    return check_launch("warp_affine_normalize");
+}

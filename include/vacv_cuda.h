@@ -1,0 +1,133 @@
+/* vacv_cuda.h -- C-ABI of the B200-native vacv operator set (libvacv_cuda.so).
+ *
+ * This is the drop-in boundary beneath the reference's C++ API (reference: src/cv/cv.h:85-239 and
+ * src/common/tensor.h:53-54).  The reference has no FFI of its own -- its dispatchers pick a backend at
+ * compile time (`#if USE_NEON / USE_CUDA / else naive`, e.g. src/cv/resize.cpp:19-27) and call raw-pointer
+ * kernels (e.g. src/cv/resize_naive.h:9-33).  Each entry point below replaces one of those raw-pointer
+ * kernel families; the reference-side binding is shown in INTEGRATION.md and implemented by the C++
+ * shim library libvacv.so (include/vacv/cv.h keeps the `va_cv::*` signatures).
+ *
+ * Conventions
+ *   - plain C: pointers, ints, no C++/torch types.  Every function returns 0 on success, a negative
+ *     vacv_status otherwise; vacv_cuda_last_error() gives the message (thread-local).
+ *   - all data pointers are DEVICE pointers unless the parameter name starts with `h_`.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  All launches are asynchronous
+ *     and stream-ordered; nothing here synchronises or allocates.
+ *   - tensors are dense, no row pitch, exactly like vision::Tensor (src/common/tensor.cpp:524);
+ *     a batch is `batch` frames back to back.
+ *   - dtype / layout codes are the reference's: vision::DType (tensor.h:12-18), vision::DLayout (:21-24).
+ *   - u8 pixels have unsigned-char semantics (ARM ABI) unless VACV_FLAG_SIGNED_CHAR.
+ */
+#ifndef VACV_CUDA_H
+#define VACV_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define VACV_API
+#else
+#define VACV_API __attribute__((visibility("default")))
+#endif
+
+typedef enum {
+    VACV_OK = 0,
+    VACV_ERR_INVALID_ARG = -1,   /* null pointer, non-positive size, odd NV12 size ... */
+    VACV_ERR_UNSUPPORTED = -2,   /* dtype/layout/interpolation combination the reference has no native path for */
+    VACV_ERR_CUDA = -3           /* a CUDA runtime call or launch failed; message has the CUDA error string */
+} vacv_status;
+
+enum { VACV_FP32 = 0, VACV_FP16 = 1, VACV_INT8 = 2, VACV_FP64 = 3 };      /* vision::DType  */
+enum { VACV_NCHW = 0, VACV_NHWC = 1 };                                    /* vision::DLayout */
+enum { VACV_INTER_LINEAR = 1, VACV_INTER_CUBIC = 2 };                     /* va_cv::VInterMode (cv.h:28-36) */
+enum {
+    VACV_FLAG_NONE = 0,
+    VACV_FLAG_NEON_RULE = 1,     /* u8 bilinear with the rounding of resize_neon.cpp (aarch64 builds of the reference) */
+    VACV_FLAG_SIGNED_CHAR = 2    /* reproduce an x86 default-signed-char build of resize_naive/warp_affine_naive */
+};
+
+VACV_API int vacv_cuda_abi_version(void);
+VACV_API const char* vacv_cuda_last_error(void);
+
+/* ---- a1: CvtColor::nv_to_bgr_naive (src/cv/cvt_color.cpp:39-135) ------------------------------------------
+ * src: batch x [Y plane w*h | interleaved chroma w*h/2];  dst: batch x (h x w x 3) BGR.  w, h even.
+ * v_first = 1: chroma byte 0 is V (NV21 -- and what the reference does for BOTH codes 91 and 93);
+ * v_first = 0: true NV12. */
+VACV_API int vacv_cuda_cvt_nv2bgr(const uint8_t* src, uint8_t* dst, int batch, int w, int h, int v_first, void* stream);
+
+/* ---- a2: Crop::crop_naive_{hwc_rgb,chw} (src/cv/crop.cpp:44-142) -------------------------------------------
+ * ROI copy; dst = batch x (ch x cw x c) in the source layout.  dtype INT8 or FP32.  The rect must lie inside
+ * the frame (the reference does not clip; here it is rejected with VACV_ERR_INVALID_ARG). */
+VACV_API int vacv_cuda_crop(const void* src, void* dst, int batch, int w, int h, int c, int dtype, int layout,
+                            int left, int top, int cw, int ch, void* stream);
+
+/* ---- a3: Tensor::change_layout (src/common/tensor.cpp:393-457) --------------------------------------------
+ * HWC <-> CHW permutation per frame; dtype INT8, FP16 (moved as 16-bit) or FP32. */
+VACV_API int vacv_cuda_layout_change(const void* src, void* dst, int batch, int w, int h, int c, int dtype,
+                                     int from_layout, int to_layout, void* stream);
+
+/* ---- a4: Tensor::change_dtype (src/common/tensor.cpp:459-502) ---------------------------------------------
+ * INT8->FP32 (unsigned) or FP32->INT8 (truncate toward zero, domain [0,256)); n = element count. */
+VACV_API int vacv_cuda_dtype_change(const void* src, void* dst, size_t n, int from_dtype, int to_dtype, void* stream);
+
+/* ---- a5-a9: Resize::resize_naive (src/cv/resize.cpp:42-100) -----------------------------------------------
+ *   INTER_LINEAR INT8 : ResizeNaive::resize_naive_inter_linear_u8   (resize_naive.cpp:10-68)   bit-exact
+ *                       (+VACV_FLAG_NEON_RULE: ResizeNeon::resize_neon_inter_linear_* resize_neon.cpp:12-347)
+ *   INTER_LINEAR FP32 : resize_naive_inter_linear_fp32              (resize_naive.cpp:70-128)
+ *   INTER_CUBIC  FP32 : resize_naive_inter_cubic_fp32_{hwc,chw}     (resize_naive.cpp:130-569), intended buffers
+ *   INTER_CUBIC  INT8 : OpenCV 2.4.13 cv::resize (the reference's only path, resize.cpp:33-36), HWC only
+ * Same-size input is copied (resize.cpp:58-61, full length). */
+VACV_API int vacv_cuda_resize(const void* src, void* dst, int batch, int w, int h, int c, int dtype, int layout,
+                              int w_out, int h_out, int interpolation, int flags, void* stream);
+
+/* ---- a10: WarpAffine (src/cv/warp_affine.cpp:76-169, warp_affine_naive.cpp:9-106) --------------------------
+ * Host helpers reproduce the reference's mixed float/double matrix arithmetic exactly. */
+VACV_API void vacv_invert_affine(float h_m[6]);                                         /* warp_affine.cpp:121-133 */
+VACV_API void vacv_rotation_matrix(float scale, float rot_deg, const double h_aux[4], float h_m[6]); /* :76-109 */
+/* Crop i samples frame frame_idx[i] (frame i if frame_idx == NULL) of `frames` (n_frames dense frames) with the
+ * INVERTED 2x3 matrix minv[6*i .. 6*i+5]; dst = n_crops x (h_out x w_out x c) in the source layout.
+ * Destination pixels that map outside the source are written as 0 (== the reference with a zeroed dst). */
+VACV_API int vacv_cuda_warp_affine(const void* frames, int n_frames, int w, int h, int c, int dtype, int layout,
+                                   const int* frame_idx, const float* minv, int n_crops,
+                                   void* dst, int w_out, int h_out, int flags, void* stream);
+
+/* ---- a11: mean / stddev (src/cv/normalize_naive.cpp:7-72; exact-sum decision SURVEY App. C-4) -------------
+ * Accumulates per-channel sum(x) and sum(x^2) of u8 pixels into sums[set][2*c] (u64; [2k]=Sx, [2k+1]=Sxx).
+ * per_frame = 0: one set for the whole batch; 1: one set per frame.  The caller zeroes `sums`.  For a
+ * batch-global statistic over several GPUs, all-reduce `sums` (sum, 2*c u64) between the two calls. */
+VACV_API int vacv_cuda_sums_u8(const uint8_t* src, int batch, int w, int h, int c, int layout,
+                               unsigned long long* sums, int per_frame, void* stream);
+/* mean = Sx/n, stddev = sqrt(max(Sxx/n - mean^2, 0)) in fp64, stored fp32 (population stddev). */
+VACV_API int vacv_cuda_finalize_mean_stddev(const unsigned long long* sums, int n_sets, int c,
+                                            unsigned long long n_per_channel, float* mean, float* stddev, void* stream);
+
+/* ---- a12: NormalizeNaive::normalize_naive_{hwc_bgr,chw} (src/cv/normalize_naive.cpp:74-90) -----------------
+ * dst = (float)((double)(x - mean[k]) / ((double)stddev[k] + 1e-6)), x converted from u8 first when
+ * src_dtype == INT8 (normalize.cpp:92-95).  mean/stddev: c floats (stats_per_frame = 0) or batch x c. */
+VACV_API int vacv_cuda_normalize(const void* src, float* dst, int batch, int w, int h, int c, int src_dtype, int layout,
+                                 const float* mean, const float* stddev, int stats_per_frame, void* stream);
+
+/* ---- a13: fused entry points (API: cv.h:154-201; semantics = composition) ----------------------
+ * Config 2: nv->bgr -> resize INTER_LINEAR u8 -> u8->fp32 -> normalize -> HWC->CHW in ONE pass; intermediates
+ * never touch HBM.  dst = batch x (3 x h_out x w_out) fp32 planes, bit-identical to the unfused chain. */
+VACV_API int vacv_cuda_nv_resize_normalize_chw(const uint8_t* src, float* dst, int batch, int w, int h, int v_first,
+                                               int w_out, int h_out, const float* mean, const float* stddev, void* stream);
+/* ResizeNormalize::resize_normalize (resize_normalize.cpp:15-31): resize INTER_LINEAR u8 HWC -> fp32 normalised;
+ * out_layout chooses HWC (reference) or CHW (fuses the change_layout that usually follows). */
+VACV_API int vacv_cuda_resize_normalize(const uint8_t* src, float* dst, int batch, int w, int h, int c,
+                                        int w_out, int h_out, const float* mean, const float* stddev,
+                                        int out_layout, void* stream);
+/* WarpAffineNormalize::warp_affine_normalize (warp_affine_normalize.cpp:13-45): warp u8 HWC -> fp32 normalised. */
+VACV_API int vacv_cuda_warp_affine_normalize(const uint8_t* frames, int n_frames, int w, int h, int c,
+                                             const int* frame_idx, const float* minv, int n_crops,
+                                             float* dst, int w_out, int h_out, const float* mean, const float* stddev,
+                                             int out_layout, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VACV_CUDA_H */

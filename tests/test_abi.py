@@ -1,0 +1,71 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads, and exports exactly the symbols
+include/vacv_cuda.h declares; argument validation and the host-side matrix helpers work without a GPU."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "vacv_cuda.h")
+LIB = os.path.join(ROOT, "arm-neon-opencv_b200", "libvacv_cuda.so")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    return sorted(set(re.findall(r"VACV_API\s+[\w\s\*]+?\b(vacv_\w+)\s*\(", text)))
+
+
+def test_header_declares_the_operator_set():
+    syms = declared_symbols()
+    for op in ["cvt_nv2bgr", "crop", "layout_change", "dtype_change", "resize", "warp_affine", "sums_u8",
+               "finalize_mean_stddev", "normalize", "nv_resize_normalize_chw", "resize_normalize",
+               "warp_affine_normalize"]:
+        assert f"vacv_cuda_{op}" in syms
+    assert "vacv_invert_affine" in syms and "vacv_rotation_matrix" in syms
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(LIB), "run __graft_entry__.build() first"
+    out = subprocess.check_output(["nm", "-D", "--defined-only", LIB], text=True)
+    exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
+    missing = [s for s in declared_symbols() if s not in exported]
+    assert not missing, f"declared in the header but not exported: {missing}"
+    stray = [s for s in exported if not s.startswith("vacv_")]
+    assert not stray, f"non-API symbols leak from the library: {stray}"
+
+
+def test_library_is_built_for_sm_100a_only():
+    out = subprocess.check_output(["cuobjdump", "--list-elf", LIB], text=True)
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_python_binding_covers_the_header():
+    import vacv_b200 as vacv
+    assert sorted(vacv.EXPORTS) == declared_symbols()
+    assert vacv.lib.vacv_cuda_abi_version() == 1
+
+
+def test_argument_validation_without_gpu():
+    import vacv_b200 as vacv
+    # validation happens before any CUDA call, so these return error codes even with no device
+    assert vacv.lib.vacv_cuda_cvt_nv2bgr(None, None, 1, 16, 16, 1, None) == -1
+    assert b"null" in vacv.lib.vacv_cuda_last_error()
+    buf = C.create_string_buffer(64)
+    p = C.cast(buf, C.c_void_p)
+    assert vacv.lib.vacv_cuda_cvt_nv2bgr(p, p, 1, 15, 16, 1, None) == -1          # odd width
+    assert vacv.lib.vacv_cuda_crop(p, p, 1, 10, 10, 3, vacv.INT8, vacv.NHWC, 5, 5, 10, 10, None) == -1   # rect outside
+    assert vacv.lib.vacv_cuda_dtype_change(p, p, 8, vacv.FP16, vacv.FP32, None) == -2   # unsupported pair
+    assert vacv.lib.vacv_cuda_resize(p, p, 1, 8, 8, 3, vacv.INT8, vacv.NHWC, 4, 4, 0, 0, None) == -2   # INTER_NEAREST
+
+
+def test_host_matrix_helpers_match_oracle(oracle):
+    import vacv_b200 as vacv
+    m = [0.849158, 0.012257, -474.827, -0.01225, 0.849158, -379.18]   # test_warp_affine.cpp:31-32
+    assert np.array_equal(np.array(vacv.invert_affine(m), np.float32).view(np.uint32), oracle.invert_affine(m).view(np.uint32))
+    aux = [738.518372, 537.672852, 204.766998, 73.329681]
+    got = np.array(vacv.rotation_matrix(1.073914, -3.314525, aux), np.float32)
+    assert np.array_equal(got.view(np.uint32), oracle.rotation_matrix(1.073914, -3.314525, aux).view(np.uint32))
+    assert np.array_equal(np.array(vacv.invert_affine([0, 0, 1, 0, 0, 1]), np.float32)[[0, 4]], [0, 0])   # singular: D = 0

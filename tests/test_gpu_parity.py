@@ -1,0 +1,433 @@
+"""GPU parity: every CUDA operator, called through the C-ABI (libvacv_cuda.so via ctypes), against the oracle
+(oracle/vacv_oracle.c) and -- when oracle/_ref travelled to the box -- the unmodified reference itself, on the same
+seeded inputs.  Integer / u8 outputs: bit-exact.  fp32 outputs: bit-exact where the operation order is reproduced
+(everything here), which implies the north star's 1e-5 relative / cosine >= 0.99999 bounds; those bounds are also
+asserted explicitly for the fused pipeline."""
+import numpy as np
+import pytest
+
+from oracle_lib import (COLOR_YUV2BGR_NV21, INTER_CUBIC as R_CUBIC, INTER_LINEAR as R_LINEAR, NCHW, NHWC, Ref,
+                        load_fixture, ref_available)
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def vacv():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import vacv_b200
+    return vacv_b200
+
+
+def rng(seed):
+    return np.random.default_rng(seed)
+
+
+def u8(seed, *shape):
+    return rng(seed).integers(0, 256, shape, dtype=np.uint8)
+
+
+def f32(seed, *shape):
+    return (rng(seed).random(shape, dtype=np.float32) * 255).astype(np.float32)
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def host(t):
+    torch.cuda.synchronize()
+    return t.cpu().numpy()
+
+
+def bits(a):
+    return a.view(np.uint32) if a.dtype == np.float32 else a
+
+
+def assert_same(got, want):
+    assert got.shape == want.shape, (got.shape, want.shape)
+    if not np.array_equal(bits(got), bits(want)):
+        bad = np.flatnonzero(bits(got).ravel() != bits(want).ravel())
+        raise AssertionError(f"{bad.size} of {got.size} elements differ; first at {bad[0]}: got {got.ravel()[bad[0]]} want {want.ravel()[bad[0]]}")
+
+
+MEAN = np.array([103.53, 116.28, 123.675], np.float32)
+STD = np.array([57.375, 57.12, 58.395], np.float32)
+
+
+# ------------------------------------------------------------------ a1 yuv -> bgr
+@pytest.mark.parametrize("w,h,b", [(1920, 1080, 2), (640, 360, 3), (16, 2, 1), (2, 2, 1), (642, 362, 2), (4096, 16, 1)])
+@pytest.mark.parametrize("v_first", [True, False])
+def test_cvt_nv2bgr(vacv, oracle, w, h, b, v_first):
+    src = u8(w + h, b, w * h * 3 // 2)
+    got = host(vacv.cvt_nv2bgr(dev(src), w, h, v_first))
+    want = np.stack([oracle.nv_to_bgr(src[i], w, h, int(v_first)) for i in range(b)])
+    assert_same(got, want)
+
+
+def test_cvt_nv2bgr_vs_reference_roundtrip_fixture(vacv):
+    """The reference's own test: BGR fixture -> bgr2nv21 -> cvt_color (test_cvt_color.cpp:23-77)."""
+    img = load_fixture("universe1920x1080")
+    if img is None or not ref_available():
+        pytest.skip("oracle/_ref not staged")
+    ref = Ref()
+    nv = ref.bgr2nv21(img)
+    want = ref.cvt_color(nv, 1920, 1080, COLOR_YUV2BGR_NV21)
+    got = host(vacv.cvt_nv2bgr(dev(nv[None]), 1920, 1080, True))[0]
+    assert_same(got, want)
+
+
+def test_cvt_nv2bgr_rejects_odd(vacv):
+    with pytest.raises(vacv.VacvError):
+        vacv.cvt_nv2bgr(dev(u8(0, 1, 15 * 10 * 3 // 2 + 8)), 15, 10)
+
+
+# ------------------------------------------------------------------ a2 crop
+@pytest.mark.parametrize("layout", [NHWC, NCHW])
+@pytest.mark.parametrize("dt", ["u8", "f32"])
+@pytest.mark.parametrize("rect", [(0, 0, 5, 5), (0, 0, 320, 180), (7, 3, 193, 96), (33, 17, 607, 343), (1, 0, 639, 360)])
+def test_crop(vacv, oracle, layout, dt, rect):
+    w, h, c, b = 640, 360, 3, 2
+    shape = (b, h, w, c) if layout == NHWC else (b, c, h, w)
+    src = u8(1, *shape) if dt == "u8" else f32(1, *shape)
+    l, t, cw, ch = rect
+    got = host(vacv.crop(dev(src), layout, l, t, cw, ch))
+    want = np.stack([oracle.crop(src[i], w, h, c, layout, l, t, cw, ch) for i in range(b)])
+    assert_same(got, want)
+
+
+def test_crop_reference_sizes(vacv, oracle):
+    """test_crop.cpp:16-20 rects at the origin of the 2560x1440 fixture shape."""
+    src = u8(2, 1, 1440, 2560, 3)
+    for cw, ch in [(5, 5), (320, 180), (640, 360), (1280, 720), (1920, 1080)]:
+        got = host(vacv.crop(dev(src), NHWC, 0, 0, cw, ch))[0]
+        assert_same(got, oracle.crop(src[0], 2560, 1440, 3, NHWC, 0, 0, cw, ch))
+
+
+def test_crop_rejects_out_of_frame(vacv):
+    with pytest.raises(vacv.VacvError):
+        vacv.crop(dev(u8(0, 1, 10, 10, 3)), NHWC, 5, 5, 10, 10)
+
+
+# ------------------------------------------------------------------ a3 / a4 layout, dtype
+@pytest.mark.parametrize("dt", ["u8", "f32"])
+@pytest.mark.parametrize("w,h,c", [(176, 144, 3), (1920, 1080, 3), (33, 7, 3), (33, 7, 4), (5, 3, 2), (64, 64, 1)])
+def test_layout_roundtrip(vacv, oracle, dt, w, h, c):
+    b = 2
+    src = u8(3, b, h, w, c) if dt == "u8" else f32(3, b, h, w, c)
+    chw = host(vacv.layout_change(dev(src), NHWC, NCHW))
+    want = np.stack([oracle.hwc_to_chw(src[i], w, h, c) for i in range(b)])
+    assert_same(chw, want)
+    back = host(vacv.layout_change(dev(chw), NCHW, NHWC))
+    assert_same(back, src)
+
+
+def test_dtype_change(vacv, oracle):
+    for n in [176 * 144 * 3, 1920 * 1080 * 3, 1001, 3]:
+        src = u8(4, n)
+        assert_same(host(vacv.dtype_change(dev(src), vacv.FP32)), oracle.u8_to_f32(src))
+        g = (rng(5).random(n, dtype=np.float32) * 255.999).astype(np.float32)
+        assert_same(host(vacv.dtype_change(dev(g), vacv.INT8)), oracle.f32_to_u8(g))
+    with pytest.raises(vacv.VacvError):   # the reference silently returns garbage here (tensor.cpp:494-499)
+        vacv.dtype_change(dev(np.zeros(8, np.float16)), vacv.FP32)
+
+
+# ------------------------------------------------------------------ a5-a7 bilinear
+LIN_SIZES = [((64, 48), (20, 16)), ((64, 48), (200, 111)), ((1920, 1080), (640, 360)), ((1920, 1080), (640, 640)),
+             ((333, 211), (500, 300)), ((2, 2), (7, 5)), ((640, 360), (639, 359)), ((2560, 1440), (320, 180))]
+
+
+@pytest.mark.parametrize("layout", [NHWC, NCHW])
+@pytest.mark.parametrize("sz", LIN_SIZES)
+def test_resize_linear_u8(vacv, oracle, layout, sz):
+    (w, h), (wo, ho) = sz
+    b, c = 2, 3
+    shape = (b, h, w, c) if layout == NHWC else (b, c, h, w)
+    src = u8(6, *shape)
+    got = host(vacv.resize(dev(src), layout, wo, ho, vacv.INTER_LINEAR))
+    want = np.stack([oracle.resize_linear(src[i], w, h, c, layout, wo, ho) for i in range(b)])
+    assert_same(got, want)
+
+
+def test_resize_linear_u8_config1_fixture_vs_reference(vacv):
+    img = load_fixture("universe1920x1080")
+    if img is None or not ref_available():
+        pytest.skip("oracle/_ref not staged")
+    want = Ref().resize(img, 1920, 1080, 3, NHWC, 640, 360, R_LINEAR)
+    got = host(vacv.resize(dev(img[None]), NHWC, 640, 360))[0]
+    assert_same(got, want)
+
+
+def test_resize_linear_u8_flags(vacv, oracle):
+    w, h, c, wo, ho = 333, 211, 3, 200, 100
+    src = u8(7, 1, h, w, c)
+    got = host(vacv.resize(dev(src), NHWC, wo, ho, vacv.INTER_LINEAR, vacv.FLAG_SIGNED_CHAR))[0]
+    assert_same(got, oracle.resize_linear(src[0], w, h, c, NHWC, wo, ho, signed_char=1))
+    got = host(vacv.resize(dev(src), NHWC, wo, ho, vacv.INTER_LINEAR, vacv.FLAG_NEON_RULE))[0]
+    assert_same(got, oracle.resize_linear_neon_rule(src[0], w, h, c, NHWC, wo, ho))
+    chw = np.ascontiguousarray(src.transpose(0, 3, 1, 2))
+    got = host(vacv.resize(dev(chw), NCHW, wo, ho, vacv.INTER_LINEAR, vacv.FLAG_NEON_RULE))[0]
+    assert_same(got, oracle.resize_linear_neon_rule(chw[0], w, h, c, NCHW, wo, ho))
+
+
+@pytest.mark.parametrize("layout", [NHWC, NCHW])
+@pytest.mark.parametrize("sz", LIN_SIZES[:5] + [((2560, 1440), (320, 180))])
+def test_resize_linear_f32(vacv, oracle, layout, sz):
+    (w, h), (wo, ho) = sz
+    b, c = 1, 3
+    shape = (b, h, w, c) if layout == NHWC else (b, c, h, w)
+    src = f32(8, *shape)
+    got = host(vacv.resize(dev(src), layout, wo, ho, vacv.INTER_LINEAR))
+    want = np.stack([oracle.resize_linear(src[i], w, h, c, layout, wo, ho) for i in range(b)])
+    assert_same(got, want)
+
+
+def test_resize_same_size_is_copy(vacv):
+    src = f32(9, 2, 30, 40, 3)
+    assert_same(host(vacv.resize(dev(src), NHWC, 40, 30)), src)
+
+
+# ------------------------------------------------------------------ a8 / a9 bicubic
+@pytest.mark.parametrize("layout", [NHWC, NCHW])
+@pytest.mark.parametrize("sz", [((64, 48), (37, 20)), ((64, 48), (20, 37)), ((2560, 1440), (1920, 1080)),
+                                ((320, 180), (640, 360)), ((16, 16), (5, 9)), ((64, 48), (100, 100))])
+def test_resize_cubic_f32(vacv, oracle, layout, sz):
+    (w, h), (wo, ho) = sz
+    c = 3
+    shape = (1, h, w, c) if layout == NHWC else (1, c, h, w)
+    src = f32(10, *shape)
+    got = host(vacv.resize(dev(src), layout, wo, ho, vacv.INTER_CUBIC))[0]
+    want = oracle.resize_cubic_f32(src[0], w, h, c, layout, wo, ho)
+    assert_same(got, want)
+
+
+@pytest.mark.parametrize("c", [1, 3, 4])
+@pytest.mark.parametrize("sz", [((2560, 1440), (1920, 1080)), ((256, 144), (100, 70)), ((176, 144), (640, 640)),
+                                ((257, 145), (300, 171)), ((64, 48), (333, 77)), ((64, 48), (21, 13)),
+                                ((8, 8), (3, 3)), ((5, 4), (13, 11))])
+def test_resize_cubic_u8(vacv, oracle, c, sz):
+    (w, h), (wo, ho) = sz
+    if c != 3 and w > 1000:
+        pytest.skip("big case only for c=3")
+    src = u8(11 + c, 2, h, w, c)
+    got = host(vacv.resize(dev(src), NHWC, wo, ho, vacv.INTER_CUBIC))
+    want = np.stack([oracle.resize_cubic_u8(src[i], w, h, c, wo, ho) for i in range(2)])
+    assert_same(got, want)
+
+
+def test_resize_cubic_u8_config4_fixture_vs_bundled_opencv(vacv):
+    img = load_fixture("lakers2560x1440")
+    if img is None or not ref_available():
+        pytest.skip("oracle/_ref not staged")
+    want = Ref().cv_resize(img, 2560, 1440, 3, 1920, 1080, R_CUBIC)
+    got = host(vacv.resize(dev(img[None]), NHWC, 1920, 1080, vacv.INTER_CUBIC))[0]
+    assert_same(got, want)
+
+
+# ------------------------------------------------------------------ a10 warp affine
+M_TEST = [0.849158, 0.012257, -474.827, -0.01225, 0.849158, -379.18]           # test_warp_affine.cpp:31-32
+ROT_TEST = dict(scale=1.073914, rot=-3.314525, aux=[738.518372, 537.672852, 204.766998, 73.329681])
+
+
+def test_host_matrix_helpers(vacv, oracle):
+    assert np.array_equal(np.array(vacv.invert_affine(M_TEST), np.float32).view(np.uint32),
+                          oracle.invert_affine(M_TEST).view(np.uint32))
+    m = np.array(vacv.rotation_matrix(ROT_TEST["scale"], ROT_TEST["rot"], ROT_TEST["aux"]), np.float32)
+    assert np.array_equal(m.view(np.uint32), oracle.rotation_matrix(ROT_TEST["scale"], ROT_TEST["rot"], ROT_TEST["aux"]).view(np.uint32))
+
+
+@pytest.mark.parametrize("layout", [NHWC, NCHW])
+@pytest.mark.parametrize("dt", ["u8", "f32"])
+def test_warp_affine_reference_matrix(vacv, oracle, layout, dt):
+    w, h, c, wo, ho = 1280, 720, 3, 240, 240
+    img = load_fixture("t1280x720")
+    hwc = img if img is not None else u8(12, h, w, c)
+    src = hwc if layout == NHWC else np.ascontiguousarray(hwc.transpose(2, 0, 1))
+    if dt == "f32":
+        src = src.astype(np.float32)
+    minv = np.array(vacv.invert_affine(M_TEST), np.float32)
+    got = host(vacv.warp_affine(dev(src[None]), layout, dev(minv[None]), wo, ho))[0]
+    want = oracle.warp_affine(src, w, h, c, layout, wo, ho, minv)
+    assert_same(got, want)
+    if ref_available() and img is not None:
+        want_ref, _ = Ref().warp_affine(src, w, h, c, layout, wo, ho, M_TEST)
+        assert_same(got, want_ref)
+
+
+def test_warp_affine_rotation_variant(vacv, oracle):
+    w, h, wo, ho = 1280, 720, 140, 210
+    img = load_fixture("t1280x720_grey")
+    src = img if img is not None else u8(13, h, w, 1)
+    minv = np.array(vacv.invert_affine(vacv.rotation_matrix(ROT_TEST["scale"], ROT_TEST["rot"], ROT_TEST["aux"])), np.float32)
+    got = host(vacv.warp_affine(dev(src[None]), NHWC, dev(minv[None]), wo, ho))[0]
+    assert_same(got, oracle.warp_affine(src, w, h, 1, NHWC, wo, ho, minv))
+    if ref_available() and img is not None:
+        assert_same(got, Ref().warp_affine_rot(src, w, h, 1, NHWC, wo, ho, ROT_TEST["scale"], ROT_TEST["rot"], ROT_TEST["aux"]))
+
+
+def random_face_matrices(n, w, h, wo, seed):
+    r = rng(seed)
+    ms = []
+    for _ in range(n):
+        s = r.uniform(0.3, 0.6)
+        a = np.deg2rad(r.uniform(-15, 15))
+        cx, cy = r.uniform(0.3 * w, 0.7 * w), r.uniform(0.3 * h, 0.7 * h)
+        al, be = s * np.cos(a), s * np.sin(a)
+        ms.append([al, be, wo / 2 - al * cx - be * cy, -be, al, wo / 2 + be * cx - al * cy])
+    return ms
+
+
+def test_warp_affine_batch_with_frame_pool(vacv, oracle):
+    w, h, c, wo, ho, nf, n = 320, 200, 3, 112, 112, 4, 24
+    frames = u8(14, nf, h, w, c)
+    fwd = random_face_matrices(n, w, h, wo, 7) + [[5, 0, 1000, 0, 5, 1000]]   # last one maps fully outside -> zeros
+    n += 1
+    minv = np.array([vacv.invert_affine(m) for m in fwd], np.float32)
+    idx = (np.arange(n) % nf).astype(np.int32)
+    got = host(vacv.warp_affine(dev(frames), NHWC, dev(minv), wo, ho, dev(idx)))
+    for i in range(n):
+        assert_same(got[i], oracle.warp_affine(frames[idx[i]], w, h, c, NHWC, wo, ho, minv[i]))
+    assert not got[-1].any()
+    got_sc = host(vacv.warp_affine(dev(frames), NHWC, dev(minv), wo, ho, dev(idx), vacv.FLAG_SIGNED_CHAR))
+    assert_same(got_sc[3], oracle.warp_affine(frames[idx[3]], w, h, c, NHWC, wo, ho, minv[3], signed_char=1))
+
+
+def test_warp_affine_normalize_fused(vacv, oracle):
+    w, h, c, wo, ho, nf, n = 320, 200, 3, 112, 112, 3, 10
+    frames = u8(15, nf, h, w, c)
+    minv = np.array([vacv.invert_affine(m) for m in random_face_matrices(n, w, h, wo, 8)], np.float32)
+    idx = (np.arange(n) % nf).astype(np.int32)
+    got = host(vacv.warp_affine_normalize(dev(frames), dev(minv), wo, ho, dev(MEAN), dev(STD), dev(idx)))
+    for i in range(n):
+        assert_same(got[i], oracle.warp_affine_normalize(frames[idx[i]], w, h, c, minv[i], wo, ho, MEAN, STD))
+    got_chw = host(vacv.warp_affine_normalize(dev(frames), dev(minv), wo, ho, dev(MEAN), dev(STD), dev(idx), out_layout=NCHW))
+    assert_same(got_chw, np.ascontiguousarray(got.transpose(0, 3, 1, 2)))
+
+
+# ------------------------------------------------------------------ a11 / a12 statistics, normalize
+@pytest.mark.parametrize("layout", [NHWC, NCHW])
+@pytest.mark.parametrize("w,h,b", [(284, 214, 3), (3840, 2160, 2), (176, 144, 1), (33, 7, 2)])
+def test_sums_and_mean_stddev(vacv, oracle, layout, w, h, b):
+    c = 3
+    shape = (b, h, w, c) if layout == NHWC else (b, c, h, w)
+    src = u8(16, *shape)
+    want = np.stack([oracle.sums_u8(src[i], w * h, c, layout) for i in range(b)]).astype(np.int64).reshape(b, c, 2)
+    got_pf = host(vacv.sums_u8(dev(src), layout, per_frame=True))
+    assert_same(got_pf, want)
+    got_all = host(vacv.sums_u8(dev(src), layout, per_frame=False))
+    assert_same(got_all, want.sum(0, keepdims=True))
+    mean, std = vacv.finalize_mean_stddev(dev(got_all), b * w * h)
+    m_o, s_o = oracle.finalize_mean_stddev(want.sum(0).astype(np.uint64).ravel(), c, b * w * h)
+    assert_same(host(mean)[0], m_o)
+    assert_same(host(std)[0], s_o)
+    if ref_available() and layout == NHWC and b == 1:
+        m_cv, s_cv = Ref().cv_mean_stddev(src[0], w, h, c)   # the truth the reference's own test uses
+        assert np.allclose(host(mean)[0], m_cv, rtol=1e-6) and np.allclose(host(std)[0], s_cv, rtol=1e-6)
+
+
+@pytest.mark.parametrize("layout", [NHWC, NCHW])
+@pytest.mark.parametrize("dt", ["u8", "f32"])
+@pytest.mark.parametrize("w,h,b", [(176, 144, 2), (284, 214, 1), (33, 7, 1)])
+def test_normalize(vacv, oracle, layout, dt, w, h, b):
+    c = 3
+    shape = (b, h, w, c) if layout == NHWC else (b, c, h, w)
+    if dt == "u8" and b > 1 and (w * h * c) % 4:
+        pytest.skip("u8 batch needs 4-byte frames")
+    src = u8(17, *shape) if dt == "u8" else f32(17, *shape)
+    got = host(vacv.normalize(dev(src), layout, dev(MEAN), dev(STD)))
+    want = np.stack([oracle.normalize(src[i], w * h, c, layout, MEAN, STD) for i in range(b)])
+    assert_same(got, want)
+    # per-frame statistics
+    means = np.stack([MEAN + i for i in range(b)]).astype(np.float32)
+    stds = np.stack([STD + 0.5 * i for i in range(b)]).astype(np.float32)
+    got = host(vacv.normalize(dev(src), layout, dev(means), dev(stds), stats_per_frame=True))
+    want = np.stack([oracle.normalize(src[i], w * h, c, layout, means[i], stds[i]) for i in range(b)])
+    assert_same(got, want)
+
+
+def test_auto_stats_normalize_matches_reference_semantics(vacv, oracle):
+    """va_cv::normalize with empty mean/stddev (normalize.cpp:98-108) = stats pass + apply pass."""
+    img = load_fixture("t284x214")
+    src = img if img is not None else u8(18, 214, 284, 3)
+    d = dev(src[None])
+    mean, std = vacv.finalize_mean_stddev(vacv.sums_u8(d, NHWC), 284 * 214)
+    got = host(vacv.normalize(d, NHWC, mean[0], std[0]))[0]
+    sums = oracle.sums_u8(src, 284 * 214, 3, NHWC)
+    m, s = oracle.finalize_mean_stddev(sums, 3, 284 * 214)
+    assert_same(got, oracle.normalize(src, 284 * 214, 3, NHWC, m, s))
+    if ref_available() and img is not None:
+        want = Ref().normalize(src, 284, 214, 3, NHWC)      # reference: sequential-fp32 statistics
+        assert np.abs(got - want).max() < 5e-3               # documented deviation (App. C-4), tiny at this size
+
+
+# ------------------------------------------------------------------ a13 fused pipelines
+@pytest.mark.parametrize("v_first", [True, False])
+@pytest.mark.parametrize("w,h,wo,ho,b", [(1920, 1080, 640, 640, 2), (640, 360, 224, 224, 3), (64, 48, 100, 37, 2),
+                                         (1280, 720, 640, 384, 1), (642, 362, 300, 200, 2), (3840, 2160, 640, 640, 1),
+                                         (320, 240, 1000, 700, 1), (1920, 1080, 1919, 1079, 1)])
+def test_fused_pipeline_config2(vacv, oracle, v_first, w, h, wo, ho, b):
+    src = u8(19 + w, b, w * h * 3 // 2)
+    got = host(vacv.nv_resize_normalize_chw(dev(src), w, h, wo, ho, dev(MEAN), dev(STD), v_first))
+    want = oracle.nv_resize_normalize_chw(src, w, h, int(v_first), wo, ho, MEAN, STD, batch=b, threads=4)
+    assert_same(got, want)
+    # the north star's stated bounds, explicitly
+    rel = np.abs(got - want) / np.maximum(np.abs(want), 1e-6)
+    assert rel.max() <= 1e-5
+    a, bb = got.astype(np.float64).ravel(), want.astype(np.float64).ravel()
+    assert a @ bb / np.sqrt((a @ a) * (bb @ bb)) >= 0.99999
+
+
+def test_fused_pipeline_equals_unfused_cuda_chain(vacv):
+    w, h, wo, ho, b = 1920, 1080, 640, 640, 2
+    src = dev(u8(20, b, w * h * 3 // 2))
+    fused = vacv.nv_resize_normalize_chw(src, w, h, wo, ho, dev(MEAN), dev(STD))
+    bgr = vacv.cvt_nv2bgr(src, w, h)
+    small = vacv.resize(bgr, NHWC, wo, ho)
+    norm = vacv.normalize(small, NHWC, dev(MEAN), dev(STD))
+    chain = vacv.layout_change(norm, NHWC, NCHW)
+    assert_same(host(fused), host(chain))
+
+
+def test_fused_pipeline_vs_reference_chain(vacv):
+    if not ref_available():
+        pytest.skip("oracle/_ref not staged")
+    w, h, wo, ho = 1920, 1080, 640, 640
+    src = u8(21, 1, w * h * 3 // 2)
+    want = Ref().pipeline(src[0], w, h, COLOR_YUV2BGR_NV21, wo, ho, MEAN, STD)
+    got = host(vacv.nv_resize_normalize_chw(dev(src), w, h, wo, ho, dev(MEAN), dev(STD)))[0]
+    assert_same(got, want)
+
+
+@pytest.mark.parametrize("out_layout", [NHWC, NCHW])
+def test_resize_normalize_fused(vacv, oracle, out_layout):
+    w, h, c, wo, ho, b = 640, 360, 3, 224, 200, 2
+    src = u8(22, b, h, w, c)
+    got = host(vacv.resize_normalize(dev(src), wo, ho, dev(MEAN), dev(STD), out_layout))
+    for i in range(b):
+        small = oracle.resize_linear(src[i], w, h, c, NHWC, wo, ho)
+        want = oracle.normalize(small, wo * ho, c, NHWC, MEAN, STD)
+        if out_layout == NCHW:
+            want = oracle.hwc_to_chw(want, wo, ho, c)
+        assert_same(got[i], want)
+
+
+# ------------------------------------------------------------------ full-size, size-independent properties
+def test_full_size_config2_properties(vacv):
+    """256 x 1080p is too slow for the CPU oracle; check (i) batch independence: every frame equals the same
+    frame processed alone, (ii) a flat grey frame maps to the single table value."""
+    w, h, wo, ho, b = 1920, 1080, 640, 640, 64
+    g = torch.Generator(device="cuda").manual_seed(0)
+    src = torch.randint(0, 256, (b, w * h * 3 // 2), dtype=torch.uint8, device="cuda", generator=g)
+    src[5] = 128   # Y=128, U=V=128 -> BGR (128,128,128)
+    mean, std = dev(MEAN), dev(STD)
+    out = vacv.nv_resize_normalize_chw(src, w, h, wo, ho, mean, std)
+    for i in (0, 5, 63):
+        single = vacv.nv_resize_normalize_chw(src[i:i + 1], w, h, wo, ho, mean, std)
+        assert torch.equal(out[i], single[0])
+    flat = host(out[5])
+    for k in range(3):
+        want = np.float32((np.float32(128.0) - MEAN[k]).astype(np.float64) / (np.float64(STD[k]) + 1e-6))
+        assert np.all(flat[k] == want)
