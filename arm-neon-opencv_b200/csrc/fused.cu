@@ -17,6 +17,9 @@
 // carrying the horizontally interpolated row (3 ints) over when the next output row starts on it.
 // Stores: lanes = consecutive columns -> 128 B per warp per plane, streaming.
 #include "vacv_common.cuh"
+#include "fused_pipeline.cuh"
+#include <cmath>
+#include <vector>
 
 namespace vacv {
 
@@ -184,6 +187,80 @@ __global__ void __launch_bounds__(256) resize_normalize_kernel(const uint8_t* __
 
 using namespace vacv;
 
+// Host copy of linear_coord's source index (identical IEEE arithmetic on x86-64: no FMA, same rounding).
+static int host_linear_index(int d, double scale, int n_in) {
+    float fx = (float)(((double)d + 0.5) * scale - 0.5);
+    int sx = (int)floorf(fx);
+    if (sx < 0) sx = 0;
+    if (sx >= n_in - 1) sx = n_in - 2;
+    return sx;
+}
+
+template <bool kVFirst>
+static const void* pipe_kernel_for(int ncol) {
+    switch (ncol) {
+        case 1: return (const void*)nv_resize_normalize_chw_pipe_kernel<kVFirst, 1>;
+        case 2: return (const void*)nv_resize_normalize_chw_pipe_kernel<kVFirst, 2>;
+        case 3: return (const void*)nv_resize_normalize_chw_pipe_kernel<kVFirst, 3>;
+        default: return (const void*)nv_resize_normalize_chw_pipe_kernel<kVFirst, 4>;
+    }
+}
+
+// Returns 1 if the persistent TMA pipeline was launched, 0 if the shape does not qualify (caller falls back to the
+// tiled kernel), < 0 on error.
+static int try_launch_pipe(const uint8_t* src, float* dst, int batch, int w, int h, int v_first, int w_out, int h_out,
+                           const float* mean, const float* stddev, cudaStream_t s) {
+    if ((w % 16) != 0 || (((uintptr_t)src) & 15) != 0) return 0;             // bulk copies need 16-byte granularity
+    if (w_out > kPipeThreads * kPipeMaxCols || h_out > 8192) return 0;
+    // row source indices, exactly as the device computes them -> exact band sizes per tile
+    const double scale_y = (double)((float)h / (float)h_out);
+    std::vector<int> sy(h_out);
+    for (int d = 0; d < h_out; ++d) sy[d] = host_linear_index(d, scale_y, h);
+    const int table_bytes = (2 * h_out * (int)sizeof(int) + 127) & ~127;
+    const int static_bytes = 768 * 4 + 64;
+    PipeGeom g;
+    g.w = w; g.h = h; g.wo = w_out; g.ho = h_out; g.table_bytes = table_bytes;
+    int best_TH = 0;
+    size_t best_smem = 0;
+    for (int TH = 8; TH >= 1; --TH) {
+        int yrows = 0, crows = 0;
+        for (int d0 = 0; d0 < h_out; d0 += TH) {
+            const int d1 = std::min(d0 + TH, h_out) - 1;
+            const int y0 = sy[d0], y1 = sy[d1] + 1;
+            yrows = std::max(yrows, y1 - y0 + 1);
+            crows = std::max(crows, (y1 >> 1) - (y0 >> 1) + 1);
+        }
+        const size_t ystage = ((size_t)yrows * w + 127) & ~(size_t)127, cstage = ((size_t)crows * w + 127) & ~(size_t)127;
+        const size_t smem = table_bytes + 2 * (ystage + cstage);
+        if (smem + static_bytes <= 113 * 1024 || (TH == 1 && smem + static_bytes <= 226 * 1024)) {   // 2 CTAs / SM
+            best_TH = TH; best_smem = smem; g.ystage = (int)ystage; g.cstage = (int)cstage;
+            break;
+        }
+    }
+    if (!best_TH) return 0;
+    g.TH = best_TH;
+    g.tiles_per_frame = (h_out + best_TH - 1) / best_TH;
+    const long long total = (long long)g.tiles_per_frame * batch;
+    if (total > 0x7fffffffLL - 4096) return 0;
+    g.total_tiles = (int)total;
+    const int ncol = (w_out + kPipeThreads - 1) / kPipeThreads;
+    const int threads = std::min(kPipeThreads, ((w_out + ncol - 1) / ncol + 31) & ~31);
+    const void* kern = v_first ? pipe_kernel_for<true>(ncol) : pipe_kernel_for<false>(ncol);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)best_smem);
+    if (e != cudaSuccess) return set_error(VACV_ERR_CUDA, "nv_resize_normalize_chw: %s", cudaGetErrorString(e));
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, best_smem);
+    if (e != cudaSuccess || per_sm < 1) return 0;
+    int dev = 0, sms = kNumSMs;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = (int)std::min<long long>(total, (long long)sms * per_sm);
+    void* args[] = {(void*)&src, (void*)&dst, (void*)&g, (void*)&mean, (void*)&stddev};
+    e = cudaLaunchKernel(kern, dim3(grid), dim3(threads), args, best_smem, s);
+    if (e != cudaSuccess) return set_error(VACV_ERR_CUDA, "nv_resize_normalize_chw: %s", cudaGetErrorString(e));
+    return 1;
+}
+
 extern "C" int vacv_cuda_nv_resize_normalize_chw(const uint8_t* src, float* dst, int batch, int w, int h, int v_first,
                                                  int w_out, int h_out, const float* mean, const float* stddev, void* stream) {
     VACV_REQUIRE(src && dst && mean && stddev, "nv_resize_normalize_chw: null pointer");
@@ -192,6 +269,11 @@ extern "C" int vacv_cuda_nv_resize_normalize_chw(const uint8_t* src, float* dst,
     VACV_REQUIRE(batch <= 65535, "nv_resize_normalize_chw: batch <= 65535 per call");
     if (w_out == w && h_out == h)   // resize.cpp:58-61 memcpy shortcut == identity taps; not on the fused fast path
         return set_error(VACV_ERR_UNSUPPORTED, "nv_resize_normalize_chw: same-size resize (compose cvt_nv2bgr + normalize + layout_change)");
+    cudaStream_t s = as_stream(stream);
+    if (int rc = try_launch_pipe(src, dst, batch, w, h, v_first, w_out, h_out, mean, stddev, s)) {
+        if (rc < 0) return rc;
+        return check_launch("nv_resize_normalize_chw (persistent)");
+    }
     FusedGeom g;
     g.w = w; g.h = h; g.wo = w_out; g.ho = h_out;
     g.vec = (w % 16) == 0 && (((uintptr_t)src) & 15) == 0;
@@ -216,7 +298,6 @@ extern "C" int vacv_cuda_nv_resize_normalize_chw(const uint8_t* src, float* dst,
     int threads = 32 * max(1, min(10, (min(TW, w_out) + 63) / 64));   // ~2 columns per thread, <= 320
     const int tiles = ceil_div(w_out, TW) * ceil_div(h_out, TH);
     dim3 grid(tiles, batch);
-    cudaStream_t s = as_stream(stream);
     auto kern = v_first ? nv_resize_normalize_chw_kernel<true> : nv_resize_normalize_chw_kernel<false>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

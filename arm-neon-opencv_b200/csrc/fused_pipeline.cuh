@@ -1,0 +1,233 @@
+// Persistent, TMA-fed version of the config-2 fused pipeline (see fused.cu for the arithmetic contract).
+//
+//   grid  = 148 SMs x kCtasPerSm persistent CTAs; CTA c processes tiles c, c+grid, c+2*grid, ...
+//   tile  = TH full-width output rows of one frame.  Its source is one CONTIGUOUS byte range of the Y plane and
+//           one of the chroma plane (dense frames, full rows), so each is fetched by a single 1-D bulk copy
+//           (cp.async.bulk global->shared, completion on an mbarrier; SASS: UBLKCP) issued by one thread.
+//   pipe  = two shared-memory stages: the copy for tile i+1 is in flight while all warps compute tile i;
+//           a stage is handed back with one __syncthreads per tile.
+//   once per CTA (amortised over ~70 tiles): the exact 3x256 normalisation table, all h_out row coefficients
+//           (shared memory) and each thread's column coefficients (registers).
+//   inner loop: a thread owns NCOL output columns and walks down the tile rows.  Per source row it forms the
+//           horizontally interpolated BGR triple H = p_left*cx0 + p_right*cx1 from u8-clamped taps; chroma terms are
+//           cached per chroma row (two luma rows share one), H of the lower row is carried to the next output row
+//           when it starts there.  out = table[c][(H0*cy0 + H1*cy1) >> 22], stored 128 B / warp / plane, streaming.
+#pragma once
+#include "vacv_common.cuh"
+
+namespace vacv {
+
+constexpr int kPipeThreads = 384;    // max threads per CTA (2 CTAs / SM -> <= 85 registers per thread)
+constexpr int kPipeMaxCols = 4;      // output columns per thread -> w_out <= 1536
+
+struct PipeGeom {
+    int w, h, wo, ho;
+    int TH;                 // output rows per tile
+    int tiles_per_frame;    // ceil(ho / TH)
+    int total_tiles;        // tiles_per_frame * batch
+    int ystage, cstage;     // bytes reserved per stage for the Y / chroma band (multiples of 128)
+    int table_bytes;        // bytes of the two row tables at the start of dynamic shared memory (multiple of 128)
+};
+
+// ---- mbarrier / bulk-copy PTX (sm_90+; SASS on sm_100a: SYNCS.*, UBLKCP)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// ---- explicit shared-window accesses (32-bit addresses: no generic->shared conversion in the inner loop)
+__device__ __forceinline__ int lds_u8(uint32_t a) { int v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ unsigned lds_u16(uint32_t a) { unsigned v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ int lds_s32(uint32_t a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+
+struct ColState {
+    int yo;        // byte offset of the left tap inside a Y row
+    int ca, cb;    // byte offsets of the chroma pairs of the left / right tap inside a chroma row
+    int cx0, cx1;
+};
+
+template <bool kVFirst>
+__device__ __forceinline__ ChromaTerms terms_at(uint32_t addr) {
+    const unsigned p = lds_u16(addr);
+    return kVFirst ? chroma_terms(p & 0xff, p >> 8) : chroma_terms(p >> 8, p & 0xff);
+}
+
+template <bool kRightTap>
+__device__ __forceinline__ void hrow_cached(uint32_t yaddr, const ColState& c, const ChromaTerms& ta,
+                                            const ChromaTerms& tb, int (&H)[3]) {
+    const int Y0 = lds_u8(yaddr);
+    if (kRightTap) {
+        const int Y1 = lds_u8(yaddr + 1);
+        H[0] = clamp255(Y0 + ta.ba) * c.cx0 + clamp255(Y1 + tb.ba) * c.cx1;
+        H[1] = clamp255(Y0 - ta.ga) * c.cx0 + clamp255(Y1 - tb.ga) * c.cx1;
+        H[2] = clamp255(Y0 + ta.ra) * c.cx0 + clamp255(Y1 + tb.ra) * c.cx1;
+    } else {   // every cx1 of this launch is 0 (odd integer x ratio): the right tap contributes p*0
+        H[0] = clamp255(Y0 + ta.ba) * c.cx0;
+        H[1] = clamp255(Y0 - ta.ga) * c.cx0;
+        H[2] = clamp255(Y0 + ta.ra) * c.cx0;
+    }
+}
+
+// ybuf/cbuf/tab_sy/tab_cy/lut are shared-window addresses.  out[j] points at (frame, plane 0, row dy0, column of j).
+template <bool kVFirst, bool kRightTap, int NCOL>
+__device__ __forceinline__ void compute_tile(uint32_t ybuf, uint32_t cbuf, uint32_t tab_sy, uint32_t tab_cy, uint32_t lut,
+                                             const ColState (&col)[NCOL], int dy0, int th, int w,
+                                             char* (&out)[NCOL], size_t row_bytes, size_t plane_bytes) {
+    const int y_first = lds_s32(tab_sy + 4 * dy0), c_first = y_first >> 1;
+    int H0[NCOL][3], H1[NCOL][3];
+    ChromaTerms ta[NCOL], tb[NCOL];
+    int have = -2, have_c = -1;
+    auto row = [&](int r, int (&H)[NCOL][3]) {
+        const int cr = r >> 1;
+        if (cr != have_c) {   // all threads walk the same rows: no divergence
+            const uint32_t crow = cbuf + (cr - c_first) * w;
+#pragma unroll
+            for (int j = 0; j < NCOL; ++j) {
+                ta[j] = terms_at<kVFirst>(crow + col[j].ca);
+                if (kRightTap) tb[j] = terms_at<kVFirst>(crow + col[j].cb);
+            }
+            have_c = cr;
+        }
+        const uint32_t yrow = ybuf + (r - y_first) * w;
+#pragma unroll
+        for (int j = 0; j < NCOL; ++j) hrow_cached<kRightTap>(yrow + col[j].yo, col[j], ta[j], tb[j], H[j]);
+    };
+    for (int ty = 0; ty < th; ++ty) {
+        const int sy = lds_s32(tab_sy + 4 * (dy0 + ty));
+        const int cy = lds_s32(tab_cy + 4 * (dy0 + ty));
+        const int cy0 = cy & 0xffff, cy1 = cy >> 16;   // both in [0, 2048]
+        if (sy == have) {
+#pragma unroll
+            for (int j = 0; j < NCOL; ++j) { H0[j][0] = H1[j][0]; H0[j][1] = H1[j][1]; H0[j][2] = H1[j][2]; }
+        } else if (sy + 1 != have) {
+            row(sy, H0);
+        }
+        if (sy + 1 != have) {
+            row(sy + 1, H1);
+            have = sy + 1;
+        }
+#pragma unroll
+        for (int j = 0; j < NCOL; ++j) {
+            char* o = out[j];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const unsigned v = (unsigned)(H0[j][k] * cy0 + H1[j][k] * cy1) >> 22;   // the u8 the unfused chain stores
+                st_stream4f(o, lds_f32(lut + k * 1024 + v * 4));
+                o += plane_bytes;
+            }
+            out[j] += row_bytes;
+        }
+    }
+}
+
+template <bool kVFirst, int NCOL>
+__global__ void __launch_bounds__(kPipeThreads, 2)
+nv_resize_normalize_chw_pipe_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, PipeGeom g,
+                                    const float* __restrict__ mean, const float* __restrict__ stddev) {
+    extern __shared__ __align__(128) uint8_t dyn_smem[];     // [s_sy: ho][s_cy: ho][pad] 2 x (ystage + cstage)
+    __shared__ float lut[768];
+    int* s_sy = reinterpret_cast<int*>(dyn_smem);
+    int* s_cy = s_sy + g.ho;
+    uint8_t* stages = dyn_smem + g.table_bytes;
+    __shared__ __align__(8) uint64_t full_bar[2];
+    __shared__ int s_any_right;
+
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const size_t in_frame = (size_t)g.w * g.h * 3 / 2;
+    const size_t plane_bytes = (size_t)g.wo * g.ho * 4, row_bytes = (size_t)g.wo * 4;
+    const uint32_t stages_s = smem_u32(stages), sy_s = smem_u32(s_sy), cy_s = smem_u32(s_cy), lut_s = smem_u32(lut);
+
+    // ---- once per CTA: barriers, normalisation table, row and column coefficients
+    if (tid == 0) {
+        mbar_init(&full_bar[0], 1);
+        mbar_init(&full_bar[1], 1);
+        s_any_right = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int t = tid; t < 768; t += nthr)
+        lut[t] = normalize_one((float)(t & 255), __ldg(mean + (t >> 8)), (double)__ldg(stddev + (t >> 8)) + 1e-6);
+    const double scale_x = (double)((float)g.w / (float)g.wo), scale_y = (double)((float)g.h / (float)g.ho);
+    for (int dy = tid; dy < g.ho; dy += nthr) {
+        int s; float f;
+        linear_coord(dy, scale_y, g.h, s, f);
+        s_sy[dy] = s;
+        s_cy[dy] = sat_short((1.f - f) * 2048.f) | (sat_short(2048.f * f) << 16);
+    }
+    __syncthreads();
+    // Column ownership: thread t owns columns t, t+nthr, ...; a column index past the row end is clamped to the
+    // last column (the thread then recomputes and rewrites that pixel with the identical value: no branch needed).
+    ColState col[NCOL];
+    int colx[NCOL];
+    int any_right = 0;
+#pragma unroll
+    for (int j = 0; j < NCOL; ++j) {
+        const int dx = min(tid + j * nthr, g.wo - 1);
+        colx[j] = dx;
+        int sx; float fx;
+        linear_coord(dx, scale_x, g.w, sx, fx);
+        col[j].cx0 = sat_short((1.f - fx) * 2048.f);
+        col[j].cx1 = sat_short(2048.f * fx);
+        col[j].yo = sx;
+        col[j].ca = sx & ~1;
+        col[j].cb = (sx + 1) & ~1;
+        any_right |= col[j].cx1;
+    }
+    if (any_right) s_any_right = 1;   // benign race: all writers store 1
+
+    auto issue = [&](int tile, int b) {   // one thread
+        const int frame = tile / g.tiles_per_frame, dy0 = (tile - frame * g.tiles_per_frame) * g.TH;
+        const int th = min(g.TH, g.ho - dy0);
+        const int y_first = s_sy[dy0], y_last = s_sy[dy0 + th - 1] + 1;
+        const int c_first = y_first >> 1, c_last = y_last >> 1;
+        const uint32_t ybytes = (uint32_t)(y_last - y_first + 1) * g.w, cbytes = (uint32_t)(c_last - c_first + 1) * g.w;
+        const uint8_t* f = src + (size_t)frame * in_frame;
+        uint8_t* st = stages + (size_t)b * (g.ystage + g.cstage);
+        mbar_expect_tx(&full_bar[b], ybytes + cbytes);
+        bulk_g2s(st, f + (size_t)y_first * g.w, ybytes, &full_bar[b]);
+        bulk_g2s(st + g.ystage, f + (size_t)g.w * g.h + (size_t)c_first * g.w, cbytes, &full_bar[b]);
+    };
+
+    int tile = blockIdx.x;
+    if (tid == 0 && tile < g.total_tiles) issue(tile, 0);
+    __syncthreads();
+    const bool right = s_any_right != 0;
+
+    for (int it = 0; tile < g.total_tiles; tile += gridDim.x, ++it) {
+        const int b = it & 1;
+        const int next = tile + gridDim.x;
+        if (tid == 0 && next < g.total_tiles) issue(next, b ^ 1);   // stage b^1 was released by the sync below
+        mbar_wait(&full_bar[b], (it >> 1) & 1);
+        const int frame = tile / g.tiles_per_frame, dy0 = (tile - frame * g.tiles_per_frame) * g.TH;
+        const int th = min(g.TH, g.ho - dy0);
+        const uint32_t ybuf = stages_s + b * (g.ystage + g.cstage);
+        const uint32_t cbuf = ybuf + g.ystage;
+        char* out[NCOL];
+        char* const row0 = reinterpret_cast<char*>(dst + ((size_t)frame * 3 * g.ho + dy0) * g.wo);
+#pragma unroll
+        for (int j = 0; j < NCOL; ++j) out[j] = row0 + 4 * colx[j];
+        if (right) compute_tile<kVFirst, true, NCOL>(ybuf, cbuf, sy_s, cy_s, lut_s, col, dy0, th, g.w, out, row_bytes, plane_bytes);
+        else compute_tile<kVFirst, false, NCOL>(ybuf, cbuf, sy_s, cy_s, lut_s, col, dy0, th, g.w, out, row_bytes, plane_bytes);
+        __syncthreads();   // all reads of stage b done -> it may be refilled by the next iteration's issue
+    }
+}
+
+}  // namespace vacv

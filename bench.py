@@ -273,7 +273,7 @@ def run_ours(args, rank, world, local_rank):
                    "timing": "CUDA events on the launching stream, max over ranks"},
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
-                     "kernel": "nv_resize_normalize_chw_kernel", "algorithmic_bytes_per_launch": BATCH * ALGO_BYTES_PER_FRAME,
+                     "kernel": "nv_resize_normalize_chw_pipe_kernel", "algorithmic_bytes_per_launch": BATCH * ALGO_BYTES_PER_FRAME,
                      "avg_launch_ms": round(own_ms, 4)},
         "e2e": {"value": round(e2e_value, 1), "unit": "Mpix/s", "h2d_bytes_per_step": BATCH * IN_FRAME,
                 "d2h_bytes_per_step": BATCH * OUT_FRAME, "steps": e2e_steps,
