@@ -40,6 +40,18 @@ _SIGS = {
     "vacv_cuda_nv_resize_normalize_chw": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp],
     "vacv_cuda_resize_normalize": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp],
     "vacv_cuda_warp_affine_normalize": [_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _vp],
+    "vacv_cuda_device_count": [_vp],
+    "vacv_cuda_set_device": [_i],
+    "vacv_cuda_malloc": [_vp, _sz],
+    "vacv_cuda_free": [_vp],
+    "vacv_cuda_host_alloc": [_vp, _sz],
+    "vacv_cuda_host_free": [_vp],
+    "vacv_cuda_memcpy_h2d": [_vp, _vp, _sz, _vp],
+    "vacv_cuda_memcpy_d2h": [_vp, _vp, _sz, _vp],
+    "vacv_cuda_memset": [_vp, _i, _sz, _vp],
+    "vacv_cuda_stream_create": [_vp],
+    "vacv_cuda_stream_destroy": [_vp],
+    "vacv_cuda_stream_sync": [_vp],
     "vacv_invert_affine": [_vp],
     "vacv_rotation_matrix": [_f, _f, _vp, _vp],
 }

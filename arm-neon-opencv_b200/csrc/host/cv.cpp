@@ -1,0 +1,213 @@
+// va_cv::* for libvacv.so: the reference's public operator API (src/cv/cv.cpp:16-89) bound to the CUDA C-ABI.
+//
+// The reference routes each call through a class-static dispatcher that picks a backend at compile time
+// (e.g. Resize::resize -> resize_naive, src/cv/resize.cpp:19-27) and then does shape bookkeeping +
+// dst.create(...) before calling a raw-pointer kernel.  This file is that dispatcher layer with the CUDA backend:
+// same bookkeeping, then  host tensor -> device scratch -> vacv_cuda_* -> host tensor, synchronously.
+#include "cv/cv.h"
+
+#include <cstring>
+#include <stdexcept>
+#include <string>
+
+#include "device_context.h"
+#include "vacv_cuda.h"
+
+namespace va_cv {
+
+using vision::Tensor;
+using vacv_host::DeviceContext;
+
+namespace {
+
+[[noreturn]] void unsupported(const std::string& what) {
+    throw std::runtime_error("vacv: " + what + " has no native implementation (neither in the reference nor here)");
+}
+
+// mean / stddev tensors as the reference expects them: c fp32 values (normalize.cpp:109-112)
+void require_stats(const Tensor& mean, const Tensor& stddev, int c) {
+    if (mean.empty() || stddev.empty() || static_cast<int>(mean.size()) != c || static_cast<int>(stddev.size()) != c ||
+        mean.dtype != vision::FP32 || stddev.dtype != vision::FP32)
+        throw std::runtime_error("vacv: mean / stddev must be FP32 tensors with one value per channel");
+}
+
+// uploads mean|stddev into one scratch slot; returns device pointers
+void upload_stats(DeviceContext& ctx, int slot, const Tensor& mean, const Tensor& stddev, int c, float*& d_mean, float*& d_std) {
+    float tmp[2 * 16];
+    if (c > 16) throw std::runtime_error("vacv: more than 16 channels");
+    std::memcpy(tmp, mean.data, sizeof(float) * c);
+    std::memcpy(tmp + c, stddev.data, sizeof(float) * c);
+    d_mean = static_cast<float*>(ctx.upload(slot, tmp, sizeof(float) * 2 * c));
+    ctx.sync();   // tmp is a stack buffer
+    d_std = d_mean + c;
+}
+
+void build_matrix(float scale, float rot, const VScalar& aux, float m[6]) {
+    const double a[4] = {aux.v0, aux.v1, aux.v2, aux.v3};
+    vacv_rotation_matrix(scale, rot, a, m);   // warp_affine.cpp:76-109
+}
+
+void check_warp_mode(const Tensor& src, int flags, int borderMode) {
+    if ((src.dtype != vision::INT8 && src.dtype != vision::FP32) || borderMode != BORDER_CONSTANT || flags != INTER_LINEAR)
+        unsupported("warp_affine with this dtype / border mode / interpolation (warp_affine.cpp:114-119)");
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------- resize
+void resize(const Tensor& src, Tensor& dst, VSize dsize, double /*fx*/, double /*fy*/, int interpolation) {
+    if (src.empty()) throw std::runtime_error("vacv: resize of an empty tensor");
+    if (interpolation != INTER_LINEAR && interpolation != INTER_CUBIC) unsupported("resize with this interpolation");
+    if (src.dtype != vision::INT8 && src.dtype != vision::FP32) unsupported("resize of this dtype");
+    const Tensor in = src;   // keep the source alive if dst aliases it
+    dst.create(dsize.w, dsize.h, in.c, in.dtype, in.layout);   // resize.cpp:56
+    DeviceContext& ctx = DeviceContext::current();
+    void* d_in = ctx.upload(0, in.data, in.len());
+    void* d_out = ctx.scratch(1, dst.len());
+    ctx.check(vacv_cuda_resize(d_in, d_out, 1, in.w, in.h, in.c, in.dtype, in.layout, dsize.w, dsize.h, interpolation,
+                               VACV_FLAG_NONE, ctx.stream()));
+    ctx.download(dst.data, d_out, dst.len());
+}
+
+// ---------------------------------------------------------------------------------------------------- cvt_color
+void cvt_color(const Tensor& src, Tensor& dst, int code) {
+    if (code != COLOR_YUV2BGR_NV21 && code != COLOR_YUV2BGR_NV12) unsupported("cvt_color with this code (cvt_color.cpp:139-141)");
+    if (src.empty() || src.dtype != vision::INT8) throw std::runtime_error("vacv: cvt_color needs an INT8 NV21/NV12 tensor");
+    const Tensor in = src;
+    const int w = in.w, h = in.h / 3 * 2;   // cvt_color.cpp:151-152
+    dst.create(w, h, 3, vision::NHWC, vision::INT8);
+    DeviceContext& ctx = DeviceContext::current();
+    void* d_in = ctx.upload(0, in.data, (size_t)w * h * 3 / 2);
+    void* d_out = ctx.scratch(1, dst.len());
+    // the reference decodes both codes with V-first chroma (the swap at :146 tests the wrong enum), kept for parity
+    ctx.check(vacv_cuda_cvt_nv2bgr(static_cast<const uint8_t*>(d_in), static_cast<uint8_t*>(d_out), 1, w, h, 1, ctx.stream()));
+    ctx.download(dst.data, d_out, dst.len());
+}
+
+// ---------------------------------------------------------------------------------------------------- normalize
+void normalize(const Tensor& src, Tensor& dst, const Tensor& mean, const Tensor& stddev) {
+    if (src.empty()) throw std::runtime_error("vacv: normalize of an empty tensor");
+    if (src.dtype != vision::INT8 && src.dtype != vision::FP32) unsupported("normalize of this dtype");
+    const Tensor in = src;
+    dst.create(in.w, in.h, in.c, vision::FP32, in.layout);   // normalize.cpp:90
+    DeviceContext& ctx = DeviceContext::current();
+    void* d_in = ctx.upload(0, in.data, in.len());
+    float* d_out = static_cast<float*>(ctx.scratch(1, dst.len()));
+    float *d_mean, *d_std;
+    if (mean.empty() && stddev.empty()) {   // normalize.cpp:98: statistics of the image itself
+        if (in.dtype != vision::INT8)
+            unsupported("automatic statistics of an FP32 tensor (exact integer sums are defined on u8 pixels)");
+        auto* d_sums = static_cast<unsigned long long*>(ctx.scratch(2, sizeof(unsigned long long) * 2 * in.c));
+        d_mean = static_cast<float*>(ctx.scratch(3, sizeof(float) * 2 * in.c));
+        d_std = d_mean + in.c;
+        ctx.check(vacv_cuda_memset(d_sums, 0, sizeof(unsigned long long) * 2 * in.c, ctx.stream()));
+        ctx.check(vacv_cuda_sums_u8(static_cast<const uint8_t*>(d_in), 1, in.w, in.h, in.c, in.layout, d_sums, 0, ctx.stream()));
+        ctx.check(vacv_cuda_finalize_mean_stddev(d_sums, 1, in.c, (unsigned long long)in.w * in.h, d_mean, d_std, ctx.stream()));
+    } else {
+        require_stats(mean, stddev, in.c);
+        upload_stats(ctx, 3, mean, stddev, in.c, d_mean, d_std);
+    }
+    ctx.check(vacv_cuda_normalize(d_in, d_out, 1, in.w, in.h, in.c, in.dtype, in.layout, d_mean, d_std, 0, ctx.stream()));
+    ctx.download(dst.data, d_out, dst.len());
+}
+
+// ---------------------------------------------------------------------------------------------------- warp_affine
+void warp_affine(const Tensor& src, Tensor& dst, const Tensor& M, VSize dsize, int flags, int borderMode,
+                 const VScalar& /*borderValue*/) {
+    if (src.empty() || M.empty() || M.size() < 6 || M.dtype != vision::FP32)
+        throw std::runtime_error("vacv: warp_affine needs a source and a 2x3 FP32 matrix");
+    check_warp_mode(src, flags, borderMode);
+    float* m = static_cast<float*>(M.data);
+    vacv_invert_affine(m);   // in place in the caller's tensor, like warp_affine.cpp:121-133
+    const Tensor in = src;
+    dst.create(dsize.w, dsize.h, in.c, in.dtype, in.layout);
+    DeviceContext& ctx = DeviceContext::current();
+    void* d_in = ctx.upload(0, in.data, in.len());
+    void* d_out = ctx.scratch(1, dst.len());
+    float* d_m = static_cast<float*>(ctx.upload(2, m, sizeof(float) * 6));
+    ctx.check(vacv_cuda_warp_affine(d_in, 1, in.w, in.h, in.c, in.dtype, in.layout, nullptr, d_m, 1, d_out, dsize.w, dsize.h,
+                                    VACV_FLAG_NONE, ctx.stream()));
+    ctx.download(dst.data, d_out, dst.len());
+}
+
+void warp_affine(const Tensor& src, Tensor& dst, float scale, float rot, VSize dsize, const VScalar& aux_param, int flags,
+                 int borderMode, const VScalar& borderValue) {
+    Tensor M(3, 2, 1, vision::FP32, vision::NCHW);
+    build_matrix(scale, rot, aux_param, static_cast<float*>(M.data));
+    warp_affine(src, dst, M, dsize, flags, borderMode, borderValue);
+}
+
+// ---------------------------------------------------------------------------------------------------- fused ops
+void resize_normalize(const Tensor& src, Tensor& dst, VSize dsize, double /*fx*/, double /*fy*/, int interpolation,
+                      const Tensor& mean, const Tensor& stddev) {
+    if (src.empty() || src.dtype != vision::INT8 || src.layout != vision::NHWC || interpolation != INTER_LINEAR)
+        unsupported("resize_normalize other than INTER_LINEAR on a u8 HWC tensor");
+    require_stats(mean, stddev, src.c);
+    const Tensor in = src;
+    dst.create(dsize.w, dsize.h, in.c, vision::FP32, vision::NHWC);
+    DeviceContext& ctx = DeviceContext::current();
+    void* d_in = ctx.upload(0, in.data, in.len());
+    float* d_out = static_cast<float*>(ctx.scratch(1, dst.len()));
+    float *d_mean, *d_std;
+    upload_stats(ctx, 3, mean, stddev, in.c, d_mean, d_std);
+    if (dsize.w == in.w && dsize.h == in.h)   // resize.cpp:58-61: plain copy, so only the normalisation remains
+        ctx.check(vacv_cuda_normalize(d_in, d_out, 1, in.w, in.h, in.c, vision::INT8, vision::NHWC, d_mean, d_std, 0, ctx.stream()));
+    else
+        ctx.check(vacv_cuda_resize_normalize(static_cast<const uint8_t*>(d_in), d_out, 1, in.w, in.h, in.c, dsize.w, dsize.h,
+                                             d_mean, d_std, VACV_NHWC, ctx.stream()));
+    ctx.download(dst.data, d_out, dst.len());
+}
+
+void warp_affine_normalize(const Tensor& src, Tensor& dst, const Tensor& M, VSize dsize, int flags, int borderMode,
+                           const VScalar& /*borderValue*/, const Tensor& mean, const Tensor& stddev) {
+    if (src.empty() || M.empty() || M.size() < 6 || M.dtype != vision::FP32)
+        throw std::runtime_error("vacv: warp_affine_normalize needs a source and a 2x3 FP32 matrix");
+    if (src.dtype != vision::INT8 || src.layout != vision::NHWC || borderMode != BORDER_CONSTANT || flags != INTER_LINEAR)
+        unsupported("warp_affine_normalize other than INTER_LINEAR / BORDER_CONSTANT on a u8 HWC tensor");
+    require_stats(mean, stddev, src.c);
+    float* m = static_cast<float*>(M.data);
+    vacv_invert_affine(m);
+    const Tensor in = src;
+    dst.create(dsize.w, dsize.h, in.c, vision::FP32, vision::NHWC);
+    DeviceContext& ctx = DeviceContext::current();
+    void* d_in = ctx.upload(0, in.data, in.len());
+    float* d_out = static_cast<float*>(ctx.scratch(1, dst.len()));
+    float* d_m = static_cast<float*>(ctx.upload(2, m, sizeof(float) * 6));
+    float *d_mean, *d_std;
+    upload_stats(ctx, 3, mean, stddev, in.c, d_mean, d_std);
+    ctx.check(vacv_cuda_warp_affine_normalize(static_cast<const uint8_t*>(d_in), 1, in.w, in.h, in.c, nullptr, d_m, 1, d_out,
+                                              dsize.w, dsize.h, d_mean, d_std, VACV_NHWC, ctx.stream()));
+    ctx.download(dst.data, d_out, dst.len());
+}
+
+void warp_affine_normalize(const Tensor& src, Tensor& dst, float scale, float rot, VSize dsize, const VScalar& aux_param,
+                           int flags, int borderMode, const VScalar& borderValue, const Tensor& mean, const Tensor& stddev) {
+    Tensor M(3, 2, 1, vision::FP32, vision::NCHW);
+    build_matrix(scale, rot, aux_param, static_cast<float*>(M.data));
+    warp_affine_normalize(src, dst, M, dsize, flags, borderMode, borderValue, mean, stddev);
+}
+
+// ---------------------------------------------------------------------------------------------------- crop
+void crop(const Tensor& src, Tensor& dst, const vision::VRect& rect) {
+    if (src.empty()) throw std::runtime_error("vacv: crop of an empty tensor");
+    if (src.dtype != vision::INT8 && src.dtype != vision::FP32) unsupported("crop of this dtype (crop.cpp:133-141)");
+    const int left = static_cast<int>(rect.left), top = static_cast<int>(rect.top);           // crop.cpp:128-131
+    const int cw = static_cast<int>(rect.width()), ch = static_cast<int>(rect.height());
+    const Tensor in = src;
+    if (cw <= 0 || ch <= 0 || left < 0 || top < 0 || left + cw > in.w || top + ch > in.h)
+        throw std::runtime_error("vacv: crop rectangle outside the source (the reference would read out of bounds)");
+    dst.create(cw, ch, in.c, in.dtype, in.layout);
+    DeviceContext& ctx = DeviceContext::current();
+    void* d_in = ctx.upload(0, in.data, in.len());
+    void* d_out = ctx.scratch(1, dst.len());
+    ctx.check(vacv_cuda_crop(d_in, d_out, 1, in.w, in.h, in.c, in.dtype, in.layout, left, top, cw, ch, ctx.stream()));
+    ctx.download(dst.data, d_out, dst.len());
+}
+
+// ---------------------------------------------------------------------------------------------------- not on the path
+// Without USE_OPENCV the reference's bodies are empty (match_template.cpp:48-60, imencode.cpp:11-15).
+void match_template(const Tensor&, const Tensor&, Tensor&, int) {}
+void minMaxIdx(const Tensor&, double*, double*, int*, int*, const Tensor&) {}
+void imencode(const Tensor&, std::vector<unsigned char>&, const char*) {}
+
+}  // namespace va_cv

@@ -61,3 +61,43 @@ extern "C" void vacv_rotation_matrix(float scale, float rot_deg, const double* a
     m[2] = (float)(aux[2] - m[0] * aux[0] - m[1] * aux[1]);
     m[5] = (float)(aux[3] - m[3] * aux[0] - m[4] * aux[1]);
 }
+
+// ---- runtime helpers (the host layer's only door to CUDA) -------------------------------------------------------
+#define VACV_RT(call, what)                                                              \
+    do {                                                                                 \
+        cudaError_t e_ = (call);                                                         \
+        if (e_ != cudaSuccess) return vacv::set_error(VACV_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e_)); \
+        return VACV_OK;                                                                  \
+    } while (0)
+
+extern "C" int vacv_cuda_device_count(int* count) {
+    VACV_REQUIRE(count, "device_count: null pointer");
+    *count = 0;
+    VACV_RT(cudaGetDeviceCount(count), "device_count");
+}
+extern "C" int vacv_cuda_set_device(int device) { VACV_RT(cudaSetDevice(device), "set_device"); }
+extern "C" int vacv_cuda_malloc(void** dptr, size_t bytes) {
+    VACV_REQUIRE(dptr, "malloc: null pointer");
+    VACV_RT(cudaMalloc(dptr, bytes), "malloc");
+}
+extern "C" int vacv_cuda_free(void* dptr) { VACV_RT(cudaFree(dptr), "free"); }
+extern "C" int vacv_cuda_host_alloc(void** h_ptr, size_t bytes) {
+    VACV_REQUIRE(h_ptr, "host_alloc: null pointer");
+    VACV_RT(cudaHostAlloc(h_ptr, bytes, cudaHostAllocDefault), "host_alloc");
+}
+extern "C" int vacv_cuda_host_free(void* h_ptr) { VACV_RT(cudaFreeHost(h_ptr), "host_free"); }
+extern "C" int vacv_cuda_memcpy_h2d(void* dptr, const void* h_ptr, size_t bytes, void* stream) {
+    VACV_RT(cudaMemcpyAsync(dptr, h_ptr, bytes, cudaMemcpyHostToDevice, vacv::as_stream(stream)), "memcpy_h2d");
+}
+extern "C" int vacv_cuda_memcpy_d2h(void* h_ptr, const void* dptr, size_t bytes, void* stream) {
+    VACV_RT(cudaMemcpyAsync(h_ptr, dptr, bytes, cudaMemcpyDeviceToHost, vacv::as_stream(stream)), "memcpy_d2h");
+}
+extern "C" int vacv_cuda_memset(void* dptr, int value, size_t bytes, void* stream) {
+    VACV_RT(cudaMemsetAsync(dptr, value, bytes, vacv::as_stream(stream)), "memset");
+}
+extern "C" int vacv_cuda_stream_create(void** stream) {
+    VACV_REQUIRE(stream, "stream_create: null pointer");
+    VACV_RT(cudaStreamCreateWithFlags(reinterpret_cast<cudaStream_t*>(stream), cudaStreamNonBlocking), "stream_create");
+}
+extern "C" int vacv_cuda_stream_destroy(void* stream) { VACV_RT(cudaStreamDestroy(vacv::as_stream(stream)), "stream_destroy"); }
+extern "C" int vacv_cuda_stream_sync(void* stream) { VACV_RT(cudaStreamSynchronize(vacv::as_stream(stream)), "stream_sync"); }

@@ -12,7 +12,8 @@
  *     vacv_status otherwise; vacv_cuda_last_error() gives the message (thread-local).
  *   - all data pointers are DEVICE pointers unless the parameter name starts with `h_`.
  *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  All launches are asynchronous
- *     and stream-ordered; nothing here synchronises or allocates.
+ *     and stream-ordered; the operator entry points never synchronise or allocate (only the runtime
+ *     helpers at the end of this header do).
  *   - tensors are dense, no row pitch, exactly like vision::Tensor (src/common/tensor.cpp:524);
  *     a batch is `batch` frames back to back.
  *   - dtype / layout codes are the reference's: vision::DType (tensor.h:12-18), vision::DLayout (:21-24).
@@ -126,6 +127,23 @@ VACV_API int vacv_cuda_warp_affine_normalize(const uint8_t* frames, int n_frames
                                              const int* frame_idx, const float* minv, int n_crops,
                                              float* dst, int w_out, int h_out, const float* mean, const float* stddev,
                                              int out_layout, void* stream);
+
+/* ---- runtime helpers: the host layer (libvacv.so) reaches CUDA only through this C-ABI -----------
+ * Thin wrappers over the CUDA runtime so that C/C++ host code needs no CUDA headers: device memory, pinned staging
+ * memory (the reference's USE_CUDA allocator, src/common/va_cuda_allocator.cu:8-34, made checkable), copies,
+ * streams.  Copies are asynchronous on `stream`; vacv_cuda_stream_sync waits. */
+VACV_API int vacv_cuda_device_count(int* count);
+VACV_API int vacv_cuda_set_device(int device);
+VACV_API int vacv_cuda_malloc(void** dptr, size_t bytes);
+VACV_API int vacv_cuda_free(void* dptr);
+VACV_API int vacv_cuda_host_alloc(void** h_ptr, size_t bytes);      /* pinned */
+VACV_API int vacv_cuda_host_free(void* h_ptr);
+VACV_API int vacv_cuda_memcpy_h2d(void* dptr, const void* h_ptr, size_t bytes, void* stream);
+VACV_API int vacv_cuda_memcpy_d2h(void* h_ptr, const void* dptr, size_t bytes, void* stream);
+VACV_API int vacv_cuda_memset(void* dptr, int value, size_t bytes, void* stream);
+VACV_API int vacv_cuda_stream_create(void** stream);
+VACV_API int vacv_cuda_stream_destroy(void* stream);
+VACV_API int vacv_cuda_stream_sync(void* stream);
 
 #ifdef __cplusplus
 }

@@ -431,3 +431,15 @@ def test_full_size_config2_properties(vacv):
     for k in range(3):
         want = np.float32((np.float32(128.0) - MEAN[k]).astype(np.float64) / (np.float64(STD[k]) + 1e-6))
         assert np.all(flat[k] == want)
+
+
+# ------------------------------------------------------------------ the C++ drop-in (libvacv.so) end to end
+def test_cpp_dropin_binary(vacv):
+    """tests/cpp/test_dropin: a reference-style C++ caller linked against libvacv.so, checked against the oracle."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpp", "test_dropin")
+    assert os.path.exists(exe), "run __graft_entry__.build() first"
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    print(r.stdout)
+    assert r.returncode == 0, r.stdout + r.stderr
