@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libvacv_cuda.so")
 FP32, FP16, INT8, FP64 = 0, 1, 2, 3
 NCHW, NHWC = 0, 1
 INTER_LINEAR, INTER_CUBIC = 1, 2
-FLAG_NONE, FLAG_NEON_RULE, FLAG_SIGNED_CHAR = 0, 1, 2
+FLAG_NONE, FLAG_NEON_RULE, FLAG_SIGNED_CHAR, FLAG_DIRECT_GATHER, FLAG_TILED = 0, 1, 2, 0x100, 0x200
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(f"{LIB_PATH} not built -- run `python -c 'import __graft_entry__ as g; g.build()'` "

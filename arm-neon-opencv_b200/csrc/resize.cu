@@ -6,6 +6,7 @@
 // pixels of one image; x-coefficients are computed once per column and y-coefficients once per row of the tile
 // into shared memory, then each thread gathers its taps through the read-only path.
 #include "vacv_common.cuh"
+#include "resize_coeffs.cuh"
 
 namespace vacv {
 
@@ -92,25 +93,6 @@ __global__ void __launch_bounds__(kTileX * kTileY) resize_linear_f32_kernel(cons
 }
 
 // ----------------------------------------------------------------------------------------------------
-// a8 bicubic fp32 (resize_naive.cpp:130-185 coefficients with border folding; :230,:345 accumulation order)
-__device__ __forceinline__ void cubic_naive(int d, int n_in, int n_out, int& ofs, float (&a)[4]) {
-    const double scale = (double)n_in / (double)n_out;
-    float fx = (float)(((double)d + 0.5) * scale - 0.5);
-    int sx = (int)floorf(fx);
-    fx -= (float)sx;
-    const float A = -0.75f;
-    const float fx0 = fx + 1, fx1 = fx, fx2 = 1 - fx;
-    a[0] = A * fx0 * fx0 * fx0 - 5 * A * fx0 * fx0 + 8 * A * fx0 - 4 * A;
-    a[1] = (A + 2) * fx1 * fx1 * fx1 - (A + 3) * fx1 * fx1 + 1;
-    a[2] = (A + 2) * fx2 * fx2 * fx2 - (A + 3) * fx2 * fx2 + 1;
-    a[3] = 1.f - a[0] - a[1] - a[2];
-    if (sx <= -1) { sx = 1; a[0] = 1.f - a[3]; a[1] = a[3]; a[2] = 0.f; a[3] = 0.f; }
-    if (sx == 0) { sx = 1; a[0] = a[0] + a[1]; a[1] = a[2]; a[2] = a[3]; a[3] = 0.f; }
-    if (sx == n_in - 2) { sx = n_in - 3; a[3] = a[2] + a[3]; a[2] = a[1]; a[1] = a[0]; a[0] = 0.f; }
-    if (sx >= n_in - 1) { sx = n_in - 3; a[3] = 1.f - a[0]; a[2] = a[0]; a[1] = 0.f; a[0] = 0.f; }
-    ofs = sx;
-}
-
 __global__ void __launch_bounds__(kTileX * kTileY) resize_cubic_f32_kernel(const float* __restrict__ src,
                                                                             float* __restrict__ dst, ResizeGeom g) {
     __shared__ int s_sx[kTileX], s_sy[kTileY];
@@ -146,18 +128,6 @@ __global__ void __launch_bounds__(kTileX * kTileY) resize_cubic_f32_kernel(const
 }
 
 // ----------------------------------------------------------------------------------------------------
-// a9 bicubic u8 = OpenCV 2.4.13 cv::resize(CV_8UCn, INTER_CUBIC): int32 horizontal pass with
-// 11-bit coefficients (round-half-even), fp32 vertical pass with round-half-even for the first (W*cn & ~7)
-// elements of a row (the SSE2 body) and an integer (+2^21)>>22 vertical pass for the <=7 tail elements.
-__device__ __forceinline__ void cubic_cv(float x, float (&k)[4]) {
-    const float A = -0.75f;
-    k[0] = ((A * (x + 1) - 5 * A) * (x + 1) + 8 * A) * (x + 1) - 4 * A;
-    k[1] = ((A + 2) * x - (A + 3)) * x * x + 1;
-    k[2] = ((A + 2) * (1 - x) - (A + 3)) * (1 - x) * (1 - x) + 1;
-    k[3] = 1.f - k[0] - k[1] - k[2];
-}
-__device__ __forceinline__ int sat_short_rhe(float v) { return max(min(__float2int_rn(v), 32767), -32768); }
-
 __global__ void __launch_bounds__(kTileX * kTileY) resize_cubic_u8_cv24_kernel(const uint8_t* __restrict__ src,
                                                                                 uint8_t* __restrict__ dst, ResizeGeom g) {
     __shared__ int s_sx[kTileX], s_sy[kTileY];
@@ -225,6 +195,9 @@ __global__ void __launch_bounds__(kTileX * kTileY) resize_cubic_u8_cv24_kernel(c
 
 }  // namespace vacv
 
+namespace vacv {
+int try_launch_resize_tiled(int kind, const void* src, void* dst, int images, int w, int h, int c, int wo, int ho, cudaStream_t s);
+}
 using namespace vacv;
 
 extern "C" int vacv_cuda_resize(const void* src, void* dst, int batch, int w, int h, int c, int dtype, int layout,
@@ -253,6 +226,17 @@ extern "C" int vacv_cuda_resize(const void* src, void* dst, int batch, int w, in
     else { g.c = 1; images = batch * c; }   // resize.cpp:73-87: per-plane calls with c = 1
     g.src_image = (size_t)w * h * g.c;
     g.dst_image = (size_t)w_out * h_out * g.c;
+    {   // shared-memory tiled kernels (resize_tiled.cu); kinds: 0 u8 linear, 1 signed-char, 2 NEON rule, 3 f32 linear, 4 f32 cubic, 5 u8 cubic
+        const int kind = cubic ? (dtype == VACV_FP32 ? 4 : 5)
+                               : (dtype == VACV_FP32 ? 3 : (flags & VACV_FLAG_NEON_RULE) ? 2 : (flags & VACV_FLAG_SIGNED_CHAR) ? 1 : 0);
+        // measured on B200: staging pays for the 16-tap bicubic kernels, not (yet) for the 4-tap bilinear ones
+        const bool tiled = (flags & VACV_FLAG_TILED) || (cubic && !(flags & VACV_FLAG_DIRECT_GATHER));
+        if (tiled) {
+            const int rc = try_launch_resize_tiled(kind, src, dst, images, w, h, g.c, w_out, h_out, s);
+            if (rc < 0) return rc;
+            if (rc > 0) return check_launch("resize (tiled)");
+        }
+    }
     dim3 block(kTileX, kTileY);
     for (int i0 = 0; i0 < images; i0 += 65535) {
         const int ni = min(images - i0, 65535);

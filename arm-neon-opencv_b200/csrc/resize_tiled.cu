@@ -1,0 +1,321 @@
+// Tiled resize kernels (a5-a9): the source window of an output tile is staged ONCE in shared memory with coalesced
+// 128-bit loads, every tap is then a shared-memory read, and the output tile leaves through shared memory as
+// lane-contiguous 128-bit stores.  Replaces the byte-granular global gathers of the direct kernels in resize.cu
+// (kept as fallback), which were LSU-bound (ncu: c4 u8 cubic at 7 % of the HBM roofline).
+//
+//   tile          TH output rows x up to 256 output ELEMENTS (pixels x channels) of one image; thread t owns element
+//                 column t of the tile and walks down the rows, so its x taps/coefficients live in registers.
+//   source rows   only the rows some tap of the tile touches are staged (row -> slot table), so large vertical
+//                 down-scales do not fetch unused rows.
+//   bilinear      (u8 naive rule / NEON rule / signed-char compat, fp32): the reference's 4-tap expression evaluated
+//                 directly on the staged taps (bit-exact operation order).
+//   bicubic       separable like the reference (resize_naive.cpp:187-366) and like OpenCV 2.4: pass 1 forms the
+//                 horizontal sums H[slot][element] in shared memory (each source row once per tile instead of once
+//                 per output row: 2.5x fewer MACs at 4:3), pass 2 combines 4 slots vertically.
+//                 u8: H is an exact integer carried as fp32 (|H| < 2^22), vertical pass = OpenCV's fp32 SSE2 body
+//                 with round-half-even, or its integer tail for the last <= 7 elements of an output row.
+#include <algorithm>
+
+#include "resize_coeffs.cuh"
+#include "vacv_common.cuh"
+
+namespace vacv {
+
+enum { kLinU8 = 0, kLinU8Signed = 1, kLinU8Neon = 2, kLinF32 = 3, kCubF32 = 4, kCubU8 = 5 };
+
+constexpr int kRtThreads = 256;
+constexpr int kRtMaxTH = 16;
+constexpr int kRtMaxBand = 96;   // source rows spanned by one tile (host picks TH accordingly)
+
+struct TiledGeom {
+    int w, h, c, wo, ho;
+    int TWE, TH;              // tile: elements (multiple of c, <= 256) x rows
+    int hpitch;               // floats per row of the horizontal-sum buffer (TWE rounded up to 4)
+    int tiles_x, tiles_y;
+    int src_pitch;            // shared-memory bytes per staged source row (multiple of 16)
+    int max_slots;            // staged row capacity
+    int opitch;               // shared-memory bytes per output row (multiple of 16, >= TWE*es + 16)
+    int align;                // staging granularity in bytes: 16, 4 or 1
+    size_t src_image, dst_image;   // elements between images
+};
+
+template <int KIND> struct Kind {
+    using S = uint8_t;
+    static constexpr int TAPS = 2;
+};
+template <> struct Kind<kLinF32> { using S = float; static constexpr int TAPS = 2; };
+template <> struct Kind<kCubF32> { using S = float; static constexpr int TAPS = 4; };
+template <> struct Kind<kCubU8> { using S = uint8_t; static constexpr int TAPS = 4; };
+
+// Tap indices (absolute, along one axis) and coefficients (int, or float bits) of output coordinate d.
+template <int KIND>
+__device__ __forceinline__ void axis_coefs(int d, int n_in, int n_out, bool is_x, int (&idx)[Kind<KIND>::TAPS],
+                                           int (&coef)[Kind<KIND>::TAPS]) {
+    if constexpr (KIND == kLinU8 || KIND == kLinU8Signed || KIND == kLinU8Neon || KIND == kLinF32) {
+        // naive: fp32 scale (resize_naive.cpp:17-18); NEON rule: fp64 scale (resize_neon.cpp:17-18)
+        const double scale = KIND == kLinU8Neon ? (double)n_in / (double)n_out : (double)((float)n_in / (float)n_out);
+        int s; float f;
+        linear_coord(d, scale, n_in, s, f);
+        idx[0] = s; idx[1] = s + 1;
+        if constexpr (KIND == kLinF32) { coef[0] = __float_as_int(1.f - f); coef[1] = __float_as_int(f); }
+        else { coef[0] = sat_short((1.f - f) * 2048.f); coef[1] = sat_short(f * 2048.f); }
+    } else if constexpr (KIND == kCubF32) {
+        int ofs; float a[4];
+        cubic_naive(d, n_in, n_out, ofs, a);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { idx[j] = ofs - 1 + j; coef[j] = __float_as_int(a[j]); }
+    } else {
+        int s, q[4];
+        cubic_cv_coord(d, n_in, n_out, is_x, s, q);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { idx[j] = min(max(s - 1 + j, 0), n_in - 1); coef[j] = q[j]; }
+    }
+}
+
+__device__ __forceinline__ float int_to_float_exact(int v) {   // |v| < 2^22: two ALU ops instead of an XU conversion
+    return __int_as_float(0x4B400000 + v) - 12582912.0f;
+}
+__device__ __forceinline__ int float_to_int_rhe(float f) {     // |f| < 2^22, round half to even (cvtps2dq)
+    return __float_as_int(f + 12582912.0f) - 0x4B400000;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(kRtThreads) resize_tiled_kernel(const void* __restrict__ src_, void* __restrict__ dst_, TiledGeom g) {
+    using S = typename Kind<KIND>::S;
+    constexpr int K = Kind<KIND>::TAPS;
+    constexpr int ES = sizeof(S);
+    constexpr bool kTwoPass = K == 4;
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ int s_yidx[kRtMaxTH][K], s_ycoef[kRtMaxTH][K];
+    __shared__ short s_slot[kRtMaxBand];
+    __shared__ int s_rows[kRtMaxBand];
+    __shared__ int s_x[2], s_nslots;
+    __shared__ float s_yfb[kRtMaxTH][4];   // u8 bicubic: (float)ibeta * 2^-22, the vertical weights of OpenCV's fp32 body
+
+    uint8_t* tile = smem;                                                        // [max_slots][src_pitch]
+    float* hbuf = reinterpret_cast<float*>(smem + (size_t)g.max_slots * g.src_pitch);   // [max_slots][hpitch] (two-pass)
+    uint8_t* obuf = smem + (size_t)g.max_slots * g.src_pitch + (kTwoPass ? (size_t)g.max_slots * g.hpitch * 4 : 0);
+
+    const int tid = threadIdx.x;
+    const int tile_x = blockIdx.x % g.tiles_x, tile_y = blockIdx.x / g.tiles_x;
+    const int e0 = tile_x * g.TWE, dy0 = tile_y * g.TH;
+    const int twe = min(g.TWE, g.wo * g.c - e0), th = min(g.TH, g.ho - dy0);
+    const uint8_t* img = reinterpret_cast<const uint8_t*>(src_) + blockIdx.y * g.src_image * ES;
+    uint8_t* out_img = reinterpret_cast<uint8_t*>(dst_) + blockIdx.y * g.dst_image * ES;
+
+    // ---- coefficients: this thread's element column (registers), the tile's rows (shared)
+    const bool active = tid < twe;
+    const int xe = active ? tid : twe - 1;
+    const int dxl = xe / g.c, ch = xe - dxl * g.c;
+    int xidx[K], xcoef[K];
+    axis_coefs<KIND>(e0 / g.c + dxl, g.w, g.wo, true, xidx, xcoef);
+    if (tid == 0) s_x[0] = xidx[0];
+    if (tid == twe - 1) s_x[1] = xidx[K - 1];
+    if (tid < th) {
+        int yi[K], yc[K];
+        axis_coefs<KIND>(dy0 + tid, g.h, g.ho, false, yi, yc);
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            s_yidx[tid][j] = yi[j]; s_ycoef[tid][j] = yc[j];
+            if constexpr (KIND == kCubU8) s_yfb[tid][j] = (float)yc[j] * (1.f / (2048 * 2048));
+        }
+    }
+    __syncthreads();
+
+    // ---- which source rows does the tile touch?  row -> slot
+    const int y_lo = s_yidx[0][0], band = s_yidx[th - 1][K - 1] - y_lo + 1;
+    for (int r = tid; r < band; r += kRtThreads) s_slot[r] = -1;
+    __syncthreads();
+    for (int i = tid; i < th * K; i += kRtThreads) s_slot[s_yidx[i / K][i % K] - y_lo] = 0;
+    __syncthreads();
+    if (tid == 0) {
+        int n = 0;
+        for (int r = 0; r < band; ++r)
+            if (s_slot[r] == 0) { s_slot[r] = (short)n; s_rows[n] = y_lo + r; ++n; }
+        s_nslots = n;
+    }
+    __syncthreads();
+    const int nslots = s_nslots;
+
+    // ---- stage the touched rows, columns [x_lo, x_hi], at the widest legal granularity
+    const int row_bytes = g.w * g.c * ES;
+    const int xb0 = s_x[0] * g.c * ES, xb1 = (s_x[1] + 1) * g.c * ES;
+    const int xb0a = xb0 & ~(g.align - 1);
+    const int width = ((xb1 + g.align - 1) & ~(g.align - 1)) - xb0a;
+    if (g.align == 16) {
+        const int units = width >> 4;
+        for (int i = tid; i < nslots * units; i += kRtThreads) {
+            const int r = i / units, u = i - r * units;
+            *reinterpret_cast<uint4*>(tile + r * g.src_pitch + 16 * u) = ld_stream16(img + (size_t)s_rows[r] * row_bytes + xb0a + 16 * u);
+        }
+    } else if (g.align == 4) {
+        const int units = width >> 2;
+        for (int i = tid; i < nslots * units; i += kRtThreads) {
+            const int r = i / units, u = i - r * units;
+            *reinterpret_cast<uint32_t*>(tile + r * g.src_pitch + 4 * u) = __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)s_rows[r] * row_bytes + xb0a) + u);
+        }
+    } else {
+        for (int i = tid; i < nslots * width; i += kRtThreads) {
+            const int r = i / width, u = i - r * width;
+            tile[r * g.src_pitch + u] = __ldg(img + (size_t)s_rows[r] * row_bytes + xb0a + u);
+        }
+    }
+    __syncthreads();
+
+    int toff[K];   // byte offset of each x tap of this thread's element inside a staged row
+#pragma unroll
+    for (int j = 0; j < K; ++j) toff[j] = (xidx[j] * g.c + ch) * ES - xb0a;
+
+    // ---- pass 1 (bicubic): horizontal sums per staged row
+    if constexpr (kTwoPass) {
+        if (active) {
+            for (int s = 0; s < nslots; ++s) {
+                const uint8_t* row = tile + s * g.src_pitch;
+                float hval;
+                if constexpr (KIND == kCubF32) {   // resize_naive.cpp:230: S[-1]*a0 + S[0]*a1 + S[1]*a2 + S[2]*a3, left to right
+                    const float t0 = *reinterpret_cast<const float*>(row + toff[0]), t1 = *reinterpret_cast<const float*>(row + toff[1]);
+                    const float t2 = *reinterpret_cast<const float*>(row + toff[2]), t3 = *reinterpret_cast<const float*>(row + toff[3]);
+                    hval = t0 * __int_as_float(xcoef[0]) + t1 * __int_as_float(xcoef[1]) + t2 * __int_as_float(xcoef[2]) +
+                           t3 * __int_as_float(xcoef[3]);
+                } else {
+                    const int hi = row[toff[0]] * xcoef[0] + row[toff[1]] * xcoef[1] + row[toff[2]] * xcoef[2] + row[toff[3]] * xcoef[3];
+                    hval = int_to_float_exact(hi);
+                }
+                hbuf[s * g.hpitch + tid] = hval;
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- pass 2: one output row at a time into the output tile
+    // row r of the tile goes to global bytes [ga, ga + twe*ES); it is laid out in shared memory with the same 16-byte phase
+    const size_t out_row_bytes = (size_t)g.wo * g.c * ES;
+    if (active) {
+        const int vec_end = (g.wo * g.c) & ~7;   // OpenCV's SSE2 body covers x < (width & ~7)
+        for (int ty = 0; ty < th; ++ty) {
+            const uintptr_t ga = reinterpret_cast<uintptr_t>(out_img) + (size_t)(dy0 + ty) * out_row_bytes + (size_t)e0 * ES;
+            S* o = reinterpret_cast<S*>(obuf + ty * g.opitch + (ga & 15)) + tid;
+            int slot[K];
+#pragma unroll
+            for (int j = 0; j < K; ++j) slot[j] = s_slot[s_yidx[ty][j] - y_lo];
+            if constexpr (KIND == kLinU8 || KIND == kLinU8Signed || KIND == kLinU8Neon) {
+                constexpr bool kS = KIND == kLinU8Signed;
+                const uint8_t* r0 = tile + slot[0] * g.src_pitch;
+                const uint8_t* r1 = tile + slot[1] * g.src_pitch;
+                const int p00 = pix<kS>(r0[toff[0]]), p01 = pix<kS>(r0[toff[1]]), p10 = pix<kS>(r1[toff[0]]), p11 = pix<kS>(r1[toff[1]]);
+                const int cx0 = xcoef[0], cx1 = xcoef[1], cy0 = s_ycoef[ty][0], cy1 = s_ycoef[ty][1];
+                int v;
+                if constexpr (KIND == kLinU8Neon) {   // resize_neon.cpp:145-181
+                    const int h0 = (short)((p00 * cx0 + p01 * cx1) >> 4), h1 = (short)((p10 * cx0 + p11 * cx1) >> 4);
+                    v = clamp255(((short)((cy0 * h0) >> 16) + (short)((cy1 * h1) >> 16) + 2) >> 2);
+                } else {                              // resize_naive.cpp:60-65
+                    v = (p00 * cx0 * cy0 + p10 * cx0 * cy1 + p01 * cx1 * cy0 + p11 * cx1 * cy1) >> 22;
+                }
+                *o = (uint8_t)v;
+            } else if constexpr (KIND == kLinF32) {   // resize_naive.cpp:121-124 evaluation order
+                const uint8_t* r0 = tile + slot[0] * g.src_pitch;
+                const uint8_t* r1 = tile + slot[1] * g.src_pitch;
+                const float lt = *reinterpret_cast<const float*>(r0 + toff[0]), rt = *reinterpret_cast<const float*>(r0 + toff[1]);
+                const float lb = *reinterpret_cast<const float*>(r1 + toff[0]), rb = *reinterpret_cast<const float*>(r1 + toff[1]);
+                const float cx0 = __int_as_float(xcoef[0]), cx1 = __int_as_float(xcoef[1]);
+                const float cy0 = __int_as_float(s_ycoef[ty][0]), cy1 = __int_as_float(s_ycoef[ty][1]);
+                *o = lt * cx0 * cy0 + lb * cx0 * cy1 + rt * cx1 * cy0 + rb * cx1 * cy1;
+            } else {
+                const float h0 = hbuf[slot[0] * g.hpitch + tid], h1 = hbuf[slot[1] * g.hpitch + tid];
+                const float h2 = hbuf[slot[2] * g.hpitch + tid], h3 = hbuf[slot[3] * g.hpitch + tid];
+                if constexpr (KIND == kCubF32) {      // resize_naive.cpp:345
+                    *o = h0 * __int_as_float(s_ycoef[ty][0]) + h1 * __int_as_float(s_ycoef[ty][1]) +
+                         h2 * __int_as_float(s_ycoef[ty][2]) + h3 * __int_as_float(s_ycoef[ty][3]);
+                } else {
+                    const int b0 = s_ycoef[ty][0], b1 = s_ycoef[ty][1], b2 = s_ycoef[ty][2], b3 = s_ycoef[ty][3];
+                    int v;
+                    if (e0 + tid < vec_end) {         // fp32 body: mul, then add, one rounding each; cvtps2dq; packs; packus
+                        float f = h0 * s_yfb[ty][0];
+                        f = f + h1 * s_yfb[ty][1];
+                        f = f + h2 * s_yfb[ty][2];
+                        f = f + h3 * s_yfb[ty][3];
+                        v = max(min(float_to_int_rhe(f), 32767), -32768);
+                    } else {                          // scalar tail: FixedPtCast<int, uchar, 22>
+                        v = (__float2int_rn(h0) * b0 + __float2int_rn(h1) * b1 + __float2int_rn(h2) * b2 + __float2int_rn(h3) * b3 + (1 << 21)) >> 22;
+                    }
+                    *o = (uint8_t)clamp255(v);
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- copy the output tile out: 16-byte aligned chunks, partial chunks at the row ends byte by byte
+    const int seg = twe * ES;
+    const int chunks_per_row = (seg + 15 + 15) >> 4;   // upper bound incl. phase
+    for (int i = tid; i < th * chunks_per_row; i += kRtThreads) {
+        const int ty = i / chunks_per_row, q = i - ty * chunks_per_row;
+        const uintptr_t ga = reinterpret_cast<uintptr_t>(out_img) + (size_t)(dy0 + ty) * out_row_bytes + (size_t)e0 * ES;
+        const int mis = (int)(ga & 15);
+        const int lo = max(mis, 16 * q), hi = min(mis + seg, 16 * q + 16);
+        if (lo >= hi) continue;
+        const uint8_t* sp = obuf + ty * g.opitch + 16 * q;
+        uint8_t* gp = reinterpret_cast<uint8_t*>(ga - mis) + 16 * q;
+        if (hi - lo == 16) st_stream16(gp, *reinterpret_cast<const uint4*>(sp));
+        else for (int b = lo - 16 * q; b < hi - 16 * q; ++b) gp[b] = sp[b];
+    }
+}
+
+template <int KIND>
+static int launch_tiled_kind(const void* src, void* dst, int images, TiledGeom g, size_t smem, cudaStream_t s) {
+    auto kern = resize_tiled_kernel<KIND>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return set_error(VACV_ERR_CUDA, "resize: %s", cudaGetErrorString(e));
+    }
+    constexpr int ES = sizeof(typename Kind<KIND>::S);
+    for (int i0 = 0; i0 < images; i0 += 65535) {
+        dim3 grid(g.tiles_x * g.tiles_y, std::min(images - i0, 65535));
+        kern<<<grid, kRtThreads, smem, s>>>((const uint8_t*)src + (size_t)i0 * g.src_image * ES,
+                                            (uint8_t*)dst + (size_t)i0 * g.dst_image * ES, g);
+    }
+    return 1;
+}
+
+// Returns 1 if launched, 0 if the shape does not fit the tiled kernel (caller uses the direct kernels), < 0 on error.
+int try_launch_resize_tiled(int kind, const void* src, void* dst, int images, int w, int h, int c, int wo, int ho, cudaStream_t s) {
+    const int es = (kind == kLinF32 || kind == kCubF32) ? 4 : 1;
+    const int K = (kind == kCubF32 || kind == kCubU8) ? 4 : 2;
+    if (c > 64 || (size_t)wo * c > 0x3fffffff) return 0;
+    TiledGeom g;
+    g.w = w; g.h = h; g.c = c; g.wo = wo; g.ho = ho;
+    g.src_image = (size_t)w * h * c; g.dst_image = (size_t)wo * ho * c;
+    g.TWE = std::min(256, wo * c) / c * c;
+    if (g.TWE <= 0) return 0;
+    const size_t row_bytes = (size_t)w * c * es;
+    g.align = ((row_bytes % 16) == 0 && ((uintptr_t)src % 16) == 0) ? 16 : ((row_bytes % 4) == 0 && ((uintptr_t)src % 4) == 0) ? 4 : 1;
+    const double sx = (double)w / wo, sy = (double)h / ho;
+    const int tw = g.TWE / c;
+    const int span_px = std::min(w, (int)(sx * (tw - 1)) + K + 3);
+    g.src_pitch = (int)((((size_t)span_px * c * es + 2 * g.align + 15)) & ~(size_t)15);
+    g.opitch = (g.TWE * es + 16 + 15) & ~15;
+    g.hpitch = (g.TWE + 3) & ~3;
+    const size_t budget = 56 * 1024;
+    int TH = kRtMaxTH;
+    for (; TH >= 1; --TH) {
+        const int band = (int)(sy * (TH - 1)) + K + 3;
+        const int slots = std::min(band, TH * K);
+        const size_t smem = (size_t)slots * g.src_pitch + (K == 4 ? (size_t)slots * g.hpitch * 4 : 0) + (size_t)TH * g.opitch;
+        if (band <= kRtMaxBand && smem <= budget) {
+            g.TH = TH; g.max_slots = slots;
+            g.tiles_x = (wo * c + g.TWE - 1) / g.TWE; g.tiles_y = (ho + TH - 1) / TH;
+            if ((long long)g.tiles_x * g.tiles_y > 0x7fffffffLL) return 0;
+            switch (kind) {
+                case kLinU8: return launch_tiled_kind<kLinU8>(src, dst, images, g, smem, s);
+                case kLinU8Signed: return launch_tiled_kind<kLinU8Signed>(src, dst, images, g, smem, s);
+                case kLinU8Neon: return launch_tiled_kind<kLinU8Neon>(src, dst, images, g, smem, s);
+                case kLinF32: return launch_tiled_kind<kLinF32>(src, dst, images, g, smem, s);
+                case kCubF32: return launch_tiled_kind<kCubF32>(src, dst, images, g, smem, s);
+                default: return launch_tiled_kind<kCubU8>(src, dst, images, g, smem, s);
+            }
+        }
+    }
+    return 0;
+}
+
+}  // namespace vacv

@@ -146,76 +146,150 @@ __global__ void dtype_tail_kernel(const void* src, void* dst, size_t begin, size
 
 // =====================================================================================================
 // a12 normalize (src/cv/normalize_naive.cpp:74-90): (float)((double)(x - mean) / ((double)std + 1e-6)).
-// fp32 input: exact double division per element.  u8 input: there are only 256 possible inputs per channel,
-// so each CTA builds the 256 x c table once with that exact expression and the stream becomes
-// 4-byte load -> 4 shared-memory lookups -> 16-byte store.
+//
+// u8 input: only 256 inputs per channel exist, so each CTA builds the 256 x c table once with that exact expression
+//   and the stream becomes  4-byte load -> 4 shared-memory lookups -> 16-byte store.
+// fp32 input: q = (double)(x - mean) * (1/den) is within 2 ulp(double) of the correctly rounded quotient, so
+//   (float)q equals the reference's (float)(d/den) unless q sits within a few double-ulps of a float rounding
+//   boundary; exactly those (about 1 in 2^25) are redone with the IEEE double division.  Bit-exact, 1 DMUL per element.
+//
+// Channel of an element: HWC -> (index mod c) tracked incrementally (no per-element division);
+//                        CHW -> one plane per blockIdx.y, the channel is a CTA constant.
 constexpr int kNormMaxC = 4;
 
+__device__ __forceinline__ float normalize_fast_exact(float x, float mean, double den, double rden) {
+    const double d = (double)(x - mean);
+    const double q = d * rden;
+    // low 29 bits of the fp64 mantissa are what the fp32 rounding discards; 0x10000000 is the midpoint
+    const unsigned lo = (unsigned)__double2loint(q) & 0x1fffffffu;
+    const float f = (float)q;
+    // redo exactly when q is within 8 double-ulps of an fp32 rounding boundary (|q - exact| <= 2.5 ulp), or when
+    // the fp32 result is (near) subnormal, where the boundary sits at a different bit
+    if (__builtin_expect(lo - 0x0ffffff8u <= 16u || fabsf(f) < 1e-30f, 0)) return (float)(d / den);
+    return f;
+}
+
 struct NormGeom {
-    int c, layout;
-    unsigned wh;           // pixels per plane
-    size_t per_frame;      // wh * c
+    int c;
+    unsigned wh;            // pixels per plane
+    unsigned per_frame;     // wh * c
     int stats_per_frame;
 };
 
-__device__ __forceinline__ int channel_of(const NormGeom& g, size_t r /* index within the frame */) {
-    return g.layout == VACV_NHWC ? (int)(r % g.c) : (int)(r / g.wh);
-}
-
-__global__ void __launch_bounds__(256) normalize_f32_kernel(const float* __restrict__ src, float* __restrict__ dst,
-                                                             const float* __restrict__ mean, const float* __restrict__ stddev,
-                                                             NormGeom g, size_t n4, size_t n) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (; i < n4; i += stride) {
-        const size_t e = 4 * i;
-        uint4 r = ld_stream16(src + e);
-        const float x[4] = {__uint_as_float(r.x), __uint_as_float(r.y), __uint_as_float(r.z), __uint_as_float(r.w)};
-        float o[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const size_t frame = (e + j) / g.per_frame, rr = (e + j) % g.per_frame;
-            const int k = channel_of(g, rr) + (g.stats_per_frame ? (int)frame * g.c : 0);
-            o[j] = normalize_one(x[j], __ldg(mean + k), (double)__ldg(stddev + k) + 1e-6);
-        }
-        st_stream16f(dst + e, make_float4(o[0], o[1], o[2], o[3]));
-    }
-    // tail (< 4 elements)
-    if (blockIdx.x == 0 && threadIdx.x < n - 4 * n4) {
-        const size_t e = 4 * n4 + threadIdx.x;
-        const size_t frame = e / g.per_frame, rr = e % g.per_frame;
-        const int k = channel_of(g, rr) + (g.stats_per_frame ? (int)frame * g.c : 0);
-        dst[e] = normalize_one(src[e], mean[k], (double)stddev[k] + 1e-6);
-    }
-}
-
-// grid = (ctas_per_frame, frames_in_launch) so that a CTA's table belongs to one frame's statistics.
-__global__ void __launch_bounds__(256) normalize_u8_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst,
-                                                            const float* __restrict__ mean, const float* __restrict__ stddev,
-                                                            NormGeom g) {
-    __shared__ float lut[kNormMaxC][256];
+// ---- HWC.  grid = (ctas_per_frame, frames).  C = channel count (1..4).
+template <int C>
+__global__ void __launch_bounds__(256) normalize_u8_hwc_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst,
+                                                                const float* __restrict__ mean, const float* __restrict__ stddev,
+                                                                NormGeom g) {
+    __shared__ float lut[C * 256];
     const size_t frame = blockIdx.y;
-    const float* mu = mean + (g.stats_per_frame ? frame * g.c : 0);
-    const float* sd = stddev + (g.stats_per_frame ? frame * g.c : 0);
-    for (int t = threadIdx.x; t < 256 * g.c; t += blockDim.x) {
-        const int k = t >> 8, v = t & 255;
-        lut[k][v] = normalize_one((float)v, mu[k], (double)sd[k] + 1e-6);
-    }
+    const float* mu = mean + (g.stats_per_frame ? frame * C : 0);
+    const float* sd = stddev + (g.stats_per_frame ? frame * C : 0);
+    for (int t = threadIdx.x; t < 256 * C; t += blockDim.x)
+        lut[t] = normalize_one((float)(t & 255), mu[t >> 8], (double)sd[t >> 8] + 1e-6);
     __syncthreads();
     const uint8_t* s = src + frame * g.per_frame;
     float* d = dst + frame * g.per_frame;
-    const size_t n4 = g.per_frame >> 2;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t e = 4 * i;
-        const uint32_t v = ld_stream4(s + e);
+    const unsigned n4 = g.per_frame >> 2, stride = gridDim.x * blockDim.x;
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    // element 4*i has channel (4*i) mod C; advance it by (4*stride) mod C per iteration
+    unsigned ph = (4u * (i % C)) % C;
+    const unsigned dph = (4u * (stride % C)) % C;
+    for (; i < n4; i += stride) {
+        const uint32_t v = ld_stream4(s + 4 * (size_t)i);
         float o[4];
+        unsigned k = ph;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) o[j] = lut[channel_of(g, e + j)][(v >> (8 * j)) & 0xff];
-        st_stream16f(d + e, make_float4(o[0], o[1], o[2], o[3]));
+        for (int j = 0; j < 4; ++j) {
+            o[j] = lut[k * 256 + ((v >> (8 * j)) & 0xff)];
+            k = (k + 1 == C) ? 0 : k + 1;
+        }
+        st_stream16f(d + 4 * (size_t)i, make_float4(o[0], o[1], o[2], o[3]));
+        ph += dph;
+        if (ph >= C) ph -= C;
     }
     if (blockIdx.x == 0 && threadIdx.x < g.per_frame - 4 * n4) {
-        const size_t e = 4 * n4 + threadIdx.x;
-        d[e] = lut[channel_of(g, e)][s[e]];
+        const unsigned e = 4 * n4 + threadIdx.x;
+        d[e] = lut[(e % C) * 256 + s[e]];
+    }
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) normalize_f32_hwc_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                                 const float* __restrict__ mean, const float* __restrict__ stddev,
+                                                                 NormGeom g) {
+    const size_t frame = blockIdx.y;
+    float mu[C]; double den[C], rden[C];
+#pragma unroll
+    for (int k = 0; k < C; ++k) {
+        mu[k] = __ldg(mean + (g.stats_per_frame ? frame * C : 0) + k);
+        den[k] = (double)__ldg(stddev + (g.stats_per_frame ? frame * C : 0) + k) + 1e-6;
+        rden[k] = 1.0 / den[k];
+    }
+    const float* s = src + frame * g.per_frame;
+    float* d = dst + frame * g.per_frame;
+    const unsigned n4 = g.per_frame >> 2, stride = gridDim.x * blockDim.x;
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned ph = (4u * (i % C)) % C;
+    const unsigned dph = (4u * (stride % C)) % C;
+    for (; i < n4; i += stride) {
+        const uint4 r = ld_stream16(s + 4 * (size_t)i);
+        const float x[4] = {__uint_as_float(r.x), __uint_as_float(r.y), __uint_as_float(r.z), __uint_as_float(r.w)};
+        float o[4];
+        unsigned k = ph;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            // select the channel's constants without dynamic register indexing
+            float m = mu[0]; double dn = den[0], rd = rden[0];
+#pragma unroll
+            for (int q = 1; q < C; ++q) if (k == q) { m = mu[q]; dn = den[q]; rd = rden[q]; }
+            o[j] = normalize_fast_exact(x[j], m, dn, rd);
+            k = (k + 1 == C) ? 0 : k + 1;
+        }
+        st_stream16f(d + 4 * (size_t)i, make_float4(o[0], o[1], o[2], o[3]));
+        ph += dph;
+        if (ph >= C) ph -= C;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < g.per_frame - 4 * n4) {
+        const unsigned e = 4 * n4 + threadIdx.x, k = e % C;
+        d[e] = normalize_one(s[e], mean[(g.stats_per_frame ? frame * C : 0) + k], (double)stddev[(g.stats_per_frame ? frame * C : 0) + k] + 1e-6);
+    }
+}
+
+// ---- planes (CHW, or c == 1).  grid = (ctas_per_plane, planes); plane p = frame p / c, channel p % c.
+template <bool kU8>
+__global__ void __launch_bounds__(256) normalize_plane_kernel(const void* __restrict__ src_, float* __restrict__ dst,
+                                                               const float* __restrict__ mean, const float* __restrict__ stddev,
+                                                               NormGeom g) {
+    __shared__ float lut[256];
+    const unsigned plane = blockIdx.y, frame = plane / g.c, k = plane - frame * g.c;
+    const float mu = __ldg(mean + (g.stats_per_frame ? frame * g.c : 0) + k);
+    const double den = (double)__ldg(stddev + (g.stats_per_frame ? frame * g.c : 0) + k) + 1e-6;
+    const size_t base = (size_t)plane * g.wh;
+    float* d = dst + base;
+    // vector body needs the plane start 16-byte (f32) / 4-byte (u8) aligned: true when wh % 4 == 0, else scalar
+    const bool vec = (g.wh & 3) == 0;
+    const unsigned n4 = vec ? g.wh >> 2 : 0, stride = gridDim.x * blockDim.x;
+    if (kU8) {
+        const uint8_t* s = (const uint8_t*)src_ + base;
+        for (int t = threadIdx.x; t < 256; t += blockDim.x) lut[t] = normalize_one((float)t, mu, den);
+        __syncthreads();
+        for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+            const uint32_t v = ld_stream4(s + 4 * (size_t)i);
+            st_stream16f(d + 4 * (size_t)i, make_float4(lut[v & 0xff], lut[(v >> 8) & 0xff], lut[(v >> 16) & 0xff], lut[v >> 24]));
+        }
+        for (unsigned e = 4 * n4 + blockIdx.x * blockDim.x + threadIdx.x; e < g.wh; e += stride) d[e] = lut[s[e]];
+    } else {
+        const float* s = (const float*)src_ + base;
+        const double rden = 1.0 / den;
+        for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+            const uint4 r = ld_stream16(s + 4 * (size_t)i);
+            st_stream16f(d + 4 * (size_t)i, make_float4(normalize_fast_exact(__uint_as_float(r.x), mu, den, rden),
+                                                        normalize_fast_exact(__uint_as_float(r.y), mu, den, rden),
+                                                        normalize_fast_exact(__uint_as_float(r.z), mu, den, rden),
+                                                        normalize_fast_exact(__uint_as_float(r.w), mu, den, rden)));
+        }
+        for (unsigned e = 4 * n4 + blockIdx.x * blockDim.x + threadIdx.x; e < g.wh; e += stride) d[e] = normalize_one(s[e], mu, den);
     }
 }
 
@@ -303,30 +377,50 @@ extern "C" int vacv_cuda_dtype_change(const void* src, void* dst, size_t n, int 
     return check_launch("dtype_change");
 }
 
+template <int C>
+static void launch_norm_hwc(const void* src, float* dst, const float* mean, const float* stddev, const NormGeom& g, int src_dtype,
+                            dim3 grid, cudaStream_t s) {
+    if (src_dtype == VACV_INT8) normalize_u8_hwc_kernel<C><<<grid, 256, 0, s>>>((const uint8_t*)src, dst, mean, stddev, g);
+    else normalize_f32_hwc_kernel<C><<<grid, 256, 0, s>>>((const float*)src, dst, mean, stddev, g);
+}
+
 extern "C" int vacv_cuda_normalize(const void* src, float* dst, int batch, int w, int h, int c, int src_dtype, int layout,
                                    const float* mean, const float* stddev, int stats_per_frame, void* stream) {
     VACV_REQUIRE(src && dst && mean && stddev, "normalize: null pointer");
     VACV_REQUIRE(batch > 0 && w > 0 && h > 0 && c > 0, "normalize: non-positive size");
     if (src_dtype != VACV_INT8 && src_dtype != VACV_FP32) return set_error(VACV_ERR_UNSUPPORTED, "normalize: src dtype %d", src_dtype);
     VACV_REQUIRE((((uintptr_t)src | (uintptr_t)dst) & 15) == 0, "normalize: buffers must be 16-byte aligned");
+    VACV_REQUIRE((size_t)w * h * c < 0xffffffffull, "normalize: frame too large");
     cudaStream_t s = as_stream(stream);
     NormGeom g;
-    g.c = c; g.layout = layout; g.wh = (unsigned)w * h; g.per_frame = (size_t)w * h * c; g.stats_per_frame = stats_per_frame;
-    const size_t n = g.per_frame * batch;
-    if (src_dtype == VACV_FP32) {
-        const size_t n4 = n / 4;
-        const unsigned blocks = (unsigned)max((size_t)1, min((size_t)kNumSMs * 16, (size_t)ceil_div(n4, 256)));
-        normalize_f32_kernel<<<blocks, 256, 0, s>>>((const float*)src, dst, mean, stddev, g, n4, n);
-    } else {
-        if (c > kNormMaxC) return set_error(VACV_ERR_UNSUPPORTED, "normalize: u8 input supports c <= %d", kNormMaxC);
-        VACV_REQUIRE((g.per_frame % 4) == 0 || batch == 1, "normalize: u8 batch needs w*h*c %% 4 == 0");
-        const unsigned per_frame_ctas = (unsigned)max((size_t)1, min((size_t)ceil_div(g.per_frame / 4, 256 * 8), (size_t)4096));
+    g.c = c; g.wh = (unsigned)w * h; g.per_frame = g.wh * c; g.stats_per_frame = stats_per_frame;
+    const size_t es = src_dtype == VACV_INT8 ? 1 : 4;
+    if (layout == VACV_NHWC && c > 1) {
+        if (c > kNormMaxC) return set_error(VACV_ERR_UNSUPPORTED, "normalize: HWC supports c <= %d", kNormMaxC);
+        VACV_REQUIRE((g.per_frame % 4) == 0 || batch == 1, "normalize: HWC batch needs w*h*c %% 4 == 0");
+        const unsigned ctas = (unsigned)max(1u, min(ceil_div(g.per_frame / 4, 256 * 8), (unsigned)(kNumSMs * 16 / min(batch, kNumSMs * 16) + 1)));
         for (int f0 = 0; f0 < batch; f0 += 65535) {
-            const int nf = min(batch - f0, 65535);
-            dim3 grid(per_frame_ctas, nf);
-            normalize_u8_kernel<<<grid, 256, 0, s>>>((const uint8_t*)src + (size_t)f0 * g.per_frame, dst + (size_t)f0 * g.per_frame,
-                                                     mean + (stats_per_frame ? (size_t)f0 * c : 0),
-                                                     stddev + (stats_per_frame ? (size_t)f0 * c : 0), g);
+            dim3 grid(ctas, min(batch - f0, 65535));
+            const void* sp = (const uint8_t*)src + (size_t)f0 * g.per_frame * es;
+            float* dp = dst + (size_t)f0 * g.per_frame;
+            const float* mp = mean + (stats_per_frame ? (size_t)f0 * c : 0);
+            const float* dvp = stddev + (stats_per_frame ? (size_t)f0 * c : 0);
+            if (c == 2) launch_norm_hwc<2>(sp, dp, mp, dvp, g, src_dtype, grid, s);
+            else if (c == 3) launch_norm_hwc<3>(sp, dp, mp, dvp, g, src_dtype, grid, s);
+            else launch_norm_hwc<4>(sp, dp, mp, dvp, g, src_dtype, grid, s);
+        }
+    } else {
+        const long long planes = (long long)batch * c;
+        const int chunk = 65535 / c * c;
+        const unsigned ctas = (unsigned)max(1u, min(ceil_div(g.wh / 4 + 1, 256 * 8), (unsigned)(kNumSMs * 16 / (unsigned)min(planes, (long long)kNumSMs * 16) + 1)));
+        for (long long p0 = 0; p0 < planes; p0 += chunk) {
+            dim3 grid(ctas, (unsigned)min((long long)chunk, planes - p0));
+            const void* sp = (const uint8_t*)src + (size_t)p0 * g.wh * es;
+            float* dp = dst + (size_t)p0 * g.wh;
+            const float* mp = mean + (stats_per_frame ? (size_t)(p0 / c) * c : 0);
+            const float* dvp = stddev + (stats_per_frame ? (size_t)(p0 / c) * c : 0);
+            if (src_dtype == VACV_INT8) normalize_plane_kernel<true><<<grid, 256, 0, s>>>(sp, dp, mp, dvp, g);
+            else normalize_plane_kernel<false><<<grid, 256, 0, s>>>(sp, dp, mp, dvp, g);
         }
     }
     return check_launch("normalize");

@@ -1,0 +1,228 @@
+#!/usr/bin/env python
+"""bench_ops.py -- per-operator / per-config measurements next to the headline bench.py (not the driver contract).
+
+    python bench_ops.py [--workload all|c1|c2|c2g|c3|c4|c5|ops] [--iters N] [--json out.jsonl]
+    torchrun --nproc-per-node N bench_ops.py --workload c5        # batch-global statistics with the all-reduce
+
+For every kernel: device-resident time per launch (CUDA events, median of N after warm-up, batch >> L2), output
+Mpix/s, achieved GB/s = algorithmic bytes / time, fraction of the measured HBM copy peak.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import vacv_b200 as vacv  # noqa: E402
+from bench import MEAN, STD, measured_peak  # noqa: E402
+
+PEAK, _ = measured_peak()
+RESULTS = []
+
+
+def timeit(fn, iters, warmup=5):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        e1.synchronize()
+        times.append(e0.elapsed_time(e1))
+    return statistics.median(times), min(times)
+
+
+def report(name, ms, out_pix, algo_bytes, note=""):
+    gbs = algo_bytes / (ms * 1e-3) / 1e9
+    r = {"name": name, "ms": round(ms, 4), "out_Mpix_s": round(out_pix / (ms * 1e-3) / 1e6, 1), "GB_s": round(gbs, 1),
+         "frac_of_measured_peak": round(gbs / PEAK, 3), "algo_bytes": algo_bytes, "note": note}
+    RESULTS.append(r)
+    print(f"{name:58s} {ms:9.4f} ms {r['out_Mpix_s']:12.1f} Mpix/s {gbs:8.1f} GB/s  frac {r['frac_of_measured_peak']:.3f}  {note}", flush=True)
+
+
+def rand_u8(*shape, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return torch.randint(0, 256, shape, dtype=torch.uint8, device="cuda", generator=g)
+
+
+def stats():
+    return torch.tensor(MEAN, device="cuda"), torch.tensor(STD, device="cuda")
+
+
+def c1(iters):   # resize INTER_LINEAR u8 BGR 1920x1080 -> 640x360, batch 256
+    b = 256
+    src = rand_u8(b, 1080, 1920, 3)
+    ms, _ = timeit(lambda: vacv.resize(src, vacv.NHWC, 640, 360), iters)
+    report("c1 resize linear u8 hwc 1920x1080->640x360 x256", ms, b * 640 * 360, b * (1920 * 1080 * 3 + 640 * 360 * 3))
+    ms, _ = timeit(lambda: vacv.resize(src, vacv.NHWC, 500, 300), iters)
+    report("   resize linear u8 hwc 1920x1080->500x300 x256", ms, b * 500 * 300, b * (1920 * 1080 * 3 + 500 * 300 * 3))
+
+
+def c2(iters, wo=640, ho=640, w=1920, h=1080, tag="c2"):
+    b = 256
+    mean, std = stats()
+    src = rand_u8(b, w * h * 3 // 2)
+    out = torch.empty((b, 3, ho, wo), dtype=torch.float32, device="cuda")
+    ms, _ = timeit(lambda: vacv.nv_resize_normalize_chw(src, w, h, wo, ho, mean, std, True, out=out), iters)
+    report(f"{tag} fused nv12->chw f32 {w}x{h}->{wo}x{ho} x{b}", ms, b * wo * ho, b * (w * h * 3 // 2 + wo * ho * 12))
+
+
+def c2_unfused(iters):
+    b = 64
+    mean, std = stats()
+    src = rand_u8(b, 1920 * 1080 * 3 // 2)
+
+    def chain():
+        bgr = vacv.cvt_nv2bgr(src, 1920, 1080)
+        small = vacv.resize(bgr, vacv.NHWC, 640, 640)
+        norm = vacv.normalize(small, vacv.NHWC, mean, std)
+        return vacv.layout_change(norm, vacv.NHWC, vacv.NCHW)
+    ms, _ = timeit(chain, iters)
+    report("   unfused CUDA chain (4 kernels) 1080p->640x640 x64", ms, b * 640 * 640, b * (1920 * 1080 * 3 // 2 + 640 * 640 * 12),
+           "algo bytes of the fused op")
+
+
+def face_matrices(n, w, h, wo, seed=7):
+    r = np.random.default_rng(seed)
+    ms = []
+    for _ in range(n):
+        s = r.uniform(0.3, 0.6)
+        a = np.deg2rad(r.uniform(-15, 15))
+        cx, cy = r.uniform(0.25 * w, 0.75 * w), r.uniform(0.3 * h, 0.7 * h)
+        al, be = s * np.cos(a), s * np.sin(a)
+        ms.append(vacv.invert_affine([al, be, wo / 2 - al * cx - be * cy, -be, al, wo / 2 + be * cx - al * cy]))
+    return torch.tensor(np.array(ms, np.float32), device="cuda"), r
+
+
+def c3(iters):   # warp_affine face crops: 4096 x (1280x720 -> 112x112 fp32 normalised), frame pool of 512
+    n, nf, w, h, wo = 4096, 512, 1280, 720, 112
+    mean, std = stats()
+    frames = rand_u8(nf, h, w, 3)
+    minv, _ = face_matrices(n, w, h, wo)
+    idx = (torch.arange(n, device="cuda") % nf).to(torch.int32)
+    roi = int(np.mean([(wo / s) ** 2 * 3 for s in np.random.default_rng(7).uniform(0.3, 0.6, 1000)]))
+    ms, _ = timeit(lambda: vacv.warp_affine_normalize(frames, minv, wo, wo, mean, std, idx), iters)
+    report("c3 warp_affine_normalize 1280x720->112x112 f32 x4096", ms, n * wo * wo, n * (roi + wo * wo * 12), "bytes = mean source ROI + out")
+    ms, _ = timeit(lambda: vacv.warp_affine(frames, vacv.NHWC, minv, wo, wo, idx), iters)
+    report("   warp_affine u8 1280x720->112x112 x4096", ms, n * wo * wo, n * (roi + wo * wo * 3))
+
+
+def c4(iters):   # resize INTER_CUBIC u8 2560x1440 -> 1920x1080, batch 128
+    b = 128
+    src = rand_u8(b, 1440, 2560, 3)
+    ms, _ = timeit(lambda: vacv.resize(src, vacv.NHWC, 1920, 1080, vacv.INTER_CUBIC), iters)
+    report("c4 resize cubic u8 hwc 2560x1440->1920x1080 x128", ms, b * 1920 * 1080, b * (2560 * 1440 * 3 + 1920 * 1080 * 3))
+    srcf = src[:32].to(torch.float32)
+    ms, _ = timeit(lambda: vacv.resize(srcf, vacv.NHWC, 1920, 1080, vacv.INTER_CUBIC), iters)
+    report("   resize cubic f32 hwc 2560x1440->1920x1080 x32", ms, 32 * 1920 * 1080, 32 * 4 * (2560 * 1440 * 3 + 1920 * 1080 * 3))
+
+
+def c5(iters):   # batch-global mean/stddev + normalize, 4K frames, 128 per GPU (all-reduce of the sums under torchrun)
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+    from arm_neon_opencv_b200 import distributed as vd
+    b, w, h = 128, 3840, 2160
+    frames = rand_u8(b, h, w, 3, seed=int(os.environ.get("RANK", 0)))
+    out = torch.empty((b, h, w, 3), dtype=torch.float32, device="cuda")
+    sums = torch.zeros((1, 3, 2), dtype=torch.int64, device="cuda")
+
+    def step():
+        sums.zero_()
+        vacv.sums_u8(frames, vacv.NHWC, False, sums)
+        vd.allreduce_sums(sums)                         # 48 bytes over NCCL: the only inter-GPU exchange of the path
+        mean, std = vacv.finalize_mean_stddev(sums, world * b * w * h)
+        vacv.normalize(frames, vacv.NHWC, mean[0], std[0], out=out)
+    ms, _ = timeit(step, iters, warmup=3)
+    if dist:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    if int(os.environ.get("RANK", 0)) == 0:
+        report(f"c5 global mean/stddev + normalize 4K x{b}/GPU, {world} GPU(s)", ms, world * b * w * h, world * b * w * h * 3 * (1 + 1 + 4),
+               f"2 reads + 1 fp32 write; aggregate over {world} GPU(s): per-GPU frac = {b * w * h * 18 / (ms * 1e-3) / 1e9 / PEAK:.3f}")
+    if world == 1:
+        ms, _ = timeit(lambda: vacv.sums_u8(frames, vacv.NHWC, False, sums), iters)
+        report("   sums_u8 (stats pass) 4K x128", ms, b * w * h, b * w * h * 3)
+        mean, std = stats()
+        ms, _ = timeit(lambda: vacv.normalize(frames, vacv.NHWC, mean, std, out=out), iters)
+        report("   normalize u8->f32 (apply pass) 4K x128", ms, b * w * h, b * w * h * 3 * 5)
+    if dist:
+        dist.destroy_process_group()
+
+
+def ops(iters):
+    b = 128
+    nv = rand_u8(b, 1920 * 1080 * 3 // 2)
+    ms, _ = timeit(lambda: vacv.cvt_nv2bgr(nv, 1920, 1080), iters)
+    report("op cvt_nv2bgr 1080p x128", ms, b * 1920 * 1080, b * 1920 * 1080 * 4.5)
+    bgr = rand_u8(b, 1080, 1920, 3)
+    ms, _ = timeit(lambda: vacv.layout_change(bgr, vacv.NHWC, vacv.NCHW), iters)
+    report("op layout hwc->chw u8 1080p x128", ms, b * 1920 * 1080, b * 1920 * 1080 * 6)
+    chw = vacv.layout_change(bgr, vacv.NHWC, vacv.NCHW)
+    ms, _ = timeit(lambda: vacv.layout_change(chw, vacv.NCHW, vacv.NHWC), iters)
+    report("op layout chw->hwc u8 1080p x128", ms, b * 1920 * 1080, b * 1920 * 1080 * 6)
+    f = torch.rand((32, 1080, 1920, 3), device="cuda") * 255
+    ms, _ = timeit(lambda: vacv.layout_change(f, vacv.NHWC, vacv.NCHW), iters)
+    report("op layout hwc->chw f32 1080p x32", ms, 32 * 1920 * 1080, 32 * 1920 * 1080 * 24)
+    ms, _ = timeit(lambda: vacv.dtype_change(bgr, vacv.FP32), iters)
+    report("op dtype u8->f32 1080p x128", ms, b * 1920 * 1080, b * 1920 * 1080 * 15)
+    ms, _ = timeit(lambda: vacv.dtype_change(f, vacv.INT8), iters)
+    report("op dtype f32->u8 1080p x32", ms, 32 * 1920 * 1080, 32 * 1920 * 1080 * 15)
+    mean, std = stats()
+    ms, _ = timeit(lambda: vacv.normalize(f, vacv.NHWC, mean, std), iters)
+    report("op normalize f32 hwc 1080p x32", ms, 32 * 1920 * 1080, 32 * 1920 * 1080 * 24)
+    ms, _ = timeit(lambda: vacv.crop(bgr, vacv.NHWC, 321, 181, 1280, 720), iters)
+    report("op crop u8 hwc 1080p->1280x720 @(321,181) x128", ms, b * 1280 * 720, b * 1280 * 720 * 6)
+    big = rand_u8(64, 1440, 2560, 3)
+    ms, _ = timeit(lambda: vacv.resize(big, vacv.NHWC, 320, 180), iters)
+    report("op resize linear u8 2560x1440->320x180 x64", ms, 64 * 320 * 180, 64 * (2560 * 1440 * 3 // 4 + 320 * 180 * 3), "bytes: 2 of 8 rows touched")
+    ms, _ = timeit(lambda: vacv.resize_normalize(bgr, 640, 640, mean, std, vacv.NCHW), iters)
+    report("op resize_normalize u8 hwc 1080p->640x640 chw x128", ms, b * 640 * 640, b * (1920 * 1080 * 3 + 640 * 640 * 12))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="all")
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--json", default=None)
+    args = ap.parse_args()
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
+    wl = args.workload
+    if wl in ("all", "c2"):
+        c2(args.iters)
+    if wl in ("all", "c2g"):   # general (non-integer-ratio) shapes of the fused kernel
+        c2(args.iters, 608, 608, tag="c2g")
+        c2(args.iters, 640, 640, 1280, 720, tag="c2g")
+        c2(args.iters, 416, 416, tag="c2g")
+        c2_unfused(args.iters)
+    if wl in ("all", "c1"):
+        c1(args.iters)
+    if wl in ("all", "c3"):
+        c3(args.iters)
+    if wl in ("all", "c4"):
+        c4(args.iters)
+    if wl in ("all", "ops"):
+        ops(args.iters)
+    if wl in ("all", "c5"):
+        c5(max(3, args.iters // 4))
+    if args.json and int(os.environ.get("RANK", 0)) == 0:
+        with open(args.json, "a") as f:
+            for r in RESULTS:
+                f.write(json.dumps(r) + "\n")
+
+
+if __name__ == "__main__":
+    main()

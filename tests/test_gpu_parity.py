@@ -140,14 +140,19 @@ LIN_SIZES = [((64, 48), (20, 16)), ((64, 48), (200, 111)), ((1920, 1080), (640, 
              ((333, 211), (500, 300)), ((2, 2), (7, 5)), ((640, 360), (639, 359)), ((2560, 1440), (320, 180))]
 
 
+# every resize case runs through both implementations: shared-memory tiled (default) and direct global gather
+PATHS = [0x200, 0x100]
+
+
+@pytest.mark.parametrize("path", PATHS)
 @pytest.mark.parametrize("layout", [NHWC, NCHW])
 @pytest.mark.parametrize("sz", LIN_SIZES)
-def test_resize_linear_u8(vacv, oracle, layout, sz):
+def test_resize_linear_u8(vacv, oracle, layout, sz, path):
     (w, h), (wo, ho) = sz
     b, c = 2, 3
     shape = (b, h, w, c) if layout == NHWC else (b, c, h, w)
     src = u8(6, *shape)
-    got = host(vacv.resize(dev(src), layout, wo, ho, vacv.INTER_LINEAR))
+    got = host(vacv.resize(dev(src), layout, wo, ho, vacv.INTER_LINEAR, path))
     want = np.stack([oracle.resize_linear(src[i], w, h, c, layout, wo, ho) for i in range(b)])
     assert_same(got, want)
 
@@ -161,26 +166,28 @@ def test_resize_linear_u8_config1_fixture_vs_reference(vacv):
     assert_same(got, want)
 
 
-def test_resize_linear_u8_flags(vacv, oracle):
+@pytest.mark.parametrize("path", PATHS)
+def test_resize_linear_u8_flags(vacv, oracle, path):
     w, h, c, wo, ho = 333, 211, 3, 200, 100
     src = u8(7, 1, h, w, c)
-    got = host(vacv.resize(dev(src), NHWC, wo, ho, vacv.INTER_LINEAR, vacv.FLAG_SIGNED_CHAR))[0]
+    got = host(vacv.resize(dev(src), NHWC, wo, ho, vacv.INTER_LINEAR, vacv.FLAG_SIGNED_CHAR | path))[0]
     assert_same(got, oracle.resize_linear(src[0], w, h, c, NHWC, wo, ho, signed_char=1))
-    got = host(vacv.resize(dev(src), NHWC, wo, ho, vacv.INTER_LINEAR, vacv.FLAG_NEON_RULE))[0]
+    got = host(vacv.resize(dev(src), NHWC, wo, ho, vacv.INTER_LINEAR, vacv.FLAG_NEON_RULE | path))[0]
     assert_same(got, oracle.resize_linear_neon_rule(src[0], w, h, c, NHWC, wo, ho))
     chw = np.ascontiguousarray(src.transpose(0, 3, 1, 2))
-    got = host(vacv.resize(dev(chw), NCHW, wo, ho, vacv.INTER_LINEAR, vacv.FLAG_NEON_RULE))[0]
+    got = host(vacv.resize(dev(chw), NCHW, wo, ho, vacv.INTER_LINEAR, vacv.FLAG_NEON_RULE | path))[0]
     assert_same(got, oracle.resize_linear_neon_rule(chw[0], w, h, c, NCHW, wo, ho))
 
 
+@pytest.mark.parametrize("path", PATHS)
 @pytest.mark.parametrize("layout", [NHWC, NCHW])
 @pytest.mark.parametrize("sz", LIN_SIZES[:5] + [((2560, 1440), (320, 180))])
-def test_resize_linear_f32(vacv, oracle, layout, sz):
+def test_resize_linear_f32(vacv, oracle, layout, sz, path):
     (w, h), (wo, ho) = sz
     b, c = 1, 3
     shape = (b, h, w, c) if layout == NHWC else (b, c, h, w)
     src = f32(8, *shape)
-    got = host(vacv.resize(dev(src), layout, wo, ho, vacv.INTER_LINEAR))
+    got = host(vacv.resize(dev(src), layout, wo, ho, vacv.INTER_LINEAR, path))
     want = np.stack([oracle.resize_linear(src[i], w, h, c, layout, wo, ho) for i in range(b)])
     assert_same(got, want)
 
@@ -194,12 +201,13 @@ def test_resize_same_size_is_copy(vacv):
 @pytest.mark.parametrize("layout", [NHWC, NCHW])
 @pytest.mark.parametrize("sz", [((64, 48), (37, 20)), ((64, 48), (20, 37)), ((2560, 1440), (1920, 1080)),
                                 ((320, 180), (640, 360)), ((16, 16), (5, 9)), ((64, 48), (100, 100))])
-def test_resize_cubic_f32(vacv, oracle, layout, sz):
+@pytest.mark.parametrize("path", PATHS)
+def test_resize_cubic_f32(vacv, oracle, layout, sz, path):
     (w, h), (wo, ho) = sz
     c = 3
     shape = (1, h, w, c) if layout == NHWC else (1, c, h, w)
     src = f32(10, *shape)
-    got = host(vacv.resize(dev(src), layout, wo, ho, vacv.INTER_CUBIC))[0]
+    got = host(vacv.resize(dev(src), layout, wo, ho, vacv.INTER_CUBIC, path))[0]
     want = oracle.resize_cubic_f32(src[0], w, h, c, layout, wo, ho)
     assert_same(got, want)
 
@@ -208,12 +216,13 @@ def test_resize_cubic_f32(vacv, oracle, layout, sz):
 @pytest.mark.parametrize("sz", [((2560, 1440), (1920, 1080)), ((256, 144), (100, 70)), ((176, 144), (640, 640)),
                                 ((257, 145), (300, 171)), ((64, 48), (333, 77)), ((64, 48), (21, 13)),
                                 ((8, 8), (3, 3)), ((5, 4), (13, 11))])
-def test_resize_cubic_u8(vacv, oracle, c, sz):
+@pytest.mark.parametrize("path", PATHS)
+def test_resize_cubic_u8(vacv, oracle, c, sz, path):
     (w, h), (wo, ho) = sz
     if c != 3 and w > 1000:
         pytest.skip("big case only for c=3")
     src = u8(11 + c, 2, h, w, c)
-    got = host(vacv.resize(dev(src), NHWC, wo, ho, vacv.INTER_CUBIC))
+    got = host(vacv.resize(dev(src), NHWC, wo, ho, vacv.INTER_CUBIC, path))
     want = np.stack([oracle.resize_cubic_u8(src[i], w, h, c, wo, ho) for i in range(2)])
     assert_same(got, want)
 
