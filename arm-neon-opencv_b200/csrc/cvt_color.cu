@@ -20,9 +20,9 @@ __device__ __forceinline__ void convert16(const uint4& y, const ChromaTerms (&t)
     for (int i = 0; i < 16; ++i) {
         int Y = (yw[i >> 2] >> (8 * (i & 3))) & 0xff;
         const ChromaTerms& c = t[i >> 1];
-        px[3 * i + 0] = (uint8_t)clamp255(Y + c.ba);
-        px[3 * i + 1] = (uint8_t)clamp255(Y - c.ga);
-        px[3 * i + 2] = (uint8_t)clamp255(Y + c.ra);
+        px[3 * i + 0] = (uint8_t)add_clamp255(Y, c.ba);
+        px[3 * i + 1] = (uint8_t)add_clamp255(Y, -c.ga);
+        px[3 * i + 2] = (uint8_t)add_clamp255(Y, c.ra);
     }
 #pragma unroll
     for (int j = 0; j < 12; ++j) out[j] = pack4(px[4 * j], px[4 * j + 1], px[4 * j + 2], px[4 * j + 3]);
@@ -99,9 +99,9 @@ __global__ void nv2bgr_quad_kernel(const uint8_t* __restrict__ src, uint8_t* __r
         for (int x = 0; x < 2; ++x) {
             size_t p = (size_t)(2 * qy + r) * w + 2 * qx + x;
             int Y = f[p];
-            o[3 * p + 0] = (uint8_t)clamp255(Y + t.ba);
-            o[3 * p + 1] = (uint8_t)clamp255(Y - t.ga);
-            o[3 * p + 2] = (uint8_t)clamp255(Y + t.ra);
+            o[3 * p + 0] = (uint8_t)add_clamp255(Y, t.ba);
+            o[3 * p + 1] = (uint8_t)add_clamp255(Y, -t.ga);
+            o[3 * p + 2] = (uint8_t)add_clamp255(Y, t.ra);
         }
 }
 

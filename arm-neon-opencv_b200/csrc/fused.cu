@@ -19,6 +19,7 @@
 #include "vacv_common.cuh"
 #include "fused_pipeline.cuh"
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 namespace vacv {
@@ -39,9 +40,9 @@ __device__ __forceinline__ void hrow(const uint8_t* __restrict__ yrow, const uin
     const unsigned pb = *reinterpret_cast<const uint16_t*>(crow + cb);
     const ChromaTerms ta = kVFirst ? chroma_terms(pa & 0xff, pa >> 8) : chroma_terms(pa >> 8, pa & 0xff);
     const ChromaTerms tb = kVFirst ? chroma_terms(pb & 0xff, pb >> 8) : chroma_terms(pb >> 8, pb & 0xff);
-    H[0] = clamp255(Y0 + ta.ba) * cx0 + clamp255(Y1 + tb.ba) * cx1;
-    H[1] = clamp255(Y0 - ta.ga) * cx0 + clamp255(Y1 - tb.ga) * cx1;
-    H[2] = clamp255(Y0 + ta.ra) * cx0 + clamp255(Y1 + tb.ra) * cx1;
+    H[0] = add_clamp255(Y0, ta.ba) * cx0 + add_clamp255(Y1, tb.ba) * cx1;
+    H[1] = add_clamp255(Y0, -ta.ga) * cx0 + add_clamp255(Y1, -tb.ga) * cx1;
+    H[2] = add_clamp255(Y0, ta.ra) * cx0 + add_clamp255(Y1, tb.ra) * cx1;
 }
 
 template <bool kVFirst>
@@ -243,8 +244,26 @@ static int try_launch_pipe(const uint8_t* src, float* dst, int batch, int w, int
     const long long total = (long long)g.tiles_per_frame * batch;
     if (total > 0x7fffffffLL - 4096) return 0;
     g.total_tiles = (int)total;
-    const int ncol = (w_out + kPipeThreads - 1) / kPipeThreads;
-    const int threads = std::min(kPipeThreads, ((w_out + ncol - 1) / ncol + 31) & ~31);
+    // Columns per thread.  Measured on B200 (bench_ops.py c2/c2g): when some right tap has weight (general ratios) the
+    // loop is issue-bound and 4 columns per thread (more ILP, less per-row overhead) win; when every cx1 is 0 (odd
+    // integer x ratio) the kernel is HBM-bound and 2 columns per thread (twice the warps) win.
+    bool any_right = false;
+    {
+        const double scale_x = (double)((float)w / (float)w_out);
+        for (int d = 0; d < w_out && !any_right; ++d) {
+            float fx = (float)(((double)d + 0.5) * scale_x - 0.5);
+            int sx = (int)floorf(fx);
+            fx -= (float)sx;
+            if (sx < 0) fx = 0.f;
+            if (sx >= w - 1) fx = 1.f;
+            const float x = 2048.f * fx;
+            any_right = (int)(x + (x >= 0.f ? 0.5f : -0.5f)) != 0;
+        }
+    }
+    int ncol = (w_out + kPipeThreads - 1) / kPipeThreads;
+    if (any_right && w_out <= 4 * 192) ncol = 4;
+    if (const char* e = getenv("VACV_PIPE_NCOL")) { const int v = atoi(e); if (v >= 1 && v <= kPipeMaxCols && (w_out + v - 1) / v <= (v == 1 ? 640 : kPipeThreads)) ncol = v; }   // tuning knob
+    const int threads = std::min(ncol == 1 ? 640 : kPipeThreads, ((w_out + ncol - 1) / ncol + 31) & ~31);
     const void* kern = v_first ? pipe_kernel_for<true>(ncol) : pipe_kernel_for<false>(ncol);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)best_smem);
     if (e != cudaSuccess) return set_error(VACV_ERR_CUDA, "nv_resize_normalize_chw: %s", cudaGetErrorString(e));

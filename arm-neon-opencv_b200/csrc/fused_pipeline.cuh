@@ -77,13 +77,13 @@ __device__ __forceinline__ void hrow_cached(uint32_t yaddr, const ColState& c, c
     const int Y0 = lds_u8(yaddr);
     if (kRightTap) {
         const int Y1 = lds_u8(yaddr + 1);
-        H[0] = clamp255(Y0 + ta.ba) * c.cx0 + clamp255(Y1 + tb.ba) * c.cx1;
-        H[1] = clamp255(Y0 - ta.ga) * c.cx0 + clamp255(Y1 - tb.ga) * c.cx1;
-        H[2] = clamp255(Y0 + ta.ra) * c.cx0 + clamp255(Y1 + tb.ra) * c.cx1;
+        H[0] = add_clamp255(Y0, ta.ba) * c.cx0 + add_clamp255(Y1, tb.ba) * c.cx1;
+        H[1] = add_clamp255(Y0, -ta.ga) * c.cx0 + add_clamp255(Y1, -tb.ga) * c.cx1;
+        H[2] = add_clamp255(Y0, ta.ra) * c.cx0 + add_clamp255(Y1, tb.ra) * c.cx1;
     } else {   // every cx1 of this launch is 0 (odd integer x ratio): the right tap contributes p*0
-        H[0] = clamp255(Y0 + ta.ba) * c.cx0;
-        H[1] = clamp255(Y0 - ta.ga) * c.cx0;
-        H[2] = clamp255(Y0 + ta.ra) * c.cx0;
+        H[0] = add_clamp255(Y0, ta.ba) * c.cx0;
+        H[1] = add_clamp255(Y0, -ta.ga) * c.cx0;
+        H[2] = add_clamp255(Y0, ta.ra) * c.cx0;
     }
 }
 
@@ -140,7 +140,7 @@ __device__ __forceinline__ void compute_tile(uint32_t ybuf, uint32_t cbuf, uint3
 }
 
 template <bool kVFirst, int NCOL>
-__global__ void __launch_bounds__(kPipeThreads, 2)
+__global__ void __launch_bounds__(NCOL == 1 ? 640 : kPipeThreads, NCOL <= 2 ? 2 : 1)
 nv_resize_normalize_chw_pipe_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, PipeGeom g,
                                     const float* __restrict__ mean, const float* __restrict__ stddev) {
     extern __shared__ __align__(128) uint8_t dyn_smem[];     // [s_sy: ho][s_cy: ho][pad] 2 x (ystage + cstage)

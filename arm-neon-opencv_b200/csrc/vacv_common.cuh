@@ -94,5 +94,7 @@ __device__ __forceinline__ ChromaTerms chroma_terms(int v, int u) {
     return t;
 }
 __device__ __forceinline__ int clamp255(int v) { return min(max(v, 0), 255); }
+// clamp(a + b, 0, 255) in one DPX instruction (SASS: VIADDMNMX.RELU)
+__device__ __forceinline__ int add_clamp255(int a, int b) { return __viaddmin_s32_relu(a, b, 255); }
 
 }  // namespace vacv
