@@ -7,8 +7,8 @@ namespace vacv {
 
 // ----------------------------------------------------------------------------------------------------
 // a8 bicubic fp32 (resize_naive.cpp:130-185 coefficients with border folding; :230,:345 accumulation order)
-__device__ __forceinline__ void cubic_naive(int d, int n_in, int n_out, int& ofs, float (&a)[4]) {
-    const double scale = (double)n_in / (double)n_out;
+// scale = (double)n_in / n_out (resize_naive.cpp:144)
+__device__ __forceinline__ void cubic_naive_scaled(int d, int n_in, double scale, int& ofs, float (&a)[4]) {
     float fx = (float)(((double)d + 0.5) * scale - 0.5);
     int sx = (int)floorf(fx);
     fx -= (float)sx;
@@ -23,6 +23,9 @@ __device__ __forceinline__ void cubic_naive(int d, int n_in, int n_out, int& ofs
     if (sx == n_in - 2) { sx = n_in - 3; a[3] = a[2] + a[3]; a[2] = a[1]; a[1] = a[0]; a[0] = 0.f; }
     if (sx >= n_in - 1) { sx = n_in - 3; a[3] = 1.f - a[0]; a[2] = a[0]; a[1] = 0.f; a[0] = 0.f; }
     ofs = sx;
+}
+__device__ __forceinline__ void cubic_naive(int d, int n_in, int n_out, int& ofs, float (&a)[4]) {
+    cubic_naive_scaled(d, n_in, (double)n_in / (double)n_out, ofs, a);
 }
 
 
@@ -42,8 +45,7 @@ __device__ __forceinline__ int sat_short_rhe(float v) { return max(min(__float2i
 
 // OpenCV 2.4.13 cubic source index / fixed-point taps for one output coordinate: scale = 1/(n_out/n_in)
 // in double; the [0, n_in-1] clamp of (s, f) is applied along x only.
-__device__ __forceinline__ void cubic_cv_coord(int d, int n_in, int n_out, bool is_x, int& s, int (&q)[4]) {
-    const double scale = 1. / ((double)n_out / (double)n_in);
+__device__ __forceinline__ void cubic_cv_coord_scaled(int d, int n_in, double scale, bool is_x, int& s, int (&q)[4]) {
     float f = (float)(((double)d + 0.5) * scale - 0.5);
     s = (int)floorf(f);
     f -= (float)s;
@@ -55,6 +57,9 @@ __device__ __forceinline__ void cubic_cv_coord(int d, int n_in, int n_out, bool 
     cubic_cv(f, k);
 #pragma unroll
     for (int j = 0; j < 4; ++j) q[j] = sat_short_rhe(k[j] * 2048.f);
+}
+__device__ __forceinline__ void cubic_cv_coord(int d, int n_in, int n_out, bool is_x, int& s, int (&q)[4]) {
+    cubic_cv_coord_scaled(d, n_in, 1. / ((double)n_out / (double)n_in), is_x, s, q);
 }
 
 }  // namespace vacv

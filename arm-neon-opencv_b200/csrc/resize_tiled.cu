@@ -36,6 +36,9 @@ struct TiledGeom {
     int max_slots;            // staged row capacity
     int opitch;               // shared-memory bytes per output row (multiple of 16, >= TWE*es + 16)
     int align;                // staging granularity in bytes: 16, 4 or 1
+    int tiles_per_cta;        // consecutive y tiles walked by one CTA (x coefficients are computed once)
+    int dense;                // 1: vertical scale <= taps, every row of a tile's band is touched -> slot = row - first row
+    double scale_x, scale_y;  // coordinate scales, formed on the host with the reference's expression for the kind
     size_t src_image, dst_image;   // elements between images
 };
 
@@ -49,11 +52,9 @@ template <> struct Kind<kCubU8> { using S = uint8_t; static constexpr int TAPS =
 
 // Tap indices (absolute, along one axis) and coefficients (int, or float bits) of output coordinate d.
 template <int KIND>
-__device__ __forceinline__ void axis_coefs(int d, int n_in, int n_out, bool is_x, int (&idx)[Kind<KIND>::TAPS],
+__device__ __forceinline__ void axis_coefs(int d, int n_in, double scale, bool is_x, int (&idx)[Kind<KIND>::TAPS],
                                            int (&coef)[Kind<KIND>::TAPS]) {
     if constexpr (KIND == kLinU8 || KIND == kLinU8Signed || KIND == kLinU8Neon || KIND == kLinF32) {
-        // naive: fp32 scale (resize_naive.cpp:17-18); NEON rule: fp64 scale (resize_neon.cpp:17-18)
-        const double scale = KIND == kLinU8Neon ? (double)n_in / (double)n_out : (double)((float)n_in / (float)n_out);
         int s; float f;
         linear_coord(d, scale, n_in, s, f);
         idx[0] = s; idx[1] = s + 1;
@@ -61,12 +62,12 @@ __device__ __forceinline__ void axis_coefs(int d, int n_in, int n_out, bool is_x
         else { coef[0] = sat_short((1.f - f) * 2048.f); coef[1] = sat_short(f * 2048.f); }
     } else if constexpr (KIND == kCubF32) {
         int ofs; float a[4];
-        cubic_naive(d, n_in, n_out, ofs, a);
+        cubic_naive_scaled(d, n_in, scale, ofs, a);
 #pragma unroll
         for (int j = 0; j < 4; ++j) { idx[j] = ofs - 1 + j; coef[j] = __float_as_int(a[j]); }
     } else {
         int s, q[4];
-        cubic_cv_coord(d, n_in, n_out, is_x, s, q);
+        cubic_cv_coord_scaled(d, n_in, scale, is_x, s, q);
 #pragma unroll
         for (int j = 0; j < 4; ++j) { idx[j] = min(max(s - 1 + j, 0), n_in - 1); coef[j] = q[j]; }
     }
@@ -86,178 +87,214 @@ __global__ void __launch_bounds__(kRtThreads) resize_tiled_kernel(const void* __
     constexpr int ES = sizeof(S);
     constexpr bool kTwoPass = K == 4;
     extern __shared__ __align__(16) uint8_t smem[];
-    __shared__ int s_yidx[kRtMaxTH][K], s_ycoef[kRtMaxTH][K];
+    __shared__ int s_yidx[kRtMaxTH][K];
+    __shared__ __align__(16) int s_ycoef[kRtMaxTH][4];    // int, or float bits (fp32 kinds; u8 bicubic: (float)ibeta * 2^-22)
+    __shared__ __align__(16) int s_yint[kRtMaxTH][4];     // u8 bicubic: integer ibeta for OpenCV's scalar tail
+    __shared__ __align__(16) int s_yoff[kRtMaxTH][4];     // byte offset of each tap's row inside tile (1-pass) / hbuf (2-pass)
+    __shared__ int s_ooff[kRtMaxTH];                      // byte offset of the row inside obuf (includes its 16-byte phase)
     __shared__ short s_slot[kRtMaxBand];
     __shared__ int s_rows[kRtMaxBand];
     __shared__ int s_x[2], s_nslots;
-    __shared__ float s_yfb[kRtMaxTH][4];   // u8 bicubic: (float)ibeta * 2^-22, the vertical weights of OpenCV's fp32 body
 
-    uint8_t* tile = smem;                                                        // [max_slots][src_pitch]
-    float* hbuf = reinterpret_cast<float*>(smem + (size_t)g.max_slots * g.src_pitch);   // [max_slots][hpitch] (two-pass)
-    uint8_t* obuf = smem + (size_t)g.max_slots * g.src_pitch + (kTwoPass ? (size_t)g.max_slots * g.hpitch * 4 : 0);
+    uint8_t* tile = smem;                                                                 // [max_slots][src_pitch]
+    uint8_t* hbuf = smem + (size_t)g.max_slots * g.src_pitch;                             // [max_slots][hpitch] floats (two-pass)
+    uint8_t* obuf = hbuf + (kTwoPass ? (size_t)g.max_slots * g.hpitch * 4 : 0);          // [TH][opitch]
 
     const int tid = threadIdx.x;
-    const int tile_x = blockIdx.x % g.tiles_x, tile_y = blockIdx.x / g.tiles_x;
-    const int e0 = tile_x * g.TWE, dy0 = tile_y * g.TH;
-    const int twe = min(g.TWE, g.wo * g.c - e0), th = min(g.TH, g.ho - dy0);
+    const int tile_x = blockIdx.x % g.tiles_x, ychunk = blockIdx.x / g.tiles_x;
+    const int e0 = tile_x * g.TWE;
+    const int twe = min(g.TWE, g.wo * g.c - e0);
     const uint8_t* img = reinterpret_cast<const uint8_t*>(src_) + blockIdx.y * g.src_image * ES;
     uint8_t* out_img = reinterpret_cast<uint8_t*>(dst_) + blockIdx.y * g.dst_image * ES;
+    const int row_bytes = g.w * g.c * ES;
+    const size_t out_row_bytes = (size_t)g.wo * g.c * ES;
+    const int seg = twe * ES;
 
-    // ---- coefficients: this thread's element column (registers), the tile's rows (shared)
+    // ---- once per CTA: this thread's element column -> x taps / coefficients in registers, staged column range
     const bool active = tid < twe;
     const int xe = active ? tid : twe - 1;
     const int dxl = xe / g.c, ch = xe - dxl * g.c;
     int xidx[K], xcoef[K];
-    axis_coefs<KIND>(e0 / g.c + dxl, g.w, g.wo, true, xidx, xcoef);
+    axis_coefs<KIND>(e0 / g.c + dxl, g.w, g.scale_x, true, xidx, xcoef);
     if (tid == 0) s_x[0] = xidx[0];
     if (tid == twe - 1) s_x[1] = xidx[K - 1];
-    if (tid < th) {
-        int yi[K], yc[K];
-        axis_coefs<KIND>(dy0 + tid, g.h, g.ho, false, yi, yc);
-#pragma unroll
-        for (int j = 0; j < K; ++j) {
-            s_yidx[tid][j] = yi[j]; s_ycoef[tid][j] = yc[j];
-            if constexpr (KIND == kCubU8) s_yfb[tid][j] = (float)yc[j] * (1.f / (2048 * 2048));
-        }
-    }
     __syncthreads();
-
-    // ---- which source rows does the tile touch?  row -> slot
-    const int y_lo = s_yidx[0][0], band = s_yidx[th - 1][K - 1] - y_lo + 1;
-    for (int r = tid; r < band; r += kRtThreads) s_slot[r] = -1;
-    __syncthreads();
-    for (int i = tid; i < th * K; i += kRtThreads) s_slot[s_yidx[i / K][i % K] - y_lo] = 0;
-    __syncthreads();
-    if (tid == 0) {
-        int n = 0;
-        for (int r = 0; r < band; ++r)
-            if (s_slot[r] == 0) { s_slot[r] = (short)n; s_rows[n] = y_lo + r; ++n; }
-        s_nslots = n;
-    }
-    __syncthreads();
-    const int nslots = s_nslots;
-
-    // ---- stage the touched rows, columns [x_lo, x_hi], at the widest legal granularity
-    const int row_bytes = g.w * g.c * ES;
     const int xb0 = s_x[0] * g.c * ES, xb1 = (s_x[1] + 1) * g.c * ES;
     const int xb0a = xb0 & ~(g.align - 1);
     const int width = ((xb1 + g.align - 1) & ~(g.align - 1)) - xb0a;
-    if (g.align == 16) {
-        const int units = width >> 4;
-        for (int i = tid; i < nslots * units; i += kRtThreads) {
-            const int r = i / units, u = i - r * units;
-            *reinterpret_cast<uint4*>(tile + r * g.src_pitch + 16 * u) = ld_stream16(img + (size_t)s_rows[r] * row_bytes + xb0a + 16 * u);
-        }
-    } else if (g.align == 4) {
-        const int units = width >> 2;
-        for (int i = tid; i < nslots * units; i += kRtThreads) {
-            const int r = i / units, u = i - r * units;
-            *reinterpret_cast<uint32_t*>(tile + r * g.src_pitch + 4 * u) = __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)s_rows[r] * row_bytes + xb0a) + u);
-        }
-    } else {
-        for (int i = tid; i < nslots * width; i += kRtThreads) {
-            const int r = i / width, u = i - r * width;
-            tile[r * g.src_pitch + u] = __ldg(img + (size_t)s_rows[r] * row_bytes + xb0a + u);
-        }
-    }
-    __syncthreads();
-
     int toff[K];   // byte offset of each x tap of this thread's element inside a staged row
 #pragma unroll
     for (int j = 0; j < K; ++j) toff[j] = (xidx[j] * g.c + ch) * ES - xb0a;
+    const int vec_end = (g.wo * g.c) & ~7;   // OpenCV's SSE2 body covers x < (width & ~7)
+    const bool in_vec_body = e0 + tid < vec_end;
 
-    // ---- pass 1 (bicubic): horizontal sums per staged row
-    if constexpr (kTwoPass) {
-        if (active) {
-            for (int s = 0; s < nslots; ++s) {
-                const uint8_t* row = tile + s * g.src_pitch;
-                float hval;
-                if constexpr (KIND == kCubF32) {   // resize_naive.cpp:230: S[-1]*a0 + S[0]*a1 + S[1]*a2 + S[2]*a3, left to right
-                    const float t0 = *reinterpret_cast<const float*>(row + toff[0]), t1 = *reinterpret_cast<const float*>(row + toff[1]);
-                    const float t2 = *reinterpret_cast<const float*>(row + toff[2]), t3 = *reinterpret_cast<const float*>(row + toff[3]);
-                    hval = t0 * __int_as_float(xcoef[0]) + t1 * __int_as_float(xcoef[1]) + t2 * __int_as_float(xcoef[2]) +
-                           t3 * __int_as_float(xcoef[3]);
-                } else {
-                    const int hi = row[toff[0]] * xcoef[0] + row[toff[1]] * xcoef[1] + row[toff[2]] * xcoef[2] + row[toff[3]] * xcoef[3];
-                    hval = int_to_float_exact(hi);
+    for (int t = 0; t < g.tiles_per_cta; ++t) {
+        const int tile_y = ychunk * g.tiles_per_cta + t;
+        if (tile_y >= g.tiles_y) break;
+        const int dy0 = tile_y * g.TH, th = min(g.TH, g.ho - dy0);
+
+        // ---- row taps / coefficients of the tile
+        if (tid < th) {
+            int yi[K], yc[K];
+            axis_coefs<KIND>(dy0 + tid, g.h, g.scale_y, false, yi, yc);
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                s_yidx[tid][j] = yi[j];
+                if constexpr (KIND == kCubU8) { s_ycoef[tid][j] = __float_as_int((float)yc[j] * (1.f / (2048 * 2048))); s_yint[tid][j] = yc[j]; }
+                else s_ycoef[tid][j] = yc[j];
+            }
+            const uintptr_t ga = reinterpret_cast<uintptr_t>(out_img) + (size_t)(dy0 + tid) * out_row_bytes + (size_t)e0 * ES;
+            s_ooff[tid] = tid * g.opitch + (int)(ga & 15);
+        }
+        __syncthreads();
+
+        // ---- which source rows does the tile touch?  row -> slot
+        const int y_lo = s_yidx[0][0], band = s_yidx[th - 1][K - 1] - y_lo + 1;
+        int nslots;
+        if (g.dense) {   // consecutive tap windows leave no gaps: the band IS the slot list
+            nslots = band;
+            for (int i = tid; i < th * K; i += kRtThreads)
+                s_yoff[i / K][i % K] = (s_yidx[i / K][i % K] - y_lo) * (kTwoPass ? g.hpitch * 4 : g.src_pitch);
+        } else {         // large vertical down-scale: stage only the rows some tap touches
+            for (int r = tid; r < band; r += kRtThreads) s_slot[r] = -1;
+            __syncthreads();
+            for (int i = tid; i < th * K; i += kRtThreads) s_slot[s_yidx[i / K][i % K] - y_lo] = 0;
+            __syncthreads();
+            if (tid < 32) {   // warp 0: slot = number of touched rows below (ballot + popc prefix)
+                int base = 0;
+                for (int r0 = 0; r0 < band; r0 += 32) {
+                    const int r = r0 + tid;
+                    const bool used = r < band && s_slot[r] == 0;
+                    const unsigned m = __ballot_sync(0xffffffffu, used);
+                    if (used) {
+                        const int slot = base + __popc(m & ((1u << tid) - 1));
+                        s_slot[r] = (short)slot;
+                        s_rows[slot] = y_lo + r;
+                    }
+                    base += __popc(m);
                 }
-                hbuf[s * g.hpitch + tid] = hval;
+                if (tid == 0) s_nslots = base;
+            }
+            __syncthreads();
+            nslots = s_nslots;
+            for (int i = tid; i < th * K; i += kRtThreads)
+                s_yoff[i / K][i % K] = s_slot[s_yidx[i / K][i % K] - y_lo] * (kTwoPass ? g.hpitch * 4 : g.src_pitch);
+        }
+        const int row0 = g.dense ? y_lo : 0;   // dense: staged row r is source row y_lo + r
+
+        // ---- stage the touched rows, columns [x_lo, x_hi], at the widest legal granularity
+        if (g.align == 16) {
+            const int units = width >> 4;
+            for (int i = tid; i < nslots * units; i += kRtThreads) {
+                const int r = i / units, u = i - r * units;
+                *reinterpret_cast<uint4*>(tile + r * g.src_pitch + 16 * u) = ld_stream16(img + (size_t)(g.dense ? row0 + r : s_rows[r]) * row_bytes + xb0a + 16 * u);
+            }
+        } else if (g.align == 4) {
+            const int units = width >> 2;
+            for (int i = tid; i < nslots * units; i += kRtThreads) {
+                const int r = i / units, u = i - r * units;
+                *reinterpret_cast<uint32_t*>(tile + r * g.src_pitch + 4 * u) = __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)(g.dense ? row0 + r : s_rows[r]) * row_bytes + xb0a) + u);
+            }
+        } else {
+            for (int i = tid; i < nslots * width; i += kRtThreads) {
+                const int r = i / width, u = i - r * width;
+                tile[r * g.src_pitch + u] = __ldg(img + (size_t)(g.dense ? row0 + r : s_rows[r]) * row_bytes + xb0a + u);
             }
         }
         __syncthreads();
-    }
 
-    // ---- pass 2: one output row at a time into the output tile
-    // row r of the tile goes to global bytes [ga, ga + twe*ES); it is laid out in shared memory with the same 16-byte phase
-    const size_t out_row_bytes = (size_t)g.wo * g.c * ES;
-    if (active) {
-        const int vec_end = (g.wo * g.c) & ~7;   // OpenCV's SSE2 body covers x < (width & ~7)
-        for (int ty = 0; ty < th; ++ty) {
-            const uintptr_t ga = reinterpret_cast<uintptr_t>(out_img) + (size_t)(dy0 + ty) * out_row_bytes + (size_t)e0 * ES;
-            S* o = reinterpret_cast<S*>(obuf + ty * g.opitch + (ga & 15)) + tid;
-            int slot[K];
-#pragma unroll
-            for (int j = 0; j < K; ++j) slot[j] = s_slot[s_yidx[ty][j] - y_lo];
-            if constexpr (KIND == kLinU8 || KIND == kLinU8Signed || KIND == kLinU8Neon) {
-                constexpr bool kS = KIND == kLinU8Signed;
-                const uint8_t* r0 = tile + slot[0] * g.src_pitch;
-                const uint8_t* r1 = tile + slot[1] * g.src_pitch;
-                const int p00 = pix<kS>(r0[toff[0]]), p01 = pix<kS>(r0[toff[1]]), p10 = pix<kS>(r1[toff[0]]), p11 = pix<kS>(r1[toff[1]]);
-                const int cx0 = xcoef[0], cx1 = xcoef[1], cy0 = s_ycoef[ty][0], cy1 = s_ycoef[ty][1];
-                int v;
-                if constexpr (KIND == kLinU8Neon) {   // resize_neon.cpp:145-181
-                    const int h0 = (short)((p00 * cx0 + p01 * cx1) >> 4), h1 = (short)((p10 * cx0 + p11 * cx1) >> 4);
-                    v = clamp255(((short)((cy0 * h0) >> 16) + (short)((cy1 * h1) >> 16) + 2) >> 2);
-                } else {                              // resize_naive.cpp:60-65
-                    v = (p00 * cx0 * cy0 + p10 * cx0 * cy1 + p01 * cx1 * cy0 + p11 * cx1 * cy1) >> 22;
-                }
-                *o = (uint8_t)v;
-            } else if constexpr (KIND == kLinF32) {   // resize_naive.cpp:121-124 evaluation order
-                const uint8_t* r0 = tile + slot[0] * g.src_pitch;
-                const uint8_t* r1 = tile + slot[1] * g.src_pitch;
-                const float lt = *reinterpret_cast<const float*>(r0 + toff[0]), rt = *reinterpret_cast<const float*>(r0 + toff[1]);
-                const float lb = *reinterpret_cast<const float*>(r1 + toff[0]), rb = *reinterpret_cast<const float*>(r1 + toff[1]);
-                const float cx0 = __int_as_float(xcoef[0]), cx1 = __int_as_float(xcoef[1]);
-                const float cy0 = __int_as_float(s_ycoef[ty][0]), cy1 = __int_as_float(s_ycoef[ty][1]);
-                *o = lt * cx0 * cy0 + lb * cx0 * cy1 + rt * cx1 * cy0 + rb * cx1 * cy1;
-            } else {
-                const float h0 = hbuf[slot[0] * g.hpitch + tid], h1 = hbuf[slot[1] * g.hpitch + tid];
-                const float h2 = hbuf[slot[2] * g.hpitch + tid], h3 = hbuf[slot[3] * g.hpitch + tid];
-                if constexpr (KIND == kCubF32) {      // resize_naive.cpp:345
-                    *o = h0 * __int_as_float(s_ycoef[ty][0]) + h1 * __int_as_float(s_ycoef[ty][1]) +
-                         h2 * __int_as_float(s_ycoef[ty][2]) + h3 * __int_as_float(s_ycoef[ty][3]);
-                } else {
-                    const int b0 = s_ycoef[ty][0], b1 = s_ycoef[ty][1], b2 = s_ycoef[ty][2], b3 = s_ycoef[ty][3];
-                    int v;
-                    if (e0 + tid < vec_end) {         // fp32 body: mul, then add, one rounding each; cvtps2dq; packs; packus
-                        float f = h0 * s_yfb[ty][0];
-                        f = f + h1 * s_yfb[ty][1];
-                        f = f + h2 * s_yfb[ty][2];
-                        f = f + h3 * s_yfb[ty][3];
-                        v = max(min(float_to_int_rhe(f), 32767), -32768);
-                    } else {                          // scalar tail: FixedPtCast<int, uchar, 22>
-                        v = (__float2int_rn(h0) * b0 + __float2int_rn(h1) * b1 + __float2int_rn(h2) * b2 + __float2int_rn(h3) * b3 + (1 << 21)) >> 22;
+        // ---- pass 1 (bicubic): horizontal sums per staged row
+        if constexpr (kTwoPass) {
+            if (active) {
+                const uint8_t* r0 = tile + toff[0];
+                const uint8_t* r1 = tile + toff[1];
+                const uint8_t* r2 = tile + toff[2];
+                const uint8_t* r3 = tile + toff[3];
+                float* hp = reinterpret_cast<float*>(hbuf) + tid;
+#pragma unroll 4
+                for (int s = 0; s < nslots; ++s) {
+                    float hval;
+                    if constexpr (KIND == kCubF32) {   // resize_naive.cpp:230: S[-1]*a0 + S[0]*a1 + S[1]*a2 + S[2]*a3, left to right
+                        hval = *reinterpret_cast<const float*>(r0) * __int_as_float(xcoef[0]) + *reinterpret_cast<const float*>(r1) * __int_as_float(xcoef[1]) +
+                               *reinterpret_cast<const float*>(r2) * __int_as_float(xcoef[2]) + *reinterpret_cast<const float*>(r3) * __int_as_float(xcoef[3]);
+                    } else {
+                        hval = int_to_float_exact(*r0 * xcoef[0] + *r1 * xcoef[1] + *r2 * xcoef[2] + *r3 * xcoef[3]);
                     }
-                    *o = (uint8_t)clamp255(v);
+                    *hp = hval;
+                    r0 += g.src_pitch; r1 += g.src_pitch; r2 += g.src_pitch; r3 += g.src_pitch;
+                    hp += g.hpitch;
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---- pass 2: one output row at a time into the output tile (same 16-byte phase as its global destination)
+        if (active) {
+            for (int ty = 0; ty < th; ++ty) {
+                const int4 yo = *reinterpret_cast<const int4*>(s_yoff[ty]);
+                const int4 yc = *reinterpret_cast<const int4*>(s_ycoef[ty]);
+                S* o = reinterpret_cast<S*>(obuf + s_ooff[ty]) + tid;
+                if constexpr (KIND == kLinU8 || KIND == kLinU8Signed || KIND == kLinU8Neon) {
+                    constexpr bool kS = KIND == kLinU8Signed;
+                    const uint8_t* r0 = tile + yo.x;
+                    const uint8_t* r1 = tile + yo.y;
+                    const int p00 = pix<kS>(r0[toff[0]]), p01 = pix<kS>(r0[toff[1]]), p10 = pix<kS>(r1[toff[0]]), p11 = pix<kS>(r1[toff[1]]);
+                    const int cx0 = xcoef[0], cx1 = xcoef[1], cy0 = yc.x, cy1 = yc.y;
+                    int v;
+                    if constexpr (KIND == kLinU8Neon) {   // resize_neon.cpp:145-181
+                        const int h0 = (short)((p00 * cx0 + p01 * cx1) >> 4), h1 = (short)((p10 * cx0 + p11 * cx1) >> 4);
+                        v = clamp255(((short)((cy0 * h0) >> 16) + (short)((cy1 * h1) >> 16) + 2) >> 2);
+                    } else {                              // resize_naive.cpp:60-65
+                        v = (p00 * cx0 * cy0 + p10 * cx0 * cy1 + p01 * cx1 * cy0 + p11 * cx1 * cy1) >> 22;
+                    }
+                    *o = (uint8_t)v;
+                } else if constexpr (KIND == kLinF32) {   // resize_naive.cpp:121-124 evaluation order
+                    const uint8_t* r0 = tile + yo.x;
+                    const uint8_t* r1 = tile + yo.y;
+                    const float lt = *reinterpret_cast<const float*>(r0 + toff[0]), rt = *reinterpret_cast<const float*>(r0 + toff[1]);
+                    const float lb = *reinterpret_cast<const float*>(r1 + toff[0]), rb = *reinterpret_cast<const float*>(r1 + toff[1]);
+                    const float cx0 = __int_as_float(xcoef[0]), cx1 = __int_as_float(xcoef[1]);
+                    const float cy0 = __int_as_float(yc.x), cy1 = __int_as_float(yc.y);
+                    *o = lt * cx0 * cy0 + lb * cx0 * cy1 + rt * cx1 * cy0 + rb * cx1 * cy1;
+                } else {
+                    const uint8_t* hb = hbuf + 4 * tid;
+                    const float h0 = *reinterpret_cast<const float*>(hb + yo.x), h1 = *reinterpret_cast<const float*>(hb + yo.y);
+                    const float h2 = *reinterpret_cast<const float*>(hb + yo.z), h3 = *reinterpret_cast<const float*>(hb + yo.w);
+                    const float b0 = __int_as_float(yc.x), b1 = __int_as_float(yc.y), b2 = __int_as_float(yc.z), b3 = __int_as_float(yc.w);
+                    if constexpr (KIND == kCubF32) {      // resize_naive.cpp:345
+                        *o = h0 * b0 + h1 * b1 + h2 * b2 + h3 * b3;
+                    } else {
+                        int v;
+                        if (in_vec_body) {                // fp32 body: mul, then add, one rounding each; cvtps2dq; packs; packus
+                            float f = h0 * b0;
+                            f = f + h1 * b1;
+                            f = f + h2 * b2;
+                            f = f + h3 * b3;
+                            v = max(min(float_to_int_rhe(f), 32767), -32768);
+                        } else {                          // scalar tail: FixedPtCast<int, uchar, 22>
+                            const int4 ib = *reinterpret_cast<const int4*>(s_yint[ty]);
+                            v = (__float2int_rn(h0) * ib.x + __float2int_rn(h1) * ib.y + __float2int_rn(h2) * ib.z + __float2int_rn(h3) * ib.w + (1 << 21)) >> 22;
+                        }
+                        *o = (uint8_t)clamp255(v);
+                    }
                 }
             }
         }
-    }
-    __syncthreads();
+        __syncthreads();
 
-    // ---- copy the output tile out: 16-byte aligned chunks, partial chunks at the row ends byte by byte
-    const int seg = twe * ES;
-    const int chunks_per_row = (seg + 15 + 15) >> 4;   // upper bound incl. phase
-    for (int i = tid; i < th * chunks_per_row; i += kRtThreads) {
-        const int ty = i / chunks_per_row, q = i - ty * chunks_per_row;
-        const uintptr_t ga = reinterpret_cast<uintptr_t>(out_img) + (size_t)(dy0 + ty) * out_row_bytes + (size_t)e0 * ES;
-        const int mis = (int)(ga & 15);
-        const int lo = max(mis, 16 * q), hi = min(mis + seg, 16 * q + 16);
-        if (lo >= hi) continue;
-        const uint8_t* sp = obuf + ty * g.opitch + 16 * q;
-        uint8_t* gp = reinterpret_cast<uint8_t*>(ga - mis) + 16 * q;
-        if (hi - lo == 16) st_stream16(gp, *reinterpret_cast<const uint4*>(sp));
-        else for (int b = lo - 16 * q; b < hi - 16 * q; ++b) gp[b] = sp[b];
+        // ---- copy the output tile out: 16-byte aligned chunks, partial chunks at the row ends byte by byte
+        const int chunks_per_row = (seg + 15 + 15) >> 4;   // upper bound incl. phase
+        for (int i = tid; i < th * chunks_per_row; i += kRtThreads) {
+            const int ty = i / chunks_per_row, q = i - ty * chunks_per_row;
+            const int mis = s_ooff[ty] - ty * g.opitch;
+            const int lo = max(mis, 16 * q), hi = min(mis + seg, 16 * q + 16);
+            if (lo >= hi) continue;
+            const uint8_t* sp = obuf + ty * g.opitch + 16 * q;
+            uint8_t* gp = out_img + (size_t)(dy0 + ty) * out_row_bytes + (size_t)e0 * ES - mis + 16 * q;
+            if (hi - lo == 16) st_stream16(gp, *reinterpret_cast<const uint4*>(sp));
+            else for (int b = lo - 16 * q; b < hi - 16 * q; ++b) gp[b] = sp[b];
+        }
+        __syncthreads();   // tile / hbuf / obuf / row tables are reused by the next y tile
     }
 }
 
@@ -269,8 +306,9 @@ static int launch_tiled_kind(const void* src, void* dst, int images, TiledGeom g
         if (e != cudaSuccess) return set_error(VACV_ERR_CUDA, "resize: %s", cudaGetErrorString(e));
     }
     constexpr int ES = sizeof(typename Kind<KIND>::S);
+    const int ychunks = (g.tiles_y + g.tiles_per_cta - 1) / g.tiles_per_cta;
     for (int i0 = 0; i0 < images; i0 += 65535) {
-        dim3 grid(g.tiles_x * g.tiles_y, std::min(images - i0, 65535));
+        dim3 grid(g.tiles_x * ychunks, std::min(images - i0, 65535));
         kern<<<grid, kRtThreads, smem, s>>>((const uint8_t*)src + (size_t)i0 * g.src_image * ES,
                                             (uint8_t*)dst + (size_t)i0 * g.dst_image * ES, g);
     }
@@ -290,21 +328,29 @@ int try_launch_resize_tiled(int kind, const void* src, void* dst, int images, in
     const size_t row_bytes = (size_t)w * c * es;
     g.align = ((row_bytes % 16) == 0 && ((uintptr_t)src % 16) == 0) ? 16 : ((row_bytes % 4) == 0 && ((uintptr_t)src % 4) == 0) ? 4 : 1;
     const double sx = (double)w / wo, sy = (double)h / ho;
+    // coordinate scales with the reference's expression per kind (host IEEE arithmetic == device, no FMA involved)
+    if (kind == kCubU8) { g.scale_x = 1. / ((double)wo / (double)w); g.scale_y = 1. / ((double)ho / (double)h); }            // OpenCV 2.4
+    else if (kind == kCubF32 || kind == kLinU8Neon) { g.scale_x = (double)w / (double)wo; g.scale_y = (double)h / (double)ho; }  // resize_naive.cpp:144, resize_neon.cpp:17-18
+    else { g.scale_x = (double)((float)w / (float)wo); g.scale_y = (double)((float)h / (float)ho); }                          // resize_naive.cpp:17-18
     const int tw = g.TWE / c;
     const int span_px = std::min(w, (int)(sx * (tw - 1)) + K + 3);
     g.src_pitch = (int)((((size_t)span_px * c * es + 2 * g.align + 15)) & ~(size_t)15);
     g.opitch = (g.TWE * es + 16 + 15) & ~15;
     g.hpitch = (g.TWE + 3) & ~3;
+    g.dense = sy <= (double)K ? 1 : 0;
     const size_t budget = 56 * 1024;
     int TH = kRtMaxTH;
     for (; TH >= 1; --TH) {
         const int band = (int)(sy * (TH - 1)) + K + 3;
-        const int slots = std::min(band, TH * K);
+        const int slots = g.dense ? band : std::min(band, TH * K);
         const size_t smem = (size_t)slots * g.src_pitch + (K == 4 ? (size_t)slots * g.hpitch * 4 : 0) + (size_t)TH * g.opitch;
         if (band <= kRtMaxBand && smem <= budget) {
             g.TH = TH; g.max_slots = slots;
             g.tiles_x = (wo * c + g.TWE - 1) / g.TWE; g.tiles_y = (ho + TH - 1) / TH;
             if ((long long)g.tiles_x * g.tiles_y > 0x7fffffffLL) return 0;
+            // several y tiles per CTA amortise the per-CTA column set-up, but keep >= ~8 CTAs per SM in flight
+            const long long ctas1 = (long long)g.tiles_x * g.tiles_y * images;
+            g.tiles_per_cta = (int)std::max<long long>(1, std::min<long long>(8, ctas1 / (kNumSMs * 8LL)));
             switch (kind) {
                 case kLinU8: return launch_tiled_kind<kLinU8>(src, dst, images, g, smem, s);
                 case kLinU8Signed: return launch_tiled_kind<kLinU8Signed>(src, dst, images, g, smem, s);
