@@ -17,6 +17,7 @@
 #include <algorithm>
 
 #include "resize_coeffs.cuh"
+#include "resize_cubic3.cuh"
 #include "vacv_common.cuh"
 
 namespace vacv {
@@ -298,6 +299,281 @@ __global__ void __launch_bounds__(kRtThreads) resize_tiled_kernel(const void* __
     }
 }
 
+// =====================================================================================================
+// Bicubic, 3-channel interleaved (the C4 shape): PIXEL-per-thread variant.  The element-per-thread kernel above is
+// bound by shared-memory instructions (ncu: LSU wavefronts 84 % of peak, profiles/r1_cubic_u8_tiled_v2_ncu_raw.txt);
+// here a thread owns all 3 channels of one output column, so
+//   pass 1 reads the 12 contiguous tap bytes of a pixel as four aligned words + funnel shifts (4 loads instead of 12)
+//          and writes one float4 (H_b, H_g, H_r, -) per staged row;
+//   pass 2 reads four float4 per output pixel (4 loads instead of 12) and the per-row tables once per pixel.
+constexpr int kC3Px = 128;        // tile width in pixels
+constexpr int kC3Threads = 256;   // two threads per pixel column: they split the staged rows (pass 1) and the output rows (pass 2)
+
+struct Cubic3Geom {
+    int w, h, wo, ho;
+    int TH, tiles_x, tiles_y, tiles_per_cta;
+    int src_pitch, max_slots, opitch, align;
+    double scale_x, scale_y;
+    size_t src_image, dst_image;   // elements between images
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(kC3Threads) resize_cubic3_kernel(const void* __restrict__ src_, void* __restrict__ dst_, Cubic3Geom g) {
+    using S = typename Kind<KIND>::S;
+    constexpr int ES = sizeof(S), C = 3, PX = C * ES;   // bytes per pixel
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ int s_yidx[kRtMaxTH][4];
+    __shared__ __align__(16) int s_ycoef[kRtMaxTH][4];   // float bits: naive beta, or (float)ibeta * 2^-22
+    __shared__ __align__(16) int s_yint[kRtMaxTH][4];    // u8: integer ibeta for OpenCV's scalar tail
+    __shared__ __align__(16) int s_yoff[kRtMaxTH][4];    // byte offset of each tap's row inside hbuf
+    __shared__ int s_ooff[kRtMaxTH];
+    __shared__ int s_x[2];
+
+    uint8_t* tile = smem;                                             // [max_slots][src_pitch]
+    uint8_t* hbuf = smem + (size_t)g.max_slots * g.src_pitch;         // [max_slots][128] float4
+    uint8_t* obuf = hbuf + (size_t)g.max_slots * kC3Px * 16;     // [TH][opitch]
+    constexpr int kHRow = kC3Px * 16;
+
+    const int tid = threadIdx.x, px = tid & (kC3Px - 1), half = tid >> 7;
+    const int tile_x = blockIdx.x % g.tiles_x, ychunk = blockIdx.x / g.tiles_x;
+    const int dx0 = tile_x * kC3Px;
+    const int tw = min(kC3Px, g.wo - dx0);
+    const uint8_t* img = reinterpret_cast<const uint8_t*>(src_) + blockIdx.y * g.src_image * ES;
+    uint8_t* out_img = reinterpret_cast<uint8_t*>(dst_) + blockIdx.y * g.dst_image * ES;
+    const int row_bytes = g.w * PX;
+    const size_t out_row_bytes = (size_t)g.wo * PX;
+    const int seg = tw * PX;
+
+    // ---- once per CTA: x taps of this thread's column
+    const bool active = px < tw;
+    int xidx[4], xcoef[4];
+    axis_coefs<KIND>(dx0 + (active ? px : tw - 1), g.w, g.scale_x, true, xidx, xcoef);
+    if (tid == 0) s_x[0] = xidx[0];
+    if (tid == tw - 1) s_x[1] = xidx[3];
+    __syncthreads();
+    const int xb0 = s_x[0] * PX, xb1 = (s_x[1] + 1) * PX;
+    const int xb0a = xb0 & ~(g.align - 1);
+    const int width = ((xb1 + g.align - 1) & ~(g.align - 1)) - xb0a;
+    int toff[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) toff[j] = xidx[j] * PX - xb0a;
+    const bool consecutive = toff[1] == toff[0] + PX && toff[2] == toff[1] + PX && toff[3] == toff[2] + PX;   // false only where taps are clamped
+    const int vec_end = (g.wo * C) & ~7;
+    const int e_first = (dx0 + px) * C;   // element index of this pixel's first channel in the output row
+
+    for (int t = 0; t < g.tiles_per_cta; ++t) {
+        const int tile_y = ychunk * g.tiles_per_cta + t;
+        if (tile_y >= g.tiles_y) break;
+        const int dy0 = tile_y * g.TH, th = min(g.TH, g.ho - dy0);
+        if (tid < th) {
+            int yi[4], yc[4];
+            axis_coefs<KIND>(dy0 + tid, g.h, g.scale_y, false, yi, yc);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                s_yidx[tid][j] = yi[j];
+                if constexpr (KIND == kCubU8) { s_ycoef[tid][j] = __float_as_int((float)yc[j] * (1.f / (2048 * 2048))); s_yint[tid][j] = yc[j]; }
+                else s_ycoef[tid][j] = yc[j];
+            }
+            const uintptr_t ga = reinterpret_cast<uintptr_t>(out_img) + (size_t)(dy0 + tid) * out_row_bytes + (size_t)dx0 * PX;
+            s_ooff[tid] = tid * g.opitch + (int)(ga & 15);
+        }
+        __syncthreads();
+        // vertical scale <= 4 on this path (host check): every row of the band is touched -> slot = row - first row
+        const int y_lo = s_yidx[0][0], nslots = s_yidx[th - 1][3] - y_lo + 1;
+        for (int i = tid; i < th * 4; i += kC3Threads) s_yoff[i >> 2][i & 3] = (s_yidx[i >> 2][i & 3] - y_lo) * kHRow;
+
+        // ---- stage rows [y_lo, y_lo + nslots), byte columns [xb0a, xb0a + width)
+        if (g.align == 16) {
+            const int units = width >> 4;
+            for (int i = tid; i < nslots * units; i += kC3Threads) {
+                const int r = i / units, u = i - r * units;
+                *reinterpret_cast<uint4*>(tile + r * g.src_pitch + 16 * u) = ld_stream16(img + (size_t)(y_lo + r) * row_bytes + xb0a + 16 * u);
+            }
+        } else if (g.align == 4) {
+            const int units = width >> 2;
+            for (int i = tid; i < nslots * units; i += kC3Threads) {
+                const int r = i / units, u = i - r * units;
+                *reinterpret_cast<uint32_t*>(tile + r * g.src_pitch + 4 * u) = __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)(y_lo + r) * row_bytes + xb0a) + u);
+            }
+        } else {
+            for (int i = tid; i < nslots * width; i += kC3Threads) {
+                const int r = i / width, u = i - r * width;
+                tile[r * g.src_pitch + u] = __ldg(img + (size_t)(y_lo + r) * row_bytes + xb0a + u);
+            }
+        }
+        __syncthreads();
+
+        // ---- pass 1: horizontal sums of the 3 channels per staged row -> float4
+        if (active) {
+            float4* hp = reinterpret_cast<float4*>(hbuf) + half * kC3Px + px;
+            if constexpr (KIND == kCubU8) {
+                if (consecutive) {   // 12 contiguous bytes: four aligned words, funnel-shifted
+                    const uint8_t* base = tile + half * g.src_pitch + (toff[0] & ~3);
+                    const int sh = (toff[0] & 3) * 8;
+#pragma unroll 2
+                    for (int s = half; s < nslots; s += 2, base += 2 * g.src_pitch, hp += 2 * kC3Px) {
+                        const uint32_t w0 = *reinterpret_cast<const uint32_t*>(base), w1 = *reinterpret_cast<const uint32_t*>(base + 4);
+                        const uint32_t w2 = *reinterpret_cast<const uint32_t*>(base + 8), w3 = *reinterpret_cast<const uint32_t*>(base + 12);
+                        const uint32_t b0 = __funnelshift_r(w0, w1, sh), b1 = __funnelshift_r(w1, w2, sh), b2 = __funnelshift_r(w2, w3, sh);
+                        // bytes: b0 = [t0.b t0.g t0.r t1.b]  b1 = [t1.g t1.r t2.b t2.g]  b2 = [t2.r t3.b t3.g t3.r]
+                        const int hb = (int)(b0 & 0xff) * xcoef[0] + (int)(b0 >> 24) * xcoef[1] + (int)((b1 >> 16) & 0xff) * xcoef[2] + (int)((b2 >> 8) & 0xff) * xcoef[3];
+                        const int hg = (int)((b0 >> 8) & 0xff) * xcoef[0] + (int)(b1 & 0xff) * xcoef[1] + (int)(b1 >> 24) * xcoef[2] + (int)((b2 >> 16) & 0xff) * xcoef[3];
+                        const int hr = (int)((b0 >> 16) & 0xff) * xcoef[0] + (int)((b1 >> 8) & 0xff) * xcoef[1] + (int)(b2 & 0xff) * xcoef[2] + (int)(b2 >> 24) * xcoef[3];
+                        *hp = make_float4(int_to_float_exact(hb), int_to_float_exact(hg), int_to_float_exact(hr), 0.f);
+                    }
+                } else {
+                    const uint8_t* row = tile + half * g.src_pitch;
+                    for (int s = half; s < nslots; s += 2, row += 2 * g.src_pitch, hp += 2 * kC3Px) {
+                        int h[3];
+#pragma unroll
+                        for (int k = 0; k < 3; ++k)
+                            h[k] = row[toff[0] + k] * xcoef[0] + row[toff[1] + k] * xcoef[1] + row[toff[2] + k] * xcoef[2] + row[toff[3] + k] * xcoef[3];
+                        *hp = make_float4(int_to_float_exact(h[0]), int_to_float_exact(h[1]), int_to_float_exact(h[2]), 0.f);
+                    }
+                }
+            } else {
+                const uint8_t* row = tile + half * g.src_pitch;
+                const float a0 = __int_as_float(xcoef[0]), a1 = __int_as_float(xcoef[1]), a2 = __int_as_float(xcoef[2]), a3 = __int_as_float(xcoef[3]);
+                for (int s = half; s < nslots; s += 2, row += 2 * g.src_pitch, hp += 2 * kC3Px) {
+                    float h[3];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {   // resize_naive.cpp:230 order
+                        const float t0 = *reinterpret_cast<const float*>(row + toff[0] + 4 * k), t1 = *reinterpret_cast<const float*>(row + toff[1] + 4 * k);
+                        const float t2 = *reinterpret_cast<const float*>(row + toff[2] + 4 * k), t3 = *reinterpret_cast<const float*>(row + toff[3] + 4 * k);
+                        h[k] = t0 * a0 + t1 * a1 + t2 * a2 + t3 * a3;
+                    }
+                    *hp = make_float4(h[0], h[1], h[2], 0.f);
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- pass 2: vertical combination, 3 channels per thread
+        if (active) {
+            const uint8_t* hb = hbuf + 16 * px;
+            for (int ty = half; ty < th; ty += 2) {
+                const int4 yo = *reinterpret_cast<const int4*>(s_yoff[ty]);
+                const int4 yc = *reinterpret_cast<const int4*>(s_ycoef[ty]);
+                const float4 h0 = *reinterpret_cast<const float4*>(hb + yo.x), h1 = *reinterpret_cast<const float4*>(hb + yo.y);
+                const float4 h2 = *reinterpret_cast<const float4*>(hb + yo.z), h3 = *reinterpret_cast<const float4*>(hb + yo.w);
+                const float b0 = __int_as_float(yc.x), b1 = __int_as_float(yc.y), b2 = __int_as_float(yc.z), b3 = __int_as_float(yc.w);
+                const float c0[3] = {h0.x, h0.y, h0.z}, c1[3] = {h1.x, h1.y, h1.z}, c2[3] = {h2.x, h2.y, h2.z}, c3[3] = {h3.x, h3.y, h3.z};
+                S* o = reinterpret_cast<S*>(obuf + s_ooff[ty]) + C * px;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    if constexpr (KIND == kCubF32) {   // resize_naive.cpp:345
+                        o[k] = c0[k] * b0 + c1[k] * b1 + c2[k] * b2 + c3[k] * b3;
+                    } else {
+                        int v;
+                        if (e_first + k < vec_end) {   // OpenCV SSE2 body
+                            float f = c0[k] * b0;
+                            f = f + c1[k] * b1;
+                            f = f + c2[k] * b2;
+                            f = f + c3[k] * b3;
+                            v = max(min(float_to_int_rhe(f), 32767), -32768);
+                        } else {                       // scalar tail
+                            const int4 ib = *reinterpret_cast<const int4*>(s_yint[ty]);
+                            v = (__float2int_rn(c0[k]) * ib.x + __float2int_rn(c1[k]) * ib.y + __float2int_rn(c2[k]) * ib.z + __float2int_rn(c3[k]) * ib.w + (1 << 21)) >> 22;
+                        }
+                        o[k] = (uint8_t)clamp255(v);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- copy out
+        const int chunks_per_row = (seg + 15 + 15) >> 4;
+        for (int i = tid; i < th * chunks_per_row; i += kC3Threads) {
+            const int ty = i / chunks_per_row, q = i - ty * chunks_per_row;
+            const int mis = s_ooff[ty] - ty * g.opitch;
+            const int lo = max(mis, 16 * q), hi = min(mis + seg, 16 * q + 16);
+            if (lo >= hi) continue;
+            const uint8_t* sp = obuf + ty * g.opitch + 16 * q;
+            uint8_t* gp = out_img + (size_t)(dy0 + ty) * out_row_bytes + (size_t)dx0 * PX - mis + 16 * q;
+            if (hi - lo == 16) st_stream16(gp, *reinterpret_cast<const uint4*>(sp));
+            else for (int b = lo - 16 * q; b < hi - 16 * q; ++b) gp[b] = sp[b];
+        }
+        __syncthreads();
+    }
+}
+
+template <int KIND>
+static int launch_cubic3(const void* src, void* dst, int images, int w, int h, int wo, int ho, cudaStream_t s) {
+    constexpr int ES = sizeof(typename Kind<KIND>::S), PX = 3 * ES;
+    Cubic3Geom g;
+    g.w = w; g.h = h; g.wo = wo; g.ho = ho;
+    g.src_image = (size_t)w * h * 3; g.dst_image = (size_t)wo * ho * 3;
+    const double sx = (double)w / wo, sy = (double)h / ho;
+    if (sy > 3.75 || sx > 6.0) return 0;   // dense band assumption / staged span; larger down-scales use the generic kernel
+    if (KIND == kCubU8) { g.scale_x = 1. / ((double)wo / (double)w); g.scale_y = 1. / ((double)ho / (double)h); }
+    else { g.scale_x = (double)w / (double)wo; g.scale_y = (double)h / (double)ho; }
+    const size_t row_bytes = (size_t)w * PX;
+    g.align = ((row_bytes % 16) == 0 && ((uintptr_t)src % 16) == 0) ? 16 : ((row_bytes % 4) == 0 && ((uintptr_t)src % 4) == 0) ? 4 : 1;
+    const int span_px = std::min(w, (int)(sx * (kC3Px - 1)) + 4 + 3);
+    g.src_pitch = (int)(((size_t)span_px * PX + 2 * g.align + 15 + 16) & ~(size_t)15);   // +16: the funnel-shift loads read one word past the last tap
+    g.opitch = (kC3Px * PX + 16 + 15) & ~15;
+    const size_t budget = 44 * 1024;   // 5 CTAs x 8 warps per SM
+    for (int TH = kRtMaxTH; TH >= 1; --TH) {
+        const int slots = (int)(sy * (TH - 1)) + 4 + 3;
+        const size_t smem = (size_t)slots * g.src_pitch + (size_t)slots * kC3Px * 16 + (size_t)TH * g.opitch;
+        if (smem > budget) continue;
+        g.TH = TH; g.max_slots = slots;
+        g.tiles_x = (wo + kC3Px - 1) / kC3Px; g.tiles_y = (ho + TH - 1) / TH;
+        const long long ctas1 = (long long)g.tiles_x * g.tiles_y * images;
+        g.tiles_per_cta = (int)std::max<long long>(1, std::min<long long>(8, ctas1 / (kNumSMs * 16LL)));
+        const int ychunks = (g.tiles_y + g.tiles_per_cta - 1) / g.tiles_per_cta;
+        auto kern = resize_cubic3_kernel<KIND>;
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return set_error(VACV_ERR_CUDA, "resize: %s", cudaGetErrorString(e));
+        }
+        for (int i0 = 0; i0 < images; i0 += 65535) {
+            dim3 grid(g.tiles_x * ychunks, std::min(images - i0, 65535));
+            kern<<<grid, kC3Threads, smem, s>>>((const uint8_t*)src + (size_t)i0 * g.src_image * ES, (uint8_t*)dst + (size_t)i0 * g.dst_image * ES, g);
+        }
+        return 1;
+    }
+    return 0;
+}
+
+
+// Rolling bicubic for interleaved 3-channel images (resize_cubic3.cuh).  1 = launched, 0 = shape not eligible.
+template <bool kU8>
+static int launch_cubic3_rolling(const void* src, void* dst, int images, int w, int h, int wo, int ho, cudaStream_t s) {
+    constexpr int ES = kU8 ? 1 : 4, PX = 3 * ES;
+    const double sy = (double)h / ho;
+    if (((size_t)w * PX) % 4 != 0 || ((uintptr_t)src % 4) != 0) return 0;       // pass 1 reads aligned 32-bit words
+    int G = kRollMaxG;
+    while (G > 1 && (int)(sy * (G - 1)) + 6 > kRollRing) --G;                   // a group's source rows must fit the ring
+    if ((int)(sy * (G - 1)) + 6 > kRollRing) return 0;
+    RollGeom g;
+    g.w = w; g.h = h; g.wo = wo; g.ho = ho; g.G = G;
+    g.src_image = (size_t)w * h * 3; g.dst_image = (size_t)wo * ho * 3;
+    if (kU8) { g.scale_x = 1. / ((double)wo / (double)w); g.scale_y = 1. / ((double)ho / (double)h); }   // OpenCV 2.4
+    else { g.scale_x = (double)w / (double)wo; g.scale_y = (double)h / (double)ho; }                     // resize_naive.cpp:144
+    g.strips = (wo + kRollPx - 1) / kRollPx;
+    g.opitch = (kRollPx * PX + 16 + 15) & ~15;
+    // vertical segments: enough CTAs for >= ~6 waves of 5 CTAs/SM, each segment a multiple of G rows
+    const long long want = 6LL * 5 * kNumSMs;
+    long long segs = std::max<long long>(1, std::min<long long>((want + (long long)g.strips * images - 1) / ((long long)g.strips * images), (ho + G - 1) / G));
+    int rps = (int)((ho + segs - 1) / segs);
+    rps = std::min(kRollMaxRows / G * G, (rps + G - 1) / G * G);
+    g.rows_per_seg = rps;
+    g.segs = (ho + rps - 1) / rps;
+    const size_t smem = (size_t)kRollRing * kRollPx * 16 + (size_t)rps * sizeof(RowEntry) + (((size_t)rps * 4 + 15) & ~(size_t)15) + (size_t)G * g.opitch;
+    auto kern = resize_cubic3_rolling_kernel<kU8>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return set_error(VACV_ERR_CUDA, "resize: %s", cudaGetErrorString(e));
+    }
+    for (int i0 = 0; i0 < images; i0 += 65535) {
+        dim3 grid(g.strips * g.segs, std::min(images - i0, 65535));
+        kern<<<grid, kRollThreads, smem, s>>>((const uint8_t*)src + (size_t)i0 * g.src_image * ES, (uint8_t*)dst + (size_t)i0 * g.dst_image * ES, g);
+    }
+    return 1;
+}
+
 template <int KIND>
 static int launch_tiled_kind(const void* src, void* dst, int images, TiledGeom g, size_t smem, cudaStream_t s) {
     auto kern = resize_tiled_kernel<KIND>;
@@ -317,6 +593,12 @@ static int launch_tiled_kind(const void* src, void* dst, int images, TiledGeom g
 
 // Returns 1 if launched, 0 if the shape does not fit the tiled kernel (caller uses the direct kernels), < 0 on error.
 int try_launch_resize_tiled(int kind, const void* src, void* dst, int images, int w, int h, int c, int wo, int ho, cudaStream_t s) {
+    if (c == 3 && (kind == kCubU8 || kind == kCubF32)) {   // interleaved BGR: rolling separable kernel, else the tiled pixel-per-thread one
+        int rc = kind == kCubU8 ? launch_cubic3_rolling<true>(src, dst, images, w, h, wo, ho, s) : launch_cubic3_rolling<false>(src, dst, images, w, h, wo, ho, s);
+        if (rc != 0) return rc;
+        rc = kind == kCubU8 ? launch_cubic3<kCubU8>(src, dst, images, w, h, wo, ho, s) : launch_cubic3<kCubF32>(src, dst, images, w, h, wo, ho, s);
+        if (rc != 0) return rc;
+    }
     const int es = (kind == kLinF32 || kind == kCubF32) ? 4 : 1;
     const int K = (kind == kCubF32 || kind == kCubU8) ? 4 : 2;
     if (c > 64 || (size_t)wo * c > 0x3fffffff) return 0;
