@@ -113,6 +113,89 @@ __global__ void __launch_bounds__(256) warp_affine_normalize_kernel(const uint8_
     }
 }
 
+
+// ----------------------------------------------------------------------------------------------------
+// u8, 3 interleaved channels (the C3 shape), word-granular taps and coalesced output.
+// ncu on the byte-granular kernels above: L1/LSU wavefronts at 80 % of peak (12 byte loads per pixel), i.e. LSU-bound.
+// Here the 6 contiguous bytes of a tap row (2 pixels x BGR) come from 2-3 aligned 32-bit words + funnel shifts, and
+// every warp re-chunks its 32 output pixels through a private shared-memory line so that global stores are
+// lane-contiguous (96 B of u8, or 3 x 128 B of fp32) instead of 3 strided partial-sector stores per lane.
+enum { kWarpOutU8 = 0, kWarpOutF32HWC = 1, kWarpOutF32CHW = 2 };
+
+template <bool kSigned>
+__device__ __forceinline__ void taps_u8c3(const uint8_t* __restrict__ img, int a, int (&pl)[3], int (&pr)[3]) {
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(img + (a & ~3));
+    const int sh = (a & 3) * 8;
+    const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = (a & 3) == 3 ? __ldg(wp + 2) : 0u;
+    const uint32_t b0 = __funnelshift_r(w0, w1, sh), b1 = __funnelshift_r(w1, w2, sh);   // [L.b L.g L.r R.b] [R.g R.r . .]
+    pl[0] = pix<kSigned>((uint8_t)b0); pl[1] = pix<kSigned>((uint8_t)(b0 >> 8)); pl[2] = pix<kSigned>((uint8_t)(b0 >> 16));
+    pr[0] = pix<kSigned>((uint8_t)(b0 >> 24)); pr[1] = pix<kSigned>((uint8_t)b1); pr[2] = pix<kSigned>((uint8_t)(b1 >> 8));
+}
+
+// grid = (crops, bands); each CTA walks pixels [y0*wo, y1*wo) of its crop in flat order (a warp = 32 consecutive pixels)
+template <int OUT, bool kSigned>
+__global__ void __launch_bounds__(256) warp_affine_u8c3_kernel(const uint8_t* __restrict__ frames, const int* __restrict__ frame_idx,
+                                                                const float* __restrict__ minv, void* __restrict__ dst_, WarpGeom g,
+                                                                const float* __restrict__ mean, const float* __restrict__ stddev,
+                                                                int rows_per_cta, int crop0) {
+    __shared__ float lut[OUT == kWarpOutU8 ? 1 : 3 * 256];
+    __shared__ float m[6];
+    __shared__ __align__(16) uint32_t stage[8][OUT == kWarpOutU8 ? 24 : 96];   // per warp: 32 px x 3 ch
+    const int crop = crop0 + blockIdx.x;
+    if (threadIdx.x < 6) m[threadIdx.x] = __ldg(minv + 6 * (size_t)crop + threadIdx.x);
+    if (OUT != kWarpOutU8)
+        for (int t = threadIdx.x; t < 768; t += blockDim.x)
+            lut[t] = normalize_one((float)(t & 255), __ldg(mean + (t >> 8)), (double)__ldg(stddev + (t >> 8)) + 1e-6);
+    __syncthreads();
+    const size_t f = frame_idx ? (size_t)__ldg(frame_idx + crop) : (size_t)crop;
+    const uint8_t* img = frames + f * g.frame_elems;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i_begin = blockIdx.y * rows_per_cta * g.wo, i_end = min((blockIdx.y + 1) * rows_per_cta, g.ho) * g.wo;
+    const size_t crop_px = (size_t)g.wo * g.ho;
+    const int row = g.w * 3;
+    for (int i0 = i_begin + warp * 32; i0 < i_end; i0 += 256) {   // warp-uniform loop
+        const int i = i0 + lane;
+        int v[3] = {0, 0, 0};
+        if (i < i_end) {
+            const int dy = i / g.wo, dx = i - dy * g.wo;
+            const Taps t = warp_taps(m, dx, dy, g.w, g.h);
+            if (t.in) {
+                int tl[3], tr[3], bl[3], br[3];
+                taps_u8c3<kSigned>(img, t.ofs * 3, tl, tr);
+                taps_u8c3<kSigned>(img, t.ofs * 3 + row, bl, br);
+                const int w00 = t.cx0 * t.cy0, w10 = t.cx0 * t.cy1, w01 = t.cx1 * t.cy0, w11 = t.cx1 * t.cy1;
+#pragma unroll
+                for (int k = 0; k < 3; ++k)   // warp_affine_naive.cpp:50-54: same integer, products regrouped
+                    v[k] = ((tl[k] * w00 + bl[k] * w10 + tr[k] * w01 + br[k] * w11) >> 22) & 0xff;
+            }
+        }
+        const int n = min(32, i_end - i0);   // valid pixels of this warp
+        if (OUT == kWarpOutU8) {
+            uint8_t* sb = reinterpret_cast<uint8_t*>(stage[warp]);
+            sb[3 * lane] = (uint8_t)v[0]; sb[3 * lane + 1] = (uint8_t)v[1]; sb[3 * lane + 2] = (uint8_t)v[2];
+            __syncwarp();
+            uint8_t* o = reinterpret_cast<uint8_t*>(dst_) + ((size_t)crop * crop_px + i0) * 3;   // 96 B per warp, 4-byte aligned when dst is
+            if ((reinterpret_cast<uintptr_t>(o) & 3) == 0 && n == 32) { if (lane < 24) st_stream4(o + 4 * lane, stage[warp][lane]); }
+            else for (int b = lane; b < 3 * n; b += 32) o[b] = sb[b];
+            __syncwarp();
+        } else {
+            const float r0 = lut[v[0]], r1 = lut[256 + v[1]], r2 = lut[512 + v[2]];
+            float* out = reinterpret_cast<float*>(dst_) + (size_t)crop * crop_px * 3;
+            if (OUT == kWarpOutF32CHW) {
+                if (i < i_end) { st_stream4f(out + i, r0); st_stream4f(out + crop_px + i, r1); st_stream4f(out + 2 * crop_px + i, r2); }
+            } else {
+                float* sf = reinterpret_cast<float*>(stage[warp]);
+                sf[3 * lane] = r0; sf[3 * lane + 1] = r1; sf[3 * lane + 2] = r2;
+                __syncwarp();
+                float* o = out + (size_t)i0 * 3;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) if (32 * j + lane < 3 * n) st_stream4f(o + 32 * j + lane, sf[32 * j + lane]);
+                __syncwarp();
+            }
+        }
+    }
+}
+
 }  // namespace vacv
 
 using namespace vacv;
@@ -133,6 +216,16 @@ extern "C" int vacv_cuda_warp_affine(const void* frames, int n_frames, int w, in
     WarpGeom g;
     g.w = w; g.h = h; g.c = c; g.wo = w_out; g.ho = h_out; g.frame_elems = (size_t)w * h * c; g.planar = layout == VACV_NCHW;
     cudaStream_t s = as_stream(stream);
+    const bool words_ok = (((size_t)w * h * 3) % 4) == 0 && ((uintptr_t)frames % 4) == 0;
+    if (dtype == VACV_INT8 && c == 3 && layout == VACV_NHWC && words_ok) {
+        const int rows_per_cta = max(1, min(h_out, (4096 + w_out - 1) / w_out));
+        dim3 grid(n_crops, ceil_div(h_out, rows_per_cta));
+        if (flags & VACV_FLAG_SIGNED_CHAR)
+            warp_affine_u8c3_kernel<kWarpOutU8, true><<<grid, 256, 0, s>>>((const uint8_t*)frames, frame_idx, minv, dst, g, nullptr, nullptr, rows_per_cta, 0);
+        else
+            warp_affine_u8c3_kernel<kWarpOutU8, false><<<grid, 256, 0, s>>>((const uint8_t*)frames, frame_idx, minv, dst, g, nullptr, nullptr, rows_per_cta, 0);
+        return check_launch("warp_affine");
+    }
     dim3 block(32, 8);
     for (int c0 = 0; c0 < n_crops; c0 += 65535) {
         dim3 grid(ceil_div(w_out, 32), ceil_div(h_out, 8), min(n_crops - c0, 65535));
@@ -160,6 +253,11 @@ extern "C" int vacv_cuda_warp_affine_normalize(const uint8_t* frames, int n_fram
     const int rows_per_cta = max(1, min(h_out, (8192 + w_out - 1) / w_out));
     dim3 grid(n_crops, ceil_div(h_out, rows_per_cta));
     cudaStream_t s = as_stream(stream);
+    if (c == 3 && (((size_t)w * h * 3) % 4) == 0 && ((uintptr_t)frames % 4) == 0) {
+        if (out_layout == VACV_NHWC) warp_affine_u8c3_kernel<kWarpOutF32HWC, false><<<grid, 256, 0, s>>>(frames, frame_idx, minv, dst, g, mean, stddev, rows_per_cta, 0);
+        else warp_affine_u8c3_kernel<kWarpOutF32CHW, false><<<grid, 256, 0, s>>>(frames, frame_idx, minv, dst, g, mean, stddev, rows_per_cta, 0);
+        return check_launch("warp_affine_normalize");
+    }
     if (c == 3) warp_affine_normalize_kernel<3><<<grid, 256, 0, s>>>(frames, frame_idx, minv, dst, g, mean, stddev, out_layout, rows_per_cta);
     else warp_affine_normalize_kernel<1><<<grid, 256, 0, s>>>(frames, frame_idx, minv, dst, g, mean, stddev, out_layout, rows_per_cta);
     return check_launch("warp_affine_normalize");
