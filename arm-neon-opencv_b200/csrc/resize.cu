@@ -7,6 +7,7 @@
 // into shared memory, then each thread gathers its taps through the read-only path.
 #include "vacv_common.cuh"
 #include "resize_coeffs.cuh"
+#include "gather_u8c3.cuh"
 
 namespace vacv {
 
@@ -66,14 +67,6 @@ __global__ void __launch_bounds__(kTileX * kTileY) resize_linear_u8_kernel(const
 // stores per pixel and is LSU-bound; here the 6 contiguous bytes of a tap row (2 pixels x BGR) come from 2-3 aligned
 // 32-bit words + funnel shifts, and each warp (32 consecutive pixels of one output row) re-chunks its 96 output bytes
 // through shared memory into lane-contiguous 32-bit stores.
-__device__ __forceinline__ void linear_taps_u8c3(const uint8_t* __restrict__ img, size_t a, uint32_t& b0, uint32_t& b1) {
-    const uint32_t* wp = reinterpret_cast<const uint32_t*>(img + (a & ~(size_t)3));
-    const int r = (int)(a & 3), sh = r * 8;
-    const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = r == 3 ? __ldg(wp + 2) : 0u;
-    b0 = __funnelshift_r(w0, w1, sh);   // [L.b L.g L.r R.b]
-    b1 = __funnelshift_r(w1, w2, sh);   // [R.g R.r  .   . ]
-}
-
 template <bool kSigned, bool kNeonRule>
 __global__ void __launch_bounds__(kTileX * kTileY) resize_linear_u8c3_kernel(const uint8_t* __restrict__ src,
                                                                               uint8_t* __restrict__ dst, ResizeGeom g) {
