@@ -195,18 +195,28 @@ __global__ void __launch_bounds__(256) normalize_u8_hwc_kernel(const uint8_t* __
     // element 4*i has channel (4*i) mod C; advance it by (4*stride) mod C per iteration
     unsigned ph = (4u * (i % C)) % C;
     const unsigned dph = (4u * (stride % C)) % C;
-    for (; i < n4; i += stride) {
-        const uint32_t v = ld_stream4(s + 4 * (size_t)i);
-        float o[4];
-        unsigned k = ph;
+    // kU independent 4-byte loads are in flight per thread before the first table lookup: with one load per iteration the
+    // kernel was latency-bound (ncu: long_scoreboard 47 stall cycles per issue, DRAM at 57 %)
+    constexpr int kU = 4;
+    for (; i < n4; i += kU * stride) {
+        uint32_t v[kU];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            o[j] = lut[k * 256 + ((v >> (8 * j)) & 0xff)];
-            k = (k + 1 == C) ? 0 : k + 1;
+        for (int u = 0; u < kU; ++u) v[u] = i + u * stride < n4 ? ld_stream4(s + 4 * (size_t)(i + u * stride)) : 0u;
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            if (i + u * stride < n4) {
+                float o[4];
+                unsigned k = ph;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    o[j] = lut[k * 256 + ((v[u] >> (8 * j)) & 0xff)];
+                    k = (k + 1 == C) ? 0 : k + 1;
+                }
+                st_stream16f(d + 4 * (size_t)(i + u * stride), make_float4(o[0], o[1], o[2], o[3]));
+            }
+            ph += dph;
+            if (ph >= C) ph -= C;
         }
-        st_stream16f(d + 4 * (size_t)i, make_float4(o[0], o[1], o[2], o[3]));
-        ph += dph;
-        if (ph >= C) ph -= C;
     }
     if (blockIdx.x == 0 && threadIdx.x < g.per_frame - 4 * n4) {
         const unsigned e = 4 * n4 + threadIdx.x;
@@ -232,23 +242,31 @@ __global__ void __launch_bounds__(256) normalize_f32_hwc_kernel(const float* __r
     unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned ph = (4u * (i % C)) % C;
     const unsigned dph = (4u * (stride % C)) % C;
-    for (; i < n4; i += stride) {
-        const uint4 r = ld_stream16(s + 4 * (size_t)i);
-        const float x[4] = {__uint_as_float(r.x), __uint_as_float(r.y), __uint_as_float(r.z), __uint_as_float(r.w)};
-        float o[4];
-        unsigned k = ph;
+    constexpr int kU = 2;   // two independent 16-byte loads in flight per thread
+    for (; i < n4; i += kU * stride) {
+        uint4 rr[kU];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            // select the channel's constants without dynamic register indexing
-            float m = mu[0]; double dn = den[0], rd = rden[0];
+        for (int u = 0; u < kU; ++u) rr[u] = i + u * stride < n4 ? ld_stream16(s + 4 * (size_t)(i + u * stride)) : make_uint4(0, 0, 0, 0);
 #pragma unroll
-            for (int q = 1; q < C; ++q) if (k == q) { m = mu[q]; dn = den[q]; rd = rden[q]; }
-            o[j] = normalize_fast_exact(x[j], m, dn, rd);
-            k = (k + 1 == C) ? 0 : k + 1;
+        for (int u = 0; u < kU; ++u) {
+            if (i + u * stride < n4) {
+                const float x[4] = {__uint_as_float(rr[u].x), __uint_as_float(rr[u].y), __uint_as_float(rr[u].z), __uint_as_float(rr[u].w)};
+                float o[4];
+                unsigned k = ph;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    // select the channel's constants without dynamic register indexing
+                    float m = mu[0]; double dn = den[0], rd = rden[0];
+#pragma unroll
+                    for (int q = 1; q < C; ++q) if (k == q) { m = mu[q]; dn = den[q]; rd = rden[q]; }
+                    o[j] = normalize_fast_exact(x[j], m, dn, rd);
+                    k = (k + 1 == C) ? 0 : k + 1;
+                }
+                st_stream16f(d + 4 * (size_t)(i + u * stride), make_float4(o[0], o[1], o[2], o[3]));
+            }
+            ph += dph;
+            if (ph >= C) ph -= C;
         }
-        st_stream16f(d + 4 * (size_t)i, make_float4(o[0], o[1], o[2], o[3]));
-        ph += dph;
-        if (ph >= C) ph -= C;
     }
     if (blockIdx.x == 0 && threadIdx.x < g.per_frame - 4 * n4) {
         const unsigned e = 4 * n4 + threadIdx.x, k = e % C;
