@@ -452,3 +452,41 @@ def test_cpp_dropin_binary(vacv):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     print(r.stdout)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+# ------------------------------------------------------------------ CUDA path vs the committed golden digests
+def test_cuda_vs_golden_digests(vacv):
+    """sha256 of CUDA outputs == digests the compiled reference produced (tests/golden/golden.json)."""
+    import json
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    import cases as gc
+    golden = json.load(open(os.path.join(here, "golden", "golden.json")))
+    img, imgf = gc.u8(2, 360, 640, 3), gc.f32(3, 360, 640, 3)
+    big, grey = gc.u8(4, 720, 1280, 3), gc.u8(5, 720, 1280, 1)
+    nv, nv2 = gc.u8(1, 640 * 360 * 3 // 2), gc.u8(6, 1920 * 1080 * 3 // 2)
+    minv = dev(np.array(vacv.invert_affine(gc.M_TEST), np.float32)[None])
+    mrot = dev(np.array(vacv.invert_affine(vacv.rotation_matrix(gc.ROT["scale"], gc.ROT["rot"], gc.ROT["aux"])), np.float32)[None])
+    mean, std = dev(gc.MEAN), dev(gc.STD)
+    got = {
+        "nv21_to_bgr_640x360": vacv.cvt_nv2bgr(dev(nv[None]), 640, 360, True),
+        "crop_hwc_u8": vacv.crop(dev(img[None]), NHWC, 7, 3, 192, 96),
+        "hwc_to_chw_u8": vacv.layout_change(dev(img[None]), NHWC, NCHW),
+        "u8_to_f32": vacv.dtype_change(dev(img[None]), vacv.FP32),
+        "f32_to_u8": vacv.dtype_change(dev(imgf[None]), vacv.INT8),
+        "resize_linear_u8_hwc_320x180": vacv.resize(dev(img[None]), NHWC, 320, 180),
+        "resize_linear_f32_hwc_500x300": vacv.resize(dev(imgf[None]), NHWC, 500, 300),
+        "resize_cubic_f32_hwc_300x300": vacv.resize(dev(imgf[None]), NHWC, 300, 300, vacv.INTER_CUBIC),
+        "resize_cubic_f32_hwc_480x270_fixed": vacv.resize(dev(imgf[None]), NHWC, 480, 270, vacv.INTER_CUBIC),
+        "resize_cubic_u8_cv24_480x270": vacv.resize(dev(img[None]), NHWC, 480, 270, vacv.INTER_CUBIC),
+        "resize_cubic_u8_cv24_up_803x451": vacv.resize(dev(img[None]), NHWC, 803, 451, vacv.INTER_CUBIC),
+        "warp_affine_u8_240x240": vacv.warp_affine(dev(big[None]), NHWC, minv, 240, 240),
+        "warp_affine_f32_240x240": vacv.warp_affine(dev(big.astype(np.float32)[None]), NHWC, minv, 240, 240),
+        "warp_affine_rot_grey_140x210": vacv.warp_affine(dev(grey[None]), NHWC, mrot, 140, 210),
+        "normalize_u8_hwc": vacv.normalize(dev(img[None]), NHWC, mean, std),
+        "pipeline_c2_1080p_to_640x640": vacv.nv_resize_normalize_chw(dev(nv2[None]), 1920, 1080, 640, 640, mean, std),
+    }
+    bad = [k for k, v in got.items() if gc.digest(host(v)[0]) != golden[k]]
+    assert not bad, f"CUDA output differs from the reference digest for: {bad}"
