@@ -38,6 +38,7 @@ _SIGS = {
     "vacv_cuda_finalize_mean_stddev": [_vp, _i, _i, _u64, _vp, _vp, _vp],
     "vacv_cuda_normalize": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp],
     "vacv_cuda_nv_resize_normalize_chw": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp],
+    "vacv_cuda_nv_resize_normalize_chw_host": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i],
     "vacv_cuda_resize_normalize": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp],
     "vacv_cuda_warp_affine_normalize": [_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _vp],
     "vacv_cuda_device_count": [_vp],
@@ -248,3 +249,16 @@ def warp_affine_normalize(frames, minv, w_out, h_out, mean, std, frame_idx=None,
                                                minv.data_ptr(), n, dst.data_ptr(), w_out, h_out, mean.data_ptr(),
                                                std.data_ptr(), out_layout, _stream()))
     return dst
+
+
+def nv_resize_normalize_chw_host(h_src, h_out, w, h, w_out, h_out_, mean, std, v_first=True, chunk_frames=32):
+    """End-to-end host-buffer call: h_src uint8 [B, w*h*3/2] and h_out float32 [B,3,h_out,w_out] are HOST tensors
+    (pinned for full PCIe speed); mean/std are 3-element host sequences.  Synchronous."""
+    if h_src.is_cuda or h_out.is_cuda:
+        raise VacvError("nv_resize_normalize_chw_host takes host tensors")
+    b = h_src.numel() // (w * h * 3 // 2)
+    m = (C.c_float * 3)(*[float(v) for v in mean])
+    s = (C.c_float * 3)(*[float(v) for v in std])
+    _check(lib.vacv_cuda_nv_resize_normalize_chw_host(h_src.data_ptr(), h_out.data_ptr(), b, w, h, int(bool(v_first)), w_out, h_out_,
+                                                      C.cast(m, _vp), C.cast(s, _vp), chunk_frames))
+    return h_out

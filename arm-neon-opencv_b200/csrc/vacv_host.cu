@@ -101,3 +101,87 @@ extern "C" int vacv_cuda_stream_create(void** stream) {
 }
 extern "C" int vacv_cuda_stream_destroy(void* stream) { VACV_RT(cudaStreamDestroy(vacv::as_stream(stream)), "stream_destroy"); }
 extern "C" int vacv_cuda_stream_sync(void* stream) { VACV_RT(cudaStreamSynchronize(vacv::as_stream(stream)), "stream_sync"); }
+
+// ---- end-to-end host-buffer pipeline ------------------------------------------------------------------------------
+namespace {
+struct HostPipe {   // per host thread: streams, events and double-buffered device staging, created on first use
+    cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
+    cudaEvent_t in_done[2] = {}, k_done[2] = {}, out_done[2] = {};
+    uint8_t* d_in[2] = {};
+    float* d_out[2] = {};
+    float* d_stats = nullptr;
+    size_t in_cap = 0, out_cap = 0;
+    bool ready = false;
+    cudaError_t init() {
+        if (ready) return cudaSuccess;
+        cudaError_t e;
+        if ((e = cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        if ((e = cudaStreamCreateWithFlags(&s_k, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        if ((e = cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        for (int b = 0; b < 2; ++b) {
+            if ((e = cudaEventCreateWithFlags(&in_done[b], cudaEventDisableTiming)) != cudaSuccess) return e;
+            if ((e = cudaEventCreateWithFlags(&k_done[b], cudaEventDisableTiming)) != cudaSuccess) return e;
+            if ((e = cudaEventCreateWithFlags(&out_done[b], cudaEventDisableTiming)) != cudaSuccess) return e;
+        }
+        if ((e = cudaMalloc(&d_stats, 6 * sizeof(float))) != cudaSuccess) return e;
+        ready = true;
+        return cudaSuccess;
+    }
+    cudaError_t reserve(size_t in_bytes, size_t out_bytes) {
+        cudaError_t e;
+        if (in_bytes > in_cap) {
+            if ((e = cudaDeviceSynchronize()) != cudaSuccess) return e;
+            for (int b = 0; b < 2; ++b) { cudaFree(d_in[b]); d_in[b] = nullptr; if ((e = cudaMalloc(&d_in[b], in_bytes)) != cudaSuccess) return e; }
+            in_cap = in_bytes;
+        }
+        if (out_bytes > out_cap) {
+            if ((e = cudaDeviceSynchronize()) != cudaSuccess) return e;
+            for (int b = 0; b < 2; ++b) { cudaFree(d_out[b]); d_out[b] = nullptr; if ((e = cudaMalloc(&d_out[b], out_bytes)) != cudaSuccess) return e; }
+            out_cap = out_bytes;
+        }
+        return cudaSuccess;
+    }
+};
+thread_local HostPipe g_pipe;
+}  // namespace
+
+#define VACV_CU(call)                                                                                           \
+    do {                                                                                                        \
+        cudaError_t e_ = (call);                                                                                \
+        if (e_ != cudaSuccess) return vacv::set_error(VACV_ERR_CUDA, "nv_resize_normalize_chw_host: %s", cudaGetErrorString(e_)); \
+    } while (0)
+
+extern "C" int vacv_cuda_nv_resize_normalize_chw_host(const uint8_t* h_src, float* h_dst, int batch, int w, int h, int v_first,
+                                                      int w_out, int h_out, const float* h_mean, const float* h_stddev,
+                                                      int chunk_frames) {
+    VACV_REQUIRE(h_src && h_dst && h_mean && h_stddev, "nv_resize_normalize_chw_host: null pointer");
+    VACV_REQUIRE(batch > 0 && chunk_frames > 0, "nv_resize_normalize_chw_host: bad batch / chunk");
+    HostPipe& p = g_pipe;
+    VACV_CU(p.init());
+    const size_t in_frame = (size_t)w * h * 3 / 2, out_frame = (size_t)w_out * h_out * 3 * sizeof(float);
+    const int chunk = chunk_frames < batch ? chunk_frames : batch;
+    VACV_CU(p.reserve(in_frame * chunk, out_frame * chunk));
+    float stats[6] = {h_mean[0], h_mean[1], h_mean[2], h_stddev[0], h_stddev[1], h_stddev[2]};
+    VACV_CU(cudaMemcpyAsync(p.d_stats, stats, sizeof(stats), cudaMemcpyHostToDevice, p.s_k));
+    VACV_CU(cudaStreamSynchronize(p.s_k));   // `stats` lives on this stack frame
+    int i = 0;
+    for (int f0 = 0; f0 < batch; f0 += chunk, ++i) {
+        const int b = i & 1, n = (batch - f0 < chunk) ? batch - f0 : chunk;
+        // H2D of chunk i may start once the kernel that last read d_in[b] (chunk i-2) is done
+        if (i >= 2) VACV_CU(cudaStreamWaitEvent(p.s_in, p.k_done[b], 0));
+        VACV_CU(cudaMemcpyAsync(p.d_in[b], h_src + (size_t)f0 * in_frame, in_frame * n, cudaMemcpyHostToDevice, p.s_in));
+        VACV_CU(cudaEventRecord(p.in_done[b], p.s_in));
+        // kernel of chunk i: needs its input, and d_out[b] drained by the D2H of chunk i-2
+        VACV_CU(cudaStreamWaitEvent(p.s_k, p.in_done[b], 0));
+        if (i >= 2) VACV_CU(cudaStreamWaitEvent(p.s_k, p.out_done[b], 0));
+        const int rc = vacv_cuda_nv_resize_normalize_chw(p.d_in[b], p.d_out[b], n, w, h, v_first, w_out, h_out, p.d_stats, p.d_stats + 3, p.s_k);
+        if (rc != VACV_OK) { cudaDeviceSynchronize(); return rc; }
+        VACV_CU(cudaEventRecord(p.k_done[b], p.s_k));
+        VACV_CU(cudaStreamWaitEvent(p.s_out, p.k_done[b], 0));
+        VACV_CU(cudaMemcpyAsync(h_dst + (size_t)f0 * (out_frame / sizeof(float)), p.d_out[b], out_frame * n, cudaMemcpyDeviceToHost, p.s_out));
+        VACV_CU(cudaEventRecord(p.out_done[b], p.s_out));
+    }
+    VACV_CU(cudaStreamSynchronize(p.s_out));
+    VACV_CU(cudaStreamSynchronize(p.s_k));
+    return VACV_OK;
+}

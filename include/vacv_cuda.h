@@ -130,6 +130,15 @@ VACV_API int vacv_cuda_warp_affine_normalize(const uint8_t* frames, int n_frames
                                              float* dst, int w_out, int h_out, const float* mean, const float* stddev,
                                              int out_layout, void* stream);
 
+/* ---- host-buffer entry point of the fused pipeline (the end-to-end path) ------------------------------------------
+ * Same operation as vacv_cuda_nv_resize_normalize_chw, but `h_src` / `h_dst` / `h_mean` / `h_stddev` are HOST pointers
+ * (pinned memory -- vacv_cuda_host_alloc -- for full PCIe speed; pageable works, slower).  The batch is cut into chunks of
+ * `chunk_frames` frames that are pipelined over three internal streams (H2D copy | kernel | D2H copy, double-buffered
+ * device staging, grown on demand and cached per host thread).  Synchronous: returns when h_dst is complete. */
+VACV_API int vacv_cuda_nv_resize_normalize_chw_host(const uint8_t* h_src, float* h_dst, int batch, int w, int h, int v_first,
+                                                    int w_out, int h_out, const float* h_mean, const float* h_stddev,
+                                                    int chunk_frames);
+
 /* ---- runtime helpers: the host layer (libvacv.so) reaches CUDA only through this C-ABI -----------
  * Thin wrappers over the CUDA runtime so that C/C++ host code needs no CUDA headers: device memory, pinned staging
  * memory (the reference's USE_CUDA allocator, src/common/va_cuda_allocator.cu:8-34, made checkable), copies,

@@ -490,3 +490,20 @@ def test_cuda_vs_golden_digests(vacv):
     }
     bad = [k for k, v in got.items() if gc.digest(host(v)[0]) != golden[k]]
     assert not bad, f"CUDA output differs from the reference digest for: {bad}"
+
+
+def test_host_buffer_pipeline_entry(vacv, oracle):
+    """vacv_cuda_nv_resize_normalize_chw_host: host pointers in/out, chunked + pipelined inside the library."""
+    w, h, wo, ho, b = 640, 360, 224, 224, 7
+    src = u8(23, b, w * h * 3 // 2)
+    h_in = torch.from_numpy(src).pin_memory()
+    h_out = torch.empty((b, 3, ho, wo), dtype=torch.float32).pin_memory()
+    for chunk in (3, 2, 16):   # ragged last chunk, more than two chunks (buffer reuse), single chunk
+        h_out.zero_()
+        vacv.nv_resize_normalize_chw_host(h_in, h_out, w, h, wo, ho, MEAN, STD, True, chunk)
+        want = oracle.nv_resize_normalize_chw(src, w, h, 1, wo, ho, MEAN, STD, batch=b, threads=4)
+        assert_same(h_out.numpy(), want)
+    pageable = torch.from_numpy(src.copy())          # pageable host memory also works
+    out2 = torch.empty((b, 3, ho, wo), dtype=torch.float32)
+    vacv.nv_resize_normalize_chw_host(pageable, out2, w, h, wo, ho, MEAN, STD, True, 4)
+    assert_same(out2.numpy(), want)
