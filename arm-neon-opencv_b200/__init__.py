@@ -36,6 +36,8 @@ _SIGS = {
     "vacv_cuda_warp_affine": [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i, _i, _i, _vp],
     "vacv_cuda_sums_u8": [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp],
     "vacv_cuda_finalize_mean_stddev": [_vp, _i, _i, _u64, _vp, _vp, _vp],
+    "vacv_cuda_sums_f32": [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp],
+    "vacv_cuda_finalize_mean_stddev_f64": [_vp, _i, _i, _u64, _vp, _vp, _vp],
     "vacv_cuda_normalize": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp],
     "vacv_cuda_nv_resize_normalize_chw": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp],
     "vacv_cuda_nv_resize_normalize_chw_host": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i],
@@ -262,3 +264,24 @@ def nv_resize_normalize_chw_host(h_src, h_out, w, h, w_out, h_out_, mean, std, v
     _check(lib.vacv_cuda_nv_resize_normalize_chw_host(h_src.data_ptr(), h_out.data_ptr(), b, w, h, int(bool(v_first)), w_out, h_out_,
                                                       C.cast(m, _vp), C.cast(s, _vp), chunk_frames))
     return h_out
+
+
+def sums_f32(src, layout, per_frame=False):
+    """fp64 per-channel (sum x, sum x^2) of fp32 pixels: float64 [sets, c, 2]."""
+    src = _dev(src, torch.float32)
+    if layout == NHWC:
+        b, h, w, c = src.shape
+    else:
+        b, c, h, w = src.shape
+    sums = torch.zeros((b if per_frame else 1, c, 2), dtype=torch.float64, device=src.device)
+    _check(lib.vacv_cuda_sums_f32(src.data_ptr(), b, w, h, c, layout, sums.data_ptr(), int(per_frame), _stream()))
+    return sums
+
+
+def finalize_mean_stddev_f64(sums, n_per_channel):
+    sums = _dev(sums, torch.float64)
+    sets, c = sums.shape[0], sums.shape[1]
+    mean = torch.empty((sets, c), dtype=torch.float32, device=sums.device)
+    std = torch.empty((sets, c), dtype=torch.float32, device=sums.device)
+    _check(lib.vacv_cuda_finalize_mean_stddev_f64(sums.data_ptr(), sets, c, n_per_channel, mean.data_ptr(), std.data_ptr(), _stream()))
+    return mean, std

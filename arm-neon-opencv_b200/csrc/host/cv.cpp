@@ -95,14 +95,20 @@ void normalize(const Tensor& src, Tensor& dst, const Tensor& mean, const Tensor&
     float* d_out = static_cast<float*>(ctx.scratch(1, dst.len()));
     float *d_mean, *d_std;
     if (mean.empty() && stddev.empty()) {   // normalize.cpp:98: statistics of the image itself
-        if (in.dtype != vision::INT8)
-            unsupported("automatic statistics of an FP32 tensor (exact integer sums are defined on u8 pixels)");
-        auto* d_sums = static_cast<unsigned long long*>(ctx.scratch(2, sizeof(unsigned long long) * 2 * in.c));
+        void* d_sums = ctx.scratch(2, 8 * 2 * in.c);   // u64 or fp64 counters
         d_mean = static_cast<float*>(ctx.scratch(3, sizeof(float) * 2 * in.c));
         d_std = d_mean + in.c;
-        ctx.check(vacv_cuda_memset(d_sums, 0, sizeof(unsigned long long) * 2 * in.c, ctx.stream()));
-        ctx.check(vacv_cuda_sums_u8(static_cast<const uint8_t*>(d_in), 1, in.w, in.h, in.c, in.layout, d_sums, 0, ctx.stream()));
-        ctx.check(vacv_cuda_finalize_mean_stddev(d_sums, 1, in.c, (unsigned long long)in.w * in.h, d_mean, d_std, ctx.stream()));
+        ctx.check(vacv_cuda_memset(d_sums, 0, 8 * 2 * in.c, ctx.stream()));
+        const unsigned long long n = (unsigned long long)in.w * in.h;
+        if (in.dtype == vision::INT8) {   // exact integer sums
+            auto* su = static_cast<unsigned long long*>(d_sums);
+            ctx.check(vacv_cuda_sums_u8(static_cast<const uint8_t*>(d_in), 1, in.w, in.h, in.c, in.layout, su, 0, ctx.stream()));
+            ctx.check(vacv_cuda_finalize_mean_stddev(su, 1, in.c, n, d_mean, d_std, ctx.stream()));
+        } else {                          // fp64 sums (exact for integer-valued pixels)
+            auto* sd = static_cast<double*>(d_sums);
+            ctx.check(vacv_cuda_sums_f32(static_cast<const float*>(d_in), 1, in.w, in.h, in.c, in.layout, sd, 0, ctx.stream()));
+            ctx.check(vacv_cuda_finalize_mean_stddev_f64(sd, 1, in.c, n, d_mean, d_std, ctx.stream()));
+        }
     } else {
         require_stats(mean, stddev, in.c);
         upload_stats(ctx, 3, mean, stddev, in.c, d_mean, d_std);

@@ -118,6 +118,57 @@ __global__ void sums_hwc_generic_kernel(const uint8_t* __restrict__ src, size_t 
         }
 }
 
+// fp32 pixels, any layout, c <= 4.  grid = (ctas, images); HWC: image = frame, channel = element index mod c;
+// CHW: image = plane, one channel per image.  fp64 accumulation, warp-shuffle tree, one atomicAdd(double) per CTA.
+template <int C>
+__global__ void __launch_bounds__(256) sums_f32_kernel(const float* __restrict__ src, size_t image_elems, int c_total,
+                                                        double* __restrict__ sums, int per_frame) {
+    const float* f = src + (size_t)blockIdx.y * image_elems;
+    double s[C], q[C];
+#pragma unroll
+    for (int k = 0; k < C; ++k) s[k] = q[k] = 0.0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned ph = (unsigned)(i % C);
+    const unsigned dph = (unsigned)(stride % C);
+    for (; i < image_elems; i += stride) {
+        const double v = (double)__ldg(f + i);
+#pragma unroll
+        for (int k = 0; k < C; ++k) if (ph == (unsigned)k) { s[k] += v; q[k] += v * v; }
+        ph += dph;
+        if (ph >= C) ph -= C;
+    }
+    __shared__ double part[8][2 * C];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < C; ++k) {
+        double a = s[k], b = q[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { a += __shfl_down_sync(0xffffffffu, a, o); b += __shfl_down_sync(0xffffffffu, b, o); }
+        if (lane == 0) { part[warp][2 * k] = a; part[warp][2 * k + 1] = b; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * C) {
+        double v = 0;
+        for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) v += part[wv][threadIdx.x];
+        // HWC (C == c_total): set = frame; planes (C == 1): image = frame * c_total + channel
+        const size_t frame = C == 1 ? blockIdx.y / c_total : blockIdx.y;
+        const int k0 = C == 1 ? 2 * (int)(blockIdx.y % c_total) : 0;
+        atomicAdd(sums + (per_frame ? frame * 2 * c_total : 0) + k0 + threadIdx.x, v);
+    }
+}
+
+__global__ void finalize_mean_stddev_f64_kernel(const double* __restrict__ sums, int total, double n,
+                                                float* __restrict__ mean, float* __restrict__ stddev) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const double m = sums[2 * i] / n;
+    double var = sums[2 * i + 1] / n - m * m;
+    if (var < 0) var = 0;
+    mean[i] = (float)m;
+    stddev[i] = (float)sqrt(var);
+}
+
 __global__ void finalize_mean_stddev_kernel(const unsigned long long* __restrict__ sums, int total, double n,
                                             float* __restrict__ mean, float* __restrict__ stddev) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;   // (set, channel) flattened
@@ -173,4 +224,32 @@ extern "C" int vacv_cuda_finalize_mean_stddev(const unsigned long long* sums, in
     const int total = n_sets * c;
     finalize_mean_stddev_kernel<<<ceil_div(total, 128), 128, 0, as_stream(stream)>>>(sums, total, (double)n_per_channel, mean, stddev);
     return check_launch("finalize_mean_stddev");
+}
+
+extern "C" int vacv_cuda_sums_f32(const float* src, int batch, int w, int h, int c, int layout, double* sums, int per_frame, void* stream) {
+    VACV_REQUIRE(src && sums, "sums_f32: null pointer");
+    VACV_REQUIRE(batch > 0 && w > 0 && h > 0 && c > 0, "sums_f32: non-positive size");
+    if (c > 4) return set_error(VACV_ERR_UNSUPPORTED, "sums_f32: c <= 4");
+    cudaStream_t s = as_stream(stream);
+    const size_t wh = (size_t)w * h;
+    const bool planes = layout == VACV_NCHW || c == 1;
+    const long long images = planes ? (long long)batch * c : batch;
+    VACV_REQUIRE(images <= 65535, "sums_f32: at most 65535 frames (planes) per call");
+    const size_t elems = planes ? wh : wh * c;
+    const unsigned ctas = (unsigned)max((size_t)1, min((elems + 256 * 16 - 1) / (256 * 16), (size_t)(kNumSMs * 16 / (size_t)images + 1)));
+    dim3 grid(ctas, (unsigned)images);
+    if (planes) sums_f32_kernel<1><<<grid, 256, 0, s>>>(src, elems, c, sums, per_frame);
+    else if (c == 2) sums_f32_kernel<2><<<grid, 256, 0, s>>>(src, elems, c, sums, per_frame);
+    else if (c == 3) sums_f32_kernel<3><<<grid, 256, 0, s>>>(src, elems, c, sums, per_frame);
+    else sums_f32_kernel<4><<<grid, 256, 0, s>>>(src, elems, c, sums, per_frame);
+    return check_launch("sums_f32");
+}
+
+extern "C" int vacv_cuda_finalize_mean_stddev_f64(const double* sums, int n_sets, int c, unsigned long long n_per_channel,
+                                                  float* mean, float* stddev, void* stream) {
+    VACV_REQUIRE(sums && mean && stddev, "finalize_mean_stddev_f64: null pointer");
+    VACV_REQUIRE(n_sets > 0 && c > 0 && n_per_channel > 0, "finalize_mean_stddev_f64: bad size");
+    const int total = n_sets * c;
+    finalize_mean_stddev_f64_kernel<<<ceil_div(total, 128), 128, 0, as_stream(stream)>>>(sums, total, (double)n_per_channel, mean, stddev);
+    return check_launch("finalize_mean_stddev_f64");
 }

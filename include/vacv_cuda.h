@@ -108,6 +108,13 @@ VACV_API int vacv_cuda_sums_u8(const uint8_t* src, int batch, int w, int h, int 
 VACV_API int vacv_cuda_finalize_mean_stddev(const unsigned long long* sums, int n_sets, int c,
                                             unsigned long long n_per_channel, float* mean, float* stddev, void* stream);
 
+/* fp32 pixels (the reference computes statistics on the fp32 copy, normalize.cpp:92-108): sums in fp64, [2k]=Sx, [2k+1]=Sxx.
+ * Exact -- and therefore identical to the u8 path -- whenever the data are integer-valued (pixels converted from u8);
+ * for general fp32 data the cross-CTA summation order is not fixed (last-bit differences in fp64). */
+VACV_API int vacv_cuda_sums_f32(const float* src, int batch, int w, int h, int c, int layout, double* sums, int per_frame, void* stream);
+VACV_API int vacv_cuda_finalize_mean_stddev_f64(const double* sums, int n_sets, int c, unsigned long long n_per_channel,
+                                                float* mean, float* stddev, void* stream);
+
 /* ---- a12: NormalizeNaive::normalize_naive_{hwc_bgr,chw} (src/cv/normalize_naive.cpp:74-90) -----------------
  * dst = (float)((double)(x - mean[k]) / ((double)stddev[k] + 1e-6)), x converted from u8 first when
  * src_dtype == INT8 (normalize.cpp:92-95).  mean/stddev: c floats (stats_per_frame = 0) or batch x c. */

@@ -428,6 +428,25 @@ void orc_sums_u8(const uint8_t* src, size_t pixels, int c, int layout, uint64_t*
         sums[2 * k] += sx; sums[2 * k + 1] += sxx;
     }
 }
+void orc_sums_f32(const float* src, size_t pixels, int c, int layout, double* sums) {
+    for (int k = 0; k < c; ++k) {
+        double sx = 0, sxx = 0;
+        for (size_t i = 0; i < pixels; ++i) {
+            double v = layout == 1 ? src[i * c + k] : src[(size_t)k * pixels + i];
+            sx += v; sxx += v * v;
+        }
+        sums[2 * k] += sx; sums[2 * k + 1] += sxx;
+    }
+}
+void orc_finalize_mean_stddev_f64(const double* sums, int c, uint64_t n, float* mean, float* stddev) {
+    for (int k = 0; k < c; ++k) {
+        double m = sums[2 * k] / (double)n;
+        double var = sums[2 * k + 1] / (double)n - m * m;
+        if (var < 0) var = 0;
+        mean[k] = (float)m;
+        stddev[k] = (float)sqrt(var);
+    }
+}
 void orc_finalize_mean_stddev(const uint64_t* sums, int c, uint64_t n, float* mean, float* stddev) {
     for (int k = 0; k < c; ++k) {
         double m = (double)sums[2 * k] / (double)n;

@@ -76,6 +76,9 @@ void orc_warp_affine_f32(const float* src, int w, int h, int c, int layout,
 /* Exact statistics (decision App. C-4): per-channel sum and sum of squares in u64. sums[2*k]=Sx, [2*k+1]=Sxx.
  * They are ACCUMULATED into sums (caller zeroes). */
 void orc_sums_u8(const uint8_t* src, size_t pixels, int c, int layout, uint64_t* sums);
+/* fp32 pixels: the same two sums accumulated in fp64 (exact for integer-valued data). ACCUMULATED into sums. */
+void orc_sums_f32(const float* src, size_t pixels, int c, int layout, double* sums);
+void orc_finalize_mean_stddev_f64(const double* sums, int c, uint64_t n_per_channel, float* mean, float* stddev);
 /* mean = Sx/N, std = sqrt(max(Sxx/N - mean^2, 0)) in double, rounded to fp32. */
 void orc_finalize_mean_stddev(const uint64_t* sums, int c, uint64_t n_per_channel, float* mean, float* stddev);
 /* normalize_naive.cpp:7-72 verbatim semantics (sequential fp32) -- for reporting the deviation only. */

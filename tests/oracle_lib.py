@@ -165,6 +165,19 @@ class Oracle:
         self.lib.orc_sums_u8(_ptr(src), C.c_size_t(pixels), _i(c), _i(layout), _ptr(sums))
         return sums
 
+    def sums_f32(self, src, pixels, c, layout):
+        src = _c(src, np.float32)
+        sums = np.zeros(2 * c, np.float64)
+        self.lib.orc_sums_f32(_ptr(src), C.c_size_t(pixels), _i(c), _i(layout), _ptr(sums))
+        return sums
+
+    def finalize_mean_stddev_f64(self, sums, c, n):
+        sums = _c(sums, np.float64)
+        mean = np.empty(c, np.float32)
+        std = np.empty(c, np.float32)
+        self.lib.orc_finalize_mean_stddev_f64(_ptr(sums), _i(c), C.c_uint64(n), _ptr(mean), _ptr(std))
+        return mean, std
+
     def finalize_mean_stddev(self, sums, c, n):
         sums = _c(sums, np.uint64)
         mean = np.empty(c, np.float32)

@@ -507,3 +507,47 @@ def test_host_buffer_pipeline_entry(vacv, oracle):
     out2 = torch.empty((b, 3, ho, wo), dtype=torch.float32)
     vacv.nv_resize_normalize_chw_host(pageable, out2, w, h, wo, ho, MEAN, STD, True, 4)
     assert_same(out2.numpy(), want)
+
+
+# ------------------------------------------------------------------ the reference's OWN test-suite on the drop-in
+def test_reference_test_suite_links_and_passes_on_dropin(vacv):
+    """oracle/_ref/va_cv_ut_b200 = the reference's src/test sources, compiled unmodified, linked against libvacv.so.
+    Every case must score at least what the same suite scores against the reference itself (va_cv_ut_ref)."""
+    import os
+    import subprocess
+    ref_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")
+    b200, ref = os.path.join(ref_dir, "va_cv_ut_b200"), os.path.join(ref_dir, "va_cv_ut_ref")
+    if not (os.path.exists(b200) and os.path.exists(ref) and os.path.isdir(os.path.join(ref_dir, "res"))):
+        pytest.skip("oracle/_ref test-suite binaries not staged (make -C oracle ref)")
+
+    def run(exe):
+        out = subprocess.run([exe], cwd=ref_dir, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+        return {l.split()[1]: float(l.split()[2]) for l in out.stdout.splitlines() if l.startswith("CASE ")}
+
+    ours, theirs = run(b200), run(ref)
+    assert len(ours) == 36 and ours.keys() == theirs.keys()
+    passed = lambda d: sum(abs(v - 1.0) <= 5e-4 for v in d.values())      # the reference's criterion (cv_profile.cpp:10,108)
+    worse = {k: (ours[k], theirs[k]) for k in ours if abs(ours[k] - 1.0) > abs(theirs[k] - 1.0) + 2e-4}
+    print(f"reference suite: drop-in passes {passed(ours)}/36, reference itself passes {passed(theirs)}/36")
+    assert not worse, f"cases where the drop-in scores worse than the reference: {worse}"
+    assert passed(ours) >= passed(theirs)
+
+
+@pytest.mark.parametrize("layout", [NHWC, NCHW])
+def test_sums_f32_statistics(vacv, oracle, layout):
+    """fp32 pixels (integer-valued, as after change_dtype): fp64 sums are exact -> same statistics as the u8 path."""
+    w, h, c, b = 284, 214, 3, 2
+    shape = (b, h, w, c) if layout == NHWC else (b, c, h, w)
+    src8 = u8(24, *shape)
+    src = src8.astype(np.float32)
+    sums = host(vacv.sums_f32(dev(src), layout, per_frame=True))
+    for i in range(b):
+        want = oracle.sums_f32(src[i], w * h, c, layout)
+        assert np.array_equal(sums[i].ravel(), want)
+        assert np.array_equal(want, oracle.sums_u8(src8[i], w * h, c, layout).astype(np.float64))
+    mean, std = vacv.finalize_mean_stddev_f64(vacv.sums_f32(dev(src), layout), b * w * h)
+    tot = sum(oracle.sums_f32(src[i], w * h, c, layout) for i in range(b))
+    m_o, s_o = oracle.finalize_mean_stddev_f64(tot, c, b * w * h)
+    assert_same(host(mean)[0], m_o)
+    assert_same(host(std)[0], s_o)
