@@ -67,16 +67,18 @@ __global__ void __launch_bounds__(kTileX * kTileY) resize_linear_u8_kernel(const
 // stores per pixel and is LSU-bound; here the 6 contiguous bytes of a tap row (2 pixels x BGR) come from 2-3 aligned
 // 32-bit words + funnel shifts, and each warp (32 consecutive pixels of one output row) re-chunks its 96 output bytes
 // through shared memory into lane-contiguous 32-bit stores.
+constexpr int kC3Rows = 32;   // output rows per CTA of the u8c3 kernel (4 passes of 8 rows): amortises the coefficient set-up
+
 template <bool kSigned, bool kNeonRule>
 __global__ void __launch_bounds__(kTileX * kTileY) resize_linear_u8c3_kernel(const uint8_t* __restrict__ src,
                                                                               uint8_t* __restrict__ dst, ResizeGeom g) {
-    __shared__ int s_sx[kTileX], s_cx[kTileX], s_sy[kTileY], s_cy[kTileY];
+    __shared__ int s_sx[kTileX], s_cx[kTileX], s_sy[kC3Rows], s_cy[kC3Rows];
     __shared__ __align__(16) uint32_t stage[kTileY][24];
-    const int dx0 = blockIdx.x * kTileX, dy0 = blockIdx.y * kTileY;
+    const int dx0 = blockIdx.x * kTileX, dy00 = blockIdx.y * kC3Rows;
     const int t = threadIdx.y * kTileX + threadIdx.x;
-    if (t < kTileX + kTileY) {
+    if (t < kTileX + kC3Rows) {
         const bool isx = t < kTileX;
-        const int d = isx ? dx0 + t : dy0 + (t - kTileX);
+        const int d = isx ? dx0 + t : dy00 + (t - kTileX);
         const int n_in = isx ? g.w : g.h, n_out = isx ? g.wo : g.ho;
         const double scale = kNeonRule ? (double)n_in / (double)n_out : (double)((float)n_in / (float)n_out);
         int s; float f;
@@ -86,39 +88,45 @@ __global__ void __launch_bounds__(kTileX * kTileY) resize_linear_u8c3_kernel(con
         else { s_sy[t - kTileX] = s; s_cy[t - kTileX] = (c0 & 0xffff) | (c1 << 16); }
     }
     __syncthreads();
-    const int lane = threadIdx.x, dx = dx0 + lane, dy = dy0 + threadIdx.y;
-    if (dy >= g.ho) return;   // whole warp
+    const int lane = threadIdx.x;
     const int n = min(32, g.wo - dx0);
-    const int sx = s_sx[lane], sy = s_sy[threadIdx.y];
-    const int cx0 = (short)(s_cx[lane] & 0xffff), cx1 = s_cx[lane] >> 16;
-    const int cy0 = (short)(s_cy[threadIdx.y] & 0xffff), cy1 = s_cy[threadIdx.y] >> 16;
-    const uint8_t* img = src + blockIdx.z * g.src_image;
-    int v[3] = {0, 0, 0};
-    if (lane < n) {
-        const size_t a = ((size_t)sy * g.w + sx) * 3;
-        uint32_t t0, t1, u0, u1;
-        linear_taps_u8c3(img, a, t0, t1);
-        linear_taps_u8c3(img, a + (size_t)g.w * 3, u0, u1);
-        const int p00[3] = {pix<kSigned>((uint8_t)t0), pix<kSigned>((uint8_t)(t0 >> 8)), pix<kSigned>((uint8_t)(t0 >> 16))};
-        const int p01[3] = {pix<kSigned>((uint8_t)(t0 >> 24)), pix<kSigned>((uint8_t)t1), pix<kSigned>((uint8_t)(t1 >> 8))};
-        const int p10[3] = {pix<kSigned>((uint8_t)u0), pix<kSigned>((uint8_t)(u0 >> 8)), pix<kSigned>((uint8_t)(u0 >> 16))};
-        const int p11[3] = {pix<kSigned>((uint8_t)(u0 >> 24)), pix<kSigned>((uint8_t)u1), pix<kSigned>((uint8_t)(u1 >> 8))};
+    const unsigned sx3 = (unsigned)s_sx[lane] * 3u;
+    const uint32_t cx = (uint32_t)s_cx[lane];   // cx0 | cx1 << 16
+    const uint8_t* img = src + blockIdx.z * g.src_image;   // every byte offset inside one image fits 32 bits (host check)
+    const unsigned row3 = (unsigned)g.w * 3u;
+    uint8_t* sb = reinterpret_cast<uint8_t*>(stage[threadIdx.y]);
+    uint8_t* o = dst + blockIdx.z * g.dst_image + ((size_t)(dy00 + threadIdx.y) * g.wo + dx0) * 3;
+    const size_t o_step = (size_t)kTileY * g.wo * 3;
+#pragma unroll 2
+    for (int pass = 0; pass < kC3Rows / kTileY; ++pass, o += o_step) {
+        const int ry = pass * kTileY + threadIdx.y;
+        if (dy00 + ry >= g.ho) break;   // whole warp
+        const int cy0 = (short)(s_cy[ry] & 0xffff), cy1 = s_cy[ry] >> 16;
+        int v[3] = {0, 0, 0};
+        if (lane < n) {
+            const unsigned a = (unsigned)s_sy[ry] * row3 + sx3;
+            uint32_t t0, t1, u0, u1;
+            linear_taps_u8c3(img, a, t0, t1);
+            linear_taps_u8c3(img, a + row3, u0, u1);
+            int Ht[3], Hb[3];
+            hsum_u8c3<kSigned>(t0, t1, cx, Ht);   // p00*cx0 + p01*cx1
+            hsum_u8c3<kSigned>(u0, u1, cx, Hb);   // p10*cx0 + p11*cx1
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            if (kNeonRule) {
-                const int r0 = (short)((p00[k] * cx0 + p01[k] * cx1) >> 4), r1 = (short)((p10[k] * cx0 + p11[k] * cx1) >> 4);
-                v[k] = clamp255(((short)((cy0 * r0) >> 16) + (short)((cy1 * r1) >> 16) + 2) >> 2);
-            } else {
-                v[k] = (p00[k] * cx0 * cy0 + p10[k] * cx0 * cy1 + p01[k] * cx1 * cy0 + p11[k] * cx1 * cy1) >> 22;   // :60-65
+            for (int k = 0; k < 3; ++k) {
+                if (kNeonRule) {   // resize_neon.cpp:145-181
+                    const int r0 = (short)(Ht[k] >> 4), r1 = (short)(Hb[k] >> 4);
+                    v[k] = clamp255(((short)((cy0 * r0) >> 16) + (short)((cy1 * r1) >> 16) + 2) >> 2);
+                } else {           // resize_naive.cpp:60-65, the same integer regrouped row-wise (no overflow: < 2^31)
+                    v[k] = (Ht[k] * cy0 + Hb[k] * cy1) >> 22;
+                }
             }
         }
+        sb[3 * lane] = (uint8_t)v[0]; sb[3 * lane + 1] = (uint8_t)v[1]; sb[3 * lane + 2] = (uint8_t)v[2];
+        __syncwarp();
+        if ((reinterpret_cast<uintptr_t>(o) & 3) == 0 && n == 32) { if (lane < 24) st_stream4(o + 4 * lane, stage[threadIdx.y][lane]); }
+        else for (int bb = lane; bb < 3 * n; bb += 32) o[bb] = sb[bb];
+        __syncwarp();
     }
-    uint8_t* sb = reinterpret_cast<uint8_t*>(stage[threadIdx.y]);
-    sb[3 * lane] = (uint8_t)v[0]; sb[3 * lane + 1] = (uint8_t)v[1]; sb[3 * lane + 2] = (uint8_t)v[2];
-    __syncwarp();
-    uint8_t* o = dst + blockIdx.z * g.dst_image + ((size_t)dy * g.wo + dx0) * 3;
-    if ((reinterpret_cast<uintptr_t>(o) & 3) == 0 && n == 32) { if (lane < 24) st_stream4(o + 4 * lane, stage[threadIdx.y][lane]); }
-    else for (int b = lane; b < 3 * n; b += 32) o[b] = sb[b];
 }
 
 // ----------------------------------------------------------------------------------------------------
@@ -303,9 +311,10 @@ extern "C" int vacv_cuda_resize(const void* src, void* dst, int batch, int w, in
         dim3 grid(ceil_div(w_out, kTileX), ceil_div(h_out, kTileY), ni);
         const uint8_t* sp = (const uint8_t*)src + (size_t)i0 * g.src_image * es;
         uint8_t* dp = (uint8_t*)dst + (size_t)i0 * g.dst_image * es;
-        const bool c3_words = g.c == 3 && (((size_t)w * h * 3) % 4) == 0 && ((uintptr_t)src % 4) == 0;
+        const bool c3_words = g.c == 3 && (((size_t)w * h * 3) % 4) == 0 && ((uintptr_t)src % 4) == 0 && (size_t)w * h * 3 < 0xfffffff0ull;
         if (!cubic && dtype == VACV_INT8 && c3_words) {
             const bool sc = flags & VACV_FLAG_SIGNED_CHAR;
+            grid.y = ceil_div(h_out, kC3Rows);
             if (flags & VACV_FLAG_NEON_RULE) resize_linear_u8c3_kernel<false, true><<<grid, block, 0, s>>>(sp, dp, g);
             else if (sc) resize_linear_u8c3_kernel<true, false><<<grid, block, 0, s>>>(sp, dp, g);
             else resize_linear_u8c3_kernel<false, false><<<grid, block, 0, s>>>(sp, dp, g);

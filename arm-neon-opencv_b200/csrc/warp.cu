@@ -4,6 +4,7 @@
 // Matrix inversion / rotation-matrix construction stay on the host (vacv_host.cpp) with the reference's mixed
 // float/double arithmetic; the device evaluates fx = (m0*dx + m1*dy) + m2 in fp32 with no FMA contraction.
 // One launch covers a whole batch of crops; each crop reads its own frame of a device-resident frame pool.
+#include "gather_u8c3.cuh"
 #include "vacv_common.cuh"
 
 namespace vacv {
@@ -122,16 +123,6 @@ __global__ void __launch_bounds__(256) warp_affine_normalize_kernel(const uint8_
 // lane-contiguous (96 B of u8, or 3 x 128 B of fp32) instead of 3 strided partial-sector stores per lane.
 enum { kWarpOutU8 = 0, kWarpOutF32HWC = 1, kWarpOutF32CHW = 2 };
 
-template <bool kSigned>
-__device__ __forceinline__ void taps_u8c3(const uint8_t* __restrict__ img, int a, int (&pl)[3], int (&pr)[3]) {
-    const uint32_t* wp = reinterpret_cast<const uint32_t*>(img + (a & ~3));
-    const int sh = (a & 3) * 8;
-    const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = (a & 3) == 3 ? __ldg(wp + 2) : 0u;
-    const uint32_t b0 = __funnelshift_r(w0, w1, sh), b1 = __funnelshift_r(w1, w2, sh);   // [L.b L.g L.r R.b] [R.g R.r . .]
-    pl[0] = pix<kSigned>((uint8_t)b0); pl[1] = pix<kSigned>((uint8_t)(b0 >> 8)); pl[2] = pix<kSigned>((uint8_t)(b0 >> 16));
-    pr[0] = pix<kSigned>((uint8_t)(b0 >> 24)); pr[1] = pix<kSigned>((uint8_t)b1); pr[2] = pix<kSigned>((uint8_t)(b1 >> 8));
-}
-
 // grid = (crops, bands); each CTA walks pixels [y0*wo, y1*wo) of its crop in flat order (a warp = 32 consecutive pixels)
 template <int OUT, bool kSigned>
 __global__ void __launch_bounds__(256) warp_affine_u8c3_kernel(const uint8_t* __restrict__ frames, const int* __restrict__ frame_idx,
@@ -160,13 +151,16 @@ __global__ void __launch_bounds__(256) warp_affine_u8c3_kernel(const uint8_t* __
             const int dy = i / g.wo, dx = i - dy * g.wo;
             const Taps t = warp_taps(m, dx, dy, g.w, g.h);
             if (t.in) {
-                int tl[3], tr[3], bl[3], br[3];
-                taps_u8c3<kSigned>(img, t.ofs * 3, tl, tr);
-                taps_u8c3<kSigned>(img, t.ofs * 3 + row, bl, br);
-                const int w00 = t.cx0 * t.cy0, w10 = t.cx0 * t.cy1, w01 = t.cx1 * t.cy0, w11 = t.cx1 * t.cy1;
+                uint32_t t0, t1, u0, u1;
+                linear_taps_u8c3(img, (unsigned)t.ofs * 3u, t0, t1);
+                linear_taps_u8c3(img, (unsigned)t.ofs * 3u + (unsigned)row, u0, u1);
+                const uint32_t cx = (uint32_t)t.cx0 | ((uint32_t)t.cx1 << 16);
+                int Ht[3], Hb[3];
+                hsum_u8c3<kSigned>(t0, t1, cx, Ht);   // p00*cx0 + p01*cx1 (two PRMT + three IDP.2A)
+                hsum_u8c3<kSigned>(u0, u1, cx, Hb);   // p10*cx0 + p11*cx1
 #pragma unroll
-                for (int k = 0; k < 3; ++k)   // warp_affine_naive.cpp:50-54: same integer, products regrouped
-                    v[k] = ((tl[k] * w00 + bl[k] * w10 + tr[k] * w01 + br[k] * w11) >> 22) & 0xff;
+                for (int k = 0; k < 3; ++k)   // warp_affine_naive.cpp:50-54: the same integer regrouped row-wise
+                    v[k] = ((Ht[k] * t.cy0 + Hb[k] * t.cy1) >> 22) & 0xff;
             }
         }
         const int n = min(32, i_end - i0);   // valid pixels of this warp
@@ -216,7 +210,7 @@ extern "C" int vacv_cuda_warp_affine(const void* frames, int n_frames, int w, in
     WarpGeom g;
     g.w = w; g.h = h; g.c = c; g.wo = w_out; g.ho = h_out; g.frame_elems = (size_t)w * h * c; g.planar = layout == VACV_NCHW;
     cudaStream_t s = as_stream(stream);
-    const bool words_ok = (((size_t)w * h * 3) % 4) == 0 && ((uintptr_t)frames % 4) == 0;
+    const bool words_ok = (((size_t)w * h * 3) % 4) == 0 && ((uintptr_t)frames % 4) == 0 && (size_t)w * h * 3 < 0xfffffff0ull;
     if (dtype == VACV_INT8 && c == 3 && layout == VACV_NHWC && words_ok) {
         const int rows_per_cta = max(1, min(h_out, (4096 + w_out - 1) / w_out));
         dim3 grid(n_crops, ceil_div(h_out, rows_per_cta));
@@ -253,7 +247,7 @@ extern "C" int vacv_cuda_warp_affine_normalize(const uint8_t* frames, int n_fram
     const int rows_per_cta = max(1, min(h_out, (8192 + w_out - 1) / w_out));
     dim3 grid(n_crops, ceil_div(h_out, rows_per_cta));
     cudaStream_t s = as_stream(stream);
-    if (c == 3 && (((size_t)w * h * 3) % 4) == 0 && ((uintptr_t)frames % 4) == 0) {
+    if (c == 3 && (((size_t)w * h * 3) % 4) == 0 && ((uintptr_t)frames % 4) == 0 && (size_t)w * h * 3 < 0xfffffff0ull) {
         if (out_layout == VACV_NHWC) warp_affine_u8c3_kernel<kWarpOutF32HWC, false><<<grid, 256, 0, s>>>(frames, frame_idx, minv, dst, g, mean, stddev, rows_per_cta, 0);
         else warp_affine_u8c3_kernel<kWarpOutF32CHW, false><<<grid, 256, 0, s>>>(frames, frame_idx, minv, dst, g, mean, stddev, rows_per_cta, 0);
         return check_launch("warp_affine_normalize");

@@ -193,6 +193,43 @@ def ops(iters):
     report("op resize_normalize u8 hwc 1080p->640x640 chw x128", ms, b * 640 * 640, b * (1920 * 1080 * 3 + 640 * 640 * 12))
 
 
+def ops2(iters):   # shapes off the headline path: planar layouts, fp32 gathers, generic channel counts
+    b = 64
+    bgr = rand_u8(b, 1080, 1920, 3)
+    chw = vacv.layout_change(bgr, vacv.NHWC, vacv.NCHW)
+    f = bgr[:16].to(torch.float32)
+    fchw = chw[:16].to(torch.float32)
+    mean, std = stats()
+    ms, _ = timeit(lambda: vacv.resize(chw, vacv.NCHW, 640, 360), iters)
+    report("op2 resize linear u8 chw 1080p->640x360 x64", ms, b * 640 * 360, b * (1920 * 1080 * 3 * 2 // 3 + 640 * 360 * 3), "2 of 3 rows touched")
+    ms, _ = timeit(lambda: vacv.resize(f, vacv.NHWC, 640, 360), iters)
+    report("op2 resize linear f32 hwc 1080p->640x360 x16", ms, 16 * 640 * 360, 16 * 4 * (1920 * 1080 * 3 * 2 // 3 + 640 * 360 * 3), "2 of 3 rows touched")
+    ms, _ = timeit(lambda: vacv.resize(f, vacv.NHWC, 1280, 720), iters)
+    report("op2 resize linear f32 hwc 1080p->1280x720 x16", ms, 16 * 1280 * 720, 16 * 4 * (1920 * 1080 * 3 + 1280 * 720 * 3))
+    ms, _ = timeit(lambda: vacv.resize(bgr, vacv.NHWC, 1280, 720), iters)
+    report("op2 resize linear u8 hwc 1080p->1280x720 x64", ms, b * 1280 * 720, b * (1920 * 1080 * 3 + 1280 * 720 * 3))
+    ms, _ = timeit(lambda: vacv.resize(chw, vacv.NCHW, 1280, 720, vacv.INTER_CUBIC) if False else vacv.resize(fchw, vacv.NCHW, 1280, 720, vacv.INTER_CUBIC), iters)
+    report("op2 resize cubic f32 chw 1080p->1280x720 x16", ms, 16 * 1280 * 720, 16 * 4 * (1920 * 1080 * 3 + 1280 * 720 * 3))
+    ms, _ = timeit(lambda: vacv.normalize(chw, vacv.NCHW, mean, std), iters)
+    report("op2 normalize u8 chw 1080p x64", ms, b * 1920 * 1080, b * 1920 * 1080 * 15)
+    ms, _ = timeit(lambda: vacv.crop(chw, vacv.NCHW, 321, 181, 1280, 720), iters)
+    report("op2 crop u8 chw 1080p->1280x720 x64", ms, b * 1280 * 720, b * 1280 * 720 * 6)
+    ms, _ = timeit(lambda: vacv.crop(f, vacv.NHWC, 321, 181, 1280, 720), iters)
+    report("op2 crop f32 hwc 1080p->1280x720 x16", ms, 16 * 1280 * 720, 16 * 1280 * 720 * 24)
+    n, nf = 1024, 64
+    frames = bgr[:nf].to(torch.float32)
+    minv, _ = face_matrices(n, 1920, 1080, 112)
+    idx = (torch.arange(n, device="cuda") % nf).to(torch.int32)
+    ms, _ = timeit(lambda: vacv.warp_affine(frames, vacv.NHWC, minv, 112, 112, idx), iters)
+    report("op2 warp_affine f32 hwc 1080p->112x112 x1024", ms, n * 112 * 112, n * (250000 * 4 + 112 * 112 * 12))
+    grey = rand_u8(nf, 1080, 1920, 1)
+    ms, _ = timeit(lambda: vacv.warp_affine(grey, vacv.NHWC, minv, 112, 112, idx), iters)
+    report("op2 warp_affine u8 grey 1080p->112x112 x1024", ms, n * 112 * 112, n * (83000 + 112 * 112))
+    rgba = rand_u8(b, 1080, 1920, 4)
+    ms, _ = timeit(lambda: vacv.layout_change(rgba, vacv.NHWC, vacv.NCHW), iters)
+    report("op2 layout hwc->chw u8 c=4 1080p x64", ms, b * 1920 * 1080, b * 1920 * 1080 * 8)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="all")
@@ -216,6 +253,8 @@ def main():
         c4(args.iters)
     if wl in ("all", "ops"):
         ops(args.iters)
+    if wl in ("ops2",):
+        ops2(args.iters)
     if wl in ("all", "c5"):
         c5(max(3, args.iters // 4))
     if args.json and int(os.environ.get("RANK", 0)) == 0:
