@@ -40,6 +40,7 @@ _SIGS = {
     "vacv_cuda_finalize_mean_stddev_f64": [_vp, _i, _i, _u64, _vp, _vp, _vp],
     "vacv_cuda_normalize": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp],
     "vacv_cuda_nv_resize_normalize_chw": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp],
+    "vacv_cuda_yuv_resize_normalize_chw": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp],
     "vacv_cuda_nv_resize_normalize_chw_host": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i],
     "vacv_cuda_resize_normalize": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp],
     "vacv_cuda_warp_affine_normalize": [_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _vp],
@@ -226,6 +227,34 @@ def nv_resize_normalize_chw(src, w, h, w_out, h_out, mean, std, v_first=True, ou
     dst = out if out is not None else torch.empty((b, 3, h_out, w_out), dtype=torch.float32, device=src.device)
     _check(lib.vacv_cuda_nv_resize_normalize_chw(src.data_ptr(), dst.data_ptr(), b, w, h, int(bool(v_first)), w_out, h_out,
                                                  mean.data_ptr(), std.data_ptr(), _stream()))
+    return dst
+
+
+YUV_NV21, YUV_NV12, YUV_I420, YUV_YV12 = 0, 1, 2, 3
+
+
+class YuvLayout(C.Structure):
+    """Mirror of vacv_yuv_layout (include/vacv_cuda.h)."""
+    _fields_ = [("format", C.c_int), ("w", C.c_int), ("h", C.c_int), ("y_pitch", C.c_int), ("c_pitch", C.c_int),
+                ("frame_stride", C.c_size_t)]
+
+
+def yuv_resize_normalize_chw(src, fmt, w, h, w_out, h_out, mean, std, y_pitch=0, c_pitch=0, frame_stride=0, batch=None,
+                             half=False, out=None):
+    """Fused pipeline on pitched / planar decoder surfaces; fp32 or fp16 CHW planes out.  src: uint8 device tensor holding
+    `batch` frames `frame_stride` bytes apart (dense when 0)."""
+    src = _dev(src, torch.uint8)
+    mean, std = _dev(mean, torch.float32), _dev(std, torch.float32)
+    lay = YuvLayout(fmt, w, h, y_pitch, c_pitch, frame_stride)
+    if batch is None:
+        yp = y_pitch or w
+        cp = c_pitch or (w // 2 if fmt >= YUV_I420 else w)
+        per = frame_stride or (yp * h + cp * (h // 2) * (2 if fmt >= YUV_I420 else 1))
+        batch = src.numel() // per
+    dt = torch.float16 if half else torch.float32
+    dst = out if out is not None else torch.empty((batch, 3, h_out, w_out), dtype=dt, device=src.device)
+    _check(lib.vacv_cuda_yuv_resize_normalize_chw(src.data_ptr(), C.addressof(lay), dst.data_ptr(), FP16 if half else FP32, batch,
+                                                  w_out, h_out, mean.data_ptr(), std.data_ptr(), _stream()))
     return dst
 
 

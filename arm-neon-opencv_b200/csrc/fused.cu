@@ -197,21 +197,43 @@ static int host_linear_index(int d, double scale, int n_in) {
     return sx;
 }
 
-template <bool kVFirst>
-static const void* pipe_kernel_for(int ncol) {
+template <int FMT, typename OutT, bool kDense = false>
+static const void* pipe_kernel_ncol(int ncol) {
     switch (ncol) {
-        case 1: return (const void*)nv_resize_normalize_chw_pipe_kernel<kVFirst, 1>;
-        case 2: return (const void*)nv_resize_normalize_chw_pipe_kernel<kVFirst, 2>;
-        case 3: return (const void*)nv_resize_normalize_chw_pipe_kernel<kVFirst, 3>;
-        default: return (const void*)nv_resize_normalize_chw_pipe_kernel<kVFirst, 4>;
+        case 1: return (const void*)nv_resize_normalize_chw_pipe_kernel<FMT, OutT, 1, kDense>;
+        case 2: return (const void*)nv_resize_normalize_chw_pipe_kernel<FMT, OutT, 2, kDense>;
+        case 3: return (const void*)nv_resize_normalize_chw_pipe_kernel<FMT, OutT, 3, kDense>;
+        default: return (const void*)nv_resize_normalize_chw_pipe_kernel<FMT, OutT, 4, kDense>;
     }
 }
+template <int FMT>
+static const void* pipe_kernel_pairs(int ncol) {   // fp16 column pairs: even column counts only
+    return ncol <= 2 ? (const void*)nv_resize_normalize_chw_pipe_kernel<FMT, __half2, 2, false>
+                     : (const void*)nv_resize_normalize_chw_pipe_kernel<FMT, __half2, 4, false>;
+}
+static const void* pipe_kernel_for(int fmt, bool half_out, bool pairs, bool dense, int ncol) {
+    if (half_out && pairs) return fmt == kFmtVU ? pipe_kernel_pairs<kFmtVU>(ncol) : fmt == kFmtUV ? pipe_kernel_pairs<kFmtUV>(ncol) : pipe_kernel_pairs<kFmtPlanar>(ncol);
+    if (dense && !half_out && fmt != kFmtPlanar)   // the reference's own case keeps its dedicated instantiation
+        return fmt == kFmtVU ? pipe_kernel_ncol<kFmtVU, float, true>(ncol) : pipe_kernel_ncol<kFmtUV, float, true>(ncol);
+    if (half_out) return fmt == kFmtVU ? pipe_kernel_ncol<kFmtVU, __half>(ncol) : fmt == kFmtUV ? pipe_kernel_ncol<kFmtUV, __half>(ncol) : pipe_kernel_ncol<kFmtPlanar, __half>(ncol);
+    return fmt == kFmtVU ? pipe_kernel_ncol<kFmtVU, float>(ncol) : fmt == kFmtUV ? pipe_kernel_ncol<kFmtUV, float>(ncol) : pipe_kernel_ncol<kFmtPlanar, float>(ncol);
+}
+
+// Source description resolved from a vacv_yuv_layout (or the dense NV12/NV21 default).
+struct YuvSource {
+    int fmt;                 // kFmtVU / kFmtUV / kFmtPlanar
+    int w, h, y_pitch, c_pitch;
+    size_t frame_stride, c_off, c2_off;
+};
 
 // Returns 1 if the persistent TMA pipeline was launched, 0 if the shape does not qualify (caller falls back to the
-// tiled kernel), < 0 on error.
-static int try_launch_pipe(const uint8_t* src, float* dst, int batch, int w, int h, int v_first, int w_out, int h_out,
+// tiled kernel where one exists), < 0 on error.
+static int try_launch_pipe(const uint8_t* src, void* dst, bool half_out, int batch, const YuvSource& y, int w_out, int h_out,
                            const float* mean, const float* stddev, cudaStream_t s) {
-    if ((w % 16) != 0 || (((uintptr_t)src) & 15) != 0) return 0;             // bulk copies need 16-byte granularity
+    const int w = y.w, h = y.h;
+    // bulk copies need 16-byte granularity of every band start and length
+    if ((y.y_pitch % 16) != 0 || (y.c_pitch % 16) != 0 || (y.frame_stride % 16) != 0 || (y.c_off % 16) != 0 || (y.c2_off % 16) != 0 ||
+        (((uintptr_t)src) & 15) != 0) return 0;
     if (w_out > kPipeThreads * kPipeMaxCols || h_out > 8192) return 0;
     // row source indices, exactly as the device computes them -> exact band sizes per tile
     const double scale_y = (double)((float)h / (float)h_out);
@@ -221,6 +243,8 @@ static int try_launch_pipe(const uint8_t* src, float* dst, int batch, int w, int
     const int static_bytes = 768 * 4 + 64;
     PipeGeom g;
     g.w = w; g.h = h; g.wo = w_out; g.ho = h_out; g.table_bytes = table_bytes;
+    g.y_pitch = y.y_pitch; g.c_pitch = y.c_pitch; g.frame_stride = y.frame_stride; g.c_off = y.c_off; g.c2_off = y.c2_off;
+    const bool planar = y.fmt == kFmtPlanar;
     int best_TH = 0;
     size_t best_smem = 0;
     for (int TH = 8; TH >= 1; --TH) {
@@ -231,10 +255,12 @@ static int try_launch_pipe(const uint8_t* src, float* dst, int batch, int w, int
             yrows = std::max(yrows, y1 - y0 + 1);
             crows = std::max(crows, (y1 >> 1) - (y0 >> 1) + 1);
         }
-        const size_t ystage = ((size_t)yrows * w + 127) & ~(size_t)127, cstage = ((size_t)crows * w + 127) & ~(size_t)127;
+        const size_t ystage = ((size_t)yrows * y.y_pitch + 127) & ~(size_t)127;
+        const size_t cband = ((size_t)crows * y.c_pitch + 127) & ~(size_t)127;
+        const size_t cstage = planar ? 2 * cband : cband;
         const size_t smem = table_bytes + 2 * (ystage + cstage);
         if (smem + static_bytes <= 113 * 1024 || (TH == 1 && smem + static_bytes <= 226 * 1024)) {   // 2 CTAs / SM
-            best_TH = TH; best_smem = smem; g.ystage = (int)ystage; g.cstage = (int)cstage;
+            best_TH = TH; best_smem = smem; g.ystage = (int)ystage; g.cstage = (int)cstage; g.vstage_off = (int)cband;
             break;
         }
     }
@@ -263,8 +289,11 @@ static int try_launch_pipe(const uint8_t* src, float* dst, int batch, int w, int
     int ncol = (w_out + kPipeThreads - 1) / kPipeThreads;
     if (any_right && w_out <= 4 * 192) ncol = 4;
     if (const char* e = getenv("VACV_PIPE_NCOL")) { const int v = atoi(e); if (v >= 1 && v <= kPipeMaxCols && (w_out + v - 1) / v <= (v == 1 ? 640 : kPipeThreads)) ncol = v; }   // tuning knob
+    const bool pairs = half_out && (w_out % 2) == 0 && (((uintptr_t)dst) & 3) == 0;   // fp16: 32-bit stores of column pairs
+    if (pairs) ncol = ncol <= 2 ? 2 : 4;
     const int threads = std::min(ncol == 1 ? 640 : kPipeThreads, ((w_out + ncol - 1) / ncol + 31) & ~31);
-    const void* kern = v_first ? pipe_kernel_for<true>(ncol) : pipe_kernel_for<false>(ncol);
+    const bool dense = y.y_pitch == w && y.c_pitch == w && y.c_off == (size_t)w * h && y.frame_stride == (size_t)w * h * 3 / 2;
+    const void* kern = pipe_kernel_for(y.fmt, half_out, pairs, dense, ncol);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)best_smem);
     if (e != cudaSuccess) return set_error(VACV_ERR_CUDA, "nv_resize_normalize_chw: %s", cudaGetErrorString(e));
     int per_sm = 0;
@@ -289,7 +318,10 @@ extern "C" int vacv_cuda_nv_resize_normalize_chw(const uint8_t* src, float* dst,
     if (w_out == w && h_out == h)   // resize.cpp:58-61 memcpy shortcut == identity taps; not on the fused fast path
         return set_error(VACV_ERR_UNSUPPORTED, "nv_resize_normalize_chw: same-size resize (compose cvt_nv2bgr + normalize + layout_change)");
     cudaStream_t s = as_stream(stream);
-    if (int rc = try_launch_pipe(src, dst, batch, w, h, v_first, w_out, h_out, mean, stddev, s)) {
+    YuvSource ys;
+    ys.fmt = v_first ? kFmtVU : kFmtUV; ys.w = w; ys.h = h; ys.y_pitch = w; ys.c_pitch = w;
+    ys.frame_stride = (size_t)w * h * 3 / 2; ys.c_off = (size_t)w * h; ys.c2_off = 0;
+    if (int rc = try_launch_pipe(src, dst, false, batch, ys, w_out, h_out, mean, stddev, s)) {
         if (rc < 0) return rc;
         return check_launch("nv_resize_normalize_chw (persistent)");
     }
@@ -340,4 +372,42 @@ extern "C" int vacv_cuda_resize_normalize(const uint8_t* src, float* dst, int ba
     if (c == 3) resize_normalize_kernel<3><<<grid, 256, 0, s>>>(src, dst, w, h, w_out, h_out, rows_per_cta, mean, stddev, out_layout);
     else resize_normalize_kernel<1><<<grid, 256, 0, s>>>(src, dst, w, h, w_out, h_out, rows_per_cta, mean, stddev, out_layout);
     return check_launch("resize_normalize");
+}
+
+// Next-row extension of the fused pipeline: decoder-style surfaces (row pitch, planar I420 / YV12
+// chroma) in, fp32 or fp16 CHW planes out.  Same arithmetic as vacv_cuda_nv_resize_normalize_chw; fp16 = the exact fp32
+// result rounded to nearest-even.  Runs on the persistent TMA pipeline only (pitches / strides must be multiples of 16).
+extern "C" int vacv_cuda_yuv_resize_normalize_chw(const uint8_t* src, const vacv_yuv_layout* layout, void* dst, int out_dtype,
+                                                  int batch, int w_out, int h_out, const float* mean, const float* stddev, void* stream) {
+    VACV_REQUIRE(src && layout && dst && mean && stddev, "yuv_resize_normalize_chw: null pointer");
+    const int w = layout->w, h = layout->h;
+    VACV_REQUIRE(batch > 0 && w >= 2 && h >= 2 && w_out > 0 && h_out > 0, "yuv_resize_normalize_chw: bad size");
+    VACV_REQUIRE((w % 2) == 0 && (h % 2) == 0, "yuv_resize_normalize_chw: w and h must be even (got %dx%d)", w, h);
+    if (out_dtype != VACV_FP32 && out_dtype != VACV_FP16) return set_error(VACV_ERR_UNSUPPORTED, "yuv_resize_normalize_chw: out dtype %d (FP32 or FP16)", out_dtype);
+    if (w_out == w && h_out == h) return set_error(VACV_ERR_UNSUPPORTED, "yuv_resize_normalize_chw: same-size resize");
+    const bool planar = layout->format == VACV_YUV_I420 || layout->format == VACV_YUV_YV12;
+    if (!planar && layout->format != VACV_YUV_NV12 && layout->format != VACV_YUV_NV21)
+        return set_error(VACV_ERR_UNSUPPORTED, "yuv_resize_normalize_chw: format %d", layout->format);
+    YuvSource ys;
+    ys.w = w; ys.h = h;
+    ys.y_pitch = layout->y_pitch ? layout->y_pitch : w;
+    ys.c_pitch = layout->c_pitch ? layout->c_pitch : (planar ? w / 2 : w);
+    VACV_REQUIRE(ys.y_pitch >= w && ys.c_pitch >= (planar ? w / 2 : w), "yuv_resize_normalize_chw: pitch smaller than the row");
+    const size_t y_bytes = (size_t)ys.y_pitch * h, c_bytes = (size_t)ys.c_pitch * (h / 2);
+    ys.frame_stride = layout->frame_stride ? layout->frame_stride : y_bytes + (planar ? 2 * c_bytes : c_bytes);
+    VACV_REQUIRE(ys.frame_stride >= y_bytes + (planar ? 2 * c_bytes : c_bytes), "yuv_resize_normalize_chw: frame_stride too small");
+    if (planar) {
+        ys.fmt = kFmtPlanar;
+        const size_t first = y_bytes, second = y_bytes + c_bytes;
+        ys.c_off = layout->format == VACV_YUV_I420 ? first : second;    // U plane
+        ys.c2_off = layout->format == VACV_YUV_I420 ? second : first;   // V plane
+    } else {
+        ys.fmt = layout->format == VACV_YUV_NV21 ? kFmtVU : kFmtUV;
+        ys.c_off = y_bytes; ys.c2_off = 0;
+    }
+    const int rc = try_launch_pipe(src, dst, out_dtype == VACV_FP16, batch, ys, w_out, h_out, mean, stddev, as_stream(stream));
+    if (rc < 0) return rc;
+    if (rc == 0) return set_error(VACV_ERR_UNSUPPORTED, "yuv_resize_normalize_chw: layout not eligible for the TMA pipeline "
+                                  "(pitches, plane offsets and frame stride must be multiples of 16; w_out <= 1536)");
+    return check_launch("yuv_resize_normalize_chw");
 }

@@ -13,6 +13,8 @@
 //           cached per chroma row (two luma rows share one), H of the lower row is carried to the next output row
 //           when it starts there.  out = table[c][(H0*cy0 + H1*cy1) >> 22], stored 128 B / warp / plane, streaming.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "vacv_common.cuh"
 
 namespace vacv {
@@ -27,7 +29,14 @@ struct PipeGeom {
     int total_tiles;        // tiles_per_frame * batch
     int ystage, cstage;     // bytes reserved per stage for the Y / chroma band (multiples of 128)
     int table_bytes;        // bytes of the two row tables at the start of dynamic shared memory (multiple of 128)
+    // source layout (dense NV12/NV21: y_pitch = c_pitch = w, c_off = w*h, frame_stride = w*h*3/2)
+    int y_pitch, c_pitch;   // bytes per luma row / per chroma row (planar formats: per U or V row)
+    int vstage_off;         // planar formats: byte offset of the V band inside the chroma stage
+    size_t frame_stride;    // bytes between frames
+    size_t c_off, c2_off;   // byte offset of the chroma plane (semi-planar) / of the U and V planes (planar) inside a frame
 };
+
+enum { kFmtVU = 0, kFmtUV = 1, kFmtPlanar = 2 };   // interleaved chroma V-first (NV21), U-first (NV12), separate U and V planes (I420 / YV12)
 
 // ---- mbarrier / bulk-copy PTX (sm_90+; SASS on sm_100a: SYNCS.*, UBLKCP)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -65,11 +74,40 @@ struct ColState {
     int cx0, cx1;
 };
 
-template <bool kVFirst>
-__device__ __forceinline__ ChromaTerms terms_at(uint32_t addr) {
+template <int FMT>
+__device__ __forceinline__ ChromaTerms terms_at(uint32_t addr, int vstage_off) {
+    if (FMT == kFmtPlanar) return chroma_terms(lds_u8(addr + vstage_off), lds_u8(addr));   // (v, u)
     const unsigned p = lds_u16(addr);
-    return kVFirst ? chroma_terms(p & 0xff, p >> 8) : chroma_terms(p >> 8, p & 0xff);
+    return FMT == kFmtVU ? chroma_terms(p & 0xff, p >> 8) : chroma_terms(p >> 8, p & 0xff);
 }
+
+// normalisation table entry -> global memory.  OutT = float: fp32 planes; __half: fp16 planes, one 16-bit store per element
+// (odd w_out); __half2: fp16 planes, a thread owns column PAIRS and stores 32 bits (128 B per warp and store).
+template <typename OutT> struct OutOps;
+template <> struct OutOps<float> {
+    typedef float Lut;
+    enum { kElem = 4, kCols = 1 };
+    static __device__ __forceinline__ float make(float v) { return v; }
+    static __device__ __forceinline__ void copy(char* o, uint32_t lut, int k, unsigned v, unsigned) { st_stream4f(o, lds_f32(lut + k * 1024 + v * 4)); }
+};
+template <> struct OutOps<__half> {
+    typedef __half Lut;
+    enum { kElem = 2, kCols = 1 };
+    static __device__ __forceinline__ __half make(float v) { return __float2half_rn(v); }   // exact fp32 value rounded to nearest-even fp16
+    static __device__ __forceinline__ void copy(char* o, uint32_t lut, int k, unsigned v, unsigned) {
+        const unsigned short h = (unsigned short)lds_u16(lut + k * 512 + v * 2);
+        asm volatile("st.global.cs.u16 [%0], %1;" ::"l"(o), "h"(h) : "memory");
+    }
+};
+template <> struct OutOps<__half2> {
+    typedef __half Lut;
+    enum { kElem = 2, kCols = 2 };
+    static __device__ __forceinline__ __half make(float v) { return __float2half_rn(v); }
+    static __device__ __forceinline__ void copy(char* o, uint32_t lut, int k, unsigned v0, unsigned v1) {
+        const unsigned pair = lds_u16(lut + k * 512 + v0 * 2) | (lds_u16(lut + k * 512 + v1 * 2) << 16);
+        asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(o), "r"(pair) : "memory");
+    }
+};
 
 template <bool kRightTap>
 __device__ __forceinline__ void hrow_cached(uint32_t yaddr, const ColState& c, const ChromaTerms& ta,
@@ -88,9 +126,9 @@ __device__ __forceinline__ void hrow_cached(uint32_t yaddr, const ColState& c, c
 }
 
 // ybuf/cbuf/tab_sy/tab_cy/lut are shared-window addresses.  out[j] points at (frame, plane 0, row dy0, column of j).
-template <bool kVFirst, bool kRightTap, int NCOL>
+template <int FMT, typename OutT, bool kRightTap, int NCOL>
 __device__ __forceinline__ void compute_tile(uint32_t ybuf, uint32_t cbuf, uint32_t tab_sy, uint32_t tab_cy, uint32_t lut,
-                                             const ColState (&col)[NCOL], int dy0, int th, int w,
+                                             const ColState (&col)[NCOL], int dy0, int th, int y_pitch, int c_pitch, int vstage_off,
                                              char* (&out)[NCOL], size_t row_bytes, size_t plane_bytes) {
     const int y_first = lds_s32(tab_sy + 4 * dy0), c_first = y_first >> 1;
     int H0[NCOL][3], H1[NCOL][3];
@@ -99,15 +137,15 @@ __device__ __forceinline__ void compute_tile(uint32_t ybuf, uint32_t cbuf, uint3
     auto row = [&](int r, int (&H)[NCOL][3]) {
         const int cr = r >> 1;
         if (cr != have_c) {   // all threads walk the same rows: no divergence
-            const uint32_t crow = cbuf + (cr - c_first) * w;
+            const uint32_t crow = cbuf + (cr - c_first) * c_pitch;
 #pragma unroll
             for (int j = 0; j < NCOL; ++j) {
-                ta[j] = terms_at<kVFirst>(crow + col[j].ca);
-                if (kRightTap) tb[j] = terms_at<kVFirst>(crow + col[j].cb);
+                ta[j] = terms_at<FMT>(crow + col[j].ca, vstage_off);
+                if (kRightTap) tb[j] = terms_at<FMT>(crow + col[j].cb, vstage_off);
             }
             have_c = cr;
         }
-        const uint32_t yrow = ybuf + (r - y_first) * w;
+        const uint32_t yrow = ybuf + (r - y_first) * y_pitch;
 #pragma unroll
         for (int j = 0; j < NCOL; ++j) hrow_cached<kRightTap>(yrow + col[j].yo, col[j], ta[j], tb[j], H[j]);
     };
@@ -125,13 +163,16 @@ __device__ __forceinline__ void compute_tile(uint32_t ybuf, uint32_t cbuf, uint3
             row(sy + 1, H1);
             have = sy + 1;
         }
+        constexpr int kCols = OutOps<OutT>::kCols;
 #pragma unroll
-        for (int j = 0; j < NCOL; ++j) {
+        for (int j = 0; j < NCOL; j += kCols) {
             char* o = out[j];
+            constexpr int j1 = kCols == 2 ? 1 : 0;
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 const unsigned v = (unsigned)(H0[j][k] * cy0 + H1[j][k] * cy1) >> 22;   // the u8 the unfused chain stores
-                st_stream4f(o, lds_f32(lut + k * 1024 + v * 4));
+                const unsigned v1 = kCols == 2 ? (unsigned)(H0[j + j1][k] * cy0 + H1[j + j1][k] * cy1) >> 22 : 0u;
+                OutOps<OutT>::copy(o, lut, k, v, v1);
                 o += plane_bytes;
             }
             out[j] += row_bytes;
@@ -139,12 +180,15 @@ __device__ __forceinline__ void compute_tile(uint32_t ybuf, uint32_t cbuf, uint3
     }
 }
 
-template <bool kVFirst, int NCOL>
+// kDense: the reference's own layout (tensor.cpp:524: no pitch; chroma right after luma) -- one pitch register, constants folded.
+template <int FMT, typename OutT, int NCOL, bool kDense>
 __global__ void __launch_bounds__(NCOL == 1 ? 640 : kPipeThreads, NCOL <= 2 ? 2 : 1)
-nv_resize_normalize_chw_pipe_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, PipeGeom g,
+nv_resize_normalize_chw_pipe_kernel(const uint8_t* __restrict__ src, OutT* __restrict__ dst, PipeGeom g,
                                     const float* __restrict__ mean, const float* __restrict__ stddev) {
     extern __shared__ __align__(128) uint8_t dyn_smem[];     // [s_sy: ho][s_cy: ho][pad] 2 x (ystage + cstage)
-    __shared__ float lut[768];
+    typedef OutOps<OutT> Ops;
+    static_assert(NCOL % Ops::kCols == 0, "column pairs need an even column count");
+    __shared__ typename Ops::Lut lut[768];
     int* s_sy = reinterpret_cast<int*>(dyn_smem);
     int* s_cy = s_sy + g.ho;
     uint8_t* stages = dyn_smem + g.table_bytes;
@@ -152,8 +196,9 @@ nv_resize_normalize_chw_pipe_kernel(const uint8_t* __restrict__ src, float* __re
     __shared__ int s_any_right;
 
     const int tid = threadIdx.x, nthr = blockDim.x;
-    const size_t in_frame = (size_t)g.w * g.h * 3 / 2;
-    const size_t plane_bytes = (size_t)g.wo * g.ho * 4, row_bytes = (size_t)g.wo * 4;
+    const size_t plane_bytes = (size_t)g.wo * g.ho * Ops::kElem, row_bytes = (size_t)g.wo * Ops::kElem;
+    const int y_pitch = kDense ? g.w : g.y_pitch, c_pitch = kDense ? g.w : g.c_pitch;
+    const size_t frame_stride = kDense ? (size_t)g.w * g.h * 3 / 2 : g.frame_stride, c_off = kDense ? (size_t)g.w * g.h : g.c_off;
     const uint32_t stages_s = smem_u32(stages), sy_s = smem_u32(s_sy), cy_s = smem_u32(s_cy), lut_s = smem_u32(lut);
 
     // ---- once per CTA: barriers, normalisation table, row and column coefficients
@@ -164,7 +209,7 @@ nv_resize_normalize_chw_pipe_kernel(const uint8_t* __restrict__ src, float* __re
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int t = tid; t < 768; t += nthr)
-        lut[t] = normalize_one((float)(t & 255), __ldg(mean + (t >> 8)), (double)__ldg(stddev + (t >> 8)) + 1e-6);
+        lut[t] = Ops::make(normalize_one((float)(t & 255), __ldg(mean + (t >> 8)), (double)__ldg(stddev + (t >> 8)) + 1e-6));
     const double scale_x = (double)((float)g.w / (float)g.wo), scale_y = (double)((float)g.h / (float)g.ho);
     for (int dy = tid; dy < g.ho; dy += nthr) {
         int s; float f;
@@ -180,15 +225,16 @@ nv_resize_normalize_chw_pipe_kernel(const uint8_t* __restrict__ src, float* __re
     int any_right = 0;
 #pragma unroll
     for (int j = 0; j < NCOL; ++j) {
-        const int dx = min(tid + j * nthr, g.wo - 1);
+        // column pairs (fp16x2 stores, w_out even): pair p of thread t = columns 2(t + p nthr), +1
+        const int dx = Ops::kCols == 2 ? min(2 * (tid + (j >> 1) * nthr), g.wo - 2) + (j & 1) : min(tid + j * nthr, g.wo - 1);
         colx[j] = dx;
         int sx; float fx;
         linear_coord(dx, scale_x, g.w, sx, fx);
         col[j].cx0 = sat_short((1.f - fx) * 2048.f);
         col[j].cx1 = sat_short(2048.f * fx);
         col[j].yo = sx;
-        col[j].ca = sx & ~1;
-        col[j].cb = (sx + 1) & ~1;
+        col[j].ca = FMT == kFmtPlanar ? sx >> 1 : sx & ~1;
+        col[j].cb = FMT == kFmtPlanar ? (sx + 1) >> 1 : (sx + 1) & ~1;
         any_right |= col[j].cx1;
     }
     if (any_right) s_any_right = 1;   // benign race: all writers store 1
@@ -198,12 +244,13 @@ nv_resize_normalize_chw_pipe_kernel(const uint8_t* __restrict__ src, float* __re
         const int th = min(g.TH, g.ho - dy0);
         const int y_first = s_sy[dy0], y_last = s_sy[dy0 + th - 1] + 1;
         const int c_first = y_first >> 1, c_last = y_last >> 1;
-        const uint32_t ybytes = (uint32_t)(y_last - y_first + 1) * g.w, cbytes = (uint32_t)(c_last - c_first + 1) * g.w;
-        const uint8_t* f = src + (size_t)frame * in_frame;
+        const uint32_t ybytes = (uint32_t)(y_last - y_first + 1) * y_pitch, cbytes = (uint32_t)(c_last - c_first + 1) * c_pitch;
+        const uint8_t* f = src + (size_t)frame * frame_stride;
         uint8_t* st = stages + (size_t)b * (g.ystage + g.cstage);
-        mbar_expect_tx(&full_bar[b], ybytes + cbytes);
-        bulk_g2s(st, f + (size_t)y_first * g.w, ybytes, &full_bar[b]);
-        bulk_g2s(st + g.ystage, f + (size_t)g.w * g.h + (size_t)c_first * g.w, cbytes, &full_bar[b]);
+        mbar_expect_tx(&full_bar[b], ybytes + (FMT == kFmtPlanar ? 2 * cbytes : cbytes));
+        bulk_g2s(st, f + (size_t)y_first * y_pitch, ybytes, &full_bar[b]);
+        bulk_g2s(st + g.ystage, f + c_off + (size_t)c_first * c_pitch, cbytes, &full_bar[b]);
+        if (FMT == kFmtPlanar) bulk_g2s(st + g.ystage + g.vstage_off, f + g.c2_off + (size_t)c_first * c_pitch, cbytes, &full_bar[b]);
     };
 
     int tile = blockIdx.x;
@@ -221,11 +268,11 @@ nv_resize_normalize_chw_pipe_kernel(const uint8_t* __restrict__ src, float* __re
         const uint32_t ybuf = stages_s + b * (g.ystage + g.cstage);
         const uint32_t cbuf = ybuf + g.ystage;
         char* out[NCOL];
-        char* const row0 = reinterpret_cast<char*>(dst + ((size_t)frame * 3 * g.ho + dy0) * g.wo);
+        char* const row0 = reinterpret_cast<char*>(reinterpret_cast<typename Ops::Lut*>(dst) + ((size_t)frame * 3 * g.ho + dy0) * g.wo);
 #pragma unroll
-        for (int j = 0; j < NCOL; ++j) out[j] = row0 + 4 * colx[j];
-        if (right) compute_tile<kVFirst, true, NCOL>(ybuf, cbuf, sy_s, cy_s, lut_s, col, dy0, th, g.w, out, row_bytes, plane_bytes);
-        else compute_tile<kVFirst, false, NCOL>(ybuf, cbuf, sy_s, cy_s, lut_s, col, dy0, th, g.w, out, row_bytes, plane_bytes);
+        for (int j = 0; j < NCOL; ++j) out[j] = row0 + (int)Ops::kElem * colx[j];
+        if (right) compute_tile<FMT, OutT, true, NCOL>(ybuf, cbuf, sy_s, cy_s, lut_s, col, dy0, th, y_pitch, c_pitch, g.vstage_off, out, row_bytes, plane_bytes);
+        else compute_tile<FMT, OutT, false, NCOL>(ybuf, cbuf, sy_s, cy_s, lut_s, col, dy0, th, y_pitch, c_pitch, g.vstage_off, out, row_bytes, plane_bytes);
         __syncthreads();   // all reads of stage b done -> it may be refilled by the next iteration's issue
     }
 }

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench_ops.py -- per-operator / per-config measurements next to the headline bench.py (not the driver contract).
 
-    python bench_ops.py [--workload all|c1|c2|c2g|c3|c4|c5|ops] [--iters N] [--json out.jsonl]
+    python bench_ops.py [--workload all|c1|c2|c2g|c2s|c3|c4|c5|ops] [--iters N] [--json out.jsonl]
     torchrun --nproc-per-node N bench_ops.py --workload c5        # batch-global statistics with the all-reduce
 
 For every kernel: device-resident time per launch (CUDA events, median of N after warm-up, batch >> L2), output
@@ -75,6 +75,22 @@ def c2(iters, wo=640, ho=640, w=1920, h=1080, tag="c2"):
     out = torch.empty((b, 3, ho, wo), dtype=torch.float32, device="cuda")
     ms, _ = timeit(lambda: vacv.nv_resize_normalize_chw(src, w, h, wo, ho, mean, std, True, out=out), iters)
     report(f"{tag} fused nv12->chw f32 {w}x{h}->{wo}x{ho} x{b}", ms, b * wo * ho, b * (w * h * 3 // 2 + wo * ho * 12))
+
+
+def c2_surfaces(iters):
+    """Next rows 8f-1 / 8f-3: pitched and planar surfaces in, fp32 / fp16 planes out (same shape as config 2)."""
+    b, w, h, wo, ho = 256, 1920, 1080, 640, 640
+    mean, std = stats()
+    for name, fmt, yp, half in [("nv12 dense  -> f32", vacv.YUV_NV12, 1920, False), ("nv12 p2048  -> f32", vacv.YUV_NV12, 2048, False),
+                                ("i420 dense  -> f32", vacv.YUV_I420, 1920, False), ("nv12 dense  -> f16", vacv.YUV_NV12, 1920, True),
+                                ("i420 p2048  -> f16", vacv.YUV_I420, 2048, True)]:
+        cp = yp // 2 if fmt >= vacv.YUV_I420 else yp
+        per = yp * h * 3 // 2
+        src = rand_u8(b * per)
+        out = torch.empty((b, 3, ho, wo), dtype=torch.float16 if half else torch.float32, device="cuda")
+        ms, _ = timeit(lambda: vacv.yuv_resize_normalize_chw(src, fmt, w, h, wo, ho, mean, std, y_pitch=yp, c_pitch=cp, batch=b,
+                                                             half=half, out=out), iters)
+        report(f"c2s fused {name} 1080p->640x640 x{b}", ms, b * wo * ho, b * (w * h * 3 // 2 + wo * ho * (6 if half else 12)))
 
 
 def c2_unfused(iters):
@@ -245,6 +261,8 @@ def main():
         c2(args.iters, 640, 640, 1280, 720, tag="c2g")
         c2(args.iters, 416, 416, tag="c2g")
         c2_unfused(args.iters)
+    if wl in ("all", "c2s"):
+        c2_surfaces(args.iters)
     if wl in ("all", "c1"):
         c1(args.iters)
     if wl in ("all", "c3"):

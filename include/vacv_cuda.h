@@ -137,6 +137,23 @@ VACV_API int vacv_cuda_warp_affine_normalize(const uint8_t* frames, int n_frames
                                              float* dst, int w_out, int h_out, const float* mean, const float* stddev,
                                              int out_layout, void* stream);
 
+/* ---- next rows: decoder surfaces in, fp32 / fp16 planes out -----------------------------------------
+ * The fused pipeline on frames as a hardware decoder delivers them: row pitch, semi-planar (NV12 / NV21) or planar
+ * (I420 = Y,U,V; YV12 = Y,V,U; enum slot COLOR_YUV2BGR_YV12 of cv.h:73 has no reference implementation) chroma, same
+ * integer colour matrix (cvt_color.cpp:76-78).  Plane order inside a frame: Y (h rows of y_pitch bytes), then chroma
+ * (semi-planar: h/2 rows of c_pitch; planar: two planes of h/2 rows of c_pitch each).  0 = dense defaults.
+ * dst: batch x 3 x h_out x w_out planes of out_dtype VACV_FP32 or VACV_FP16 (fp16 = the fp32 result rounded to nearest even).
+ * Pitches, plane sizes and frame_stride must be multiples of 16 bytes (TMA bulk copies); otherwise VACV_ERR_UNSUPPORTED. */
+enum { VACV_YUV_NV21 = 0, VACV_YUV_NV12 = 1, VACV_YUV_I420 = 2, VACV_YUV_YV12 = 3 };
+typedef struct {
+    int format;            /* VACV_YUV_* */
+    int w, h;              /* luma size, both even */
+    int y_pitch, c_pitch;  /* bytes per luma / chroma row; 0 = dense (w, and w or w/2) */
+    size_t frame_stride;   /* bytes between frames; 0 = dense */
+} vacv_yuv_layout;
+VACV_API int vacv_cuda_yuv_resize_normalize_chw(const uint8_t* src, const vacv_yuv_layout* layout, void* dst, int out_dtype,
+                                                int batch, int w_out, int h_out, const float* mean, const float* stddev, void* stream);
+
 /* ---- host-buffer entry point of the fused pipeline (the end-to-end path) ------------------------------------------
  * Same operation as vacv_cuda_nv_resize_normalize_chw, but `h_src` / `h_dst` / `h_mean` / `h_stddev` are HOST pointers
  * (pinned memory -- vacv_cuda_host_alloc -- for full PCIe speed; pageable works, slower).  The batch is cut into chunks of

@@ -41,6 +41,30 @@ void orc_nv_to_bgr(const uint8_t* src, int w, int h, int v_first, uint8_t* dst) 
     }
 }
 
+/* Next-row extension: the same colour matrix on pitched / planar surfaces.  format 0 = NV21 (VU pairs),
+ * 1 = NV12 (UV pairs), 2 = I420 (Y,U,V planes), 3 = YV12 (Y,V,U planes).  Plane order: Y (h x y_pitch), chroma.
+ * Done by re-packing to a dense VU surface and running the pinned routine above. */
+void orc_yuv_to_bgr(const uint8_t* src, int format, int w, int h, int y_pitch, int c_pitch, uint8_t* dst) {
+    uint8_t* dense = (uint8_t*)malloc((size_t)w * h * 3 / 2);
+    const uint8_t* cbase = src + (size_t)y_pitch * h;
+    for (int r = 0; r < h; ++r) memcpy(dense + (size_t)r * w, src + (size_t)r * y_pitch, (size_t)w);
+    for (int r = 0; r < h / 2; ++r) {
+        uint8_t* o = dense + (size_t)w * h + (size_t)r * w;
+        if (format <= 1) {
+            const uint8_t* c = cbase + (size_t)r * c_pitch;
+            for (int x = 0; x < w; x += 2) { o[x] = c[x + (format == 1)]; o[x + 1] = c[x + (format != 1)]; }
+        } else {
+            const uint8_t* p0 = cbase + (size_t)r * c_pitch;                            /* first plane  */
+            const uint8_t* p1 = cbase + (size_t)c_pitch * (h / 2) + (size_t)r * c_pitch; /* second plane */
+            const uint8_t* up = format == 2 ? p0 : p1;
+            const uint8_t* vp = format == 2 ? p1 : p0;
+            for (int x = 0; x < w; x += 2) { o[x] = vp[x / 2]; o[x + 1] = up[x / 2]; }
+        }
+    }
+    orc_nv_to_bgr(dense, w, h, 1, dst);
+    free(dense);
+}
+
 /* image_util.cpp:9-40.  NB the U/V expressions wrap through unsigned int (no clamp). */
 void orc_bgr_to_nv21(const uint8_t* src, int w, int h, uint8_t* dst) {
     uint8_t* yp = dst;

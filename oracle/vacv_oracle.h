@@ -27,6 +27,10 @@ extern "C" {
  * v_first=0: chroma byte 0 is U (true NV12).  w,h even. */
 void orc_nv_to_bgr(const uint8_t* src, int w, int h, int v_first, uint8_t* dst);
 
+/* Next-row extension (no reference implementation: cv.h:73 enum only): pitched NV21/NV12 (format 0/1) and
+ * planar I420/YV12 (2/3) surfaces through the same matrix, by re-packing into the dense VU form of orc_nv_to_bgr. */
+void orc_yuv_to_bgr(const uint8_t* src, int format, int w, int h, int y_pitch, int c_pitch, uint8_t* dst);
+
 /* image_util.cpp:9-40 (fixture generator). */
 void orc_bgr_to_nv21(const uint8_t* bgr, int w, int h, uint8_t* dst);
 

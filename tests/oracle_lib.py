@@ -61,6 +61,12 @@ class Oracle:
         self.lib.orc_nv_to_bgr(_ptr(src), _i(w), _i(h), _i(v_first), _ptr(dst))
         return dst
 
+    def yuv_to_bgr(self, src, fmt, w, h, y_pitch, c_pitch):
+        src = _c(src, np.uint8)
+        dst = np.empty((h, w, 3), np.uint8)
+        self.lib.orc_yuv_to_bgr(_ptr(src), _i(fmt), _i(w), _i(h), _i(y_pitch), _i(c_pitch), _ptr(dst))
+        return dst
+
     def bgr_to_nv21(self, bgr):
         bgr = _c(bgr, np.uint8)
         h, w = bgr.shape[:2]

@@ -389,6 +389,55 @@ def test_fused_pipeline_config2(vacv, oracle, v_first, w, h, wo, ho, b):
     assert a @ bb / np.sqrt((a @ a) * (bb @ bb)) >= 0.99999
 
 
+@pytest.mark.parametrize("half", [False, True])
+@pytest.mark.parametrize("fmt", [0, 1, 2, 3])
+@pytest.mark.parametrize("w,h,yp,cp,wo,ho,b", [(1920, 1080, 2048, 0, 640, 640, 2), (1920, 1080, 0, 0, 640, 640, 1),
+                                              (640, 480, 768, 512, 224, 224, 3), (1280, 720, 1280, 0, 1000, 500, 1),
+                                              (64, 32, 0, 0, 100, 37, 2), (64, 32, 0, 0, 101, 37, 2), (1920, 1080, 0, 0, 1100, 360, 1),
+                                              (3840, 2160, 4096, 0, 640, 384, 1)])
+def test_fused_pipeline_yuv_surfaces(vacv, oracle, fmt, half, w, h, yp, cp, wo, ho, b):
+    """Next rows 8f-1 / 8f-3: pitched NV21/NV12 and planar I420/YV12 surfaces in, fp32 / fp16 planes out."""
+    from test_oracle_vs_ref import make_yuv_surface
+    planar = fmt >= 2
+    y_pitch = yp or w
+    c_pitch = cp or (w // 2 if planar else w)
+    if not planar:
+        c_pitch = max(c_pitch, y_pitch)
+    elif not cp:
+        c_pitch = y_pitch // 2
+    per = y_pitch * h + c_pitch * (h // 2) * (2 if planar else 1)
+    stride = per + 256                                # gap between frames
+    buf = u8(91, b * stride)
+    want = np.empty((b, 3, ho, wo), np.float32)
+    for i in range(b):
+        surf, _ = make_yuv_surface(100 * i + w + fmt, fmt, w, h, y_pitch, c_pitch)
+        buf[i * stride:i * stride + per] = surf
+        bgr = oracle.yuv_to_bgr(surf, fmt, w, h, y_pitch, c_pitch)
+        small = oracle.resize_linear(bgr, w, h, 3, NHWC, wo, ho)
+        want[i] = oracle.hwc_to_chw(oracle.normalize(small, wo * ho, 3, NHWC, MEAN, STD), wo, ho, 3)
+    got = host(vacv.yuv_resize_normalize_chw(dev(buf), fmt, w, h, wo, ho, dev(MEAN), dev(STD), y_pitch=y_pitch,
+                                             c_pitch=c_pitch, frame_stride=stride, batch=b, half=half))
+    if half:
+        assert got.dtype == np.float16
+        assert_same(got, want.astype(np.float16))    # fp16 = the exact fp32 result rounded to nearest even
+    else:
+        assert_same(got, want)
+
+
+def test_fused_pipeline_yuv_dense_nv21_equals_base_entry(vacv):
+    w, h, wo, ho, b = 1920, 1080, 640, 640, 2
+    src = dev(u8(92, b, w * h * 3 // 2))
+    a = vacv.nv_resize_normalize_chw(src, w, h, wo, ho, dev(MEAN), dev(STD), True)
+    c = vacv.yuv_resize_normalize_chw(src, 0, w, h, wo, ho, dev(MEAN), dev(STD))
+    assert_same(host(a), host(c))
+
+
+def test_fused_pipeline_yuv_rejects_unaligned_pitch(vacv):
+    src = dev(u8(93, 2 * (72 * 32 * 3 // 2)))
+    with pytest.raises(vacv.VacvError):
+        vacv.yuv_resize_normalize_chw(src, 0, 64, 32, 20, 20, dev(MEAN), dev(STD), y_pitch=72, c_pitch=72, batch=1)
+
+
 def test_fused_pipeline_equals_unfused_cuda_chain(vacv):
     w, h, wo, ho, b = 1920, 1080, 640, 640, 2
     src = dev(u8(20, b, w * h * 3 // 2))

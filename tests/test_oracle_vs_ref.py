@@ -36,6 +36,41 @@ def test_nv_to_bgr(oracle, ref, w, h, code):
     assert np.array_equal(oracle.nv_to_bgr(sw, w, h, v_first=0), want)
 
 
+def make_yuv_surface(seed, fmt, w, h, y_pitch, c_pitch):
+    """Random pitched surface (padding bytes random too) + the dense NV21 frame holding the same samples."""
+    r = rng(seed)
+    planar = fmt >= 2
+    yp = r.integers(0, 256, (h, y_pitch), dtype=np.uint8)
+    u = r.integers(0, 256, (h // 2, w // 2), dtype=np.uint8)
+    v = r.integers(0, 256, (h // 2, w // 2), dtype=np.uint8)
+    if planar:
+        up = r.integers(0, 256, (h // 2, c_pitch), dtype=np.uint8)
+        vp = r.integers(0, 256, (h // 2, c_pitch), dtype=np.uint8)
+        up[:, :w // 2], vp[:, :w // 2] = u, v
+        chroma = np.concatenate([up.ravel(), vp.ravel()] if fmt == 2 else [vp.ravel(), up.ravel()])
+    else:
+        cp = r.integers(0, 256, (h // 2, c_pitch), dtype=np.uint8)
+        cp[:, 0:w:2], cp[:, 1:w:2] = (v, u) if fmt == 0 else (u, v)
+        chroma = cp.ravel()
+    dense = np.empty(w * h * 3 // 2, np.uint8)
+    dense[:w * h] = yp[:, :w].ravel()
+    dense[w * h::2], dense[w * h + 1::2] = v.ravel(), u.ravel()
+    return np.concatenate([yp.ravel(), chroma]), dense
+
+
+@pytest.mark.parametrize("fmt", [0, 1, 2, 3])
+@pytest.mark.parametrize("w,h,yp,cp", [(16, 8, 0, 0), (176, 144, 192, 0), (642, 362, 656, 336), (1920, 1080, 2048, 0)])
+def test_yuv_surface_to_bgr(oracle, ref, fmt, w, h, yp, cp):
+    """Next-row extension (pitch, I420/YV12): same matrix as the reference on the re-packed frame."""
+    y_pitch = yp or w
+    c_pitch = cp or (w // 2 if fmt >= 2 else w)
+    if fmt < 2:
+        c_pitch = max(c_pitch, w)
+    surf, dense = make_yuv_surface(w + fmt, fmt, w, h, y_pitch, c_pitch)
+    want = ref.cvt_color(dense, w, h, COLOR_YUV2BGR_NV21)
+    assert np.array_equal(oracle.yuv_to_bgr(surf, fmt, w, h, y_pitch, c_pitch), want)
+
+
 def test_bgr2nv21_roundtrip_fixture(oracle, ref):
     img = load_fixture("t640x360")
     if img is None:
