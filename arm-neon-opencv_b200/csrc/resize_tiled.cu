@@ -15,9 +15,12 @@
 //                 u8: H is an exact integer carried as fp32 (|H| < 2^22), vertical pass = OpenCV's fp32 SSE2 body
 //                 with round-half-even, or its integer tail for the last <= 7 elements of an output row.
 #include <algorithm>
+#include <cmath>
+#include <cstdlib>
 
 #include "resize_coeffs.cuh"
 #include "resize_cubic3.cuh"
+#include "resize_cubic3_walk.cuh"
 #include "vacv_common.cuh"
 
 namespace vacv {
@@ -574,6 +577,92 @@ static int launch_cubic3_rolling(const void* src, void* dst, int images, int w, 
     return 1;
 }
 
+// Column-walking bicubic for interleaved 3-channel fp32 images (resize_cubic3_walk.cuh).  1 = launched, 0 = shape not eligible.
+static int launch_cubic3_walk_f32(const float* src, float* dst, int images, int w, int h, int wo, int ho, cudaStream_t s) {
+    constexpr int PX = 12;
+    if (w < 4 || h < 4 || (size_t)w * h * PX >= 0xffffffffull || (size_t)wo * ho * PX >= 0xffffffffull) return 0;
+    if ((double)h / ho > 4.0) return 0;                                           // the walk filters every source row in a segment
+    WalkGeom g;
+    g.w = w; g.h = h; g.wo = wo; g.ho = ho;
+    g.src_image = (size_t)w * h * 3; g.dst_image = (size_t)wo * ho * 3;
+    g.scale_x = (double)w / (double)wo; g.scale_y = (double)h / (double)ho;      // resize_naive.cpp:144
+    g.strips = (wo + kWalkThreads - 1) / kWalkThreads;
+    g.store16 = (((size_t)wo * PX) % 16 == 0 && ((uintptr_t)dst % 16) == 0) ? 1 : 0;
+    const long long want = 8LL * 8 * kNumSMs;
+    const long long per_seg = (long long)g.strips * images;
+    long long segs = std::max<long long>(1, std::min<long long>((want + per_seg - 1) / per_seg, (ho + 63) / 64));
+    if (const char* e = getenv("VACV_WALK_SEGS")) segs = std::max(1, atoi(e));   // tuning knob
+    int rps = (int)((ho + segs - 1) / segs);
+    rps = std::min(kWalkMaxRows, std::max(rps, 1));
+    g.rows_per_seg = rps;
+    g.segs = (ho + rps - 1) / rps;
+    // widest byte span of a warp's 32 columns in a source row: x_first differences <= ceil(31 * scale) + 2 pixels, + 4 tap
+    // pixels, + 15 (alignment of the span start), rounded up
+    const int span_px = (int)std::ceil(31.0 * g.scale_x) + 2 + 4;
+    g.ring_pitch = (span_px * PX + 15 + 15) & ~15;
+    static const char* sync_only = getenv("VACV_WALK_SYNC");   // tuning knob: register prefetch instead of the cp.async ring
+    const bool async = !sync_only && ((size_t)w * PX) % 16 == 0 && ((uintptr_t)src % 16) == 0 && g.ring_pitch <= 1024;
+    const size_t smem = (size_t)(rps + 1) * sizeof(WalkRow) + (size_t)(kWalkThreads / 32) * kWalkStageRows * 32 * PX +
+                        (async ? (size_t)(kWalkThreads / 32) * kWalkRing * g.ring_pitch : 0);
+    auto kern = async ? resize_cubic3_walk_f32_kernel<true> : resize_cubic3_walk_f32_kernel<false>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return set_error(VACV_ERR_CUDA, "resize: %s", cudaGetErrorString(e));
+    }
+    for (int i0 = 0; i0 < images; i0 += 65535) {
+        dim3 grid(g.strips * g.segs, std::min(images - i0, 65535));
+        kern<<<grid, kWalkThreads, smem, s>>>(src + (size_t)i0 * g.src_image, dst + (size_t)i0 * g.dst_image, g);
+    }
+    return 1;
+}
+
+// u8: two columns per thread, packed fp32 vertical pass, tail pixels rewritten by a second small kernel.
+static int launch_cubic3_walk2(const uint8_t* src, uint8_t* dst, int images, int w, int h, int wo, int ho, cudaStream_t s) {
+    if (((size_t)w * 3) % 4 != 0 || ((uintptr_t)src % 4) != 0) return 0;        // rows are read as aligned 32-bit words
+    if (w < 4 || h < 4 || (size_t)w * h * 3 >= 0xffffffffull || (size_t)wo * ho * 3 >= 0xffffffffull) return 0;
+    if ((double)h / ho > 4.0) return 0;                                           // the walk filters every source row in a segment
+    Walk2Geom g;
+    g.w = w; g.h = h; g.wo = wo; g.ho = ho;
+    g.src_image = (size_t)w * h * 3; g.dst_image = (size_t)wo * ho * 3;
+    g.scale_x = 1. / ((double)wo / (double)w); g.scale_y = 1. / ((double)ho / (double)h);   // OpenCV 2.4
+    g.strips = (wo + kWalk2Cols - 1) / kWalk2Cols;
+    g.store16 = (((size_t)wo * 3) % 16 == 0 && ((uintptr_t)dst % 16) == 0) ? 1 : 0;
+    g.one2 = 0x3F8000003F800000ull; g.negzero2 = 0x8000000080000000ull; g.magic2 = 0x4B4000004B400000ull; g.negmagic2 = 0xCB400000CB400000ull;
+    const long long want = 8LL * 6 * kNumSMs;
+    const long long per_seg = (long long)g.strips * images;
+    long long segs = std::max<long long>(1, std::min<long long>((want + per_seg - 1) / per_seg, (ho + 63) / 64));
+    if (const char* e = getenv("VACV_WALK_SEGS")) segs = std::max(1, atoi(e));   // tuning knob
+    int rps = (int)((ho + segs - 1) / segs);
+    rps = std::min(kWalkMaxRows, std::max(rps, 1));
+    g.rows_per_seg = rps;
+    g.segs = (ho + rps - 1) / rps;
+    // widest byte span of a warp's 64 columns in a source row: x_first differences <= ceil(63 * scale) + 2 pixels, + 12 tap
+    // bytes + 4 (word 3) + 15 (alignment of the span start), rounded up, + 16 slack
+    const int span_px = (int)std::ceil(63.0 * g.scale_x) + 2;
+    g.ring_pitch = ((span_px * 3 + 12 + 4 + 15 + 15) & ~15) + 16;
+    static const char* sync_only = getenv("VACV_WALK2_SYNC");   // tuning knob: register prefetch instead of the cp.async ring
+    const bool async = !sync_only && ((size_t)w * 3) % 16 == 0 && ((uintptr_t)src % 16) == 0 && g.ring_pitch <= 1024;
+    const size_t smem = (size_t)(rps + 1) * sizeof(Walk2Row) + (size_t)(kWalkThreads / 32) * kWalkStageRows * 64 * 3 +
+                        (async ? (size_t)(kWalkThreads / 32) * kWalk2Ring * g.ring_pitch : 0);
+    auto kern = async ? resize_cubic3_walk2_kernel<true> : resize_cubic3_walk2_kernel<false>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return set_error(VACV_ERR_CUDA, "resize: %s", cudaGetErrorString(e));
+    }
+    const int first_px = ((wo * 3) & ~7) / 3;
+    for (int i0 = 0; i0 < images; i0 += 65535) {
+        const int n = std::min(images - i0, 65535);
+        dim3 grid(g.strips * g.segs, n);
+        kern<<<grid, kWalkThreads, smem, s>>>(src + (size_t)i0 * g.src_image, dst + (size_t)i0 * g.dst_image, g);
+        if (first_px < wo) {
+            const long long items = (long long)n * ho * (wo - first_px);
+            resize_cubic3_tail_kernel<<<(unsigned)((items + 127) / 128), 128, 0, s>>>(src + (size_t)i0 * g.src_image, dst + (size_t)i0 * g.dst_image, w, h, wo, ho,
+                                                                                  g.scale_x, g.scale_y, g.src_image, g.dst_image, first_px, n);
+        }
+    }
+    return 1;
+}
+
 template <int KIND>
 static int launch_tiled_kind(const void* src, void* dst, int images, TiledGeom g, size_t smem, cudaStream_t s) {
     auto kern = resize_tiled_kernel<KIND>;
@@ -594,7 +683,13 @@ static int launch_tiled_kind(const void* src, void* dst, int images, TiledGeom g
 // Returns 1 if launched, 0 if the shape does not fit the tiled kernel (caller uses the direct kernels), < 0 on error.
 int try_launch_resize_tiled(int kind, const void* src, void* dst, int images, int w, int h, int c, int wo, int ho, cudaStream_t s) {
     if (c == 3 && (kind == kCubU8 || kind == kCubF32)) {   // interleaved BGR: rolling separable kernel, else the tiled pixel-per-thread one
-        int rc = kind == kCubU8 ? launch_cubic3_rolling<true>(src, dst, images, w, h, wo, ho, s) : launch_cubic3_rolling<false>(src, dst, images, w, h, wo, ho, s);
+        static const char* pick = getenv("VACV_CUBIC3");   // tuning knob: "roll" = shared-memory ring kernel, default = column walker
+        int rc = 0;
+        if (kind == kCubU8 && (!pick || pick[0] != 'r')) rc = launch_cubic3_walk2((const uint8_t*)src, (uint8_t*)dst, images, w, h, wo, ho, s);
+        if (rc != 0) return rc;
+        if (kind == kCubF32 && (!pick || pick[0] != 'r')) rc = launch_cubic3_walk_f32((const float*)src, (float*)dst, images, w, h, wo, ho, s);
+        if (rc != 0) return rc;
+        rc = kind == kCubU8 ? launch_cubic3_rolling<true>(src, dst, images, w, h, wo, ho, s) : launch_cubic3_rolling<false>(src, dst, images, w, h, wo, ho, s);
         if (rc != 0) return rc;
         rc = kind == kCubU8 ? launch_cubic3<kCubU8>(src, dst, images, w, h, wo, ho, s) : launch_cubic3<kCubF32>(src, dst, images, w, h, wo, ho, s);
         if (rc != 0) return rc;

@@ -200,7 +200,8 @@ def test_resize_same_size_is_copy(vacv):
 # ------------------------------------------------------------------ a8 / a9 bicubic
 @pytest.mark.parametrize("layout", [NHWC, NCHW])
 @pytest.mark.parametrize("sz", [((64, 48), (37, 20)), ((64, 48), (20, 37)), ((2560, 1440), (1920, 1080)),
-                                ((320, 180), (640, 360)), ((16, 16), (5, 9)), ((64, 48), (100, 100))])
+                                ((320, 180), (640, 360)), ((16, 16), (5, 9)), ((64, 48), (100, 100)),
+                                ((50, 40), (33, 27)), ((640, 480), (100, 60)), ((1000, 200), (1400, 150))])
 @pytest.mark.parametrize("path", PATHS)
 def test_resize_cubic_f32(vacv, oracle, layout, sz, path):
     (w, h), (wo, ho) = sz
@@ -215,11 +216,12 @@ def test_resize_cubic_f32(vacv, oracle, layout, sz, path):
 @pytest.mark.parametrize("c", [1, 3, 4])
 @pytest.mark.parametrize("sz", [((2560, 1440), (1920, 1080)), ((256, 144), (100, 70)), ((176, 144), (640, 640)),
                                 ((257, 145), (300, 171)), ((64, 48), (333, 77)), ((64, 48), (21, 13)),
-                                ((8, 8), (3, 3)), ((5, 4), (13, 11))])
+                                ((8, 8), (3, 3)), ((5, 4), (13, 11)), ((100, 60), (75, 45)), ((640, 480), (100, 60)),
+                                ((1000, 200), (1401, 150)), ((1920, 1080), (2560, 1440))])
 @pytest.mark.parametrize("path", PATHS)
 def test_resize_cubic_u8(vacv, oracle, c, sz, path):
     (w, h), (wo, ho) = sz
-    if c != 3 and w > 1000:
+    if c != 3 and w >= 1000:
         pytest.skip("big case only for c=3")
     src = u8(11 + c, 2, h, w, c)
     got = host(vacv.resize(dev(src), NHWC, wo, ho, vacv.INTER_CUBIC, path))
