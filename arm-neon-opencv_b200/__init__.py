@@ -16,6 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvacv_cuda.so")
 
 FP32, FP16, INT8, FP64 = 0, 1, 2, 3
+BF16 = 16   # extension: output type of the fused pipeline only
 NCHW, NHWC = 0, 1
 INTER_LINEAR, INTER_CUBIC = 1, 2
 FLAG_NONE, FLAG_NEON_RULE, FLAG_SIGNED_CHAR, FLAG_DIRECT_GATHER, FLAG_TILED = 0, 1, 2, 0x100, 0x200
@@ -41,6 +42,8 @@ _SIGS = {
     "vacv_cuda_normalize": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp],
     "vacv_cuda_nv_resize_normalize_chw": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp],
     "vacv_cuda_yuv_resize_normalize_chw": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp],
+    "vacv_cuda_yuv_letterbox_normalize_chw": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "vacv_letterbox_rect": [_i, _i, _i, _i, _vp],
     "vacv_cuda_nv_resize_normalize_chw_host": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i],
     "vacv_cuda_resize_normalize": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp],
     "vacv_cuda_warp_affine_normalize": [_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _vp],
@@ -62,7 +65,7 @@ _SIGS = {
 for _name, _args in _SIGS.items():
     _fn = getattr(lib, _name)
     _fn.argtypes = _args
-    _fn.restype = None if _name.startswith("vacv_invert") or _name.startswith("vacv_rotation") else _i
+    _fn.restype = None if _name.startswith(("vacv_invert", "vacv_rotation", "vacv_letterbox")) else _i
 EXPORTS = ["vacv_cuda_abi_version", "vacv_cuda_last_error"] + list(_SIGS)
 
 
@@ -239,22 +242,63 @@ class YuvLayout(C.Structure):
                 ("frame_stride", C.c_size_t)]
 
 
+def _torch_out_dtype(out_dtype):
+    return {FP32: torch.float32, FP16: torch.float16, BF16: torch.bfloat16}[out_dtype]
+
+
+def _yuv_batch(src, fmt, w, h, y_pitch, c_pitch, frame_stride):
+    yp = y_pitch or w
+    cp = c_pitch or (w // 2 if fmt >= YUV_I420 else w)
+    per = frame_stride or (yp * h + cp * (h // 2) * (2 if fmt >= YUV_I420 else 1))
+    return src.numel() // per
+
+
 def yuv_resize_normalize_chw(src, fmt, w, h, w_out, h_out, mean, std, y_pitch=0, c_pitch=0, frame_stride=0, batch=None,
-                             half=False, out=None):
-    """Fused pipeline on pitched / planar decoder surfaces; fp32 or fp16 CHW planes out.  src: uint8 device tensor holding
-    `batch` frames `frame_stride` bytes apart (dense when 0)."""
+                             half=False, out=None, out_dtype=None):
+    """Fused pipeline on pitched / planar decoder surfaces; fp32, fp16 or bf16 CHW planes out.  src: uint8 device tensor
+    holding `batch` frames `frame_stride` bytes apart (dense when 0)."""
     src = _dev(src, torch.uint8)
     mean, std = _dev(mean, torch.float32), _dev(std, torch.float32)
     lay = YuvLayout(fmt, w, h, y_pitch, c_pitch, frame_stride)
     if batch is None:
-        yp = y_pitch or w
-        cp = c_pitch or (w // 2 if fmt >= YUV_I420 else w)
-        per = frame_stride or (yp * h + cp * (h // 2) * (2 if fmt >= YUV_I420 else 1))
-        batch = src.numel() // per
-    dt = torch.float16 if half else torch.float32
-    dst = out if out is not None else torch.empty((batch, 3, h_out, w_out), dtype=dt, device=src.device)
-    _check(lib.vacv_cuda_yuv_resize_normalize_chw(src.data_ptr(), C.addressof(lay), dst.data_ptr(), FP16 if half else FP32, batch,
+        batch = _yuv_batch(src, fmt, w, h, y_pitch, c_pitch, frame_stride)
+    if out_dtype is None:
+        out_dtype = FP16 if half else FP32
+    dst = out if out is not None else torch.empty((batch, 3, h_out, w_out), dtype=_torch_out_dtype(out_dtype), device=src.device)
+    _check(lib.vacv_cuda_yuv_resize_normalize_chw(src.data_ptr(), C.addressof(lay), dst.data_ptr(), out_dtype, batch,
                                                   w_out, h_out, mean.data_ptr(), std.data_ptr(), _stream()))
+    return dst
+
+
+class Rect(C.Structure):
+    """Mirror of vacv_rect."""
+    _fields_ = [("x", C.c_int), ("y", C.c_int), ("w", C.c_int), ("h", C.c_int)]
+
+
+def letterbox_rect(w, h, canvas_w, canvas_h):
+    r = Rect()
+    lib.vacv_letterbox_rect(w, h, canvas_w, canvas_h, C.addressof(r))
+    return r.x, r.y, r.w, r.h
+
+
+def yuv_letterbox_normalize_chw(src, fmt, w, h, canvas_w, canvas_h, mean, std, pad_bgr=(114, 114, 114), content=None, y_pitch=0,
+                                c_pitch=0, frame_stride=0, batch=None, out_dtype=FP32, out=None):
+    """Aspect-preserving variant: the frame is resized into `content` (x, y, w, h; default vacv_letterbox_rect) of a
+    canvas_w x canvas_h canvas filled with pad_bgr, then normalised -> CHW planes.  mean/std: 3-element host sequences."""
+    src = _dev(src, torch.uint8)
+    m = (C.c_float * 3)(*[float(v) for v in mean])
+    s = (C.c_float * 3)(*[float(v) for v in std])
+    dm = torch.tensor(list(m), dtype=torch.float32, device=src.device)
+    ds = torch.tensor(list(s), dtype=torch.float32, device=src.device)
+    lay = YuvLayout(fmt, w, h, y_pitch, c_pitch, frame_stride)
+    if batch is None:
+        batch = _yuv_batch(src, fmt, w, h, y_pitch, c_pitch, frame_stride)
+    r = Rect(*(content if content is not None else letterbox_rect(w, h, canvas_w, canvas_h)))
+    pad = (C.c_uint8 * 3)(*[int(v) for v in pad_bgr])
+    dst = out if out is not None else torch.empty((batch, 3, canvas_h, canvas_w), dtype=_torch_out_dtype(out_dtype), device=src.device)
+    _check(lib.vacv_cuda_yuv_letterbox_normalize_chw(src.data_ptr(), C.addressof(lay), dst.data_ptr(), out_dtype, batch, canvas_w, canvas_h,
+                                                     C.addressof(r), C.cast(pad, _vp), dm.data_ptr(), ds.data_ptr(), C.cast(m, _vp),
+                                                     C.cast(s, _vp), _stream()))
     return dst
 
 

@@ -228,8 +228,11 @@ struct YuvSource {
 
 // Returns 1 if the persistent TMA pipeline was launched, 0 if the shape does not qualify (caller falls back to the
 // tiled kernel where one exists), < 0 on error.
-static int try_launch_pipe(const uint8_t* src, void* dst, bool half_out, int batch, const YuvSource& y, int w_out, int h_out,
-                           const float* mean, const float* stddev, cudaStream_t s) {
+struct Canvas { int w, h, x0, y0; };   // destination plane size and where the w_out x h_out result goes inside it
+
+static int try_launch_pipe(const uint8_t* src, void* dst, int out_dtype, int batch, const YuvSource& y, int w_out, int h_out,
+                           const Canvas& cv, const float* mean, const float* stddev, cudaStream_t s) {
+    const bool half_out = out_dtype != VACV_FP32;   // fp16 / bf16: 16-bit table entries
     const int w = y.w, h = y.h;
     // bulk copies need 16-byte granularity of every band start and length
     if ((y.y_pitch % 16) != 0 || (y.c_pitch % 16) != 0 || (y.frame_stride % 16) != 0 || (y.c_off % 16) != 0 || (y.c2_off % 16) != 0 ||
@@ -244,6 +247,7 @@ static int try_launch_pipe(const uint8_t* src, void* dst, bool half_out, int bat
     PipeGeom g;
     g.w = w; g.h = h; g.wo = w_out; g.ho = h_out; g.table_bytes = table_bytes;
     g.y_pitch = y.y_pitch; g.c_pitch = y.c_pitch; g.frame_stride = y.frame_stride; g.c_off = y.c_off; g.c2_off = y.c2_off;
+    g.canvas_w = cv.w; g.canvas_h = cv.h; g.x0 = cv.x0; g.y0 = cv.y0; g.bf16 = out_dtype == VACV_BF16 ? 1 : 0;
     const bool planar = y.fmt == kFmtPlanar;
     int best_TH = 0;
     size_t best_smem = 0;
@@ -289,10 +293,11 @@ static int try_launch_pipe(const uint8_t* src, void* dst, bool half_out, int bat
     int ncol = (w_out + kPipeThreads - 1) / kPipeThreads;
     if (any_right && w_out <= 4 * 192) ncol = 4;
     if (const char* e = getenv("VACV_PIPE_NCOL")) { const int v = atoi(e); if (v >= 1 && v <= kPipeMaxCols && (w_out + v - 1) / v <= (v == 1 ? 640 : kPipeThreads)) ncol = v; }   // tuning knob
-    const bool pairs = half_out && (w_out % 2) == 0 && (((uintptr_t)dst) & 3) == 0;   // fp16: 32-bit stores of column pairs
+    const bool pairs = half_out && (w_out % 2) == 0 && (cv.w % 2) == 0 && (cv.x0 % 2) == 0 && (((uintptr_t)dst) & 3) == 0;   // 16-bit outputs: 32-bit stores of column pairs
     if (pairs) ncol = ncol <= 2 ? 2 : 4;
     const int threads = std::min(ncol == 1 ? 640 : kPipeThreads, ((w_out + ncol - 1) / ncol + 31) & ~31);
-    const bool dense = y.y_pitch == w && y.c_pitch == w && y.c_off == (size_t)w * h && y.frame_stride == (size_t)w * h * 3 / 2;
+    const bool dense = y.y_pitch == w && y.c_pitch == w && y.c_off == (size_t)w * h && y.frame_stride == (size_t)w * h * 3 / 2 &&
+                       cv.w == w_out && cv.h == h_out;
     const void* kern = pipe_kernel_for(y.fmt, half_out, pairs, dense, ncol);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)best_smem);
     if (e != cudaSuccess) return set_error(VACV_ERR_CUDA, "nv_resize_normalize_chw: %s", cudaGetErrorString(e));
@@ -321,7 +326,8 @@ extern "C" int vacv_cuda_nv_resize_normalize_chw(const uint8_t* src, float* dst,
     YuvSource ys;
     ys.fmt = v_first ? kFmtVU : kFmtUV; ys.w = w; ys.h = h; ys.y_pitch = w; ys.c_pitch = w;
     ys.frame_stride = (size_t)w * h * 3 / 2; ys.c_off = (size_t)w * h; ys.c2_off = 0;
-    if (int rc = try_launch_pipe(src, dst, false, batch, ys, w_out, h_out, mean, stddev, s)) {
+    const Canvas whole = {w_out, h_out, 0, 0};
+    if (int rc = try_launch_pipe(src, dst, VACV_FP32, batch, ys, w_out, h_out, whole, mean, stddev, s)) {
         if (rc < 0) return rc;
         return check_launch("nv_resize_normalize_chw (persistent)");
     }
@@ -374,28 +380,23 @@ extern "C" int vacv_cuda_resize_normalize(const uint8_t* src, float* dst, int ba
     return check_launch("resize_normalize");
 }
 
-// Next-row extension of the fused pipeline: decoder-style surfaces (row pitch, planar I420 / YV12
-// chroma) in, fp32 or fp16 CHW planes out.  Same arithmetic as vacv_cuda_nv_resize_normalize_chw; fp16 = the exact fp32
-// result rounded to nearest-even.  Runs on the persistent TMA pipeline only (pitches / strides must be multiples of 16).
-extern "C" int vacv_cuda_yuv_resize_normalize_chw(const uint8_t* src, const vacv_yuv_layout* layout, void* dst, int out_dtype,
-                                                  int batch, int w_out, int h_out, const float* mean, const float* stddev, void* stream) {
-    VACV_REQUIRE(src && layout && dst && mean && stddev, "yuv_resize_normalize_chw: null pointer");
+// Next-row extensions of the fused pipeline: decoder-style surfaces (row pitch, planar I420 / YV12
+// chroma) in; fp32, fp16 or bf16 CHW planes out; optional letterbox placement.  Same arithmetic as
+// vacv_cuda_nv_resize_normalize_chw; 16-bit outputs = the exact fp32 result rounded to nearest-even.  These run on the
+// persistent TMA pipeline only (pitches / strides must be multiples of 16).
+static int parse_yuv_layout(const char* who, const vacv_yuv_layout* layout, YuvSource& ys) {
     const int w = layout->w, h = layout->h;
-    VACV_REQUIRE(batch > 0 && w >= 2 && h >= 2 && w_out > 0 && h_out > 0, "yuv_resize_normalize_chw: bad size");
-    VACV_REQUIRE((w % 2) == 0 && (h % 2) == 0, "yuv_resize_normalize_chw: w and h must be even (got %dx%d)", w, h);
-    if (out_dtype != VACV_FP32 && out_dtype != VACV_FP16) return set_error(VACV_ERR_UNSUPPORTED, "yuv_resize_normalize_chw: out dtype %d (FP32 or FP16)", out_dtype);
-    if (w_out == w && h_out == h) return set_error(VACV_ERR_UNSUPPORTED, "yuv_resize_normalize_chw: same-size resize");
+    VACV_REQUIRE(w >= 2 && h >= 2 && (w % 2) == 0 && (h % 2) == 0, "%s: w and h must be even and >= 2 (got %dx%d)", who, w, h);
     const bool planar = layout->format == VACV_YUV_I420 || layout->format == VACV_YUV_YV12;
     if (!planar && layout->format != VACV_YUV_NV12 && layout->format != VACV_YUV_NV21)
-        return set_error(VACV_ERR_UNSUPPORTED, "yuv_resize_normalize_chw: format %d", layout->format);
-    YuvSource ys;
+        return set_error(VACV_ERR_UNSUPPORTED, "%s: format %d", who, layout->format);
     ys.w = w; ys.h = h;
     ys.y_pitch = layout->y_pitch ? layout->y_pitch : w;
     ys.c_pitch = layout->c_pitch ? layout->c_pitch : (planar ? w / 2 : w);
-    VACV_REQUIRE(ys.y_pitch >= w && ys.c_pitch >= (planar ? w / 2 : w), "yuv_resize_normalize_chw: pitch smaller than the row");
+    VACV_REQUIRE(ys.y_pitch >= w && ys.c_pitch >= (planar ? w / 2 : w), "%s: pitch smaller than the row", who);
     const size_t y_bytes = (size_t)ys.y_pitch * h, c_bytes = (size_t)ys.c_pitch * (h / 2);
     ys.frame_stride = layout->frame_stride ? layout->frame_stride : y_bytes + (planar ? 2 * c_bytes : c_bytes);
-    VACV_REQUIRE(ys.frame_stride >= y_bytes + (planar ? 2 * c_bytes : c_bytes), "yuv_resize_normalize_chw: frame_stride too small");
+    VACV_REQUIRE(ys.frame_stride >= y_bytes + (planar ? 2 * c_bytes : c_bytes), "%s: frame_stride too small", who);
     if (planar) {
         ys.fmt = kFmtPlanar;
         const size_t first = y_bytes, second = y_bytes + c_bytes;
@@ -405,9 +406,75 @@ extern "C" int vacv_cuda_yuv_resize_normalize_chw(const uint8_t* src, const vacv
         ys.fmt = layout->format == VACV_YUV_NV21 ? kFmtVU : kFmtUV;
         ys.c_off = y_bytes; ys.c2_off = 0;
     }
-    const int rc = try_launch_pipe(src, dst, out_dtype == VACV_FP16, batch, ys, w_out, h_out, mean, stddev, as_stream(stream));
+    return VACV_OK;
+}
+
+extern "C" int vacv_cuda_yuv_resize_normalize_chw(const uint8_t* src, const vacv_yuv_layout* layout, void* dst, int out_dtype,
+                                                  int batch, int w_out, int h_out, const float* mean, const float* stddev, void* stream) {
+    VACV_REQUIRE(src && layout && dst && mean && stddev, "yuv_resize_normalize_chw: null pointer");
+    VACV_REQUIRE(batch > 0 && w_out > 0 && h_out > 0, "yuv_resize_normalize_chw: bad size");
+    if (out_dtype != VACV_FP32 && out_dtype != VACV_FP16 && out_dtype != VACV_BF16)
+        return set_error(VACV_ERR_UNSUPPORTED, "yuv_resize_normalize_chw: out dtype %d (FP32, FP16 or BF16)", out_dtype);
+    YuvSource ys;
+    if (int rc = parse_yuv_layout("yuv_resize_normalize_chw", layout, ys)) return rc;
+    if (w_out == ys.w && h_out == ys.h) return set_error(VACV_ERR_UNSUPPORTED, "yuv_resize_normalize_chw: same-size resize");
+    const Canvas whole = {w_out, h_out, 0, 0};
+    const int rc = try_launch_pipe(src, dst, out_dtype, batch, ys, w_out, h_out, whole, mean, stddev, as_stream(stream));
     if (rc < 0) return rc;
     if (rc == 0) return set_error(VACV_ERR_UNSUPPORTED, "yuv_resize_normalize_chw: layout not eligible for the TMA pipeline "
                                   "(pitches, plane offsets and frame stride must be multiples of 16; w_out <= 1536)");
     return check_launch("yuv_resize_normalize_chw");
+}
+
+// Aspect-preserving placement of a w x h frame on a canvas (the usual detector "letterbox"): scale = min(cw/w, ch/h),
+// content size rounded to nearest, centred.
+extern "C" void vacv_letterbox_rect(int w, int h, int canvas_w, int canvas_h, vacv_rect* content) {
+    const double sc = std::min((double)canvas_w / w, (double)canvas_h / h);
+    int cw = (int)std::floor(w * sc + 0.5), ch = (int)std::floor(h * sc + 0.5);
+    cw = std::max(1, std::min(cw, canvas_w)); ch = std::max(1, std::min(ch, canvas_h));
+    content->x = (canvas_w - cw) / 2; content->y = (canvas_h - ch) / 2; content->w = cw; content->h = ch;
+}
+
+template <typename T>
+static void launch_pad(void* dst, int batch, int cw_, int ch_, const vacv_rect& r, const float pad[3], cudaStream_t s, T (*conv)(float)) {
+    const long long total = (long long)(ch_ - r.h) * cw_ + (long long)r.h * (cw_ - r.w);   // border elements per plane
+    const int chunks = (int)std::max<long long>(1, std::min<long long>((total + 256 * 8 - 1) / (256 * 8), 64));
+    for (int b0 = 0; b0 < batch; b0 += 20000) {
+        dim3 grid(chunks, 3 * std::min(batch - b0, 20000));
+        letterbox_pad_kernel<T><<<grid, 256, 0, s>>>((T*)dst + (size_t)b0 * 3 * cw_ * ch_, cw_, ch_, r.x, r.y, r.w, r.h, conv(pad[0]), conv(pad[1]), conv(pad[2]));
+    }
+}
+static float conv_f32(float v) { return v; }
+static unsigned short conv_f16(float v) { return __half_as_ushort(__float2half_rn(v)); }
+static unsigned short conv_bf16(float v) { return __bfloat16_as_ushort(__float2bfloat16_rn(v)); }
+
+// Letterbox: frame -> bilinear resize (reference rule) to content->w x content->h -> placed at (content->x, content->y) of a
+// canvas_w x canvas_h canvas filled with pad_bgr -> normalise -> CHW planes.  Equals the unfused chain on the padded u8 canvas.
+extern "C" int vacv_cuda_yuv_letterbox_normalize_chw(const uint8_t* src, const vacv_yuv_layout* layout, void* dst, int out_dtype, int batch,
+                                                     int canvas_w, int canvas_h, const vacv_rect* content, const uint8_t* pad_bgr,
+                                                     const float* mean, const float* stddev, const float* mean_host, const float* stddev_host,
+                                                     void* stream) {
+    VACV_REQUIRE(src && layout && dst && content && pad_bgr && mean && stddev && mean_host && stddev_host, "yuv_letterbox_normalize_chw: null pointer");
+    VACV_REQUIRE(batch > 0 && canvas_w > 0 && canvas_h > 0, "yuv_letterbox_normalize_chw: bad size");
+    VACV_REQUIRE(content->w > 0 && content->h > 0 && content->x >= 0 && content->y >= 0 && content->x + content->w <= canvas_w &&
+                 content->y + content->h <= canvas_h, "yuv_letterbox_normalize_chw: content rectangle outside the canvas");
+    if (out_dtype != VACV_FP32 && out_dtype != VACV_FP16 && out_dtype != VACV_BF16)
+        return set_error(VACV_ERR_UNSUPPORTED, "yuv_letterbox_normalize_chw: out dtype %d (FP32, FP16 or BF16)", out_dtype);
+    YuvSource ys;
+    if (int rc = parse_yuv_layout("yuv_letterbox_normalize_chw", layout, ys)) return rc;
+    if (content->w == ys.w && content->h == ys.h) return set_error(VACV_ERR_UNSUPPORTED, "yuv_letterbox_normalize_chw: same-size resize");
+    cudaStream_t s = as_stream(stream);
+    // border first (it never overlaps the content rectangle); the pad colour goes through the same exact expression
+    float pad[3];
+    for (int k = 0; k < 3; ++k) pad[k] = (float)((double)((float)pad_bgr[k] - mean_host[k]) / ((double)stddev_host[k] + 1e-6));   // normalize_naive.cpp:74-90
+    if (content->w != canvas_w || content->h != canvas_h) {
+        if (out_dtype == VACV_FP32) launch_pad<float>(dst, batch, canvas_w, canvas_h, *content, pad, s, conv_f32);
+        else launch_pad<unsigned short>(dst, batch, canvas_w, canvas_h, *content, pad, s, out_dtype == VACV_FP16 ? conv_f16 : conv_bf16);
+    }
+    const Canvas cv = {canvas_w, canvas_h, content->x, content->y};
+    const int rc = try_launch_pipe(src, dst, out_dtype, batch, ys, content->w, content->h, cv, mean, stddev, s);
+    if (rc < 0) return rc;
+    if (rc == 0) return set_error(VACV_ERR_UNSUPPORTED, "yuv_letterbox_normalize_chw: layout not eligible for the TMA pipeline "
+                                  "(pitches, plane offsets and frame stride must be multiples of 16; content width <= 1536)");
+    return check_launch("yuv_letterbox_normalize_chw");
 }

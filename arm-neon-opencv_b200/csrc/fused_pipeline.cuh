@@ -13,6 +13,7 @@
 //           cached per chroma row (two luma rows share one), H of the lower row is carried to the next output row
 //           when it starts there.  out = table[c][(H0*cy0 + H1*cy1) >> 22], stored 128 B / warp / plane, streaming.
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
 #include "vacv_common.cuh"
@@ -34,6 +35,10 @@ struct PipeGeom {
     int vstage_off;         // planar formats: byte offset of the V band inside the chroma stage
     size_t frame_stride;    // bytes between frames
     size_t c_off, c2_off;   // byte offset of the chroma plane (semi-planar) / of the U and V planes (planar) inside a frame
+    // destination canvas (letterbox): the wo x ho result is written at (x0, y0) of a canvas_w x canvas_h plane; without
+    // letterbox canvas = result and x0 = y0 = 0
+    int canvas_w, canvas_h, x0, y0;
+    int bf16;               // 16-bit outputs: table holds bfloat16 instead of half
 };
 
 enum { kFmtVU = 0, kFmtUV = 1, kFmtPlanar = 2 };   // interleaved chroma V-first (NV21), U-first (NV12), separate U and V planes (I420 / YV12)
@@ -87,22 +92,24 @@ template <typename OutT> struct OutOps;
 template <> struct OutOps<float> {
     typedef float Lut;
     enum { kElem = 4, kCols = 1 };
-    static __device__ __forceinline__ float make(float v) { return v; }
+    static __device__ __forceinline__ float make(float v, int) { return v; }
     static __device__ __forceinline__ void copy(char* o, uint32_t lut, int k, unsigned v, unsigned) { st_stream4f(o, lds_f32(lut + k * 1024 + v * 4)); }
 };
 template <> struct OutOps<__half> {
-    typedef __half Lut;
+    typedef unsigned short Lut;
     enum { kElem = 2, kCols = 1 };
-    static __device__ __forceinline__ __half make(float v) { return __float2half_rn(v); }   // exact fp32 value rounded to nearest-even fp16
+    static __device__ __forceinline__ unsigned short make(float v, int bf16) {   // exact fp32 value rounded to nearest-even fp16 / bf16
+        return bf16 ? __bfloat16_as_ushort(__float2bfloat16_rn(v)) : __half_as_ushort(__float2half_rn(v));
+    }
     static __device__ __forceinline__ void copy(char* o, uint32_t lut, int k, unsigned v, unsigned) {
         const unsigned short h = (unsigned short)lds_u16(lut + k * 512 + v * 2);
         asm volatile("st.global.cs.u16 [%0], %1;" ::"l"(o), "h"(h) : "memory");
     }
 };
 template <> struct OutOps<__half2> {
-    typedef __half Lut;
+    typedef unsigned short Lut;
     enum { kElem = 2, kCols = 2 };
-    static __device__ __forceinline__ __half make(float v) { return __float2half_rn(v); }
+    static __device__ __forceinline__ unsigned short make(float v, int bf16) { return OutOps<__half>::make(v, bf16); }
     static __device__ __forceinline__ void copy(char* o, uint32_t lut, int k, unsigned v0, unsigned v1) {
         const unsigned pair = lds_u16(lut + k * 512 + v0 * 2) | (lds_u16(lut + k * 512 + v1 * 2) << 16);
         asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(o), "r"(pair) : "memory");
@@ -196,7 +203,8 @@ nv_resize_normalize_chw_pipe_kernel(const uint8_t* __restrict__ src, OutT* __res
     __shared__ int s_any_right;
 
     const int tid = threadIdx.x, nthr = blockDim.x;
-    const size_t plane_bytes = (size_t)g.wo * g.ho * Ops::kElem, row_bytes = (size_t)g.wo * Ops::kElem;
+    const size_t plane_bytes = kDense ? (size_t)g.wo * g.ho * Ops::kElem : (size_t)g.canvas_w * g.canvas_h * Ops::kElem;
+    const size_t row_bytes = kDense ? (size_t)g.wo * Ops::kElem : (size_t)g.canvas_w * Ops::kElem;
     const int y_pitch = kDense ? g.w : g.y_pitch, c_pitch = kDense ? g.w : g.c_pitch;
     const size_t frame_stride = kDense ? (size_t)g.w * g.h * 3 / 2 : g.frame_stride, c_off = kDense ? (size_t)g.w * g.h : g.c_off;
     const uint32_t stages_s = smem_u32(stages), sy_s = smem_u32(s_sy), cy_s = smem_u32(s_cy), lut_s = smem_u32(lut);
@@ -209,7 +217,7 @@ nv_resize_normalize_chw_pipe_kernel(const uint8_t* __restrict__ src, OutT* __res
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int t = tid; t < 768; t += nthr)
-        lut[t] = Ops::make(normalize_one((float)(t & 255), __ldg(mean + (t >> 8)), (double)__ldg(stddev + (t >> 8)) + 1e-6));
+        lut[t] = Ops::make(normalize_one((float)(t & 255), __ldg(mean + (t >> 8)), (double)__ldg(stddev + (t >> 8)) + 1e-6), g.bf16);
     const double scale_x = (double)((float)g.w / (float)g.wo), scale_y = (double)((float)g.h / (float)g.ho);
     for (int dy = tid; dy < g.ho; dy += nthr) {
         int s; float f;
@@ -268,12 +276,35 @@ nv_resize_normalize_chw_pipe_kernel(const uint8_t* __restrict__ src, OutT* __res
         const uint32_t ybuf = stages_s + b * (g.ystage + g.cstage);
         const uint32_t cbuf = ybuf + g.ystage;
         char* out[NCOL];
-        char* const row0 = reinterpret_cast<char*>(reinterpret_cast<typename Ops::Lut*>(dst) + ((size_t)frame * 3 * g.ho + dy0) * g.wo);
+        char* const row0 = kDense ? reinterpret_cast<char*>(reinterpret_cast<typename Ops::Lut*>(dst) + ((size_t)frame * 3 * g.ho + dy0) * g.wo)
+                                  : reinterpret_cast<char*>(reinterpret_cast<typename Ops::Lut*>(dst) + ((size_t)frame * 3 * g.canvas_h + g.y0 + dy0) * g.canvas_w + g.x0);
 #pragma unroll
         for (int j = 0; j < NCOL; ++j) out[j] = row0 + (int)Ops::kElem * colx[j];
         if (right) compute_tile<FMT, OutT, true, NCOL>(ybuf, cbuf, sy_s, cy_s, lut_s, col, dy0, th, y_pitch, c_pitch, g.vstage_off, out, row_bytes, plane_bytes);
         else compute_tile<FMT, OutT, false, NCOL>(ybuf, cbuf, sy_s, cy_s, lut_s, col, dy0, th, y_pitch, c_pitch, g.vstage_off, out, row_bytes, plane_bytes);
         __syncthreads();   // all reads of stage b done -> it may be refilled by the next iteration's issue
+    }
+}
+
+// Letterbox border: every canvas pixel outside the content rectangle gets the normalised pad colour of its plane.
+// blockIdx.y = frame * 3 + plane; the CTAs of a plane stride over its border elements in the order top rows, bottom rows
+// (both contiguous spans), then the strips left and right of the content.
+template <typename T>
+__global__ void letterbox_pad_kernel(T* __restrict__ dst, int canvas_w, int canvas_h, int x0, int y0, int cw, int ch, T pad0, T pad1, T pad2) {
+    const int plane = blockIdx.y % 3;
+    T* p = dst + (size_t)blockIdx.y * canvas_w * canvas_h;
+    const T v = plane == 0 ? pad0 : plane == 1 ? pad1 : pad2;
+    const int top = y0 * canvas_w, full = (canvas_h - ch) * canvas_w, side_w = canvas_w - cw;
+    const int total = full + ch * side_w;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int pos;
+        if (i < top) pos = i;
+        else if (i < full) pos = i + ch * canvas_w;
+        else {
+            const int j = i - full, r = j / side_w, xx = j - r * side_w;
+            pos = (y0 + r) * canvas_w + (xx < x0 ? xx : xx + cw);
+        }
+        p[pos] = v;
     }
 }
 

@@ -91,6 +91,12 @@ def c2_surfaces(iters):
         ms, _ = timeit(lambda: vacv.yuv_resize_normalize_chw(src, fmt, w, h, wo, ho, mean, std, y_pitch=yp, c_pitch=cp, batch=b,
                                                              half=half, out=out), iters)
         report(f"c2s fused {name} 1080p->640x640 x{b}", ms, b * wo * ho, b * (w * h * 3 // 2 + wo * ho * (6 if half else 12)))
+    src = rand_u8(b * w * h * 3 // 2)
+    for name, dt, tdt, eb in [("f32", vacv.FP32, torch.float32, 4), ("bf16", vacv.BF16, torch.bfloat16, 2)]:
+        out = torch.empty((b, 3, ho, wo), dtype=tdt, device="cuda")
+        ms, _ = timeit(lambda: vacv.yuv_letterbox_normalize_chw(src, vacv.YUV_NV12, w, h, wo, ho, [104., 117., 123.], [58., 57., 57.], batch=b,
+                                                                out_dtype=dt, out=out), iters)
+        report(f"c2s letterbox nv12 -> {name} 1080p->640x360 in 640x640 x{b}", ms, b * wo * ho, b * (w * h * 3 // 2 + wo * ho * 3 * eb))
 
 
 def c2_unfused(iters):

@@ -42,7 +42,8 @@ typedef enum {
     VACV_ERR_CUDA = -3           /* a CUDA runtime call or launch failed; message has the CUDA error string */
 } vacv_status;
 
-enum { VACV_FP32 = 0, VACV_FP16 = 1, VACV_INT8 = 2, VACV_FP64 = 3 };      /* vision::DType  */
+enum { VACV_FP32 = 0, VACV_FP16 = 1, VACV_INT8 = 2, VACV_FP64 = 3,        /* vision::DType (tensor.h:12-17) */
+       VACV_BF16 = 16 };                                                   /* extension: output type of the fused pipeline only */
 enum { VACV_NCHW = 0, VACV_NHWC = 1 };                                    /* vision::DLayout */
 enum { VACV_INTER_LINEAR = 1, VACV_INTER_CUBIC = 2 };                     /* va_cv::VInterMode (cv.h:28-36) */
 enum {
@@ -142,7 +143,8 @@ VACV_API int vacv_cuda_warp_affine_normalize(const uint8_t* frames, int n_frames
  * (I420 = Y,U,V; YV12 = Y,V,U; enum slot COLOR_YUV2BGR_YV12 of cv.h:73 has no reference implementation) chroma, same
  * integer colour matrix (cvt_color.cpp:76-78).  Plane order inside a frame: Y (h rows of y_pitch bytes), then chroma
  * (semi-planar: h/2 rows of c_pitch; planar: two planes of h/2 rows of c_pitch each).  0 = dense defaults.
- * dst: batch x 3 x h_out x w_out planes of out_dtype VACV_FP32 or VACV_FP16 (fp16 = the fp32 result rounded to nearest even).
+ * dst: batch x 3 x h_out x w_out planes of out_dtype VACV_FP32, VACV_FP16 or VACV_BF16 (16-bit = the fp32 result rounded to
+ * nearest even).
  * Pitches, plane sizes and frame_stride must be multiples of 16 bytes (TMA bulk copies); otherwise VACV_ERR_UNSUPPORTED. */
 enum { VACV_YUV_NV21 = 0, VACV_YUV_NV12 = 1, VACV_YUV_I420 = 2, VACV_YUV_YV12 = 3 };
 typedef struct {
@@ -153,6 +155,19 @@ typedef struct {
 } vacv_yuv_layout;
 VACV_API int vacv_cuda_yuv_resize_normalize_chw(const uint8_t* src, const vacv_yuv_layout* layout, void* dst, int out_dtype,
                                                 int batch, int w_out, int h_out, const float* mean, const float* stddev, void* stream);
+
+/* Letterbox (no reference implementation -- the reference resizes without preserving aspect, 8d C2):
+ * frame -> bilinear resize (the reference's rule, resize_naive.cpp:10-68) to content->w x content->h -> placed at
+ * (content->x, content->y) of a canvas_w x canvas_h canvas filled with pad_bgr -> normalise -> 3 CHW planes of
+ * out_dtype (VACV_FP32 / VACV_FP16 / VACV_BF16).  Bit-identical to running the unfused operators on the padded u8 canvas.
+ * mean / stddev: device pointers (3 floats); mean_host / stddev_host: the same values in host memory (for the pad colour).
+ * vacv_letterbox_rect computes the usual centred aspect-preserving content rectangle. */
+typedef struct { int x, y, w, h; } vacv_rect;
+VACV_API void vacv_letterbox_rect(int w, int h, int canvas_w, int canvas_h, vacv_rect* content);
+VACV_API int vacv_cuda_yuv_letterbox_normalize_chw(const uint8_t* src, const vacv_yuv_layout* layout, void* dst, int out_dtype, int batch,
+                                                   int canvas_w, int canvas_h, const vacv_rect* content, const uint8_t* pad_bgr,
+                                                   const float* mean, const float* stddev, const float* mean_host, const float* stddev_host,
+                                                   void* stream);
 
 /* ---- host-buffer entry point of the fused pipeline (the end-to-end path) ------------------------------------------
  * Same operation as vacv_cuda_nv_resize_normalize_chw, but `h_src` / `h_dst` / `h_mean` / `h_stddev` are HOST pointers

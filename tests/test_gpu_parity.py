@@ -426,6 +426,53 @@ def test_fused_pipeline_yuv_surfaces(vacv, oracle, fmt, half, w, h, yp, cp, wo, 
         assert_same(got, want)
 
 
+def _bf16_round(x):
+    """fp32 -> bfloat16 (round to nearest even) -> fp32, in numpy."""
+    u = x.astype(np.float32).view(np.uint32).astype(np.uint64)
+    r = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16).astype(np.uint32) << 16
+    return r.view(np.float32)
+
+
+@pytest.mark.parametrize("out_dtype", ["f32", "f16", "bf16"])
+@pytest.mark.parametrize("fmt,w,h,cw,ch,content", [(1, 1920, 1080, 640, 640, None), (0, 1280, 720, 640, 384, (10, 6, 600, 338)),
+                                                  (2, 640, 480, 416, 416, None), (3, 64, 32, 101, 77, (7, 9, 51, 40)),
+                                                  (1, 1080, 1920, 640, 640, None), (0, 1920, 1080, 640, 360, (0, 0, 640, 360))])
+def test_fused_pipeline_letterbox(vacv, oracle, out_dtype, fmt, w, h, cw, ch, content):
+    """Next row 8f-3: aspect-preserving placement on a padded canvas + fp16 / bf16 planes == unfused chain on the padded canvas."""
+    from test_oracle_vs_ref import make_yuv_surface
+    b, pad = 2, (114, 100, 7)
+    planar = fmt >= 2
+    y_pitch = (w + 31) & ~31                      # decoder surfaces: pitch aligned (the TMA path needs multiples of 16)
+    c_pitch = y_pitch // 2 if planar else y_pitch
+    per = y_pitch * h * 3 // 2
+    buf = np.empty(b * per, np.uint8)
+    x0, y0, rw, rh = content if content is not None else vacv.letterbox_rect(w, h, cw, ch)
+    want = np.empty((b, 3, ch, cw), np.float32)
+    for i in range(b):
+        surf, _ = make_yuv_surface(200 * i + w + fmt, fmt, w, h, y_pitch, c_pitch)
+        buf[i * per:(i + 1) * per] = surf
+        bgr = oracle.yuv_to_bgr(surf, fmt, w, h, y_pitch, c_pitch)
+        canvas = np.empty((ch, cw, 3), np.uint8)
+        canvas[:] = np.array(pad, np.uint8)
+        canvas[y0:y0 + rh, x0:x0 + rw] = oracle.resize_linear(bgr, w, h, 3, NHWC, rw, rh)
+        want[i] = oracle.hwc_to_chw(oracle.normalize(canvas, cw * ch, 3, NHWC, MEAN, STD), cw, ch, 3)
+    dt = {"f32": vacv.FP32, "f16": vacv.FP16, "bf16": vacv.BF16}[out_dtype]
+    got = vacv.yuv_letterbox_normalize_chw(dev(buf), fmt, w, h, cw, ch, MEAN, STD, pad_bgr=pad, content=content, y_pitch=y_pitch,
+                                           c_pitch=c_pitch, batch=b, out_dtype=dt)
+    if out_dtype == "bf16":
+        assert_same(got.float().cpu().numpy(), _bf16_round(want))
+    elif out_dtype == "f16":
+        assert_same(host(got), want.astype(np.float16))
+    else:
+        assert_same(host(got), want)
+
+
+def test_letterbox_rect_is_centred_and_aspect_preserving(vacv):
+    assert vacv.letterbox_rect(1920, 1080, 640, 640) == (0, 140, 640, 360)
+    assert vacv.letterbox_rect(1080, 1920, 640, 640) == (140, 0, 360, 640)
+    assert vacv.letterbox_rect(640, 480, 416, 416) == (0, 52, 416, 312)
+
+
 def test_fused_pipeline_yuv_dense_nv21_equals_base_entry(vacv):
     w, h, wo, ho, b = 1920, 1080, 640, 640, 2
     src = dev(u8(92, b, w * h * 3 // 2))
