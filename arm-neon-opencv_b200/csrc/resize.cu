@@ -69,25 +69,11 @@ __global__ void __launch_bounds__(kTileX * kTileY) resize_linear_u8_kernel(const
 // through shared memory into lane-contiguous 32-bit stores.
 constexpr int kC3Rows = 32;   // output rows per CTA of the u8c3 kernel (4 passes of 8 rows): amortises the coefficient set-up
 
-template <bool kSigned, bool kNeonRule>
-__global__ void __launch_bounds__(kTileX * kTileY) resize_linear_u8c3_kernel(const uint8_t* __restrict__ src,
-                                                                              uint8_t* __restrict__ dst, ResizeGeom g) {
-    __shared__ int s_sx[kTileX], s_cx[kTileX], s_sy[kC3Rows], s_cy[kC3Rows];
-    __shared__ __align__(16) uint32_t stage[kTileY][24];
+template <bool kSigned, bool kNeonRule, bool kLowRow>
+__device__ __forceinline__ void resize_linear_u8c3_rows(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, const ResizeGeom& g,
+                                                        const int* s_sx, const int* s_cx, const int* s_sy, const int* s_cy,
+                                                        uint32_t (*stage)[24]) {
     const int dx0 = blockIdx.x * kTileX, dy00 = blockIdx.y * kC3Rows;
-    const int t = threadIdx.y * kTileX + threadIdx.x;
-    if (t < kTileX + kC3Rows) {
-        const bool isx = t < kTileX;
-        const int d = isx ? dx0 + t : dy00 + (t - kTileX);
-        const int n_in = isx ? g.w : g.h, n_out = isx ? g.wo : g.ho;
-        const double scale = kNeonRule ? (double)n_in / (double)n_out : (double)((float)n_in / (float)n_out);
-        int s; float f;
-        linear_coord(min(d, n_out - 1), scale, n_in, s, f);
-        const int c0 = sat_short((1.f - f) * 2048.f), c1 = sat_short(f * 2048.f);
-        if (isx) { s_sx[t] = s; s_cx[t] = (c0 & 0xffff) | (c1 << 16); }
-        else { s_sy[t - kTileX] = s; s_cy[t - kTileX] = (c0 & 0xffff) | (c1 << 16); }
-    }
-    __syncthreads();
     const int lane = threadIdx.x;
     const int n = min(32, g.wo - dx0);
     const unsigned sx3 = (unsigned)s_sx[lane] * 3u;
@@ -107,10 +93,10 @@ __global__ void __launch_bounds__(kTileX * kTileY) resize_linear_u8c3_kernel(con
             const unsigned a = (unsigned)s_sy[ry] * row3 + sx3;
             uint32_t t0, t1, u0, u1;
             linear_taps_u8c3(img, a, t0, t1);
-            linear_taps_u8c3(img, a + row3, u0, u1);
-            int Ht[3], Hb[3];
-            hsum_u8c3<kSigned>(t0, t1, cx, Ht);   // p00*cx0 + p01*cx1
-            hsum_u8c3<kSigned>(u0, u1, cx, Hb);   // p10*cx0 + p11*cx1
+            if (kLowRow) linear_taps_u8c3(img, a + row3, u0, u1);
+            int Ht[3], Hb[3] = {0, 0, 0};
+            hsum_u8c3<kSigned>(t0, t1, cx, Ht);                 // p00*cx0 + p01*cx1
+            if (kLowRow) hsum_u8c3<kSigned>(u0, u1, cx, Hb);    // p10*cx0 + p11*cx1
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 if (kNeonRule) {   // resize_neon.cpp:145-181
@@ -127,6 +113,35 @@ __global__ void __launch_bounds__(kTileX * kTileY) resize_linear_u8c3_kernel(con
         else for (int bb = lane; bb < 3 * n; bb += 32) o[bb] = sb[bb];
         __syncwarp();
     }
+}
+
+
+template <bool kSigned, bool kNeonRule>
+__global__ void __launch_bounds__(kTileX * kTileY) resize_linear_u8c3_kernel(const uint8_t* __restrict__ src,
+                                                                              uint8_t* __restrict__ dst, ResizeGeom g) {
+    __shared__ int s_sx[kTileX], s_cx[kTileX], s_sy[kC3Rows], s_cy[kC3Rows];
+    __shared__ __align__(16) uint32_t stage[kTileY][24];
+    const int dx0 = blockIdx.x * kTileX, dy00 = blockIdx.y * kC3Rows;
+    const int t = threadIdx.y * kTileX + threadIdx.x;
+    if (t < kTileX + kC3Rows) {
+        const bool isx = t < kTileX;
+        const int d = isx ? dx0 + t : dy00 + (t - kTileX);
+        const int n_in = isx ? g.w : g.h, n_out = isx ? g.wo : g.ho;
+        const double scale = kNeonRule ? (double)n_in / (double)n_out : (double)((float)n_in / (float)n_out);
+        int s; float f;
+        linear_coord(min(d, n_out - 1), scale, n_in, s, f);
+        const int c0 = sat_short((1.f - f) * 2048.f), c1 = sat_short(f * 2048.f);
+        if (isx) { s_sx[t] = s; s_cx[t] = (c0 & 0xffff) | (c1 << 16); }
+        else { s_sy[t - kTileX] = s; s_cy[t - kTileX] = (c0 & 0xffff) | (c1 << 16); }
+    }
+    __syncthreads();
+    // Integer ratios (1080 -> 360) put every sample on a source row: the lower tap row has weight 0 everywhere.  When that holds
+    // for all rows of this CTA the lower row is not read at all (a third of the source traffic instead of two thirds); the
+    // test is CTA-uniform so the general case keeps its straight-line loop.
+    static_assert(kC3Rows == 32 && kTileX == 32, "one lane per row of the CTA");
+    const int any_low = __any_sync(0xffffffffu, dy00 + (int)threadIdx.x < g.ho && (s_cy[threadIdx.x] >> 16) != 0);
+    if (any_low) resize_linear_u8c3_rows<kSigned, kNeonRule, true>(src, dst, g, s_sx, s_cx, s_sy, s_cy, stage);
+    else resize_linear_u8c3_rows<kSigned, kNeonRule, false>(src, dst, g, s_sx, s_cx, s_sy, s_cy, stage);
 }
 
 // ----------------------------------------------------------------------------------------------------
