@@ -19,6 +19,7 @@
 #include "vacv_common.cuh"
 #include "fused_pipeline.cuh"
 #include <cmath>
+#include <type_traits>
 #include <cstdlib>
 #include <vector>
 
@@ -29,41 +30,59 @@ struct FusedGeom {
     int TW, TH;            // output tile
     int ypitch, cpitch;    // shared-memory row pitch (bytes) of the Y / chroma bands
     int yrows, crows;      // band capacity in rows
-    int vec;               // 1: 16-byte staging legal (w % 16 == 0, aligned base)
+    int vec;               // 1: 16-byte staging legal (pitches, offsets and base 16-byte aligned)
+    // source surface and destination canvas, as in PipeGeom
+    int y_pitch, c_pitch;
+    size_t frame_stride, c_off, c2_off;
+    int canvas_w, canvas_h, x0, y0;
+    int bf16;
 };
 
-template <bool kVFirst>
-__device__ __forceinline__ void hrow(const uint8_t* __restrict__ yrow, const uint8_t* __restrict__ crow,
+template <int FMT>
+__device__ __forceinline__ void hrow(const uint8_t* __restrict__ yrow, const uint8_t* __restrict__ crow, int vplane_off,
                                      int yo, int ca, int cb, int cx0, int cx1, int (&H)[3]) {
     const int Y0 = yrow[yo], Y1 = yrow[yo + 1];
-    const unsigned pa = *reinterpret_cast<const uint16_t*>(crow + ca);
-    const unsigned pb = *reinterpret_cast<const uint16_t*>(crow + cb);
-    const ChromaTerms ta = kVFirst ? chroma_terms(pa & 0xff, pa >> 8) : chroma_terms(pa >> 8, pa & 0xff);
-    const ChromaTerms tb = kVFirst ? chroma_terms(pb & 0xff, pb >> 8) : chroma_terms(pb >> 8, pb & 0xff);
+    ChromaTerms ta, tb;
+    if (FMT == kFmtPlanar) {   // crow = U row, crow + vplane_off = V row
+        ta = chroma_terms(crow[vplane_off + ca], crow[ca]);
+        tb = chroma_terms(crow[vplane_off + cb], crow[cb]);
+    } else {
+        const unsigned pa = *reinterpret_cast<const uint16_t*>(crow + ca);
+        const unsigned pb = *reinterpret_cast<const uint16_t*>(crow + cb);
+        ta = FMT == kFmtVU ? chroma_terms(pa & 0xff, pa >> 8) : chroma_terms(pa >> 8, pa & 0xff);
+        tb = FMT == kFmtVU ? chroma_terms(pb & 0xff, pb >> 8) : chroma_terms(pb >> 8, pb & 0xff);
+    }
     H[0] = add_clamp255(Y0, ta.ba) * cx0 + add_clamp255(Y1, tb.ba) * cx1;
     H[1] = add_clamp255(Y0, -ta.ga) * cx0 + add_clamp255(Y1, -tb.ga) * cx1;
     H[2] = add_clamp255(Y0, ta.ra) * cx0 + add_clamp255(Y1, tb.ra) * cx1;
 }
 
-template <bool kVFirst>
-__global__ void __launch_bounds__(320) nv_resize_normalize_chw_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst,
-                                                                       FusedGeom g, const float* __restrict__ mean,
-                                                                       const float* __restrict__ stddev) {
+__device__ __forceinline__ void store_out(float* p, float v) { st_stream4f(p, v); }
+__device__ __forceinline__ void store_out(unsigned short* p, unsigned short v) { asm volatile("st.global.cs.u16 [%0], %1;" ::"l"(p), "h"(v) : "memory"); }
+
+// Tiled kernel for every shape the persistent TMA pipeline does not take (pitch / width not a multiple of 16, bands too large
+// for its stages, w_out > 1536).  OutT = float or unsigned short (fp16 / bf16 bits).
+template <int FMT, typename OutT>
+__global__ void __launch_bounds__(320) yuv_resize_normalize_chw_tiled_kernel(const uint8_t* __restrict__ src, OutT* __restrict__ dst,
+                                                                             FusedGeom g, const float* __restrict__ mean,
+                                                                             const float* __restrict__ stddev) {
     extern __shared__ __align__(16) uint8_t smem[];
-    float* lut = reinterpret_cast<float*>(smem);                       // [3][256]
+    OutT* lut = reinterpret_cast<OutT*>(smem);                         // [3][256]
     int* s_sy = reinterpret_cast<int*>(smem + 3072);                   // [TH]
     int* s_cy = s_sy + g.TH;                                           // [TH]  cy0 | cy1 << 16
     int* s_misc = s_cy + g.TH;                                         // [4]   sx_first, sx_last
     uint8_t* ybuf = smem + 3072 + ((8 * g.TH + 16 + 15) & ~15);
-    uint8_t* cbuf = ybuf + (size_t)g.yrows * g.ypitch;
+    uint8_t* cbuf = ybuf + (size_t)g.yrows * g.ypitch;                 // semi-planar: VU / UV rows; planar: U rows then V rows
+    const int vplane_off = g.crows * g.cpitch;
 
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int tiles_x = (g.wo + g.TW - 1) / g.TW;
     const int dx0 = (blockIdx.x % tiles_x) * g.TW, dy0 = (blockIdx.x / tiles_x) * g.TH;
     const int tw = min(g.TW, g.wo - dx0), th = min(g.TH, g.ho - dy0);
     const size_t frame = blockIdx.y;
-    const uint8_t* yplane = src + frame * ((size_t)g.w * g.h * 3 / 2);
-    const uint8_t* cplane = yplane + (size_t)g.w * g.h;
+    const uint8_t* yplane = src + frame * g.frame_stride;
+    const uint8_t* cplane = yplane + g.c_off;
+    const uint8_t* c2plane = yplane + g.c2_off;
 
     // ---- coefficients (resize_naive.cpp:17-53) + normalisation table
     const double scale_x = (double)((float)g.w / (float)g.wo), scale_y = (double)((float)g.h / (float)g.ho);
@@ -78,7 +97,8 @@ __global__ void __launch_bounds__(320) nv_resize_normalize_chw_kernel(const uint
         linear_coord(dx0 + tw - 1, scale_x, g.w, s, f); s_misc[1] = s;
     }
     for (int t = tid; t < 768; t += nthr)
-        lut[t] = normalize_one((float)(t & 255), __ldg(mean + (t >> 8)), (double)__ldg(stddev + (t >> 8)) + 1e-6);
+        lut[t] = OutOps<typename std::conditional<sizeof(OutT) == 4, float, __half>::type>::make(
+            normalize_one((float)(t & 255), __ldg(mean + (t >> 8)), (double)__ldg(stddev + (t >> 8)) + 1e-6), g.bf16);
     __syncthreads();
 
     // ---- stage the source band
@@ -86,43 +106,49 @@ __global__ void __launch_bounds__(320) nv_resize_normalize_chw_kernel(const uint
     const int c_first = y_first >> 1, c_last = y_last >> 1;            // chroma rows
     const int xb0 = s_misc[0] & ~15;                                   // Y byte columns [xb0, xb1)
     const int xb1 = min((s_misc[1] + 2 + 15) & ~15, (g.w + 15) & ~15);
-    const int cb0 = xb0, cb1 = xb1;                                    // chroma bytes cover the same x range (2 bytes per 2 px)
+    const int cb0 = FMT == kFmtPlanar ? xb0 >> 1 : xb0;                // first chroma byte column (semi-planar: 2 bytes per 2 px)
     const int ywidth = xb1 - xb0;
-    if (g.vec) {
+    if (g.vec && FMT != kFmtPlanar) {
         const int cpr = ywidth >> 4;                                   // 16-byte chunks per row
         const int ny = (y_last - y_first + 1) * cpr, nc = (c_last - c_first + 1) * cpr;
         for (int i = tid; i < ny + nc; i += nthr) {
             const bool isy = i < ny;
             const int j = isy ? i : i - ny;
             const int r = j / cpr, q = j - r * cpr;
-            const uint8_t* gp = (isy ? yplane + (size_t)(y_first + r) * g.w : cplane + (size_t)(c_first + r) * g.w) + xb0 + 16 * q;
+            const uint8_t* gp = (isy ? yplane + (size_t)(y_first + r) * g.y_pitch : cplane + (size_t)(c_first + r) * g.c_pitch) + xb0 + 16 * q;
             uint8_t* sp = (isy ? ybuf + r * g.ypitch : cbuf + r * g.cpitch) + 16 * q;
             *reinterpret_cast<uint4*>(sp) = ld_stream16(gp);
         }
     } else {
         const int wy = min(xb1, g.w) - xb0;
-        const int ny = (y_last - y_first + 1) * wy, nc = (c_last - c_first + 1) * wy;
-        for (int i = tid; i < ny + nc; i += nthr) {
-            const bool isy = i < ny;
-            const int j = isy ? i : i - ny;
-            const int r = j / wy, q = j - r * wy;
-            if (isy) ybuf[r * g.ypitch + q] = __ldg(yplane + (size_t)(y_first + r) * g.w + xb0 + q);
-            else cbuf[r * g.cpitch + q] = __ldg(cplane + (size_t)(c_first + r) * g.w + cb0 + q);
+        const int wc = FMT == kFmtPlanar ? (wy + 1) >> 1 : wy;          // chroma bytes per row of one plane
+        const int ny = (y_last - y_first + 1) * wy, nc = (c_last - c_first + 1) * wc;
+        const int total = ny + (FMT == kFmtPlanar ? 2 * nc : nc);
+        for (int i = tid; i < total; i += nthr) {
+            if (i < ny) {
+                const int r = i / wy, q = i - r * wy;
+                ybuf[r * g.ypitch + q] = __ldg(yplane + (size_t)(y_first + r) * g.y_pitch + xb0 + q);
+            } else {
+                int j = i - ny;
+                const bool second = j >= nc;                            // planar: the V plane
+                if (second) j -= nc;
+                const int r = j / wc, q = j - r * wc;
+                cbuf[(second ? vplane_off : 0) + r * g.cpitch + q] = __ldg((second ? c2plane : cplane) + (size_t)(c_first + r) * g.c_pitch + cb0 + q);
+            }
         }
     }
-    (void)cb1;
     __syncthreads();
 
     // ---- compute: thread-owned columns, walk down the tile rows
-    const size_t plane = (size_t)g.wo * g.ho;
-    float* out = dst + frame * 3 * plane;
+    const size_t plane = (size_t)g.canvas_w * g.canvas_h;
+    OutT* out = dst + frame * 3 * plane + (size_t)g.y0 * g.canvas_w + g.x0;
     for (int col = tid; col < tw; col += nthr) {
         const int dx = dx0 + col;
         int sx; float fx;
         linear_coord(dx, scale_x, g.w, sx, fx);
         const int cx0 = sat_short((1.f - fx) * 2048.f), cx1 = sat_short(2048.f * fx);
         const int yo = sx - xb0;
-        const int ca = (sx & ~1) - cb0, cb = ((sx + 1) & ~1) - cb0;
+        const int ca = (FMT == kFmtPlanar ? sx >> 1 : sx & ~1) - cb0, cb = (FMT == kFmtPlanar ? (sx + 1) >> 1 : (sx + 1) & ~1) - cb0;
         int H0[3], H1[3];
         int have = -2;   // source row held in H1
         for (int ty = 0; ty < th; ++ty) {
@@ -132,17 +158,17 @@ __global__ void __launch_bounds__(320) nv_resize_normalize_chw_kernel(const uint
             if (sy == have) {   // the row below the previous output's pair is this output's top row
                 H0[0] = H1[0]; H0[1] = H1[1]; H0[2] = H1[2];
             } else if (sy + 1 != have) {
-                hrow<kVFirst>(ybuf + (sy - y_first) * g.ypitch, cbuf + ((sy >> 1) - c_first) * g.cpitch, yo, ca, cb, cx0, cx1, H0);
+                hrow<FMT>(ybuf + (sy - y_first) * g.ypitch, cbuf + ((sy >> 1) - c_first) * g.cpitch, vplane_off, yo, ca, cb, cx0, cx1, H0);
             }
             if (sy + 1 != have) {
-                hrow<kVFirst>(ybuf + (sy + 1 - y_first) * g.ypitch, cbuf + (((sy + 1) >> 1) - c_first) * g.cpitch, yo, ca, cb, cx0, cx1, H1);
+                hrow<FMT>(ybuf + (sy + 1 - y_first) * g.ypitch, cbuf + (((sy + 1) >> 1) - c_first) * g.cpitch, vplane_off, yo, ca, cb, cx0, cx1, H1);
                 have = sy + 1;
             }
-            const size_t o = (size_t)(dy0 + ty) * g.wo + dx;
+            const size_t o = (size_t)(dy0 + ty) * g.canvas_w + dx;
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 const int v = (H0[k] * cy0 + H1[k] * cy1) >> 22;
-                st_stream4f(out + k * plane + o, lut[k * 256 + (v & 0xff)]);
+                store_out(out + k * plane + o, lut[k * 256 + (v & 0xff)]);
             }
         }
     }
@@ -314,12 +340,63 @@ static int try_launch_pipe(const uint8_t* src, void* dst, int out_dtype, int bat
     return 1;
 }
 
+template <int FMT>
+static const void* tiled_kernel_for(bool half_out) {
+    return half_out ? (const void*)yuv_resize_normalize_chw_tiled_kernel<FMT, unsigned short> : (const void*)yuv_resize_normalize_chw_tiled_kernel<FMT, float>;
+}
+
+// The tiled kernel: any pitch, any width.  Returns a status code.
+static int launch_fused_tiled(const char* who, const uint8_t* src, void* dst, int out_dtype, int batch, const YuvSource& y, int w_out, int h_out,
+                              const Canvas& cv, const float* mean, const float* stddev, cudaStream_t s) {
+    const int w = y.w, h = y.h;
+    FusedGeom g;
+    g.w = w; g.h = h; g.wo = w_out; g.ho = h_out;
+    g.y_pitch = y.y_pitch; g.c_pitch = y.c_pitch; g.frame_stride = y.frame_stride; g.c_off = y.c_off; g.c2_off = y.c2_off;
+    g.canvas_w = cv.w; g.canvas_h = cv.h; g.x0 = cv.x0; g.y0 = cv.y0; g.bf16 = out_dtype == VACV_BF16 ? 1 : 0;
+    g.vec = (y.y_pitch % 16) == 0 && (y.c_pitch % 16) == 0 && (y.frame_stride % 16) == 0 && (y.c_off % 16) == 0 && (((uintptr_t)src) & 15) == 0;
+    const double sx = (double)w / w_out, sy = (double)h / h_out;
+    // tile: full output rows when the source span fits comfortably, else split in x
+    const int budget = 44 * 1024;   // ~4 CTAs / SM
+    const int cplanes = y.fmt == kFmtPlanar ? 2 : 1;
+    int TW = w_out, TH = 8;
+    auto span = [](double scale, int n) { return (int)(scale * (n - 1)) + 4; };
+    auto bytes = [&](int tw, int th) {
+        const int yp = (span(sx, tw) + 32 + 15) & ~15;
+        const int yr = span(sy, th) + 1, cr = yr / 2 + 2;
+        return (size_t)yp * (yr + cplanes * cr);
+    };
+    while (TH > 1 && bytes(TW, TH) > (size_t)budget) --TH;
+    while (TW > 32 && bytes(TW, TH) > (size_t)budget) TW = (TW + 1) / 2;
+    TW = (TW + 31) & ~31;
+    if (bytes(TW, TH) > 200 * 1024) return set_error(VACV_ERR_UNSUPPORTED, "%s: scale too large for the staged tile", who);
+    g.TW = TW; g.TH = TH;
+    g.ypitch = g.cpitch = (span(sx, TW) + 32 + 15) & ~15;
+    g.yrows = span(sy, TH) + 1; g.crows = g.yrows / 2 + 2;
+    const size_t smem = 3072 + ((8 * TH + 16 + 15) & ~15) + (size_t)g.ypitch * (g.yrows + cplanes * g.crows);
+    const int threads = 32 * std::max(1, std::min(10, (std::min(TW, w_out) + 63) / 64));   // ~2 columns per thread, <= 320
+    const int tiles = ceil_div(w_out, TW) * ceil_div(h_out, TH);
+    const bool half_out = out_dtype != VACV_FP32;
+    const void* kern = y.fmt == kFmtVU ? tiled_kernel_for<kFmtVU>(half_out) : y.fmt == kFmtUV ? tiled_kernel_for<kFmtUV>(half_out) : tiled_kernel_for<kFmtPlanar>(half_out);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return set_error(VACV_ERR_CUDA, "%s: %s", who, cudaGetErrorString(e));
+    }
+    const size_t dst_frame = (size_t)3 * cv.w * cv.h * (half_out ? 2 : 4);
+    for (int b0 = 0; b0 < batch; b0 += 65535) {
+        const uint8_t* sp = src + (size_t)b0 * y.frame_stride;
+        void* dp = (uint8_t*)dst + (size_t)b0 * dst_frame;
+        void* args[] = {(void*)&sp, (void*)&dp, (void*)&g, (void*)&mean, (void*)&stddev};
+        cudaError_t e = cudaLaunchKernel(kern, dim3(tiles, std::min(batch - b0, 65535)), dim3(threads), args, smem, s);
+        if (e != cudaSuccess) return set_error(VACV_ERR_CUDA, "%s: %s", who, cudaGetErrorString(e));
+    }
+    return check_launch(who);
+}
+
 extern "C" int vacv_cuda_nv_resize_normalize_chw(const uint8_t* src, float* dst, int batch, int w, int h, int v_first,
                                                  int w_out, int h_out, const float* mean, const float* stddev, void* stream) {
     VACV_REQUIRE(src && dst && mean && stddev, "nv_resize_normalize_chw: null pointer");
     VACV_REQUIRE(batch > 0 && w >= 2 && h >= 2 && w_out > 0 && h_out > 0, "nv_resize_normalize_chw: bad size");
     VACV_REQUIRE((w % 2) == 0 && (h % 2) == 0, "nv_resize_normalize_chw: w and h must be even (got %dx%d)", w, h);
-    VACV_REQUIRE(batch <= 65535, "nv_resize_normalize_chw: batch <= 65535 per call");
     if (w_out == w && h_out == h)   // resize.cpp:58-61 memcpy shortcut == identity taps; not on the fused fast path
         return set_error(VACV_ERR_UNSUPPORTED, "nv_resize_normalize_chw: same-size resize (compose cvt_nv2bgr + normalize + layout_change)");
     cudaStream_t s = as_stream(stream);
@@ -331,37 +408,7 @@ extern "C" int vacv_cuda_nv_resize_normalize_chw(const uint8_t* src, float* dst,
         if (rc < 0) return rc;
         return check_launch("nv_resize_normalize_chw (persistent)");
     }
-    FusedGeom g;
-    g.w = w; g.h = h; g.wo = w_out; g.ho = h_out;
-    g.vec = (w % 16) == 0 && (((uintptr_t)src) & 15) == 0;
-    const double sx = (double)w / w_out, sy = (double)h / h_out;
-    // tile: full output rows when the source span fits comfortably, else split in x
-    const int budget = 44 * 1024;   // ~4 CTAs / SM
-    int TW = w_out, TH = 8;
-    auto span = [](double scale, int n) { return (int)(scale * (n - 1)) + 4; };
-    auto bytes = [&](int tw, int th) {
-        const int yp = (span(sx, tw) + 32 + 15) & ~15;
-        const int yr = span(sy, th) + 1, cr = yr / 2 + 2;
-        return (size_t)yp * (yr + cr);
-    };
-    while (TH > 1 && bytes(TW, TH) > (size_t)budget) --TH;
-    while (TW > 32 && bytes(TW, TH) > (size_t)budget) TW = (TW + 1) / 2;
-    TW = (TW + 31) & ~31;
-    if (bytes(TW, TH) > 200 * 1024) return set_error(VACV_ERR_UNSUPPORTED, "nv_resize_normalize_chw: scale too large for the staged tile");
-    g.TW = TW; g.TH = TH;
-    g.ypitch = g.cpitch = (span(sx, TW) + 32 + 15) & ~15;
-    g.yrows = span(sy, TH) + 1; g.crows = g.yrows / 2 + 2;
-    const size_t smem = 3072 + ((8 * TH + 16 + 15) & ~15) + (size_t)g.ypitch * (g.yrows + g.crows);
-    int threads = 32 * max(1, min(10, (min(TW, w_out) + 63) / 64));   // ~2 columns per thread, <= 320
-    const int tiles = ceil_div(w_out, TW) * ceil_div(h_out, TH);
-    dim3 grid(tiles, batch);
-    auto kern = v_first ? nv_resize_normalize_chw_kernel<true> : nv_resize_normalize_chw_kernel<false>;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return set_error(VACV_ERR_CUDA, "nv_resize_normalize_chw: %s", cudaGetErrorString(e));
-    }
-    kern<<<grid, threads, smem, s>>>(src, dst, g, mean, stddev);
-    return check_launch("nv_resize_normalize_chw");
+    return launch_fused_tiled("nv_resize_normalize_chw", src, dst, VACV_FP32, batch, ys, w_out, h_out, whole, mean, stddev, s);
 }
 
 extern "C" int vacv_cuda_resize_normalize(const uint8_t* src, float* dst, int batch, int w, int h, int c,
@@ -421,8 +468,7 @@ extern "C" int vacv_cuda_yuv_resize_normalize_chw(const uint8_t* src, const vacv
     const Canvas whole = {w_out, h_out, 0, 0};
     const int rc = try_launch_pipe(src, dst, out_dtype, batch, ys, w_out, h_out, whole, mean, stddev, as_stream(stream));
     if (rc < 0) return rc;
-    if (rc == 0) return set_error(VACV_ERR_UNSUPPORTED, "yuv_resize_normalize_chw: layout not eligible for the TMA pipeline "
-                                  "(pitches, plane offsets and frame stride must be multiples of 16; w_out <= 1536)");
+    if (rc == 0) return launch_fused_tiled("yuv_resize_normalize_chw", src, dst, out_dtype, batch, ys, w_out, h_out, whole, mean, stddev, as_stream(stream));
     return check_launch("yuv_resize_normalize_chw");
 }
 
@@ -474,7 +520,6 @@ extern "C" int vacv_cuda_yuv_letterbox_normalize_chw(const uint8_t* src, const v
     const Canvas cv = {canvas_w, canvas_h, content->x, content->y};
     const int rc = try_launch_pipe(src, dst, out_dtype, batch, ys, content->w, content->h, cv, mean, stddev, s);
     if (rc < 0) return rc;
-    if (rc == 0) return set_error(VACV_ERR_UNSUPPORTED, "yuv_letterbox_normalize_chw: layout not eligible for the TMA pipeline "
-                                  "(pitches, plane offsets and frame stride must be multiples of 16; content width <= 1536)");
+    if (rc == 0) return launch_fused_tiled("yuv_letterbox_normalize_chw", src, dst, out_dtype, batch, ys, content->w, content->h, cv, mean, stddev, s);
     return check_launch("yuv_letterbox_normalize_chw");
 }

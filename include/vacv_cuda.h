@@ -145,7 +145,8 @@ VACV_API int vacv_cuda_warp_affine_normalize(const uint8_t* frames, int n_frames
  * (semi-planar: h/2 rows of c_pitch; planar: two planes of h/2 rows of c_pitch each).  0 = dense defaults.
  * dst: batch x 3 x h_out x w_out planes of out_dtype VACV_FP32, VACV_FP16 or VACV_BF16 (16-bit = the fp32 result rounded to
  * nearest even).
- * Pitches, plane sizes and frame_stride must be multiples of 16 bytes (TMA bulk copies); otherwise VACV_ERR_UNSUPPORTED. */
+ * Pitches, plane sizes and frame_stride that are multiples of 16 bytes run on the persistent TMA pipeline; anything else on
+ * the tiled kernel (same results, register-staged loads). */
 enum { VACV_YUV_NV21 = 0, VACV_YUV_NV12 = 1, VACV_YUV_I420 = 2, VACV_YUV_YV12 = 3 };
 typedef struct {
     int format;            /* VACV_YUV_* */

@@ -442,7 +442,7 @@ def test_fused_pipeline_letterbox(vacv, oracle, out_dtype, fmt, w, h, cw, ch, co
     from test_oracle_vs_ref import make_yuv_surface
     b, pad = 2, (114, 100, 7)
     planar = fmt >= 2
-    y_pitch = (w + 31) & ~31                      # decoder surfaces: pitch aligned (the TMA path needs multiples of 16)
+    y_pitch = (w + 31) & ~31 if fmt != 1 else w   # aligned decoder pitch (TMA pipeline); dense NV12 1080-wide -> tiled kernel
     c_pitch = y_pitch // 2 if planar else y_pitch
     per = y_pitch * h * 3 // 2
     buf = np.empty(b * per, np.uint8)
@@ -481,10 +481,25 @@ def test_fused_pipeline_yuv_dense_nv21_equals_base_entry(vacv):
     assert_same(host(a), host(c))
 
 
-def test_fused_pipeline_yuv_rejects_unaligned_pitch(vacv):
-    src = dev(u8(93, 2 * (72 * 32 * 3 // 2)))
-    with pytest.raises(vacv.VacvError):
-        vacv.yuv_resize_normalize_chw(src, 0, 64, 32, 20, 20, dev(MEAN), dev(STD), y_pitch=72, c_pitch=72, batch=1)
+@pytest.mark.parametrize("half", [False, True])
+@pytest.mark.parametrize("fmt", [0, 1, 2, 3])
+@pytest.mark.parametrize("w,h,yp,cp,wo,ho", [(64, 32, 72, 0, 20, 20), (1080, 1920, 0, 0, 360, 640), (100, 60, 104, 60, 333, 77),
+                                            (1920, 1080, 0, 0, 1600, 900)])
+def test_fused_pipeline_yuv_tiled_kernel_shapes(vacv, oracle, fmt, half, w, h, yp, cp, wo, ho):
+    """Shapes the TMA pipeline does not take (pitch / width not a multiple of 16, w_out > 1536) run on the tiled kernel."""
+    from test_oracle_vs_ref import make_yuv_surface
+    planar = fmt >= 2
+    y_pitch = yp or w
+    c_pitch = cp or (y_pitch // 2 if planar else y_pitch)
+    if not planar:
+        c_pitch = max(c_pitch, w)
+    surf, _ = make_yuv_surface(300 + w + fmt, fmt, w, h, y_pitch, c_pitch)
+    bgr = oracle.yuv_to_bgr(surf, fmt, w, h, y_pitch, c_pitch)
+    small = oracle.resize_linear(bgr, w, h, 3, NHWC, wo, ho)
+    want = oracle.hwc_to_chw(oracle.normalize(small, wo * ho, 3, NHWC, MEAN, STD), wo, ho, 3)[None]
+    got = host(vacv.yuv_resize_normalize_chw(dev(surf), fmt, w, h, wo, ho, dev(MEAN), dev(STD), y_pitch=y_pitch, c_pitch=c_pitch,
+                                             batch=1, half=half))
+    assert_same(got, want.astype(np.float16) if half else want)
 
 
 def test_fused_pipeline_equals_unfused_cuda_chain(vacv):
