@@ -42,6 +42,7 @@ _SIGS = {
     "vacv_cuda_normalize": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp],
     "vacv_cuda_nv_resize_normalize_chw": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp],
     "vacv_cuda_yuv_resize_normalize_chw": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp],
+    "vacv_cuda_cvt_yuv2bgr": [_vp, _vp, _vp, _i, _vp],
     "vacv_cuda_yuv_letterbox_normalize_chw": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "vacv_letterbox_rect": [_i, _i, _i, _i, _vp],
     "vacv_cuda_nv_resize_normalize_chw_host": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i],
@@ -267,6 +268,17 @@ def yuv_resize_normalize_chw(src, fmt, w, h, w_out, h_out, mean, std, y_pitch=0,
     dst = out if out is not None else torch.empty((batch, 3, h_out, w_out), dtype=_torch_out_dtype(out_dtype), device=src.device)
     _check(lib.vacv_cuda_yuv_resize_normalize_chw(src.data_ptr(), C.addressof(lay), dst.data_ptr(), out_dtype, batch,
                                                   w_out, h_out, mean.data_ptr(), std.data_ptr(), _stream()))
+    return dst
+
+
+def cvt_yuv2bgr(src, fmt, w, h, y_pitch=0, c_pitch=0, frame_stride=0, batch=None):
+    """Colour conversion of pitched / planar surfaces -> dense HWC BGR uint8 [batch, h, w, 3]."""
+    src = _dev(src, torch.uint8)
+    lay = YuvLayout(fmt, w, h, y_pitch, c_pitch, frame_stride)
+    if batch is None:
+        batch = _yuv_batch(src, fmt, w, h, y_pitch, c_pitch, frame_stride)
+    dst = torch.empty((batch, h, w, 3), dtype=torch.uint8, device=src.device)
+    _check(lib.vacv_cuda_cvt_yuv2bgr(src.data_ptr(), C.addressof(lay), dst.data_ptr(), batch, _stream()))
     return dst
 
 

@@ -4,6 +4,8 @@
 // 8 chroma pairs it needs are loaded once (the reference does the same per 2x2 quad, cvt_color.cpp:68-131):
 // three 128-bit loads in, 2 x 48 B out.  The 48-byte-per-lane output is re-chunked through a per-warp shared
 // memory buffer so that every global store is a full-sector, lane-contiguous 128-bit access.
+#include <algorithm>
+
 #include "vacv_common.cuh"
 
 namespace vacv {
@@ -30,32 +32,49 @@ __device__ __forceinline__ void convert16(const uint4& y, const ChromaTerms (&t)
 
 constexpr int kCvtThreads = 128;
 
-// grid.x = batch * h/2 (row pairs), grid.y = ceil(w/16 / 128).   Requires w % 16 == 0 and 16-byte aligned frames.
-template <bool kVFirst>
-__global__ void __launch_bounds__(kCvtThreads) nv2bgr_strip16_kernel(const uint8_t* __restrict__ src,
-                                                                       uint8_t* __restrict__ dst, int w, int h) {
+enum { kCvtVU = 0, kCvtUV = 1, kCvtPlanar = 2 };   // interleaved chroma V-first (NV21) / U-first (NV12), separate U and V planes (I420 / YV12)
+
+struct CvtGeom {
+    int w, h;
+    int y_pitch, c_pitch;          // bytes per luma / chroma row (planar: per U or V row)
+    size_t frame_stride;           // bytes between frames
+    size_t c_off, c2_off;          // chroma plane (semi-planar) or U and V planes (planar) inside a frame
+};
+
+// grid.x = batch * h/2 (row pairs), grid.y = ceil(w/16 / 128).   Requires w % 16 == 0 and 16-byte aligned rows (planar chroma: 8).
+template <int FMT>
+__global__ void __launch_bounds__(kCvtThreads) yuv2bgr_strip16_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, CvtGeom g) {
     __shared__ __align__(16) uint4 stage[kCvtThreads / 32][2][96];   // per warp: 2 rows x 1536 B
+    const int w = g.w, h = g.h;
     const int strips = w >> 4;
     const int strip = blockIdx.y * kCvtThreads + threadIdx.x;
     const int pair = blockIdx.x % (h >> 1);
     const int frame = blockIdx.x / (h >> 1);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const size_t in_frame = (size_t)w * h * 3 / 2, out_frame = (size_t)w * h * 3;
-    const uint8_t* y0p = src + frame * in_frame + (size_t)(2 * pair) * w;
-    const uint8_t* cp = src + frame * in_frame + (size_t)w * h + (size_t)pair * w;
+    const size_t out_frame = (size_t)w * h * 3;
+    const uint8_t* f = src + frame * g.frame_stride;
+    const uint8_t* y0p = f + (size_t)(2 * pair) * g.y_pitch;
     const bool active = strip < strips;
 
     if (active) {
         const uint4 y0 = ld_stream16(y0p + 16 * strip);
-        const uint4 y1 = ld_stream16(y0p + w + 16 * strip);
-        const uint4 vu = ld_stream16(cp + 16 * strip);
-        const uint32_t cw[4] = {vu.x, vu.y, vu.z, vu.w};
+        const uint4 y1 = ld_stream16(y0p + g.y_pitch + 16 * strip);
         ChromaTerms t[8];
+        if (FMT == kCvtPlanar) {
+            const uint2 u8 = __ldg(reinterpret_cast<const uint2*>(f + g.c_off + (size_t)pair * g.c_pitch + 8 * strip));
+            const uint2 v8 = __ldg(reinterpret_cast<const uint2*>(f + g.c2_off + (size_t)pair * g.c_pitch + 8 * strip));
+            const uint32_t uw[2] = {u8.x, u8.y}, vw[2] = {v8.x, v8.y};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            uint32_t pr = (cw[i >> 1] >> (16 * (i & 1))) & 0xffff;
-            int c0 = pr & 0xff, c1 = pr >> 8;
-            t[i] = kVFirst ? chroma_terms(c0, c1) : chroma_terms(c1, c0);
+            for (int i = 0; i < 8; ++i) t[i] = chroma_terms((vw[i >> 2] >> (8 * (i & 3))) & 0xff, (uw[i >> 2] >> (8 * (i & 3))) & 0xff);
+        } else {
+            const uint4 vu = ld_stream16(f + g.c_off + (size_t)pair * g.c_pitch + 16 * strip);
+            const uint32_t cw[4] = {vu.x, vu.y, vu.z, vu.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                uint32_t pr = (cw[i >> 1] >> (16 * (i & 1))) & 0xffff;
+                int c0 = pr & 0xff, c1 = pr >> 8;
+                t[i] = FMT == kCvtVU ? chroma_terms(c0, c1) : chroma_terms(c1, c0);
+            }
         }
         uint32_t o[12];
         convert16(y0, t, o);
@@ -79,26 +98,33 @@ __global__ void __launch_bounds__(kCvtThreads) nv2bgr_strip16_kernel(const uint8
         }
 }
 
-// any even w, h: one thread per 2x2 quad (the reference's own unit of work)
-template <bool kVFirst>
-__global__ void nv2bgr_quad_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int w, int h, size_t quads) {
+// any even w, h, any pitch: one thread per 2x2 quad (the reference's own unit of work)
+template <int FMT>
+__global__ void yuv2bgr_quad_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, CvtGeom g, size_t quads) {
     size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= quads) return;
+    const int w = g.w, h = g.h;
     const int qw = w >> 1, qh = h >> 1;
     const int qx = (int)(q % qw);
     const int qy = (int)((q / qw) % qh);
     const size_t frame = q / ((size_t)qw * qh);
-    const uint8_t* f = src + frame * ((size_t)w * h * 3 / 2);
-    const uint8_t* cp = f + (size_t)w * h + (size_t)qy * w + 2 * qx;
-    const int c0 = cp[0], c1 = cp[1];
-    const ChromaTerms t = kVFirst ? chroma_terms(c0, c1) : chroma_terms(c1, c0);
+    const uint8_t* f = src + frame * g.frame_stride;
+    ChromaTerms t;
+    if (FMT == kCvtPlanar) {
+        t = chroma_terms(f[g.c2_off + (size_t)qy * g.c_pitch + qx], f[g.c_off + (size_t)qy * g.c_pitch + qx]);
+    } else {
+        const uint8_t* cp = f + g.c_off + (size_t)qy * g.c_pitch + 2 * qx;
+        const int c0 = cp[0], c1 = cp[1];
+        t = FMT == kCvtVU ? chroma_terms(c0, c1) : chroma_terms(c1, c0);
+    }
     uint8_t* o = dst + frame * ((size_t)w * h * 3);
 #pragma unroll
     for (int r = 0; r < 2; ++r)
 #pragma unroll
         for (int x = 0; x < 2; ++x) {
-            size_t p = (size_t)(2 * qy + r) * w + 2 * qx + x;
-            int Y = f[p];
+            const int row = 2 * qy + r, col = 2 * qx + x;
+            const size_t p = (size_t)row * w + col;
+            int Y = f[(size_t)row * g.y_pitch + col];
             o[3 * p + 0] = (uint8_t)add_clamp255(Y, t.ba);
             o[3 * p + 1] = (uint8_t)add_clamp255(Y, -t.ga);
             o[3 * p + 2] = (uint8_t)add_clamp255(Y, t.ra);
@@ -109,20 +135,67 @@ __global__ void nv2bgr_quad_kernel(const uint8_t* __restrict__ src, uint8_t* __r
 
 using namespace vacv;
 
+template <int FMT>
+static void launch_cvt(const uint8_t* src, uint8_t* dst, int batch, const CvtGeom& g, bool aligned, cudaStream_t s) {
+    if (aligned) {
+        const long long pairs = (long long)batch * (g.h / 2);
+        for (long long p0 = 0; p0 < pairs; p0 += 0x7fffff00LL / (g.h / 2) * (g.h / 2)) {   // whole frames per launch, grid.x < 2^31
+            const long long np = std::min<long long>(pairs - p0, 0x7fffff00LL / (g.h / 2) * (g.h / 2));
+            const size_t f0 = (size_t)(p0 / (g.h / 2));
+            dim3 grid((unsigned)np, ceil_div(g.w / 16, kCvtThreads));
+            yuv2bgr_strip16_kernel<FMT><<<grid, kCvtThreads, 0, s>>>(src + f0 * g.frame_stride, dst + f0 * (size_t)g.w * g.h * 3, g);
+        }
+    } else {
+        const size_t quads = (size_t)batch * (g.w / 2) * (g.h / 2);
+        yuv2bgr_quad_kernel<FMT><<<ceil_div(quads, 256), 256, 0, s>>>(src, dst, g, quads);
+    }
+}
+
+static int cvt_dispatch(const char* who, const uint8_t* src, uint8_t* dst, int batch, int fmt, const CvtGeom& g, cudaStream_t s) {
+    const int cpix = fmt == kCvtPlanar ? 8 : 16;   // chroma bytes per 16-pixel strip
+    const bool aligned = (g.w % 16) == 0 && (g.y_pitch % 16) == 0 && (g.c_pitch % cpix) == 0 && (g.frame_stride % 16) == 0 &&
+                         (g.c_off % cpix) == 0 && (g.c2_off % cpix) == 0 && (((uintptr_t)src | (uintptr_t)dst) & 15) == 0;
+    if (fmt == kCvtVU) launch_cvt<kCvtVU>(src, dst, batch, g, aligned, s);
+    else if (fmt == kCvtUV) launch_cvt<kCvtUV>(src, dst, batch, g, aligned, s);
+    else launch_cvt<kCvtPlanar>(src, dst, batch, g, aligned, s);
+    return check_launch(who);
+}
+
 extern "C" int vacv_cuda_cvt_nv2bgr(const uint8_t* src, uint8_t* dst, int batch, int w, int h, int v_first, void* stream) {
     VACV_REQUIRE(src && dst, "cvt_nv2bgr: null pointer");
     VACV_REQUIRE(batch > 0 && w > 0 && h > 0, "cvt_nv2bgr: non-positive size");
     VACV_REQUIRE((w % 2) == 0 && (h % 2) == 0, "cvt_nv2bgr: w and h must be even (got %dx%d)", w, h);
-    cudaStream_t s = as_stream(stream);
-    const bool aligned = (w % 16) == 0 && (((uintptr_t)src | (uintptr_t)dst) & 15) == 0;
-    if (aligned) {
-        dim3 grid((unsigned)(batch * (h / 2)), ceil_div(w / 16, kCvtThreads));
-        if (v_first) nv2bgr_strip16_kernel<true><<<grid, kCvtThreads, 0, s>>>(src, dst, w, h);
-        else nv2bgr_strip16_kernel<false><<<grid, kCvtThreads, 0, s>>>(src, dst, w, h);
+    CvtGeom g;
+    g.w = w; g.h = h; g.y_pitch = w; g.c_pitch = w; g.frame_stride = (size_t)w * h * 3 / 2; g.c_off = (size_t)w * h; g.c2_off = 0;
+    return cvt_dispatch("cvt_nv2bgr", src, dst, batch, v_first ? kCvtVU : kCvtUV, g, as_stream(stream));
+}
+
+// Next row 8f-1: the same colour matrix on decoder surfaces -- row pitch, NV12 / NV21 or planar I420 / YV12 chroma
+// (the reference declares COLOR_YUV2BGR_YV12, cv.h:73, without implementing it).  dst: dense HWC BGR.
+extern "C" int vacv_cuda_cvt_yuv2bgr(const uint8_t* src, const vacv_yuv_layout* layout, uint8_t* dst, int batch, void* stream) {
+    VACV_REQUIRE(src && layout && dst, "cvt_yuv2bgr: null pointer");
+    const int w = layout->w, h = layout->h;
+    VACV_REQUIRE(batch > 0 && w > 0 && h > 0, "cvt_yuv2bgr: non-positive size");
+    VACV_REQUIRE((w % 2) == 0 && (h % 2) == 0, "cvt_yuv2bgr: w and h must be even (got %dx%d)", w, h);
+    const bool planar = layout->format == VACV_YUV_I420 || layout->format == VACV_YUV_YV12;
+    if (!planar && layout->format != VACV_YUV_NV12 && layout->format != VACV_YUV_NV21)
+        return set_error(VACV_ERR_UNSUPPORTED, "cvt_yuv2bgr: format %d", layout->format);
+    CvtGeom g;
+    g.w = w; g.h = h;
+    g.y_pitch = layout->y_pitch ? layout->y_pitch : w;
+    g.c_pitch = layout->c_pitch ? layout->c_pitch : (planar ? w / 2 : w);
+    VACV_REQUIRE(g.y_pitch >= w && g.c_pitch >= (planar ? w / 2 : w), "cvt_yuv2bgr: pitch smaller than the row");
+    const size_t y_bytes = (size_t)g.y_pitch * h, c_bytes = (size_t)g.c_pitch * (h / 2);
+    g.frame_stride = layout->frame_stride ? layout->frame_stride : y_bytes + (planar ? 2 * c_bytes : c_bytes);
+    VACV_REQUIRE(g.frame_stride >= y_bytes + (planar ? 2 * c_bytes : c_bytes), "cvt_yuv2bgr: frame_stride too small");
+    int fmt;
+    if (planar) {
+        fmt = kCvtPlanar;
+        g.c_off = layout->format == VACV_YUV_I420 ? y_bytes : y_bytes + c_bytes;    // U plane
+        g.c2_off = layout->format == VACV_YUV_I420 ? y_bytes + c_bytes : y_bytes;   // V plane
     } else {
-        size_t quads = (size_t)batch * (w / 2) * (h / 2);
-        if (v_first) nv2bgr_quad_kernel<true><<<ceil_div(quads, 256), 256, 0, s>>>(src, dst, w, h, quads);
-        else nv2bgr_quad_kernel<false><<<ceil_div(quads, 256), 256, 0, s>>>(src, dst, w, h, quads);
+        fmt = layout->format == VACV_YUV_NV21 ? kCvtVU : kCvtUV;
+        g.c_off = y_bytes; g.c2_off = 0;
     }
-    return check_launch("cvt_nv2bgr");
+    return cvt_dispatch("cvt_yuv2bgr", src, dst, batch, fmt, g, as_stream(stream));
 }

@@ -71,14 +71,21 @@ void resize(const Tensor& src, Tensor& dst, VSize dsize, double /*fx*/, double /
 
 // ---------------------------------------------------------------------------------------------------- cvt_color
 void cvt_color(const Tensor& src, Tensor& dst, int code) {
-    if (code != COLOR_YUV2BGR_NV21 && code != COLOR_YUV2BGR_NV12) unsupported("cvt_color with this code (cvt_color.cpp:139-141)");
-    if (src.empty() || src.dtype != vision::INT8) throw std::runtime_error("vacv: cvt_color needs an INT8 NV21/NV12 tensor");
+    if (code != COLOR_YUV2BGR_NV21 && code != COLOR_YUV2BGR_NV12 && code != COLOR_YUV2BGR_YV12)
+        unsupported("cvt_color with this code (cvt_color.cpp:139-141)");
+    if (src.empty() || src.dtype != vision::INT8) throw std::runtime_error("vacv: cvt_color needs an INT8 NV21/NV12/YV12 tensor");
     const Tensor in = src;
     const int w = in.w, h = in.h / 3 * 2;   // cvt_color.cpp:151-152
     dst.create(w, h, 3, vision::NHWC, vision::INT8);
     DeviceContext& ctx = DeviceContext::current();
     void* d_in = ctx.upload(0, in.data, (size_t)w * h * 3 / 2);
     void* d_out = ctx.scratch(1, dst.len());
+    if (code == COLOR_YUV2BGR_YV12) {   // declared by the reference (cv.h:73) but never implemented there: planar Y, V, U
+        vacv_yuv_layout lay = {VACV_YUV_YV12, w, h, 0, 0, 0};
+        ctx.check(vacv_cuda_cvt_yuv2bgr(static_cast<const uint8_t*>(d_in), &lay, static_cast<uint8_t*>(d_out), 1, ctx.stream()));
+        ctx.download(dst.data, d_out, dst.len());
+        return;
+    }
     // the reference decodes both codes with V-first chroma (the swap at :146 tests the wrong enum), kept for parity
     ctx.check(vacv_cuda_cvt_nv2bgr(static_cast<const uint8_t*>(d_in), static_cast<uint8_t*>(d_out), 1, w, h, 1, ctx.stream()));
     ctx.download(dst.data, d_out, dst.len());

@@ -156,6 +156,9 @@ typedef struct {
 } vacv_yuv_layout;
 VACV_API int vacv_cuda_yuv_resize_normalize_chw(const uint8_t* src, const vacv_yuv_layout* layout, void* dst, int out_dtype,
                                                 int batch, int w_out, int h_out, const float* mean, const float* stddev, void* stream);
+/* The colour conversion alone on such surfaces (cvt_color.cpp:39-135 generalised; gives va_cv::cvt_color its
+ * COLOR_YUV2BGR_YV12 case).  dst: batch dense HWC BGR frames. */
+VACV_API int vacv_cuda_cvt_yuv2bgr(const uint8_t* src, const vacv_yuv_layout* layout, uint8_t* dst, int batch, void* stream);
 
 /* Letterbox (no reference implementation -- the reference resizes without preserving aspect, 8d C2):
  * frame -> bilinear resize (the reference's rule, resize_naive.cpp:10-68) to content->w x content->h -> placed at

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <stdexcept>
+#include <algorithm>
 #include <vector>
 
 #include "common/tensor.h"
@@ -87,6 +88,16 @@ int main() {
             orc_nv_to_bgr(nv.data(), w, h, 1, want.data());
             report("cvt_color NV21 -> BGR", bgr21.w == w && bgr21.h == h && bgr21.c == 3 && bgr21.layout == NHWC && same(bgr21, want));
             report("cvt_color NV12 code decodes V-first like the reference", same(bgr12, want));
+            // COLOR_YUV2BGR_YV12 (declared at cv.h:73, no reference implementation): the same samples as planar Y, V, U
+            std::vector<uint8_t> yv((size_t)w * h * 3 / 2);
+            std::copy(nv.begin(), nv.begin() + (size_t)w * h, yv.begin());
+            for (size_t i = 0; i < (size_t)w * h / 4; ++i) {
+                yv[(size_t)w * h + i] = nv[(size_t)w * h + 2 * i];                          // V plane
+                yv[(size_t)w * h + (size_t)w * h / 4 + i] = nv[(size_t)w * h + 2 * i + 1];  // U plane
+            }
+            Tensor yvt(w, h * 3 / 2, 1, yv.data(), INT8, NCHW), bgryv;
+            va_cv::cvt_color(yvt, bgryv, va_cv::COLOR_YUV2BGR_YV12);
+            report("cvt_color YV12 (planar) -> BGR", same(bgryv, want));
         }
         {   // test_change_dtype.cpp
             Tensor f = src_u8.change_dtype(FP32);

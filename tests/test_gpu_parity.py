@@ -391,6 +391,30 @@ def test_fused_pipeline_config2(vacv, oracle, v_first, w, h, wo, ho, b):
     assert a @ bb / np.sqrt((a @ a) * (bb @ bb)) >= 0.99999
 
 
+@pytest.mark.parametrize("fmt", [0, 1, 2, 3])
+@pytest.mark.parametrize("w,h,yp,cp", [(16, 8, 0, 0), (176, 144, 192, 0), (642, 362, 656, 336), (1920, 1080, 2048, 0), (1920, 1080, 0, 0),
+                                       (100, 60, 0, 0)])
+def test_cvt_yuv2bgr_surfaces(vacv, oracle, fmt, w, h, yp, cp):
+    """Next row 8f-1: pitched NV21 / NV12 and planar I420 / YV12 surfaces -> BGR with the reference's matrix."""
+    from test_oracle_vs_ref import make_yuv_surface
+    planar = fmt >= 2
+    y_pitch = yp or w
+    c_pitch = cp or (y_pitch // 2 if planar else y_pitch)
+    if not planar:
+        c_pitch = max(c_pitch, w)
+    b = 2
+    per = y_pitch * h + c_pitch * (h // 2) * (2 if planar else 1)
+    stride = per + 48
+    buf = u8(94, b * stride)
+    want = np.empty((b, h, w, 3), np.uint8)
+    for i in range(b):
+        surf, _ = make_yuv_surface(400 * i + w + fmt, fmt, w, h, y_pitch, c_pitch)
+        buf[i * stride:i * stride + per] = surf
+        want[i] = oracle.yuv_to_bgr(surf, fmt, w, h, y_pitch, c_pitch)
+    got = host(vacv.cvt_yuv2bgr(dev(buf), fmt, w, h, y_pitch=y_pitch, c_pitch=c_pitch, frame_stride=stride, batch=b))
+    assert_same(got, want)
+
+
 @pytest.mark.parametrize("half", [False, True])
 @pytest.mark.parametrize("fmt", [0, 1, 2, 3])
 @pytest.mark.parametrize("w,h,yp,cp,wo,ho,b", [(1920, 1080, 2048, 0, 640, 640, 2), (1920, 1080, 0, 0, 640, 640, 1),
