@@ -145,6 +145,90 @@ __global__ void __launch_bounds__(kTileX * kTileY) resize_linear_u8c3_kernel(con
 }
 
 // ----------------------------------------------------------------------------------------------------
+// a5 / a7 for single-channel u8 planes (CHW tensors are resized plane by plane, resize.cpp:73-87).  Same structure as the
+// 3-channel kernel: a warp owns 128 consecutive output pixels of a row (lane: pixels lane, lane+32, +64, +96 so that every
+// gather instruction reads neighbouring addresses), the two tap bytes of a row come from one aligned 32-bit word (two when
+// they straddle it), one IDP.2A forms L*cx0 + R*cx1, and the 128 output bytes leave as one lane-contiguous 32-bit store.
+constexpr int kC1Cols = 128;
+
+template <bool kSigned, bool kNeonRule, bool kLowRow>
+__device__ __forceinline__ void resize_linear_u8c1_rows(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, const ResizeGeom& g,
+                                                        const int* s_sx, const int* s_cx, const int* s_sy, const int* s_cy,
+                                                        uint32_t (*stage)[kC1Cols / 4]) {
+    const int dx0 = blockIdx.x * kC1Cols, dy00 = blockIdx.y * kC3Rows;
+    const int lane = threadIdx.x;
+    const int n = min(kC1Cols, g.wo - dx0);
+    unsigned sx[4]; uint32_t cx[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { sx[j] = (unsigned)s_sx[lane + 32 * j]; cx[j] = (uint32_t)s_cx[lane + 32 * j]; }
+    const uint8_t* img = src + blockIdx.z * g.src_image;   // every byte offset inside one plane fits 32 bits (host check)
+    uint8_t* sb = reinterpret_cast<uint8_t*>(stage[threadIdx.y]);
+    uint8_t* o = dst + blockIdx.z * g.dst_image + (size_t)(dy00 + threadIdx.y) * g.wo + dx0;
+    const size_t o_step = (size_t)kTileY * g.wo;
+    auto taps = [&](unsigned a) -> uint32_t {   // bytes a, a+1 of the plane in the low half-word
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(img + (a & ~3u));
+        const int r = (int)(a & 3u);
+        const uint32_t w0 = __ldg(wp), w1 = r == 3 ? __ldg(wp + 1) : 0u;
+        return __funnelshift_r(w0, w1, r * 8);
+    };
+    auto hsum = [&](uint32_t pair, uint32_t c) -> int {
+        return kSigned ? __dp2a_lo((int)c, (int)pair, 0) : (int)__dp2a_lo(c, pair, 0u);
+    };
+    for (int pass = 0; pass < kC3Rows / kTileY; ++pass, o += o_step) {
+        const int ry = pass * kTileY + threadIdx.y;
+        if (dy00 + ry >= g.ho) break;   // whole warp
+        const int cy0 = (short)(s_cy[ry] & 0xffff), cy1 = s_cy[ry] >> 16;
+        const unsigned row = (unsigned)s_sy[ry] * (unsigned)g.w;
+        uint32_t t[4], u[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {   // all loads first
+            t[j] = lane + 32 * j < n ? taps(row + sx[j]) : 0u;
+            u[j] = kLowRow && lane + 32 * j < n ? taps(row + (unsigned)g.w + sx[j]) : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int Ht = hsum(t[j], cx[j]), Hb = kLowRow ? hsum(u[j], cx[j]) : 0;
+            int v;
+            if (kNeonRule) {   // resize_neon.cpp:145-181
+                const int r0 = (short)(Ht >> 4), r1 = (short)(Hb >> 4);
+                v = clamp255(((short)((cy0 * r0) >> 16) + (short)((cy1 * r1) >> 16) + 2) >> 2);
+            } else {           // resize_naive.cpp:60-65, the same integer regrouped row-wise (no overflow: < 2^31)
+                v = (Ht * cy0 + Hb * cy1) >> 22;
+            }
+            sb[lane + 32 * j] = (uint8_t)v;
+        }
+        __syncwarp();
+        if ((reinterpret_cast<uintptr_t>(o) & 3) == 0 && n == kC1Cols) st_stream4(o + 4 * lane, stage[threadIdx.y][lane]);
+        else for (int bb = lane; bb < n; bb += 32) o[bb] = sb[bb];
+        __syncwarp();
+    }
+}
+
+template <bool kSigned, bool kNeonRule>
+__global__ void __launch_bounds__(kTileX * kTileY) resize_linear_u8c1_kernel(const uint8_t* __restrict__ src,
+                                                                              uint8_t* __restrict__ dst, ResizeGeom g) {
+    __shared__ int s_sx[kC1Cols], s_cx[kC1Cols], s_sy[kC3Rows], s_cy[kC3Rows];
+    __shared__ __align__(16) uint32_t stage[kTileY][kC1Cols / 4];
+    const int dx0 = blockIdx.x * kC1Cols, dy00 = blockIdx.y * kC3Rows;
+    const int t = threadIdx.y * kTileX + threadIdx.x;
+    if (t < kC1Cols + kC3Rows) {
+        const bool isx = t < kC1Cols;
+        const int d = isx ? dx0 + t : dy00 + (t - kC1Cols);
+        const int n_in = isx ? g.w : g.h, n_out = isx ? g.wo : g.ho;
+        const double scale = kNeonRule ? (double)n_in / (double)n_out : (double)((float)n_in / (float)n_out);
+        int s; float f;
+        linear_coord(min(d, n_out - 1), scale, n_in, s, f);
+        const int c0 = sat_short((1.f - f) * 2048.f), c1 = sat_short(f * 2048.f);
+        if (isx) { s_sx[t] = s; s_cx[t] = (c0 & 0xffff) | (c1 << 16); }
+        else { s_sy[t - kC1Cols] = s; s_cy[t - kC1Cols] = (c0 & 0xffff) | (c1 << 16); }
+    }
+    __syncthreads();
+    const int any_low = __any_sync(0xffffffffu, dy00 + (int)threadIdx.x < g.ho && (s_cy[threadIdx.x] >> 16) != 0);   // see the 3-channel kernel
+    if (any_low) resize_linear_u8c1_rows<kSigned, kNeonRule, true>(src, dst, g, s_sx, s_cx, s_sy, s_cy, stage);
+    else resize_linear_u8c1_rows<kSigned, kNeonRule, false>(src, dst, g, s_sx, s_cx, s_sy, s_cy, stage);
+}
+
+// ----------------------------------------------------------------------------------------------------
 // a6 bilinear fp32 (resize_naive.cpp:70-128)
 __global__ void __launch_bounds__(kTileX * kTileY) resize_linear_f32_kernel(const float* __restrict__ src,
                                                                              float* __restrict__ dst, ResizeGeom g) {
@@ -333,6 +417,13 @@ extern "C" int vacv_cuda_resize(const void* src, void* dst, int batch, int w, in
             if (flags & VACV_FLAG_NEON_RULE) resize_linear_u8c3_kernel<false, true><<<grid, block, 0, s>>>(sp, dp, g);
             else if (sc) resize_linear_u8c3_kernel<true, false><<<grid, block, 0, s>>>(sp, dp, g);
             else resize_linear_u8c3_kernel<false, false><<<grid, block, 0, s>>>(sp, dp, g);
+        } else if (!cubic && dtype == VACV_INT8 && g.c == 1 && (((size_t)w * h) % 4) == 0 && ((uintptr_t)src % 4) == 0 && (size_t)w * h < 0xfffffff0ull) {
+            const bool sc = flags & VACV_FLAG_SIGNED_CHAR;
+            grid.x = ceil_div(w_out, kC1Cols);
+            grid.y = ceil_div(h_out, kC3Rows);
+            if (flags & VACV_FLAG_NEON_RULE) resize_linear_u8c1_kernel<false, true><<<grid, block, 0, s>>>(sp, dp, g);
+            else if (sc) resize_linear_u8c1_kernel<true, false><<<grid, block, 0, s>>>(sp, dp, g);
+            else resize_linear_u8c1_kernel<false, false><<<grid, block, 0, s>>>(sp, dp, g);
         } else if (!cubic && dtype == VACV_INT8) {
             const bool sc = flags & VACV_FLAG_SIGNED_CHAR;
             if (flags & VACV_FLAG_NEON_RULE) resize_linear_u8_kernel<false, true><<<grid, block, 0, s>>>(sp, dp, g);

@@ -54,51 +54,51 @@ __global__ void __launch_bounds__(256) crop_rows_kernel(const uint8_t* __restric
 
 // =====================================================================================================
 // a3 layout_change (src/common/tensor.cpp:160-182): chw[k*wh + j] = hwc[j*c + k].
-// c == 3 fast path: a thread moves V = 16/sizeof(T) pixels: 48 contiguous bytes on the interleaved side
-// (three 128-bit accesses; neighbouring lanes complete each other's sectors) and one 128-bit access per plane.
-template <typename T>
-__device__ __forceinline__ void deinterleave3(const uint4 (&in)[3], uint4 (&out)[3]) {
+// c in {2, 3, 4} fast path: a thread moves V = 16/sizeof(T) pixels: 16*c contiguous bytes on the interleaved side
+// (c 128-bit accesses; neighbouring lanes complete each other's sectors) and one 128-bit access per plane.
+template <typename T, int C>
+__device__ __forceinline__ void deinterleave(const uint4 (&in)[C], uint4 (&out)[C]) {
     constexpr int V = 16 / sizeof(T);
     const T* a = reinterpret_cast<const T*>(in);
     T* o = reinterpret_cast<T*>(out);
 #pragma unroll
     for (int i = 0; i < V; ++i)
 #pragma unroll
-        for (int k = 0; k < 3; ++k) o[k * V + i] = a[3 * i + k];
+        for (int k = 0; k < C; ++k) o[k * V + i] = a[C * i + k];
 }
-template <typename T>
-__device__ __forceinline__ void interleave3(const uint4 (&in)[3], uint4 (&out)[3]) {
+template <typename T, int C>
+__device__ __forceinline__ void interleave(const uint4 (&in)[C], uint4 (&out)[C]) {
     constexpr int V = 16 / sizeof(T);
     const T* a = reinterpret_cast<const T*>(in);
     T* o = reinterpret_cast<T*>(out);
 #pragma unroll
     for (int i = 0; i < V; ++i)
 #pragma unroll
-        for (int k = 0; k < 3; ++k) o[3 * i + k] = a[k * V + i];
+        for (int k = 0; k < C; ++k) o[C * i + k] = a[k * V + i];
 }
 
 // groups = batch * wh / V ; wh % V == 0
-template <typename T, bool kToCHW>
-__global__ void __launch_bounds__(256) layout_c3_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst,
+template <typename T, int C, bool kToCHW>
+__global__ void __launch_bounds__(256) layout_cn_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst,
                                                          size_t groups, size_t groups_per_frame) {
     size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= groups) return;
     const size_t frame = g / groups_per_frame, j = g % groups_per_frame;
-    const size_t inter = frame * groups_per_frame * 3 + j * 3;      // uint4 index on the HWC side
-    const size_t planar = frame * groups_per_frame * 3 + j;         // uint4 index of plane 0 on the CHW side
-    uint4 a[3], b[3];
+    const size_t inter = frame * groups_per_frame * C + j * C;      // uint4 index on the HWC side
+    const size_t planar = frame * groups_per_frame * C + j;         // uint4 index of plane 0 on the CHW side
+    uint4 a[C], b[C];
     if (kToCHW) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) a[k] = __ldg(src + inter + k);
-        deinterleave3<T>(a, b);
+        for (int k = 0; k < C; ++k) a[k] = __ldg(src + inter + k);
+        deinterleave<T, C>(a, b);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) st_stream16(dst + planar + k * groups_per_frame, b[k]);
+        for (int k = 0; k < C; ++k) st_stream16(dst + planar + k * groups_per_frame, b[k]);
     } else {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) a[k] = ld_stream16(src + planar + k * groups_per_frame);
-        interleave3<T>(a, b);
+        for (int k = 0; k < C; ++k) a[k] = ld_stream16(src + planar + k * groups_per_frame);
+        interleave<T, C>(a, b);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) st_stream16(dst + inter + k, b[k]);
+        for (int k = 0; k < C; ++k) st_stream16(dst + inter + k, b[k]);
     }
 }
 
@@ -337,14 +337,21 @@ extern "C" int vacv_cuda_crop(const void* src, void* dst, int batch, int w, int 
     return check_launch("crop");
 }
 
+template <typename T, int C>
+static void launch_layout_cn(const void* src, void* dst, size_t groups, size_t gpf, bool to_chw, cudaStream_t s) {
+    if (to_chw) layout_cn_kernel<T, C, true><<<ceil_div(groups, 256), 256, 0, s>>>((const uint4*)src, (uint4*)dst, groups, gpf);
+    else layout_cn_kernel<T, C, false><<<ceil_div(groups, 256), 256, 0, s>>>((const uint4*)src, (uint4*)dst, groups, gpf);
+}
+
 template <typename T>
 static void launch_layout(const void* src, void* dst, int batch, int wh, int c, bool to_chw, cudaStream_t s) {
     constexpr int V = 16 / sizeof(T);
-    const bool vec = c == 3 && (wh % V) == 0 && (((uintptr_t)src | (uintptr_t)dst) & 15) == 0;
+    const bool vec = c >= 2 && c <= 4 && (wh % V) == 0 && (((uintptr_t)src | (uintptr_t)dst) & 15) == 0;
     if (vec) {
         const size_t gpf = wh / V, groups = gpf * batch;
-        if (to_chw) layout_c3_kernel<T, true><<<ceil_div(groups, 256), 256, 0, s>>>((const uint4*)src, (uint4*)dst, groups, gpf);
-        else layout_c3_kernel<T, false><<<ceil_div(groups, 256), 256, 0, s>>>((const uint4*)src, (uint4*)dst, groups, gpf);
+        if (c == 2) launch_layout_cn<T, 2>(src, dst, groups, gpf, to_chw, s);
+        else if (c == 3) launch_layout_cn<T, 3>(src, dst, groups, gpf, to_chw, s);
+        else launch_layout_cn<T, 4>(src, dst, groups, gpf, to_chw, s);
     } else {
         const size_t total = (size_t)batch * wh * c;
         if (to_chw) layout_generic_kernel<T, true><<<ceil_div(total, 256), 256, 0, s>>>((const T*)src, (T*)dst, wh, c, total);

@@ -114,7 +114,8 @@ def test_crop_rejects_out_of_frame(vacv):
 
 # ------------------------------------------------------------------ a3 / a4 layout, dtype
 @pytest.mark.parametrize("dt", ["u8", "f32"])
-@pytest.mark.parametrize("w,h,c", [(176, 144, 3), (1920, 1080, 3), (33, 7, 3), (33, 7, 4), (5, 3, 2), (64, 64, 1)])
+@pytest.mark.parametrize("w,h,c", [(176, 144, 3), (1920, 1080, 3), (33, 7, 3), (33, 7, 4), (5, 3, 2), (64, 64, 1), (640, 360, 4),
+                                   (640, 360, 2), (64, 48, 5)])
 def test_layout_roundtrip(vacv, oracle, dt, w, h, c):
     b = 2
     src = u8(3, b, h, w, c) if dt == "u8" else f32(3, b, h, w, c)
@@ -177,6 +178,18 @@ def test_resize_linear_u8_flags(vacv, oracle, path):
     chw = np.ascontiguousarray(src.transpose(0, 3, 1, 2))
     got = host(vacv.resize(dev(chw), NCHW, wo, ho, vacv.INTER_LINEAR, vacv.FLAG_NEON_RULE | path))[0]
     assert_same(got, oracle.resize_linear_neon_rule(chw[0], w, h, c, NCHW, wo, ho))
+
+
+@pytest.mark.parametrize("sz", [((64, 48), (200, 111)), ((640, 360), (213, 120)), ((320, 240), (300, 97))])
+def test_resize_linear_u8_planar_flags(vacv, oracle, sz):
+    """CHW planes (c = 1 per call, resize.cpp:73-87) through the word-granular single-channel kernel, all three rules."""
+    (w, h), (wo, ho) = sz
+    chw = u8(12, 1, 3, h, w)
+    for flag, want in [(0, oracle.resize_linear(chw[0], w, h, 3, NCHW, wo, ho)),
+                       (vacv.FLAG_SIGNED_CHAR, oracle.resize_linear(chw[0], w, h, 3, NCHW, wo, ho, signed_char=1)),
+                       (vacv.FLAG_NEON_RULE, oracle.resize_linear_neon_rule(chw[0], w, h, 3, NCHW, wo, ho))]:
+        got = host(vacv.resize(dev(chw), NCHW, wo, ho, vacv.INTER_LINEAR, flag | 0x100))[0]
+        assert_same(got, want)
 
 
 @pytest.mark.parametrize("path", PATHS)
