@@ -10,24 +10,35 @@
 
 namespace vacv {
 
-__device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d) {
-    return (uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)c << 16) | ((uint32_t)d << 24);
+// Packed chroma terms of one 2x1 pixel pair: each 32-bit word holds the same 16-bit term twice, so that one DPX
+// VIADDMNMX.S16x2.RELU adds it to two luma samples and clamps both to [0, 255] (cvt_color.cpp:76-100).
+struct ChromaTerms2 { uint32_t ra2, nga2, ba2; };
+__device__ __forceinline__ ChromaTerms2 chroma_terms2(int v, int u) {
+    const ChromaTerms t = chroma_terms(v, u);
+    ChromaTerms2 p;
+    p.ra2 = __byte_perm((uint32_t)t.ra, 0u, 0x1010);
+    p.nga2 = __byte_perm((uint32_t)(-t.ga), 0u, 0x1010);
+    p.ba2 = __byte_perm((uint32_t)t.ba, 0u, 0x1010);
+    return p;
 }
 
-// 16 pixels of one row: y = 16 luma bytes, terms for the 8 chroma pairs -> 12 output words (48 bytes of BGR)
-__device__ __forceinline__ void convert16(const uint4& y, const ChromaTerms (&t)[8], uint32_t (&out)[12]) {
+// 16 pixels of one row: y = 16 luma bytes, terms for the 8 chroma pairs -> 12 output words (48 bytes of BGR).
+// Per pixel pair: 1 PRMT (two luma bytes -> two 16-bit lanes), 3 packed add-clamps, then PRMT byte shuffles into BGR order.
+__device__ __forceinline__ void convert16(const uint4& y, const ChromaTerms2 (&t)[8], uint32_t (&out)[12]) {
     const uint32_t yw[4] = {y.x, y.y, y.z, y.w};
-    uint8_t px[48];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        int Y = (yw[i >> 2] >> (8 * (i & 3))) & 0xff;
-        const ChromaTerms& c = t[i >> 1];
-        px[3 * i + 0] = (uint8_t)add_clamp255(Y, c.ba);
-        px[3 * i + 1] = (uint8_t)add_clamp255(Y, -c.ga);
-        px[3 * i + 2] = (uint8_t)add_clamp255(Y, c.ra);
+    for (int q = 0; q < 4; ++q) {   // 4 pixels = pairs 2q, 2q+1 = luma word q -> 3 output words
+        const uint32_t ya = __byte_perm(yw[q], 0u, 0x4140), yb = __byte_perm(yw[q], 0u, 0x4342);   // [y0 0 y1 0], [y2 0 y3 0]
+        const ChromaTerms2 &ta = t[2 * q], &tb = t[2 * q + 1];
+        const uint32_t Ba = __viaddmin_s16x2_relu(ya, ta.ba2, 0x00ff00ffu), Ga = __viaddmin_s16x2_relu(ya, ta.nga2, 0x00ff00ffu),
+                       Ra = __viaddmin_s16x2_relu(ya, ta.ra2, 0x00ff00ffu);
+        const uint32_t Bb = __viaddmin_s16x2_relu(yb, tb.ba2, 0x00ff00ffu), Gb = __viaddmin_s16x2_relu(yb, tb.nga2, 0x00ff00ffu),
+                       Rb = __viaddmin_s16x2_relu(yb, tb.ra2, 0x00ff00ffu);
+        const uint32_t xa = __byte_perm(Ba, Ga, 0x6240), xb = __byte_perm(Bb, Gb, 0x6240);   // [b0 g0 b1 g1], [b2 g2 b3 g3]
+        out[3 * q + 0] = __byte_perm(xa, Ra, 0x2410);                                          // b0 g0 r0 b1
+        out[3 * q + 1] = __byte_perm(__byte_perm(xa, Ra, 0x0063), xb, 0x5410);                 // g1 r1 b2 g2
+        out[3 * q + 2] = __byte_perm(xb, Rb, 0x6324);                                          // r2 b3 g3 r3
     }
-#pragma unroll
-    for (int j = 0; j < 12; ++j) out[j] = pack4(px[4 * j], px[4 * j + 1], px[4 * j + 2], px[4 * j + 3]);
 }
 
 constexpr int kCvtThreads = 128;
@@ -59,13 +70,13 @@ __global__ void __launch_bounds__(kCvtThreads) yuv2bgr_strip16_kernel(const uint
     if (active) {
         const uint4 y0 = ld_stream16(y0p + 16 * strip);
         const uint4 y1 = ld_stream16(y0p + g.y_pitch + 16 * strip);
-        ChromaTerms t[8];
+        ChromaTerms2 t[8];
         if (FMT == kCvtPlanar) {
             const uint2 u8 = __ldg(reinterpret_cast<const uint2*>(f + g.c_off + (size_t)pair * g.c_pitch + 8 * strip));
             const uint2 v8 = __ldg(reinterpret_cast<const uint2*>(f + g.c2_off + (size_t)pair * g.c_pitch + 8 * strip));
             const uint32_t uw[2] = {u8.x, u8.y}, vw[2] = {v8.x, v8.y};
 #pragma unroll
-            for (int i = 0; i < 8; ++i) t[i] = chroma_terms((vw[i >> 2] >> (8 * (i & 3))) & 0xff, (uw[i >> 2] >> (8 * (i & 3))) & 0xff);
+            for (int i = 0; i < 8; ++i) t[i] = chroma_terms2((vw[i >> 2] >> (8 * (i & 3))) & 0xff, (uw[i >> 2] >> (8 * (i & 3))) & 0xff);
         } else {
             const uint4 vu = ld_stream16(f + g.c_off + (size_t)pair * g.c_pitch + 16 * strip);
             const uint32_t cw[4] = {vu.x, vu.y, vu.z, vu.w};
@@ -73,7 +84,7 @@ __global__ void __launch_bounds__(kCvtThreads) yuv2bgr_strip16_kernel(const uint
             for (int i = 0; i < 8; ++i) {
                 uint32_t pr = (cw[i >> 1] >> (16 * (i & 1))) & 0xffff;
                 int c0 = pr & 0xff, c1 = pr >> 8;
-                t[i] = FMT == kCvtVU ? chroma_terms(c0, c1) : chroma_terms(c1, c0);
+                t[i] = FMT == kCvtVU ? chroma_terms2(c0, c1) : chroma_terms2(c1, c0);
             }
         }
         uint32_t o[12];
