@@ -187,6 +187,113 @@ __device__ __forceinline__ void compute_tile(uint32_t ybuf, uint32_t cbuf, uint3
     }
 }
 
+// Packed variant for an even number of columns per thread: columns are handled in PAIRS on 16-bit lanes.
+//   * add + clamp of a luma sample and a chroma term for two columns = one DPX VIADDMNMX.S16x2.RELU (was two VIADDMNMX),
+//   * the horizontal blend pa*cx0 + pb*cx1 = one IDP.2A on the byte pair (pa, pb) and the packed 16-bit weights (was two
+//     IMAD); when no right tap has weight, cx0 is exactly 2048 and the blend disappears: the clamped bytes themselves
+//     are carried and the vertical blend (p0*cy0 + p1*cy1) >> 11 -- the same integer as ((p0*2048)*cy0 + (p1*2048)*cy1)
+//     >> 22 -- is again one IDP.2A per value, with the row table's packed (cy0, cy1) entry as is.
+template <int FMT, typename OutT, bool kRightTap, int NCOL>
+__device__ __forceinline__ void compute_tile_packed(uint32_t ybuf, uint32_t cbuf, uint32_t tab_sy, uint32_t tab_cy, uint32_t lut,
+                                                    const ColState (&col)[NCOL], int dy0, int th, int y_pitch, int c_pitch, int vstage_off,
+                                                    char* (&out)[NCOL], size_t row_bytes, size_t plane_bytes) {
+    constexpr int P = NCOL >= 2 ? NCOL / 2 : 1;   // (instantiated but never called for odd NCOL)
+    constexpr int kCols = OutOps<OutT>::kCols;
+    const int y_first = lds_s32(tab_sy + 4 * dy0), c_first = y_first >> 1;
+    // row state: kRightTap: horizontally blended sums per column; else: clamped bytes of a column pair [p_j 0 p_j+1 0] per channel
+    int H0[kRightTap ? NCOL : 1][3], H1[kRightTap ? NCOL : 1][3];
+    uint32_t R0[kRightTap ? 1 : P][3], R1[kRightTap ? 1 : P][3];
+    uint32_t ta2[P][3], tb2[kRightTap ? P : 1][3];   // chroma terms (ba, -ga, ra) of the pair's two columns, one per 16-bit lane
+    uint32_t cxp[kRightTap ? NCOL : 1];
+    if (kRightTap) {
+#pragma unroll
+        for (int j = 0; j < NCOL; ++j) cxp[j] = (uint32_t)col[j].cx0 | ((uint32_t)col[j].cx1 << 16);
+    }
+    int have = -2, have_c = -1;
+    auto pack_terms = [](const ChromaTerms& a, const ChromaTerms& b, uint32_t (&t)[3]) {
+        t[0] = __byte_perm((uint32_t)a.ba, (uint32_t)b.ba, 0x5410);
+        t[1] = __byte_perm((uint32_t)(-a.ga), (uint32_t)(-b.ga), 0x5410);
+        t[2] = __byte_perm((uint32_t)a.ra, (uint32_t)b.ra, 0x5410);
+    };
+    auto row = [&](int r, int (&H)[kRightTap ? NCOL : 1][3], uint32_t (&R)[kRightTap ? 1 : P][3]) {
+        const int cr = r >> 1;
+        if (cr != have_c) {   // all threads walk the same rows: no divergence
+            const uint32_t crow = cbuf + (cr - c_first) * c_pitch;
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                pack_terms(terms_at<FMT>(crow + col[2 * p].ca, vstage_off), terms_at<FMT>(crow + col[2 * p + 1].ca, vstage_off), ta2[p]);
+                if (kRightTap) pack_terms(terms_at<FMT>(crow + col[2 * p].cb, vstage_off), terms_at<FMT>(crow + col[2 * p + 1].cb, vstage_off), tb2[p]);
+            }
+            have_c = cr;
+        }
+        const uint32_t yrow = ybuf + (r - y_first) * y_pitch;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const uint32_t ya = (uint32_t)lds_u8(yrow + col[2 * p].yo) | ((uint32_t)lds_u8(yrow + col[2 * p + 1].yo) << 16);
+            if (kRightTap) {
+                const uint32_t yb = (uint32_t)lds_u8(yrow + col[2 * p].yo + 1) | ((uint32_t)lds_u8(yrow + col[2 * p + 1].yo + 1) << 16);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const uint32_t a = __viaddmin_s16x2_relu(ya, ta2[p][k], 0x00ff00ffu), b = __viaddmin_s16x2_relu(yb, tb2[p][k], 0x00ff00ffu);
+                    const uint32_t m = __byte_perm(a, b, 0x6240);   // [pa_j pb_j pa_j+1 pb_j+1]
+                    H[2 * p][k] = (int)__dp2a_lo(cxp[2 * p], m, 0u);
+                    H[2 * p + 1][k] = (int)__dp2a_hi(cxp[2 * p + 1], m, 0u);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) R[p][k] = __viaddmin_s16x2_relu(ya, ta2[p][k], 0x00ff00ffu);
+            }
+        }
+    };
+    for (int ty = 0; ty < th; ++ty) {
+        const int sy = lds_s32(tab_sy + 4 * (dy0 + ty));
+        const uint32_t cy = (uint32_t)lds_s32(tab_cy + 4 * (dy0 + ty));   // cy0 | cy1 << 16, both in [0, 2048]
+        const int cy0 = cy & 0xffff, cy1 = cy >> 16;
+        if (sy == have) {
+            if (kRightTap) {
+#pragma unroll
+                for (int j = 0; j < NCOL; ++j) { H0[j][0] = H1[j][0]; H0[j][1] = H1[j][1]; H0[j][2] = H1[j][2]; }
+            } else {
+#pragma unroll
+                for (int p = 0; p < P; ++p) { R0[p][0] = R1[p][0]; R0[p][1] = R1[p][1]; R0[p][2] = R1[p][2]; }
+            }
+        } else if (sy + 1 != have) {
+            row(sy, H0, R0);
+        }
+        if (sy + 1 != have) {
+            row(sy + 1, H1, R1);
+            have = sy + 1;
+        }
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            char* o0 = out[2 * p];
+            char* o1 = out[2 * p + 1];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                unsigned v0, v1;   // the u8 the unfused chain stores
+                if (kRightTap) {
+                    v0 = (unsigned)(H0[2 * p][k] * cy0 + H1[2 * p][k] * cy1) >> 22;
+                    v1 = (unsigned)(H0[2 * p + 1][k] * cy0 + H1[2 * p + 1][k] * cy1) >> 22;
+                } else {
+                    const uint32_t m = __byte_perm(R0[p][k], R1[p][k], 0x6240);   // [p0_j p1_j p0_j+1 p1_j+1]
+                    v0 = __dp2a_lo(cy, m, 0u) >> 11;
+                    v1 = __dp2a_hi(cy, m, 0u) >> 11;
+                }
+                if (kCols == 2) {
+                    OutOps<OutT>::copy(o0, lut, k, v0, v1);
+                } else {
+                    OutOps<OutT>::copy(o0, lut, k, v0, 0u);
+                    OutOps<OutT>::copy(o1, lut, k, v1, 0u);
+                    o1 += plane_bytes;
+                }
+                o0 += plane_bytes;
+            }
+            out[2 * p] += row_bytes;
+            if (kCols != 2) out[2 * p + 1] += row_bytes;
+        }
+    }
+}
+
 // kDense: the reference's own layout (tensor.cpp:524: no pitch; chroma right after luma) -- one pitch register, constants folded.
 template <int FMT, typename OutT, int NCOL, bool kDense>
 __global__ void __launch_bounds__(NCOL == 1 ? 640 : kPipeThreads, NCOL <= 2 ? 2 : 1)
@@ -280,8 +387,15 @@ nv_resize_normalize_chw_pipe_kernel(const uint8_t* __restrict__ src, OutT* __res
                                   : reinterpret_cast<char*>(reinterpret_cast<typename Ops::Lut*>(dst) + ((size_t)frame * 3 * g.canvas_h + g.y0 + dy0) * g.canvas_w + g.x0);
 #pragma unroll
         for (int j = 0; j < NCOL; ++j) out[j] = row0 + (int)Ops::kElem * colx[j];
-        if (right) compute_tile<FMT, OutT, true, NCOL>(ybuf, cbuf, sy_s, cy_s, lut_s, col, dy0, th, y_pitch, c_pitch, g.vstage_off, out, row_bytes, plane_bytes);
-        else compute_tile<FMT, OutT, false, NCOL>(ybuf, cbuf, sy_s, cy_s, lut_s, col, dy0, th, y_pitch, c_pitch, g.vstage_off, out, row_bytes, plane_bytes);
+        // measured on B200 (bench_ops.py c2 / c2g / c2s): the packed variant wins for 16-bit outputs (issue-bound: 0.312 -> 0.282 ms)
+        // and loses for fp32 (0.367 -> 0.384 ms: it moves the blend from the FMA pipe's IMADs onto the already busier ALU pipe)
+        if (NCOL % 2 == 0 && sizeof(typename Ops::Lut) == 2) {
+            if (right) compute_tile_packed<FMT, OutT, true, NCOL>(ybuf, cbuf, sy_s, cy_s, lut_s, col, dy0, th, y_pitch, c_pitch, g.vstage_off, out, row_bytes, plane_bytes);
+            else compute_tile_packed<FMT, OutT, false, NCOL>(ybuf, cbuf, sy_s, cy_s, lut_s, col, dy0, th, y_pitch, c_pitch, g.vstage_off, out, row_bytes, plane_bytes);
+        } else {
+            if (right) compute_tile<FMT, OutT, true, NCOL>(ybuf, cbuf, sy_s, cy_s, lut_s, col, dy0, th, y_pitch, c_pitch, g.vstage_off, out, row_bytes, plane_bytes);
+            else compute_tile<FMT, OutT, false, NCOL>(ybuf, cbuf, sy_s, cy_s, lut_s, col, dy0, th, y_pitch, c_pitch, g.vstage_off, out, row_bytes, plane_bytes);
+        }
         __syncthreads();   // all reads of stage b done -> it may be refilled by the next iteration's issue
     }
 }
