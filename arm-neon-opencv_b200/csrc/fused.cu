@@ -18,6 +18,7 @@
 // Stores: lanes = consecutive columns -> 128 B per warp per plane, streaming.
 #include "vacv_common.cuh"
 #include "fused_pipeline.cuh"
+#include "gather_u8c3.cuh"
 #include <cmath>
 #include <type_traits>
 #include <cstdlib>
@@ -208,6 +209,87 @@ __global__ void __launch_bounds__(256) resize_normalize_kernel(const uint8_t* __
             else st_stream4f(out + k * plane + i, r);
         }
     }
+}
+
+// 3-channel fast path of resize_normalize: the structure of resize_linear_u8c3_kernel (resize.cu) -- a warp owns 32
+// consecutive output pixels of a row, tap bytes come as aligned 32-bit words + funnel shifts, PRMT + IDP.2A form the
+// horizontal sums -- followed by the exact normalisation table.  CHW: one lane-contiguous 128-byte store per plane;
+// HWC: the warp's 96 floats are re-chunked through shared memory into three lane-contiguous 128-byte stores.
+constexpr int kRnRows = 32;   // output rows per CTA (4 passes of 8 rows)
+
+template <bool kCHW, bool kLowRow>
+__device__ __forceinline__ void resize_normalize_u8c3_rows(const uint8_t* __restrict__ src, float* __restrict__ dst, int w, int wo, int ho,
+                                                           const int* s_sx, const int* s_cx, const int* s_sy, const int* s_cy,
+                                                           const float* lut, float (*stage)[96]) {
+    const int dx0 = blockIdx.x * 32, dy00 = blockIdx.y * kRnRows;
+    const int lane = threadIdx.x;
+    const int n = min(32, wo - dx0);
+    const unsigned sx3 = (unsigned)s_sx[lane] * 3u;
+    const uint32_t cx = (uint32_t)s_cx[lane];   // cx0 | cx1 << 16
+    const unsigned row3 = (unsigned)w * 3u;
+    const size_t plane = (size_t)wo * ho;
+    float* out = dst + (size_t)blockIdx.z * plane * 3;
+    for (int pass = 0; pass < kRnRows / 8; ++pass) {
+        const int ry = pass * 8 + threadIdx.y, dy = dy00 + ry;
+        if (dy >= ho) break;   // whole warp
+        const int cy0 = (short)(s_cy[ry] & 0xffff), cy1 = s_cy[ry] >> 16;
+        float r[3] = {0.f, 0.f, 0.f};
+        if (lane < n) {
+            const unsigned a = (unsigned)s_sy[ry] * row3 + sx3;
+            uint32_t t0, t1, u0, u1;
+            linear_taps_u8c3(src, a, t0, t1);
+            if (kLowRow) linear_taps_u8c3(src, a + row3, u0, u1);
+            int Ht[3], Hb[3] = {0, 0, 0};
+            hsum_u8c3<false>(t0, t1, cx, Ht);                 // p00*cx0 + p01*cx1
+            if (kLowRow) hsum_u8c3<false>(u0, u1, cx, Hb);    // p10*cx0 + p11*cx1
+#pragma unroll
+            for (int k = 0; k < 3; ++k) r[k] = lut[k * 256 + (((Ht[k] * cy0 + Hb[k] * cy1) >> 22) & 0xff)];   // resize_naive.cpp:60-65
+        }
+        if (kCHW) {
+            if (lane < n) {
+                const size_t o = (size_t)dy * wo + dx0 + lane;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) st_stream4f(out + k * plane + o, r[k]);
+            }
+        } else {
+            float* sb = stage[threadIdx.y];
+            sb[3 * lane] = r[0]; sb[3 * lane + 1] = r[1]; sb[3 * lane + 2] = r[2];
+            __syncwarp();
+            float* o = out + ((size_t)dy * wo + dx0) * 3;
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                if (lane + 32 * k < 3 * n) st_stream4f(o + lane + 32 * k, sb[lane + 32 * k]);
+            __syncwarp();
+        }
+    }
+}
+
+template <bool kCHW>
+__global__ void __launch_bounds__(256) resize_normalize_u8c3_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, int w, int h,
+                                                                     int wo, int ho, size_t src_image, const float* __restrict__ mean,
+                                                                     const float* __restrict__ stddev) {
+    __shared__ int s_sx[32], s_cx[32], s_sy[kRnRows], s_cy[kRnRows];
+    __shared__ float lut[768];
+    __shared__ __align__(16) float stage[8][96];
+    const int dx0 = blockIdx.x * 32, dy00 = blockIdx.y * kRnRows;
+    const int t = threadIdx.y * 32 + threadIdx.x;
+    if (t < 32 + kRnRows) {
+        const bool isx = t < 32;
+        const int d = isx ? dx0 + t : dy00 + (t - 32);
+        const int n_in = isx ? w : h, n_out = isx ? wo : ho;
+        int s; float f;
+        linear_coord(min(d, n_out - 1), (double)((float)n_in / (float)n_out), n_in, s, f);
+        const int c0 = sat_short((1.f - f) * 2048.f), c1 = sat_short(f * 2048.f);
+        if (isx) { s_sx[t] = s; s_cx[t] = (c0 & 0xffff) | (c1 << 16); }
+        else { s_sy[t - 32] = s; s_cy[t - 32] = (c0 & 0xffff) | (c1 << 16); }
+    }
+    for (int i = t; i < 768; i += 256)
+        lut[i] = normalize_one((float)(i & 255), __ldg(mean + (i >> 8)), (double)__ldg(stddev + (i >> 8)) + 1e-6);
+    __syncthreads();
+    const uint8_t* img = src + blockIdx.z * src_image;
+    const int any_low = __any_sync(0xffffffffu, dy00 + (int)threadIdx.x < ho && (s_cy[threadIdx.x] >> 16) != 0);   // see resize_linear_u8c3_kernel
+    if (any_low) resize_normalize_u8c3_rows<kCHW, true>(img, dst, w, wo, ho, s_sx, s_cx, s_sy, s_cy, lut, stage);
+    else resize_normalize_u8c3_rows<kCHW, false>(img, dst, w, wo, ho, s_sx, s_cx, s_sy, s_cy, lut, stage);
 }
 
 }  // namespace vacv
@@ -422,7 +504,12 @@ extern "C" int vacv_cuda_resize_normalize(const uint8_t* src, float* dst, int ba
     const int rows_per_cta = max(1, min(h_out, (8192 + w_out - 1) / w_out));
     dim3 grid(ceil_div(h_out, rows_per_cta), batch);
     cudaStream_t s = as_stream(stream);
-    if (c == 3) resize_normalize_kernel<3><<<grid, 256, 0, s>>>(src, dst, w, h, w_out, h_out, rows_per_cta, mean, stddev, out_layout);
+    const bool words = c == 3 && (((size_t)w * h * 3) % 4) == 0 && ((uintptr_t)src % 4) == 0 && (size_t)w * h * 3 < 0xfffffff0ull;
+    if (words) {   // word-granular taps
+        dim3 g3(ceil_div(w_out, 32), ceil_div(h_out, kRnRows), batch), b3(32, 8);
+        if (out_layout == VACV_NCHW) resize_normalize_u8c3_kernel<true><<<g3, b3, 0, s>>>(src, dst, w, h, w_out, h_out, (size_t)w * h * 3, mean, stddev);
+        else resize_normalize_u8c3_kernel<false><<<g3, b3, 0, s>>>(src, dst, w, h, w_out, h_out, (size_t)w * h * 3, mean, stddev);
+    } else if (c == 3) resize_normalize_kernel<3><<<grid, 256, 0, s>>>(src, dst, w, h, w_out, h_out, rows_per_cta, mean, stddev, out_layout);
     else resize_normalize_kernel<1><<<grid, 256, 0, s>>>(src, dst, w, h, w_out, h_out, rows_per_cta, mean, stddev, out_layout);
     return check_launch("resize_normalize");
 }

@@ -47,7 +47,7 @@ def measured_peak():
 
 def ncu_traffic_bytes():
     """DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture (profiles/)."""
-    path = os.path.join(ROOT, "profiles", "r1_fused_v2_ncu_raw.txt")
+    path = os.path.join(ROOT, "profiles", "r1_fused_v3_ncu_raw.txt")
     scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     try:
         total = 0.0
@@ -270,7 +270,7 @@ def run_ours(args, rank, world, local_rank):
                    "timing": "CUDA events on the launching stream, max over ranks"},
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": ncu_traffic_bytes(),
-                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r1_fused_v2_ncu_raw.txt",
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r1_fused_v3_ncu_raw.txt",
                      "peak_source": peak_src,
                      "kernel": "nv_resize_normalize_chw_pipe_kernel", "algorithmic_bytes_per_launch": BATCH * ALGO_BYTES_PER_FRAME,
                      "avg_launch_ms": round(own_ms, 4)},

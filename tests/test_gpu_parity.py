@@ -561,8 +561,9 @@ def test_fused_pipeline_vs_reference_chain(vacv):
 
 
 @pytest.mark.parametrize("out_layout", [NHWC, NCHW])
-def test_resize_normalize_fused(vacv, oracle, out_layout):
-    w, h, c, wo, ho, b = 640, 360, 3, 224, 200, 2
+@pytest.mark.parametrize("w,h,wo,ho", [(640, 360, 224, 200), (1920, 1080, 640, 360), (333, 211, 500, 300), (64, 48, 37, 45)])
+def test_resize_normalize_fused(vacv, oracle, out_layout, w, h, wo, ho):
+    c, b = 3, 2
     src = u8(22, b, h, w, c)
     got = host(vacv.resize_normalize(dev(src), wo, ho, dev(MEAN), dev(STD), out_layout))
     for i in range(b):
