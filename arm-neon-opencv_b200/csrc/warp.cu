@@ -36,6 +36,27 @@ __device__ __forceinline__ Taps warp_taps(const float* __restrict__ m, int dx, i
     return t;
 }
 
+// Same values with the saturating casts resolved: fy - floor(fy) lies in [0, 1], so (1 - fy) * 2048 lies in [0, 2048]:
+// SATURATE_CAST_SHORT (macro.h:25-30) reduces to trunc(x + 0.5f) and never clamps, and the cast of the integer 2048 - c0
+// returns it unchanged.
+__device__ __forceinline__ Taps warp_taps_fast(const float (&m)[6], int dx, int dy, int w, int h) {
+    Taps t;
+    float fx = m[0] * (float)dx + m[1] * (float)dy + m[2];
+    float fy = m[3] * (float)dx + m[4] * (float)dy + m[5];
+    const float flx = floorf(fx), fly = floorf(fy);
+    const int sy = (int)fly, sx = (int)flx;
+    fy -= fly;
+    fx -= flx;
+    t.in = !(sy < 0 || sy >= h - 1 || sx < 0 || sx >= w - 1);
+    t.cy0 = (int)((1.f - fy) * 2048.f + 0.5f);
+    t.cy1 = 2048 - t.cy0;
+    t.cx0 = (int)((1.f - fx) * 2048.f + 0.5f);
+    t.cx1 = 2048 - t.cx0;
+    t.fx = fx; t.fy = fy;
+    t.ofs = sy * w + sx;
+    return t;
+}
+
 template <bool kSigned>
 __device__ __forceinline__ int warp_u8(const uint8_t* __restrict__ lt, int row, int c, const Taps& t) {
     const int p00 = pix<kSigned>(__ldg(lt)), p01 = pix<kSigned>(__ldg(lt + c));
@@ -144,12 +165,16 @@ __global__ void __launch_bounds__(256) warp_affine_u8c3_kernel(const uint8_t* __
     const int i_begin = blockIdx.y * rows_per_cta * g.wo, i_end = min((blockIdx.y + 1) * rows_per_cta, g.ho) * g.wo;
     const size_t crop_px = (size_t)g.wo * g.ho;
     const int row = g.w * 3;
-    for (int i0 = i_begin + warp * 32; i0 < i_end; i0 += 256) {   // warp-uniform loop
+    const float mr[6] = {m[0], m[1], m[2], m[3], m[4], m[5]};
+    // (dx, dy) of this lane's pixel, advanced by 256 pixels per iteration without a division
+    const int step_y = 256 / g.wo, step_x = 256 - step_y * g.wo;
+    int dy = (i_begin + warp * 32 + lane) / g.wo, dx = (i_begin + warp * 32 + lane) - dy * g.wo;
+    for (int i0 = i_begin + warp * 32; i0 < i_end; i0 += 256, dx += step_x, dy += step_y) {   // warp-uniform loop
         const int i = i0 + lane;
+        if (dx >= g.wo) { dx -= g.wo; ++dy; }
         int v[3] = {0, 0, 0};
         if (i < i_end) {
-            const int dy = i / g.wo, dx = i - dy * g.wo;
-            const Taps t = warp_taps(m, dx, dy, g.w, g.h);
+            const Taps t = warp_taps_fast(mr, dx, dy, g.w, g.h);
             if (t.in) {
                 uint32_t t0, t1, u0, u1;
                 linear_taps_u8c3(img, (unsigned)t.ofs * 3u, t0, t1);
