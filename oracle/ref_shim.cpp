@@ -24,6 +24,7 @@
 #include "cv/cuda_device.h"
 #include "cv/normalize_naive.h"
 #include "cv/resize_naive.h"
+#include "cv/resize_neon.h"
 #include "util/image_util.h"
 
 using vision::DLayout;
@@ -90,6 +91,18 @@ void ref_resize(const void* src, int w, int h, int c, int dtype, int layout,
     Tensor s = wrap(src, w, h, c, dtype, layout);
     Tensor d = wrap(dst, w_out, h_out, c, dtype, layout);
     va_cv::resize(s, d, va_cv::VSize(w_out, h_out), 0, 0, interpolation);
+}
+
+// The reference's NEON bilinear path, glue of Resize::resize_neon (resize.cpp:132-146) restated here because that
+// function only exists in aarch64 builds; the kernels themselves are the reference's resize_neon.cpp compiled against
+// oracle/neon_emul/arm_neon.h.  NHWC: 3 channels, called with tripled widths exactly like the glue; NCHW: 3 planes.
+void ref_resize_neon(const uint8_t* src, int w, int h, int layout, uint8_t* dst, int w_out, int h_out) {
+    if (layout == vision::NHWC) {
+        va_cv::ResizeNeon::resize_neon_inter_linear_three_channel(src, w * 3, h, dst, w_out * 3, h_out);
+    } else {
+        for (int i = 0; i < 3; i++)
+            va_cv::ResizeNeon::resize_neon_inter_linear_one_channel(src + (size_t)w * h * i, w, h, dst + (size_t)w_out * h_out * i, w_out, h_out);
+    }
 }
 
 // The reference's own cubic building blocks (resize_naive.cpp:143-529) driven with *non-aliased*

@@ -52,7 +52,8 @@ void orc_resize_linear_u8(const uint8_t* src, int w, int h, int c, int layout,
 void orc_resize_linear_f32(const float* src, int w, int h, int c, int layout,
                            float* dst, int w_out, int h_out);
 
-/* resize_neon.cpp:12-347 (scalar restatement of the NEON rule; aarch64 hosts only in the reference). */
+/* resize_neon.cpp:12-347 (scalar restatement of the NEON rule; aarch64 hosts only in the reference -- pinned against that
+ * source compiled over oracle/neon_emul/arm_neon.h, tests/test_oracle_vs_ref.py). */
 void orc_resize_linear_u8_neon_rule(const uint8_t* src, int w, int h, int c, int layout,
                                     uint8_t* dst, int w_out, int h_out);
 

@@ -292,6 +292,16 @@ class Ref:
                             _i(interpolation))
         return dst
 
+    def resize_neon(self, src, w, h, layout, wo, ho):
+        """The reference's NEON bilinear source (resize_neon.cpp) executed through oracle/neon_emul; 3 channels."""
+        src = _c(src, np.uint8)
+        pad = 8   # NHWC upscales make the reference read past the row / buffer end (its right-edge clamp uses the tripled width)
+        buf = np.zeros(src.size + pad, np.uint8)
+        buf[:src.size] = src.ravel()
+        dst = np.empty(self._shape(layout, wo, ho, 3), np.uint8)
+        self.lib.ref_resize_neon(_ptr(buf), _i(w), _i(h), _i(layout), _ptr(dst), _i(wo), _i(ho))
+        return dst
+
     def resize_cubic_f32_fixed(self, src, w, h, c, layout, wo, ho):
         src = _c(src, np.float32)
         dst = np.empty(self._shape(layout, wo, ho, c), np.float32)

@@ -138,6 +138,29 @@ def test_resize_linear_u8_signed_char_compat(oracle, ref_schar):
 
 
 @pytest.mark.parametrize("layout", [NHWC, NCHW])
+@pytest.mark.parametrize("sz", [((64, 48), (20, 16)), ((640, 360), (213, 120)), ((1920, 1080), (640, 360)), ((333, 211), (200, 100)),
+                                ((1280, 720), (500, 300)), ((64, 48), (200, 111)), ((176, 144), (640, 640))])
+def test_resize_linear_u8_neon_rule_vs_reference_neon_source(oracle, ref, layout, sz):
+    """Row a7: the NEON rounding rule (resize_neon.cpp:12-347) is aarch64-only in the reference; its source is compiled
+    unmodified against a scalar emulation of the nine intrinsics it uses (oracle/neon_emul/arm_neon.h) and compared with
+    the oracle's restatement.  CHW (one-channel kernel): identical everywhere.  HWC (three-channel kernel, called with
+    tripled widths, resize.cpp:133-134): identical wherever the right-edge clamp cannot trigger, i.e. for down-scaling;
+    when up-scaling the reference compares sx with the tripled width (:220), never clamps and reads past the row end --
+    there the oracle keeps the pixel-unit clamp of the one-channel kernel and only the columns left of the clamp agree."""
+    (w, h), (wo, ho) = sz
+    shape = (h, w, 3) if layout == NHWC else (3, h, w)
+    src = u8(w + 7 * ho, *shape)
+    want = ref.resize_neon(src, w, h, layout, wo, ho)
+    got = oracle.resize_linear_neon_rule(src, w, h, 3, layout, wo, ho)
+    if layout == NCHW or wo <= w:
+        assert np.array_equal(got, want)
+    else:
+        scale = w / wo
+        safe = int(np.floor((w - 1 + 0.5) / scale - 0.5))      # columns whose left tap is <= w - 2
+        assert np.array_equal(got[:, :safe], want[:, :safe])
+
+
+@pytest.mark.parametrize("layout", [NHWC, NCHW])
 @pytest.mark.parametrize("sz", SIZES[:5])
 def test_resize_linear_f32(oracle, ref, layout, sz):
     (w, h), (wo, ho) = sz
