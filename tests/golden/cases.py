@@ -42,6 +42,10 @@ def build_cases():
     c.append(("f32_to_u8", lambda r: r.change_dtype(imgf, 640, 360, 3, NHWC, INT8), lambda o: o.f32_to_u8(imgf)))
     c.append(("resize_linear_u8_hwc_320x180", lambda r: r.resize(img, 640, 360, 3, NHWC, 320, 180, 1), lambda o: o.resize_linear(img, 640, 360, 3, NHWC, 320, 180)))
     c.append(("resize_linear_u8_chw_213x97", lambda r: r.resize(chw, 640, 360, 3, NCHW, 213, 97, 1), lambda o: o.resize_linear(chw, 640, 360, 3, NCHW, 213, 97)))
+    c.append(("resize_linear_u8_neon_source_chw_213x97", lambda r: r.resize_neon(chw, 640, 360, NCHW, 213, 97),   # resize_neon.cpp over neon_emul
+              lambda o: o.resize_linear_neon_rule(chw, 640, 360, 3, NCHW, 213, 97)))
+    c.append(("resize_linear_u8_neon_source_hwc_320x180", lambda r: r.resize_neon(img, 640, 360, NHWC, 320, 180),
+              lambda o: o.resize_linear_neon_rule(img, 640, 360, 3, NHWC, 320, 180)))
     c.append(("resize_linear_f32_hwc_500x300", lambda r: r.resize(imgf, 640, 360, 3, NHWC, 500, 300, 1), lambda o: o.resize_linear(imgf, 640, 360, 3, NHWC, 500, 300)))
     c.append(("resize_cubic_f32_hwc_300x300", lambda r: r.resize(imgf, 640, 360, 3, NHWC, 300, 300, 2), lambda o: o.resize_cubic_f32(imgf, 640, 360, 3, NHWC, 300, 300)))
     c.append(("resize_cubic_f32_hwc_480x270_fixed", lambda r: r.resize_cubic_f32_fixed(imgf, 640, 360, 3, NHWC, 480, 270), lambda o: o.resize_cubic_f32(imgf, 640, 360, 3, NHWC, 480, 270)))

@@ -628,6 +628,10 @@ def test_cuda_vs_golden_digests(vacv):
         "u8_to_f32": vacv.dtype_change(dev(img[None]), vacv.FP32),
         "f32_to_u8": vacv.dtype_change(dev(imgf[None]), vacv.INT8),
         "resize_linear_u8_hwc_320x180": vacv.resize(dev(img[None]), NHWC, 320, 180),
+        "resize_linear_u8_chw_213x97": vacv.resize(dev(np.ascontiguousarray(img.transpose(2, 0, 1))[None]), NCHW, 213, 97),
+        "resize_linear_u8_neon_source_chw_213x97": vacv.resize(dev(np.ascontiguousarray(img.transpose(2, 0, 1))[None]), NCHW, 213, 97,
+                                                               vacv.INTER_LINEAR, vacv.FLAG_NEON_RULE),
+        "resize_linear_u8_neon_source_hwc_320x180": vacv.resize(dev(img[None]), NHWC, 320, 180, vacv.INTER_LINEAR, vacv.FLAG_NEON_RULE),
         "resize_linear_f32_hwc_500x300": vacv.resize(dev(imgf[None]), NHWC, 500, 300),
         "resize_cubic_f32_hwc_300x300": vacv.resize(dev(imgf[None]), NHWC, 300, 300, vacv.INTER_CUBIC),
         "resize_cubic_f32_hwc_480x270_fixed": vacv.resize(dev(imgf[None]), NHWC, 480, 270, vacv.INTER_CUBIC),
