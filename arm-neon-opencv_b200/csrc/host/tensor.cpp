@@ -1,6 +1,6 @@
 // vision::Tensor for libvacv.so -- same observable behaviour as the reference's src/common/tensor.cpp (cited per
-// function), written for this library: plain malloc'd host storage with an intrusive reference count placed behind
-// the (4-byte aligned) payload, and change_layout / change_dtype executed on the GPU through the C-ABI.
+// function), written for this library: pooled page-locked host storage (host_pool.h; the reference's USE_CUDA allocator is
+// cudaHostAlloc, va_allocator.cpp:12-31) with an intrusive reference count placed behind the (4-byte aligned) payload, and change_layout / change_dtype executed on the GPU through the C-ABI.
 #include "common/tensor.h"
 
 #include <atomic>
@@ -8,6 +8,7 @@
 #include <stdexcept>
 
 #include "device_context.h"
+#include "host_pool.h"
 #include "vacv_cuda.h"
 
 namespace vision {
@@ -83,14 +84,13 @@ void Tensor::create(int w_, int h_, int c_, DType dtype_, DLayout layout_) {   /
     const size_t bytes = len();
     if (bytes == 0) return;
     const size_t padded = (bytes + 3) & ~size_t(3);   // allocation = align4(len) + sizeof(int) (:534-539)
-    data = std::malloc(padded + sizeof(int));
-    if (!data) throw std::bad_alloc();
+    data = vacv_host::HostPool::instance().allocate(padded + sizeof(int));
     _ref_count = reinterpret_cast<int*>(static_cast<unsigned char*>(data) + padded);
     *_ref_count = 1;
 }
 
 void Tensor::release() {   // tensor.cpp:552-568
-    if (_ref_count && counter(_ref_count)->fetch_sub(1, std::memory_order_acq_rel) == 1) std::free(data);
+    if (_ref_count && counter(_ref_count)->fetch_sub(1, std::memory_order_acq_rel) == 1) vacv_host::HostPool::instance().release(data);
     data = nullptr; _ref_count = nullptr;
     dtype = FP32; layout = NCHW;
     stride = 0; w = 0; h = 0; c = 0;
