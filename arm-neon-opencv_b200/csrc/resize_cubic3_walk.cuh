@@ -53,13 +53,14 @@ __device__ __forceinline__ int dp2a_hi_su(int a, unsigned b, int c) {   // a.lo1
 constexpr int kWalkRing = 8;      // kAsync: ring slots (source rows) per warp
 constexpr int kWalkAhead = 6;     // kAsync: rows in flight ahead of the one being filtered (<= kWalkRing - 2)
 
-// fp32 (resize_naive.cpp:187-366), one output column per thread.
+// fp32, one output column per thread; C = 3: interleaved BGR (resize_naive.cpp:187-366), C = 1: one plane of a CHW tensor
+// (resize_naive_inter_cubic_fp32_one_channel, :368-529; the CHW wrapper :547-569 calls it per plane).
 // kAsync (source rows and base 16-byte aligned): each WARP streams the bytes its 32 columns need, row by row, into its own
 // shared-memory ring with cp.async (LDGSTS) kWalkAhead rows ahead, so DRAM latency is covered without holding registers;
 // otherwise the next row is prefetched into registers.
-template <bool kAsync>
+template <int C, bool kAsync>
 __global__ void __launch_bounds__(kWalkThreads) resize_cubic3_walk_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, WalkGeom g) {
-    constexpr int PX = 12, NW = 12;                  // bytes per pixel, 32-bit words a thread reads per source row
+    constexpr int PX = 4 * C, NW = 4 * C;            // bytes per pixel, 32-bit words a thread reads per source row
     constexpr int kWarpRow = 32 * PX;                // bytes one warp produces per output row
     extern __shared__ __align__(16) uint8_t smem[];
     WalkRow* rows = reinterpret_cast<WalkRow*>(smem);                                   // [rows_per_seg + 1]
@@ -124,12 +125,12 @@ __global__ void __launch_bounds__(kWalkThreads) resize_cubic3_walk_f32_kernel(co
 #pragma unroll
         for (int i = 0; i < NW; ++i) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(pf[i]) : "r"(p + 4 * i));
     };
-    auto hfilter = [&](float (&H)[3]) {               // horizontal pass of the fetched row, resize_naive.cpp:230 order
+    auto hfilter = [&](float (&H)[C]) {               // horizontal pass of the fetched row, resize_naive.cpp:230 order
 #pragma unroll
-        for (int k = 0; k < 3; ++k) H[k] = pf[k] * xa[0] + pf[3 + k] * xa[1] + pf[6 + k] * xa[2] + pf[9 + k] * xa[3];
+        for (int k = 0; k < C; ++k) H[k] = pf[k] * xa[0] + pf[C + k] * xa[1] + pf[2 * C + k] * xa[2] + pf[3 * C + k] * xa[3];
     };
 
-    float H[4][3];                                     // filtered rows: row t of the walk lives in slot t & 3
+    float H[4][C];                                     // filtered rows: row t of the walk lives in slot t & 3
     int staged = 0;
     const bool staged_store = g.store16 && dx_warp + 32 <= g.wo;
     const uint32_t stage_lane = (uint32_t)__cvta_generic_to_shared(stage) + PX * lane;
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(kWalkThreads) resize_cubic3_walk_f32_kernel(co
     constexpr int kChunks = kWarpRow / 16;             // 16-byte chunks per staged row
     constexpr int kFlushIters = (kWalkStageRows * kChunks + 31) / 32;
     uint8_t* gflush = out_img + (size_t)dy_begin * out_row_bytes + (size_t)dx_warp * PX;   // first staged row of this warp in global memory
-    float* gdirect = reinterpret_cast<float*>(out_img + (size_t)dy_begin * out_row_bytes) + (size_t)dx * 3;
+    float* gdirect = reinterpret_cast<float*>(out_img + (size_t)dy_begin * out_row_bytes) + (size_t)dx * C;
     auto flush = [&]() {                               // the warp's staged rows -> global, 16 bytes per lane
         __syncwarp();
 #pragma unroll
@@ -152,21 +153,23 @@ __global__ void __launch_bounds__(kWalkThreads) resize_cubic3_walk_f32_kernel(co
         sp = stage_lane;
     };
     // vertical pass + store of one output pixel from the window (h0 = oldest row)
-    auto emit = [&](const float (&h0)[3], const float (&h1)[3], const float (&h2)[3], const float (&h3)[3], uint32_t entry) {
+    auto emit = [&](const float (&h0)[C], const float (&h1)[C], const float (&h2)[C], const float (&h3)[C], uint32_t entry) {
         float4 bw;
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bw.x), "=f"(bw.y), "=f"(bw.z), "=f"(bw.w) : "r"(entry));
-        float o[3];
+        float o[C];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) o[k] = h0[k] * bw.x + h1[k] * bw.y + h2[k] * bw.z + h3[k] * bw.w;   // resize_naive.cpp:345
+        for (int k = 0; k < C; ++k) o[k] = h0[k] * bw.x + h1[k] * bw.y + h2[k] * bw.z + h3[k] * bw.w;   // resize_naive.cpp:345
         if (staged_store) {
-            asm volatile("st.shared.f32 [%0], %1;" ::"r"(sp), "f"(o[0]) : "memory");
-            asm volatile("st.shared.f32 [%0+4], %1;" ::"r"(sp), "f"(o[1]) : "memory");
-            asm volatile("st.shared.f32 [%0+8], %1;" ::"r"(sp), "f"(o[2]) : "memory");
+#pragma unroll
+            for (int k = 0; k < C; ++k) asm volatile("st.shared.f32 [%0], %1;" ::"r"(sp + 4 * k), "f"(o[k]) : "memory");
             sp += kWarpRow;
             if (++staged == kWalkStageRows) flush();
         } else {
-            if (dx < g.wo) { gdirect[0] = o[0]; gdirect[1] = o[1]; gdirect[2] = o[2]; }
-            gdirect += (size_t)g.wo * 3;
+            if (dx < g.wo) {
+#pragma unroll
+                for (int k = 0; k < C; ++k) gdirect[k] = o[k];
+            }
+            gdirect += (size_t)g.wo * C;
         }
     };
 
@@ -184,12 +187,12 @@ __global__ void __launch_bounds__(kWalkThreads) resize_cubic3_walk_f32_kernel(co
         prefetch(t);
     }
     while ((t & 3) != 0) {                             // leading rows up to the first multiple of 4: no complete window yet
-        float hv[3];
+        float hv[C];
         if (kAsync) { prefetch(t); fetch(t); }
         hfilter(hv);
         const int slot = t & 3;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
+        for (int k = 0; k < C; ++k) {
             if (slot == 1) H[1][k] = hv[k];
             if (slot == 2) H[2][k] = hv[k];
             if (slot == 3) H[3][k] = hv[k];

@@ -577,14 +577,16 @@ static int launch_cubic3_rolling(const void* src, void* dst, int images, int w, 
     return 1;
 }
 
-// Column-walking bicubic for interleaved 3-channel fp32 images (resize_cubic3_walk.cuh).  1 = launched, 0 = shape not eligible.
-static int launch_cubic3_walk_f32(const float* src, float* dst, int images, int w, int h, int wo, int ho, cudaStream_t s) {
-    constexpr int PX = 12;
+// Column-walking bicubic for fp32 images, C = 3 interleaved or C = 1 planes (resize_cubic3_walk.cuh).  1 = launched, 0 = shape
+// not eligible.
+template <int C>
+static int launch_cubic_walk_f32(const float* src, float* dst, int images, int w, int h, int wo, int ho, cudaStream_t s) {
+    constexpr int PX = 4 * C;
     if (w < 4 || h < 4 || (size_t)w * h * PX >= 0xffffffffull || (size_t)wo * ho * PX >= 0xffffffffull) return 0;
     if ((double)h / ho > 4.0) return 0;                                           // the walk filters every source row in a segment
     WalkGeom g;
     g.w = w; g.h = h; g.wo = wo; g.ho = ho;
-    g.src_image = (size_t)w * h * 3; g.dst_image = (size_t)wo * ho * 3;
+    g.src_image = (size_t)w * h * C; g.dst_image = (size_t)wo * ho * C;
     g.scale_x = (double)w / (double)wo; g.scale_y = (double)h / (double)ho;      // resize_naive.cpp:144
     g.strips = (wo + kWalkThreads - 1) / kWalkThreads;
     g.store16 = (((size_t)wo * PX) % 16 == 0 && ((uintptr_t)dst % 16) == 0) ? 1 : 0;
@@ -601,10 +603,10 @@ static int launch_cubic3_walk_f32(const float* src, float* dst, int images, int 
     const int span_px = (int)std::ceil(31.0 * g.scale_x) + 2 + 4;
     g.ring_pitch = (span_px * PX + 15 + 15) & ~15;
     static const char* sync_only = getenv("VACV_WALK_SYNC");   // tuning knob: register prefetch instead of the cp.async ring
-    const bool async = !sync_only && ((size_t)w * PX) % 16 == 0 && ((uintptr_t)src % 16) == 0 && g.ring_pitch <= 1024;
+    const bool async = !sync_only && ((size_t)w * PX) % 16 == 0 && ((size_t)w * h * PX) % 16 == 0 && ((uintptr_t)src % 16) == 0 && g.ring_pitch <= 1024;
     const size_t smem = (size_t)(rps + 1) * sizeof(WalkRow) + (size_t)(kWalkThreads / 32) * kWalkStageRows * 32 * PX +
                         (async ? (size_t)(kWalkThreads / 32) * kWalkRing * g.ring_pitch : 0);
-    auto kern = async ? resize_cubic3_walk_f32_kernel<true> : resize_cubic3_walk_f32_kernel<false>;
+    auto kern = async ? resize_cubic3_walk_f32_kernel<C, true> : resize_cubic3_walk_f32_kernel<C, false>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return set_error(VACV_ERR_CUDA, "resize: %s", cudaGetErrorString(e));
@@ -687,11 +689,15 @@ int try_launch_resize_tiled(int kind, const void* src, void* dst, int images, in
         int rc = 0;
         if (kind == kCubU8 && (!pick || pick[0] != 'r')) rc = launch_cubic3_walk2((const uint8_t*)src, (uint8_t*)dst, images, w, h, wo, ho, s);
         if (rc != 0) return rc;
-        if (kind == kCubF32 && (!pick || pick[0] != 'r')) rc = launch_cubic3_walk_f32((const float*)src, (float*)dst, images, w, h, wo, ho, s);
+        if (kind == kCubF32 && (!pick || pick[0] != 'r')) rc = launch_cubic_walk_f32<3>((const float*)src, (float*)dst, images, w, h, wo, ho, s);
         if (rc != 0) return rc;
         rc = kind == kCubU8 ? launch_cubic3_rolling<true>(src, dst, images, w, h, wo, ho, s) : launch_cubic3_rolling<false>(src, dst, images, w, h, wo, ho, s);
         if (rc != 0) return rc;
         rc = kind == kCubU8 ? launch_cubic3<kCubU8>(src, dst, images, w, h, wo, ho, s) : launch_cubic3<kCubF32>(src, dst, images, w, h, wo, ho, s);
+        if (rc != 0) return rc;
+    }
+    if (c == 1 && kind == kCubF32) {   // planes of a CHW tensor
+        const int rc = launch_cubic_walk_f32<1>((const float*)src, (float*)dst, images, w, h, wo, ho, s);
         if (rc != 0) return rc;
     }
     const int es = (kind == kLinF32 || kind == kCubF32) ? 4 : 1;
