@@ -2,5 +2,5 @@ set -x
 python -m pytest tests -m gpu -q 2>&1 | tail -3
 python bench_ops.py --workload all --iters 30 --json gpurun_out/r1_bench_ops.jsonl 2>&1 | grep -v "^\[" > gpurun_out/r1_bench_ops.txt
 python bench_ops.py --workload ops2 --iters 30 --json gpurun_out/r1_bench_ops2.jsonl 2>&1 | grep -v "^\[" >> gpurun_out/r1_bench_ops.txt
-python bench.py --steps 10 --warmup 3 > gpurun_out/r1_bench_c2_n1.json 2> gpurun_out/bench_err.txt; tail -c 600 gpurun_out/r1_bench_c2_n1.json
-ncu --set full --import-source on --clock-control none -k regex:resize_cubic3_walk -c 10 -o gpurun_out/r1_cubic3_walk python bench_ops.py --workload c4 --iters 2 > gpurun_out/ncu_c4.log 2>&1; tail -1 gpurun_out/ncu_c4.log
+python bench.py --steps 10 --warmup 3 > gpurun_out/r1_bench_c2_n1.json 2> gpurun_out/bench_err.txt; tail -c 300 gpurun_out/r1_bench_c2_n1.json
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r1_launches_bench_c2.csv python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_launch.log 2>&1; tail -1 gpurun_out/ncu_launch.log | cut -c1-200
