@@ -215,6 +215,67 @@ __global__ void __launch_bounds__(256) warp_affine_u8c3_kernel(const uint8_t* __
     }
 }
 
+// ----------------------------------------------------------------------------------------------------
+// u8, one channel (grey frames / one plane of a CHW frame), same structure: the two tap bytes of a row come from one aligned
+// 32-bit word (two when they straddle it), one IDP.2A forms L*cx0 + R*cx1; OUT = u8 (a warp's 32 bytes leave as 8 words) or
+// normalised fp32 (lane-contiguous 128-byte store, HWC == CHW for one channel).
+template <int OUT, bool kSigned>
+__global__ void __launch_bounds__(256) warp_affine_u8c1_kernel(const uint8_t* __restrict__ frames, const int* __restrict__ frame_idx,
+                                                                const float* __restrict__ minv, void* __restrict__ dst_, WarpGeom g,
+                                                                const float* __restrict__ mean, const float* __restrict__ stddev,
+                                                                int rows_per_cta, int crop0, size_t plane_elems, int planes) {
+    __shared__ float lut[OUT == kWarpOutU8 ? 1 : 256];
+    __shared__ float m[6];
+    __shared__ __align__(16) uint32_t stage[8][8];   // per warp: 32 px
+    // blockIdx.x = crop * planes + plane (planes > 1: the c planes of a CHW frame share the crop's matrix)
+    const int unit = crop0 + blockIdx.x, crop = unit / planes, plane = unit - crop * planes;
+    if (threadIdx.x < 6) m[threadIdx.x] = __ldg(minv + 6 * (size_t)crop + threadIdx.x);
+    if (OUT != kWarpOutU8)
+        for (int t = threadIdx.x; t < 256; t += blockDim.x) lut[t] = normalize_one((float)t, __ldg(mean), (double)__ldg(stddev) + 1e-6);
+    __syncthreads();
+    const size_t f = frame_idx ? (size_t)__ldg(frame_idx + crop) : (size_t)crop;
+    const uint8_t* img = frames + f * g.frame_elems + (size_t)plane * plane_elems;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i_begin = blockIdx.y * rows_per_cta * g.wo, i_end = min((blockIdx.y + 1) * rows_per_cta, g.ho) * g.wo;
+    const size_t crop_px = (size_t)g.wo * g.ho;
+    const float mr[6] = {m[0], m[1], m[2], m[3], m[4], m[5]};
+    const int step_y = 256 / g.wo, step_x = 256 - step_y * g.wo;
+    int dy = (i_begin + warp * 32 + lane) / g.wo, dx = (i_begin + warp * 32 + lane) - dy * g.wo;
+    auto taps = [&](unsigned a) -> uint32_t {   // bytes a, a+1 of the plane in the low half-word
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(img + (a & ~3u));
+        const int r = (int)(a & 3u);
+        const uint32_t w0 = __ldg(wp), w1 = r == 3 ? __ldg(wp + 1) : 0u;
+        return __funnelshift_r(w0, w1, r * 8);
+    };
+    for (int i0 = i_begin + warp * 32; i0 < i_end; i0 += 256, dx += step_x, dy += step_y) {   // warp-uniform loop
+        const int i = i0 + lane;
+        if (dx >= g.wo) { dx -= g.wo; ++dy; }
+        int v = 0;
+        if (i < i_end) {
+            const Taps t = warp_taps_fast(mr, dx, dy, g.w, g.h);
+            if (t.in) {
+                const uint32_t p0 = taps((unsigned)t.ofs), p1 = taps((unsigned)t.ofs + (unsigned)g.w);
+                const uint32_t cx = (uint32_t)t.cx0 | ((uint32_t)t.cx1 << 16);
+                const int Ht = kSigned ? __dp2a_lo((int)cx, (int)p0, 0) : (int)__dp2a_lo(cx, p0, 0u);
+                const int Hb = kSigned ? __dp2a_lo((int)cx, (int)p1, 0) : (int)__dp2a_lo(cx, p1, 0u);
+                v = ((Ht * t.cy0 + Hb * t.cy1) >> 22) & 0xff;   // warp_affine_naive.cpp:50-54 regrouped row-wise
+            }
+        }
+        const int n = min(32, i_end - i0);   // valid pixels of this warp
+        if (OUT == kWarpOutU8) {
+            uint8_t* sb = reinterpret_cast<uint8_t*>(stage[warp]);
+            sb[lane] = (uint8_t)v;
+            __syncwarp();
+            uint8_t* o = reinterpret_cast<uint8_t*>(dst_) + (size_t)unit * crop_px + i0;
+            if ((reinterpret_cast<uintptr_t>(o) & 3) == 0 && n == 32) { if (lane < 8) st_stream4(o + 4 * lane, stage[warp][lane]); }
+            else if (lane < n) o[lane] = sb[lane];
+            __syncwarp();
+        } else if (i < i_end) {
+            st_stream4f(reinterpret_cast<float*>(dst_) + (size_t)unit * crop_px + i, lut[v]);
+        }
+    }
+}
+
 }  // namespace vacv
 
 using namespace vacv;
@@ -243,6 +304,22 @@ extern "C" int vacv_cuda_warp_affine(const void* frames, int n_frames, int w, in
             warp_affine_u8c3_kernel<kWarpOutU8, true><<<grid, 256, 0, s>>>((const uint8_t*)frames, frame_idx, minv, dst, g, nullptr, nullptr, rows_per_cta, 0);
         else
             warp_affine_u8c3_kernel<kWarpOutU8, false><<<grid, 256, 0, s>>>((const uint8_t*)frames, frame_idx, minv, dst, g, nullptr, nullptr, rows_per_cta, 0);
+        return check_launch("warp_affine");
+    }
+    const bool planes_ok = (((size_t)w * h) % 4) == 0 && ((uintptr_t)frames % 4) == 0 && (size_t)w * h < 0xfffffff0ull;
+    if (dtype == VACV_INT8 && (c == 1 || layout == VACV_NCHW) && planes_ok && (long long)n_crops * c <= 0x7fffffffLL) {
+        // grey frames, or a CHW frame = c planes warped with the same matrix (warp_affine.cpp:150-166)
+        const int rows_per_cta = max(1, min(h_out, (4096 + w_out - 1) / w_out));
+        const int planes = c;
+        const long long units = (long long)n_crops * planes;
+        for (long long u0 = 0; u0 < units; u0 += 0x7ffffff0LL / planes * planes) {
+            const int nu = (int)min(units - u0, 0x7ffffff0LL / planes * planes);
+            dim3 grid(nu, ceil_div(h_out, rows_per_cta));
+            if (flags & VACV_FLAG_SIGNED_CHAR)
+                warp_affine_u8c1_kernel<kWarpOutU8, true><<<grid, 256, 0, s>>>((const uint8_t*)frames, frame_idx, minv, dst, g, nullptr, nullptr, rows_per_cta, (int)u0, (size_t)w * h, planes);
+            else
+                warp_affine_u8c1_kernel<kWarpOutU8, false><<<grid, 256, 0, s>>>((const uint8_t*)frames, frame_idx, minv, dst, g, nullptr, nullptr, rows_per_cta, (int)u0, (size_t)w * h, planes);
+        }
         return check_launch("warp_affine");
     }
     dim3 block(32, 8);
@@ -275,6 +352,10 @@ extern "C" int vacv_cuda_warp_affine_normalize(const uint8_t* frames, int n_fram
     if (c == 3 && (((size_t)w * h * 3) % 4) == 0 && ((uintptr_t)frames % 4) == 0 && (size_t)w * h * 3 < 0xfffffff0ull) {
         if (out_layout == VACV_NHWC) warp_affine_u8c3_kernel<kWarpOutF32HWC, false><<<grid, 256, 0, s>>>(frames, frame_idx, minv, dst, g, mean, stddev, rows_per_cta, 0);
         else warp_affine_u8c3_kernel<kWarpOutF32CHW, false><<<grid, 256, 0, s>>>(frames, frame_idx, minv, dst, g, mean, stddev, rows_per_cta, 0);
+        return check_launch("warp_affine_normalize");
+    }
+    if (c == 1 && (((size_t)w * h) % 4) == 0 && ((uintptr_t)frames % 4) == 0 && (size_t)w * h < 0xfffffff0ull) {
+        warp_affine_u8c1_kernel<kWarpOutF32HWC, false><<<grid, 256, 0, s>>>(frames, frame_idx, minv, dst, g, mean, stddev, rows_per_cta, 0, (size_t)w * h, 1);
         return check_launch("warp_affine_normalize");
     }
     if (c == 3) warp_affine_normalize_kernel<3><<<grid, 256, 0, s>>>(frames, frame_idx, minv, dst, g, mean, stddev, out_layout, rows_per_cta);

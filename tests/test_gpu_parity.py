@@ -331,6 +331,27 @@ def test_warp_affine_normalize_fused(vacv, oracle):
     assert_same(got_chw, np.ascontiguousarray(got.transpose(0, 3, 1, 2)))
 
 
+def test_warp_affine_grey_and_planar_batches(vacv, oracle):
+    """Single-channel frames and CHW frames (c planes, one matrix) through the word-granular single-channel kernel."""
+    w, h, wo, ho, nf, n = 320, 200, 112, 100, 3, 9
+    minv = np.array([vacv.invert_affine(m) for m in random_face_matrices(n, w, h, wo, 9)], np.float32)
+    idx = (np.arange(n) % nf).astype(np.int32)
+    grey = u8(24, nf, h, w, 1)
+    got = host(vacv.warp_affine(dev(grey), NHWC, dev(minv), wo, ho, dev(idx)))
+    for i in range(n):
+        assert_same(got[i], oracle.warp_affine(grey[idx[i]], w, h, 1, NHWC, wo, ho, minv[i]))
+    got_sc = host(vacv.warp_affine(dev(grey), NHWC, dev(minv), wo, ho, dev(idx), vacv.FLAG_SIGNED_CHAR))
+    assert_same(got_sc[2], oracle.warp_affine(grey[idx[2]], w, h, 1, NHWC, wo, ho, minv[2], signed_char=1))
+    chw = u8(25, nf, 3, h, w)
+    got = host(vacv.warp_affine(dev(chw), NCHW, dev(minv), wo, ho, dev(idx)))
+    for i in range(n):
+        assert_same(got[i], oracle.warp_affine(chw[idx[i]], w, h, 3, NCHW, wo, ho, minv[i]))
+    m1, s1 = np.array([117.0], np.float32), np.array([57.5], np.float32)
+    got = host(vacv.warp_affine_normalize(dev(grey), dev(minv), wo, ho, dev(m1), dev(s1), dev(idx)))
+    for i in range(n):
+        assert_same(got[i], oracle.warp_affine_normalize(grey[idx[i]], w, h, 1, minv[i], wo, ho, m1, s1))
+
+
 # ------------------------------------------------------------------ a11 / a12 statistics, normalize
 @pytest.mark.parametrize("layout", [NHWC, NCHW])
 @pytest.mark.parametrize("w,h,b", [(284, 214, 3), (3840, 2160, 2), (176, 144, 1), (33, 7, 2)])
