@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench_ops.py -- per-operator / per-config measurements next to the headline bench.py (not the driver contract).
 
-    python bench_ops.py [--workload all|c1|c2|c2g|c2s|c3|c4|c5|ops] [--iters N] [--json out.jsonl]
+    python bench_ops.py [--workload all|cpu|c1|c2|c2g|c2s|c3|c4|c5|ops] [--iters N] [--json out.jsonl]
     torchrun --nproc-per-node N bench_ops.py --workload c5        # batch-global statistics with the all-reduce
 
 For every kernel: device-resident time per launch (CUDA events, median of N after warm-up, batch >> L2), output
@@ -252,14 +252,61 @@ def ops2(iters):   # shapes off the headline path: planar layouts, fp32 gathers,
     report("op2 layout hwc->chw u8 c=4 1080p x64", ms, b * 1920 * 1080, b * 1920 * 1080 * 8)
 
 
+def cpu_reference():
+    """SURVEY 8(d) 'CPU reference alongside': the compiled reference (oracle/_ref, test infrastructure) timed on the box's host
+    cores for every config -- (i) one thread, as the reference runs, (ii) frames spread over all host cores.  Bounded samples."""
+    import ctypes as C
+    import time
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests"))
+    from oracle_lib import COLOR_YUV2BGR_NV21, Ref, ref_available
+    if not ref_available():
+        print("cpu: oracle/_ref not staged (make -C oracle ref)")
+        return
+    r = Ref()
+    cores = len(os.sched_getaffinity(0))
+    rng = np.random.default_rng(0)
+    mean, std = np.array(MEAN, np.float32), np.array(STD, np.float32)
+
+    r.lib.ref_time_config.restype = C.c_double
+    r.lib.ref_time_config.argtypes = [C.c_int, C.c_int, C.c_int]
+
+    def rate(name, cfg, out_pix, reps):
+        one = reps * out_pix / r.lib.ref_time_config(cfg, 1, reps) / 1e6
+        allc = cores * reps * out_pix / r.lib.ref_time_config(cfg, cores, reps) / 1e6
+        rec = {"name": f"cpu {name}", "Mpix_s_1_thread": round(one, 1), f"Mpix_s_{cores}_threads": round(allc, 1), "cores": cores,
+               "kind": "reference (oracle/_ref): C++ threads in the harness, one frame stream per thread", "frames_per_thread": reps}
+        RESULTS.append(rec)
+        print(f"cpu {name:58s} 1 thread {one:8.1f} Mpix/s   {cores} threads {allc:9.1f} Mpix/s", flush=True)
+
+    rate("c1 resize linear u8 1080p->640x360", 1, 640 * 360, 100)
+    rate("c3 warp_affine 720p->112x112 + f32 + normalize", 3, 112 * 112, 1500)
+    rate("c4 cv::resize u8 cubic 1440p->1080p (bundled OpenCV 2.4)", 4, 1920 * 1080, 20)
+    rate("c5 normalize u8 4K, own mean/stddev", 5, 3840 * 2160, 8)
+    nv = rng.integers(0, 256, (cores, 1920 * 1080 * 3 // 2), dtype=np.uint8)
+    t0 = time.perf_counter(); r.pipeline(nv[:1], 1920, 1080, COLOR_YUV2BGR_NV21, 640, 640, mean, std, batch=1, threads=1); t1 = time.perf_counter()
+    for _ in range(3):
+        r.pipeline(nv, 1920, 1080, COLOR_YUV2BGR_NV21, 640, 640, mean, std, batch=cores, threads=cores)
+    t2 = time.perf_counter()
+    one, allc = 640 * 640 / (t1 - t0) / 1e6, 3 * cores * 640 * 640 / (t2 - t1) / 1e6
+    RESULTS.append({"name": "cpu c2 chain", "Mpix_s_1_thread": round(one, 1), f"Mpix_s_{cores}_threads": round(allc, 1), "cores": cores})
+    print(f"cpu {'c2 chain nv21->bgr->640x640->f32->normalize->chw':58s} 1 thread {one:8.1f} Mpix/s   {cores} threads {allc:9.1f} Mpix/s", flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="all")
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--json", default=None)
     args = ap.parse_args()
-    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
     wl = args.workload
+    if wl == "cpu":   # host cores only
+        cpu_reference()
+        if args.json:
+            with open(args.json, "w") as f:
+                for r in RESULTS:
+                    f.write(json.dumps(r) + "\n")
+        return
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
     if wl in ("all", "c2"):
         c2(args.iters)
     if wl in ("all", "c2g"):   # general (non-integer-ratio) shapes of the fused kernel

@@ -7,6 +7,7 @@
 //
 // dtype codes = vision::DType (tensor.h:12-18): FP32=0 FP16=1 INT8=2 ; layout = vision::DLayout
 // (tensor.h:21-24): NCHW=0 NHWC=1.
+#include <chrono>
 #include <cstdint>
 #include <cstring>
 #include <atomic>
@@ -238,6 +239,49 @@ void ref_pipeline_nv_resize_norm_chw_batch(const uint8_t* src, int n, int w, int
     for (int t = 1; t < threads; ++t) pool.emplace_back(work);
     work();
     for (auto& t : pool) t.join();
+}
+
+
+// SURVEY 8(d) "CPU reference alongside": wall-clock seconds for `threads` host threads to run `reps` frames each of one
+// config through the reference's public API (each thread owns its tensors; frames are independent).  The harness, not the
+// reference, provides the threads.  cfg: 1 = resize linear u8 1080p -> 640x360, 3 = warp_affine 720p -> 112x112 + fp32 +
+// normalize, 4 = cv::resize u8 cubic 1440p -> 1080p (bundled OpenCV 2.4, the reference's only u8 cubic), 5 = normalize u8 4K
+// with its own mean/stddev.
+double ref_time_config(int cfg, int threads, int reps) {
+    auto fill = [](std::vector<uint8_t>& v, uint32_t seed) { for (auto& x : v) { seed = seed * 1664525u + 1013904223u; x = (uint8_t)(seed >> 24); } };
+    const float mean_v[3] = {103.53f, 116.28f, 123.675f}, std_v[3] = {57.375f, 57.12f, 58.395f};
+    cv::setNumThreads(1);
+    auto work = [&](int tid) {
+        if (cfg == 1) {
+            std::vector<uint8_t> img((size_t)1920 * 1080 * 3); fill(img, 1 + tid);
+            Tensor s = wrap(img.data(), 1920, 1080, 3, vision::INT8, vision::NHWC), d;
+            for (int i = 0; i < reps; ++i) va_cv::resize(s, d, va_cv::VSize(640, 360));
+        } else if (cfg == 3) {
+            std::vector<uint8_t> img((size_t)1280 * 720 * 3); fill(img, 3 + tid);
+            Tensor s = wrap(img.data(), 1280, 720, 3, vision::INT8, vision::NHWC), d, n;
+            Tensor m = wrap(mean_v, 3, 1, 1, vision::FP32, vision::NCHW), sd = wrap(std_v, 3, 1, 1, vision::FP32, vision::NCHW);
+            for (int i = 0; i < reps; ++i) {
+                float mat[6] = {0.4f, 0.05f, -100.f, -0.05f, 0.4f, -20.f};   // warp_affine inverts it in place
+                Tensor M = wrap(mat, 3, 2, 1, vision::FP32, vision::NCHW);
+                va_cv::warp_affine(s, d, M, va_cv::VSize(112, 112));
+                va_cv::normalize(d, n, m, sd);
+            }
+        } else if (cfg == 4) {
+            std::vector<uint8_t> img((size_t)2560 * 1440 * 3), out((size_t)1920 * 1080 * 3); fill(img, 4 + tid);
+            cv::Mat sm(1440, 2560, CV_8UC3, img.data()), dm(1080, 1920, CV_8UC3, out.data());
+            for (int i = 0; i < reps; ++i) cv::resize(sm, dm, cv::Size(1920, 1080), 0, 0, cv::INTER_CUBIC);
+        } else if (cfg == 5) {
+            std::vector<uint8_t> img((size_t)3840 * 2160 * 3); fill(img, 5 + tid);
+            Tensor s = wrap(img.data(), 3840, 2160, 3, vision::INT8, vision::NHWC), n;
+            for (int i = 0; i < reps; ++i) va_cv::normalize(s, n);
+        }
+    };
+    std::vector<std::thread> pool;
+    auto t0 = std::chrono::steady_clock::now();
+    for (int t = 1; t < threads; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto& t : pool) t.join();
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
 }  // extern "C"

@@ -372,7 +372,7 @@ class Ref:
         self.lib.ref_imread(path.encode(), _i(color), _ptr(dst), C.byref(w), C.byref(h), C.byref(c))
         return dst
 
-    def pipeline(self, src, w, h, code, wo, ho, mean, std, batch=None, threads=1):
+    def pipeline(self, src, w, h, code, wo, ho, mean, std, batch=None, threads=1, out=None):
         src = _c(src, np.uint8)
         mean = _c(mean, np.float32)
         std = _c(std, np.float32)
@@ -381,7 +381,7 @@ class Ref:
             self.lib.ref_pipeline_nv_resize_norm_chw(_ptr(src), _i(w), _i(h), _i(code), _i(wo), _i(ho), _ptr(mean),
                                                      _ptr(std), _ptr(dst))
         else:
-            dst = np.empty((batch, 3, ho, wo), np.float32)
+            dst = out if out is not None else np.empty((batch, 3, ho, wo), np.float32)
             self.lib.ref_pipeline_nv_resize_norm_chw_batch(_ptr(src), _i(batch), _i(w), _i(h), _i(code), _i(wo), _i(ho),
                                                            _ptr(mean), _ptr(std), _ptr(dst), _i(threads))
         return dst
