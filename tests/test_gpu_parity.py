@@ -614,6 +614,79 @@ def test_full_size_config2_properties(vacv):
         assert np.all(flat[k] == want)
 
 
+def _gpu_rand_u8(seed, *shape):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return torch.randint(0, 256, shape, dtype=torch.uint8, device="cuda", generator=g)
+
+
+def test_full_size_config2_batch256_sampled_vs_oracle(vacv, oracle):
+    """BASELINE config 2 at its full size (256 x 1080p NV12 -> 640x640 CHW fp32): sampled frames against the oracle."""
+    w, h, wo, ho, b = 1920, 1080, 640, 640, 256
+    src = _gpu_rand_u8(1, b, w * h * 3 // 2)
+    out = vacv.nv_resize_normalize_chw(src, w, h, wo, ho, dev(MEAN), dev(STD))
+    for i in (0, 131, 255):
+        want = oracle.nv_resize_normalize_chw(host(src[i]), w, h, 1, wo, ho, MEAN, STD)
+        assert_same(host(out[i]), want)
+
+
+def test_full_size_config1_batch256_sampled_vs_oracle(vacv, oracle):
+    """BASELINE config 1 shape, batch 256: sampled frames against the oracle; the batch equals frame-by-frame processing."""
+    w, h, wo, ho, b = 1920, 1080, 640, 360, 256
+    src = _gpu_rand_u8(2, b, h, w, 3)
+    out = vacv.resize(src, NHWC, wo, ho)
+    for i in (0, 100, 255):
+        assert_same(host(out[i]), oracle.resize_linear(host(src[i]), w, h, 3, NHWC, wo, ho))
+        assert torch.equal(out[i], vacv.resize(src[i:i + 1], NHWC, wo, ho)[0])
+
+
+def test_full_size_config3_4096_crops_sampled_vs_oracle(vacv, oracle):
+    """BASELINE config 3 at its full size: 4096 face crops from a pool of 720p frames; sampled crops against the oracle."""
+    w, h, wo, ho, nf, n = 1280, 720, 112, 112, 64, 4096
+    frames = _gpu_rand_u8(3, nf, h, w, 3)
+    minv = np.array([vacv.invert_affine(m) for m in random_face_matrices(n, w, h, wo, 11)], np.float32)
+    idx = (np.arange(n) % nf).astype(np.int32)
+    out = vacv.warp_affine_normalize(frames, dev(minv), wo, ho, dev(MEAN), dev(STD), dev(idx))
+    assert tuple(out.shape) == (n, ho, wo, 3)
+    for i in (0, 777, 2048, 4095):
+        want = oracle.warp_affine_normalize(host(frames[idx[i]]), w, h, 3, minv[i], wo, ho, MEAN, STD)
+        assert_same(host(out[i]), want)
+
+
+def test_full_size_config4_batch128_properties(vacv, oracle):
+    """BASELINE config 4 at its full size (128 x 2560x1440 -> 1920x1080 u8 bicubic): one frame against the oracle (OpenCV-2.4
+    rule), and the batch result is independent of the batch position (the same frame replicated gives identical outputs)."""
+    w, h, wo, ho, b = 2560, 1440, 1920, 1080, 128
+    one = _gpu_rand_u8(4, 1, h, w, 3)
+    src = one.expand(b, h, w, 3).contiguous()
+    src[77] = _gpu_rand_u8(5, h, w, 3)
+    out = vacv.resize(src, NHWC, wo, ho, vacv.INTER_CUBIC)
+    assert_same(host(out[0]), oracle.resize_cubic_u8(host(one[0]), w, h, 3, wo, ho))
+    for i in (1, 64, 127):
+        assert torch.equal(out[i], out[0])
+    assert_same(host(out[77]), oracle.resize_cubic_u8(host(src[77]), w, h, 3, wo, ho))
+
+
+def test_full_size_config5_per_gpu_shard_properties(vacv, oracle):
+    """BASELINE config 5, one GPU's shard at full size (128 x 3840x2160 BGR u8): the exact sums are additive over frames
+    (sum of per-frame sums == batch sums == numpy's exact integer sums of sampled frames), and sampled frames of the
+    normalised output equal the oracle's normalise with the batch-global statistics."""
+    w, h, b = 3840, 2160, 128
+    src = _gpu_rand_u8(6, b, h, w, 3)
+    per_frame = vacv.sums_u8(src, NHWC, per_frame=True)            # [b, 3, 2] int64
+    total = vacv.sums_u8(src, NHWC, per_frame=False)               # [1, 3, 2]
+    assert torch.equal(per_frame.sum(0, keepdim=True), total)
+    for i in (0, 127):
+        f = host(src[i]).astype(np.int64).reshape(-1, 3)
+        assert np.array_equal(host(per_frame[i])[:, 0], f.sum(0)) and np.array_equal(host(per_frame[i])[:, 1], (f * f).sum(0))
+    mean, std = vacv.finalize_mean_stddev(total, b * w * h)
+    m, s = oracle.finalize_mean_stddev(host(total)[0].astype(np.uint64).ravel(), 3, b * w * h)
+    assert_same(host(mean)[0], m)
+    assert_same(host(std)[0], s)
+    out = vacv.normalize(src, NHWC, mean[0], std[0])
+    for i in (3, 90):
+        assert_same(host(out[i]), oracle.normalize(host(src[i]), w * h, 3, NHWC, m, s))
+
+
 # ------------------------------------------------------------------ the C++ drop-in (libvacv.so) end to end
 def test_cpp_dropin_binary(vacv):
     """tests/cpp/test_dropin: a reference-style C++ caller linked against libvacv.so, checked against the oracle."""
