@@ -45,6 +45,7 @@ _SIGS = {
     "vacv_cuda_cvt_yuv2bgr": [_vp, _vp, _vp, _i, _vp],
     "vacv_cuda_yuv_letterbox_normalize_chw": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "vacv_letterbox_rect": [_i, _i, _i, _i, _vp],
+    "vacv_cuda_yuv_normalize_chw_host": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i],
     "vacv_cuda_nv_resize_normalize_chw_host": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i],
     "vacv_cuda_resize_normalize": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp],
     "vacv_cuda_warp_affine_normalize": [_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _vp],
@@ -348,6 +349,27 @@ def nv_resize_normalize_chw_host(h_src, h_out, w, h, w_out, h_out_, mean, std, v
     s = (C.c_float * 3)(*[float(v) for v in std])
     _check(lib.vacv_cuda_nv_resize_normalize_chw_host(h_src.data_ptr(), h_out.data_ptr(), b, w, h, int(bool(v_first)), w_out, h_out_,
                                                       C.cast(m, _vp), C.cast(s, _vp), chunk_frames))
+    return h_out
+
+
+def yuv_normalize_chw_host(h_src, h_out, fmt, w, h, canvas_w, canvas_h, mean, std, content=None, pad_bgr=(114, 114, 114), y_pitch=0,
+                           c_pitch=0, frame_stride=0, batch=None, out_dtype=FP32, chunk_frames=8):
+    """Host-buffer form of yuv_resize_normalize_chw (content None) / yuv_letterbox_normalize_chw: host surfaces in, host planes
+    (fp32 / fp16 / bf16, dtype of h_out must match out_dtype) out.  Synchronous."""
+    if h_src.is_cuda or h_out.is_cuda:
+        raise VacvError("yuv_normalize_chw_host takes host tensors")
+    if h_out.dtype != _torch_out_dtype(out_dtype):
+        raise VacvError("h_out dtype does not match out_dtype")
+    lay = YuvLayout(fmt, w, h, y_pitch, c_pitch, frame_stride)
+    if batch is None:
+        batch = _yuv_batch(h_src, fmt, w, h, y_pitch, c_pitch, frame_stride)
+    m = (C.c_float * 3)(*[float(v) for v in mean])
+    s = (C.c_float * 3)(*[float(v) for v in std])
+    pad = (C.c_uint8 * 3)(*[int(v) for v in pad_bgr])
+    r = Rect(*content) if content is not None else None
+    _check(lib.vacv_cuda_yuv_normalize_chw_host(h_src.data_ptr(), C.addressof(lay), h_out.data_ptr(), out_dtype, batch, canvas_w, canvas_h,
+                                                C.addressof(r) if r is not None else None, C.cast(pad, _vp), C.cast(m, _vp), C.cast(s, _vp),
+                                                chunk_frames))
     return h_out
 
 

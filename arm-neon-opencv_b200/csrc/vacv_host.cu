@@ -151,37 +151,86 @@ thread_local HostPipe g_pipe;
         if (e_ != cudaSuccess) return vacv::set_error(VACV_ERR_CUDA, "nv_resize_normalize_chw_host: %s", cudaGetErrorString(e_)); \
     } while (0)
 
+// Chunked, three-stream pipeline shared by the host-buffer entry points: chunk i's H2D copy, chunk i-1's kernel and chunk
+// i-2's D2H copy overlap.  `launch(d_in, d_out, frames, stream)` enqueues the kernel(s) of one chunk and returns a status.
+template <typename Launch>
+static int run_host_pipeline(const char* who, const uint8_t* h_src, void* h_dst, int batch, size_t in_frame, size_t out_frame,
+                             int chunk_frames, const float* h_mean, const float* h_stddev, float** d_stats_out, Launch launch) {
+#define VACV_CUP(call)                                                                                          \
+    do {                                                                                                        \
+        cudaError_t e_ = (call);                                                                                \
+        if (e_ != cudaSuccess) return vacv::set_error(VACV_ERR_CUDA, "%s: %s", who, cudaGetErrorString(e_));   \
+    } while (0)
+    HostPipe& p = g_pipe;
+    VACV_CUP(p.init());
+    const int chunk = chunk_frames < batch ? chunk_frames : batch;
+    VACV_CUP(p.reserve(in_frame * chunk, out_frame * chunk));
+    float stats[6] = {h_mean[0], h_mean[1], h_mean[2], h_stddev[0], h_stddev[1], h_stddev[2]};
+    VACV_CUP(cudaMemcpyAsync(p.d_stats, stats, sizeof(stats), cudaMemcpyHostToDevice, p.s_k));
+    VACV_CUP(cudaStreamSynchronize(p.s_k));   // `stats` lives on this stack frame
+    *d_stats_out = p.d_stats;
+    int i = 0;
+    for (int f0 = 0; f0 < batch; f0 += chunk, ++i) {
+        const int b = i & 1, n = (batch - f0 < chunk) ? batch - f0 : chunk;
+        // H2D of chunk i may start once the kernel that last read d_in[b] (chunk i-2) is done
+        if (i >= 2) VACV_CUP(cudaStreamWaitEvent(p.s_in, p.k_done[b], 0));
+        VACV_CUP(cudaMemcpyAsync(p.d_in[b], h_src + (size_t)f0 * in_frame, in_frame * n, cudaMemcpyHostToDevice, p.s_in));
+        VACV_CUP(cudaEventRecord(p.in_done[b], p.s_in));
+        // kernel of chunk i: needs its input, and d_out[b] drained by the D2H of chunk i-2
+        VACV_CUP(cudaStreamWaitEvent(p.s_k, p.in_done[b], 0));
+        if (i >= 2) VACV_CUP(cudaStreamWaitEvent(p.s_k, p.out_done[b], 0));
+        const int rc = launch(p.d_in[b], (void*)p.d_out[b], n, (void*)p.s_k);
+        if (rc != VACV_OK) { cudaDeviceSynchronize(); return rc; }
+        VACV_CUP(cudaEventRecord(p.k_done[b], p.s_k));
+        VACV_CUP(cudaStreamWaitEvent(p.s_out, p.k_done[b], 0));
+        VACV_CUP(cudaMemcpyAsync((uint8_t*)h_dst + (size_t)f0 * out_frame, p.d_out[b], out_frame * n, cudaMemcpyDeviceToHost, p.s_out));
+        VACV_CUP(cudaEventRecord(p.out_done[b], p.s_out));
+    }
+    VACV_CUP(cudaStreamSynchronize(p.s_out));
+    VACV_CUP(cudaStreamSynchronize(p.s_k));
+    return VACV_OK;
+#undef VACV_CUP
+}
+
 extern "C" int vacv_cuda_nv_resize_normalize_chw_host(const uint8_t* h_src, float* h_dst, int batch, int w, int h, int v_first,
                                                       int w_out, int h_out, const float* h_mean, const float* h_stddev,
                                                       int chunk_frames) {
     VACV_REQUIRE(h_src && h_dst && h_mean && h_stddev, "nv_resize_normalize_chw_host: null pointer");
     VACV_REQUIRE(batch > 0 && chunk_frames > 0, "nv_resize_normalize_chw_host: bad batch / chunk");
-    HostPipe& p = g_pipe;
-    VACV_CU(p.init());
-    const size_t in_frame = (size_t)w * h * 3 / 2, out_frame = (size_t)w_out * h_out * 3 * sizeof(float);
-    const int chunk = chunk_frames < batch ? chunk_frames : batch;
-    VACV_CU(p.reserve(in_frame * chunk, out_frame * chunk));
-    float stats[6] = {h_mean[0], h_mean[1], h_mean[2], h_stddev[0], h_stddev[1], h_stddev[2]};
-    VACV_CU(cudaMemcpyAsync(p.d_stats, stats, sizeof(stats), cudaMemcpyHostToDevice, p.s_k));
-    VACV_CU(cudaStreamSynchronize(p.s_k));   // `stats` lives on this stack frame
-    int i = 0;
-    for (int f0 = 0; f0 < batch; f0 += chunk, ++i) {
-        const int b = i & 1, n = (batch - f0 < chunk) ? batch - f0 : chunk;
-        // H2D of chunk i may start once the kernel that last read d_in[b] (chunk i-2) is done
-        if (i >= 2) VACV_CU(cudaStreamWaitEvent(p.s_in, p.k_done[b], 0));
-        VACV_CU(cudaMemcpyAsync(p.d_in[b], h_src + (size_t)f0 * in_frame, in_frame * n, cudaMemcpyHostToDevice, p.s_in));
-        VACV_CU(cudaEventRecord(p.in_done[b], p.s_in));
-        // kernel of chunk i: needs its input, and d_out[b] drained by the D2H of chunk i-2
-        VACV_CU(cudaStreamWaitEvent(p.s_k, p.in_done[b], 0));
-        if (i >= 2) VACV_CU(cudaStreamWaitEvent(p.s_k, p.out_done[b], 0));
-        const int rc = vacv_cuda_nv_resize_normalize_chw(p.d_in[b], p.d_out[b], n, w, h, v_first, w_out, h_out, p.d_stats, p.d_stats + 3, p.s_k);
-        if (rc != VACV_OK) { cudaDeviceSynchronize(); return rc; }
-        VACV_CU(cudaEventRecord(p.k_done[b], p.s_k));
-        VACV_CU(cudaStreamWaitEvent(p.s_out, p.k_done[b], 0));
-        VACV_CU(cudaMemcpyAsync(h_dst + (size_t)f0 * (out_frame / sizeof(float)), p.d_out[b], out_frame * n, cudaMemcpyDeviceToHost, p.s_out));
-        VACV_CU(cudaEventRecord(p.out_done[b], p.s_out));
-    }
-    VACV_CU(cudaStreamSynchronize(p.s_out));
-    VACV_CU(cudaStreamSynchronize(p.s_k));
-    return VACV_OK;
+    float* d_stats = nullptr;
+    float** ds = &d_stats;
+    return run_host_pipeline("nv_resize_normalize_chw_host", h_src, h_dst, batch, (size_t)w * h * 3 / 2, (size_t)w_out * h_out * 3 * sizeof(float),
+                             chunk_frames, h_mean, h_stddev, ds, [=](const uint8_t* d_in, void* d_out, int n, void* stream) {
+                                 return vacv_cuda_nv_resize_normalize_chw(d_in, (float*)d_out, n, w, h, v_first, w_out, h_out, *ds, *ds + 3, stream);
+                             });
+}
+
+// Host-buffer form of the decoder-surface entries: pitched / planar frames in host memory in, fp32 / fp16 / bf16 planes back in
+// host memory; content == NULL: plain resize to canvas_w x canvas_h, else letterbox placement (see the device entries).
+extern "C" int vacv_cuda_yuv_normalize_chw_host(const uint8_t* h_src, const vacv_yuv_layout* layout, void* h_dst, int out_dtype, int batch,
+                                                int canvas_w, int canvas_h, const vacv_rect* content, const uint8_t* pad_bgr,
+                                                const float* h_mean, const float* h_stddev, int chunk_frames) {
+    VACV_REQUIRE(h_src && layout && h_dst && h_mean && h_stddev, "yuv_normalize_chw_host: null pointer");
+    VACV_REQUIRE(batch > 0 && chunk_frames > 0 && canvas_w > 0 && canvas_h > 0, "yuv_normalize_chw_host: bad batch / chunk / size");
+    VACV_REQUIRE(!content || pad_bgr, "yuv_normalize_chw_host: letterbox needs a pad colour");
+    if (out_dtype != VACV_FP32 && out_dtype != VACV_FP16 && out_dtype != VACV_BF16)
+        return vacv::set_error(VACV_ERR_UNSUPPORTED, "yuv_normalize_chw_host: out dtype %d (FP32, FP16 or BF16)", out_dtype);
+    const bool planar = layout->format == VACV_YUV_I420 || layout->format == VACV_YUV_YV12;
+    const size_t yp = layout->y_pitch ? layout->y_pitch : layout->w, cp = layout->c_pitch ? layout->c_pitch : (planar ? layout->w / 2 : layout->w);
+    const size_t in_frame = layout->frame_stride ? layout->frame_stride : yp * layout->h + cp * (layout->h / 2) * (planar ? 2 : 1);
+    const size_t out_frame = (size_t)canvas_w * canvas_h * 3 * (out_dtype == VACV_FP32 ? 4 : 2);
+    vacv_yuv_layout lay = *layout;
+    lay.frame_stride = in_frame;
+    vacv_rect box = content ? *content : vacv_rect{0, 0, canvas_w, canvas_h};
+    uint8_t pad[3] = {pad_bgr ? pad_bgr[0] : (uint8_t)0, pad_bgr ? pad_bgr[1] : (uint8_t)0, pad_bgr ? pad_bgr[2] : (uint8_t)0};
+    float* d_stats = nullptr;
+    float** ds = &d_stats;
+    const bool letterbox = content != nullptr;
+    return run_host_pipeline("yuv_normalize_chw_host", h_src, h_dst, batch, in_frame, out_frame, chunk_frames, h_mean, h_stddev, ds,
+                             [=](const uint8_t* d_in, void* d_out, int n, void* stream) {
+                                 if (letterbox)
+                                     return vacv_cuda_yuv_letterbox_normalize_chw(d_in, &lay, d_out, out_dtype, n, canvas_w, canvas_h, &box, pad, *ds, *ds + 3,
+                                                                                  h_mean, h_stddev, stream);
+                                 return vacv_cuda_yuv_resize_normalize_chw(d_in, &lay, d_out, out_dtype, n, canvas_w, canvas_h, *ds, *ds + 3, stream);
+                             });
 }

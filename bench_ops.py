@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench_ops.py -- per-operator / per-config measurements next to the headline bench.py (not the driver contract).
 
-    python bench_ops.py [--workload all|cpu|c1|c2|c2g|c2s|c3|c4|c5|ops] [--iters N] [--json out.jsonl]
+    python bench_ops.py [--workload all|cpu|e2e|c1|c2|c2g|c2s|c3|c4|c5|ops] [--iters N] [--json out.jsonl]
     torchrun --nproc-per-node N bench_ops.py --workload c5        # batch-global statistics with the all-reduce
 
 For every kernel: device-resident time per launch (CUDA events, median of N after warm-up, batch >> L2), output
@@ -252,6 +252,25 @@ def ops2(iters):   # shapes off the headline path: planar layouts, fp32 gathers,
     report("op2 layout hwc->chw u8 c=4 1080p x64", ms, b * 1920 * 1080, b * 1920 * 1080 * 8)
 
 
+def e2e(iters):
+    """Host buffers in, host buffers out (pinned), through the chunked three-stream pipeline: the config-2 shape with fp32 and
+    fp16 planes.  Wall clock; PCIe-bound (the fp16 planes halve the D2H bytes)."""
+    import time
+    b, w, h, wo, ho = 256, 1920, 1080, 640, 640
+    h_in = torch.randint(0, 256, (b, w * h * 3 // 2), dtype=torch.uint8).pin_memory()
+    for name, dt, tdt, eb in [("fp32", vacv.FP32, torch.float32, 4), ("fp16", vacv.FP16, torch.float16, 2)]:
+        h_out = torch.empty((b, 3, ho, wo), dtype=tdt).pin_memory()
+        run = lambda: vacv.yuv_normalize_chw_host(h_in, h_out, vacv.YUV_NV12, w, h, wo, ho, MEAN, STD, batch=b, out_dtype=dt, chunk_frames=8)
+        for _ in range(2):
+            run()
+        n = max(3, iters // 4)
+        t0 = time.perf_counter()
+        for _ in range(n):
+            run()
+        ms = (time.perf_counter() - t0) / n * 1e3
+        report(f"e2e host nv12 -> host {name} planes 1080p->640x640 x{b}", ms, b * wo * ho, b * (w * h * 3 // 2 + wo * ho * 3 * eb), "PCIe bytes (H2D + D2H)")
+
+
 def cpu_reference():
     """SURVEY 8(d) 'CPU reference alongside': the compiled reference (oracle/_ref, test infrastructure) timed on the box's host
     cores for every config -- (i) one thread, as the reference runs, (ii) frames spread over all host cores.  Bounded samples."""
@@ -307,6 +326,8 @@ def main():
                     f.write(json.dumps(r) + "\n")
         return
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
+    if wl in ("all", "e2e"):
+        e2e(args.iters)
     if wl in ("all", "c2"):
         c2(args.iters)
     if wl in ("all", "c2g"):   # general (non-integer-ratio) shapes of the fused kernel

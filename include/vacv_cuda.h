@@ -173,6 +173,13 @@ VACV_API int vacv_cuda_yuv_letterbox_normalize_chw(const uint8_t* src, const vac
                                                    const float* mean, const float* stddev, const float* mean_host, const float* stddev_host,
                                                    void* stream);
 
+/* Host-buffer form of the two entries above (same chunked H2D / kernel / D2H pipeline as
+ * vacv_cuda_nv_resize_normalize_chw_host below): h_src holds `batch` surfaces, h_dst receives batch x 3 x canvas_h x canvas_w
+ * planes of out_dtype.  content == NULL: plain resize to the canvas; else letterbox (pad_bgr required).  Synchronous. */
+VACV_API int vacv_cuda_yuv_normalize_chw_host(const uint8_t* h_src, const vacv_yuv_layout* layout, void* h_dst, int out_dtype, int batch,
+                                              int canvas_w, int canvas_h, const vacv_rect* content, const uint8_t* pad_bgr,
+                                              const float* h_mean, const float* h_stddev, int chunk_frames);
+
 /* ---- host-buffer entry point of the fused pipeline (the end-to-end path) ------------------------------------------
  * Same operation as vacv_cuda_nv_resize_normalize_chw, but `h_src` / `h_dst` / `h_mean` / `h_stddev` are HOST pointers
  * (pinned memory -- vacv_cuda_host_alloc -- for full PCIe speed; pageable works, slower).  The batch is cut into chunks of

@@ -758,6 +758,33 @@ def test_host_buffer_pipeline_entry(vacv, oracle):
     assert_same(out2.numpy(), want)
 
 
+def test_host_buffer_yuv_entry(vacv, oracle):
+    """vacv_cuda_yuv_normalize_chw_host: pitched NV12 surfaces in host memory -> fp16 letterboxed planes in host memory."""
+    from test_oracle_vs_ref import make_yuv_surface
+    w, h, cw, ch, b, yp = 640, 360, 416, 416, 5, 704
+    per = yp * h * 3 // 2
+    buf = np.empty(b * per, np.uint8)
+    x0, y0, rw, rh = vacv.letterbox_rect(w, h, cw, ch)
+    want = np.empty((b, 3, ch, cw), np.float32)
+    want_plain = np.empty((b, 3, ch, cw), np.float32)
+    for i in range(b):
+        surf, _ = make_yuv_surface(500 + i, 1, w, h, yp, yp)
+        buf[i * per:(i + 1) * per] = surf
+        bgr = oracle.yuv_to_bgr(surf, 1, w, h, yp, yp)
+        canvas = np.full((ch, cw, 3), 114, np.uint8)
+        canvas[y0:y0 + rh, x0:x0 + rw] = oracle.resize_linear(bgr, w, h, 3, NHWC, rw, rh)
+        want[i] = oracle.hwc_to_chw(oracle.normalize(canvas, cw * ch, 3, NHWC, MEAN, STD), cw, ch, 3)
+        want_plain[i] = oracle.hwc_to_chw(oracle.normalize(oracle.resize_linear(bgr, w, h, 3, NHWC, cw, ch), cw * ch, 3, NHWC, MEAN, STD), cw, ch, 3)
+    h_in = torch.from_numpy(buf).pin_memory()
+    h_out = torch.empty((b, 3, ch, cw), dtype=torch.float16).pin_memory()
+    vacv.yuv_normalize_chw_host(h_in, h_out, vacv.YUV_NV12, w, h, cw, ch, MEAN, STD, content=(x0, y0, rw, rh), y_pitch=yp, c_pitch=yp,
+                                batch=b, out_dtype=vacv.FP16, chunk_frames=2)
+    assert_same(h_out.numpy(), want.astype(np.float16))
+    h_out32 = torch.empty((b, 3, ch, cw), dtype=torch.float32)
+    vacv.yuv_normalize_chw_host(h_in, h_out32, vacv.YUV_NV12, w, h, cw, ch, MEAN, STD, y_pitch=yp, c_pitch=yp, batch=b, chunk_frames=3)
+    assert_same(h_out32.numpy(), want_plain)
+
+
 # ------------------------------------------------------------------ the reference's OWN test-suite on the drop-in
 def test_reference_test_suite_links_and_passes_on_dropin(vacv):
     """oracle/_ref/va_cv_ut_b200 = the reference's src/test sources, compiled unmodified, linked against libvacv.so.
