@@ -219,8 +219,9 @@ __global__ void __launch_bounds__(kWalkThreads) resize_cubic3_walk_f32_kernel(co
 }
 
 // =====================================================================================================================
-// u8, two adjacent output columns per thread.  Same walk as above; the vertical pass runs on PACKED fp32 pairs (FFMA2 /
-// FMUL2, sm_100): lane value = (column A, column B) of one channel, so OpenCV's mul/add chain costs 8 instructions per
+// u8, two output columns per thread (32 columns apart, so that a warp's tap reads stay bank-conflict free).  Same walk as
+// above; the vertical pass runs on PACKED fp32 pairs (FFMA2 /
+// FMUL2, sm_100): packed value = (column A, column B) of one channel, so OpenCV's mul/add chain costs 8 instructions per
 // two output values instead of 16.  Each product and each sum is rounded separately, exactly like mulps / addps:
 // ptxas contracts mul.f32x2 + add.f32x2 (even .rn ones) into one FFMA2, so both are written as fma.rn.f32x2 with the
 // neutral operand (-0.0 resp. 1.0) coming from a KERNEL PARAMETER -- a value ptxas cannot see, hence cannot fold.
@@ -266,7 +267,8 @@ __global__ void __launch_bounds__(kWalkThreads, kAsync ? 6 : 1) resize_cubic3_wa
                     (tid >> 5) * (kWalk2Ring * g.ring_pitch);
     const int strip = blockIdx.x % g.strips, seg = blockIdx.x / g.strips;
     const int dx_warp = strip * kWalk2Cols + (tid >> 5) * 64;
-    const int dx = dx_warp + 2 * lane;               // columns dx, dx + 1
+    const int dx = dx_warp + lane;                   // columns dx, dx + 32: each tap-word read of a warp then covers one contiguous
+                                                     // ~128-byte span (adjacent columns per lane cost a 2-way bank conflict on every read)
     const int dy_begin = seg * g.rows_per_seg, nrows = min(g.ho, dy_begin + g.rows_per_seg) - dy_begin;
     const uint8_t* img = src + blockIdx.y * g.src_image;
     uint8_t* out_img = dst + blockIdx.y * g.dst_image;
@@ -288,7 +290,7 @@ __global__ void __launch_bounds__(kWalkThreads, kAsync ? 6 : 1) resize_cubic3_wa
     int sh[2], c01[2], c23[2], aw[2];
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
-        const int dxc = min(dx + c, g.wo - 1);
+        const int dxc = min(dx + 32 * c, g.wo - 1);
         int s, q[4], xc[4] = {0, 0, 0, 0};
         cubic_cv_coord_scaled(dxc, g.w, g.scale_x, true, s, q);
         const int x_first = min(max(s - 1, 0), g.w - 4);
@@ -313,7 +315,7 @@ __global__ void __launch_bounds__(kWalkThreads, kAsync ? 6 : 1) resize_cubic3_wa
     const uint32_t tap_s[2] = {ring_s + (uint32_t)(aw[0] - span0), ring_s + (uint32_t)(aw[1] - span0)};
     const uint8_t* const spanp = img + span0 + 16 * lane;
     const uint32_t rows_s = (uint32_t)__cvta_generic_to_shared(rows);
-    const uint32_t stage_lane = (uint32_t)__cvta_generic_to_shared(stage) + 6 * lane;
+    const uint32_t stage_lane = (uint32_t)__cvta_generic_to_shared(stage) + 3 * lane;
     const f32x2 one2 = g.one2, negzero2 = g.negzero2, magic2 = g.magic2, negmagic2 = g.negmagic2;
     __syncthreads();
 
@@ -408,16 +410,17 @@ __global__ void __launch_bounds__(kWalkThreads, kAsync ? 6 : 1) resize_cubic3_wa
             v[k][0] = __viaddmin_s32_relu(lo, -0x4B400000, 255);
             v[k][1] = __viaddmin_s32_relu(hi, -0x4B400000, 255);
         }
-        if (staged_store) {   // 6 bytes [bA gA rA bB gB rB] as three 16-bit stores
-            const unsigned p0 = v[0][0] | (v[1][0] << 8), p1 = v[2][0] | (v[0][1] << 8), p2 = v[1][1] | (v[2][1] << 8);
-            asm volatile("st.shared.u16 [%0], %1;" ::"r"(sp), "h"((unsigned short)p0) : "memory");
-            asm volatile("st.shared.u16 [%0+2], %1;" ::"r"(sp), "h"((unsigned short)p1) : "memory");
-            asm volatile("st.shared.u16 [%0+4], %1;" ::"r"(sp), "h"((unsigned short)p2) : "memory");
+        if (staged_store) {   // the two pixels are 32 columns = 96 bytes apart in the staged row
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                asm volatile("st.shared.u8 [%0], %1;" ::"r"(sp + k), "r"(v[k][0]) : "memory");
+                asm volatile("st.shared.u8 [%0], %1;" ::"r"(sp + 96 + k), "r"(v[k][1]) : "memory");
+            }
             sp += kWarpRow;
             if (++staged == kWalkStageRows) flush();
         } else {
             if (dx < g.wo) { gdirect[0] = (uint8_t)v[0][0]; gdirect[1] = (uint8_t)v[1][0]; gdirect[2] = (uint8_t)v[2][0]; }
-            if (dx + 1 < g.wo) { gdirect[3] = (uint8_t)v[0][1]; gdirect[4] = (uint8_t)v[1][1]; gdirect[5] = (uint8_t)v[2][1]; }
+            if (dx + 32 < g.wo) { gdirect[96] = (uint8_t)v[0][1]; gdirect[97] = (uint8_t)v[1][1]; gdirect[98] = (uint8_t)v[2][1]; }
             gdirect += out_row_bytes;
         }
     };
