@@ -338,13 +338,31 @@ struct YuvSource {
 // tiled kernel where one exists), < 0 on error.
 struct Canvas { int w, h, x0, y0; };   // destination plane size and where the w_out x h_out result goes inside it
 
-static int try_launch_pipe(const uint8_t* src, void* dst, int out_dtype, int batch, const YuvSource& y, int w_out, int h_out,
-                           const Canvas& cv, const float* mean, const float* stddev, cudaStream_t s) {
+// Everything about a launch that depends on the shapes only: computed once per (shape, layout, output) and cached per host
+// thread, so that a steady stream of equally shaped calls (one frame or one small batch per call) pays ~nothing on the host.
+struct PipePlan {
+    // key
+    YuvSource y; int w_out, h_out, out_dtype; Canvas cv; bool pairs_ok; int device;
+    // plan
+    bool eligible; PipeGeom g; const void* kern; int threads, per_sm, sms; size_t smem;
+};
+
+static bool same_key(const PipePlan& p, const YuvSource& y, int w_out, int h_out, int out_dtype, const Canvas& cv, bool pairs_ok, int device) {
+    return p.y.fmt == y.fmt && p.y.w == y.w && p.y.h == y.h && p.y.y_pitch == y.y_pitch && p.y.c_pitch == y.c_pitch && p.y.frame_stride == y.frame_stride &&
+           p.y.c_off == y.c_off && p.y.c2_off == y.c2_off && p.w_out == w_out && p.h_out == h_out && p.out_dtype == out_dtype && p.cv.w == cv.w &&
+           p.cv.h == cv.h && p.cv.x0 == cv.x0 && p.cv.y0 == cv.y0 && p.pairs_ok == pairs_ok && p.device == device;
+}
+
+// Fills plan.eligible / g / kern / threads / per_sm / smem.  Returns < 0 on a CUDA error.
+static int build_pipe_plan(PipePlan& plan) {
+    const YuvSource& y = plan.y;
+    const int w_out = plan.w_out, h_out = plan.h_out, out_dtype = plan.out_dtype;
+    const Canvas& cv = plan.cv;
+    plan.eligible = false;
     const bool half_out = out_dtype != VACV_FP32;   // fp16 / bf16: 16-bit table entries
     const int w = y.w, h = y.h;
     // bulk copies need 16-byte granularity of every band start and length
-    if ((y.y_pitch % 16) != 0 || (y.c_pitch % 16) != 0 || (y.frame_stride % 16) != 0 || (y.c_off % 16) != 0 || (y.c2_off % 16) != 0 ||
-        (((uintptr_t)src) & 15) != 0) return 0;
+    if ((y.y_pitch % 16) != 0 || (y.c_pitch % 16) != 0 || (y.frame_stride % 16) != 0 || (y.c_off % 16) != 0 || (y.c2_off % 16) != 0) return 0;
     if (w_out > kPipeThreads * kPipeMaxCols || h_out > 8192) return 0;
     // row source indices, exactly as the device computes them -> exact band sizes per tile
     const double scale_y = (double)((float)h / (float)h_out);
@@ -352,7 +370,7 @@ static int try_launch_pipe(const uint8_t* src, void* dst, int out_dtype, int bat
     for (int d = 0; d < h_out; ++d) sy[d] = host_linear_index(d, scale_y, h);
     const int table_bytes = (2 * h_out * (int)sizeof(int) + 127) & ~127;
     const int static_bytes = 768 * 4 + 64;
-    PipeGeom g;
+    PipeGeom& g = plan.g;
     g.w = w; g.h = h; g.wo = w_out; g.ho = h_out; g.table_bytes = table_bytes;
     g.y_pitch = y.y_pitch; g.c_pitch = y.c_pitch; g.frame_stride = y.frame_stride; g.c_off = y.c_off; g.c2_off = y.c2_off;
     g.canvas_w = cv.w; g.canvas_h = cv.h; g.x0 = cv.x0; g.y0 = cv.y0; g.bf16 = out_dtype == VACV_BF16 ? 1 : 0;
@@ -379,9 +397,7 @@ static int try_launch_pipe(const uint8_t* src, void* dst, int out_dtype, int bat
     if (!best_TH) return 0;
     g.TH = best_TH;
     g.tiles_per_frame = (h_out + best_TH - 1) / best_TH;
-    const long long total = (long long)g.tiles_per_frame * batch;
-    if (total > 0x7fffffffLL - 4096) return 0;
-    g.total_tiles = (int)total;
+    g.total_tiles = 0;   // per call
     // Columns per thread.  Measured on B200 (bench_ops.py c2/c2g): when some right tap has weight (general ratios) the
     // loop is issue-bound and 4 columns per thread (more ILP, less per-row overhead) win; when every cx1 is 0 (odd
     // integer x ratio) the kernel is HBM-bound and 2 columns per thread (twice the warps) win.
@@ -401,26 +417,61 @@ static int try_launch_pipe(const uint8_t* src, void* dst, int out_dtype, int bat
     int ncol = (w_out + kPipeThreads - 1) / kPipeThreads;
     if (any_right && w_out <= 4 * 192) ncol = 4;
     if (const char* e = getenv("VACV_PIPE_NCOL")) { const int v = atoi(e); if (v >= 1 && v <= kPipeMaxCols && (w_out + v - 1) / v <= (v == 1 ? 640 : kPipeThreads)) ncol = v; }   // tuning knob
-    const bool pairs = half_out && (w_out % 2) == 0 && (cv.w % 2) == 0 && (cv.x0 % 2) == 0 && (((uintptr_t)dst) & 3) == 0;   // 16-bit outputs: 32-bit stores of column pairs
+    const bool pairs = half_out && (w_out % 2) == 0 && (cv.w % 2) == 0 && (cv.x0 % 2) == 0 && plan.pairs_ok;   // 16-bit outputs: 32-bit stores of column pairs
     if (pairs) ncol = ncol <= 2 ? 2 : 4;
     const int threads = std::min(ncol == 1 ? 640 : kPipeThreads, ((w_out + ncol - 1) / ncol + 31) & ~31);
     const bool dense = y.y_pitch == w && y.c_pitch == w && y.c_off == (size_t)w * h && y.frame_stride == (size_t)w * h * 3 / 2 &&
                        cv.w == w_out && cv.h == h_out;
     const void* kern = pipe_kernel_for(y.fmt, half_out, pairs, dense, ncol);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)best_smem);
+    // the opt-in limit, not this shape's size: plans of other host threads for the same kernel must stay launchable
+    int optin = 0;
+    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, plan.device);
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, kern);
+    if (e != cudaSuccess) return set_error(VACV_ERR_CUDA, "nv_resize_normalize_chw: %s", cudaGetErrorString(e));
+    const int max_dyn = optin - (int)fa.sharedSizeBytes;   // static + dynamic <= opt-in limit
+    if ((size_t)max_dyn < best_smem) return 0;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
     if (e != cudaSuccess) return set_error(VACV_ERR_CUDA, "nv_resize_normalize_chw: %s", cudaGetErrorString(e));
     int per_sm = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, best_smem);
     if (e != cudaSuccess || per_sm < 1) return 0;
-    int dev = 0, sms = kNumSMs;
+    int sms = kNumSMs;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, plan.device);
+    plan.kern = kern; plan.threads = threads; plan.per_sm = per_sm; plan.sms = sms; plan.smem = best_smem;
+    plan.eligible = true;
+    return 0;
+}
+
+// Returns 1 if the persistent TMA pipeline was launched, 0 if the shape does not qualify (caller falls back to the
+// tiled kernel), < 0 on error.
+static int try_launch_pipe(const uint8_t* src, void* dst, int out_dtype, int batch, const YuvSource& y, int w_out, int h_out,
+                           const Canvas& cv, const float* mean, const float* stddev, cudaStream_t s) {
+    if ((((uintptr_t)src) & 15) != 0) return 0;   // bulk copies need 16-byte aligned band starts
+    static thread_local PipePlan plan = {};
+    static thread_local bool have_plan = false;
+    int dev = 0;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int grid = (int)std::min<long long>(total, (long long)sms * per_sm);
+    const bool pairs_ok = (((uintptr_t)dst) & 3) == 0;
+    if (!have_plan || !same_key(plan, y, w_out, h_out, out_dtype, cv, pairs_ok, dev) || getenv("VACV_PIPE_NCOL")) {
+        have_plan = false;
+        plan.y = y; plan.w_out = w_out; plan.h_out = h_out; plan.out_dtype = out_dtype; plan.cv = cv; plan.pairs_ok = pairs_ok; plan.device = dev;
+        const int rc = build_pipe_plan(plan);
+        if (rc < 0) return rc;
+        have_plan = true;
+    }
+    if (!plan.eligible) return 0;
+    PipeGeom g = plan.g;
+    const long long total = (long long)g.tiles_per_frame * batch;
+    if (total > 0x7fffffffLL - 4096) return 0;
+    g.total_tiles = (int)total;
+    const int grid = (int)std::min<long long>(total, (long long)plan.sms * plan.per_sm);
     void* args[] = {(void*)&src, (void*)&dst, (void*)&g, (void*)&mean, (void*)&stddev};
-    e = cudaLaunchKernel(kern, dim3(grid), dim3(threads), args, best_smem, s);
+    const cudaError_t e = cudaLaunchKernel(plan.kern, dim3(grid), dim3(plan.threads), args, plan.smem, s);
     if (e != cudaSuccess) return set_error(VACV_ERR_CUDA, "nv_resize_normalize_chw: %s", cudaGetErrorString(e));
     return 1;
 }
+
 
 template <int FMT>
 static const void* tiled_kernel_for(bool half_out) {
