@@ -741,6 +741,30 @@ def test_cuda_vs_golden_digests(vacv):
     assert not bad, f"CUDA output differs from the reference digest for: {bad}"
 
 
+def test_fused_pipeline_is_cuda_graph_capturable(vacv):
+    """After the first call of a shape the entry point only launches (the plan is cached): it can be captured and replayed."""
+    w, h, wo, ho, b = 1280, 720, 640, 384, 4
+    mean, std = dev(MEAN), dev(STD)
+    src = _gpu_rand_u8(31, b, w * h * 3 // 2)
+    out = torch.empty((b, 3, ho, wo), dtype=torch.float32, device="cuda")
+    vacv.nv_resize_normalize_chw(src, w, h, wo, ho, mean, std, True, out=out)          # builds the plan
+    want = out.clone()
+    out.zero_()
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            vacv.nv_resize_normalize_chw(src, w, h, wo, ho, mean, std, True, out=out)
+    torch.cuda.current_stream().wait_stream(side)
+    src2 = _gpu_rand_u8(32, b, w * h * 3 // 2)
+    src.copy_(src2)                                                                   # new input, same buffers
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, vacv.nv_resize_normalize_chw(src2, w, h, wo, ho, mean, std, True))
+    assert not torch.equal(out, want)
+
+
 def test_host_buffer_pipeline_entry(vacv, oracle):
     """vacv_cuda_nv_resize_normalize_chw_host: host pointers in/out, chunked + pipelined inside the library."""
     w, h, wo, ho, b = 640, 360, 224, 224, 7
