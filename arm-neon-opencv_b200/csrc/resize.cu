@@ -259,6 +259,56 @@ __global__ void __launch_bounds__(kTileX * kTileY) resize_linear_f32_kernel(cons
                __ldg(lb + g.c + k) * cx1 * cy1;
 }
 
+// a6 for interleaved 3-channel fp32 (HWC): same arithmetic as resize_linear_f32_kernel, but a warp owns 32 consecutive output
+// pixels of a row for 4 passes (coefficients in registers), issues the 12 tap loads of a pixel before any use, and re-chunks its
+// 96 output floats through shared memory into three lane-contiguous 128-byte stores (the generic kernel's three 12-byte-strided
+// stores per lane cost 3-4 LSU wavefronts each).
+__global__ void __launch_bounds__(kTileX * kTileY) resize_linear_f32c3_kernel(const float* __restrict__ src, float* __restrict__ dst, ResizeGeom g) {
+    __shared__ int s_sx[kTileX], s_sy[kC3Rows];
+    __shared__ float s_fx[kTileX], s_fy[kC3Rows];
+    __shared__ __align__(16) float stage[kTileY][96];
+    const int dx0 = blockIdx.x * kTileX, dy00 = blockIdx.y * kC3Rows;
+    const int t = threadIdx.y * kTileX + threadIdx.x;
+    if (t < kTileX + kC3Rows) {
+        const bool isx = t < kTileX;
+        const int d = isx ? dx0 + t : dy00 + (t - kTileX);
+        const int n_in = isx ? g.w : g.h, n_out = isx ? g.wo : g.ho;
+        int s; float f;
+        linear_coord(min(d, n_out - 1), (double)((float)n_in / (float)n_out), n_in, s, f);
+        if (isx) { s_sx[t] = s; s_fx[t] = f; } else { s_sy[t - kTileX] = s; s_fy[t - kTileX] = f; }
+    }
+    __syncthreads();
+    const int lane = threadIdx.x;
+    const int n = min(32, g.wo - dx0);
+    const int sx = s_sx[lane];
+    const float fx = s_fx[lane], cx0 = 1.f - fx, cx1 = fx;
+    const float* img = src + blockIdx.z * g.src_image;
+    float* sb = stage[threadIdx.y];
+    for (int pass = 0; pass < kC3Rows / kTileY; ++pass) {
+        const int ry = pass * kTileY + threadIdx.y, dy = dy00 + ry;
+        if (dy >= g.ho) break;   // whole warp
+        const float fy = s_fy[ry], cy0 = 1.f - fy, cy1 = fy;
+        float v[3] = {0.f, 0.f, 0.f};
+        if (lane < n) {
+            const float* lt = img + ((size_t)s_sy[ry] * g.w + sx) * 3;
+            const float* lb = lt + (size_t)g.w * 3;
+            float a[6], b[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) { a[i] = __ldg(lt + i); b[i] = __ldg(lb + i); }
+#pragma unroll
+            for (int k = 0; k < 3; ++k)   // resize_naive.cpp:121-124 evaluation order
+                v[k] = a[k] * cx0 * cy0 + b[k] * cx0 * cy1 + a[3 + k] * cx1 * cy0 + b[3 + k] * cx1 * cy1;
+        }
+        sb[3 * lane] = v[0]; sb[3 * lane + 1] = v[1]; sb[3 * lane + 2] = v[2];
+        __syncwarp();
+        float* o = dst + blockIdx.z * g.dst_image + ((size_t)dy * g.wo + dx0) * 3;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            if (lane + 32 * k < 3 * n) st_stream4f(o + lane + 32 * k, sb[lane + 32 * k]);
+        __syncwarp();
+    }
+}
+
 // ----------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kTileX * kTileY) resize_cubic_f32_kernel(const float* __restrict__ src,
                                                                             float* __restrict__ dst, ResizeGeom g) {
@@ -429,6 +479,9 @@ extern "C" int vacv_cuda_resize(const void* src, void* dst, int batch, int w, in
             if (flags & VACV_FLAG_NEON_RULE) resize_linear_u8_kernel<false, true><<<grid, block, 0, s>>>(sp, dp, g);
             else if (sc) resize_linear_u8_kernel<true, false><<<grid, block, 0, s>>>(sp, dp, g);
             else resize_linear_u8_kernel<false, false><<<grid, block, 0, s>>>(sp, dp, g);
+        } else if (!cubic && g.c == 3) {
+            grid.y = ceil_div(h_out, kC3Rows);
+            resize_linear_f32c3_kernel<<<grid, block, 0, s>>>((const float*)sp, (float*)dp, g);
         } else if (!cubic) {
             resize_linear_f32_kernel<<<grid, block, 0, s>>>((const float*)sp, (float*)dp, g);
         } else if (dtype == VACV_FP32) {
