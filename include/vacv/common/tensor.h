@@ -25,54 +25,58 @@ enum DLayout { NCHW = 0, NHWC = 1 };                                     // tens
 
 class Tensor {
 public:
-    // -- owning constructors (allocate); two argument orders exist in the reference and both are kept
-    Tensor();
-    explicit Tensor(int w, DLayout layout = NCHW, DType dtype = FP32);
-    Tensor(int w, int h, DLayout layout = NCHW, DType dtype = FP32);
-    Tensor(int w, int h, int c, DLayout layout = NCHW, DType type = FP32);
-    explicit Tensor(int w, DType dtype = FP32, DLayout layout = NCHW);
-    Tensor(int w, int h, DType dtype = FP32, DLayout layout = NCHW);
-    Tensor(int w, int h, int c, DType type = FP32, DLayout layout = NCHW);
-    // -- borrowing constructors (wrap caller memory, never freed here)
-    Tensor(int w, void* data, DType dtype = FP32, DLayout layout = NCHW);
-    Tensor(int w, int h, void* data, DType dtype = FP32, DLayout layout = NCHW);
-    Tensor(int w, int h, int c, void* data, DType type = FP32, DLayout layout = NCHW);
-    Tensor(int w, void* data, DLayout layout = NCHW, DType dtype = FP32);
-    Tensor(int w, int h, void* data, DLayout layout = NCHW, DType dtype = FP32);
-    Tensor(int w, int h, int c, void* data, DLayout layout = NCHW, DType type = FP32);
-
-    Tensor(const Tensor& t);
-    ~Tensor();
-    Tensor& operator=(const Tensor& t);
-
-    Tensor clone() const;
-    Tensor change_layout(DLayout layout);   // HWC <-> CHW; c == 1 or same layout -> clone
-    Tensor change_dtype(DType dtype);       // INT8 <-> FP32 (fp32 -> u8 truncates); same dtype -> clone
-
-    void create(int w, DType dtype = FP32, DLayout layout = NCHW);
-    void create(int w, int h, DType dtype = FP32, DLayout layout = NCHW);
-    void create(int w, int h, int c, DType dtype = FP32, DLayout layout = NCHW);
-    void create(int w, DLayout layout = NCHW, DType dtype = FP32);
-    void create(int w, int h, DLayout layout = NCHW, DType dtype = FP32);
-    void create(int w, int h, int c, DLayout layout = NCHW, DType dtype = FP32);
-    void release();
-
-    bool empty() const;
-    size_t size() const;   // elements
-    size_t len() const;    // bytes
-    void set_name(const std::string& name);
-    std::string get_name() const;
-    int get_ref_count() const;
-
-    // public data, order fixed by the ABI
-    int w;
-    int h;
-    int c;
-    int stride;
-    int dims;
-    void* data;
+    // ---- data: public, read directly by callers; this order IS the binary interface (reference tensor.h:71-78)
+    int w, h, c;        // width, height, channels
+    int stride;         // elements per channel plane = w * h
+    int dims;           // 1, 2 or 3
+    void* data;         // host pointer, dense
     DType dtype;
     DLayout layout;
+
+    // ---- lifetime
+    Tensor();
+    Tensor(const Tensor& other);
+    Tensor& operator=(const Tensor& other);
+    ~Tensor();
+
+    // owning: allocate width [x height [x channels]] elements; the reference offers both (layout, dtype) and
+    // (dtype, layout) argument orders and both are kept
+    explicit Tensor(int width, DLayout arrangement = NCHW, DType element = FP32);
+    explicit Tensor(int width, DType element = FP32, DLayout arrangement = NCHW);
+    Tensor(int width, int height, DLayout arrangement = NCHW, DType element = FP32);
+    Tensor(int width, int height, DType element = FP32, DLayout arrangement = NCHW);
+    Tensor(int width, int height, int channels, DLayout arrangement = NCHW, DType element = FP32);
+    Tensor(int width, int height, int channels, DType element = FP32, DLayout arrangement = NCHW);
+
+    // borrowing: wrap caller memory, never freed here
+    Tensor(int width, void* memory, DType element = FP32, DLayout arrangement = NCHW);
+    Tensor(int width, void* memory, DLayout arrangement = NCHW, DType element = FP32);
+    Tensor(int width, int height, void* memory, DType element = FP32, DLayout arrangement = NCHW);
+    Tensor(int width, int height, void* memory, DLayout arrangement = NCHW, DType element = FP32);
+    Tensor(int width, int height, int channels, void* memory, DType element = FP32, DLayout arrangement = NCHW);
+    Tensor(int width, int height, int channels, void* memory, DLayout arrangement = NCHW, DType element = FP32);
+
+    // (re)allocate; a no-op when shape, dtype and layout already match
+    void create(int width, int height, int channels, DType element = FP32, DLayout arrangement = NCHW);
+    void create(int width, int height, int channels, DLayout arrangement = NCHW, DType element = FP32);
+    void create(int width, int height, DType element = FP32, DLayout arrangement = NCHW);
+    void create(int width, int height, DLayout arrangement = NCHW, DType element = FP32);
+    void create(int width, DType element = FP32, DLayout arrangement = NCHW);
+    void create(int width, DLayout arrangement = NCHW, DType element = FP32);
+    void release();
+
+    // ---- queries
+    bool empty() const;
+    size_t size() const;                      // elements
+    size_t len() const;                       // bytes
+    int get_ref_count() const;
+    std::string get_name() const;
+    void set_name(const std::string& name);
+
+    // ---- conversions (run on the GPU)
+    Tensor clone() const;
+    Tensor change_dtype(DType element);       // INT8 <-> FP32 (fp32 -> u8 truncates); same dtype -> clone
+    Tensor change_layout(DLayout arrangement);   // HWC <-> CHW; c == 1 or same layout -> clone
 
 private:
     void add_ref() const;

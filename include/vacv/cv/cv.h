@@ -51,51 +51,49 @@ enum InputImageFormat { COLOR_GRAY2RGB = 8, COLOR_GRAY2BGR = COLOR_GRAY2RGB, COL
                         COLOR_YUV2RGBA_NV12 = 94, COLOR_YUV2BGRA_NV12 = 95, COLOR_YUV2RGBA_NV21 = 96,
                         COLOR_YUV2BGRA_NV21 = 97, COLOR_YUV2BGR_YV12 = 99 };
 
-// INTER_LINEAR (u8 / fp32) and INTER_CUBIC (fp32; u8 = OpenCV-2.4 rule, HWC); dst takes src's dtype and layout.
-void resize(const vision::Tensor& src, vision::Tensor& dst, VSize dsize, double fx = 0, double fy = 0,
-            int interpolation = INTER_LINEAR);
+typedef vision::Tensor VTensor;   // shorthand for the declarations below (same type, same mangled names)
 
-// NV21 / NV12 (w x h*3/2, one channel) -> BGR HWC u8.
-void cvt_color(const vision::Tensor& src, vision::Tensor& dst, int code);
-
-// (x - mean[k]) / (stddev[k] + 1e-6) -> fp32, layout kept; both statistics empty => computed per channel.
-void normalize(const vision::Tensor& src, vision::Tensor& dst, const vision::Tensor& mean = vision::Tensor(),
-               const vision::Tensor& stddev = vision::Tensor());
-
-// Bilinear warp with the forward 2x3 matrix M (fp32 tensor, 6 values).
-void warp_affine(const vision::Tensor& src, vision::Tensor& dst, const vision::Tensor& M, VSize dsize,
-                 int flags = INTER_LINEAR, int borderMode = BORDER_CONSTANT, const VScalar& borderValue = VScalar());
-
-// Same, M built from scale / rotation (degrees) about the origin plus the aux translation (v0..v3).
-void warp_affine(const vision::Tensor& src, vision::Tensor& dst, float scale, float rot, VSize dsize,
-                 const VScalar& aux_param = VScalar(), int flags = INTER_LINEAR, int borderMode = BORDER_CONSTANT,
-                 const VScalar& borderValue = VScalar());
-
-// Fused resize -> fp32 -> normalize (u8 HWC input), one kernel.
-void resize_normalize(const vision::Tensor& src, vision::Tensor& dst, VSize dsize, double fx = 0, double fy = 0,
-                      int interpolation = INTER_LINEAR, const vision::Tensor& mean = vision::Tensor(),
-                      const vision::Tensor& stddev = vision::Tensor());
-
-// Fused warp_affine -> fp32 -> normalize (u8 HWC input), one kernel.
-void warp_affine_normalize(const vision::Tensor& src, vision::Tensor& dst, const vision::Tensor& M, VSize dsize,
-                           int flags = INTER_LINEAR, int borderMode = BORDER_CONSTANT,
-                           const VScalar& borderValue = VScalar(), const vision::Tensor& mean = vision::Tensor(),
-                           const vision::Tensor& stddev = vision::Tensor());
-
-void warp_affine_normalize(const vision::Tensor& src, vision::Tensor& dst, float scale, float rot, VSize dsize,
-                           const VScalar& aux_param = VScalar(), int flags = INTER_LINEAR,
-                           int borderMode = BORDER_CONSTANT, const VScalar& borderValue = VScalar(),
-                           const vision::Tensor& mean = vision::Tensor(), const vision::Tensor& stddev = vision::Tensor());
+// ---- colour, geometry -------------------------------------------------------------------------------------------
+// NV21 / NV12 / YV12 frame (w x h*3/2, one channel, u8) -> BGR HWC u8.
+void cvt_color(const VTensor& yuv, VTensor& bgr, int code);
 
 // ROI copy; rect edges are truncated to int like the reference (crop.cpp:128-131).
-void crop(const vision::Tensor& src, vision::Tensor& dst, const vision::VRect& rect);
+void crop(const VTensor& image, VTensor& roi, const vision::VRect& rect);
 
-// Declared for link compatibility; like the reference without USE_OPENCV these have no native implementation
-// (match_template.cpp:48-60, imencode.cpp:11-15) and do nothing.
-void match_template(const vision::Tensor& src, const vision::Tensor& target, vision::Tensor& result, int method);
-void minMaxIdx(const vision::Tensor& src, double* minVal, double* maxVal, int* minIdx = nullptr, int* maxIdx = nullptr,
-               const vision::Tensor& mask = vision::Tensor());
-void imencode(const vision::Tensor& src, std::vector<unsigned char>& buf, const char* format);
+// INTER_LINEAR (u8 / fp32) and INTER_CUBIC (fp32; u8 = OpenCV-2.4 rule, HWC).  The result takes the input's dtype and layout;
+// scale_x / scale_y are accepted and ignored like in the reference's native paths.
+void resize(const VTensor& image, VTensor& resized, VSize out_size, double scale_x = 0, double scale_y = 0,
+            int interpolation = INTER_LINEAR);
+
+// Bilinear warp with the forward 2x3 matrix (fp32 tensor, 6 values); the matrix is overwritten with its inverse.
+void warp_affine(const VTensor& image, VTensor& warped, const VTensor& matrix, VSize out_size, int flags = INTER_LINEAR,
+                 int border_mode = BORDER_CONSTANT, const VScalar& border_value = VScalar());
+// Same, the matrix built from scale / rotation (degrees) about the origin plus the aux translation (v0..v3).
+void warp_affine(const VTensor& image, VTensor& warped, float scale, float rotation_deg, VSize out_size,
+                 const VScalar& aux = VScalar(), int flags = INTER_LINEAR, int border_mode = BORDER_CONSTANT,
+                 const VScalar& border_value = VScalar());
+
+// ---- statistics, normalisation -------------------------------------------------------------------------------------
+// (x - mean[k]) / (stddev[k] + 1e-6) -> fp32, layout kept; both statistics empty => computed per channel from the image.
+void normalize(const VTensor& image, VTensor& normalized, const VTensor& mean = VTensor(), const VTensor& stddev = VTensor());
+
+// ---- fused variants (u8 HWC input, one kernel each) -------------------------------------------------------------
+void resize_normalize(const VTensor& image, VTensor& out, VSize out_size, double scale_x = 0, double scale_y = 0,
+                      int interpolation = INTER_LINEAR, const VTensor& mean = VTensor(), const VTensor& stddev = VTensor());
+void warp_affine_normalize(const VTensor& image, VTensor& out, const VTensor& matrix, VSize out_size, int flags = INTER_LINEAR,
+                           int border_mode = BORDER_CONSTANT, const VScalar& border_value = VScalar(),
+                           const VTensor& mean = VTensor(), const VTensor& stddev = VTensor());
+void warp_affine_normalize(const VTensor& image, VTensor& out, float scale, float rotation_deg, VSize out_size,
+                           const VScalar& aux = VScalar(), int flags = INTER_LINEAR, int border_mode = BORDER_CONSTANT,
+                           const VScalar& border_value = VScalar(), const VTensor& mean = VTensor(), const VTensor& stddev = VTensor());
+
+// ---- declared for link compatibility ---------------------------------------------------------------------------
+// Like the reference without USE_OPENCV these have no native implementation (match_template.cpp:48-60, imencode.cpp:11-15)
+// and do nothing.
+void imencode(const VTensor& image, std::vector<unsigned char>& bytes, const char* format);
+void match_template(const VTensor& image, const VTensor& pattern, VTensor& scores, int method);
+void minMaxIdx(const VTensor& values, double* min_value, double* max_value, int* min_index = nullptr, int* max_index = nullptr,
+               const VTensor& mask = VTensor());
 
 }  // namespace va_cv
 
