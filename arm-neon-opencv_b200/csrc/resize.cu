@@ -5,9 +5,14 @@
 // --fmad=false), so the entry points are stateless like the reference's.  A CTA owns a 32x8 tile of output
 // pixels of one image; x-coefficients are computed once per column and y-coefficients once per row of the tile
 // into shared memory, then each thread gathers its taps through the read-only path.
+#include <vector>
+#include <cmath>
+#include <cstdlib>
+#include <algorithm>
 #include "vacv_common.cuh"
 #include "resize_coeffs.cuh"
 #include "gather_u8c3.cuh"
+#include "resize_pipe_u8c3.cuh"
 
 namespace vacv {
 
@@ -417,6 +422,87 @@ int try_launch_resize_tiled(int kind, const void* src, void* dst, int images, in
 }
 using namespace vacv;
 
+// Host copy of linear_coord's source index (identical IEEE arithmetic on x86-64: no FMA, same rounding).
+static int host_linear_index_r(int d, double scale, int n_in) {
+    float fx = (float)(((double)d + 0.5) * scale - 0.5);
+    int sx = (int)floorf(fx);
+    if (sx < 0) sx = 0;
+    if (sx >= n_in - 1) sx = n_in - 2;
+    return sx;
+}
+
+template <bool kSigned>
+static const void* resize_pipe_kernel_for(int ncol) {
+    switch (ncol) {
+        case 1: return (const void*)resize_linear_u8c3_pipe_kernel<kSigned, 1>;
+        case 2: return (const void*)resize_linear_u8c3_pipe_kernel<kSigned, 2>;
+        case 3: return (const void*)resize_linear_u8c3_pipe_kernel<kSigned, 3>;
+        default: return (const void*)resize_linear_u8c3_pipe_kernel<kSigned, 4>;
+    }
+}
+
+// Persistent TMA kernel for u8 BGR bilinear (resize_pipe_u8c3.cuh).  1 = launched, 0 = shape not eligible, < 0 = error.
+static int try_launch_resize_pipe_u8c3(const uint8_t* src, uint8_t* dst, int images, int w, int h, int wo, int ho, bool signed_char, cudaStream_t s) {
+    if (((size_t)w * 3) % 16 != 0 || ((uintptr_t)src & 15) != 0) return 0;          // bulk copies: 16-byte granularity
+    if (wo > kRpThreads * kRpMaxCols || ho > 8192 || h > 2 * ho) return 0;           // larger vertical ratios leave rows unused: gather kernel
+    const double scale_y = (double)((float)h / (float)ho);
+    std::vector<int> sy(ho);
+    bool any_low = false;
+    for (int d = 0; d < ho; ++d) {
+        sy[d] = host_linear_index_r(d, scale_y, h);
+        float fy = (float)(((double)d + 0.5) * scale_y - 0.5);
+        int s0 = (int)floorf(fy);
+        fy -= (float)s0;
+        if (s0 < 0) fy = 0.f;
+        if (s0 >= h - 1) fy = 1.f;
+        const float x = 2048.f * fy;
+        any_low = any_low || (int)(x + (x >= 0.f ? 0.5f : -0.5f)) != 0;
+    }
+    if (!any_low) return 0;                                                           // integer ratios: the gather kernel skips the unused rows
+    const size_t row_bytes = (size_t)w * 3;
+    ResizePipeGeom g;
+    g.w = w; g.h = h; g.wo = wo; g.ho = ho;
+    g.src_image = row_bytes * h; g.dst_image = (size_t)wo * ho * 3;
+    g.table_bytes = (2 * ho * (int)sizeof(int) + 127) & ~127;
+    int ncol = (wo + kRpThreads - 1) / kRpThreads;
+    if (ncol < 2) ncol = 2;
+    if (const char* e = getenv("VACV_RPIPE_NCOL")) { const int v = atoi(e); if (v >= 1 && v <= kRpMaxCols && (wo + v - 1) / v <= kRpThreads) ncol = v; }   // tuning knob
+    const int threads = std::min(kRpThreads, ((wo + ncol - 1) / ncol + 31) & ~31);
+    const size_t lines = (size_t)(threads / 32) * ncol * 96;
+    int best_TH = 0; size_t best_smem = 0;
+    for (int TH = 8; TH >= 1; --TH) {
+        int rows = 0;
+        for (int d0 = 0; d0 < ho; d0 += TH) rows = std::max(rows, sy[std::min(d0 + TH, ho) - 1] + 1 - sy[d0] + 1);
+        const size_t stage = ((size_t)rows * row_bytes + 16 + 127) & ~(size_t)127;
+        const size_t smem = g.table_bytes + 2 * stage + lines;
+        if (smem + 64 <= 113 * 1024 || (TH == 1 && smem + 64 <= 226 * 1024)) { best_TH = TH; best_smem = smem; g.stage_bytes = (int)stage; break; }
+    }
+    if (!best_TH) return 0;
+    g.TH = best_TH;
+    g.tiles_per_frame = (ho + best_TH - 1) / best_TH;
+    const long long total = (long long)g.tiles_per_frame * images;
+    if (total > 0x7fffffffLL - 4096) return 0;
+    g.total_tiles = (int)total;
+    const void* kern = signed_char ? resize_pipe_kernel_for<true>(ncol) : resize_pipe_kernel_for<false>(ncol);
+    int dev = 0, optin = 0, sms = kNumSMs, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, kern);
+    if (e != cudaSuccess) return set_error(VACV_ERR_CUDA, "resize: %s", cudaGetErrorString(e));
+    if ((size_t)(optin - (int)fa.sharedSizeBytes) < best_smem) return 0;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+    if (e != cudaSuccess) return set_error(VACV_ERR_CUDA, "resize: %s", cudaGetErrorString(e));
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, best_smem);
+    if (e != cudaSuccess || per_sm < 1) return 0;
+    const int grid = (int)std::min<long long>(total, (long long)sms * per_sm);
+    void* args[] = {(void*)&src, (void*)&dst, (void*)&g};
+    e = cudaLaunchKernel(kern, dim3(grid), dim3(threads), args, best_smem, s);
+    if (e != cudaSuccess) return set_error(VACV_ERR_CUDA, "resize: %s", cudaGetErrorString(e));
+    return 1;
+}
+
 extern "C" int vacv_cuda_resize(const void* src, void* dst, int batch, int w, int h, int c, int dtype, int layout,
                                 int w_out, int h_out, int interpolation, int flags, void* stream) {
     VACV_REQUIRE(src && dst, "resize: null pointer");
@@ -461,6 +547,11 @@ extern "C" int vacv_cuda_resize(const void* src, void* dst, int batch, int w, in
         const uint8_t* sp = (const uint8_t*)src + (size_t)i0 * g.src_image * es;
         uint8_t* dp = (uint8_t*)dst + (size_t)i0 * g.dst_image * es;
         const bool c3_words = g.c == 3 && (((size_t)w * h * 3) % 4) == 0 && ((uintptr_t)src % 4) == 0 && (size_t)w * h * 3 < 0xfffffff0ull;
+        if (!cubic && dtype == VACV_INT8 && c3_words && !(flags & (VACV_FLAG_NEON_RULE | VACV_FLAG_DIRECT_GATHER)) && !getenv("VACV_NO_RPIPE")) {
+            const int rc = try_launch_resize_pipe_u8c3(sp, dp, ni, w, h, w_out, h_out, (flags & VACV_FLAG_SIGNED_CHAR) != 0, s);
+            if (rc < 0) return rc;
+            if (rc > 0) continue;
+        }
         if (!cubic && dtype == VACV_INT8 && c3_words) {
             const bool sc = flags & VACV_FLAG_SIGNED_CHAR;
             grid.y = ceil_div(h_out, kC3Rows);

@@ -1,0 +1,149 @@
+// a5 for interleaved 3-channel u8 at small vertical ratios (every source row is a tap of some output row): persistent
+// CTAs + TMA band staging, the structure of the fused NV12 pipeline (fused_pipeline.cuh) applied to plain BGR resize.
+//
+// The gather kernel (resize_linear_u8c3_kernel) costs ~100 instructions per output pixel because every pixel fetches and
+// blends its four taps from scratch.  Here a CTA owns tiles of TH output rows x the full width of one frame; the tile's
+// source rows -- one contiguous byte range, rows are dense -- arrive by ONE bulk copy (cp.async.bulk, UBLKCP) into one of two
+// shared-memory stages while the previous tile is computed.  A thread owns NCOL output columns and walks down the rows:
+//   * the horizontally blended sums of a source row (two aligned 32-bit shared loads + funnel shift -> PRMT -> three
+//     IDP.2A with the packed 16-bit weights) are computed ONCE per source row and column; when the next output row starts
+//     on the previous lower row, its sums are carried over instead of recomputed;
+//   * vertical blend = the reference's integer expression regrouped row-wise, (Ht*cy0 + Hb*cy1) >> 22
+//     (resize_naive.cpp:60-65; same integer, < 2^31);
+//   * a warp's 32 consecutive output pixels are re-chunked through a private shared-memory line into one lane-contiguous
+//     96-byte store.
+// Integer-ratio / large-ratio shapes (most source rows unused) stay on the gather kernel, which never reads those rows.
+#pragma once
+#include "fused_pipeline.cuh"
+#include "gather_u8c3.cuh"
+
+namespace vacv {
+
+constexpr int kRpThreads = 384;   // max threads per CTA
+constexpr int kRpMaxCols = 4;     // output columns per thread
+
+struct ResizePipeGeom {
+    int w, h, wo, ho;
+    int TH, tiles_per_frame, total_tiles;
+    int stage_bytes;        // bytes reserved per stage (multiple of 128)
+    int table_bytes;        // row tables at the start of dynamic shared memory (multiple of 128)
+    size_t src_image, dst_image;   // bytes between images
+};
+
+template <bool kSigned, int NCOL>
+__global__ void __launch_bounds__(kRpThreads, NCOL <= 2 ? 2 : 1)
+resize_linear_u8c3_pipe_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, ResizePipeGeom g) {
+    extern __shared__ __align__(128) uint8_t dyn_smem[];     // [s_sy: ho][s_cy: ho][pad] 2 x stage, then per-warp output lines
+    int* s_sy = reinterpret_cast<int*>(dyn_smem);
+    int* s_cy = s_sy + g.ho;
+    uint8_t* stages = dyn_smem + g.table_bytes;
+    __shared__ __align__(8) uint64_t full_bar[2];
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t* line = reinterpret_cast<uint32_t*>(stages + 2 * (size_t)g.stage_bytes) + warp * (NCOL * 24);   // per warp: NCOL x 96 bytes
+    const unsigned row_bytes = (unsigned)g.w * 3u;
+    const uint32_t stages_s = smem_u32(stages), sy_s = smem_u32(s_sy), cy_s = smem_u32(s_cy);
+
+    if (tid == 0) {
+        mbar_init(&full_bar[0], 1);
+        mbar_init(&full_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const double scale_x = (double)((float)g.w / (float)g.wo), scale_y = (double)((float)g.h / (float)g.ho);
+    for (int dy = tid; dy < g.ho; dy += nthr) {
+        int s; float f;
+        linear_coord(dy, scale_y, g.h, s, f);
+        s_sy[dy] = s;
+        s_cy[dy] = sat_short((1.f - f) * 2048.f) | (sat_short(2048.f * f) << 16);
+    }
+    __syncthreads();
+    // thread t owns columns t, t + nthr, ...; columns past the row end are clamped (computed, not stored)
+    unsigned aw[NCOL];      // byte offset of the aligned word holding the first tap byte, inside a source row
+    int sh[NCOL];           // bit shift of the first tap byte inside that word
+    uint32_t cx[NCOL];      // cx0 | cx1 << 16
+#pragma unroll
+    for (int j = 0; j < NCOL; ++j) {
+        const int dx = min(tid + j * nthr, g.wo - 1);
+        int sx; float fx;
+        linear_coord(dx, scale_x, g.w, sx, fx);
+        cx[j] = (uint32_t)(sat_short((1.f - fx) * 2048.f) & 0xffff) | ((uint32_t)sat_short(2048.f * fx) << 16);
+        aw[j] = ((unsigned)sx * 3u) & ~3u;
+        sh[j] = (int)(((unsigned)sx * 3u) & 3u) * 8;
+    }
+
+    auto issue = [&](int tile, int b) {   // one thread
+        const int frame = tile / g.tiles_per_frame, dy0 = (tile - frame * g.tiles_per_frame) * g.TH;
+        const int th = min(g.TH, g.ho - dy0);
+        const int y_first = s_sy[dy0], y_last = s_sy[dy0 + th - 1] + 1;
+        const uint32_t bytes = (uint32_t)(y_last - y_first + 1) * row_bytes;
+        mbar_expect_tx(&full_bar[b], bytes);
+        bulk_g2s(stages + (size_t)b * g.stage_bytes, src + (size_t)frame * g.src_image + (size_t)y_first * row_bytes, bytes, &full_bar[b]);
+    };
+    // horizontal sums of one source row for this thread's columns
+    auto hrow = [&](uint32_t rowaddr, int (&H)[NCOL][3]) {
+#pragma unroll
+        for (int j = 0; j < NCOL; ++j) {
+            const uint32_t p = rowaddr + aw[j];
+            uint32_t w0, w1, w2;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(p));
+            asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(p));
+            asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(w2) : "r"(p));   // inside the stage (rows are followed by rows or slack)
+            const uint32_t b0 = __funnelshift_r(w0, w1, sh[j]), b1 = __funnelshift_r(w1, w2, sh[j]);
+            hsum_u8c3<kSigned>(b0, b1, cx[j], H[j]);
+        }
+    };
+
+    int tile = blockIdx.x;
+    if (tid == 0 && tile < g.total_tiles) issue(tile, 0);
+    __syncthreads();
+    const int n_last = g.wo - (g.wo & ~31);   // valid pixels in the last, partial warp of a row (0: none partial)
+
+    for (int it = 0; tile < g.total_tiles; tile += gridDim.x, ++it) {
+        const int b = it & 1;
+        const int next = tile + gridDim.x;
+        if (tid == 0 && next < g.total_tiles) issue(next, b ^ 1);   // stage b^1 was released by the sync below
+        mbar_wait(&full_bar[b], (it >> 1) & 1);
+        const int frame = tile / g.tiles_per_frame, dy0 = (tile - frame * g.tiles_per_frame) * g.TH;
+        const int th = min(g.TH, g.ho - dy0);
+        const uint32_t buf = stages_s + b * g.stage_bytes;
+        const int y_first = lds_s32(sy_s + 4 * dy0);
+        uint8_t* orow = dst + (size_t)frame * g.dst_image + (size_t)dy0 * g.wo * 3;
+        int H0[NCOL][3], H1[NCOL][3];
+        int have = -2;
+        for (int ty = 0; ty < th; ++ty, orow += (size_t)g.wo * 3) {
+            const int sy = lds_s32(sy_s + 4 * (dy0 + ty));
+            const int cy = lds_s32(cy_s + 4 * (dy0 + ty));
+            const int cy0 = (short)(cy & 0xffff), cy1 = cy >> 16;
+            if (sy == have) {
+#pragma unroll
+                for (int j = 0; j < NCOL; ++j) { H0[j][0] = H1[j][0]; H0[j][1] = H1[j][1]; H0[j][2] = H1[j][2]; }
+            } else if (sy + 1 != have) {
+                hrow(buf + (unsigned)(sy - y_first) * row_bytes, H0);
+            }
+            if (sy + 1 != have) {
+                hrow(buf + (unsigned)(sy + 1 - y_first) * row_bytes, H1);
+                have = sy + 1;
+            }
+            uint8_t* lb = reinterpret_cast<uint8_t*>(line);
+#pragma unroll
+            for (int j = 0; j < NCOL; ++j) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) lb[j * 96 + 3 * lane + k] = (uint8_t)((H0[j][k] * cy0 + H1[j][k] * cy1) >> 22);   // resize_naive.cpp:60-65
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < NCOL; ++j) {
+                const int c0 = (tid & ~31) + j * nthr;             // first column of this warp's j-th group
+                if (c0 >= g.wo) continue;                          // warp-uniform
+                uint8_t* o = orow + (size_t)c0 * 3;
+                const int n = min(32, g.wo - c0);
+                if (n == 32 && (reinterpret_cast<uintptr_t>(o) & 3) == 0) { if (lane < 24) st_stream4(o + 4 * lane, line[j * 24 + lane]); }
+                else for (int bb = lane; bb < 3 * n; bb += 32) o[bb] = lb[j * 96 + bb];
+            }
+            __syncwarp();
+        }
+        __syncthreads();   // all reads of stage b done -> it may be refilled by the next iteration's issue
+    }
+    (void)n_last;
+}
+
+}  // namespace vacv

@@ -158,6 +158,21 @@ def test_resize_linear_u8(vacv, oracle, layout, sz, path):
     assert_same(got, want)
 
 
+@pytest.mark.parametrize("signed", [False, True])
+@pytest.mark.parametrize("sz", [((1920, 1080), (1280, 720)), ((1920, 1080), (640, 640)), ((1280, 720), (1000, 500)), ((64, 48), (200, 111)),
+                                ((640, 360), (639, 359)), ((640, 360), (1536, 700)), ((1280, 720), (1279, 361)), ((3840, 2160), (1920, 1080))])
+def test_resize_linear_u8_default_path(vacv, oracle, sz, signed):
+    """Default dispatch (no path flag): small vertical ratios run on the persistent TMA kernel (resize_pipe_u8c3.cuh), the rest on
+    the gather kernel; both must equal the oracle."""
+    (w, h), (wo, ho) = sz
+    b = 3
+    src = u8(26, b, h, w, 3)
+    flags = vacv.FLAG_SIGNED_CHAR if signed else 0
+    got = host(vacv.resize(dev(src), NHWC, wo, ho, vacv.INTER_LINEAR, flags))
+    for i in range(b):
+        assert_same(got[i], oracle.resize_linear(src[i], w, h, 3, NHWC, wo, ho, signed_char=int(signed)))
+
+
 def test_resize_linear_u8_config1_fixture_vs_reference(vacv):
     img = load_fixture("universe1920x1080")
     if img is None or not ref_available():
