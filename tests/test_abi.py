@@ -69,3 +69,29 @@ def test_host_matrix_helpers_match_oracle(oracle):
     got = np.array(vacv.rotation_matrix(1.073914, -3.314525, aux), np.float32)
     assert np.array_equal(got.view(np.uint32), oracle.rotation_matrix(1.073914, -3.314525, aux).view(np.uint32))
     assert np.array_equal(np.array(vacv.invert_affine([0, 0, 1, 0, 0, 1]), np.float32)[[0, 4]], [0, 0])   # singular: D = 0
+
+
+def test_argument_validation_of_the_surface_entries_without_gpu():
+    """The decoder-surface / letterbox entry points validate layout, output type and rectangle before any CUDA call."""
+    import vacv_b200 as vacv
+    buf = C.create_string_buffer(256)
+    p = C.cast(buf, C.c_void_p)
+    ok = vacv.YuvLayout(vacv.YUV_NV12, 64, 32, 0, 0, 0)
+    odd = vacv.YuvLayout(vacv.YUV_NV12, 63, 32, 0, 0, 0)
+    badfmt = vacv.YuvLayout(7, 64, 32, 0, 0, 0)
+    small_pitch = vacv.YuvLayout(vacv.YUV_I420, 64, 32, 48, 0, 0)
+    f = vacv.lib.vacv_cuda_yuv_resize_normalize_chw
+    assert f(None, C.addressof(ok), p, vacv.FP32, 1, 32, 16, p, p, None) == -1
+    assert f(p, C.addressof(odd), p, vacv.FP32, 1, 32, 16, p, p, None) == -1
+    assert b"even" in vacv.lib.vacv_cuda_last_error()
+    assert f(p, C.addressof(badfmt), p, vacv.FP32, 1, 32, 16, p, p, None) == -2
+    assert f(p, C.addressof(small_pitch), p, vacv.FP32, 1, 32, 16, p, p, None) == -1
+    assert f(p, C.addressof(ok), p, vacv.INT8, 1, 32, 16, p, p, None) == -2            # output type
+    assert f(p, C.addressof(ok), p, vacv.FP32, 1, 64, 32, p, p, None) == -2            # same-size resize
+    g = vacv.lib.vacv_cuda_yuv_letterbox_normalize_chw
+    outside = vacv.Rect(10, 0, 60, 30)
+    assert g(p, C.addressof(ok), p, vacv.FP32, 1, 64, 64, C.addressof(outside), p, p, p, p, p, None) == -1
+    assert b"outside" in vacv.lib.vacv_cuda_last_error()
+    assert vacv.lib.vacv_cuda_cvt_yuv2bgr(p, C.addressof(odd), p, 1, None) == -1
+    assert vacv.lib.vacv_cuda_yuv_normalize_chw_host(p, C.addressof(ok), p, vacv.FP64, 1, 32, 16, None, None, p, p, 4) == -2
+    assert vacv.letterbox_rect(1920, 1080, 640, 640) == (0, 140, 640, 360)           # pure host helper
