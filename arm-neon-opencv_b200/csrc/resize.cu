@@ -431,23 +431,22 @@ static int host_linear_index_r(int d, double scale, int n_in) {
     return sx;
 }
 
-template <bool kSigned>
+template <bool kSigned, bool kBand>
 static const void* resize_pipe_kernel_for(int ncol) {
     switch (ncol) {
-        case 1: return (const void*)resize_linear_u8c3_pipe_kernel<kSigned, 1>;
-        case 2: return (const void*)resize_linear_u8c3_pipe_kernel<kSigned, 2>;
-        case 3: return (const void*)resize_linear_u8c3_pipe_kernel<kSigned, 3>;
-        default: return (const void*)resize_linear_u8c3_pipe_kernel<kSigned, 4>;
+        case 1: return (const void*)resize_linear_u8c3_pipe_kernel<kSigned, 1, kBand>;
+        case 2: return (const void*)resize_linear_u8c3_pipe_kernel<kSigned, 2, kBand>;
+        case 3: return (const void*)resize_linear_u8c3_pipe_kernel<kSigned, 3, kBand>;
+        default: return (const void*)resize_linear_u8c3_pipe_kernel<kSigned, 4, kBand>;
     }
 }
 
 // Persistent TMA kernel for u8 BGR bilinear (resize_pipe_u8c3.cuh).  1 = launched, 0 = shape not eligible, < 0 = error.
 static int try_launch_resize_pipe_u8c3(const uint8_t* src, uint8_t* dst, int images, int w, int h, int wo, int ho, bool signed_char, cudaStream_t s) {
     if (((size_t)w * 3) % 16 != 0 || ((uintptr_t)src & 15) != 0) return 0;          // bulk copies: 16-byte granularity
-    if (wo > kRpThreads * kRpMaxCols || ho > 8192 || h > 2 * ho) return 0;           // larger vertical ratios leave rows unused: gather kernel
+    if (wo > kRpThreads * kRpMaxCols || ho > 8192) return 0;
     const double scale_y = (double)((float)h / (float)ho);
-    std::vector<int> sy(ho);
-    bool any_low = false;
+    std::vector<int> sy(ho), cy(ho);   // cy: only "lower tap has weight" (bit 16), which is all tile_rows() looks at
     for (int d = 0; d < ho; ++d) {
         sy[d] = host_linear_index_r(d, scale_y, h);
         float fy = (float)(((double)d + 0.5) * scale_y - 0.5);
@@ -456,26 +455,33 @@ static int try_launch_resize_pipe_u8c3(const uint8_t* src, uint8_t* dst, int ima
         if (s0 < 0) fy = 0.f;
         if (s0 >= h - 1) fy = 1.f;
         const float x = 2048.f * fy;
-        any_low = any_low || (int)(x + (x >= 0.f ? 0.5f : -0.5f)) != 0;
+        cy[d] = (int)(x + (x >= 0.f ? 0.5f : -0.5f)) != 0 ? 1 << 16 : 0;
     }
-    if (!any_low) return 0;                                                           // integer ratios: the gather kernel skips the unused rows
+    // measured on B200 (bench_ops.py c1 / ops / ops2): the contiguous-band variant wins for small ratios (1080p -> 720p: gather
+    // 0.254 ms, band 0.162 ms), the row-list variant for integer ratios where no lower tap has weight (1080p -> 640x360: gather
+    // 0.233 ms, row list 0.206 ms); in between (ratio > 2 with live lower taps) the gather kernel is the fastest.
+    bool any_low = false;
+    for (int d = 0; d < ho; ++d) any_low = any_low || cy[d] != 0;
+    const bool band = h <= 2 * ho && any_low;
+    if (!band && any_low) return 0;
     const size_t row_bytes = (size_t)w * 3;
     ResizePipeGeom g;
     g.w = w; g.h = h; g.wo = wo; g.ho = ho;
     g.src_image = row_bytes * h; g.dst_image = (size_t)wo * ho * 3;
-    g.table_bytes = (2 * ho * (int)sizeof(int) + 127) & ~127;
     int ncol = (wo + kRpThreads - 1) / kRpThreads;
     if (ncol < 2) ncol = 2;
     if (const char* e = getenv("VACV_RPIPE_NCOL")) { const int v = atoi(e); if (v >= 1 && v <= kRpMaxCols && (wo + v - 1) / v <= kRpThreads) ncol = v; }   // tuning knob
     const int threads = std::min(kRpThreads, ((wo + ncol - 1) / ncol + 31) & ~31);
     const size_t lines = (size_t)(threads / 32) * ncol * 96;
     int best_TH = 0; size_t best_smem = 0;
-    for (int TH = 8; TH >= 1; --TH) {
-        int rows = 0;
-        for (int d0 = 0; d0 < ho; d0 += TH) rows = std::max(rows, sy[std::min(d0 + TH, ho) - 1] + 1 - sy[d0] + 1);
+    for (int TH = kRpMaxTH; TH >= 1; --TH) {
+        int rows = 0, tmp[2 * kRpMaxTH];
+        for (int d0 = 0; d0 < ho; d0 += TH)
+            rows = std::max(rows, band ? sy[std::min(d0 + TH, ho) - 1] + 1 - sy[d0] + 1 : tile_rows(sy.data(), cy.data(), d0, std::min(TH, ho - d0), tmp, nullptr));
         const size_t stage = ((size_t)rows * row_bytes + 16 + 127) & ~(size_t)127;
-        const size_t smem = g.table_bytes + 2 * stage + lines;
-        if (smem + 64 <= 113 * 1024 || (TH == 1 && smem + 64 <= 226 * 1024)) { best_TH = TH; best_smem = smem; g.stage_bytes = (int)stage; break; }
+        const int table_bytes = ((3 * ho + (band ? 0 : ((ho + TH - 1) / TH) * (1 + 2 * kRpMaxTH))) * (int)sizeof(int) + 127) & ~127;
+        const size_t smem = table_bytes + 2 * stage + lines;
+        if (smem + 64 <= 113 * 1024 || (TH == 1 && smem + 64 <= 226 * 1024)) { best_TH = TH; best_smem = smem; g.stage_bytes = (int)stage; g.table_bytes = table_bytes; break; }
     }
     if (!best_TH) return 0;
     g.TH = best_TH;
@@ -483,7 +489,8 @@ static int try_launch_resize_pipe_u8c3(const uint8_t* src, uint8_t* dst, int ima
     const long long total = (long long)g.tiles_per_frame * images;
     if (total > 0x7fffffffLL - 4096) return 0;
     g.total_tiles = (int)total;
-    const void* kern = signed_char ? resize_pipe_kernel_for<true>(ncol) : resize_pipe_kernel_for<false>(ncol);
+    const void* kern = band ? (signed_char ? resize_pipe_kernel_for<true, true>(ncol) : resize_pipe_kernel_for<false, true>(ncol))
+                            : (signed_char ? resize_pipe_kernel_for<true, false>(ncol) : resize_pipe_kernel_for<false, false>(ncol));
     int dev = 0, optin = 0, sms = kNumSMs, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);

@@ -1,10 +1,12 @@
-// a5 for interleaved 3-channel u8 at small vertical ratios (every source row is a tap of some output row): persistent
-// CTAs + TMA band staging, the structure of the fused NV12 pipeline (fused_pipeline.cuh) applied to plain BGR resize.
+// a5 for interleaved 3-channel u8: persistent CTAs + TMA row staging, the structure of the fused NV12 pipeline
+// (fused_pipeline.cuh) applied to plain BGR resize.
 //
 // The gather kernel (resize_linear_u8c3_kernel) costs ~100 instructions per output pixel because every pixel fetches and
-// blends its four taps from scratch.  Here a CTA owns tiles of TH output rows x the full width of one frame; the tile's
-// source rows -- one contiguous byte range, rows are dense -- arrive by ONE bulk copy (cp.async.bulk, UBLKCP) into one of two
-// shared-memory stages while the previous tile is computed.  A thread owns NCOL output columns and walks down the rows:
+// blends its four taps from scratch.  Here a CTA owns tiles of TH output rows x the full width of one frame; exactly the
+// source rows the tile's outputs give weight to (tile_rows() below: a zero-weight lower tap row is NOT fetched, so an integer
+// ratio such as 1080 -> 360 reads one row in three) arrive by bulk copies (cp.async.bulk, UBLKCP), one per run of consecutive
+// rows, into one of two shared-memory stages while the previous tile is computed.  A thread owns NCOL output columns and
+// walks down the rows:
 //   * the horizontally blended sums of a source row (two aligned 32-bit shared loads + funnel shift -> PRMT -> three
 //     IDP.2A with the packed 16-bit weights) are computed ONCE per source row and column; when the next output row starts
 //     on the previous lower row, its sums are carried over instead of recomputed;
@@ -12,7 +14,6 @@
 //     (resize_naive.cpp:60-65; same integer, < 2^31);
 //   * a warp's 32 consecutive output pixels are re-chunked through a private shared-memory line into one lane-contiguous
 //     96-byte store.
-// Integer-ratio / large-ratio shapes (most source rows unused) stay on the gather kernel, which never reads those rows.
 #pragma once
 #include "fused_pipeline.cuh"
 #include "gather_u8c3.cuh"
@@ -22,6 +23,25 @@ namespace vacv {
 constexpr int kRpThreads = 384;   // max threads per CTA
 constexpr int kRpMaxCols = 4;     // output columns per thread
 
+constexpr int kRpMaxTH = 8;
+
+// The source rows a tile of output rows [dy0, dy0 + th) needs, in increasing order: sy of every output row, and sy + 1 where
+// the lower tap has weight (cy1 != 0).  slot[ty] (optional) = position of output row ty's upper tap row in that list; its
+// lower tap row, when needed, is the next entry.  Shared by the launcher (stage size), the kernel's slot table and the copy
+// issue, so all three agree by construction.  sy / cy: the per-output-row tables (cy = cy0 | cy1 << 16).
+__host__ __device__ inline int tile_rows(const int* sy, const int* cy, int dy0, int th, int* rows, int* slot) {
+    int n = 0;
+    for (int ty = 0; ty < th; ++ty) {
+        const int r = sy[dy0 + ty];
+        int pos = n;
+        for (int i = n - 1; i >= 0 && rows[i] >= r; --i) if (rows[i] == r) pos = i;   // at most two steps back
+        if (pos == n) rows[n++] = r;
+        if (slot) slot[ty] = pos;
+        if ((cy[dy0 + ty] >> 16) != 0 && (pos + 1 >= n || rows[pos + 1] != r + 1)) rows[n++] = r + 1;   // rows stay sorted: r + 1 > everything before
+    }
+    return n;
+}
+
 struct ResizePipeGeom {
     int w, h, wo, ho;
     int TH, tiles_per_frame, total_tiles;
@@ -30,18 +50,23 @@ struct ResizePipeGeom {
     size_t src_image, dst_image;   // bytes between images
 };
 
-template <bool kSigned, int NCOL>
-__global__ void __launch_bounds__(kRpThreads, NCOL <= 2 ? 2 : 1)
+// kBand: every source row between a tile's first and last tap row is needed (small ratios): the stage is that contiguous band,
+// fetched with ONE bulk copy, row slot = row - first row.  !kBand (integer ratios, where no lower tap has weight): only the
+// listed rows are fetched, one bulk copy per run of consecutive rows.
+template <bool kSigned, int NCOL, bool kBand>
+__global__ void __launch_bounds__(kRpThreads, NCOL <= 2 || !kBand ? 2 : 1)
 resize_linear_u8c3_pipe_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, ResizePipeGeom g) {
     extern __shared__ __align__(128) uint8_t dyn_smem[];     // [s_sy: ho][s_cy: ho][pad] 2 x stage, then per-warp output lines
     int* s_sy = reinterpret_cast<int*>(dyn_smem);
     int* s_cy = s_sy + g.ho;
+    int* s_slot = s_cy + g.ho;
+    int* s_tile = s_slot + g.ho;                             // [tiles_per_frame][1 + 2 * kRpMaxTH]: row count, rows
     uint8_t* stages = dyn_smem + g.table_bytes;
     __shared__ __align__(8) uint64_t full_bar[2];
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
     uint32_t* line = reinterpret_cast<uint32_t*>(stages + 2 * (size_t)g.stage_bytes) + warp * (NCOL * 24);   // per warp: NCOL x 96 bytes
     const unsigned row_bytes = (unsigned)g.w * 3u;
-    const uint32_t stages_s = smem_u32(stages), sy_s = smem_u32(s_sy), cy_s = smem_u32(s_cy);
+    const uint32_t stages_s = smem_u32(stages), sy_s = smem_u32(s_sy), cy_s = smem_u32(s_cy), slot_s = smem_u32(s_slot);
 
     if (tid == 0) {
         mbar_init(&full_bar[0], 1);
@@ -54,6 +79,16 @@ resize_linear_u8c3_pipe_kernel(const uint8_t* __restrict__ src, uint8_t* __restr
         linear_coord(dy, scale_y, g.h, s, f);
         s_sy[dy] = s;
         s_cy[dy] = sat_short((1.f - f) * 2048.f) | (sat_short(2048.f * f) << 16);
+    }
+    __syncthreads();
+    for (int tt = tid; tt < (kBand ? 0 : g.tiles_per_frame); tt += nthr) {   // stage slot of every output row's upper tap row
+        int rows[2 * kRpMaxTH], slot[kRpMaxTH];
+        const int dy0 = tt * g.TH, th = min(g.TH, g.ho - dy0);
+        const int n = tile_rows(s_sy, s_cy, dy0, th, rows, slot);
+        for (int ty = 0; ty < th; ++ty) s_slot[dy0 + ty] = slot[ty];
+        int* tl = s_tile + tt * (1 + 2 * kRpMaxTH);            // the copy issue of every tile just replays this list
+        tl[0] = n;
+        for (int i = 0; i < n; ++i) tl[1 + i] = rows[i];
     }
     __syncthreads();
     // thread t owns columns t, t + nthr, ...; columns past the row end are clamped (computed, not stored)
@@ -70,13 +105,27 @@ resize_linear_u8c3_pipe_kernel(const uint8_t* __restrict__ src, uint8_t* __restr
         sh[j] = (int)(((unsigned)sx * 3u) & 3u) * 8;
     }
 
-    auto issue = [&](int tile, int b) {   // one thread
-        const int frame = tile / g.tiles_per_frame, dy0 = (tile - frame * g.tiles_per_frame) * g.TH;
-        const int th = min(g.TH, g.ho - dy0);
-        const int y_first = s_sy[dy0], y_last = s_sy[dy0 + th - 1] + 1;
-        const uint32_t bytes = (uint32_t)(y_last - y_first + 1) * row_bytes;
-        mbar_expect_tx(&full_bar[b], bytes);
-        bulk_g2s(stages + (size_t)b * g.stage_bytes, src + (size_t)frame * g.src_image + (size_t)y_first * row_bytes, bytes, &full_bar[b]);
+    auto issue = [&](int tile, int b) {   // one thread: one bulk copy per run of consecutive source rows
+        const int frame = tile / g.tiles_per_frame;
+        if (kBand) {
+            const int dy0 = (tile - frame * g.tiles_per_frame) * g.TH, th = min(g.TH, g.ho - dy0);
+            const int y_first = s_sy[dy0], y_last = s_sy[dy0 + th - 1] + 1;
+            const uint32_t bytes = (uint32_t)(y_last - y_first + 1) * row_bytes;
+            mbar_expect_tx(&full_bar[b], bytes);
+            bulk_g2s(stages + (size_t)b * g.stage_bytes, src + (size_t)frame * g.src_image + (size_t)y_first * row_bytes, bytes, &full_bar[b]);
+            return;
+        }
+        const int* rows = s_tile + (tile - frame * g.tiles_per_frame) * (1 + 2 * kRpMaxTH) + 1;
+        const int n = rows[-1];
+        mbar_expect_tx(&full_bar[b], (uint32_t)n * row_bytes);
+        const uint8_t* f = src + (size_t)frame * g.src_image;
+        uint8_t* st = stages + (size_t)b * g.stage_bytes;
+        for (int i = 0; i < n;) {
+            int j = i + 1;
+            while (j < n && rows[j] == rows[j - 1] + 1) ++j;
+            bulk_g2s(st + (size_t)i * row_bytes, f + (size_t)rows[i] * row_bytes, (uint32_t)(j - i) * row_bytes, &full_bar[b]);
+            i = j;
+        }
     };
     // horizontal sums of one source row for this thread's columns
     auto hrow = [&](uint32_t rowaddr, int (&H)[NCOL][3]) {
@@ -105,7 +154,7 @@ resize_linear_u8c3_pipe_kernel(const uint8_t* __restrict__ src, uint8_t* __restr
         const int frame = tile / g.tiles_per_frame, dy0 = (tile - frame * g.tiles_per_frame) * g.TH;
         const int th = min(g.TH, g.ho - dy0);
         const uint32_t buf = stages_s + b * g.stage_bytes;
-        const int y_first = lds_s32(sy_s + 4 * dy0);
+        const int y_first = kBand ? lds_s32(sy_s + 4 * dy0) : 0;
         uint8_t* orow = dst + (size_t)frame * g.dst_image + (size_t)dy0 * g.wo * 3;
         int H0[NCOL][3], H1[NCOL][3];
         int have = -2;
@@ -113,15 +162,34 @@ resize_linear_u8c3_pipe_kernel(const uint8_t* __restrict__ src, uint8_t* __restr
             const int sy = lds_s32(sy_s + 4 * (dy0 + ty));
             const int cy = lds_s32(cy_s + 4 * (dy0 + ty));
             const int cy0 = (short)(cy & 0xffff), cy1 = cy >> 16;
-            if (sy == have) {
+            if (kBand) {   // contiguous band: slot = row - first row; a zero-weight lower row is staged anyway and contributes H1 * 0
+                if (sy == have) {
 #pragma unroll
-                for (int j = 0; j < NCOL; ++j) { H0[j][0] = H1[j][0]; H0[j][1] = H1[j][1]; H0[j][2] = H1[j][2]; }
-            } else if (sy + 1 != have) {
-                hrow(buf + (unsigned)(sy - y_first) * row_bytes, H0);
-            }
-            if (sy + 1 != have) {
-                hrow(buf + (unsigned)(sy + 1 - y_first) * row_bytes, H1);
-                have = sy + 1;
+                    for (int j = 0; j < NCOL; ++j) { H0[j][0] = H1[j][0]; H0[j][1] = H1[j][1]; H0[j][2] = H1[j][2]; }
+                } else if (sy + 1 != have) {
+                    hrow(buf + (unsigned)(sy - y_first) * row_bytes, H0);
+                }
+                if (sy + 1 != have) {
+                    hrow(buf + (unsigned)(sy + 1 - y_first) * row_bytes, H1);
+                    have = sy + 1;
+                }
+            } else {
+                const uint32_t upper = buf + (unsigned)lds_s32(slot_s + 4 * (dy0 + ty)) * row_bytes;   // staged upper tap row; the lower one follows it
+                // have = source row whose sums H1 holds (-2: none).  All threads walk the same rows: no divergence.
+                if (sy == have) {
+#pragma unroll
+                    for (int j = 0; j < NCOL; ++j) { H0[j][0] = H1[j][0]; H0[j][1] = H1[j][1]; H0[j][2] = H1[j][2]; }
+                    have = -2;
+                } else if (sy + 1 != have || cy1 == 0) {
+                    hrow(upper, H0);
+                }
+                if (cy1 != 0) {
+                    if (sy + 1 != have) { hrow(upper + row_bytes, H1); have = sy + 1; }
+                } else {   // zero-weight lower tap: not staged, contributes H1 * 0
+#pragma unroll
+                    for (int j = 0; j < NCOL; ++j) { H1[j][0] = 0; H1[j][1] = 0; H1[j][2] = 0; }
+                    have = -2;
+                }
             }
             uint8_t* lb = reinterpret_cast<uint8_t*>(line);
 #pragma unroll
