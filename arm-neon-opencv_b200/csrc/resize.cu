@@ -489,7 +489,21 @@ static int try_launch_resize_pipe_u8c3(const uint8_t* src, uint8_t* dst, int ima
     const long long total = (long long)g.tiles_per_frame * images;
     if (total > 0x7fffffffLL - 4096) return 0;
     g.total_tiles = (int)total;
+    bool any_right = false;   // does any right tap have weight? (same evaluation as linear_coord + sat_short on the device)
+    {
+        const double scale_x = (double)((float)w / (float)wo);
+        for (int d = 0; d < wo && !any_right; ++d) {
+            float fx = (float)(((double)d + 0.5) * scale_x - 0.5);
+            int sx = (int)floorf(fx);
+            fx -= (float)sx;
+            if (sx < 0) fx = 0.f;
+            if (sx >= w - 1) fx = 1.f;
+            const float x = 2048.f * fx;
+            any_right = (int)(x + (x >= 0.f ? 0.5f : -0.5f)) != 0;
+        }
+    }
     const void* kern = band ? (signed_char ? resize_pipe_kernel_for<true, true>(ncol) : resize_pipe_kernel_for<false, true>(ncol))
+                     : !any_right && ncol == 2 ? (const void*)resize_linear_u8c3_pipe_kernel<false, 2, false, true>   // pure byte moves: signedness irrelevant
                             : (signed_char ? resize_pipe_kernel_for<true, false>(ncol) : resize_pipe_kernel_for<false, false>(ncol));
     int dev = 0, optin = 0, sms = kNumSMs, per_sm = 0;
     cudaGetDevice(&dev);

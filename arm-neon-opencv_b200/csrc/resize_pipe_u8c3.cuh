@@ -53,7 +53,10 @@ struct ResizePipeGeom {
 // kBand: every source row between a tile's first and last tap row is needed (small ratios): the stage is that contiguous band,
 // fetched with ONE bulk copy, row slot = row - first row.  !kBand (integer ratios, where no lower tap has weight): only the
 // listed rows are fetched, one bulk copy per run of consecutive rows.
-template <bool kSigned, int NCOL, bool kBand>
+// kPoint (with !kBand): additionally no right tap has weight (odd integer ratio in x as well, e.g. 1920x1080 -> 640x360): every
+// weight pair is (2048, 0), the reference's integer blend (p * 2048 * 2048) >> 22 returns the tap itself and the kernel only
+// moves bytes.
+template <bool kSigned, int NCOL, bool kBand, bool kPoint = false>
 __global__ void __launch_bounds__(kRpThreads, NCOL <= 2 || !kBand ? 2 : 1)
 resize_linear_u8c3_pipe_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, ResizePipeGeom g) {
     extern __shared__ __align__(128) uint8_t dyn_smem[];     // [s_sy: ho][s_cy: ho][pad] 2 x stage, then per-warp output lines
@@ -162,7 +165,18 @@ resize_linear_u8c3_pipe_kernel(const uint8_t* __restrict__ src, uint8_t* __restr
             const int sy = lds_s32(sy_s + 4 * (dy0 + ty));
             const int cy = lds_s32(cy_s + 4 * (dy0 + ty));
             const int cy0 = (short)(cy & 0xffff), cy1 = cy >> 16;
-            if (kBand) {   // contiguous band: slot = row - first row; a zero-weight lower row is staged anyway and contributes H1 * 0
+            if (kPoint) {  // all weights are (2048, 0) x (2048, 0): (p << 22) >> 22 = p, signed or not
+                const uint32_t upper = buf + (unsigned)lds_s32(slot_s + 4 * (dy0 + ty)) * row_bytes;
+                uint8_t* lbp = reinterpret_cast<uint8_t*>(line);
+#pragma unroll
+                for (int j = 0; j < NCOL; ++j) {
+                    uint32_t w0, w1;
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(upper + aw[j]));
+                    asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(upper + aw[j]));
+                    const uint32_t px = __funnelshift_r(w0, w1, sh[j]);
+                    lbp[j * 96 + 3 * lane] = (uint8_t)px; lbp[j * 96 + 3 * lane + 1] = (uint8_t)(px >> 8); lbp[j * 96 + 3 * lane + 2] = (uint8_t)(px >> 16);
+                }
+            } else if (kBand) {   // contiguous band: slot = row - first row; a zero-weight lower row is staged anyway and contributes H1 * 0
                 if (sy == have) {
 #pragma unroll
                     for (int j = 0; j < NCOL; ++j) { H0[j][0] = H1[j][0]; H0[j][1] = H1[j][1]; H0[j][2] = H1[j][2]; }
@@ -192,10 +206,12 @@ resize_linear_u8c3_pipe_kernel(const uint8_t* __restrict__ src, uint8_t* __restr
                 }
             }
             uint8_t* lb = reinterpret_cast<uint8_t*>(line);
+            if (!kPoint) {
 #pragma unroll
-            for (int j = 0; j < NCOL; ++j) {
+                for (int j = 0; j < NCOL; ++j) {
 #pragma unroll
-                for (int k = 0; k < 3; ++k) lb[j * 96 + 3 * lane + k] = (uint8_t)((H0[j][k] * cy0 + H1[j][k] * cy1) >> 22);   // resize_naive.cpp:60-65
+                    for (int k = 0; k < 3; ++k) lb[j * 96 + 3 * lane + k] = (uint8_t)((H0[j][k] * cy0 + H1[j][k] * cy1) >> 22);   // resize_naive.cpp:60-65
+                }
             }
             __syncwarp();
 #pragma unroll

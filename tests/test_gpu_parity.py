@@ -160,7 +160,8 @@ def test_resize_linear_u8(vacv, oracle, layout, sz, path):
 
 @pytest.mark.parametrize("signed", [False, True])
 @pytest.mark.parametrize("sz", [((1920, 1080), (1280, 720)), ((1920, 1080), (640, 640)), ((1280, 720), (1000, 500)), ((64, 48), (200, 111)),
-                                ((640, 360), (639, 359)), ((640, 360), (1536, 700)), ((1280, 720), (1279, 361)), ((3840, 2160), (1920, 1080))])
+                                ((640, 360), (639, 359)), ((640, 360), (1536, 700)), ((1280, 720), (1279, 361)), ((3840, 2160), (1920, 1080)),
+                                ((960, 540), (320, 180)), ((320, 200), (64, 40)), ((1920, 1080), (640, 216)), ((1920, 1080), (384, 360))])
 def test_resize_linear_u8_default_path(vacv, oracle, sz, signed):
     """Default dispatch (no path flag): small vertical ratios run on the persistent TMA kernel (resize_pipe_u8c3.cuh), the rest on
     the gather kernel; both must equal the oracle."""
