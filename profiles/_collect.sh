@@ -4,4 +4,4 @@ python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tai
 python bench_ops.py --workload all --iters 30 --json gpurun_out/r1_bench_ops.jsonl 2>&1 | grep -v "^\[" > gpurun_out/r1_bench_ops.txt
 python bench_ops.py --workload ops2 --iters 30 --json gpurun_out/r1_bench_ops2.jsonl 2>&1 | grep -v "^\[" >> gpurun_out/r1_bench_ops.txt
 python bench.py --steps 10 --warmup 3 > gpurun_out/r1_bench_c2_n1.json 2> gpurun_out/bench_err.txt; tail -c 300 gpurun_out/r1_bench_c2_n1.json
-python bench.py --impl reference --steps 3 --warmup 1 2>/dev/null | tail -1 | cut -c1-260
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r1_launches_bench_c2.csv python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_launch.log 2>&1; tail -1 gpurun_out/ncu_launch.log | cut -c1-120
