@@ -428,7 +428,8 @@ def test_auto_stats_normalize_matches_reference_semantics(vacv, oracle):
 @pytest.mark.parametrize("v_first", [True, False])
 @pytest.mark.parametrize("w,h,wo,ho,b", [(1920, 1080, 640, 640, 2), (640, 360, 224, 224, 3), (64, 48, 100, 37, 2),
                                          (1280, 720, 640, 384, 1), (642, 362, 300, 200, 2), (3840, 2160, 640, 640, 1),
-                                         (320, 240, 1000, 700, 1), (1920, 1080, 1919, 1079, 1)])
+                                         (320, 240, 1000, 700, 1), (1920, 1080, 1919, 1079, 1), (7680, 4320, 1280, 720, 1),
+                                         (7680, 4320, 1536, 864, 1), (2560, 1440, 1408, 792, 1)])
 def test_fused_pipeline_config2(vacv, oracle, v_first, w, h, wo, ho, b):
     src = u8(19 + w, b, w * h * 3 // 2)
     got = host(vacv.nv_resize_normalize_chw(dev(src), w, h, wo, ho, dev(MEAN), dev(STD), v_first))
