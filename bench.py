@@ -164,8 +164,29 @@ def run_reference(args, rank):
     }))
 
 
+def bind_to_gpu_numa(index):
+    """Run this rank on the CPUs NVML reports as local to its GPU, so that the pinned staging buffers of the e2e path are
+    first-touched on the GPU's own NUMA node (8 ranks on one host otherwise fight over one socket's memory and PCIe root).
+    Best effort: returns a short description for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        allowed = os.sched_getaffinity(0)
+        words = (max(allowed) // 64) + 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        local = {64 * i + b for i, wd in enumerate(mask) for b in range(64) if (wd >> b) & 1} & allowed
+        if local and local != allowed:
+            os.sched_setaffinity(0, local)
+            return f"{len(local)} of {len(allowed)} cpus (GPU-local NUMA node)"
+        return f"{len(allowed)} cpus (no narrower GPU-local set)"
+    except Exception as e:   # noqa: BLE001
+        return f"unbound ({type(e).__name__})"
+
+
 # ---------------------------------------------------------------------------------------------------- GPU arm
 def run_ours(args, rank, world, local_rank):
+    numa = bind_to_gpu_numa(local_rank) if world > 1 else "single rank: all cpus"
     import torch
     import vacv_b200 as vacv
 
@@ -277,7 +298,7 @@ def run_ours(args, rank, world, local_rank):
                      "avg_launch_ms": round(own_ms, 4)},
         "e2e": {"value": round(e2e_value, 1), "unit": "Mpix/s", "h2d_bytes_per_step": BATCH * IN_FRAME,
                 "d2h_bytes_per_step": BATCH * OUT_FRAME, "steps": e2e_steps,
-                "launches_per_step": n_chunks,
+                "launches_per_step": n_chunks, "host_binding": numa,
                 "note": "one vacv_cuda_nv_resize_normalize_chw_host call per step: pinned host NV12 in, fp32 planes back to pinned host; 32 chunks of 8 frames pipelined H2D/kernel/D2H on three streams; wall clock; PCIe-bound (D2H ~50 GB/s)"},
         "cpu_baseline": cpu, "gpu_launches": args.steps, "clocks": clocks,
     }))
