@@ -442,8 +442,17 @@ static const void* resize_pipe_kernel_for(int ncol) {
 }
 
 // Persistent TMA kernel for u8 BGR bilinear (resize_pipe_u8c3.cuh).  1 = launched, 0 = shape not eligible, < 0 = error.
-static int try_launch_resize_pipe_u8c3(const uint8_t* src, uint8_t* dst, int images, int w, int h, int wo, int ho, bool signed_char, cudaStream_t s) {
-    if (((size_t)w * 3) % 16 != 0 || ((uintptr_t)src & 15) != 0) return 0;          // bulk copies: 16-byte granularity
+// Shape-dependent part of a launch, cached per host thread (a stream of equally shaped calls pays it once).
+struct ResizePipePlan {
+    int w, h, wo, ho, device; bool signed_char;                   // key
+    bool eligible; ResizePipeGeom g; const void* kern; int threads, per_sm, sms; size_t smem;
+};
+
+static int build_resize_pipe_plan(ResizePipePlan& plan) {
+    const int w = plan.w, h = plan.h, wo = plan.wo, ho = plan.ho;
+    const bool signed_char = plan.signed_char;
+    plan.eligible = false;
+    if (((size_t)w * 3) % 16 != 0) return 0;                                         // bulk copies: 16-byte granularity
     if (wo > kRpThreads * kRpMaxCols || ho > 8192) return 0;
     const double scale_y = (double)((float)h / (float)ho);
     std::vector<int> sy(ho), cy(ho);   // cy: only "lower tap has weight" (bit 16), which is all tile_rows() looks at
@@ -465,7 +474,7 @@ static int try_launch_resize_pipe_u8c3(const uint8_t* src, uint8_t* dst, int ima
     const bool band = h <= 2 * ho && any_low;
     if (!band && any_low) return 0;
     const size_t row_bytes = (size_t)w * 3;
-    ResizePipeGeom g;
+    ResizePipeGeom& g = plan.g;
     g.w = w; g.h = h; g.wo = wo; g.ho = ho;
     g.src_image = row_bytes * h; g.dst_image = (size_t)wo * ho * 3;
     int ncol = (wo + kRpThreads - 1) / kRpThreads;
@@ -486,9 +495,7 @@ static int try_launch_resize_pipe_u8c3(const uint8_t* src, uint8_t* dst, int ima
     if (!best_TH) return 0;
     g.TH = best_TH;
     g.tiles_per_frame = (ho + best_TH - 1) / best_TH;
-    const long long total = (long long)g.tiles_per_frame * images;
-    if (total > 0x7fffffffLL - 4096) return 0;
-    g.total_tiles = (int)total;
+    g.total_tiles = 0;   // per call
     bool any_right = false;   // does any right tap have weight? (same evaluation as linear_coord + sat_short on the device)
     {
         const double scale_x = (double)((float)w / (float)wo);
@@ -505,8 +512,8 @@ static int try_launch_resize_pipe_u8c3(const uint8_t* src, uint8_t* dst, int ima
     const void* kern = band ? (signed_char ? resize_pipe_kernel_for<true, true>(ncol) : resize_pipe_kernel_for<false, true>(ncol))
                      : !any_right && ncol == 2 ? (const void*)resize_linear_u8c3_pipe_kernel<false, 2, false, true>   // pure byte moves: signedness irrelevant
                             : (signed_char ? resize_pipe_kernel_for<true, false>(ncol) : resize_pipe_kernel_for<false, false>(ncol));
-    int dev = 0, optin = 0, sms = kNumSMs, per_sm = 0;
-    cudaGetDevice(&dev);
+    const int dev = plan.device;
+    int optin = 0, sms = kNumSMs, per_sm = 0;
     cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaFuncAttributes fa;
@@ -517,12 +524,38 @@ static int try_launch_resize_pipe_u8c3(const uint8_t* src, uint8_t* dst, int ima
     if (e != cudaSuccess) return set_error(VACV_ERR_CUDA, "resize: %s", cudaGetErrorString(e));
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, best_smem);
     if (e != cudaSuccess || per_sm < 1) return 0;
-    const int grid = (int)std::min<long long>(total, (long long)sms * per_sm);
+    plan.kern = kern; plan.threads = threads; plan.per_sm = per_sm; plan.sms = sms; plan.smem = best_smem;
+    plan.eligible = true;
+    return 0;
+}
+
+// Persistent TMA kernel for u8 BGR bilinear (resize_pipe_u8c3.cuh).  1 = launched, 0 = shape not eligible, < 0 = error.
+static int try_launch_resize_pipe_u8c3(const uint8_t* src, uint8_t* dst, int images, int w, int h, int wo, int ho, bool signed_char, cudaStream_t s) {
+    if (((uintptr_t)src & 15) != 0) return 0;
+    static thread_local ResizePipePlan plan = {};
+    static thread_local bool have_plan = false;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!have_plan || plan.w != w || plan.h != h || plan.wo != wo || plan.ho != ho || plan.signed_char != signed_char || plan.device != dev ||
+        getenv("VACV_RPIPE_NCOL")) {
+        have_plan = false;
+        plan.w = w; plan.h = h; plan.wo = wo; plan.ho = ho; plan.signed_char = signed_char; plan.device = dev;
+        const int rc = build_resize_pipe_plan(plan);
+        if (rc < 0) return rc;
+        have_plan = true;
+    }
+    if (!plan.eligible) return 0;
+    ResizePipeGeom g = plan.g;
+    const long long total = (long long)g.tiles_per_frame * images;
+    if (total > 0x7fffffffLL - 4096) return 0;
+    g.total_tiles = (int)total;
+    const int grid = (int)std::min<long long>(total, (long long)plan.sms * plan.per_sm);
     void* args[] = {(void*)&src, (void*)&dst, (void*)&g};
-    e = cudaLaunchKernel(kern, dim3(grid), dim3(threads), args, best_smem, s);
+    const cudaError_t e = cudaLaunchKernel(plan.kern, dim3(grid), dim3(plan.threads), args, plan.smem, s);
     if (e != cudaSuccess) return set_error(VACV_ERR_CUDA, "resize: %s", cudaGetErrorString(e));
     return 1;
 }
+
 
 extern "C" int vacv_cuda_resize(const void* src, void* dst, int batch, int w, int h, int c, int dtype, int layout,
                                 int w_out, int h_out, int interpolation, int flags, void* stream) {
