@@ -135,8 +135,16 @@ def c3(iters):   # warp_affine face crops: 4096 x (1280x720 -> 112x112 fp32 norm
     roi = int(np.mean([(wo / s) ** 2 * 3 for s in np.random.default_rng(7).uniform(0.3, 0.6, 1000)]))
     ms, _ = timeit(lambda: vacv.warp_affine_normalize(frames, minv, wo, wo, mean, std, idx), iters)
     report("c3 warp_affine_normalize 1280x720->112x112 f32 x4096", ms, n * wo * wo, n * (roi + wo * wo * 12), "bytes = mean source ROI + out")
+    os.environ["VACV_WARP_GATHER"] = "1"    # A/B: the direct gather kernel instead of the TMA-staged default
+    ms, _ = timeit(lambda: vacv.warp_affine_normalize(frames, minv, wo, wo, mean, std, idx), iters)
+    del os.environ["VACV_WARP_GATHER"]
+    report("   same, direct gather kernel (VACV_WARP_GATHER=1)", ms, n * wo * wo, n * (roi + wo * wo * 12))
     ms, _ = timeit(lambda: vacv.warp_affine(frames, vacv.NHWC, minv, wo, wo, idx), iters)
     report("   warp_affine u8 1280x720->112x112 x4096", ms, n * wo * wo, n * (roi + wo * wo * 3))
+    ms, _ = timeit(lambda: vacv.warp_affine(frames, vacv.NHWC, minv, wo, wo, idx, vacv.FLAG_TILED), iters)
+    report("   warp_affine u8 (TMA-staged kernel, opt-in) x4096", ms, n * wo * wo, n * (roi + wo * wo * 3))
+    ms, _ = timeit(lambda: vacv.warp_affine_normalize(frames, minv, wo, wo, mean, std, idx, out_layout=vacv.NCHW), iters)
+    report("   warp_affine_normalize -> CHW planes x4096", ms, n * wo * wo, n * (roi + wo * wo * 12))
 
 
 def c4(iters):   # resize INTER_CUBIC u8 2560x1440 -> 1920x1080, batch 128

@@ -51,7 +51,8 @@ enum {
     VACV_FLAG_NEON_RULE = 1,     /* u8 bilinear with the rounding of resize_neon.cpp (aarch64 builds of the reference) */
     VACV_FLAG_SIGNED_CHAR = 2,   /* reproduce an x86 default-signed-char build of resize_naive/warp_affine_naive */
     VACV_FLAG_DIRECT_GATHER = 0x100, /* resize: force the direct global-gather kernels (default for bilinear) */
-    VACV_FLAG_TILED = 0x200          /* resize: force the shared-memory tiled kernels (default for bicubic) */
+    VACV_FLAG_TILED = 0x200          /* resize: force the shared-memory tiled kernels (default for bicubic);
+                                        warp_affine u8 BGR: run the TMA-staged kernel (default: direct gather) */
 };
 
 VACV_API int vacv_cuda_abi_version(void);

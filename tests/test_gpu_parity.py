@@ -347,6 +347,70 @@ def test_warp_affine_normalize_fused(vacv, oracle):
     assert_same(got_chw, np.ascontiguousarray(got.transpose(0, 3, 1, 2)))
 
 
+def _similarity(s, deg, cx, cy, wo, ho):
+    """forward matrix of a crop centred on (cx, cy) of the source: scale s, rotation deg"""
+    a = np.deg2rad(deg)
+    al, be = s * np.cos(a), s * np.sin(a)
+    return [al, be, wo / 2 - al * cx - be * cy, -be, al, ho / 2 + be * cx - al * cy]
+
+
+STAGED_CASES = [
+    # (w, h, wo, ho, forward matrices) -- frames whose rows are multiples of 16 bytes run the TMA-staged kernel
+    (320, 200, 112, 112, [_similarity(0.45, 7, 160, 100, 112, 112), _similarity(0.5, -15, 20, 10, 112, 112),        # window leaves the frame
+                          _similarity(0.5, 12, 310, 195, 112, 112), _similarity(0.35, 0, 160, 100, 112, 112)]),     # top-left / bottom-right
+    (320, 200, 100, 57, [_similarity(0.6, 3, 150, 90, 100, 57), _similarity(0.9, -8, 100, 100, 100, 57)]),           # partial tiles in x and y
+    (320, 200, 97, 33, [_similarity(0.7, 5, 150, 90, 97, 33)]),                                                       # odd width: byte stores
+    (640, 480, 112, 112, [_similarity(0.1, 30, 320, 240, 112, 112), _similarity(0.25, 45, 320, 240, 112, 112),        # windows too large for a stage
+                          _similarity(0.3, 90, 320, 240, 112, 112), _similarity(2.5, 170, 320, 240, 112, 112),        #   -> direct gather inside the kernel
+                          [1e-3, 0, 5, 0, 1e-3, 5], [1e30, 0, 0, 0, 1e30, 0]]),                                        # huge / overflowing coordinates
+    (1280, 720, 240, 240, [M_TEST, _similarity(1.0, 0, 640, 360, 240, 240), _similarity(1.7, -20, 600, 300, 240, 240)]),
+    (336, 64, 64, 40, [_similarity(0.5, 4, 168, 32, 64, 40), [0.5, 0, 0, 0, 0.5, 0]]),                                 # narrow frame, exact half scale
+]
+
+
+@pytest.mark.parametrize("case", range(len(STAGED_CASES)))
+def test_warp_affine_staged_windows(vacv, oracle, case):
+    """The TMA-staged 3-channel kernel: windows that leave the frame, partial tiles, widths without word-aligned rows, windows
+    too large for a stage and non-finite coordinates (both fall back to the gather path per tile) -- u8, fp32 HWC, fp32 CHW,
+    and identical to the direct gather kernel."""
+    w, h, wo, ho, fwd = STAGED_CASES[case]
+    nf = 3
+    frames = u8(40 + case, nf, h, w, 3)
+    with np.errstate(all="ignore"):
+        minv = np.array([vacv.invert_affine(m) for m in fwd], np.float32)
+    n = len(fwd)
+    idx = (np.arange(n) % nf).astype(np.int32)
+    got = host(vacv.warp_affine(dev(frames), NHWC, dev(minv), wo, ho, dev(idx), vacv.FLAG_TILED))   # staged kernel
+    direct = host(vacv.warp_affine(dev(frames), NHWC, dev(minv), wo, ho, dev(idx)))                # gather kernel (u8 default)
+    assert_same(got, direct)
+    f32hwc = host(vacv.warp_affine_normalize(dev(frames), dev(minv), wo, ho, dev(MEAN), dev(STD), dev(idx)))
+    f32chw = host(vacv.warp_affine_normalize(dev(frames), dev(minv), wo, ho, dev(MEAN), dev(STD), dev(idx), out_layout=NCHW))
+    assert_same(f32chw, np.ascontiguousarray(f32hwc.transpose(0, 3, 1, 2)))
+    for i in range(n):
+        if not np.all(np.isfinite(minv[i])):
+            continue   # the oracle's behaviour on non-finite matrices is not defined; the two CUDA kernels agree (above)
+        assert_same(got[i], oracle.warp_affine(frames[idx[i]], w, h, 3, NHWC, wo, ho, minv[i]))
+        assert_same(f32hwc[i], oracle.warp_affine_normalize(frames[idx[i]], w, h, 3, minv[i], wo, ho, MEAN, STD))
+    got_sc = host(vacv.warp_affine(dev(frames), NHWC, dev(minv), wo, ho, dev(idx), vacv.FLAG_SIGNED_CHAR | vacv.FLAG_TILED))
+    assert_same(got_sc[0], oracle.warp_affine(frames[idx[0]], w, h, 3, NHWC, wo, ho, minv[0], signed_char=1))
+
+
+def test_warp_affine_staged_many_tiles_per_cta(vacv, oracle):
+    """More tiles than persistent CTAs (both stages and both barrier parities are reused many times); staged == gather on every crop."""
+    w, h, wo, ho, nf, n = 640, 368, 112, 112, 8, 600
+    frames = _gpu_rand_u8(41, nf, h, w, 3)
+    minv = np.array([vacv.invert_affine(m) for m in random_face_matrices(n, w, h, wo, 12)], np.float32)
+    idx = (np.arange(n) % nf).astype(np.int32)
+    a = vacv.warp_affine(frames, NHWC, dev(minv), wo, ho, dev(idx), vacv.FLAG_TILED)
+    b = vacv.warp_affine(frames, NHWC, dev(minv), wo, ho, dev(idx))
+    assert torch.equal(a, b)
+    f = vacv.warp_affine_normalize(frames, dev(minv), wo, ho, dev(MEAN), dev(STD), dev(idx))       # staged by default
+    for i in (1, 300, 598):
+        assert_same(host(f[i]), oracle.warp_affine_normalize(host(frames[idx[i]]), w, h, 3, minv[i], wo, ho, MEAN, STD))
+    for i in (0, 299, 599):
+        assert_same(host(a[i]), oracle.warp_affine(host(frames[idx[i]]), w, h, 3, NHWC, wo, ho, minv[i]))
+
+
 def test_warp_affine_grey_and_planar_batches(vacv, oracle):
     """Single-channel frames and CHW frames (c planes, one matrix) through the word-granular single-channel kernel."""
     w, h, wo, ho, nf, n = 320, 200, 112, 100, 3, 9
