@@ -1,6 +1,9 @@
 // a2 crop, a3 layout_change, a4 dtype_change, a12 normalize -- the pure streaming operators.
 // All are HBM-bound byte movers: the design rule is "every global access a warp issues is lane-contiguous and
 // as wide as the alignment allows (128-bit in the common shapes)".
+#include <algorithm>
+#include <cstdlib>
+
 #include "vacv_common.cuh"
 
 namespace vacv {
@@ -9,7 +12,11 @@ namespace vacv {
 // a2 crop (src/cv/crop.cpp:44-142).  Both layouts reduce to "copy R byte-rows of RB bytes": HWC rows are
 // cw*c*elem bytes, CHW rows are cw*elem bytes for each of c planes.  One warp per destination row.  The
 // destination is written in 16-byte aligned chunks; the (generally misaligned) source bytes for a chunk come
-// from five aligned 32-bit words merged with funnel shifts (L1 serves the overlap between neighbouring lanes).
+// from the two aligned 16-byte chunks around them (128-bit loads; L1 serves the overlap between neighbouring lanes),
+// merged with funnel shifts.  Aligned chunks that hold valid bytes never leave the allocation (allocations are 256-byte
+// granular).  (A pure copy-engine variant -- cp.async.bulk.tensor load + store through a 4-stage shared-memory ring, one
+// thread per CTA -- was measured on 16-byte aligned crops: 0.150 ms against 0.134 ms for this kernel on 128 x 1080p ->
+// 1280x720, and TMA cannot shift bytes, so misaligned left edges would need this kernel anyway; it was dropped.)
 struct CropGeom {
     int rows_per_frame;   // ch (HWC) or c*ch (CHW)
     int ch;               // rows per plane
@@ -33,20 +40,25 @@ __global__ void __launch_bounds__(256) crop_rows_kernel(const uint8_t* __restric
     const int nchunks = (g.RB - head) >> 4;
     const uint8_t* sb = s + head;
     uint8_t* db = d + head;
-    const int m = (int)((uintptr_t)sb & 3);           // same for every chunk of this row
-    const uint32_t* sw = reinterpret_cast<const uint32_t*>(sb - m);
-    const int sh = 8 * m;
+    // 16-byte granular: output chunk q = source bytes [sb + 16 q, +16) = words k .. k+4 (shifted by 8 (m & 3) bits) of the two
+    // aligned 16-byte chunks around it; both come in as 128-bit loads (the second one is the next lane's first: an L1 hit).
+    // m is the same for every chunk of the row (and of every row: warp-uniform switch).
+    const int m = (int)((uintptr_t)sb & 15), k = m >> 2, sh = 8 * (m & 3);
+    const uint4* sa = reinterpret_cast<const uint4*>(sb - m);
+    // never read past the 16-byte chunk that holds the last source byte of the row (it may be the last of the allocation)
+    const uint4* last = reinterpret_cast<const uint4*>((uintptr_t)(s + g.RB - 1) & ~(uintptr_t)15);
     for (int q = lane; q < nchunks; q += 32) {
-        const uint32_t* p = sw + 4 * q;
-        uint4 o;
-        if (m == 0) {
-            o = make_uint4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
-        } else {
-            uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2), w3 = __ldg(p + 3), w4 = __ldg(p + 4);
-            o = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
-                           __funnelshift_r(w3, w4, sh));
+        const uint4 a = __ldg(sa + q);
+        const uint4 b4 = (m != 0 && sa + q + 1 <= last) ? __ldg(sa + q + 1) : make_uint4(0u, 0u, 0u, 0u);
+        uint32_t w0, w1, w2, w3, w4;
+        switch (k) {
+            case 0: w0 = a.x; w1 = a.y; w2 = a.z; w3 = a.w; w4 = b4.x; break;
+            case 1: w0 = a.y; w1 = a.z; w2 = a.w; w3 = b4.x; w4 = b4.y; break;
+            case 2: w0 = a.z; w1 = a.w; w2 = b4.x; w3 = b4.y; w4 = b4.z; break;
+            default: w0 = a.w; w1 = b4.x; w2 = b4.y; w3 = b4.z; w4 = b4.w; break;
         }
-        st_stream16(db + 16 * q, o);
+        st_stream16(db + 16 * q, make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
+                                            __funnelshift_r(w3, w4, sh)));
     }
     const int done = head + 16 * nchunks;
     if (lane < g.RB - done) d[done + lane] = __ldg(s + done + lane);

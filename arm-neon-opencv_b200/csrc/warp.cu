@@ -289,26 +289,13 @@ __global__ void __launch_bounds__(256) warp_affine_u8c1_kernel(const uint8_t* __
 
 }  // namespace vacv
 
+#include "tma_host.cuh"
 #include "warp_staged_u8c3.cuh"   // TMA-staged variant of the 3-channel kernel (uses Taps / warp_taps_fast / kWarpOut*)
 
 using namespace vacv;
 
 // ---- host side of the staged kernel: tensor maps over the frame pool (one per box width), cached per host thread
 namespace {
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn encode_tiled_fn() {
-    static EncodeTiledFn fn = [] {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
-        (void)cudaGetLastError();
-        return reinterpret_cast<EncodeTiledFn>(p);
-    }();
-    return fn;
-}
-
 struct StagedPlan {
     const void* frames = nullptr;
     int n_frames = 0, w = 0, h = 0;
@@ -321,20 +308,13 @@ bool staged_plan(const void* frames, int n_frames, int w, int h, const WarpStage
     static thread_local StagedPlan plan;
     if (plan.frames != frames || plan.n_frames != n_frames || plan.w != w || plan.h != h) {
         plan.frames = frames; plan.n_frames = n_frames; plan.w = w; plan.h = h; plan.ok = false;
-        EncodeTiledFn enc = encode_tiled_fn();
-        const bool shape_ok = enc && (w % 16) == 0 && w * 3 >= ws_box_bytes(kWsMaps - 1) && h >= kWsBoxRows &&
+        const bool shape_ok = (w % 16) == 0 && w * 3 >= ws_box_bytes(kWsMaps - 1) && h >= kWsBoxRows &&
                               ((uintptr_t)frames % 16) == 0 && (size_t)w * h * 3 < 0xfffffff0ull;
         if (shape_ok) {
             plan.ok = true;
-            const cuuint64_t dims[3] = {(cuuint64_t)w * 3 / 4, (cuuint64_t)h, (cuuint64_t)n_frames};
-            const cuuint64_t strides[2] = {(cuuint64_t)w * 3, (cuuint64_t)w * 3 * h};
-            const cuuint32_t estr[3] = {1, 1, 1};
-            for (int k = 0; k < kWsMaps && plan.ok; ++k) {
-                const cuuint32_t box[3] = {(cuuint32_t)ws_box_bytes(k) / 4, (cuuint32_t)kWsBoxRows, 1};
-                plan.ok = enc(&plan.maps.m[k], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<void*>(frames), dims, strides, box, estr,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-            }
+            for (int k = 0; k < kWsMaps && plan.ok; ++k)
+                plan.ok = encode_map_3d(&plan.maps.m[k], CU_TENSOR_MAP_DATA_TYPE_UINT32, frames, (cuuint64_t)w * 3 / 4, h, n_frames,
+                                        (cuuint64_t)w * 3, (cuuint64_t)w * 3 * h, ws_box_bytes(k) / 4, kWsBoxRows, 1);
         }
     }
     *maps = &plan.maps;

@@ -54,6 +54,11 @@ def assert_same(got, want):
         raise AssertionError(f"{bad.size} of {got.size} elements differ; first at {bad[0]}: got {got.ravel()[bad[0]]} want {want.ravel()[bad[0]]}")
 
 
+def _gpu_rand_u8(seed, *shape):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return torch.randint(0, 256, shape, dtype=torch.uint8, device="cuda", generator=g)
+
+
 MEAN = np.array([103.53, 116.28, 123.675], np.float32)
 STD = np.array([57.375, 57.12, 58.395], np.float32)
 
@@ -97,6 +102,31 @@ def test_crop(vacv, oracle, layout, dt, rect):
     got = host(vacv.crop(dev(src), layout, l, t, cw, ch))
     want = np.stack([oracle.crop(src[i], w, h, c, layout, l, t, cw, ch) for i in range(b)])
     assert_same(got, want)
+
+
+@pytest.mark.parametrize("layout", [NHWC, NCHW])
+@pytest.mark.parametrize("dt", ["u8", "f32"])
+@pytest.mark.parametrize("rect", [(7, 3, 192, 100), (33, 17, 400, 300), (5, 1, 336, 359), (239, 0, 400, 65), (1, 295, 512, 64)])
+def test_crop_16_byte_rows(vacv, oracle, layout, dt, rect):
+    """Rects whose rows are multiples of 16 bytes (no head / tail bytes), with left edges at every kind of byte alignment."""
+    w, h, c, b = 640, 360, 3, 3
+    shape = (b, h, w, c) if layout == NHWC else (b, c, h, w)
+    src = u8(5, *shape) if dt == "u8" else f32(5, *shape)
+    l, t, cw, ch = rect
+    got = host(vacv.crop(dev(src), layout, l, t, cw, ch))
+    want = np.stack([oracle.crop(src[i], w, h, c, layout, l, t, cw, ch) for i in range(b)])
+    assert_same(got, want)
+
+
+def test_crop_large_batch_equals_slicing(vacv):
+    """64 x 1080p -> 1280x720 at (321, 181) and at a 16-byte aligned left edge; equals plain slicing."""
+    src = _gpu_rand_u8(6, 64, 1080, 1920, 3)
+    got = vacv.crop(src, NHWC, 321, 181, 1280, 720)
+    assert torch.equal(got, src[:, 181:901, 321:1601, :])
+    assert torch.equal(vacv.crop(src, NHWC, 320, 0, 1280, 1080), src[:, :, 320:1600, :])
+    chw = _gpu_rand_u8(7, 16, 3, 1080, 1920)
+    got = vacv.crop(chw, NCHW, 321, 181, 1280, 720)
+    assert torch.equal(got, chw[:, :, 181:901, 321:1601])
 
 
 def test_crop_reference_sizes(vacv, oracle):
@@ -693,11 +723,6 @@ def test_full_size_config2_properties(vacv):
     for k in range(3):
         want = np.float32((np.float32(128.0) - MEAN[k]).astype(np.float64) / (np.float64(STD[k]) + 1e-6))
         assert np.all(flat[k] == want)
-
-
-def _gpu_rand_u8(seed, *shape):
-    g = torch.Generator(device="cuda").manual_seed(seed)
-    return torch.randint(0, 256, shape, dtype=torch.uint8, device="cuda", generator=g)
 
 
 def test_full_size_config2_batch256_sampled_vs_oracle(vacv, oracle):
