@@ -330,11 +330,13 @@ template <int OUT, bool kSigned, int NW>
 int launch_staged_nw(const WarpStagedMaps& maps, const uint8_t* frames, const int* frame_idx, const float* minv, void* dst, int w, int h,
                      int n_crops, int w_out, int h_out, const float* mean, const float* stddev, cudaStream_t s) {
     constexpr int kSmem = ws_smem_bytes<NW>();
-    static thread_local bool attr_set = false;
-    if (!attr_set) {
+    static thread_local int attr_device = -1;   // the opt-in is per device
+    int device = 0;
+    cudaGetDevice(&device);
+    if (attr_device != device) {
         if (cudaFuncSetAttribute(warp_affine_u8c3_staged_kernel<OUT, kSigned, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) != cudaSuccess)
             return check_launch("warp_affine (staged kernel attribute)");
-        attr_set = true;
+        attr_device = device;
     }
     WarpStagedGeom g;
     g.w = w; g.h = h; g.wo = w_out; g.ho = h_out;
