@@ -304,20 +304,33 @@ __global__ void __launch_bounds__(256) normalize_plane_kernel(const void* __rest
         const uint8_t* s = (const uint8_t*)src_ + base;
         for (int t = threadIdx.x; t < 256; t += blockDim.x) lut[t] = normalize_one((float)t, mu, den);
         __syncthreads();
-        for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-            const uint32_t v = ld_stream4(s + 4 * (size_t)i);
-            st_stream16f(d + 4 * (size_t)i, make_float4(lut[v & 0xff], lut[(v >> 8) & 0xff], lut[(v >> 16) & 0xff], lut[v >> 24]));
+        // four independent loads in flight per thread before the first table lookup (same reason as in the HWC kernel)
+        constexpr int kU = 4;
+        for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += kU * stride) {
+            uint32_t v[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) v[u] = i + u * stride < n4 ? ld_stream4(s + 4 * (size_t)(i + u * stride)) : 0u;
+#pragma unroll
+            for (int u = 0; u < kU; ++u)
+                if (i + u * stride < n4)
+                    st_stream16f(d + 4 * (size_t)(i + u * stride),
+                                 make_float4(lut[v[u] & 0xff], lut[(v[u] >> 8) & 0xff], lut[(v[u] >> 16) & 0xff], lut[v[u] >> 24]));
         }
         for (unsigned e = 4 * n4 + blockIdx.x * blockDim.x + threadIdx.x; e < g.wh; e += stride) d[e] = lut[s[e]];
     } else {
         const float* s = (const float*)src_ + base;
         const double rden = 1.0 / den;
-        for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-            const uint4 r = ld_stream16(s + 4 * (size_t)i);
-            st_stream16f(d + 4 * (size_t)i, make_float4(normalize_fast_exact(__uint_as_float(r.x), mu, den, rden),
-                                                        normalize_fast_exact(__uint_as_float(r.y), mu, den, rden),
-                                                        normalize_fast_exact(__uint_as_float(r.z), mu, den, rden),
-                                                        normalize_fast_exact(__uint_as_float(r.w), mu, den, rden)));
+        constexpr int kU = 2;   // two 16-byte loads in flight per thread
+        for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += kU * stride) {
+            uint4 r[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) r[u] = i + u * stride < n4 ? ld_stream16(s + 4 * (size_t)(i + u * stride)) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int u = 0; u < kU; ++u)
+                if (i + u * stride < n4)
+                    st_stream16f(d + 4 * (size_t)(i + u * stride),
+                                 make_float4(normalize_fast_exact(__uint_as_float(r[u].x), mu, den, rden), normalize_fast_exact(__uint_as_float(r[u].y), mu, den, rden),
+                                             normalize_fast_exact(__uint_as_float(r[u].z), mu, den, rden), normalize_fast_exact(__uint_as_float(r[u].w), mu, den, rden)));
         }
         for (unsigned e = 4 * n4 + blockIdx.x * blockDim.x + threadIdx.x; e < g.wh; e += stride) d[e] = normalize_one(s[e], mu, den);
     }
