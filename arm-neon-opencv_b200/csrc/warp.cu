@@ -348,14 +348,14 @@ int launch_staged_nw(const WarpStagedMaps& maps, const uint8_t* frames, const in
     g.total_tiles = g.tiles_per_crop * n_crops;           // < 2^31: checked by staged_fits()
     g.inv_tiles_x = 1.f / (float)g.tiles_x;
     g.frame_bytes = (size_t)w * h * 3;
-    const int grid = std::min(g.total_tiles, 3 * kNumSMs);
+    const int grid = std::min(g.total_tiles, kWsCtasPerSm * kNumSMs);
     warp_affine_u8c3_staged_kernel<OUT, kSigned, NW><<<grid, 32 * NW + 32, kSmem, s>>>(maps, frames, frame_idx, minv, dst, g, mean, stddev);
     return check_launch("warp_affine (staged)");
 }
 template <int OUT, bool kSigned>
 int launch_staged(const WarpStagedMaps& maps, const uint8_t* frames, const int* frame_idx, const float* minv, void* dst, int w, int h,
                   int n_crops, int w_out, int h_out, const float* mean, const float* stddev, cudaStream_t s) {
-    // 8 consumer warps: measured faster than 12 (0.335 vs 0.39 ms on config 3; the per-tile prologue is paid per warp)
+    // 8 consumer warps: measured faster than 10 or 12 (config 3: 0.318 vs 0.332 / 0.331 ms; the per-tile prologue is paid per warp)
     return launch_staged_nw<OUT, kSigned, 8>(maps, frames, frame_idx, minv, dst, w, h, n_crops, w_out, h_out, mean, stddev, s);
 }
 }  // namespace

@@ -9,7 +9,8 @@
 //               TMA copies (cp.async.bulk.tensor, SASS UTMALDG) of 16 rows each from a tensor map over the frame pool
 //               {w*3/4 words, h, frames}; the box width is picked per tile from a small family of maps (144 ... 528
 //               bytes, odd multiples of 16 B so consecutive rows start in different banks).  Parts of a box outside the
-//               frame are zero-filled by the hardware and never read.  The windows live in a shared-memory RING: a tile
+//               frame are zero-filled by the hardware and never read.  The geometry of four tiles is computed at once
+//               (8 lanes each), one pass ahead of the copies.  The windows live in a shared-memory RING: a tile
 //               takes exactly the bytes of its boxes, so several windows (typically 3-5, at most 8) are in flight while
 //               the consumer warps work on the oldest one (full / empty mbarriers per tile slot, no CTA barrier).
 //   consumers = a lane owns a pixel (flat order inside the tile), forms coordinates and weights exactly like the gather
@@ -31,7 +32,8 @@ namespace vacv {
 
 constexpr int kWsMaps = 7;             // box widths 144 + 64 k bytes
 constexpr int kWsBoxRows = 16;
-constexpr int kWsRingBytes = 64 * 1024; // shared-memory ring of source windows per CTA (2 CTAs per SM)
+constexpr int kWsRingBytes = 100 * 1024;
+constexpr int kWsCtasPerSm = 2; // shared-memory ring of source windows per CTA (2 CTAs per SM: measured best, see DESIGN)
 constexpr int kWsSlots = 8;             // tiles in flight per CTA (descriptor + full / empty barrier each)
 __host__ __device__ constexpr int ws_box_bytes(int k) { return 144 + 64 * k; }
 
@@ -69,7 +71,7 @@ template <int NW> constexpr int ws_smem_bytes() { return kWsRingBytes + 768 * 4 
 
 // NW consumer warps + 1 producer warp
 template <int OUT, bool kSigned, int NW>
-__global__ void __launch_bounds__(32 * NW + 32, 3)
+__global__ void __launch_bounds__(32 * NW + 32, kWsCtasPerSm)
 warp_affine_u8c3_staged_kernel(const __grid_constant__ WarpStagedMaps maps, const uint8_t* __restrict__ frames,
                                const int* __restrict__ frame_idx, const float* __restrict__ minv, void* __restrict__ dst_,
                                const WarpStagedGeom g, const float* __restrict__ mean, const float* __restrict__ stddev) {
@@ -95,9 +97,58 @@ warp_affine_u8c3_staged_kernel(const __grid_constant__ WarpStagedMaps maps, cons
 
     if (warp == NW) {
         // ------------------------------------------------------------------ producer
-        // Windows live in a ring: a tile takes exactly the bytes of its TMA boxes, so 3-5 typical windows (up to kWsSlots) are
-        // in flight and the latency of metadata load -> TMA is covered.  Tiles are released in order (consumers walk them in
-        // order); lane j keeps the ring interval of slot j, the overlap test against all tiles in flight is one ballot.
+        // Windows live in a ring: a tile takes exactly the bytes of its TMA boxes, so several windows (up to kWsSlots) are in
+        // flight.  Tiles are released in order (consumers walk them in order); lane j keeps the ring interval of slot j, the
+        // overlap test against all tiles in flight is one ballot.
+        // The geometry of kG = 4 tiles is worked out at once, 8 lanes per tile (matrix load, corners, bounding box), one pass
+        // ahead of the copies.  (Prefetching that pass's windows into L2 with cp.async.bulk.prefetch.tensor was measured: slower
+        // in every configuration, up to 45 % for fp32 output -- 444 CTAs x 4..8 windows ahead is tens of MB that compete with the
+        // output stream for L2.)
+        constexpr int kG = 4, kGL = 32 / kG;   // tiles per pass, lanes per tile
+        const int grp = lane / kGL, sub = lane % kGL;
+        const int n_my = (int)blockIdx.x < g.total_tiles ? (g.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+        struct TileInfo {
+            int crop, frame, x0, y0, tw, th, sy_lo, bx_lo, k, pitch, nops, need, staged;
+            float m[6];
+        };
+        auto geometry = [&](int it, TileInfo& ti) {   // it: index in this CTA's tile sequence (one value per 8-lane group)
+            const bool valid = it < n_my;
+            const int tile = (int)blockIdx.x + (valid ? it : 0) * (int)gridDim.x;
+            ti.crop = tile / g.tiles_per_crop;
+            const int t = tile - ti.crop * g.tiles_per_crop;
+            const int tyi = (int)(((float)t + 0.5f) * g.inv_tiles_x), txi = t - tyi * g.tiles_x;
+            ti.x0 = txi * g.tw; ti.y0 = tyi * g.th;
+            ti.tw = min(g.tw, g.wo - ti.x0); ti.th = min(g.th, g.ho - ti.y0);
+#pragma unroll
+            for (int q = 0; q < 6; ++q) ti.m[q] = __ldg(minv + 6 * (size_t)ti.crop + q);
+            ti.frame = frame_idx ? __ldg(frame_idx + ti.crop) : ti.crop;
+            // lanes 0..3 of the group: the four corners, with the per-pixel expression (warp_affine_naive.cpp:23-24); 4..7 repeat them
+            const int dx = (sub & 1) ? ti.x0 + ti.tw - 1 : ti.x0, dy = (sub & 2) ? ti.y0 + ti.th - 1 : ti.y0;
+            const float fx = ti.m[0] * (float)dx + ti.m[1] * (float)dy + ti.m[2];
+            const float fy = ti.m[3] * (float)dx + ti.m[4] * (float)dy + ti.m[5];
+            const float kBig = 16777216.f;
+            const bool finite = fx > -kBig && fx < kBig && fy > -kBig && fy < kBig;   // false for NaN too
+            const int sx = finite ? (int)floorf(fx) : 0, sy = finite ? (int)floorf(fy) : 0;
+            int sx_lo = sx, sx_hi = sx, sy_lo = sy, sy_hi = sy;
+#pragma unroll
+            for (int o = 1; o <= 2; o <<= 1) {
+                sx_lo = min(sx_lo, __shfl_xor_sync(0xffffffffu, sx_lo, o)); sx_hi = max(sx_hi, __shfl_xor_sync(0xffffffffu, sx_hi, o));
+                sy_lo = min(sy_lo, __shfl_xor_sync(0xffffffffu, sy_lo, o)); sy_hi = max(sy_hi, __shfl_xor_sync(0xffffffffu, sy_hi, o));
+            }
+            const unsigned gmask = (kGL == 32 ? 0xffffffffu : ((1u << kGL) - 1u)) << (kGL * grp);
+            const bool all_finite = (__ballot_sync(0xffffffffu, finite) & gmask) == gmask;
+            // taps of the tile: columns sx_lo .. sx_hi + 1, rows sy_lo .. sy_hi + 1
+            ti.sy_lo = sy_lo;
+            ti.bx_lo = ((sx_lo * 3) >> 4) << 4;                              // floor to 16 bytes (arithmetic shift: negative too)
+            const int bx_hi = (((sx_hi + 2) * 3 + 15) >> 4) << 4;
+            const int bw = bx_hi - ti.bx_lo, bh = sy_hi + 2 - sy_lo;
+            ti.k = bw <= 144 ? 0 : (bw - 144 + 63) >> 6;
+            ti.pitch = ws_box_bytes(ti.k);
+            ti.nops = (bh + kWsBoxRows - 1) / kWsBoxRows;
+            ti.need = ti.nops * kWsBoxRows * ti.pitch;                       // a multiple of 256 bytes
+            ti.staged = valid && all_finite && ti.k < kWsMaps && ti.nops <= 64 && ti.need <= kWsRingBytes;
+        };
+        auto tmap_of = [&](int k) { return reinterpret_cast<const uint8_t*>(&maps) + (size_t)k * sizeof(CUtensorMap); };
         int my_start = 0, my_end = 0;
         bool my_active = false;
         int head = 0, tail_it = 0;
@@ -106,81 +157,46 @@ warp_affine_u8c3_staged_kernel(const __grid_constant__ WarpStagedMaps maps, cons
             if (lane == (tail_it & (kWsSlots - 1))) my_active = false;
             ++tail_it;
         };
-        float m[6];
-        int frame = 0;
-        auto load_meta = [&](int crop, float (&mm)[6], int& fr) {
-#pragma unroll
-            for (int k = 0; k < 6; ++k) mm[k] = __ldg(minv + 6 * (size_t)crop + k);
-            fr = frame_idx ? __ldg(frame_idx + crop) : crop;
-        };
-        // (crop, t) of the CTA's tiles advance by a constant stride: no division per tile
-        const int step_crop = (int)gridDim.x / g.tiles_per_crop, step_t = (int)gridDim.x - step_crop * g.tiles_per_crop;
-        int crop = (int)blockIdx.x / g.tiles_per_crop, t = (int)blockIdx.x - crop * g.tiles_per_crop;
         const int full_magic = 65536 / g.tw + 1, full_step_y = NT / g.tw, full_step_x = NT - full_step_y * g.tw;
-        if ((int)blockIdx.x < g.total_tiles) load_meta(crop, m, frame);
-        int it = 0;
-        for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++it) {
-            const int slot = it & (kWsSlots - 1);
-            int crop_next = crop + step_crop, t_next = t + step_t;
-            if (t_next >= g.tiles_per_crop) { t_next -= g.tiles_per_crop; ++crop_next; }
-            float m_next[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            int frame_next = 0;
-            if (tile + (int)gridDim.x < g.total_tiles) load_meta(crop_next, m_next, frame_next);   // in flight during this tile's bookkeeping
-            const int tyi = (int)(((float)t + 0.5f) * g.inv_tiles_x), txi = t - tyi * g.tiles_x;
-            const int x0 = txi * g.tw, y0 = tyi * g.th;
-            const int tw = min(g.tw, g.wo - x0), th = min(g.th, g.ho - y0);
-            // lanes 0..3: the four corners, with the per-pixel expression (warp_affine_naive.cpp:23-24)
-            const int dx = (lane & 1) ? x0 + tw - 1 : x0, dy = (lane & 2) ? y0 + th - 1 : y0;
-            const float fx = m[0] * (float)dx + m[1] * (float)dy + m[2];
-            const float fy = m[3] * (float)dx + m[4] * (float)dy + m[5];
-            const float kBig = 16777216.f;
-            const bool finite = fx > -kBig && fx < kBig && fy > -kBig && fy < kBig;   // false for NaN too
-            int sx = finite ? (int)floorf(fx) : 0, sy = finite ? (int)floorf(fy) : 0;
-            int sx_lo = sx, sx_hi = sx, sy_lo = sy, sy_hi = sy;
-#pragma unroll
-            for (int o = 1; o <= 2; o <<= 1) {
-                sx_lo = min(sx_lo, __shfl_xor_sync(0xffffffffu, sx_lo, o)); sx_hi = max(sx_hi, __shfl_xor_sync(0xffffffffu, sx_hi, o));
-                sy_lo = min(sy_lo, __shfl_xor_sync(0xffffffffu, sy_lo, o)); sy_hi = max(sy_hi, __shfl_xor_sync(0xffffffffu, sy_hi, o));
-            }
-            const bool all_finite = __all_sync(0xffffffffu, finite);   // lanes 4..31 repeat the corners of lanes 0..3
-            // taps of the tile: columns sx_lo .. sx_hi + 1, rows sy_lo .. sy_hi + 1
-            const int bx_lo = ((sx_lo * 3) >> 4) << 4;                       // floor to 16 bytes (arithmetic shift: negative too)
-            const int bx_hi = (((sx_hi + 2) * 3 + 15) >> 4) << 4;
-            const int bw = bx_hi - bx_lo, bh = sy_hi + 2 - sy_lo;
-            const int k = bw <= 144 ? 0 : (bw - 144 + 63) >> 6;
-            const int pitch = ws_box_bytes(k), nops = (bh + kWsBoxRows - 1) / kWsBoxRows;
-            const int need = nops * kWsBoxRows * pitch;                      // a multiple of 256 bytes
-            const bool staged = all_finite && k < kWsMaps && nops <= 32 && need <= kWsRingBytes;
-            if (it >= kWsSlots && tail_it <= it - kWsSlots) wait_release();   // the slot itself (tile it - kWsSlots)
-            int pos = 0;
-            if (staged) {
-                for (;;) {
-                    pos = head + need > kWsRingBytes ? 0 : head;
-                    if (!__ballot_sync(0xffffffffu, my_active && pos < my_end && my_start < pos + need)) break;
-                    wait_release();
+        TileInfo cur, nxt;
+        geometry(grp, cur);
+        for (int it0 = 0; it0 < n_my; it0 += kG) {
+            geometry(it0 + kG + grp, nxt);   // next pass: its matrix loads are in flight while this pass is handed out
+            for (int gg = 0; gg < kG && it0 + gg < n_my; ++gg) {   // warp-uniform: ring space is handed out in tile order
+                const int it = it0 + gg, slot = it & (kWsSlots - 1);
+                const int need = __shfl_sync(0xffffffffu, cur.need, kGL * gg);
+                const bool staged = __shfl_sync(0xffffffffu, cur.staged, kGL * gg) != 0;
+                if (it >= kWsSlots && tail_it <= it - kWsSlots) wait_release();   // the slot itself (tile it - kWsSlots)
+                int pos = 0;
+                if (staged) {
+                    for (;;) {
+                        pos = head + need > kWsRingBytes ? 0 : head;
+                        if (!__ballot_sync(0xffffffffu, my_active && pos < my_end && my_start < pos + need)) break;
+                        wait_release();
+                    }
+                    head = pos + need;
+                    if (lane == slot) { my_start = pos; my_end = pos + need; my_active = true; }
                 }
-                head = pos + need;
-                if (lane == slot) { my_start = pos; my_end = pos + need; my_active = true; }
-            }
-            if (lane == 0) {
-                WsDesc& d = desc[slot];
-                d.crop = crop; d.frame = frame; d.x0 = x0; d.y0 = y0; d.tw = tw; d.npx = tw * th;
-                d.sy_lo = sy_lo; d.bx_lo = bx_lo; d.pitch = pitch; d.staged = staged ? 1 : 0; d.pos = pos;
-                if (tw == g.tw) { d.magic = full_magic; d.step_y = full_step_y; d.step_x = full_step_x; }
-                else { d.magic = 65536 / tw + 1; d.step_y = NT / tw; d.step_x = NT - d.step_y * tw; }
+                if (grp == gg) {   // the tile's own 8 lanes
+                    if (sub == 0) {
+                        WsDesc& d = desc[slot];
+                        d.crop = cur.crop; d.frame = cur.frame; d.x0 = cur.x0; d.y0 = cur.y0; d.tw = cur.tw; d.npx = cur.tw * cur.th;
+                        d.sy_lo = cur.sy_lo; d.bx_lo = cur.bx_lo; d.pitch = cur.pitch; d.staged = cur.staged; d.pos = pos;
+                        if (cur.tw == g.tw) { d.magic = full_magic; d.step_y = full_step_y; d.step_x = full_step_x; }
+                        else { d.magic = 65536 / cur.tw + 1; d.step_y = NT / cur.tw; d.step_x = NT - d.step_y * cur.tw; }
 #pragma unroll
-                for (int q = 0; q < 6; ++q) d.m[q] = m[q];
-                if (staged) mbar_expect_tx(&full_bar[slot], (uint32_t)need);
-                else mbar_arrive(&full_bar[slot]);
+                        for (int q = 0; q < 6; ++q) d.m[q] = cur.m[q];
+                        if (cur.staged) mbar_expect_tx(&full_bar[slot], (uint32_t)cur.need);
+                        else mbar_arrive(&full_bar[slot]);
+                    }
+                    if (cur.staged)
+                        for (int j = sub; j < cur.nops; j += kGL)
+                            tma_load_3d(stages_s + pos + j * kWsBoxRows * cur.pitch, tmap_of(cur.k), cur.bx_lo >> 2, cur.sy_lo + j * kWsBoxRows,
+                                        cur.frame, &full_bar[slot]);
+                }
+                __syncwarp();
             }
-            __syncwarp();
-            if (staged && lane < nops) {
-                const void* tmap = reinterpret_cast<const uint8_t*>(&maps) + (size_t)k * sizeof(CUtensorMap);
-                tma_load_3d(stages_s + pos + lane * kWsBoxRows * pitch, tmap, bx_lo >> 2, sy_lo + lane * kWsBoxRows, frame, &full_bar[slot]);
-            }
-#pragma unroll
-            for (int q = 0; q < 6; ++q) m[q] = m_next[q];
-            frame = frame_next; crop = crop_next; t = t_next;
+            cur = nxt;
         }
         return;
     }
