@@ -3,7 +3,7 @@
 //
 //   work item = one output tile (TW x TH pixels, about 28 x 28: square tiles keep the bounding box of a rotated
 //               footprint small) of one crop; persistent CTAs stride over the items.
-//   producer  = warp 8.  Its lanes evaluate the affine map at the tile's four corners with the per-pixel fp32
+//   producer  = the last warp.  Its lanes evaluate the affine map at the tile's four corners with the per-pixel fp32
 //               expression (each rounding step is monotone in dx and in dy, so the extremes over the tile sit on the
 //               corners): that is the exact range of tap columns / rows of the tile.  The window is fetched by 3-D tiled
 //               TMA copies (cp.async.bulk.tensor, SASS UTMALDG) of 16 rows each from a tensor map over the frame pool
@@ -32,9 +32,9 @@ namespace vacv {
 
 constexpr int kWsMaps = 7;             // box widths 144 + 64 k bytes
 constexpr int kWsBoxRows = 16;
-constexpr int kWsRingBytes = 100 * 1024;
-constexpr int kWsCtasPerSm = 2; // shared-memory ring of source windows per CTA (2 CTAs per SM: measured best, see DESIGN)
-constexpr int kWsSlots = 8;             // tiles in flight per CTA (descriptor + full / empty barrier each)
+constexpr int kWsRingBytes = 100 * 1024;   // shared-memory ring of source windows per CTA
+constexpr int kWsCtasPerSm = 2;            // 2 x 100 KB measured best (ring depth beats occupancy)
+constexpr int kWsSlots = 8;                // tiles in flight per CTA (descriptor + full / empty barrier each)
 __host__ __device__ constexpr int ws_box_bytes(int k) { return 144 + 64 * k; }
 
 struct WarpStagedMaps { CUtensorMap m[kWsMaps]; };
