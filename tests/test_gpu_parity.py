@@ -395,6 +395,7 @@ STAGED_CASES = [
                           [1e-3, 0, 5, 0, 1e-3, 5], [1e30, 0, 0, 0, 1e30, 0]]),                                        # huge / overflowing coordinates
     (1280, 720, 240, 240, [M_TEST, _similarity(1.0, 0, 640, 360, 240, 240), _similarity(1.7, -20, 600, 300, 240, 240)]),
     (336, 64, 64, 40, [_similarity(0.5, 4, 168, 32, 64, 40), [0.5, 0, 0, 0, 0.5, 0]]),                                 # narrow frame, exact half scale
+    (328, 200, 112, 112, [_similarity(0.45, 7, 160, 100, 112, 112), _similarity(0.6, -11, 30, 170, 112, 112)]),        # rows not a multiple of 16 bytes: no tensor map, gather kernel
 ]
 
 
