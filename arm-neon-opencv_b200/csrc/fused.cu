@@ -555,6 +555,11 @@ extern "C" int vacv_cuda_resize_normalize(const uint8_t* src, float* dst, int ba
     const int rows_per_cta = max(1, min(h_out, (8192 + w_out - 1) / w_out));
     dim3 grid(ceil_div(h_out, rows_per_cta), batch);
     cudaStream_t s = as_stream(stream);
+    if (c == 3 && !getenv("VACV_RESIZE_NORMALIZE_GATHER")) {   // persistent TMA pipeline where the shape qualifies (small or integer ratios, 16-byte rows)
+        const int rc = try_launch_resize_pipe_u8c3(src, dst, batch, w, h, w_out, h_out, false, out_layout == VACV_NCHW ? 1 : 2, mean, stddev, s);
+        if (rc < 0) return rc;
+        if (rc > 0) return check_launch("resize_normalize (persistent)");
+    }
     const bool words = c == 3 && (((size_t)w * h * 3) % 4) == 0 && ((uintptr_t)src % 4) == 0 && (size_t)w * h * 3 < 0xfffffff0ull;
     if (words) {   // word-granular taps
         dim3 g3(ceil_div(w_out, 32), ceil_div(h_out, kRnRows), batch), b3(32, 8);

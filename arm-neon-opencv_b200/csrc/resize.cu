@@ -431,20 +431,20 @@ static int host_linear_index_r(int d, double scale, int n_in) {
     return sx;
 }
 
-template <bool kSigned, bool kBand>
+template <bool kSigned, bool kBand, int OUT = kRpOutU8>
 static const void* resize_pipe_kernel_for(int ncol) {
     switch (ncol) {
-        case 1: return (const void*)resize_linear_u8c3_pipe_kernel<kSigned, 1, kBand>;
-        case 2: return (const void*)resize_linear_u8c3_pipe_kernel<kSigned, 2, kBand>;
-        case 3: return (const void*)resize_linear_u8c3_pipe_kernel<kSigned, 3, kBand>;
-        default: return (const void*)resize_linear_u8c3_pipe_kernel<kSigned, 4, kBand>;
+        case 1: return (const void*)resize_linear_u8c3_pipe_kernel<kSigned, 1, kBand, false, OUT>;
+        case 2: return (const void*)resize_linear_u8c3_pipe_kernel<kSigned, 2, kBand, false, OUT>;
+        case 3: return (const void*)resize_linear_u8c3_pipe_kernel<kSigned, 3, kBand, false, OUT>;
+        default: return (const void*)resize_linear_u8c3_pipe_kernel<kSigned, 4, kBand, false, OUT>;
     }
 }
 
 // Persistent TMA kernel for u8 BGR bilinear (resize_pipe_u8c3.cuh).  1 = launched, 0 = shape not eligible, < 0 = error.
 // Shape-dependent part of a launch, cached per host thread (a stream of equally shaped calls pays it once).
 struct ResizePipePlan {
-    int w, h, wo, ho, device; bool signed_char;                   // key
+    int w, h, wo, ho, device, out_mode; bool signed_char;         // key (out_mode: kRpOut*)
     bool eligible; ResizePipeGeom g; const void* kern; int threads, per_sm, sms; size_t smem;
 };
 
@@ -481,7 +481,7 @@ static int build_resize_pipe_plan(ResizePipePlan& plan) {
     if (ncol < 2) ncol = 2;
     if (const char* e = getenv("VACV_RPIPE_NCOL")) { const int v = atoi(e); if (v >= 1 && v <= kRpMaxCols && (wo + v - 1) / v <= kRpThreads) ncol = v; }   // tuning knob
     const int threads = std::min(kRpThreads, ((wo + ncol - 1) / ncol + 31) & ~31);
-    const size_t lines = (size_t)(threads / 32) * ncol * 96;
+    const size_t lines = (size_t)(threads / 32) * ncol * (plan.out_mode == kRpOutF32HWC ? 384 : 96);
     int best_TH = 0; size_t best_smem = 0;
     for (int TH = kRpMaxTH; TH >= 1; --TH) {
         int rows = 0, tmp[2 * kRpMaxTH];
@@ -509,7 +509,9 @@ static int build_resize_pipe_plan(ResizePipePlan& plan) {
             any_right = (int)(x + (x >= 0.f ? 0.5f : -0.5f)) != 0;
         }
     }
-    const void* kern = band ? (signed_char ? resize_pipe_kernel_for<true, true>(ncol) : resize_pipe_kernel_for<false, true>(ncol))
+    const void* kern = plan.out_mode == kRpOutF32CHW ? (band ? resize_pipe_kernel_for<false, true, kRpOutF32CHW>(ncol) : resize_pipe_kernel_for<false, false, kRpOutF32CHW>(ncol))
+                     : plan.out_mode == kRpOutF32HWC ? (band ? resize_pipe_kernel_for<false, true, kRpOutF32HWC>(ncol) : resize_pipe_kernel_for<false, false, kRpOutF32HWC>(ncol))
+                     : band ? (signed_char ? resize_pipe_kernel_for<true, true>(ncol) : resize_pipe_kernel_for<false, true>(ncol))
                      : !any_right && ncol == 2 ? (const void*)resize_linear_u8c3_pipe_kernel<false, 2, false, true>   // pure byte moves: signedness irrelevant
                             : (signed_char ? resize_pipe_kernel_for<true, false>(ncol) : resize_pipe_kernel_for<false, false>(ncol));
     const int dev = plan.device;
@@ -530,16 +532,18 @@ static int build_resize_pipe_plan(ResizePipePlan& plan) {
 }
 
 // Persistent TMA kernel for u8 BGR bilinear (resize_pipe_u8c3.cuh).  1 = launched, 0 = shape not eligible, < 0 = error.
-static int try_launch_resize_pipe_u8c3(const uint8_t* src, uint8_t* dst, int images, int w, int h, int wo, int ho, bool signed_char, cudaStream_t s) {
+// out_mode kRpOutU8: dst = u8 BGR; kRpOutF32CHW / kRpOutF32HWC (resize_normalize): dst = fp32, mean / stddev = 3 floats each (device).
+int vacv::try_launch_resize_pipe_u8c3(const uint8_t* src, void* dst, int images, int w, int h, int wo, int ho, bool signed_char, int out_mode,
+                                      const float* mean, const float* stddev, cudaStream_t s) {
     if (((uintptr_t)src & 15) != 0) return 0;
     static thread_local ResizePipePlan plan = {};
     static thread_local bool have_plan = false;
     int dev = 0;
     cudaGetDevice(&dev);
     if (!have_plan || plan.w != w || plan.h != h || plan.wo != wo || plan.ho != ho || plan.signed_char != signed_char || plan.device != dev ||
-        getenv("VACV_RPIPE_NCOL")) {
+        plan.out_mode != out_mode || getenv("VACV_RPIPE_NCOL")) {
         have_plan = false;
-        plan.w = w; plan.h = h; plan.wo = wo; plan.ho = ho; plan.signed_char = signed_char; plan.device = dev;
+        plan.w = w; plan.h = h; plan.wo = wo; plan.ho = ho; plan.signed_char = signed_char; plan.device = dev; plan.out_mode = out_mode;
         const int rc = build_resize_pipe_plan(plan);
         if (rc < 0) return rc;
         have_plan = true;
@@ -550,7 +554,7 @@ static int try_launch_resize_pipe_u8c3(const uint8_t* src, uint8_t* dst, int ima
     if (total > 0x7fffffffLL - 4096) return 0;
     g.total_tiles = (int)total;
     const int grid = (int)std::min<long long>(total, (long long)plan.sms * plan.per_sm);
-    void* args[] = {(void*)&src, (void*)&dst, (void*)&g};
+    void* args[] = {(void*)&src, (void*)&dst, (void*)&g, (void*)&mean, (void*)&stddev};
     const cudaError_t e = cudaLaunchKernel(plan.kern, dim3(grid), dim3(plan.threads), args, plan.smem, s);
     if (e != cudaSuccess) return set_error(VACV_ERR_CUDA, "resize: %s", cudaGetErrorString(e));
     return 1;
@@ -602,7 +606,7 @@ extern "C" int vacv_cuda_resize(const void* src, void* dst, int batch, int w, in
         uint8_t* dp = (uint8_t*)dst + (size_t)i0 * g.dst_image * es;
         const bool c3_words = g.c == 3 && (((size_t)w * h * 3) % 4) == 0 && ((uintptr_t)src % 4) == 0 && (size_t)w * h * 3 < 0xfffffff0ull;
         if (!cubic && dtype == VACV_INT8 && c3_words && !(flags & (VACV_FLAG_NEON_RULE | VACV_FLAG_DIRECT_GATHER)) && !getenv("VACV_NO_RPIPE")) {
-            const int rc = try_launch_resize_pipe_u8c3(sp, dp, ni, w, h, w_out, h_out, (flags & VACV_FLAG_SIGNED_CHAR) != 0, s);
+            const int rc = try_launch_resize_pipe_u8c3(sp, dp, ni, w, h, w_out, h_out, (flags & VACV_FLAG_SIGNED_CHAR) != 0, kRpOutU8, nullptr, nullptr, s);
             if (rc < 0) return rc;
             if (rc > 0) continue;
         }

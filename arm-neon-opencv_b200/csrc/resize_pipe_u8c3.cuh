@@ -56,9 +56,19 @@ struct ResizePipeGeom {
 // kPoint (with !kBand): additionally no right tap has weight (odd integer ratio in x as well, e.g. 1920x1080 -> 640x360): every
 // weight pair is (2048, 0), the reference's integer blend (p * 2048 * 2048) >> 22 returns the tap itself and the kernel only
 // moves bytes.
-template <bool kSigned, int NCOL, bool kBand, bool kPoint = false>
+// OUT: kRpOutU8 = the resized u8 BGR image (a5); kRpOutF32CHW / kRpOutF32HWC = resize_normalize (a13): every blended byte goes
+// through the exact 3 x 256 normalisation table (built once per persistent CTA) and leaves as fp32 planes (lane-contiguous
+// 128-byte stores per plane) or as interleaved fp32 (re-chunked per warp like the u8 bytes).
+enum { kRpOutU8 = 0, kRpOutF32CHW = 1, kRpOutF32HWC = 2 };
+
+template <bool kSigned, int NCOL, bool kBand, bool kPoint = false, int OUT = kRpOutU8>
 __global__ void __launch_bounds__(kRpThreads, NCOL <= 2 || !kBand ? 2 : 1)
-resize_linear_u8c3_pipe_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, ResizePipeGeom g) {
+resize_linear_u8c3_pipe_kernel(const uint8_t* __restrict__ src, void* __restrict__ dst_, ResizePipeGeom g,
+                               const float* __restrict__ mean, const float* __restrict__ stddev) {
+    static_assert(!kPoint || OUT == kRpOutU8, "the byte-moving variant exists for u8 output only");
+    uint8_t* const dst = reinterpret_cast<uint8_t*>(dst_);
+    float* const dstf = reinterpret_cast<float*>(dst_);
+    __shared__ float lut[OUT == kRpOutU8 ? 1 : 768];
     extern __shared__ __align__(128) uint8_t dyn_smem[];     // [s_sy: ho][s_cy: ho][pad] 2 x stage, then per-warp output lines
     int* s_sy = reinterpret_cast<int*>(dyn_smem);
     int* s_cy = s_sy + g.ho;
@@ -67,7 +77,8 @@ resize_linear_u8c3_pipe_kernel(const uint8_t* __restrict__ src, uint8_t* __restr
     uint8_t* stages = dyn_smem + g.table_bytes;
     __shared__ __align__(8) uint64_t full_bar[2];
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
-    uint32_t* line = reinterpret_cast<uint32_t*>(stages + 2 * (size_t)g.stage_bytes) + warp * (NCOL * 24);   // per warp: NCOL x 96 bytes
+    constexpr int kLineWords = OUT == kRpOutF32HWC ? 96 : 24;   // per warp and column group: 32 pixels x 3 channels as bytes / floats
+    uint32_t* line = reinterpret_cast<uint32_t*>(stages + 2 * (size_t)g.stage_bytes) + warp * (NCOL * kLineWords);
     const unsigned row_bytes = (unsigned)g.w * 3u;
     const uint32_t stages_s = smem_u32(stages), sy_s = smem_u32(s_sy), cy_s = smem_u32(s_cy), slot_s = smem_u32(s_slot);
 
@@ -76,6 +87,9 @@ resize_linear_u8c3_pipe_kernel(const uint8_t* __restrict__ src, uint8_t* __restr
         mbar_init(&full_bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (OUT != kRpOutU8)
+        for (int t = tid; t < 768; t += nthr)
+            lut[t] = normalize_one((float)(t & 255), __ldg(mean + (t >> 8)), (double)__ldg(stddev + (t >> 8)) + 1e-6);
     const double scale_x = (double)((float)g.w / (float)g.wo), scale_y = (double)((float)g.h / (float)g.ho);
     for (int dy = tid; dy < g.ho; dy += nthr) {
         int s; float f;
@@ -205,25 +219,55 @@ resize_linear_u8c3_pipe_kernel(const uint8_t* __restrict__ src, uint8_t* __restr
                     have = -2;
                 }
             }
-            uint8_t* lb = reinterpret_cast<uint8_t*>(line);
-            if (!kPoint) {
+            if (OUT == kRpOutU8) {
+                uint8_t* lb = reinterpret_cast<uint8_t*>(line);
+                if (!kPoint) {
+#pragma unroll
+                    for (int j = 0; j < NCOL; ++j) {
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) lb[j * 96 + 3 * lane + k] = (uint8_t)((H0[j][k] * cy0 + H1[j][k] * cy1) >> 22);   // resize_naive.cpp:60-65
+                    }
+                }
+                __syncwarp();
 #pragma unroll
                 for (int j = 0; j < NCOL; ++j) {
+                    const int c0 = (tid & ~31) + j * nthr;             // first column of this warp's j-th group
+                    if (c0 >= g.wo) continue;                          // warp-uniform
+                    uint8_t* o = orow + (size_t)c0 * 3;
+                    const int n = min(32, g.wo - c0);
+                    if (n == 32 && (reinterpret_cast<uintptr_t>(o) & 3) == 0) { if (lane < 24) st_stream4(o + 4 * lane, line[j * 24 + lane]); }
+                    else for (int bb = lane; bb < 3 * n; bb += 32) o[bb] = lb[j * 96 + bb];
+                }
+                __syncwarp();
+            } else {
+                // the u8 value the unfused resize would have stored, then the exact table
+                const size_t plane = (size_t)g.wo * g.ho;
+                const size_t prow = (size_t)(dy0 + ty) * g.wo;
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) lb[j * 96 + 3 * lane + k] = (uint8_t)((H0[j][k] * cy0 + H1[j][k] * cy1) >> 22);   // resize_naive.cpp:60-65
+                for (int j = 0; j < NCOL; ++j) {
+                    const int c0 = (tid & ~31) + j * nthr, col = c0 + lane;
+                    if (c0 >= g.wo) continue;                          // warp-uniform
+                    float r[3];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) r[k] = lut[k * 256 + (((H0[j][k] * cy0 + H1[j][k] * cy1) >> 22) & 0xff)];
+                    if (OUT == kRpOutF32CHW) {
+                        float* o = dstf + (size_t)frame * 3 * plane + prow + col;
+                        if (col < g.wo) { st_stream4f(o, r[0]); st_stream4f(o + plane, r[1]); st_stream4f(o + 2 * plane, r[2]); }
+                    } else {
+                        float* sf = reinterpret_cast<float*>(line) + j * 96;
+                        sf[3 * lane] = r[0]; sf[3 * lane + 1] = r[1]; sf[3 * lane + 2] = r[2];
+                        __syncwarp();
+                        float* o = dstf + ((size_t)frame * plane + prow + c0) * 3;
+                        const int n = min(32, g.wo - c0);
+                        if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+                            if (4 * lane < 3 * n) st_stream16f(o + 4 * lane, *reinterpret_cast<const float4*>(sf + 4 * lane));
+                        } else {
+                            for (int e = lane; e < 3 * n; e += 32) st_stream4f(o + e, sf[e]);
+                        }
+                        __syncwarp();
+                    }
                 }
             }
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < NCOL; ++j) {
-                const int c0 = (tid & ~31) + j * nthr;             // first column of this warp's j-th group
-                if (c0 >= g.wo) continue;                          // warp-uniform
-                uint8_t* o = orow + (size_t)c0 * 3;
-                const int n = min(32, g.wo - c0);
-                if (n == 32 && (reinterpret_cast<uintptr_t>(o) & 3) == 0) { if (lane < 24) st_stream4(o + 4 * lane, line[j * 24 + lane]); }
-                else for (int bb = lane; bb < 3 * n; bb += 32) o[bb] = lb[j * 96 + bb];
-            }
-            __syncwarp();
         }
         __syncthreads();   // all reads of stage b done -> it may be refilled by the next iteration's issue
     }

@@ -694,7 +694,9 @@ def test_fused_pipeline_vs_reference_chain(vacv):
 
 
 @pytest.mark.parametrize("out_layout", [NHWC, NCHW])
-@pytest.mark.parametrize("w,h,wo,ho", [(640, 360, 224, 200), (1920, 1080, 640, 360), (333, 211, 500, 300), (64, 48, 37, 45)])
+@pytest.mark.parametrize("w,h,wo,ho", [(640, 360, 224, 200), (1920, 1080, 640, 360), (333, 211, 500, 300), (64, 48, 37, 45),
+                                       (1920, 1080, 640, 640), (1280, 720, 416, 416), (1920, 1080, 1536, 864), (640, 360, 321, 181),
+                                       (1920, 1080, 500, 300)])
 def test_resize_normalize_fused(vacv, oracle, out_layout, w, h, wo, ho):
     c, b = 3, 2
     src = u8(22, b, h, w, c)
