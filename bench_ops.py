@@ -221,6 +221,8 @@ def ops(iters):
     report("op resize linear u8 2560x1440->320x180 x64", ms, 64 * 320 * 180, 64 * (2560 * 1440 * 3 // 4 + 320 * 180 * 3), "bytes: 2 of 8 rows touched")
     ms, _ = timeit(lambda: vacv.resize_normalize(bgr, 640, 640, mean, std, vacv.NCHW), iters)
     report("op resize_normalize u8 hwc 1080p->640x640 chw x128", ms, b * 640 * 640, b * (1920 * 1080 * 3 + 640 * 640 * 12))
+    ms, _ = timeit(lambda: vacv.resize_normalize(bgr, 640, 640, mean, std, vacv.NHWC), iters)
+    report("op resize_normalize u8 hwc 1080p->640x640 hwc x128", ms, b * 640 * 640, b * (1920 * 1080 * 3 + 640 * 640 * 12))
 
 
 def ops2(iters):   # shapes off the headline path: planar layouts, fp32 gathers, generic channel counts
