@@ -13,6 +13,7 @@
 #include "resize_coeffs.cuh"
 #include "gather_u8c3.cuh"
 #include "resize_pipe_u8c3.cuh"
+#include "resize_pipe_u8c1.cuh"
 
 namespace vacv {
 
@@ -441,10 +442,21 @@ static const void* resize_pipe_kernel_for(int ncol) {
     }
 }
 
-// Persistent TMA kernel for u8 BGR bilinear (resize_pipe_u8c3.cuh).  1 = launched, 0 = shape not eligible, < 0 = error.
+template <bool kSigned, bool kBand>
+static const void* resize_pipe_c1_kernel_for(int ncol) {
+    switch (ncol) {
+        case 1: return (const void*)resize_linear_u8c1_pipe_kernel<kSigned, 1, kBand>;
+        case 2: return (const void*)resize_linear_u8c1_pipe_kernel<kSigned, 2, kBand>;
+        case 3: return (const void*)resize_linear_u8c1_pipe_kernel<kSigned, 3, kBand>;
+        default: return (const void*)resize_linear_u8c1_pipe_kernel<kSigned, 4, kBand>;
+    }
+}
+
+// Persistent TMA kernel for u8 bilinear, BGR (resize_pipe_u8c3.cuh) or single planes (resize_pipe_u8c1.cuh).
+// 1 = launched, 0 = shape not eligible, < 0 = error.
 // Shape-dependent part of a launch, cached per host thread (a stream of equally shaped calls pays it once).
 struct ResizePipePlan {
-    int w, h, wo, ho, device, out_mode; bool signed_char;         // key (out_mode: kRpOut*)
+    int w, h, wo, ho, device, out_mode, c; bool signed_char;      // key (out_mode: kRpOut*, c: 3 = BGR, 1 = planes)
     bool eligible; ResizePipeGeom g; const void* kern; int threads, per_sm, sms; size_t smem;
 };
 
@@ -452,7 +464,8 @@ static int build_resize_pipe_plan(ResizePipePlan& plan) {
     const int w = plan.w, h = plan.h, wo = plan.wo, ho = plan.ho;
     const bool signed_char = plan.signed_char;
     plan.eligible = false;
-    if (((size_t)w * 3) % 16 != 0) return 0;                                         // bulk copies: 16-byte granularity
+    const int c = plan.c;
+    if (((size_t)w * c) % 16 != 0) return 0;                                         // bulk copies: 16-byte granularity
     if (wo > kRpThreads * kRpMaxCols || ho > 8192) return 0;
     const double scale_y = (double)((float)h / (float)ho);
     std::vector<int> sy(ho), cy(ho);   // cy: only "lower tap has weight" (bit 16), which is all tile_rows() looks at
@@ -473,15 +486,15 @@ static int build_resize_pipe_plan(ResizePipePlan& plan) {
     for (int d = 0; d < ho; ++d) any_low = any_low || cy[d] != 0;
     const bool band = h <= 2 * ho && any_low;
     if (!band && any_low) return 0;
-    const size_t row_bytes = (size_t)w * 3;
+    const size_t row_bytes = (size_t)w * c;
     ResizePipeGeom& g = plan.g;
     g.w = w; g.h = h; g.wo = wo; g.ho = ho;
-    g.src_image = row_bytes * h; g.dst_image = (size_t)wo * ho * 3;
+    g.src_image = row_bytes * h; g.dst_image = (size_t)wo * ho * c;
     int ncol = (wo + kRpThreads - 1) / kRpThreads;
     if (ncol < 2) ncol = 2;
     if (const char* e = getenv("VACV_RPIPE_NCOL")) { const int v = atoi(e); if (v >= 1 && v <= kRpMaxCols && (wo + v - 1) / v <= kRpThreads) ncol = v; }   // tuning knob
     const int threads = std::min(kRpThreads, ((wo + ncol - 1) / ncol + 31) & ~31);
-    const size_t lines = (size_t)(threads / 32) * ncol * (plan.out_mode == kRpOutF32HWC ? 384 : 96);
+    const size_t lines = (size_t)(threads / 32) * ncol * (c == 1 ? 32 : plan.out_mode == kRpOutF32HWC ? 384 : 96);
     int best_TH = 0; size_t best_smem = 0;
     for (int TH = kRpMaxTH; TH >= 1; --TH) {
         int rows = 0, tmp[2 * kRpMaxTH];
@@ -509,7 +522,9 @@ static int build_resize_pipe_plan(ResizePipePlan& plan) {
             any_right = (int)(x + (x >= 0.f ? 0.5f : -0.5f)) != 0;
         }
     }
-    const void* kern = plan.out_mode == kRpOutF32CHW ? (band ? resize_pipe_kernel_for<false, true, kRpOutF32CHW>(ncol) : resize_pipe_kernel_for<false, false, kRpOutF32CHW>(ncol))
+    const void* kern = c == 1 ? (band ? (signed_char ? resize_pipe_c1_kernel_for<true, true>(ncol) : resize_pipe_c1_kernel_for<false, true>(ncol))
+                                      : (signed_char ? resize_pipe_c1_kernel_for<true, false>(ncol) : resize_pipe_c1_kernel_for<false, false>(ncol)))
+                     : plan.out_mode == kRpOutF32CHW ? (band ? resize_pipe_kernel_for<false, true, kRpOutF32CHW>(ncol) : resize_pipe_kernel_for<false, false, kRpOutF32CHW>(ncol))
                      : plan.out_mode == kRpOutF32HWC ? (band ? resize_pipe_kernel_for<false, true, kRpOutF32HWC>(ncol) : resize_pipe_kernel_for<false, false, kRpOutF32HWC>(ncol))
                      : band ? (signed_char ? resize_pipe_kernel_for<true, true>(ncol) : resize_pipe_kernel_for<false, true>(ncol))
                      : !any_right && ncol == 2 ? (const void*)resize_linear_u8c3_pipe_kernel<false, 2, false, true>   // pure byte moves: signedness irrelevant
@@ -534,16 +549,16 @@ static int build_resize_pipe_plan(ResizePipePlan& plan) {
 // Persistent TMA kernel for u8 BGR bilinear (resize_pipe_u8c3.cuh).  1 = launched, 0 = shape not eligible, < 0 = error.
 // out_mode kRpOutU8: dst = u8 BGR; kRpOutF32CHW / kRpOutF32HWC (resize_normalize): dst = fp32, mean / stddev = 3 floats each (device).
 int vacv::try_launch_resize_pipe_u8c3(const uint8_t* src, void* dst, int images, int w, int h, int wo, int ho, bool signed_char, int out_mode,
-                                      const float* mean, const float* stddev, cudaStream_t s) {
+                                      const float* mean, const float* stddev, cudaStream_t s, int c) {
     if (((uintptr_t)src & 15) != 0) return 0;
     static thread_local ResizePipePlan plan = {};
     static thread_local bool have_plan = false;
     int dev = 0;
     cudaGetDevice(&dev);
     if (!have_plan || plan.w != w || plan.h != h || plan.wo != wo || plan.ho != ho || plan.signed_char != signed_char || plan.device != dev ||
-        plan.out_mode != out_mode || getenv("VACV_RPIPE_NCOL")) {
+        plan.out_mode != out_mode || plan.c != c || getenv("VACV_RPIPE_NCOL")) {
         have_plan = false;
-        plan.w = w; plan.h = h; plan.wo = wo; plan.ho = ho; plan.signed_char = signed_char; plan.device = dev; plan.out_mode = out_mode;
+        plan.w = w; plan.h = h; plan.wo = wo; plan.ho = ho; plan.signed_char = signed_char; plan.device = dev; plan.out_mode = out_mode; plan.c = c;
         const int rc = build_resize_pipe_plan(plan);
         if (rc < 0) return rc;
         have_plan = true;
@@ -617,6 +632,11 @@ extern "C" int vacv_cuda_resize(const void* src, void* dst, int batch, int w, in
             else if (sc) resize_linear_u8c3_kernel<true, false><<<grid, block, 0, s>>>(sp, dp, g);
             else resize_linear_u8c3_kernel<false, false><<<grid, block, 0, s>>>(sp, dp, g);
         } else if (!cubic && dtype == VACV_INT8 && g.c == 1 && (((size_t)w * h) % 4) == 0 && ((uintptr_t)src % 4) == 0 && (size_t)w * h < 0xfffffff0ull) {
+            if (!(flags & (VACV_FLAG_NEON_RULE | VACV_FLAG_DIRECT_GATHER)) && !getenv("VACV_NO_RPIPE")) {   // persistent TMA pipeline for planes
+                const int rc = try_launch_resize_pipe_u8c3(sp, dp, ni, w, h, w_out, h_out, (flags & VACV_FLAG_SIGNED_CHAR) != 0, kRpOutU8, nullptr, nullptr, s, 1);
+                if (rc < 0) return rc;
+                if (rc > 0) continue;
+            }
             const bool sc = flags & VACV_FLAG_SIGNED_CHAR;
             grid.x = ceil_div(w_out, kC1Cols);
             grid.y = ceil_div(h_out, kC3Rows);

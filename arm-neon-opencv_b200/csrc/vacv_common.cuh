@@ -16,7 +16,7 @@ int check_launch(const char* what);
 // resize.cu: persistent TMA kernel for u8 BGR bilinear (resize_pipe_u8c3.cuh); out_mode 0 = u8 BGR, 1 = normalised fp32 CHW planes,
 // 2 = normalised fp32 HWC.  Returns 1 = launched, 0 = shape not eligible, < 0 = error.
 int try_launch_resize_pipe_u8c3(const uint8_t* src, void* dst, int images, int w, int h, int wo, int ho, bool signed_char, int out_mode,
-                                const float* mean, const float* stddev, cudaStream_t s);
+                                const float* mean, const float* stddev, cudaStream_t s, int c = 3);   // c = 1: single planes (u8 output only)
 
 #define VACV_REQUIRE(cond, ...)                                                 \
     do {                                                                        \
