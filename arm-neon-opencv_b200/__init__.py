@@ -49,6 +49,14 @@ _SIGS = {
     "vacv_cuda_nv_resize_normalize_chw_host": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i],
     "vacv_cuda_resize_normalize": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp],
     "vacv_cuda_warp_affine_normalize": [_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _vp],
+    "vacv_cuda_normalize_batch_global_cb": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "vacv_cuda_normalize_batch_global_p2p": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "vacv_cuda_p2p_create": [_vp, _i, _i, _vp],
+    "vacv_cuda_p2p_connect": [_vp, _vp],
+    "vacv_cuda_p2p_destroy": [_vp],
+    "vacv_cuda_p2p_allreduce_u64": [_vp, _vp, _i, _vp],
+    "vacv_cuda_p2p_status": [_vp, _vp],
+    "vacv_cuda_set_last_error": [_i, C.c_char_p],
     "vacv_cuda_device_count": [_vp],
     "vacv_cuda_set_device": [_i],
     "vacv_cuda_malloc": [_vp, _sz],
@@ -69,6 +77,34 @@ for _name, _args in _SIGS.items():
     _fn.argtypes = _args
     _fn.restype = None if _name.startswith(("vacv_invert", "vacv_rotation", "vacv_letterbox")) else _i
 EXPORTS = ["vacv_cuda_abi_version", "vacv_cuda_last_error"] + list(_SIGS)
+
+
+# libvacv_dist.so = the NCCL transport of config 5 (include/vacv_dist.h); loaded on first use so that single-GPU users of this
+# module never touch NCCL.  Import torch.distributed's NCCL first if you want both to share one libnccl.so.2.
+DIST_LIB_PATH = os.path.join(_HERE, "libvacv_dist.so")
+_DIST_SIGS = {
+    "vacv_cuda_normalize_batch_global": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "vacv_dist_allreduce_u64": [_vp, _vp, _i, _vp],
+    "vacv_dist_nccl_version": [_vp],
+    "vacv_dist_nccl_unique_id": [_vp],
+    "vacv_dist_nccl_comm_create": [_vp, _i, _i, _vp],
+    "vacv_dist_nccl_comm_destroy": [_vp],
+}
+_dist_lib = None
+
+
+def dist_lib():
+    global _dist_lib
+    if _dist_lib is None:
+        if not os.path.exists(DIST_LIB_PATH):
+            raise ImportError(f"{DIST_LIB_PATH} not built -- run __graft_entry__.build()")
+        d = C.CDLL(DIST_LIB_PATH)
+        for name, args in _DIST_SIGS.items():
+            fn = getattr(d, name)
+            fn.argtypes = args
+            fn.restype = _i
+        _dist_lib = d
+    return _dist_lib
 
 
 class VacvError(RuntimeError):

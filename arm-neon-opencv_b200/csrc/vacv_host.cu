@@ -30,6 +30,7 @@ int check_launch(const char* what) {
 
 extern "C" int vacv_cuda_abi_version(void) { return 1; }
 extern "C" const char* vacv_cuda_last_error(void) { return vacv::g_err; }
+extern "C" int vacv_cuda_set_last_error(int code, const char* message) { return vacv::set_error(code, "%s", message ? message : ""); }
 
 // warp_affine.cpp:121-133, types exactly as written there (float products widened afterwards; m[1] *= -D is
 // float*double rounded back to float; b1/b2 use the UPDATED m[0], m[1], m[3], m[4] in float arithmetic).

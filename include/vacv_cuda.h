@@ -57,6 +57,8 @@ enum {
 
 VACV_API int vacv_cuda_abi_version(void);
 VACV_API const char* vacv_cuda_last_error(void);
+/* for companion libraries (libvacv_dist.so) that report through the same thread-local message; returns `code` */
+VACV_API int vacv_cuda_set_last_error(int code, const char* message);
 
 /* ---- a1: CvtColor::nv_to_bgr_naive (src/cv/cvt_color.cpp:39-135) ------------------------------------------
  * src: batch x [Y plane w*h | interleaved chroma w*h/2];  dst: batch x (h x w x 3) BGR.  w, h even.
@@ -180,6 +182,48 @@ VACV_API int vacv_cuda_yuv_letterbox_normalize_chw(const uint8_t* src, const vac
 VACV_API int vacv_cuda_yuv_normalize_chw_host(const uint8_t* h_src, const vacv_yuv_layout* layout, void* h_dst, int out_dtype, int batch,
                                               int canvas_w, int canvas_h, const vacv_rect* content, const uint8_t* pad_bgr,
                                               const float* h_mean, const float* h_stddev, int chunk_frames);
+
+/* ---- config 5: batch-global statistics over a frame batch sharded across GPUs (north_star: "a single
+ * allreduce of per-GPU sum and sum-of-squares") ------------------------------------------------------------------------
+ * Semantics = Normalize::normalize_naive's auto-statistics branch (src/cv/normalize.cpp:84-121, :98-108) with the
+ * statistic taken over EVERY frame of EVERY rank instead of one image: per-channel exact u64 sums of this rank's shard ->
+ * one sum all-reduce of 2*c+1 u64 values ([2k] = Sx, [2k+1] = Sxx, [2c] = pixels per channel; 56 bytes for BGR, so ragged
+ * shards need no side channel) -> mean / population stddev in fp64, stored fp32 (identical bits on every rank, independent of
+ * the rank count) -> dst = (float)((double)(x - mean) / ((double)stddev + 1e-6)) over this rank's shard.
+ * Everything is enqueued on `stream`; nothing synchronises or allocates.
+ *   d_work      device scratch, >= 2*c+1 u64 (16-byte aligned), owned by the call while it is in flight
+ *   d_mean_std  device, 2*c floats: receives mean[0..c) then stddev[0..c) (also the normalise kernel's input)
+ *   ev_sums_done / ev_stats_ready   optional cudaEvent_t (NULL = none) recorded after the sums kernel and right before the
+ *               normalise kernel: their distance is the cost of the exchange + finalize (bench.py reports it)
+ * Three transports for the exchange:
+ *   _cb    the caller's own all-reduce (MPI, a framework collective ...): allreduce(ctx, d_buf, count, stream) must sum
+ *          `count` u64 values in place across ranks, stream-ordered, and return 0
+ *   _p2p   this library's peer-memory exchange (below): every rank stores its 56 bytes straight into every peer's slot over
+ *          NVLink / NVSwitch and polls its OWN memory -- one tiny kernel, no library call, CUDA-graph capturable
+ *   NCCL   vacv_cuda_normalize_batch_global(ncclComm_t, ...) in libvacv_dist.so (include/vacv_dist.h), which keeps
+ *          libvacv_cuda.so free of an NCCL dependency */
+typedef int (*vacv_allreduce_u64_fn)(void* ctx, unsigned long long* d_buf, int count, void* stream);
+VACV_API int vacv_cuda_normalize_batch_global_cb(vacv_allreduce_u64_fn allreduce, void* ctx, const uint8_t* src, float* dst,
+                                                 int batch, int w, int h, int c, int layout, unsigned long long* d_work,
+                                                 float* d_mean_std, void* ev_sums_done, void* ev_stats_ready, void* stream);
+
+/* Peer-memory exchange between the ranks of ONE node (one process per GPU; several ranks may share a GPU).
+ *   create   allocates this rank's slot buffer on the current device and returns its 64-byte IPC handle in h_handle
+ *   connect  h_handles = the nranks handles in rank order (the caller all-gathers them with whatever it has: MPI,
+ *            torch.distributed, a pipe); opens every peer's buffer (cudaIpcOpenMemHandle, peer access enabled lazily)
+ *   allreduce_u64   in-place sum of count <= 15 u64 values across ranks, stream-ordered.  Collective: every rank must issue
+ *            the same sequence of calls.  A rank that does not see all peers within ~20 s gives up and raises the status word
+ *   status   0 = ok, else the number of timed-out exchanges (synchronises the device) */
+#define VACV_P2P_HANDLE_BYTES 64
+#define VACV_P2P_MAX_RANKS 16
+VACV_API int vacv_cuda_p2p_create(void** xchg, int nranks, int rank, void* h_handle);
+VACV_API int vacv_cuda_p2p_connect(void* xchg, const void* h_handles);
+VACV_API int vacv_cuda_p2p_destroy(void* xchg);
+VACV_API int vacv_cuda_p2p_allreduce_u64(void* xchg, unsigned long long* d_buf, int count, void* stream);
+VACV_API int vacv_cuda_p2p_status(void* xchg, int* timed_out);
+VACV_API int vacv_cuda_normalize_batch_global_p2p(void* xchg, const uint8_t* src, float* dst, int batch, int w, int h, int c,
+                                                  int layout, unsigned long long* d_work, float* d_mean_std,
+                                                  void* ev_sums_done, void* ev_stats_ready, void* stream);
 
 /* ---- host-buffer entry point of the fused pipeline (the end-to-end path) ------------------------------------------
  * Same operation as vacv_cuda_nv_resize_normalize_chw, but `h_src` / `h_dst` / `h_mean` / `h_stddev` are HOST pointers

@@ -36,6 +36,35 @@ def test_library_exports_every_declared_symbol():
     assert not stray, f"non-API symbols leak from the library: {stray}"
 
 
+def test_dist_library_exports_what_vacv_dist_h_declares_and_validates_arguments():
+    """libvacv_dist.so (NCCL transport of config 5): symbols of include/vacv_dist.h, NCCL reachable, argument checks before any
+    CUDA / NCCL call; libvacv_cuda.so itself must stay free of an NCCL dependency."""
+    dist_lib = os.path.join(ROOT, "arm-neon-opencv_b200", "libvacv_dist.so")
+    assert os.path.exists(dist_lib), "run __graft_entry__.build() first"
+    text = open(os.path.join(ROOT, "include", "vacv_dist.h")).read()
+    declared = sorted(set(re.findall(r"VACV_API\s+[\w\s\*]+?\b(vacv_\w+)\s*\(", text)))
+    assert "vacv_cuda_normalize_batch_global" in declared and "vacv_dist_nccl_comm_create" in declared
+    out = subprocess.check_output(["nm", "-D", "--defined-only", dist_lib], text=True)
+    exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
+    assert sorted(exported) == declared
+    needed = subprocess.check_output(["readelf", "-d", LIB], text=True)
+    assert "nccl" not in needed.lower()
+    import vacv_b200 as vacv
+    d = vacv.dist_lib()
+    ver = C.c_int(0)
+    assert d.vacv_dist_nccl_version(C.byref(ver)) == 0 and ver.value >= 22700
+    buf = C.create_string_buffer(256)
+    p = C.cast(buf, C.c_void_p)
+    assert d.vacv_cuda_normalize_batch_global(None, p, p, 1, 8, 8, 3, vacv.NHWC, p, p, None, None, None) == -1
+    assert b"communicator" in vacv.lib.vacv_cuda_last_error()
+    assert d.vacv_dist_allreduce_u64(None, p, 7, None) == -1
+    assert d.vacv_dist_nccl_comm_create(p, 2, 5, p) == -1
+    # the transport-agnostic entries of libvacv_cuda.so
+    assert vacv.lib.vacv_cuda_normalize_batch_global_p2p(None, p, p, 1, 8, 8, 3, vacv.NHWC, p, p, None, None, None) == -1
+    assert vacv.lib.vacv_cuda_normalize_batch_global_cb(None, None, p, p, 1, 8, 8, 3, vacv.NHWC, p, p, None, None, None) == -1
+    assert vacv.lib.vacv_cuda_p2p_create(p, 99, 0, p) == -1 and b"ranks" in vacv.lib.vacv_cuda_last_error()
+
+
 def test_library_is_built_for_sm_100a_only():
     out = subprocess.check_output(["cuobjdump", "--list-elf", LIB], text=True)
     archs = set(re.findall(r"sm_\d+a?", out))
