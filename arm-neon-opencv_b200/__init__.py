@@ -59,12 +59,15 @@ _SIGS = {
     "vacv_cuda_set_last_error": [_i, C.c_char_p],
     "vacv_cuda_device_count": [_vp],
     "vacv_cuda_set_device": [_i],
+    "vacv_cuda_get_device": [_vp],
+    "vacv_cuda_set_tuning": [C.c_char_p, _i],
     "vacv_cuda_malloc": [_vp, _sz],
     "vacv_cuda_free": [_vp],
     "vacv_cuda_host_alloc": [_vp, _sz],
     "vacv_cuda_host_free": [_vp],
     "vacv_cuda_memcpy_h2d": [_vp, _vp, _sz, _vp],
     "vacv_cuda_memcpy_d2h": [_vp, _vp, _sz, _vp],
+    "vacv_cuda_memcpy2d_h2d": [_vp, _sz, _vp, _sz, _sz, _sz, _vp],
     "vacv_cuda_memset": [_vp, _i, _sz, _vp],
     "vacv_cuda_stream_create": [_vp],
     "vacv_cuda_stream_destroy": [_vp],

@@ -16,6 +16,7 @@
 // between consecutive output rows are served on chip.  Each thread owns output columns and walks down the rows,
 // carrying the horizontally interpolated row (3 ints) over when the next output row starts on it.
 // Stores: lanes = consecutive columns -> 128 B per warp per plane, streaming.
+#include "host_util.cuh"
 #include "vacv_common.cuh"
 #include "fused_pipeline.cuh"
 #include "gather_u8c3.cuh"
@@ -342,7 +343,7 @@ struct Canvas { int w, h, x0, y0; };   // destination plane size and where the w
 // thread, so that a steady stream of equally shaped calls (one frame or one small batch per call) pays ~nothing on the host.
 struct PipePlan {
     // key
-    YuvSource y; int w_out, h_out, out_dtype; Canvas cv; bool pairs_ok; int device;
+    YuvSource y; int w_out, h_out, out_dtype; Canvas cv; bool pairs_ok; int device, knob_gen;
     // plan
     bool eligible; PipeGeom g; const void* kern; int threads, per_sm, sms; size_t smem;
 };
@@ -416,7 +417,7 @@ static int build_pipe_plan(PipePlan& plan) {
     }
     int ncol = (w_out + kPipeThreads - 1) / kPipeThreads;
     if (any_right && w_out <= 4 * 192) ncol = 4;
-    if (const char* e = getenv("VACV_PIPE_NCOL")) { const int v = atoi(e); if (v >= 1 && v <= kPipeMaxCols && (w_out + v - 1) / v <= (v == 1 ? 640 : kPipeThreads)) ncol = v; }   // tuning knob
+    if (const int v = knob(kKnobPipeNcol)) { if (v >= 1 && v <= kPipeMaxCols && (w_out + v - 1) / v <= (v == 1 ? 640 : kPipeThreads)) ncol = v; }   // tuning knob
     const bool pairs = half_out && (w_out % 2) == 0 && (cv.w % 2) == 0 && (cv.x0 % 2) == 0 && plan.pairs_ok;   // 16-bit outputs: 32-bit stores of column pairs
     if (pairs) ncol = ncol <= 2 ? 2 : 4;
     const int threads = std::min(ncol == 1 ? 640 : kPipeThreads, ((w_out + ncol - 1) / ncol + 31) & ~31);
@@ -436,8 +437,7 @@ static int build_pipe_plan(PipePlan& plan) {
     int per_sm = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, best_smem);
     if (e != cudaSuccess || per_sm < 1) return 0;
-    int sms = kNumSMs;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, plan.device);
+    const int sms = sm_count(plan.device);
     plan.kern = kern; plan.threads = threads; plan.per_sm = per_sm; plan.sms = sms; plan.smem = best_smem;
     plan.eligible = true;
     return 0;
@@ -448,18 +448,19 @@ static int build_pipe_plan(PipePlan& plan) {
 static int try_launch_pipe(const uint8_t* src, void* dst, int out_dtype, int batch, const YuvSource& y, int w_out, int h_out,
                            const Canvas& cv, const float* mean, const float* stddev, cudaStream_t s) {
     if ((((uintptr_t)src) & 15) != 0) return 0;   // bulk copies need 16-byte aligned band starts
-    static thread_local PipePlan plan = {};
-    static thread_local bool have_plan = false;
-    int dev = 0;
-    cudaGetDevice(&dev);
+    static thread_local PlanCache<PipePlan, 8> cache;   // keyed by device + shape: alternating shapes / GPUs on one thread do not rebuild
+    const int dev = current_device(), gen = knob_generation();
     const bool pairs_ok = (((uintptr_t)dst) & 3) == 0;
-    if (!have_plan || !same_key(plan, y, w_out, h_out, out_dtype, cv, pairs_ok, dev) || getenv("VACV_PIPE_NCOL")) {
-        have_plan = false;
-        plan.y = y; plan.w_out = w_out; plan.h_out = h_out; plan.out_dtype = out_dtype; plan.cv = cv; plan.pairs_ok = pairs_ok; plan.device = dev;
-        const int rc = build_pipe_plan(plan);
+    PipePlan* pp = cache.find([&](const PipePlan& p) { return p.knob_gen == gen && same_key(p, y, w_out, h_out, out_dtype, cv, pairs_ok, dev); });
+    if (!pp) {
+        pp = cache.claim();
+        pp->y = y; pp->w_out = w_out; pp->h_out = h_out; pp->out_dtype = out_dtype; pp->cv = cv; pp->pairs_ok = pairs_ok; pp->device = dev; pp->knob_gen = gen;
+        const int rc = build_pipe_plan(*pp);
         if (rc < 0) return rc;
-        have_plan = true;
+        cache.commit();
+        ++cache.builds;
     }
+    const PipePlan& plan = *pp;
     if (!plan.eligible) return 0;
     PipeGeom g = plan.g;
     const long long total = (long long)g.tiles_per_frame * batch;
@@ -555,7 +556,7 @@ extern "C" int vacv_cuda_resize_normalize(const uint8_t* src, float* dst, int ba
     const int rows_per_cta = max(1, min(h_out, (8192 + w_out - 1) / w_out));
     dim3 grid(ceil_div(h_out, rows_per_cta), batch);
     cudaStream_t s = as_stream(stream);
-    if (c == 3 && !getenv("VACV_RESIZE_NORMALIZE_GATHER")) {   // persistent TMA pipeline where the shape qualifies (small or integer ratios, 16-byte rows)
+    if (c == 3 && !knob(kKnobRnGather)) {   // persistent TMA pipeline where the shape qualifies (small or integer ratios, 16-byte rows)
         const int rc = try_launch_resize_pipe_u8c3(src, dst, batch, w, h, w_out, h_out, false, out_layout == VACV_NCHW ? 1 : 2, mean, stddev, s);
         if (rc < 0) return rc;
         if (rc > 0) return check_launch("resize_normalize (persistent)");

@@ -6,6 +6,8 @@
 // same bookkeeping, then  host tensor -> device scratch -> vacv_cuda_* -> host tensor, synchronously.
 #include "cv/cv.h"
 
+#include <algorithm>
+#include <cstdint>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -151,10 +153,22 @@ void warp_affine(const Tensor& src, Tensor& dst, float scale, float rot, VSize d
 }
 
 // ---------------------------------------------------------------------------------------------------- fused ops
-void resize_normalize(const Tensor& src, Tensor& dst, VSize dsize, double /*fx*/, double /*fy*/, int interpolation,
+// Semantics (the reference's only implemented body, resize_normalize.cpp:39-103): resize -> fp32 -> per-channel
+// (x - m) / (s + 1e-6), with m / s taken from the RESIZED image when `mean` or `stddev` is empty (:58) -- the defaults of
+// cv.h:154-159.  u8 HWC + INTER_LINEAR + explicit statistics is one fused kernel; everything else the composition supports
+// (fp32 input, CHW, INTER_CUBIC, automatic statistics) runs as resize() + normalize(), which defines the fused result anyway.
+void resize_normalize(const Tensor& src, Tensor& dst, VSize dsize, double fx, double fy, int interpolation,
                       const Tensor& mean, const Tensor& stddev) {
-    if (src.empty() || src.dtype != vision::INT8 || src.layout != vision::NHWC || interpolation != INTER_LINEAR)
-        unsupported("resize_normalize other than INTER_LINEAR on a u8 HWC tensor");
+    if (src.empty()) throw std::runtime_error("vacv: resize_normalize of an empty tensor");
+    const bool auto_stats = mean.empty() || stddev.empty();
+    const bool fused = !auto_stats && src.dtype == vision::INT8 && src.layout == vision::NHWC && interpolation == INTER_LINEAR;
+    if (!fused) {
+        Tensor resized;
+        resize(src, resized, dsize, fx, fy, interpolation);
+        if (auto_stats) normalize(resized, dst, Tensor(), Tensor());
+        else normalize(resized, dst, mean, stddev);
+        return;
+    }
     require_stats(mean, stddev, src.c);
     const Tensor in = src;
     dst.create(dsize.w, dsize.h, in.c, vision::FP32, vision::NHWC);
@@ -171,12 +185,21 @@ void resize_normalize(const Tensor& src, Tensor& dst, VSize dsize, double /*fx*/
     ctx.download(dst.data, d_out, dst.len());
 }
 
+// Same contract for the warp (warp_affine_normalize.cpp:47-120): statistics of the WARPED image when mean / stddev are empty;
+// fp32 input or CHW layout run as warp_affine() + normalize().
 void warp_affine_normalize(const Tensor& src, Tensor& dst, const Tensor& M, VSize dsize, int flags, int borderMode,
-                           const VScalar& /*borderValue*/, const Tensor& mean, const Tensor& stddev) {
+                           const VScalar& borderValue, const Tensor& mean, const Tensor& stddev) {
     if (src.empty() || M.empty() || M.size() < 6 || M.dtype != vision::FP32)
         throw std::runtime_error("vacv: warp_affine_normalize needs a source and a 2x3 FP32 matrix");
-    if (src.dtype != vision::INT8 || src.layout != vision::NHWC || borderMode != BORDER_CONSTANT || flags != INTER_LINEAR)
-        unsupported("warp_affine_normalize other than INTER_LINEAR / BORDER_CONSTANT on a u8 HWC tensor");
+    check_warp_mode(src, flags, borderMode);
+    const bool auto_stats = mean.empty() || stddev.empty();
+    if (auto_stats || src.dtype != vision::INT8 || src.layout != vision::NHWC) {
+        Tensor warped;
+        warp_affine(src, warped, M, dsize, flags, borderMode, borderValue);   // inverts M in place, like the fused path below
+        if (auto_stats) normalize(warped, dst, Tensor(), Tensor());
+        else normalize(warped, dst, mean, stddev);
+        return;
+    }
     require_stats(mean, stddev, src.c);
     float* m = static_cast<float*>(M.data);
     vacv_invert_affine(m);
@@ -211,9 +234,21 @@ void crop(const Tensor& src, Tensor& dst, const vision::VRect& rect) {
         throw std::runtime_error("vacv: crop rectangle outside the source (the reference would read out of bounds)");
     dst.create(cw, ch, in.c, in.dtype, in.layout);
     DeviceContext& ctx = DeviceContext::current();
-    void* d_in = ctx.upload(0, in.data, in.len());
+    // Only the ROI crosses PCIe: the rows top .. top+ch, and of each row the columns around the rectangle (widened to whole
+    // 16-pixel groups so the DMA engine moves aligned runs); the kernel then crops the few residual columns on the device.
+    const size_t es = in.dtype == vision::INT8 ? 1 : 4;
+    const int x0 = left & ~15, x1 = std::min(in.w, (left + cw + 15) & ~15), sub_w = x1 - x0;
+    const bool hwc = in.layout == vision::NHWC;
+    const size_t px = hwc ? es * in.c : es;                   // bytes per pixel step along a row
+    const size_t row_bytes = (size_t)sub_w * px, src_pitch = (size_t)in.w * px;
+    const int planes = hwc ? 1 : in.c;
+    uint8_t* d_in = static_cast<uint8_t*>(ctx.scratch(0, row_bytes * ch * planes));
+    for (int k = 0; k < planes; ++k) {
+        const uint8_t* h0 = static_cast<const uint8_t*>(in.data) + (size_t)k * in.w * in.h * es + (size_t)top * src_pitch + (size_t)x0 * px;
+        ctx.check(vacv_cuda_memcpy2d_h2d(d_in + (size_t)k * row_bytes * ch, row_bytes, h0, src_pitch, row_bytes, ch, ctx.stream()));
+    }
     void* d_out = ctx.scratch(1, dst.len());
-    ctx.check(vacv_cuda_crop(d_in, d_out, 1, in.w, in.h, in.c, in.dtype, in.layout, left, top, cw, ch, ctx.stream()));
+    ctx.check(vacv_cuda_crop(d_in, d_out, 1, sub_w, ch, in.c, in.dtype, in.layout, left - x0, 0, cw, ch, ctx.stream()));
     ctx.download(dst.data, d_out, dst.len());
 }
 

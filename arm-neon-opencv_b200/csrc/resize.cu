@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <algorithm>
+#include "host_util.cuh"
 #include "vacv_common.cuh"
 #include "resize_coeffs.cuh"
 #include "gather_u8c3.cuh"
@@ -456,7 +457,7 @@ static const void* resize_pipe_c1_kernel_for(int ncol) {
 // 1 = launched, 0 = shape not eligible, < 0 = error.
 // Shape-dependent part of a launch, cached per host thread (a stream of equally shaped calls pays it once).
 struct ResizePipePlan {
-    int w, h, wo, ho, device, out_mode, c; bool signed_char;      // key (out_mode: kRpOut*, c: 3 = BGR, 1 = planes)
+    int w, h, wo, ho, device, out_mode, c, knob_gen; bool signed_char;      // key (out_mode: kRpOut*, c: 3 = BGR, 1 = planes)
     bool eligible; ResizePipeGeom g; const void* kern; int threads, per_sm, sms; size_t smem;
 };
 
@@ -492,7 +493,7 @@ static int build_resize_pipe_plan(ResizePipePlan& plan) {
     g.src_image = row_bytes * h; g.dst_image = (size_t)wo * ho * c;
     int ncol = (wo + kRpThreads - 1) / kRpThreads;
     if (ncol < 2) ncol = 2;
-    if (const char* e = getenv("VACV_RPIPE_NCOL")) { const int v = atoi(e); if (v >= 1 && v <= kRpMaxCols && (wo + v - 1) / v <= kRpThreads) ncol = v; }   // tuning knob
+    if (const int v = knob(kKnobRpipeNcol)) { if (v >= 1 && v <= kRpMaxCols && (wo + v - 1) / v <= kRpThreads) ncol = v; }   // tuning knob
     const int threads = std::min(kRpThreads, ((wo + ncol - 1) / ncol + 31) & ~31);
     const size_t lines = (size_t)(threads / 32) * ncol * (c == 1 ? 32 : plan.out_mode == kRpOutF32HWC ? 384 : 96);
     int best_TH = 0; size_t best_smem = 0;
@@ -530,9 +531,9 @@ static int build_resize_pipe_plan(ResizePipePlan& plan) {
                      : !any_right && ncol == 2 ? (const void*)resize_linear_u8c3_pipe_kernel<false, 2, false, true>   // pure byte moves: signedness irrelevant
                             : (signed_char ? resize_pipe_kernel_for<true, false>(ncol) : resize_pipe_kernel_for<false, false>(ncol));
     const int dev = plan.device;
-    int optin = 0, sms = kNumSMs, per_sm = 0;
+    int optin = 0, per_sm = 0;
+    const int sms = sm_count(dev);
     cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaFuncAttributes fa;
     cudaError_t e = cudaFuncGetAttributes(&fa, kern);
     if (e != cudaSuccess) return set_error(VACV_ERR_CUDA, "resize: %s", cudaGetErrorString(e));
@@ -551,18 +552,21 @@ static int build_resize_pipe_plan(ResizePipePlan& plan) {
 int vacv::try_launch_resize_pipe_u8c3(const uint8_t* src, void* dst, int images, int w, int h, int wo, int ho, bool signed_char, int out_mode,
                                       const float* mean, const float* stddev, cudaStream_t s, int c) {
     if (((uintptr_t)src & 15) != 0) return 0;
-    static thread_local ResizePipePlan plan = {};
-    static thread_local bool have_plan = false;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!have_plan || plan.w != w || plan.h != h || plan.wo != wo || plan.ho != ho || plan.signed_char != signed_char || plan.device != dev ||
-        plan.out_mode != out_mode || plan.c != c || getenv("VACV_RPIPE_NCOL")) {
-        have_plan = false;
-        plan.w = w; plan.h = h; plan.wo = wo; plan.ho = ho; plan.signed_char = signed_char; plan.device = dev; plan.out_mode = out_mode; plan.c = c;
-        const int rc = build_resize_pipe_plan(plan);
+    static thread_local PlanCache<ResizePipePlan, 8> cache;
+    const int dev = current_device(), gen = knob_generation();
+    ResizePipePlan* pp = cache.find([&](const ResizePipePlan& p) {
+        return p.w == w && p.h == h && p.wo == wo && p.ho == ho && p.signed_char == signed_char && p.device == dev && p.out_mode == out_mode &&
+               p.c == c && p.knob_gen == gen;
+    });
+    if (!pp) {
+        pp = cache.claim();
+        pp->w = w; pp->h = h; pp->wo = wo; pp->ho = ho; pp->signed_char = signed_char; pp->device = dev; pp->out_mode = out_mode; pp->c = c; pp->knob_gen = gen;
+        const int rc = build_resize_pipe_plan(*pp);
         if (rc < 0) return rc;
-        have_plan = true;
+        cache.commit();
+        ++cache.builds;
     }
+    const ResizePipePlan& plan = *pp;
     if (!plan.eligible) return 0;
     ResizePipeGeom g = plan.g;
     const long long total = (long long)g.tiles_per_frame * images;
@@ -620,7 +624,7 @@ extern "C" int vacv_cuda_resize(const void* src, void* dst, int batch, int w, in
         const uint8_t* sp = (const uint8_t*)src + (size_t)i0 * g.src_image * es;
         uint8_t* dp = (uint8_t*)dst + (size_t)i0 * g.dst_image * es;
         const bool c3_words = g.c == 3 && (((size_t)w * h * 3) % 4) == 0 && ((uintptr_t)src % 4) == 0 && (size_t)w * h * 3 < 0xfffffff0ull;
-        if (!cubic && dtype == VACV_INT8 && c3_words && !(flags & (VACV_FLAG_NEON_RULE | VACV_FLAG_DIRECT_GATHER)) && !getenv("VACV_NO_RPIPE")) {
+        if (!cubic && dtype == VACV_INT8 && c3_words && !(flags & (VACV_FLAG_NEON_RULE | VACV_FLAG_DIRECT_GATHER)) && !knob(kKnobNoRpipe)) {
             const int rc = try_launch_resize_pipe_u8c3(sp, dp, ni, w, h, w_out, h_out, (flags & VACV_FLAG_SIGNED_CHAR) != 0, kRpOutU8, nullptr, nullptr, s);
             if (rc < 0) return rc;
             if (rc > 0) continue;
@@ -632,7 +636,7 @@ extern "C" int vacv_cuda_resize(const void* src, void* dst, int batch, int w, in
             else if (sc) resize_linear_u8c3_kernel<true, false><<<grid, block, 0, s>>>(sp, dp, g);
             else resize_linear_u8c3_kernel<false, false><<<grid, block, 0, s>>>(sp, dp, g);
         } else if (!cubic && dtype == VACV_INT8 && g.c == 1 && (((size_t)w * h) % 4) == 0 && ((uintptr_t)src % 4) == 0 && (size_t)w * h < 0xfffffff0ull) {
-            if (!(flags & (VACV_FLAG_NEON_RULE | VACV_FLAG_DIRECT_GATHER)) && !getenv("VACV_NO_RPIPE")) {   // persistent TMA pipeline for planes
+            if (!(flags & (VACV_FLAG_NEON_RULE | VACV_FLAG_DIRECT_GATHER)) && !knob(kKnobNoRpipe)) {   // persistent TMA pipeline for planes
                 const int rc = try_launch_resize_pipe_u8c3(sp, dp, ni, w, h, w_out, h_out, (flags & VACV_FLAG_SIGNED_CHAR) != 0, kRpOutU8, nullptr, nullptr, s, 1);
                 if (rc < 0) return rc;
                 if (rc > 0) continue;

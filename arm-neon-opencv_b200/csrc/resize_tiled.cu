@@ -21,6 +21,7 @@
 #include "resize_coeffs.cuh"
 #include "resize_cubic3.cuh"
 #include "resize_cubic3_walk.cuh"
+#include "host_util.cuh"
 #include "vacv_common.cuh"
 
 namespace vacv {
@@ -524,7 +525,7 @@ static int launch_cubic3(const void* src, void* dst, int images, int w, int h, i
         g.TH = TH; g.max_slots = slots;
         g.tiles_x = (wo + kC3Px - 1) / kC3Px; g.tiles_y = (ho + TH - 1) / TH;
         const long long ctas1 = (long long)g.tiles_x * g.tiles_y * images;
-        g.tiles_per_cta = (int)std::max<long long>(1, std::min<long long>(8, ctas1 / (kNumSMs * 16LL)));
+        g.tiles_per_cta = (int)std::max<long long>(1, std::min<long long>(8, ctas1 / (current_sm_count() * 16LL)));
         const int ychunks = (g.tiles_y + g.tiles_per_cta - 1) / g.tiles_per_cta;
         auto kern = resize_cubic3_kernel<KIND>;
         if (smem > 48 * 1024) {
@@ -558,7 +559,7 @@ static int launch_cubic3_rolling(const void* src, void* dst, int images, int w, 
     g.strips = (wo + kRollPx - 1) / kRollPx;
     g.opitch = (kRollPx * PX + 16 + 15) & ~15;
     // vertical segments: enough CTAs for >= ~6 waves of 5 CTAs/SM, each segment a multiple of G rows
-    const long long want = 6LL * 5 * kNumSMs;
+    const long long want = 6LL * 5 * current_sm_count();
     long long segs = std::max<long long>(1, std::min<long long>((want + (long long)g.strips * images - 1) / ((long long)g.strips * images), (ho + G - 1) / G));
     int rps = (int)((ho + segs - 1) / segs);
     rps = std::min(kRollMaxRows / G * G, (rps + G - 1) / G * G);
@@ -590,10 +591,10 @@ static int launch_cubic_walk_f32(const float* src, float* dst, int images, int w
     g.scale_x = (double)w / (double)wo; g.scale_y = (double)h / (double)ho;      // resize_naive.cpp:144
     g.strips = (wo + kWalkThreads - 1) / kWalkThreads;
     g.store16 = (((size_t)wo * PX) % 16 == 0 && ((uintptr_t)dst % 16) == 0) ? 1 : 0;
-    const long long want = 8LL * 8 * kNumSMs;
+    const long long want = 8LL * 8 * current_sm_count();
     const long long per_seg = (long long)g.strips * images;
     long long segs = std::max<long long>(1, std::min<long long>((want + per_seg - 1) / per_seg, (ho + 63) / 64));
-    if (const char* e = getenv("VACV_WALK_SEGS")) segs = std::max(1, atoi(e));   // tuning knob
+    if (const int v = knob(kKnobWalkSegs)) segs = std::max(1, v);   // tuning knob
     int rps = (int)((ho + segs - 1) / segs);
     rps = std::min(kWalkMaxRows, std::max(rps, 1));
     g.rows_per_seg = rps;
@@ -602,7 +603,7 @@ static int launch_cubic_walk_f32(const float* src, float* dst, int images, int w
     // pixels, + 15 (alignment of the span start), rounded up
     const int span_px = (int)std::ceil(31.0 * g.scale_x) + 2 + 4;
     g.ring_pitch = (span_px * PX + 15 + 15) & ~15;
-    static const char* sync_only = getenv("VACV_WALK_SYNC");   // tuning knob: register prefetch instead of the cp.async ring
+    const bool sync_only = knob(kKnobWalkSync) != 0;   // tuning knob: register prefetch instead of the cp.async ring
     const bool async = !sync_only && ((size_t)w * PX) % 16 == 0 && ((size_t)w * h * PX) % 16 == 0 && ((uintptr_t)src % 16) == 0 && g.ring_pitch <= 1024;
     const size_t smem = (size_t)(rps + 1) * sizeof(WalkRow) + (size_t)(kWalkThreads / 32) * kWalkStageRows * 32 * PX +
                         (async ? (size_t)(kWalkThreads / 32) * kWalkRing * g.ring_pitch : 0);
@@ -630,10 +631,10 @@ static int launch_cubic3_walk2(const uint8_t* src, uint8_t* dst, int images, int
     g.strips = (wo + kWalk2Cols - 1) / kWalk2Cols;
     g.store16 = (((size_t)wo * 3) % 16 == 0 && ((uintptr_t)dst % 16) == 0) ? 1 : 0;
     g.one2 = 0x3F8000003F800000ull; g.negzero2 = 0x8000000080000000ull; g.magic2 = 0x4B4000004B400000ull; g.negmagic2 = 0xCB400000CB400000ull;
-    const long long want = 8LL * 6 * kNumSMs;
+    const long long want = 8LL * 6 * current_sm_count();
     const long long per_seg = (long long)g.strips * images;
     long long segs = std::max<long long>(1, std::min<long long>((want + per_seg - 1) / per_seg, (ho + 63) / 64));
-    if (const char* e = getenv("VACV_WALK_SEGS")) segs = std::max(1, atoi(e));   // tuning knob
+    if (const int v = knob(kKnobWalkSegs)) segs = std::max(1, v);   // tuning knob
     int rps = (int)((ho + segs - 1) / segs);
     rps = std::min(kWalkMaxRows, std::max(rps, 1));
     g.rows_per_seg = rps;
@@ -642,7 +643,7 @@ static int launch_cubic3_walk2(const uint8_t* src, uint8_t* dst, int images, int
     // bytes + 4 (word 3) + 15 (alignment of the span start), rounded up, + 16 slack
     const int span_px = (int)std::ceil(63.0 * g.scale_x) + 2;
     g.ring_pitch = ((span_px * 3 + 12 + 4 + 15 + 15) & ~15) + 16;
-    static const char* sync_only = getenv("VACV_WALK2_SYNC");   // tuning knob: register prefetch instead of the cp.async ring
+    const bool sync_only = knob(kKnobWalk2Sync) != 0;   // tuning knob: register prefetch instead of the cp.async ring
     const bool async = !sync_only && ((size_t)w * 3) % 16 == 0 && ((uintptr_t)src % 16) == 0 && g.ring_pitch <= 1024;
     const size_t smem = (size_t)(rps + 1) * sizeof(Walk2Row) + (size_t)(kWalkThreads / 32) * kWalkStageRows * 64 * 3 +
                         (async ? (size_t)(kWalkThreads / 32) * kWalk2Ring * g.ring_pitch : 0);
@@ -685,11 +686,11 @@ static int launch_tiled_kind(const void* src, void* dst, int images, TiledGeom g
 // Returns 1 if launched, 0 if the shape does not fit the tiled kernel (caller uses the direct kernels), < 0 on error.
 int try_launch_resize_tiled(int kind, const void* src, void* dst, int images, int w, int h, int c, int wo, int ho, cudaStream_t s) {
     if (c == 3 && (kind == kCubU8 || kind == kCubF32)) {   // interleaved BGR: rolling separable kernel, else the tiled pixel-per-thread one
-        static const char* pick = getenv("VACV_CUBIC3");   // tuning knob: "roll" = shared-memory ring kernel, default = column walker
+        const bool roll = knob(kKnobCubic3Roll) != 0;   // tuning knob: shared-memory ring kernel instead of the column walker
         int rc = 0;
-        if (kind == kCubU8 && (!pick || pick[0] != 'r')) rc = launch_cubic3_walk2((const uint8_t*)src, (uint8_t*)dst, images, w, h, wo, ho, s);
+        if (kind == kCubU8 && !roll) rc = launch_cubic3_walk2((const uint8_t*)src, (uint8_t*)dst, images, w, h, wo, ho, s);
         if (rc != 0) return rc;
-        if (kind == kCubF32 && (!pick || pick[0] != 'r')) rc = launch_cubic_walk_f32<3>((const float*)src, (float*)dst, images, w, h, wo, ho, s);
+        if (kind == kCubF32 && !roll) rc = launch_cubic_walk_f32<3>((const float*)src, (float*)dst, images, w, h, wo, ho, s);
         if (rc != 0) return rc;
         rc = kind == kCubU8 ? launch_cubic3_rolling<true>(src, dst, images, w, h, wo, ho, s) : launch_cubic3_rolling<false>(src, dst, images, w, h, wo, ho, s);
         if (rc != 0) return rc;
@@ -733,7 +734,7 @@ int try_launch_resize_tiled(int kind, const void* src, void* dst, int images, in
             if ((long long)g.tiles_x * g.tiles_y > 0x7fffffffLL) return 0;
             // several y tiles per CTA amortise the per-CTA column set-up, but keep >= ~8 CTAs per SM in flight
             const long long ctas1 = (long long)g.tiles_x * g.tiles_y * images;
-            g.tiles_per_cta = (int)std::max<long long>(1, std::min<long long>(8, ctas1 / (kNumSMs * 8LL)));
+            g.tiles_per_cta = (int)std::max<long long>(1, std::min<long long>(8, ctas1 / (current_sm_count() * 8LL)));
             switch (kind) {
                 case kLinU8: return launch_tiled_kind<kLinU8>(src, dst, images, g, smem, s);
                 case kLinU8Signed: return launch_tiled_kind<kLinU8Signed>(src, dst, images, g, smem, s);

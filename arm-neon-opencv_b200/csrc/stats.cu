@@ -8,6 +8,7 @@
 // HBM-bound: one read of the frame, 16-byte loads.  Bytes are regrouped per channel with PRMT and summed with
 // dp4a (sum x: dot with 0x01010101; sum x^2: dot with itself), u32 partials per thread, warp-shuffle tree,
 // one u64 atomicAdd per counter per CTA.
+#include "host_util.cuh"
 #include "vacv_common.cuh"
 
 namespace vacv {
@@ -191,8 +192,9 @@ extern "C" int vacv_cuda_sums_u8(const uint8_t* src, int batch, int w, int h, in
     cudaStream_t s = as_stream(stream);
     const size_t wh = (size_t)w * h;
     // enough CTAs to fill the machine several times over, few enough that atomics stay negligible
-    auto ctas_for = [](size_t bytes, int images) {
-        size_t want = (size_t)kNumSMs * 16 / (size_t)max(1, images) + 1;
+    const int sms = current_sm_count();
+    auto ctas_for = [sms](size_t bytes, int images) {
+        size_t want = (size_t)sms * 16 / (size_t)max(1, images) + 1;
         return (unsigned)max((size_t)1, min(want, (bytes + 256 * 48 - 1) / (256 * 48)));
     };
     if (layout == VACV_NHWC && c == 3 && (((uintptr_t)src & 15) == 0) && ((wh * 3) % 16 == 0 || batch == 1)) {
@@ -236,7 +238,8 @@ extern "C" int vacv_cuda_sums_f32(const float* src, int batch, int w, int h, int
     const long long images = planes ? (long long)batch * c : batch;
     VACV_REQUIRE(images <= 65535, "sums_f32: at most 65535 frames (planes) per call");
     const size_t elems = planes ? wh : wh * c;
-    const unsigned ctas = (unsigned)max((size_t)1, min((elems + 256 * 16 - 1) / (256 * 16), (size_t)(kNumSMs * 16 / (size_t)images + 1)));
+    const int sms = current_sm_count();
+    const unsigned ctas = (unsigned)max((size_t)1, min((elems + 256 * 16 - 1) / (256 * 16), (size_t)(sms * 16 / (size_t)images + 1)));
     dim3 grid(ctas, (unsigned)images);
     if (planes) sums_f32_kernel<1><<<grid, 256, 0, s>>>(src, elems, c, sums, per_frame);
     else if (c == 2) sums_f32_kernel<2><<<grid, 256, 0, s>>>(src, elems, c, sums, per_frame);

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cstdlib>
 
+#include "host_util.cuh"
 #include "vacv_common.cuh"
 
 namespace vacv {
@@ -419,7 +420,8 @@ extern "C" int vacv_cuda_dtype_change(const void* src, void* dst, size_t n, int 
     const bool aligned = (((uintptr_t)src | (uintptr_t)dst) & 15) == 0;
     const size_t n4 = aligned ? n / 4 : 0;
     if (n4) {
-        const unsigned blocks = (unsigned)min((size_t)kNumSMs * 16, (size_t)ceil_div(n4, 256));
+        const int sms = current_sm_count();
+        const unsigned blocks = (unsigned)min((size_t)sms * 16, (size_t)ceil_div(n4, 256));
         if (to_f32) u8_to_f32_kernel<<<blocks, 256, 0, s>>>((const uint8_t*)src, (float*)dst, n4);
         else f32_to_u8_kernel<<<blocks, 256, 0, s>>>((const float*)src, (uint8_t*)dst, n4);
     }
@@ -442,13 +444,14 @@ extern "C" int vacv_cuda_normalize(const void* src, float* dst, int batch, int w
     VACV_REQUIRE((((uintptr_t)src | (uintptr_t)dst) & 15) == 0, "normalize: buffers must be 16-byte aligned");
     VACV_REQUIRE((size_t)w * h * c < 0xffffffffull, "normalize: frame too large");
     cudaStream_t s = as_stream(stream);
+    const int sms = current_sm_count();
     NormGeom g;
     g.c = c; g.wh = (unsigned)w * h; g.per_frame = g.wh * c; g.stats_per_frame = stats_per_frame;
     const size_t es = src_dtype == VACV_INT8 ? 1 : 4;
     if (layout == VACV_NHWC && c > 1) {
         if (c > kNormMaxC) return set_error(VACV_ERR_UNSUPPORTED, "normalize: HWC supports c <= %d", kNormMaxC);
         VACV_REQUIRE((g.per_frame % 4) == 0 || batch == 1, "normalize: HWC batch needs w*h*c %% 4 == 0");
-        const unsigned ctas = (unsigned)max(1u, min(ceil_div(g.per_frame / 4, 256 * 8), (unsigned)(kNumSMs * 16 / min(batch, kNumSMs * 16) + 1)));
+        const unsigned ctas = (unsigned)max(1u, min(ceil_div(g.per_frame / 4, 256 * 8), (unsigned)(sms * 16 / min(batch, sms * 16) + 1)));
         for (int f0 = 0; f0 < batch; f0 += 65535) {
             dim3 grid(ctas, min(batch - f0, 65535));
             const void* sp = (const uint8_t*)src + (size_t)f0 * g.per_frame * es;
@@ -462,7 +465,7 @@ extern "C" int vacv_cuda_normalize(const void* src, float* dst, int batch, int w
     } else {
         const long long planes = (long long)batch * c;
         const int chunk = 65535 / c * c;
-        const unsigned ctas = (unsigned)max(1u, min(ceil_div(g.wh / 4 + 1, 256 * 8), (unsigned)(kNumSMs * 16 / (unsigned)min(planes, (long long)kNumSMs * 16) + 1)));
+        const unsigned ctas = (unsigned)max(1u, min(ceil_div(g.wh / 4 + 1, 256 * 8), (unsigned)(sms * 16 / (unsigned)min(planes, (long long)sms * 16) + 1)));
         for (long long p0 = 0; p0 < planes; p0 += chunk) {
             dim3 grid(ctas, (unsigned)min((long long)chunk, planes - p0));
             const void* sp = (const uint8_t*)src + (size_t)p0 * g.wh * es;

@@ -5,11 +5,50 @@
 #include <cstdarg>
 #include <cstdio>
 
+#include <atomic>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include "host_util.cuh"
 #include "vacv_common.cuh"
 
 namespace vacv {
 
 static thread_local char g_err[512] = "";
+
+// ---- tuning knobs: environment read once, then plain atomics (host_util.cuh)
+static std::atomic<int> g_knobs[kKnobCount];
+static std::atomic<int> g_knob_gen{0};
+static std::once_flag g_knob_once;
+static const char* const kKnobNames[kKnobCount] = {"PIPE_NCOL", "RPIPE_NCOL", "WARP_GATHER", "NO_RPIPE", "RESIZE_NORMALIZE_GATHER",
+                                                    "WALK_SEGS", "WALK_SYNC", "WALK2_SYNC", "CUBIC3", "CUBIC_V"};
+static void init_knobs() {
+    for (int k = 0; k < kKnobCount; ++k) {
+        char name[64];
+        snprintf(name, sizeof(name), "VACV_%s", kKnobNames[k]);
+        const char* e = getenv(name);
+        int v = 0;
+        if (e) v = k == kKnobCubic3Roll ? (strcmp(e, "roll") == 0) : (*e >= '0' && *e <= '9') ? atoi(e) : 1;
+        g_knobs[k].store(v, std::memory_order_relaxed);
+    }
+}
+int knob(Knob k) {
+    std::call_once(g_knob_once, init_knobs);
+    return g_knobs[k].load(std::memory_order_relaxed);
+}
+int knob_generation() { return g_knob_gen.load(std::memory_order_relaxed); }
+
+int sm_count(int device) {
+    static std::atomic<int> cached[64];
+    if (device < 0 || device >= 64) device = 0;
+    int n = cached[device].load(std::memory_order_relaxed);
+    if (n == 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || n <= 0) { cudaGetLastError(); n = kNumSMs; }
+        cached[device].store(n, std::memory_order_relaxed);
+    }
+    return n;
+}
 
 int set_error(int code, const char* fmt, ...) {
     va_list ap;
@@ -29,6 +68,18 @@ int check_launch(const char* what) {
 }  // namespace vacv
 
 extern "C" int vacv_cuda_abi_version(void) { return 1; }
+
+extern "C" int vacv_cuda_set_tuning(const char* name, int value) {
+    VACV_REQUIRE(name, "set_tuning: null name");
+    for (int k = 0; k < vacv::kKnobCount; ++k)
+        if (strcmp(name, vacv::kKnobNames[k]) == 0) {
+            vacv::knob((vacv::Knob)k);   // make sure the environment defaults are in before overriding one
+            vacv::g_knobs[k].store(value, std::memory_order_relaxed);
+            vacv::g_knob_gen.fetch_add(1, std::memory_order_relaxed);
+            return VACV_OK;
+        }
+    return vacv::set_error(VACV_ERR_INVALID_ARG, "set_tuning: unknown knob '%s'", name);
+}
 extern "C" const char* vacv_cuda_last_error(void) { return vacv::g_err; }
 extern "C" int vacv_cuda_set_last_error(int code, const char* message) { return vacv::set_error(code, "%s", message ? message : ""); }
 
@@ -77,6 +128,10 @@ extern "C" int vacv_cuda_device_count(int* count) {
     VACV_RT(cudaGetDeviceCount(count), "device_count");
 }
 extern "C" int vacv_cuda_set_device(int device) { VACV_RT(cudaSetDevice(device), "set_device"); }
+extern "C" int vacv_cuda_get_device(int* device) {
+    VACV_REQUIRE(device, "get_device: null pointer");
+    VACV_RT(cudaGetDevice(device), "get_device");
+}
 extern "C" int vacv_cuda_malloc(void** dptr, size_t bytes) {
     VACV_REQUIRE(dptr, "malloc: null pointer");
     VACV_RT(cudaMalloc(dptr, bytes), "malloc");
@@ -93,6 +148,9 @@ extern "C" int vacv_cuda_memcpy_h2d(void* dptr, const void* h_ptr, size_t bytes,
 extern "C" int vacv_cuda_memcpy_d2h(void* h_ptr, const void* dptr, size_t bytes, void* stream) {
     VACV_RT(cudaMemcpyAsync(h_ptr, dptr, bytes, cudaMemcpyDeviceToHost, vacv::as_stream(stream)), "memcpy_d2h");
 }
+extern "C" int vacv_cuda_memcpy2d_h2d(void* dptr, size_t dst_pitch, const void* h_ptr, size_t src_pitch, size_t row_bytes, size_t rows, void* stream) {
+    VACV_RT(cudaMemcpy2DAsync(dptr, dst_pitch, h_ptr, src_pitch, row_bytes, rows, cudaMemcpyHostToDevice, vacv::as_stream(stream)), "memcpy2d_h2d");
+}
 extern "C" int vacv_cuda_memset(void* dptr, int value, size_t bytes, void* stream) {
     VACV_RT(cudaMemsetAsync(dptr, value, bytes, vacv::as_stream(stream)), "memset");
 }
@@ -105,7 +163,12 @@ extern "C" int vacv_cuda_stream_sync(void* stream) { VACV_RT(cudaStreamSynchroni
 
 // ---- end-to-end host-buffer pipeline ------------------------------------------------------------------------------
 namespace {
-struct HostPipe {   // per host thread: streams, events and double-buffered device staging, created on first use
+// Streams, events and double-buffered device staging of the host-buffer entry points.  One instance per (host thread,
+// device): everything in it belongs to the device that was current when it was created, so a thread that alternates
+// vacv_cuda_set_device() gets a separate pipeline per GPU (the reference's multi-device hook is
+// CudaDevice::set_device, src/cv/cuda_device.cu:10-18).
+struct HostPipe {
+    int device = -1;
     cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
     cudaEvent_t in_done[2] = {}, k_done[2] = {}, out_done[2] = {};
     uint8_t* d_in[2] = {};
@@ -116,53 +179,104 @@ struct HostPipe {   // per host thread: streams, events and double-buffered devi
     cudaError_t init() {
         if (ready) return cudaSuccess;
         cudaError_t e;
-        if ((e = cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking)) != cudaSuccess) return e;
-        if ((e = cudaStreamCreateWithFlags(&s_k, cudaStreamNonBlocking)) != cudaSuccess) return e;
-        if ((e = cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        if (!s_in && (e = cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        if (!s_k && (e = cudaStreamCreateWithFlags(&s_k, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        if (!s_out && (e = cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking)) != cudaSuccess) return e;
         for (int b = 0; b < 2; ++b) {
-            if ((e = cudaEventCreateWithFlags(&in_done[b], cudaEventDisableTiming)) != cudaSuccess) return e;
-            if ((e = cudaEventCreateWithFlags(&k_done[b], cudaEventDisableTiming)) != cudaSuccess) return e;
-            if ((e = cudaEventCreateWithFlags(&out_done[b], cudaEventDisableTiming)) != cudaSuccess) return e;
+            if (!in_done[b] && (e = cudaEventCreateWithFlags(&in_done[b], cudaEventDisableTiming)) != cudaSuccess) return e;
+            if (!k_done[b] && (e = cudaEventCreateWithFlags(&k_done[b], cudaEventDisableTiming)) != cudaSuccess) return e;
+            if (!out_done[b] && (e = cudaEventCreateWithFlags(&out_done[b], cudaEventDisableTiming)) != cudaSuccess) return e;
         }
-        if ((e = cudaMalloc(&d_stats, 6 * sizeof(float))) != cudaSuccess) return e;
+        if (!d_stats && (e = cudaMalloc(&d_stats, 6 * sizeof(float))) != cudaSuccess) return e;
         ready = true;
         return cudaSuccess;
     }
-    cudaError_t reserve(size_t in_bytes, size_t out_bytes) {
-        cudaError_t e;
-        if (in_bytes > in_cap) {
-            if ((e = cudaDeviceSynchronize()) != cudaSuccess) return e;
-            for (int b = 0; b < 2; ++b) { cudaFree(d_in[b]); d_in[b] = nullptr; if ((e = cudaMalloc(&d_in[b], in_bytes)) != cudaSuccess) return e; }
-            in_cap = in_bytes;
-        }
-        if (out_bytes > out_cap) {
-            if ((e = cudaDeviceSynchronize()) != cudaSuccess) return e;
-            for (int b = 0; b < 2; ++b) { cudaFree(d_out[b]); d_out[b] = nullptr; if ((e = cudaMalloc(&d_out[b], out_bytes)) != cudaSuccess) return e; }
-            out_cap = out_bytes;
-        }
+    // grow one pair of staging buffers; the capacity is only raised once BOTH allocations exist
+    template <typename T>
+    cudaError_t grow(T* (&buf)[2], size_t& cap, size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        cudaError_t e = drain();
+        if (e != cudaSuccess) return e;
+        cap = 0;
+        for (int b = 0; b < 2; ++b) { if (buf[b]) cudaFree(buf[b]); buf[b] = nullptr; }
+        for (int b = 0; b < 2; ++b)
+            if ((e = cudaMalloc(&buf[b], bytes)) != cudaSuccess) {
+                for (int q = 0; q < 2; ++q) { if (buf[q]) cudaFree(buf[q]); buf[q] = nullptr; }
+                return e;
+            }
+        cap = bytes;
         return cudaSuccess;
     }
+    cudaError_t reserve(size_t in_bytes, size_t out_bytes) {
+        cudaError_t e = grow(d_in, in_cap, in_bytes);
+        return e != cudaSuccess ? e : grow(d_out, out_cap, out_bytes);
+    }
+    // nothing of this pipeline may still be in flight on the caller's buffers when a "synchronous" call returns
+    cudaError_t drain() {
+        cudaError_t first = cudaSuccess;
+        for (cudaStream_t st : {s_in, s_k, s_out})
+            if (st) { const cudaError_t e = cudaStreamSynchronize(st); if (first == cudaSuccess) first = e; }
+        return first;
+    }
+    void destroy() {   // called with `device` current
+        drain();
+        for (int b = 0; b < 2; ++b) {
+            if (d_in[b]) cudaFree(d_in[b]);
+            if (d_out[b]) cudaFree(d_out[b]);
+            if (in_done[b]) cudaEventDestroy(in_done[b]);
+            if (k_done[b]) cudaEventDestroy(k_done[b]);
+            if (out_done[b]) cudaEventDestroy(out_done[b]);
+        }
+        if (d_stats) cudaFree(d_stats);
+        for (cudaStream_t st : {s_in, s_k, s_out}) if (st) cudaStreamDestroy(st);
+        *this = HostPipe();
+    }
 };
-thread_local HostPipe g_pipe;
-}  // namespace
 
-#define VACV_CU(call)                                                                                           \
-    do {                                                                                                        \
-        cudaError_t e_ = (call);                                                                                \
-        if (e_ != cudaSuccess) return vacv::set_error(VACV_ERR_CUDA, "nv_resize_normalize_chw_host: %s", cudaGetErrorString(e_)); \
-    } while (0)
+constexpr int kMaxPipeDevices = 16;
+struct HostPipes {
+    HostPipe pipe[kMaxPipeDevices];
+    ~HostPipes() {   // thread exit: release what this thread created (best effort: the context may already be gone at process exit)
+        int prev = -1;
+        if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); return; }
+        for (HostPipe& p : pipe)
+            if (p.device >= 0 && cudaSetDevice(p.device) == cudaSuccess) p.destroy();
+        cudaSetDevice(prev);
+        cudaGetLastError();
+    }
+};
+thread_local HostPipes g_pipes;
+
+// the pipeline of the CURRENT device (nullptr + error message if it cannot be determined)
+HostPipe* current_pipe(const char* who) {
+    int dev = -1;
+    const cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess || dev < 0 || dev >= kMaxPipeDevices) {
+        vacv::set_error(VACV_ERR_CUDA, "%s: %s", who, e != cudaSuccess ? cudaGetErrorString(e) : "device index beyond the per-thread pipeline table");
+        return nullptr;
+    }
+    HostPipe& p = g_pipes.pipe[dev];
+    p.device = dev;
+    return &p;
+}
+}  // namespace
 
 // Chunked, three-stream pipeline shared by the host-buffer entry points: chunk i's H2D copy, chunk i-1's kernel and chunk
 // i-2's D2H copy overlap.  `launch(d_in, d_out, frames, stream)` enqueues the kernel(s) of one chunk and returns a status.
+// in_frame = distance between frames in h_src; last_frame = bytes of a frame that are actually defined (a pitched decoder
+// pool may end right after the last surface: the tail of the final frame_stride is never read).
 template <typename Launch>
-static int run_host_pipeline(const char* who, const uint8_t* h_src, void* h_dst, int batch, size_t in_frame, size_t out_frame,
+static int run_host_pipeline(const char* who, const uint8_t* h_src, void* h_dst, int batch, size_t in_frame, size_t last_frame, size_t out_frame,
                              int chunk_frames, const float* h_mean, const float* h_stddev, float** d_stats_out, Launch launch) {
+    HostPipe* pp = current_pipe(who);
+    if (!pp) return VACV_ERR_CUDA;
+    HostPipe& p = *pp;
+    // on any failure: wait for whatever was already queued on the caller's buffers, then report
 #define VACV_CUP(call)                                                                                          \
     do {                                                                                                        \
         cudaError_t e_ = (call);                                                                                \
-        if (e_ != cudaSuccess) return vacv::set_error(VACV_ERR_CUDA, "%s: %s", who, cudaGetErrorString(e_));   \
+        if (e_ != cudaSuccess) { p.drain(); cudaGetLastError(); return vacv::set_error(VACV_ERR_CUDA, "%s: %s", who, cudaGetErrorString(e_)); } \
     } while (0)
-    HostPipe& p = g_pipe;
     VACV_CUP(p.init());
     const int chunk = chunk_frames < batch ? chunk_frames : batch;
     VACV_CUP(p.reserve(in_frame * chunk, out_frame * chunk));
@@ -173,15 +287,16 @@ static int run_host_pipeline(const char* who, const uint8_t* h_src, void* h_dst,
     int i = 0;
     for (int f0 = 0; f0 < batch; f0 += chunk, ++i) {
         const int b = i & 1, n = (batch - f0 < chunk) ? batch - f0 : chunk;
+        const size_t in_bytes = f0 + n == batch ? in_frame * (n - 1) + last_frame : in_frame * n;
         // H2D of chunk i may start once the kernel that last read d_in[b] (chunk i-2) is done
         if (i >= 2) VACV_CUP(cudaStreamWaitEvent(p.s_in, p.k_done[b], 0));
-        VACV_CUP(cudaMemcpyAsync(p.d_in[b], h_src + (size_t)f0 * in_frame, in_frame * n, cudaMemcpyHostToDevice, p.s_in));
+        VACV_CUP(cudaMemcpyAsync(p.d_in[b], h_src + (size_t)f0 * in_frame, in_bytes, cudaMemcpyHostToDevice, p.s_in));
         VACV_CUP(cudaEventRecord(p.in_done[b], p.s_in));
         // kernel of chunk i: needs its input, and d_out[b] drained by the D2H of chunk i-2
         VACV_CUP(cudaStreamWaitEvent(p.s_k, p.in_done[b], 0));
         if (i >= 2) VACV_CUP(cudaStreamWaitEvent(p.s_k, p.out_done[b], 0));
         const int rc = launch(p.d_in[b], (void*)p.d_out[b], n, (void*)p.s_k);
-        if (rc != VACV_OK) { cudaDeviceSynchronize(); return rc; }
+        if (rc != VACV_OK) { p.drain(); return rc; }
         VACV_CUP(cudaEventRecord(p.k_done[b], p.s_k));
         VACV_CUP(cudaStreamWaitEvent(p.s_out, p.k_done[b], 0));
         VACV_CUP(cudaMemcpyAsync((uint8_t*)h_dst + (size_t)f0 * out_frame, p.d_out[b], out_frame * n, cudaMemcpyDeviceToHost, p.s_out));
@@ -200,7 +315,7 @@ extern "C" int vacv_cuda_nv_resize_normalize_chw_host(const uint8_t* h_src, floa
     VACV_REQUIRE(batch > 0 && chunk_frames > 0, "nv_resize_normalize_chw_host: bad batch / chunk");
     float* d_stats = nullptr;
     float** ds = &d_stats;
-    return run_host_pipeline("nv_resize_normalize_chw_host", h_src, h_dst, batch, (size_t)w * h * 3 / 2, (size_t)w_out * h_out * 3 * sizeof(float),
+    return run_host_pipeline("nv_resize_normalize_chw_host", h_src, h_dst, batch, (size_t)w * h * 3 / 2, (size_t)w * h * 3 / 2, (size_t)w_out * h_out * 3 * sizeof(float),
                              chunk_frames, h_mean, h_stddev, ds, [=](const uint8_t* d_in, void* d_out, int n, void* stream) {
                                  return vacv_cuda_nv_resize_normalize_chw(d_in, (float*)d_out, n, w, h, v_first, w_out, h_out, *ds, *ds + 3, stream);
                              });
@@ -218,7 +333,8 @@ extern "C" int vacv_cuda_yuv_normalize_chw_host(const uint8_t* h_src, const vacv
         return vacv::set_error(VACV_ERR_UNSUPPORTED, "yuv_normalize_chw_host: out dtype %d (FP32, FP16 or BF16)", out_dtype);
     const bool planar = layout->format == VACV_YUV_I420 || layout->format == VACV_YUV_YV12;
     const size_t yp = layout->y_pitch ? layout->y_pitch : layout->w, cp = layout->c_pitch ? layout->c_pitch : (planar ? layout->w / 2 : layout->w);
-    const size_t in_frame = layout->frame_stride ? layout->frame_stride : yp * layout->h + cp * (layout->h / 2) * (planar ? 2 : 1);
+    const size_t surface = yp * layout->h + cp * (layout->h / 2) * (planar ? 2 : 1);   // bytes of one surface that are defined
+    const size_t in_frame = layout->frame_stride ? layout->frame_stride : surface;
     const size_t out_frame = (size_t)canvas_w * canvas_h * 3 * (out_dtype == VACV_FP32 ? 4 : 2);
     vacv_yuv_layout lay = *layout;
     lay.frame_stride = in_frame;
@@ -227,7 +343,7 @@ extern "C" int vacv_cuda_yuv_normalize_chw_host(const uint8_t* h_src, const vacv
     float* d_stats = nullptr;
     float** ds = &d_stats;
     const bool letterbox = content != nullptr;
-    return run_host_pipeline("yuv_normalize_chw_host", h_src, h_dst, batch, in_frame, out_frame, chunk_frames, h_mean, h_stddev, ds,
+    return run_host_pipeline("yuv_normalize_chw_host", h_src, h_dst, batch, in_frame, surface < in_frame ? surface : in_frame, out_frame, chunk_frames, h_mean, h_stddev, ds,
                              [=](const uint8_t* d_in, void* d_out, int n, void* stream) {
                                  if (letterbox)
                                      return vacv_cuda_yuv_letterbox_normalize_chw(d_in, &lay, d_out, out_dtype, n, canvas_w, canvas_h, &box, pad, *ds, *ds + 3,

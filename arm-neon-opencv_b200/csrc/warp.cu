@@ -8,6 +8,7 @@
 #include <cstdlib>
 
 #include "gather_u8c3.cuh"
+#include "host_util.cuh"
 #include "vacv_common.cuh"
 
 namespace vacv {
@@ -298,16 +299,20 @@ using namespace vacv;
 namespace {
 struct StagedPlan {
     const void* frames = nullptr;
-    int n_frames = 0, w = 0, h = 0;
+    int n_frames = 0, w = 0, h = 0, device = -1;
     bool ok = false;
     WarpStagedMaps maps;
 };
 
 // true when the frame pool can be described by the tensor maps (dense rows that are multiples of 16 bytes)
 bool staged_plan(const void* frames, int n_frames, int w, int h, const WarpStagedMaps** maps) {
-    static thread_local StagedPlan plan;
-    if (plan.frames != frames || plan.n_frames != n_frames || plan.w != w || plan.h != h) {
-        plan.frames = frames; plan.n_frames = n_frames; plan.w = w; plan.h = h; plan.ok = false;
+    static thread_local PlanCache<StagedPlan, 8> cache;   // a tensor map binds the pool's address: key = (device, pool, shape)
+    const int dev = current_device();
+    StagedPlan* pp = cache.find([&](const StagedPlan& p) { return p.device == dev && p.frames == frames && p.n_frames == n_frames && p.w == w && p.h == h; });
+    if (!pp) {
+        pp = cache.claim();
+        StagedPlan& plan = *pp;
+        plan.device = dev; plan.frames = frames; plan.n_frames = n_frames; plan.w = w; plan.h = h; plan.ok = false;
         const bool shape_ok = (w % 16) == 0 && w * 3 >= ws_box_bytes(kWsMaps - 1) && h >= kWsBoxRows &&
                               ((uintptr_t)frames % 16) == 0 && (size_t)w * h * 3 < 0xfffffff0ull;
         if (shape_ok) {
@@ -316,9 +321,10 @@ bool staged_plan(const void* frames, int n_frames, int w, int h, const WarpStage
                 plan.ok = encode_map_3d(&plan.maps.m[k], CU_TENSOR_MAP_DATA_TYPE_UINT32, frames, (cuuint64_t)w * 3 / 4, h, n_frames,
                                         (cuuint64_t)w * 3, (cuuint64_t)w * 3 * h, ws_box_bytes(k) / 4, kWsBoxRows, 1);
         }
+        cache.commit();
     }
-    *maps = &plan.maps;
-    return plan.ok;
+    *maps = &pp->maps;
+    return pp->ok;
 }
 
 // tile counters of the staged kernel are 32-bit
@@ -330,13 +336,12 @@ template <int OUT, bool kSigned, int NW>
 int launch_staged_nw(const WarpStagedMaps& maps, const uint8_t* frames, const int* frame_idx, const float* minv, void* dst, int w, int h,
                      int n_crops, int w_out, int h_out, const float* mean, const float* stddev, cudaStream_t s) {
     constexpr int kSmem = ws_smem_bytes<NW>();
-    static thread_local int attr_device = -1;   // the opt-in is per device
-    int device = 0;
-    cudaGetDevice(&device);
-    if (attr_device != device) {
+    static thread_local unsigned long long attr_devices = 0;   // the opt-in is per device: one bit per device already done
+    const int device = current_device();
+    if (device >= 64 || !((attr_devices >> device) & 1)) {
         if (cudaFuncSetAttribute(warp_affine_u8c3_staged_kernel<OUT, kSigned, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) != cudaSuccess)
             return check_launch("warp_affine (staged kernel attribute)");
-        attr_device = device;
+        if (device < 64) attr_devices |= 1ull << device;
     }
     WarpStagedGeom g;
     g.w = w; g.h = h; g.wo = w_out; g.ho = h_out;
@@ -348,7 +353,7 @@ int launch_staged_nw(const WarpStagedMaps& maps, const uint8_t* frames, const in
     g.total_tiles = g.tiles_per_crop * n_crops;           // < 2^31: checked by staged_fits()
     g.inv_tiles_x = 1.f / (float)g.tiles_x;
     g.frame_bytes = (size_t)w * h * 3;
-    const int grid = std::min(g.total_tiles, kWsCtasPerSm * kNumSMs);
+    const int grid = std::min(g.total_tiles, kWsCtasPerSm * sm_count(device));
     warp_affine_u8c3_staged_kernel<OUT, kSigned, NW><<<grid, 32 * NW + 32, kSmem, s>>>(maps, frames, frame_idx, minv, dst, g, mean, stddev);
     return check_launch("warp_affine (staged)");
 }
@@ -440,7 +445,7 @@ extern "C" int vacv_cuda_warp_affine_normalize(const uint8_t* frames, int n_fram
     cudaStream_t s = as_stream(stream);
     // fp32 output: the TMA-staged kernel is the default (config 3: 0.335 vs 0.373 ms); VACV_WARP_GATHER=1 forces the direct gather kernel
     const WarpStagedMaps* maps;
-    if (c == 3 && !getenv("VACV_WARP_GATHER") && staged_fits(n_crops, w_out, h_out) && staged_plan(frames, n_frames, w, h, &maps)) {
+    if (c == 3 && !knob(kKnobWarpGather) && staged_fits(n_crops, w_out, h_out) && staged_plan(frames, n_frames, w, h, &maps)) {
         if (out_layout == VACV_NHWC) return launch_staged<kWarpOutF32HWC, false>(*maps, frames, frame_idx, minv, dst, w, h, n_crops, w_out, h_out, mean, stddev, s);
         return launch_staged<kWarpOutF32CHW, false>(*maps, frames, frame_idx, minv, dst, w, h, n_crops, w_out, h_out, mean, stddev, s);
     }

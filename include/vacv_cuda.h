@@ -229,7 +229,9 @@ VACV_API int vacv_cuda_normalize_batch_global_p2p(void* xchg, const uint8_t* src
  * Same operation as vacv_cuda_nv_resize_normalize_chw, but `h_src` / `h_dst` / `h_mean` / `h_stddev` are HOST pointers
  * (pinned memory -- vacv_cuda_host_alloc -- for full PCIe speed; pageable works, slower).  The batch is cut into chunks of
  * `chunk_frames` frames that are pipelined over three internal streams (H2D copy | kernel | D2H copy, double-buffered
- * device staging, grown on demand and cached per host thread).  Synchronous: returns when h_dst is complete. */
+ * device staging, grown on demand and cached per host thread AND device: a thread that alternates vacv_cuda_set_device gets one
+ * pipeline per GPU).  h_src must span (batch-1) frames + the defined bytes of the last one.  Synchronous: returns when h_dst is
+ * complete; on an error nothing is left in flight on the caller's buffers. */
 VACV_API int vacv_cuda_nv_resize_normalize_chw_host(const uint8_t* h_src, float* h_dst, int batch, int w, int h, int v_first,
                                                     int w_out, int h_out, const float* h_mean, const float* h_stddev,
                                                     int chunk_frames);
@@ -238,14 +240,20 @@ VACV_API int vacv_cuda_nv_resize_normalize_chw_host(const uint8_t* h_src, float*
  * Thin wrappers over the CUDA runtime so that C/C++ host code needs no CUDA headers: device memory, pinned staging
  * memory (the reference's USE_CUDA allocator, src/common/va_cuda_allocator.cu:8-34, made checkable), copies,
  * streams.  Copies are asynchronous on `stream`; vacv_cuda_stream_sync waits. */
+/* Diagnostic switches ("WARP_GATHER", "NO_RPIPE", "PIPE_NCOL", ... -- DESIGN.md section 5): process-wide, initialised once from the
+ * environment (VACV_<NAME>), changeable here at run time; the operator entry points never call getenv. */
+VACV_API int vacv_cuda_set_tuning(const char* name, int value);
 VACV_API int vacv_cuda_device_count(int* count);
-VACV_API int vacv_cuda_set_device(int device);
+VACV_API int vacv_cuda_set_device(int device);      /* the reference's hook: CudaDevice::set_device (src/cv/cuda_device.cu:15-18) */
+VACV_API int vacv_cuda_get_device(int* device);
 VACV_API int vacv_cuda_malloc(void** dptr, size_t bytes);
 VACV_API int vacv_cuda_free(void* dptr);
 VACV_API int vacv_cuda_host_alloc(void** h_ptr, size_t bytes);      /* pinned */
 VACV_API int vacv_cuda_host_free(void* h_ptr);
 VACV_API int vacv_cuda_memcpy_h2d(void* dptr, const void* h_ptr, size_t bytes, void* stream);
 VACV_API int vacv_cuda_memcpy_d2h(void* h_ptr, const void* dptr, size_t bytes, void* stream);
+/* `rows` rows of `row_bytes`, src_pitch apart in host memory -> dst_pitch apart on the device (ROI uploads: va_cv::crop) */
+VACV_API int vacv_cuda_memcpy2d_h2d(void* dptr, size_t dst_pitch, const void* h_ptr, size_t src_pitch, size_t row_bytes, size_t rows, void* stream);
 VACV_API int vacv_cuda_memset(void* dptr, int value, size_t bytes, void* stream);
 VACV_API int vacv_cuda_stream_create(void** stream);
 VACV_API int vacv_cuda_stream_destroy(void* stream);

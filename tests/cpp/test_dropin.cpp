@@ -13,6 +13,7 @@
 
 #include "common/tensor.h"
 #include "cv/cv.h"
+#include "vacv_cuda.h"
 #include "vacv_oracle.h"
 
 using namespace vision;
@@ -185,6 +186,100 @@ int main() {
                 ok = ok && d8.w == cw && d8.h == ch && same(d8, w8) && same(df, wf);
             }
             report("crop hwc u8 / fp32", ok);
+        }
+        {   // the fused entry points with the header's DEFAULT arguments (cv.h:154-201: mean / stddev empty): statistics of the
+            // resized / warped image (resize_normalize.cpp:58), and the layouts / dtypes / modes the composition supports
+            Tensor dn;
+            va_cv::resize_normalize(src_u8, dn, va_cv::VSize(224, 200));
+            std::vector<uint8_t> sm(224 * 200 * 3);
+            std::vector<float> want(sm.size());
+            orc_resize_linear_u8(img.data(), w, h, c, 1, sm.data(), 224, 200, 0);
+            uint64_t sums[6] = {0};
+            float m[3], sd[3];
+            orc_sums_u8(sm.data(), 224 * 200, 3, 1, sums);
+            orc_finalize_mean_stddev(sums, 3, 224 * 200, m, sd);
+            orc_normalize_u8(sm.data(), 224 * 200, 3, 1, m, sd, want.data());
+            report("resize_normalize, default arguments (own statistics)", dn.dtype == FP32 && dn.layout == NHWC && same(dn, want));
+            Tensor dcub;
+            va_cv::resize_normalize(src_f32, dcub, va_cv::VSize(300, 170), 0, 0, va_cv::INTER_CUBIC, mean, stddev);
+            std::vector<float> cub(300 * 170 * 3), wantc(cub.size());
+            orc_resize_cubic_f32(imgf.data(), w, h, c, 1, cub.data(), 300, 170);
+            orc_normalize_f32(cub.data(), 300 * 170, 3, 1, mean_v, std_v, wantc.data());
+            report("resize_normalize fp32 INTER_CUBIC (composition)", same(dcub, wantc));
+            Tensor chw = src_u8.change_layout(NCHW), dchw;
+            va_cv::resize_normalize(chw, dchw, va_cv::VSize(320, 180), 0, 0, va_cv::INTER_LINEAR, mean, stddev);
+            std::vector<uint8_t> in_chw(img.size()), r_chw(320 * 180 * 3);
+            std::vector<float> want_chw(r_chw.size());
+            orc_hwc_to_chw(img.data(), w, h, c, 1, in_chw.data());
+            orc_resize_linear_u8(in_chw.data(), w, h, c, 0, r_chw.data(), 320, 180, 0);
+            orc_normalize_u8(r_chw.data(), 320 * 180, 3, 0, mean_v, std_v, want_chw.data());
+            report("resize_normalize chw u8 (composition)", dchw.layout == NCHW && same(dchw, want_chw));
+
+            float mv[6] = {0.5f, 0.05f, 10.f, -0.05f, 0.5f, 20.f}, inv[6];
+            std::memcpy(inv, mv, sizeof(mv));
+            orc_invert_affine(inv);
+            Tensor M(3, 2, 1, NCHW, FP32), dw;
+            std::memcpy(M.data, mv, sizeof(mv));
+            va_cv::warp_affine_normalize(src_u8, dw, M, va_cv::VSize(96, 80));
+            std::vector<uint8_t> wu(96 * 80 * 3, 0);
+            std::vector<float> wantw(wu.size());
+            orc_warp_affine_u8(img.data(), w, h, 3, 1, wu.data(), 96, 80, inv, 0);
+            uint64_t s2[6] = {0};
+            orc_sums_u8(wu.data(), 96 * 80, 3, 1, s2);
+            orc_finalize_mean_stddev(s2, 3, 96 * 80, m, sd);
+            orc_normalize_u8(wu.data(), 96 * 80, 3, 1, m, sd, wantw.data());
+            report("warp_affine_normalize, default arguments", same(dw, wantw) && std::memcmp(M.data, inv, sizeof(inv)) == 0);
+        }
+        {   // crop uploads only the ROI: off-origin rectangles at every column phase, both layouts, both dtypes
+            bool ok = true;
+            Tensor chw8 = src_u8.change_layout(NCHW), chwf = src_f32.change_layout(NCHW);
+            std::vector<uint8_t> in8(img.size());
+            std::vector<float> inf(img.size());
+            orc_hwc_to_chw(img.data(), w, h, c, 1, in8.data());
+            orc_hwc_to_chw(imgf.data(), w, h, c, 4, inf.data());
+            const int rects[][4] = {{17, 5, 101, 77}, {16, 0, 624, 360}, {1, 359, 3, 1}, {333, 100, 307, 259}, {0, 0, 640, 360}, {48, 31, 64, 64}};
+            for (auto& r : rects) {
+                vision::VRect rect((float)r[0], (float)r[1], (float)(r[0] + r[2]), (float)(r[1] + r[3]));
+                Tensor a, b, cc, d;
+                va_cv::crop(src_u8, a, rect); va_cv::crop(src_f32, b, rect); va_cv::crop(chw8, cc, rect); va_cv::crop(chwf, d, rect);
+                std::vector<uint8_t> w8((size_t)r[2] * r[3] * 3), w8c(w8.size());
+                std::vector<float> wf(w8.size()), wfc(w8.size());
+                orc_crop(img.data(), w, h, c, 1, 1, r[0], r[1], r[2], r[3], w8.data());
+                orc_crop(imgf.data(), w, h, c, 4, 1, r[0], r[1], r[2], r[3], wf.data());
+                orc_crop(in8.data(), w, h, c, 1, 0, r[0], r[1], r[2], r[3], w8c.data());
+                orc_crop(inf.data(), w, h, c, 4, 0, r[0], r[1], r[2], r[3], wfc.data());
+                ok = ok && same(a, w8) && same(b, wf) && cc.layout == NCHW && same(cc, w8c) && same(d, wfc);
+            }
+            report("crop off-origin, hwc / chw, u8 / fp32 (ROI-only upload)", ok);
+        }
+        {   // one thread, alternating shapes (and GPUs when the box has two): per-device contexts and LRU plan caches
+            int n_dev = 0;
+            vacv_cuda_device_count(&n_dev);
+            const int sizes[][2] = {{320, 180}, {200, 120}, {416, 234}};
+            std::vector<std::vector<uint8_t>> wants;
+            for (auto& sz : sizes) {
+                std::vector<uint8_t> wv((size_t)sz[0] * sz[1] * 3);
+                orc_resize_linear_u8(img.data(), w, h, c, 1, wv.data(), sz[0], sz[1], 0);
+                wants.push_back(wv);
+            }
+            std::vector<uint8_t> nv((size_t)w * h * 3 / 2);
+            orc_bgr_to_nv21(img.data(), w, h, nv.data());
+            bool ok = true;
+            for (int it = 0; it < 12; ++it) {
+                if (n_dev >= 2) ok = ok && vacv_cuda_set_device(it & 1) == 0;
+                const int k = it % 3;
+                Tensor d;
+                va_cv::resize(src_u8, d, va_cv::VSize(sizes[k][0], sizes[k][1]));
+                ok = ok && same(d, wants[k]);
+                // the host-buffer form of the fused pipeline on the same thread / device
+                const int wo = 160 + 32 * k, ho = 96 + 16 * k;
+                std::vector<float> got((size_t)3 * wo * ho), wantp(got.size());
+                ok = ok && vacv_cuda_nv_resize_normalize_chw_host(nv.data(), got.data(), 1, w, h, 1, wo, ho, mean_v, std_v, 1) == 0;
+                orc_nv_resize_normalize_chw(nv.data(), w, h, 1, wo, ho, mean_v, std_v, wantp.data());
+                ok = ok && std::memcmp(got.data(), wantp.data(), got.size() * sizeof(float)) == 0;
+            }
+            if (n_dev >= 2) vacv_cuda_set_device(0);
+            report(n_dev >= 2 ? "one thread alternating 2 GPUs x 3 shapes" : "one thread alternating 3 shapes (1 GPU)", ok);
         }
         {   // ownership: ref counting and the error path
             Tensor a(16, 16, 3, INT8, NHWC);
