@@ -64,6 +64,7 @@ _SIGS = {
     "vacv_cuda_malloc": [_vp, _sz],
     "vacv_cuda_free": [_vp],
     "vacv_cuda_host_alloc": [_vp, _sz],
+    "vacv_cuda_host_alloc_flags": [_vp, _sz, _i],
     "vacv_cuda_host_free": [_vp],
     "vacv_cuda_memcpy_h2d": [_vp, _vp, _sz, _vp],
     "vacv_cuda_memcpy_d2h": [_vp, _vp, _sz, _vp],

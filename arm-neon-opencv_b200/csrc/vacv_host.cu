@@ -141,6 +141,10 @@ extern "C" int vacv_cuda_host_alloc(void** h_ptr, size_t bytes) {
     VACV_REQUIRE(h_ptr, "host_alloc: null pointer");
     VACV_RT(cudaHostAlloc(h_ptr, bytes, cudaHostAllocDefault), "host_alloc");
 }
+extern "C" int vacv_cuda_host_alloc_flags(void** h_ptr, size_t bytes, int write_combined) {
+    VACV_REQUIRE(h_ptr, "host_alloc_flags: null pointer");
+    VACV_RT(cudaHostAlloc(h_ptr, bytes, write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault), "host_alloc_flags");
+}
 extern "C" int vacv_cuda_host_free(void* h_ptr) { VACV_RT(cudaFreeHost(h_ptr), "host_free"); }
 extern "C" int vacv_cuda_memcpy_h2d(void* dptr, const void* h_ptr, size_t bytes, void* stream) {
     VACV_RT(cudaMemcpyAsync(dptr, h_ptr, bytes, cudaMemcpyHostToDevice, vacv::as_stream(stream)), "memcpy_h2d");

@@ -13,6 +13,13 @@ synthetic 1920x1080 frames per GPU (BASELINE.json configs[1]).  Under torchrun e
   roofline   algorithmic bytes (8 025 600 B / frame) / kernel time vs the measured HBM copy peak
   cpu_baseline  the reference's own CPU chain (oracle/_ref, compiled from its sources) on this box's host cores
 
+  c5         config 5 (BASELINE.json configs[4]) measured in the same run, same ranks: batch-global mean/stddev + normalize over
+             128 4K frames per GPU through ONE C call per step (vacv_cuda_normalize_batch_global: sums -> all-reduce of 7 u64 ->
+             finalize -> normalize), for the NCCL transport and the peer-memory transport; `gap_us` = CUDA-event distance between
+             the end of the sums kernel and the start of the normalize kernel (the cost of the exchange)
+  e2e.platform_ceiling_*  the same chunked H2D + D2H copy pattern as the e2e call with NO kernels, all ranks at once: what the
+             host's PCIe / memory system delivers; e2e is reported as a fraction of it
+
 --impl reference times that CPU chain alone (same config, metric and unit).
 """
 import argparse
@@ -35,6 +42,11 @@ OUT_PIX = WO * HO
 MEAN = [103.53, 116.28, 123.675]
 STD = [57.375, 57.12, 58.395]
 METRIC = "output Mpix/s, 1080p NV12->640x640 CHW fp32 (fused yuv2bgr+resize+normalize+layout)"
+# identical in both arms (the driver compares `config`): the workload, not how an arm runs it
+CONFIG = {"workload": "c2: fused yuv2bgr+resize+normalize+HWC->CHW fp32, batch 256 NV12 1920x1080 -> 640x640 per GPU",
+          "frames_per_step_per_gpu": BATCH, "src": "NV12 1920x1080 u8", "dst": "3x640x640 fp32 planes", "data": "seeded uniform u8"}
+C5_B, C5_W, C5_H = 128, 3840, 2160           # config 5: 128 4K BGR frames per GPU
+C5_ALGO_BYTES_PER_PIX = 3 * (1 + 1 + 4)      # two u8 reads + one fp32 write per element (149 299 200 B / frame)
 
 
 def measured_peak():
@@ -45,9 +57,12 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+TRAFFIC_PROFILE = "r2_fused_head_ncu_raw.txt" if os.path.exists(os.path.join(ROOT, "profiles", "r2_fused_head_ncu_raw.txt")) else "r1_fused_v3_ncu_raw.txt"
+
+
 def ncu_traffic_bytes():
     """DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture (profiles/)."""
-    path = os.path.join(ROOT, "profiles", "r1_fused_v3_ncu_raw.txt")
+    path = os.path.join(ROOT, "profiles", TRAFFIC_PROFILE)
     scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     try:
         total = 0.0
@@ -149,44 +164,162 @@ def cpu_arm(seconds_budget, frames_per_step=None, steps=None, warmup=0):
 def run_reference(args, rank):
     if rank != 0:
         return
-    cores = len(os.sched_getaffinity(0))
-    n = 4 * max(cores, 8)
+    n = BATCH   # the same 256-frame batch per step as the GPU arm
     mpix, info, ms = cpu_arm(None, frames_per_step=n, steps=args.steps, warmup=max(1, min(args.warmup, 2)))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": info["value"], "unit": "Mpix/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "c2: fused yuv2bgr+resize+normalize+HWC->CHW fp32, NV12 1920x1080 -> 640x640",
-                   "frames_per_step": n, "note": "reference CPU chain, bounded sample per step"},
+        "config": CONFIG,
+        "arm": "reference CPU chain (oracle/_ref: unmodified reference sources), all host cores over frames, one 256-frame batch per step",
         "cpu_baseline": info,
         "e2e": {"value": info["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
 
 
+def _cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if "-" in part:
+            lo, hi = part.split("-")
+            cpus.update(range(int(lo), int(hi) + 1))
+        elif part:
+            cpus.add(int(part))
+    return cpus
+
+
 def bind_to_gpu_numa(index):
-    """Run this rank on the CPUs NVML reports as local to its GPU, so that the pinned staging buffers of the e2e path are
-    first-touched on the GPU's own NUMA node (8 ranks on one host otherwise fight over one socket's memory and PCIe root).
-    Best effort: returns a short description for the JSON line."""
+    """Pin this rank to the CPUs of its GPU's NUMA node BEFORE any pinned buffer is allocated (cudaHostAlloc places pages on the
+    allocating thread's node), so the e2e staging buffers sit next to the GPU's PCIe root.  The node comes from
+    /sys/bus/pci/devices/<bdf>/numa_node (NVML's CPU affinity as a second source).  Returns a description for the JSON line."""
+    info = {"gpu": index, "numa_node": None, "nodes_online": None, "bound_cpus": None}
     try:
+        allowed = os.sched_getaffinity(0)
+        try:
+            info["nodes_online"] = open("/sys/devices/system/node/online").read().strip()
+        except OSError:
+            pass
         import pynvml
         pynvml.nvmlInit()
         h = pynvml.nvmlDeviceGetHandleByIndex(index)
-        allowed = os.sched_getaffinity(0)
-        words = (max(allowed) // 64) + 1
-        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
-        local = {64 * i + b for i, wd in enumerate(mask) for b in range(64) if (wd >> b) & 1} & allowed
+        bdf = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bdf = (bdf.decode() if isinstance(bdf, bytes) else bdf).lower()
+        if len(bdf.split(":")[0]) == 8:      # NVML prints an 8-digit PCI domain, sysfs a 4-digit one
+            bdf = bdf[4:]
+        local = set()
+        try:
+            node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+            info["numa_node"] = node
+            if node >= 0:
+                local = _cpulist(open(f"/sys/devices/system/node/node{node}/cpulist").read()) & allowed
+        except (OSError, ValueError):
+            pass
+        if not local:
+            words = (max(allowed) // 64) + 1
+            mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+            local = {64 * i + b for i, wd in enumerate(mask) for b in range(64) if (wd >> b) & 1} & allowed
         if local and local != allowed:
             os.sched_setaffinity(0, local)
-            return f"{len(local)} of {len(allowed)} cpus (GPU-local NUMA node)"
-        return f"{len(allowed)} cpus (no narrower GPU-local set)"
+            info["bound_cpus"] = len(local)
+        info["allowed_cpus"] = len(allowed)
     except Exception as e:   # noqa: BLE001
-        return f"unbound ({type(e).__name__})"
+        info["error"] = type(e).__name__
+    return info
 
 
 # ---------------------------------------------------------------------------------------------------- GPU arm
+def pcie_ceiling(torch, dev, h_in, h_out, chunk, steps, barrier, max_over_ranks):
+    """The copy pattern of the e2e call with NO kernels: per chunk one cudaMemcpyAsync H2D (pinned NV12 frames) on one stream and
+    one cudaMemcpyAsync D2H (fp32 planes) on another, double-buffered device staging, every rank at once.  Also H2D alone and
+    D2H alone.  Returns GB/s per GPU for the three patterns (max-over-ranks time)."""
+    n = h_in.shape[0]
+    d_in = [torch.empty((chunk,) + tuple(h_in.shape[1:]), dtype=h_in.dtype, device=dev) for _ in range(2)]
+    d_out = [torch.empty((chunk,) + tuple(h_out.shape[1:]), dtype=h_out.dtype, device=dev) for _ in range(2)]
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    res = {}
+    for mode in ("h2d+d2h", "h2d", "d2h"):
+        def one():
+            for i, f0 in enumerate(range(0, n, chunk)):
+                if mode != "d2h":
+                    with torch.cuda.stream(s_in):
+                        d_in[i & 1].copy_(h_in[f0:f0 + chunk], non_blocking=True)
+                if mode != "h2d":
+                    with torch.cuda.stream(s_out):
+                        h_out[f0:f0 + chunk].copy_(d_out[i & 1], non_blocking=True)
+            s_in.synchronize()
+            s_out.synchronize()
+        one()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            one()
+        ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / steps
+        barrier()
+        nbytes = (h_in.numel() * h_in.element_size() if mode != "d2h" else 0) + (h_out.numel() * h_out.element_size() if mode != "h2d" else 0)
+        res[mode] = {"ms": round(ms, 3), "gbs_per_gpu": round(nbytes / (ms * 1e-3) / 1e9, 2)}
+    return res
+
+
+def c5_measure(torch, vacv, dev, rank, world, steps, max_over_ranks, barrier):
+    """Config 5 on this run's ranks: 128 4K BGR frames per GPU -> batch-global statistics -> normalised fp32, ONE C call per step
+    (include/vacv_dist.h / vacv_cuda.h).  Per transport: ms per step (CUDA events, max over ranks), aggregate Mpix/s, per-GPU
+    fraction of the HBM copy peak (18 B per pixel), and the exchange gap (end of sums kernel -> start of normalize kernel)."""
+    from arm_neon_opencv_b200 import distributed as vd
+    g = torch.Generator(device=dev).manual_seed(77 + rank)
+    frames = torch.randint(0, 256, (C5_B, C5_H, C5_W, 3), dtype=torch.uint8, device=dev, generator=g)
+    out = torch.empty((C5_B, C5_H, C5_W, 3), dtype=torch.float32, device=dev)
+    work = torch.empty(16, dtype=torch.int64, device=dev)
+    ms_buf = torch.empty((2, 3), dtype=torch.float32, device=dev)
+    peak, _ = measured_peak()
+    px = C5_B * C5_W * C5_H
+    res = {"workload": "c5: batch-global mean/stddev + normalize, 3840x2160 BGR u8 -> fp32, 128 frames per GPU", "frames_per_gpu": C5_B,
+           "algorithmic_bytes_per_gpu_step": px * C5_ALGO_BYTES_PER_PIX, "n_gpus": world, "steps": steps, "transports": {}}
+    stats = {}
+    for name in ("nccl", "p2p"):
+        t = vd.NcclComm() if name == "nccl" else vd.P2PExchange()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        for e in ev:
+            e.record()   # creates the underlying cudaEvent_t so the C entry can record it
+        def step():
+            ev[0].record()
+            vd.normalize_batch_global(t, frames, vacv.NHWC, out=out, work=work, mean_std=ms_buf, ev_sums_done=ev[1], ev_stats_ready=ev[2])
+            ev[3].record()
+        for _ in range(3):
+            step()
+        barrier()
+        times, gaps = [], []
+        for _ in range(steps):
+            step()
+            ev[3].synchronize()
+            times.append(ev[0].elapsed_time(ev[3]))
+            gaps.append(ev[1].elapsed_time(ev[2]) * 1e3)
+        barrier()
+        ms = max_over_ranks(statistics.median(times))
+        res["transports"][name] = {
+            "ms_per_step": round(ms, 4), "value_mpix_s": round(world * px / (ms * 1e-3) / 1e6, 1),
+            "per_gpu_gbs": round(px * C5_ALGO_BYTES_PER_PIX / (ms * 1e-3) / 1e9, 1),
+            "per_gpu_frac": round(px * C5_ALGO_BYTES_PER_PIX / (ms * 1e-3) / 1e9 / peak, 4),
+            "gap_us_median": round(max_over_ranks(statistics.median(gaps)), 1), "gap_us_min": round(max_over_ranks(min(gaps)), 1),
+            "launches_per_step": 5 if name == "nccl" else 5}
+        stats[name] = ms_buf.cpu().numpy().copy()
+        if name == "p2p":
+            res["transports"][name]["timed_out"] = t.timed_out()
+        t.close()
+    import numpy as np
+    res["transports_agree"] = bool(np.array_equal(stats["nccl"].view(np.uint32), stats["p2p"].view(np.uint32)))
+    res["mean"] = [round(float(v), 4) for v in stats["nccl"][0]]
+    res["stddev"] = [round(float(v), 4) for v in stats["nccl"][1]]
+    res["note"] = ("sums_u8 -> all-reduce of 7 u64 (56 B) -> finalize -> normalize on one stream; nccl = ncclAllReduce on this library's own "
+                   "communicator, p2p = stores into every peer's IPC-mapped slot + local polling in one 1-CTA kernel; gap = cudaEvent after "
+                   "the sums kernel -> cudaEvent before the normalize kernel (exchange + finalize + launch gaps + waiting for the slowest rank)")
+    del frames, out
+    torch.cuda.empty_cache()
+    return res
+
+
 def run_ours(args, rank, world, local_rank):
-    numa = bind_to_gpu_numa(local_rank) if world > 1 else "single rank: all cpus"
+    numa = bind_to_gpu_numa(local_rank)
     import torch
     import vacv_b200 as vacv
 
@@ -267,6 +400,19 @@ def run_ours(args, rank, world, local_rank):
     for fidx in (0, BATCH // 2 + 1, BATCH - 1):
         assert torch.equal(h_out[fidx].to(dev), out[fidx]), "e2e output differs from device-resident output"
 
+    # ---- what the platform delivers for the same copy pattern with no kernels (every rank at once)
+    ceiling = None
+    if not args.no_ceiling:
+        ceiling = pcie_ceiling(torch, dev, h_in, h_out, chunk, e2e_steps, barrier, max_over_ranks)
+    e2e_ms = t_e2e / e2e_steps
+    e2e_gbs = BATCH * (IN_FRAME + OUT_FRAME) / (e2e_ms * 1e-3) / 1e9
+    del h_in, h_out
+
+    # ---- config 5 on the same ranks (the one collective of the path)
+    c5 = None
+    if not args.no_c5:
+        c5 = c5_measure(torch, vacv, dev, rank, world, max(5, min(args.steps, 20)), max_over_ranks, barrier)
+
     clocks = clk.summary()
     c2 = clk2.summary()
     clocks["reasons"] = sorted(set(clocks["reasons"]) | set(c2["reasons"]))
@@ -286,20 +432,25 @@ def run_ours(args, rank, world, local_rank):
         "metric": METRIC, "value": round(value, 1), "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "c2: fused yuv2bgr+resize+normalize+HWC->CHW fp32, batch 256 NV12 1920x1080 -> 640x640 per GPU",
-                   "frames_per_gpu": BATCH, "parallelism": f"frames sharded over {world} GPU(s), no data-path collective",
-                   "l2": "inputs (796 MB) + outputs (1258 MB) per step exceed the 126 MB L2; no flush needed",
-                   "timing": "CUDA events on the launching stream, max over ranks"},
+        "config": CONFIG,
+        "arm": {"parallelism": f"frames sharded over {world} GPU(s), no data-path collective",
+                "l2": "inputs (796 MB) + outputs (1258 MB) per step exceed the 126 MB L2; no flush needed",
+                "timing": "CUDA events on the launching stream, max over ranks"},
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": ncu_traffic_bytes(),
-                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r1_fused_v3_ncu_raw.txt",
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/" + TRAFFIC_PROFILE,
                      "peak_source": peak_src,
                      "kernel": "nv_resize_normalize_chw_pipe_kernel", "algorithmic_bytes_per_launch": BATCH * ALGO_BYTES_PER_FRAME,
                      "avg_launch_ms": round(own_ms, 4)},
         "e2e": {"value": round(e2e_value, 1), "unit": "Mpix/s", "h2d_bytes_per_step": BATCH * IN_FRAME,
                 "d2h_bytes_per_step": BATCH * OUT_FRAME, "steps": e2e_steps,
-                "launches_per_step": n_chunks, "host_binding": numa,
+                "launches_per_step": n_chunks, "host_binding": numa, "ms_per_step": round(e2e_ms, 3),
+                "pcie_gbs_per_gpu": round(e2e_gbs, 2),
+                "platform_ceiling_gbs": ceiling["h2d+d2h"]["gbs_per_gpu"] if ceiling else None,
+                "frac_of_platform_ceiling": round(e2e_gbs / ceiling["h2d+d2h"]["gbs_per_gpu"], 3) if ceiling else None,
+                "platform_ceiling": ceiling,
                 "note": "one vacv_cuda_nv_resize_normalize_chw_host call per step: pinned host NV12 in, fp32 planes back to pinned host; 32 chunks of 8 frames pipelined H2D/kernel/D2H on three streams; wall clock; PCIe-bound (D2H ~50 GB/s)"},
+        "c5": c5,
         "cpu_baseline": cpu, "gpu_launches": args.steps, "clocks": clocks,
     }))
 
@@ -312,6 +463,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-c5", action="store_true", help="skip the config-5 object (profiling runs)")
+    ap.add_argument("--no-ceiling", action="store_true", help="skip the no-kernel PCIe ceiling measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

@@ -63,7 +63,12 @@ def c1(iters):   # resize INTER_LINEAR u8 BGR 1920x1080 -> 640x360, batch 256
     b = 256
     src = rand_u8(b, 1080, 1920, 3)
     ms, _ = timeit(lambda: vacv.resize(src, vacv.NHWC, 640, 360), iters)
-    report("c1 resize linear u8 hwc 1920x1080->640x360 x256", ms, b * 640 * 360, b * (1920 * 1080 * 3 + 640 * 360 * 3))
+    report("c1 resize linear u8 hwc 1920x1080->640x360 x256", ms, b * 640 * 360, b * (1920 * 1080 * 3 + 640 * 360 * 3),
+           "SURVEY 8d bytes (whole source frame); the kernel must touch one source row in three -> next line")
+    # bytes the operator MUST touch: ratio 3.0 samples source row 3*dy+1 only (fractional weight 0), and of that row the pixel
+    # 3*dx+1 of every 3 -- whole 32-byte sectors of the sampled rows are fetched, i.e. the full row: 360 rows x 5760 B + output
+    report("   same launch, touched bytes (360 sampled rows, whole sectors)", ms, b * 640 * 360, b * (360 * 1920 * 3 + 640 * 360 * 3),
+           "the roofline that applies: frac must be <= 1")
     ms, _ = timeit(lambda: vacv.resize(src, vacv.NHWC, 500, 300), iters)
     report("   resize linear u8 hwc 1920x1080->500x300 x256", ms, b * 500 * 300, b * (1920 * 1080 * 3 + 500 * 300 * 3))
 
@@ -135,10 +140,10 @@ def c3(iters):   # warp_affine face crops: 4096 x (1280x720 -> 112x112 fp32 norm
     roi = int(np.mean([(wo / s) ** 2 * 3 for s in np.random.default_rng(7).uniform(0.3, 0.6, 1000)]))
     ms, _ = timeit(lambda: vacv.warp_affine_normalize(frames, minv, wo, wo, mean, std, idx), iters)
     report("c3 warp_affine_normalize 1280x720->112x112 f32 x4096", ms, n * wo * wo, n * (roi + wo * wo * 12), "bytes = mean source ROI + out")
-    os.environ["VACV_WARP_GATHER"] = "1"    # A/B: the direct gather kernel instead of the TMA-staged default
+    vacv.lib.vacv_cuda_set_tuning(b"WARP_GATHER", 1)    # A/B: the direct gather kernel instead of the TMA-staged default
     ms, _ = timeit(lambda: vacv.warp_affine_normalize(frames, minv, wo, wo, mean, std, idx), iters)
-    del os.environ["VACV_WARP_GATHER"]
-    report("   same, direct gather kernel (VACV_WARP_GATHER=1)", ms, n * wo * wo, n * (roi + wo * wo * 12))
+    vacv.lib.vacv_cuda_set_tuning(b"WARP_GATHER", 0)
+    report("   same, direct gather kernel (WARP_GATHER=1)", ms, n * wo * wo, n * (roi + wo * wo * 12))
     ms, _ = timeit(lambda: vacv.warp_affine(frames, vacv.NHWC, minv, wo, wo, idx), iters)
     report("   warp_affine u8 1280x720->112x112 x4096", ms, n * wo * wo, n * (roi + wo * wo * 3))
     ms, _ = timeit(lambda: vacv.warp_affine(frames, vacv.NHWC, minv, wo, wo, idx, vacv.FLAG_TILED), iters)
@@ -157,38 +162,113 @@ def c4(iters):   # resize INTER_CUBIC u8 2560x1440 -> 1920x1080, batch 128
     report("   resize cubic f32 hwc 2560x1440->1920x1080 x32", ms, 32 * 1920 * 1080, 32 * 4 * (2560 * 1440 * 3 + 1920 * 1080 * 3))
 
 
-def c5(iters):   # batch-global mean/stddev + normalize, 4K frames, 128 per GPU (all-reduce of the sums under torchrun)
+def c5(iters):   # batch-global mean/stddev + normalize, 4K frames, 128 per GPU: ONE C call per step, NCCL and peer-memory transports
     world = int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
     dist = None
+    dev = torch.device("cuda", torch.cuda.current_device())
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
-    from arm_neon_opencv_b200 import distributed as vd
-    b, w, h = 128, 3840, 2160
-    frames = rand_u8(b, h, w, 3, seed=int(os.environ.get("RANK", 0)))
-    out = torch.empty((b, h, w, 3), dtype=torch.float32, device="cuda")
-    sums = torch.zeros((1, 3, 2), dtype=torch.int64, device="cuda")
+        dist.init_process_group("nccl", device_id=dev)
+    from bench import C5_B, C5_H, C5_W, c5_measure
 
-    def step():
-        sums.zero_()
-        vacv.sums_u8(frames, vacv.NHWC, False, sums)
-        vd.allreduce_sums(sums)                         # 48 bytes over NCCL: the only inter-GPU exchange of the path
-        mean, std = vacv.finalize_mean_stddev(sums, world * b * w * h)
-        vacv.normalize(frames, vacv.NHWC, mean[0], std[0], out=out)
-    ms, _ = timeit(step, iters, warmup=3)
-    if dist:
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    def barrier():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+
+    def max_over_ranks(v):
+        if not dist:
+            return v
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    if int(os.environ.get("RANK", 0)) == 0:
-        report(f"c5 global mean/stddev + normalize 4K x{b}/GPU, {world} GPU(s)", ms, world * b * w * h, world * b * w * h * 3 * (1 + 1 + 4),
-               f"2 reads + 1 fp32 write; aggregate over {world} GPU(s): per-GPU frac = {b * w * h * 18 / (ms * 1e-3) / 1e9 / PEAK:.3f}")
+        return float(t.item())
+    res = c5_measure(torch, vacv, dev, rank, world, iters, max_over_ranks, barrier)
+    b, w, h = C5_B, C5_W, C5_H
+    if rank == 0:
+        for name, t in res["transports"].items():
+            report(f"c5 normalize_batch_global[{name}] 4K x{b}/GPU, {world} GPU(s)", t["ms_per_step"], world * b * w * h, world * b * w * h * 18,
+                   f"per-GPU frac {t['per_gpu_frac']:.3f}; exchange gap median {t['gap_us_median']} us (min {t['gap_us_min']} us)")
+        RESULTS.append({"name": "c5 object", **res})
     if world == 1:
+        frames = rand_u8(b, h, w, 3)
+        out = torch.empty((b, h, w, 3), dtype=torch.float32, device="cuda")
+        sums = torch.zeros((1, 3, 2), dtype=torch.int64, device="cuda")
         ms, _ = timeit(lambda: vacv.sums_u8(frames, vacv.NHWC, False, sums), iters)
         report("   sums_u8 (stats pass) 4K x128", ms, b * w * h, b * w * h * 3)
         mean, std = stats()
         ms, _ = timeit(lambda: vacv.normalize(frames, vacv.NHWC, mean, std, out=out), iters)
         report("   normalize u8->f32 (apply pass) 4K x128", ms, b * w * h, b * w * h * 3 * 5)
+    if dist:
+        dist.destroy_process_group()
+
+
+def pcie(iters):
+    """The platform ceiling of the end-to-end path: the chunked cudaMemcpyAsync pattern of run_host_pipeline
+    (csrc/vacv_host.cu) -- H2D of NV12 chunks and D2H of fp32 plane chunks on two streams -- with NO kernels, on every rank at once;
+    H2D alone and D2H alone; pinned (default) vs write-combined host source.  Run under torchrun for N GPUs."""
+    import ctypes as C
+    import time
+    from bench import BATCH, HO, IN_FRAME, WO, bind_to_gpu_numa, pcie_ceiling
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    numa = bind_to_gpu_numa(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+
+    def max_over_ranks(v):
+        if not dist:
+            return v
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    h_in = torch.randint(0, 256, (BATCH, IN_FRAME), dtype=torch.uint8).pin_memory()
+    h_out = torch.empty((BATCH, 3, HO, WO), dtype=torch.float32).pin_memory()
+    out = {"name": "pcie", "n_gpus": world, "host_binding": numa, "chunks": {}}
+    for chunk in (8, 32):
+        out["chunks"][chunk] = pcie_ceiling(torch, dev, h_in, h_out, chunk, max(3, iters // 4), barrier, max_over_ranks)
+    # write-combined source for the H2D direction (cudaHostAllocWriteCombined through the C-ABI)
+    p = C.c_void_p()
+    nbytes = BATCH * IN_FRAME
+    if vacv.lib.vacv_cuda_host_alloc_flags(C.byref(p), nbytes, 1) == 0:
+        d = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        C.memset(p, 7, nbytes)
+        s = torch.cuda.current_stream().cuda_stream
+        for _ in range(2):
+            vacv.lib.vacv_cuda_memcpy_h2d(d.data_ptr(), p, nbytes, s)
+        barrier()
+        t0 = time.perf_counter()
+        n = max(3, iters // 4)
+        for _ in range(n):
+            vacv.lib.vacv_cuda_memcpy_h2d(d.data_ptr(), p, nbytes, s)
+        torch.cuda.synchronize()
+        ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / n
+        out["h2d_write_combined_gbs_per_gpu"] = round(nbytes / (ms * 1e-3) / 1e9, 2)
+        vacv.lib.vacv_cuda_host_free(p)
+    # the real e2e call beside it
+    run = lambda: vacv.nv_resize_normalize_chw_host(h_in, h_out, 1920, 1080, WO, HO, MEAN, STD, True, 8)
+    run()
+    barrier()
+    t0 = time.perf_counter()
+    n = max(3, iters // 4)
+    for _ in range(n):
+        run()
+    ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / n
+    out["e2e_ms"] = round(ms, 3)
+    out["e2e_gbs_per_gpu"] = round(BATCH * (IN_FRAME + 3 * HO * WO * 4) / (ms * 1e-3) / 1e9, 2)
+    out["e2e_frac_of_ceiling"] = round(out["e2e_gbs_per_gpu"] / out["chunks"][8]["h2d+d2h"]["gbs_per_gpu"], 3)
+    if rank == 0:
+        RESULTS.append(out)
+        print(json.dumps(out), flush=True)
     if dist:
         dist.destroy_process_group()
 
@@ -358,7 +438,9 @@ def main():
     if wl in ("ops2",):
         ops2(args.iters)
     if wl in ("all", "c5"):
-        c5(max(3, args.iters // 4))
+        c5(max(5, args.iters // 2))
+    if wl in ("pcie",):
+        pcie(args.iters)
     if args.json and int(os.environ.get("RANK", 0)) == 0:
         with open(args.json, "a") as f:
             for r in RESULTS:

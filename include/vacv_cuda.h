@@ -249,6 +249,9 @@ VACV_API int vacv_cuda_get_device(int* device);
 VACV_API int vacv_cuda_malloc(void** dptr, size_t bytes);
 VACV_API int vacv_cuda_free(void* dptr);
 VACV_API int vacv_cuda_host_alloc(void** h_ptr, size_t bytes);      /* pinned */
+/* write_combined = 1: cudaHostAllocWriteCombined (the reference's USE_CUDA allocator flag, va_cuda_allocator.cu:28-30): fast for
+ * the device to read, very slow for the CPU to read -- only for buffers the host fills once and never reads back */
+VACV_API int vacv_cuda_host_alloc_flags(void** h_ptr, size_t bytes, int write_combined);
 VACV_API int vacv_cuda_host_free(void* h_ptr);
 VACV_API int vacv_cuda_memcpy_h2d(void* dptr, const void* h_ptr, size_t bytes, void* stream);
 VACV_API int vacv_cuda_memcpy_d2h(void* h_ptr, const void* dptr, size_t bytes, void* stream);
