@@ -15,12 +15,14 @@
 //                 u8: H is an exact integer carried as fp32 (|H| < 2^22), vertical pass = OpenCV's fp32 SSE2 body
 //                 with round-half-even, or its integer tail for the last <= 7 elements of an output row.
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdlib>
 
 #include "resize_coeffs.cuh"
 #include "resize_cubic3.cuh"
 #include "resize_cubic3_walk.cuh"
+#include "resize_cubic3_walkn.cuh"
 #include "host_util.cuh"
 #include "vacv_common.cuh"
 
@@ -666,6 +668,87 @@ static int launch_cubic3_walk2(const uint8_t* src, uint8_t* dst, int images, int
     return 1;
 }
 
+// u8, second generation (resize_cubic3_walkn.cuh): NC = 4 (or 2) columns per thread, 2..4 warps per CTA chosen for the least padding.
+// Needs 16-byte aligned source rows (cp.async ring); everything else stays on launch_cubic3_walk2.
+struct WalkNPlan { int h, ho; bool down, valid; };
+static bool walkn_rows_strictly_increase(int h, int ho, double scale_y) {
+    // kDown's precondition, checked with the device's own arithmetic (cubic_cv_coord_scaled): every output row ends on a later source row
+    static thread_local PlanCache<WalkNPlan, 8> cache;
+    if (WalkNPlan* p = cache.find([&](const WalkNPlan& q) { return q.h == h && q.ho == ho; })) return p->down;
+    bool down = true;
+    int prev = INT_MIN;
+    for (int d = 0; d < ho && down; ++d) {
+        const float f = (float)(((double)d + 0.5) * scale_y - 0.5);
+        const int sy = (int)floorf(f);
+        down = sy > prev;
+        prev = sy;
+    }
+    WalkNPlan* p = cache.claim();
+    p->h = h; p->ho = ho; p->down = down;
+    cache.commit();
+    return down;
+}
+
+template <int NC>
+static int launch_cubic3_walkn_nc(const uint8_t* src, uint8_t* dst, int images, int w, int h, int wo, int ho, cudaStream_t s) {
+    WalkNGeom g;
+    g.w = w; g.h = h; g.wo = wo; g.ho = ho;
+    g.src_image = (size_t)w * h * 3; g.dst_image = (size_t)wo * ho * 3;
+    g.scale_x = 1. / ((double)wo / (double)w); g.scale_y = 1. / ((double)ho / (double)h);   // OpenCV 2.4
+    const int span_px = (int)std::ceil((32.0 * NC - 1) * g.scale_x) + 2;
+    g.ring_pitch = ((span_px * 3 + 12 + 4 + 15 + 15) & ~15) + 16;
+    if (g.ring_pitch > 1024) return 0;                 // two 16-byte chunks per lane and row at most
+    g.warp_strips = (wo + 32 * NC - 1) / (32 * NC);
+    int warps = 4, best_pad = INT_MAX;
+    for (int wv = 4; wv >= 2; --wv) {
+        const int pad = (g.warp_strips + wv - 1) / wv * wv - g.warp_strips;
+        if (pad < best_pad) { best_pad = pad; warps = wv; }
+    }
+    g.cta_strips = (g.warp_strips + warps - 1) / warps;
+    g.store16 = (((size_t)wo * 3) % 16 == 0 && ((uintptr_t)dst % 16) == 0) ? 1 : 0;
+    g.one2 = 0x3F8000003F800000ull; g.negzero2 = 0x8000000080000000ull; g.magic2 = 0x4B4000004B400000ull; g.negmagic2 = 0xCB400000CB400000ull;
+    const int per_sm = (NC == 4 ? 4 : 6) * 4 / warps;   // resident CTAs per SM at the kernel's register budget
+    const long long want = 8LL * per_sm * current_sm_count();
+    const long long per_seg = (long long)g.cta_strips * images;
+    long long segs = std::max<long long>(1, std::min<long long>((want + per_seg - 1) / per_seg, (ho + 63) / 64));
+    if (const int v = knob(kKnobWalkSegs)) segs = std::max(1, v);   // tuning knob
+    int rps = (int)((ho + segs - 1) / segs);
+    rps = std::min(kWalkMaxRows, std::max(rps, 1));
+    g.rows_per_seg = rps;
+    g.segs = (ho + rps - 1) / rps;
+    const size_t smem = (size_t)(rps + 1) * sizeof(Walk2Row) + (size_t)warps * kWnStageRows * 32 * NC * 3 + (size_t)warps * kWnRing * g.ring_pitch;
+    const bool down = walkn_rows_strictly_increase(h, ho, g.scale_y);
+    auto kern = down ? resize_cubic3_walkn_kernel<NC, true> : resize_cubic3_walkn_kernel<NC, false>;
+    if (smem > 48 * 1024) {
+        if (smem > 200 * 1024) return 0;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return set_error(VACV_ERR_CUDA, "resize: %s", cudaGetErrorString(e));
+    }
+    const int first_px = ((wo * 3) & ~7) / 3;
+    for (int i0 = 0; i0 < images; i0 += 65535) {
+        const int n = std::min(images - i0, 65535);
+        dim3 grid(g.cta_strips * g.segs, n);
+        kern<<<grid, 32 * warps, smem, s>>>(src + (size_t)i0 * g.src_image, dst + (size_t)i0 * g.dst_image, g);
+        if (first_px < wo) {
+            const long long items = (long long)n * ho * (wo - first_px);
+            resize_cubic3_tail_kernel<<<(unsigned)((items + 127) / 128), 128, 0, s>>>(src + (size_t)i0 * g.src_image, dst + (size_t)i0 * g.dst_image, w, h, wo, ho,
+                                                                                  g.scale_x, g.scale_y, g.src_image, g.dst_image, first_px, n);
+        }
+    }
+    return 1;
+}
+
+static int launch_cubic3_walkn(const uint8_t* src, uint8_t* dst, int images, int w, int h, int wo, int ho, cudaStream_t s) {
+    if (((size_t)w * 3) % 16 != 0 || ((uintptr_t)src % 16) != 0) return 0;     // the cp.async ring copies aligned 16-byte chunks
+    if (w < 4 || h < 4 || (size_t)w * h * 3 >= 0xffffffffull || (size_t)wo * ho * 3 >= 0xffffffffull) return 0;
+    if ((double)h / ho > 4.0) return 0;                                           // the walk filters every source row in a segment
+    const int v = knob(kKnobCubicV);                                              // tuning knob: 0 = automatic, 2 / 4 = columns per thread
+    int rc = 0;
+    if (v == 0 || v == 4) rc = launch_cubic3_walkn_nc<4>(src, dst, images, w, h, wo, ho, s);
+    if (rc == 0 && v != 1) rc = launch_cubic3_walkn_nc<2>(src, dst, images, w, h, wo, ho, s);
+    return rc;
+}
+
 template <int KIND>
 static int launch_tiled_kind(const void* src, void* dst, int images, TiledGeom g, size_t smem, cudaStream_t s) {
     auto kern = resize_tiled_kernel<KIND>;
@@ -688,7 +771,9 @@ int try_launch_resize_tiled(int kind, const void* src, void* dst, int images, in
     if (c == 3 && (kind == kCubU8 || kind == kCubF32)) {   // interleaved BGR: rolling separable kernel, else the tiled pixel-per-thread one
         const bool roll = knob(kKnobCubic3Roll) != 0;   // tuning knob: shared-memory ring kernel instead of the column walker
         int rc = 0;
-        if (kind == kCubU8 && !roll) rc = launch_cubic3_walk2((const uint8_t*)src, (uint8_t*)dst, images, w, h, wo, ho, s);
+        if (kind == kCubU8 && !roll && knob(kKnobCubicV) != 1) rc = launch_cubic3_walkn((const uint8_t*)src, (uint8_t*)dst, images, w, h, wo, ho, s);
+        if (rc != 0) return rc;
+        if (kind == kCubU8 && !roll) rc = launch_cubic3_walk2((const uint8_t*)src, (uint8_t*)dst, images, w, h, wo, ho, s);   // CUBIC_V=1: first generation
         if (rc != 0) return rc;
         if (kind == kCubF32 && !roll) rc = launch_cubic_walk_f32<3>((const float*)src, (float*)dst, images, w, h, wo, ho, s);
         if (rc != 0) return rc;

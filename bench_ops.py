@@ -157,6 +157,14 @@ def c4(iters):   # resize INTER_CUBIC u8 2560x1440 -> 1920x1080, batch 128
     src = rand_u8(b, 1440, 2560, 3)
     ms, _ = timeit(lambda: vacv.resize(src, vacv.NHWC, 1920, 1080, vacv.INTER_CUBIC), iters)
     report("c4 resize cubic u8 hwc 2560x1440->1920x1080 x128", ms, b * 1920 * 1080, b * (2560 * 1440 * 3 + 1920 * 1080 * 3))
+    for v, name in ((1, "first-generation walker, 2 columns / thread (CUBIC_V=1)"), (2, "second generation, 2 columns / thread (CUBIC_V=2)")):
+        vacv.lib.vacv_cuda_set_tuning(b"CUBIC_V", v)
+        ms, _ = timeit(lambda: vacv.resize(src, vacv.NHWC, 1920, 1080, vacv.INTER_CUBIC), iters)
+        vacv.lib.vacv_cuda_set_tuning(b"CUBIC_V", 0)
+        report(f"   same, {name}", ms, b * 1920 * 1080, b * (2560 * 1440 * 3 + 1920 * 1080 * 3))
+    big = rand_u8(64, 1080, 1920, 3)
+    ms, _ = timeit(lambda: vacv.resize(big, vacv.NHWC, 1280, 720, vacv.INTER_CUBIC), iters)
+    report("   resize cubic u8 hwc 1920x1080->1280x720 x64", ms, 64 * 1280 * 720, 64 * (1920 * 1080 * 3 + 1280 * 720 * 3))
     srcf = src[:32].to(torch.float32)
     ms, _ = timeit(lambda: vacv.resize(srcf, vacv.NHWC, 1920, 1080, vacv.INTER_CUBIC), iters)
     report("   resize cubic f32 hwc 2560x1440->1920x1080 x32", ms, 32 * 1920 * 1080, 32 * 4 * (2560 * 1440 * 3 + 1920 * 1080 * 3))

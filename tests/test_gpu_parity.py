@@ -288,6 +288,24 @@ def test_resize_cubic_u8(vacv, oracle, c, sz, path):
     assert_same(got, want)
 
 
+@pytest.mark.parametrize("variant", [0, 1, 2, 4])
+@pytest.mark.parametrize("sz", [((1280, 720), (960, 540)), ((1280, 720), (400, 300)), ((1024, 96), (1000, 90)), ((512, 700), (384, 1000)),
+                                ((2048, 64), (1536, 48)), ((768, 300), (1000, 200)), ((256, 256), (129, 255)), ((1920, 1080), (1280, 720))])
+def test_resize_cubic_u8_column_walker_generations(vacv, oracle, sz, variant):
+    """The u8 bicubic walkers (resize_cubic3_walk.cuh: 2 columns per thread; resize_cubic3_walkn.cuh: 4 or 2 columns per thread, 2..4
+    warps per CTA, down-scaling fast path) against the oracle's OpenCV-2.4 rule: partial warp strips, several vertical segments,
+    up- and down-scaling in either axis, a batch of 3.  variant = the CUBIC_V tuning switch (0 automatic, 1 first generation)."""
+    (w, h), (wo, ho) = sz
+    src = u8(40 + variant, 3, h, w, 3)
+    assert vacv.lib.vacv_cuda_set_tuning(b"CUBIC_V", variant) == 0
+    try:
+        got = host(vacv.resize(dev(src), NHWC, wo, ho, vacv.INTER_CUBIC))
+    finally:
+        vacv.lib.vacv_cuda_set_tuning(b"CUBIC_V", 0)
+    for i in range(3):
+        assert_same(got[i], oracle.resize_cubic_u8(src[i], w, h, 3, wo, ho))
+
+
 def test_resize_cubic_u8_config4_fixture_vs_bundled_opencv(vacv):
     img = load_fixture("lakers2560x1440")
     if img is None or not ref_available():
