@@ -6,33 +6,37 @@
 // normalise kernel -- 56 bytes: pure latency, no bandwidth.  Two transports live here (NCCL is in dist_nccl.cpp):
 //
 //  * callback -- the caller's all-reduce;
-//  * peer memory -- every rank owns a small slot buffer that all peers map (CUDA IPC).  One 1-CTA kernel per exchange:
-//    lane r STORES this rank's values straight into rank r's buffer over NVLink / NVSwitch (fire and forget), fences, raises
-//    the flag there, then polls the flag rank r raised in ITS OWN buffer (local L2, nobody spins over the fabric), and sums
-//    the slots in rank order.  No library call, no host involvement: the epoch counter lives on the device, so the kernel
-//    replays unchanged inside a CUDA graph.  Two slot sets alternate by epoch parity: a peer can only be one exchange ahead
-//    (it needs MY flag of epoch e+1 before it can start e+2, and I raise that only after my epoch-e kernel has finished).
+//  * peer memory -- every rank owns a small slot buffer that all peers map (CUDA IPC).  One 1-CTA kernel per exchange: a
+//    thread STORES one 8-byte word {32 payload bits, 32-bit epoch} straight into a peer's buffer over NVLink / NVSwitch (fire
+//    and forget; the word validates itself, so there is no fence and no flag) and then polls the matching word that peer
+//    stored into THIS rank's buffer (local L2, nobody spins over the fabric); the slots are summed in rank order and, for
+//    config 5, mean / stddev are finalised in the same kernel.  No library call, no host involvement: the epoch counter lives
+//    on the device, so the kernel replays unchanged inside a CUDA graph.  Two slot sets alternate by epoch parity: a peer can
+//    only be one exchange ahead (it needs MY words of epoch e+1 before it can start e+2, and I send those only after my
+//    epoch-e kernel has finished reading).
+#include <algorithm>
 #include <cstring>
 
 #include "vacv_common.cuh"
 
 namespace vacv {
 
-constexpr int kXchgWords = 16;   // 15 values + flag; one 128-byte line per (parity, rank)
+constexpr int kXchgMaxCount = 15;            // u64 values per exchange
+constexpr int kXchgWords = 2 * 16;           // 8-byte words per (parity, rank) slot: one per 32-bit half of a value
 
 struct XchgPeers { unsigned long long* buf[VACV_P2P_MAX_RANKS]; };
 
-// layout of a rank's buffer (u64 words): [2][nranks][16] slots, then {epoch, timeouts}
+// layout of a rank's buffer (8-byte words): [2][nranks][32] slots, then {epoch, timeouts}
 __device__ __forceinline__ size_t slot_ofs(int parity, int nranks, int r) { return ((size_t)parity * nranks + r) * kXchgWords; }
 static inline size_t xchg_words(int nranks) { return (size_t)2 * nranks * kXchgWords + 2; }
 
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
     unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ unsigned long long global_timer_ns() {
     unsigned long long t;
@@ -40,35 +44,64 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
     return t;
 }
 
-__global__ void __launch_bounds__(32) p2p_allreduce_u64_kernel(XchgPeers peers, int nranks, int rank, unsigned long long* data, int count) {
+// The exchange, "low latency" style: every 8-byte word on the wire carries 32 bits of payload AND the 32-bit epoch, so a word is
+// valid the moment its epoch matches -- 8-byte stores are single transactions, no fence and no separate flag are needed, and
+// the cost is one store, its flight over NVLink, and one poll.  Thread i handles (peer r, half-word j): it stores its own half j
+// into ITS slot of peer r's buffer and then polls the half that peer r stored into this rank's buffer (local memory).
+// mean_std != nullptr: the values are config 5's {Sx, Sxx per channel, pixel count}; the statistics are finalised right here
+// (one launch less on the critical path between the sums kernel and the normalise kernel).
+__global__ void __launch_bounds__(512) p2p_allreduce_u64_kernel(XchgPeers peers, int nranks, int rank, unsigned long long* data, int count,
+                                                                 float* mean_std, int c) {
+    __shared__ unsigned halves[VACV_P2P_MAX_RANKS][2 * kXchgMaxCount];
+    __shared__ unsigned s_epoch;
+    __shared__ int s_bad;
     unsigned long long* mine = peers.buf[rank];
     unsigned long long* ctl = mine + (size_t)2 * nranks * kXchgWords;
-    const int lane = threadIdx.x;
-    unsigned long long epoch = 0;
-    if (lane == 0) { epoch = ctl[0] + 1; ctl[0] = epoch; }
-    epoch = __shfl_sync(0xffffffffu, epoch, 0);
-    const int parity = (int)(epoch & 1);
-    bool ok = true;
-    if (lane < nranks) {
-        // publish: my values into MY slot of rank `lane`'s buffer (own buffer included), then the flag
-        unsigned long long* dst = peers.buf[lane] + slot_ofs(parity, nranks, rank);
-        for (int i = 0; i < count; ++i) dst[i] = data[i];
-        __threadfence_system();
-        st_release_sys(dst + kXchgWords - 1, epoch);
-        // wait for rank `lane`'s flag in my own buffer
-        const unsigned long long* flag = mine + slot_ofs(parity, nranks, lane) + kXchgWords - 1;
-        const unsigned long long t0 = global_timer_ns();
-        while (ld_acquire_sys(flag) != epoch) {
-            if (global_timer_ns() - t0 > 20000000000ull) { ok = false; break; }
-            __nanosleep(200);
-        }
+    if (threadIdx.x == 0) {
+        unsigned e = (unsigned)ctl[0] + 1;
+        if (e == 0) e = 1;                       // 0 is what fresh (zeroed) slots hold
+        ctl[0] = e;
+        s_epoch = e;
+        s_bad = 0;
     }
-    ok = __all_sync(0xffffffffu, ok);
-    if (!ok && lane == 0) ctl[1] += 1;
-    if (lane < count) {
+    __syncthreads();
+    const unsigned epoch = s_epoch;
+    const int parity = (int)(epoch & 1);
+    const int nhalf = 2 * count;
+    for (int i = threadIdx.x; i < nranks * nhalf; i += blockDim.x) {
+        const int r = i / nhalf, j = i - r * nhalf;
+        const unsigned half = (unsigned)(data[j >> 1] >> (32 * (j & 1)));
+        st_volatile_u64(peers.buf[r] + slot_ofs(parity, nranks, rank) + j, ((unsigned long long)epoch << 32) | half);
+        const unsigned long long* in = mine + slot_ofs(parity, nranks, r) + j;
+        unsigned long long v = ld_volatile_u64(in);
+        if ((unsigned)(v >> 32) != epoch) {
+            const unsigned long long t0 = global_timer_ns();
+            while ((unsigned)((v = ld_volatile_u64(in)) >> 32) != epoch) {
+                if (global_timer_ns() - t0 > 20000000000ull) { s_bad = 1; break; }
+            }
+        }
+        halves[r][j] = (unsigned)v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_bad) ctl[1] += 1;
+    __shared__ unsigned long long total[kXchgMaxCount];
+    if ((int)threadIdx.x < count) {
         unsigned long long v = 0;
-        for (int r = 0; r < nranks; ++r) v += __ldcg(mine + slot_ofs(parity, nranks, r) + lane);
-        data[lane] = v;
+        for (int r = 0; r < nranks; ++r) v += ((unsigned long long)halves[r][2 * threadIdx.x + 1] << 32) | halves[r][2 * threadIdx.x];
+        data[threadIdx.x] = v;
+        total[threadIdx.x] = v;
+    }
+    if (mean_std) {
+        __syncthreads();
+        const int k = threadIdx.x;
+        if (k < c) {
+            const double n = (double)total[2 * c];
+            const double m = (double)total[2 * k] / n;
+            double var = (double)total[2 * k + 1] / n - m * m;
+            if (var < 0) var = 0;
+            mean_std[k] = (float)m;
+            mean_std[c + k] = (float)sqrt(var);
+        }
     }
 }
 
@@ -98,9 +131,6 @@ struct Xchg {
     XchgPeers peers = {};
 };
 
-static int p2p_allreduce_cb(void* ctx, unsigned long long* d_buf, int count, void* stream) {
-    return vacv_cuda_p2p_allreduce_u64(ctx, d_buf, count, stream);
-}
 
 }  // namespace vacv
 
@@ -133,12 +163,32 @@ extern "C" int vacv_cuda_normalize_batch_global_cb(vacv_allreduce_u64_fn allredu
     return vacv_cuda_normalize(src, dst, batch, w, h, c, VACV_INT8, layout, d_mean_std, d_mean_std + c, 0, stream);
 }
 
+static int launch_p2p(void* xchg, unsigned long long* d_buf, int count, float* mean_std, int c, void* stream, const char* who) {
+    Xchg* x = static_cast<Xchg*>(xchg);
+    VACV_REQUIRE(x->connected || x->nranks == 1, "%s: exchange not connected", who);
+    VACV_REQUIRE(count >= 1 && count <= kXchgMaxCount, "%s: 1 <= count <= %d", who, kXchgMaxCount);
+    const int items = x->nranks * 2 * count;
+    const int threads = std::min(512, (items + 31) & ~31);
+    p2p_allreduce_u64_kernel<<<1, std::max(threads, 32), 0, as_stream(stream)>>>(x->peers, x->nranks, x->rank, d_buf, count, mean_std, c);
+    return check_launch(who);
+}
+
+// The peer-memory form of config 5 has its own sequence: the exchange kernel also finalises mean / stddev, so only ONE tiny kernel
+// sits between the sums kernel and the normalise kernel.
 extern "C" int vacv_cuda_normalize_batch_global_p2p(void* xchg, const uint8_t* src, float* dst, int batch, int w, int h, int c,
                                                     int layout, unsigned long long* d_work, float* d_mean_std,
                                                     void* ev_sums_done, void* ev_stats_ready, void* stream) {
-    VACV_REQUIRE(xchg, "normalize_batch_global_p2p: null exchange");
-    return vacv_cuda_normalize_batch_global_cb(p2p_allreduce_cb, xchg, src, dst, batch, w, h, c, layout, d_work, d_mean_std,
-                                               ev_sums_done, ev_stats_ready, stream);
+    VACV_REQUIRE(xchg && src && dst && d_work && d_mean_std, "normalize_batch_global_p2p: null pointer");
+    VACV_REQUIRE(batch > 0 && w > 0 && h > 0 && c > 0 && c <= 7, "normalize_batch_global_p2p: bad size (1 <= c <= 7)");
+    cudaStream_t s = as_stream(stream);
+    batch_global_init_kernel<<<1, 32, 0, s>>>(d_work, c, (unsigned long long)batch * w * h);
+    int rc = check_launch("normalize_batch_global_p2p(init)");
+    if (rc != VACV_OK) return rc;
+    if ((rc = vacv_cuda_sums_u8(src, batch, w, h, c, layout, d_work, 0, stream)) != VACV_OK) return rc;
+    if (ev_sums_done) VACV_DCU(cudaEventRecord((cudaEvent_t)ev_sums_done, s), "normalize_batch_global_p2p");
+    if ((rc = launch_p2p(xchg, d_work, 2 * c + 1, d_mean_std, c, stream, "normalize_batch_global_p2p")) != VACV_OK) return rc;
+    if (ev_stats_ready) VACV_DCU(cudaEventRecord((cudaEvent_t)ev_stats_ready, s), "normalize_batch_global_p2p");
+    return vacv_cuda_normalize(src, dst, batch, w, h, c, VACV_INT8, layout, d_mean_std, d_mean_std + c, 0, stream);
 }
 
 extern "C" int vacv_cuda_p2p_create(void** xchg, int nranks, int rank, void* h_handle) {
@@ -203,11 +253,7 @@ extern "C" int vacv_cuda_p2p_destroy(void* xchg) {
 
 extern "C" int vacv_cuda_p2p_allreduce_u64(void* xchg, unsigned long long* d_buf, int count, void* stream) {
     VACV_REQUIRE(xchg && d_buf, "p2p_allreduce_u64: null pointer");
-    Xchg* x = static_cast<Xchg*>(xchg);
-    VACV_REQUIRE(x->connected || x->nranks == 1, "p2p_allreduce_u64: exchange not connected");
-    VACV_REQUIRE(count >= 1 && count < kXchgWords, "p2p_allreduce_u64: 1 <= count <= %d", kXchgWords - 1);
-    p2p_allreduce_u64_kernel<<<1, 32, 0, as_stream(stream)>>>(x->peers, x->nranks, x->rank, d_buf, count);
-    return check_launch("p2p_allreduce_u64");
+    return launch_p2p(xchg, d_buf, count, nullptr, 0, stream, "p2p_allreduce_u64");
 }
 
 extern "C" int vacv_cuda_p2p_status(void* xchg, int* timed_out) {

@@ -18,51 +18,124 @@ namespace vacv {
 // granular).  (A pure copy-engine variant -- cp.async.bulk.tensor load + store through a 4-stage shared-memory ring, one
 // thread per CTA -- was measured on 16-byte aligned crops: 0.150 ms against 0.134 ms for this kernel on 128 x 1080p ->
 // 1280x720, and TMA cannot shift bytes, so misaligned left edges would need this kernel anyway; it was dropped.)
+// Division by a launch constant without the 20-instruction runtime-divisor sequence: q = (n * mul) >> sh, exact for n < 2^31.
+struct FastDiv {
+    unsigned mul, sh, d;
+    void init(unsigned div) {
+        d = div;
+        unsigned l = 0;
+        while ((1ull << l) < div) ++l;
+        sh = 31 + l;
+        mul = (unsigned)(((1ull << sh) + div - 1) / div);
+    }
+    __device__ __forceinline__ unsigned div(unsigned n) const { return (unsigned)(((unsigned long long)n * mul) >> sh); }
+};
+
 struct CropGeom {
     int rows_per_frame;   // ch (HWC) or c*ch (CHW)
     int ch;               // rows per plane
     int RB;               // destination row bytes
     size_t src_frame, src_plane, src_pitch, src_ofs;   // bytes
+    FastDiv by_rows_per_frame, by_ch, by_segs;
+    int segs;             // warps per destination row (long rows are split so that no warp loops)
+    int cpr;              // kFlat: 16-byte chunks per destination row
+    FastDiv by_cpr;
 };
 
+constexpr int kCropU = 4;                      // 16-byte chunks per lane: all loads of a warp are issued before its first store
+constexpr int kCropSeg = 32 * kCropU;          // chunks per warp
+
+// One warp per (destination row, segment of 128 chunks).  Round 1's kernel gave a whole row to one warp, looping chunk by chunk
+// with one load pair in flight per lane and three runtime divisions per thread: fp32 rows (15 KB) were latency-bound and the
+// short CHW plane rows (1.3 KB) instruction-bound (bench_ops: 0.61 / 0.65 of the copy peak against 0.81 for u8 HWC rows).
 __global__ void __launch_bounds__(256) crop_rows_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
-                                                         CropGeom g, size_t total_rows) {
-    const size_t row = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (row >= total_rows) return;
+                                                         CropGeom g, unsigned total_warps) {
+    const unsigned wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (wid >= total_warps) return;
     const int lane = threadIdx.x & 31;
-    const size_t frame = row / g.rows_per_frame;
-    const int rr = (int)(row % g.rows_per_frame);
-    const int plane = rr / g.ch, y = rr % g.ch;
+    const unsigned row = g.segs == 1 ? wid : g.by_segs.div(wid);
+    const int seg = (int)(wid - row * g.segs);
+    const unsigned frame = g.by_rows_per_frame.div(row);
+    const unsigned rr = row - frame * g.rows_per_frame;
+    const unsigned plane = g.by_ch.div(rr), y = rr - plane * g.ch;
     const uint8_t* s = src + frame * g.src_frame + plane * g.src_plane + (size_t)y * g.src_pitch + g.src_ofs;
-    uint8_t* d = dst + row * (size_t)g.RB;
+    uint8_t* d = dst + (size_t)row * (size_t)g.RB;
 
     const int head = min((int)((16 - ((uintptr_t)d & 15)) & 15), g.RB);
-    if (lane < head) d[lane] = __ldg(s + lane);
+    if (seg == 0 && lane < head) d[lane] = __ldg(s + lane);
     const int nchunks = (g.RB - head) >> 4;
     const uint8_t* sb = s + head;
     uint8_t* db = d + head;
     // 16-byte granular: output chunk q = source bytes [sb + 16 q, +16) = words k .. k+4 (shifted by 8 (m & 3) bits) of the two
     // aligned 16-byte chunks around it; both come in as 128-bit loads (the second one is the next lane's first: an L1 hit).
-    // m is the same for every chunk of the row (and of every row: warp-uniform switch).
+    // m is the same for every chunk of the row.
     const int m = (int)((uintptr_t)sb & 15), k = m >> 2, sh = 8 * (m & 3);
     const uint4* sa = reinterpret_cast<const uint4*>(sb - m);
     // never read past the 16-byte chunk that holds the last source byte of the row (it may be the last of the allocation)
     const uint4* last = reinterpret_cast<const uint4*>((uintptr_t)(s + g.RB - 1) & ~(uintptr_t)15);
-    for (int q = lane; q < nchunks; q += 32) {
-        const uint4 a = __ldg(sa + q);
-        const uint4 b4 = (m != 0 && sa + q + 1 <= last) ? __ldg(sa + q + 1) : make_uint4(0u, 0u, 0u, 0u);
+    const int q0 = seg * kCropSeg + lane;
+    uint4 a[kCropU], b4[kCropU];
+#pragma unroll
+    for (int j = 0; j < kCropU; ++j) {
+        const int q = q0 + 32 * j;
+        a[j] = q < nchunks ? ld_stream16(sa + q) : make_uint4(0u, 0u, 0u, 0u);
+        b4[j] = (q < nchunks && m != 0 && sa + q + 1 <= last) ? __ldg(sa + q + 1) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int j = 0; j < kCropU; ++j) {
+        const int q = q0 + 32 * j;
+        if (q >= nchunks) break;
         uint32_t w0, w1, w2, w3, w4;
         switch (k) {
-            case 0: w0 = a.x; w1 = a.y; w2 = a.z; w3 = a.w; w4 = b4.x; break;
-            case 1: w0 = a.y; w1 = a.z; w2 = a.w; w3 = b4.x; w4 = b4.y; break;
-            case 2: w0 = a.z; w1 = a.w; w2 = b4.x; w3 = b4.y; w4 = b4.z; break;
-            default: w0 = a.w; w1 = b4.x; w2 = b4.y; w3 = b4.z; w4 = b4.w; break;
+            case 0: w0 = a[j].x; w1 = a[j].y; w2 = a[j].z; w3 = a[j].w; w4 = b4[j].x; break;
+            case 1: w0 = a[j].y; w1 = a[j].z; w2 = a[j].w; w3 = b4[j].x; w4 = b4[j].y; break;
+            case 2: w0 = a[j].z; w1 = a[j].w; w2 = b4[j].x; w3 = b4[j].y; w4 = b4[j].z; break;
+            default: w0 = a[j].w; w1 = b4[j].x; w2 = b4[j].y; w3 = b4[j].z; w4 = b4[j].w; break;
         }
         st_stream16(db + 16 * q, make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
                                             __funnelshift_r(w3, w4, sh)));
     }
     const int done = head + 16 * nchunks;
-    if (lane < g.RB - done) d[done + lane] = __ldg(s + done + lane);
+    if (seg == g.segs - 1 && lane < g.RB - done) d[done + lane] = __ldg(s + done + lane);
+}
+
+// Rows that are whole 16-byte chunks in an aligned destination (the usual case) need no head / tail handling, so the chunks of ALL
+// rows form one flat sequence and a warp simply takes the next 128 of them -- short rows (CHW plane rows: 80 chunks) no longer
+// leave lanes idle.  A lane's chunks may belong to different rows, so row, source pointer and byte phase are per lane.
+__global__ void __launch_bounds__(256) crop_flat_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, CropGeom g,
+                                                         unsigned total_chunks) {
+    const unsigned base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * kCropSeg + (threadIdx.x & 31);
+    uint4 a[kCropU], b4[kCropU];
+    int m[kCropU];
+#pragma unroll
+    for (int j = 0; j < kCropU; ++j) {
+        const unsigned item = base + 32 * j;
+        a[j] = b4[j] = make_uint4(0u, 0u, 0u, 0u);
+        m[j] = 0;
+        if (item >= total_chunks) continue;
+        const unsigned row = g.by_cpr.div(item), q = item - row * g.cpr;
+        const unsigned frame = g.by_rows_per_frame.div(row);
+        const unsigned rr = row - frame * g.rows_per_frame;
+        const unsigned plane = g.by_ch.div(rr), y = rr - plane * g.ch;
+        const uint8_t* s = src + frame * g.src_frame + plane * g.src_plane + (size_t)y * g.src_pitch + g.src_ofs;
+        m[j] = (int)((uintptr_t)s & 15);
+        const uint4* sa = reinterpret_cast<const uint4*>(s - m[j]) + q;
+        a[j] = ld_stream16(sa);
+        // the chunk behind holds bytes of this row unless this is the row's last chunk and the row ends inside `a`
+        if (m[j] != 0) b4[j] = __ldg(sa + 1);   // m != 0: the row's last byte lies in the chunk after `a`, never past it
+    }
+#pragma unroll
+    for (int j = 0; j < kCropU; ++j) {
+        const unsigned item = base + 32 * j;
+        if (item >= total_chunks) break;
+        const int k = m[j] >> 2, sh = 8 * (m[j] & 3);
+        const uint32_t w[8] = {a[j].x, a[j].y, a[j].z, a[j].w, b4[j].x, b4[j].y, b4[j].z, b4[j].w};
+        uint32_t v[5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) v[i] = k == 0 ? w[i] : k == 1 ? w[i + 1] : k == 2 ? w[i + 2] : w[i + 3];
+        st_stream16(dst + (size_t)item * 16, make_uint4(__funnelshift_r(v[0], v[1], sh), __funnelshift_r(v[1], v[2], sh),
+                                                        __funnelshift_r(v[2], v[3], sh), __funnelshift_r(v[3], v[4], sh)));
+    }
 }
 
 // =====================================================================================================
@@ -359,7 +432,20 @@ extern "C" int vacv_cuda_crop(const void* src, void* dst, int batch, int w, int 
     }
     g.src_frame = (size_t)w * h * c * es;
     const size_t rows = (size_t)batch * g.rows_per_frame;
-    crop_rows_kernel<<<ceil_div(rows * 32, 256), 256, 0, as_stream(stream)>>>((const uint8_t*)src, (uint8_t*)dst, g, rows);
+    g.segs = std::max(1, (g.RB / 16 + kCropSeg - 1) / kCropSeg);
+    VACV_REQUIRE(rows * g.segs < 0x7fffffffull / 32, "crop: too many rows for one launch");
+    g.by_rows_per_frame.init((unsigned)g.rows_per_frame);
+    g.by_ch.init((unsigned)g.ch);
+    g.by_segs.init((unsigned)g.segs);
+    if ((g.RB % 16) == 0 && ((uintptr_t)dst % 16) == 0 && rows * (size_t)(g.RB / 16) < 0x7fffffffull) {   // flat chunk sequence
+        g.cpr = g.RB / 16;
+        g.by_cpr.init((unsigned)g.cpr);
+        const unsigned chunks = (unsigned)(rows * g.cpr);
+        crop_flat_kernel<<<ceil_div(ceil_div(chunks, kCropSeg) * (size_t)32, 256), 256, 0, as_stream(stream)>>>((const uint8_t*)src, (uint8_t*)dst, g, chunks);
+        return check_launch("crop");
+    }
+    const unsigned warps = (unsigned)(rows * g.segs);
+    crop_rows_kernel<<<ceil_div((size_t)warps * 32, 256), 256, 0, as_stream(stream)>>>((const uint8_t*)src, (uint8_t*)dst, g, warps);
     return check_launch("crop");
 }
 
