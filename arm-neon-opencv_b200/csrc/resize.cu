@@ -457,8 +457,9 @@ static const void* resize_pipe_c1_kernel_for(int ncol) {
 // 1 = launched, 0 = shape not eligible, < 0 = error.
 // Shape-dependent part of a launch, cached per host thread (a stream of equally shaped calls pays it once).
 struct ResizePipePlan {
-    int w, h, wo, ho, device, out_mode, c, knob_gen; bool signed_char;      // key (out_mode: kRpOut*, c: 3 = BGR, 1 = planes)
+    int w, h, wo, ho, device, out_mode, c, knob_gen; bool signed_char, dst4;   // key (out_mode: kRpOut*, c: 3 = BGR, 1 = planes; dst4: 4-byte aligned dst)
     bool eligible; ResizePipeGeom g; const void* kern; int threads, per_sm, sms; size_t smem;
+    int quad_tx;   // > 0: the quad kernel for planes (resize_linear_u8c1_quad_kernel), threads per row group
 };
 
 static int build_resize_pipe_plan(ResizePipePlan& plan) {
@@ -491,6 +492,51 @@ static int build_resize_pipe_plan(ResizePipePlan& plan) {
     ResizePipeGeom& g = plan.g;
     g.w = w; g.h = h; g.wo = wo; g.ho = ho;
     g.src_image = row_bytes * h; g.dst_image = (size_t)wo * ho * c;
+    plan.quad_tx = 0;
+    if (c == 1 && (wo % 4) == 0 && plan.dst4 && knob(kKnobRpipeNcol) == 0) {   // planes: quads of four adjacent columns per thread
+        const int quads = wo / 4;
+        const int nq = (quads + kRpThreads - 1) / kRpThreads;                  // quads per thread: 1 (w_out <= 1536) or 2
+        if (nq <= 2) {
+            const int tx = (((quads + nq - 1) / nq) + 31) & ~31;
+            int best_TH = 0; size_t best_smem = 0;
+            for (int TH = kQuadMaxTH; TH >= 1; --TH) {
+                int rows = 0, tmp[2 * kQuadMaxTH];
+                for (int d0 = 0; d0 < ho; d0 += TH)
+                    rows = std::max(rows, band ? sy[std::min(d0 + TH, ho) - 1] + 1 - sy[d0] + 1 : tile_rows(sy.data(), cy.data(), d0, std::min(TH, ho - d0), tmp, nullptr));
+                const size_t stage = ((size_t)rows * row_bytes + 16 + 127) & ~(size_t)127;
+                const int table_bytes = ((3 * ho + (band ? 0 : ((ho + TH - 1) / TH) * (1 + 2 * kQuadMaxTH))) * (int)sizeof(int) + 127) & ~127;
+                const size_t smem = table_bytes + kQuadStages * stage;
+                if (smem + 64 <= 113 * 1024 || (TH == 1 && smem + 64 <= 226 * 1024)) { best_TH = TH; best_smem = smem; g.stage_bytes = (int)stage; g.table_bytes = table_bytes; break; }
+            }
+            if (best_TH) {
+                g.TH = best_TH;
+                g.tiles_per_frame = (ho + best_TH - 1) / best_TH;
+                g.total_tiles = 0;
+                // row groups: as many as fit the CTA, each with at least two consecutive output rows of the tile
+                const int ry = std::max(1, std::min(kRpThreads / tx, best_TH / 2));
+                const void* kern = nq == 1 ? (band ? (signed_char ? (const void*)resize_linear_u8c1_quad_kernel<true, true, 1> : (const void*)resize_linear_u8c1_quad_kernel<false, true, 1>)
+                                                   : (signed_char ? (const void*)resize_linear_u8c1_quad_kernel<true, false, 1> : (const void*)resize_linear_u8c1_quad_kernel<false, false, 1>))
+                                           : (band ? (signed_char ? (const void*)resize_linear_u8c1_quad_kernel<true, true, 2> : (const void*)resize_linear_u8c1_quad_kernel<false, true, 2>)
+                                                   : (signed_char ? (const void*)resize_linear_u8c1_quad_kernel<true, false, 2> : (const void*)resize_linear_u8c1_quad_kernel<false, false, 2>));
+                int optin = 0, per_sm = 0;
+                cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, plan.device);
+                cudaFuncAttributes fa;
+                cudaError_t e = cudaFuncGetAttributes(&fa, kern);
+                if (e != cudaSuccess) return set_error(VACV_ERR_CUDA, "resize: %s", cudaGetErrorString(e));
+                if ((size_t)(optin - (int)fa.sharedSizeBytes) >= best_smem) {
+                    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+                    if (e != cudaSuccess) return set_error(VACV_ERR_CUDA, "resize: %s", cudaGetErrorString(e));
+                    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, tx * ry, best_smem);
+                    if (e == cudaSuccess && per_sm >= 1) {
+                        plan.kern = kern; plan.threads = tx * ry; plan.per_sm = per_sm; plan.sms = sm_count(plan.device); plan.smem = best_smem;
+                        plan.quad_tx = tx;
+                        plan.eligible = true;
+                        return 0;
+                    }
+                }
+            }
+        }
+    }
     int ncol = (wo + kRpThreads - 1) / kRpThreads;
     if (ncol < 2) ncol = 2;
     if (const int v = knob(kKnobRpipeNcol)) { if (v >= 1 && v <= kRpMaxCols && (wo + v - 1) / v <= kRpThreads) ncol = v; }   // tuning knob
@@ -554,13 +600,14 @@ int vacv::try_launch_resize_pipe_u8c3(const uint8_t* src, void* dst, int images,
     if (((uintptr_t)src & 15) != 0) return 0;
     static thread_local PlanCache<ResizePipePlan, 8> cache;
     const int dev = current_device(), gen = knob_generation();
+    const bool dst4 = ((uintptr_t)dst & 3) == 0;
     ResizePipePlan* pp = cache.find([&](const ResizePipePlan& p) {
         return p.w == w && p.h == h && p.wo == wo && p.ho == ho && p.signed_char == signed_char && p.device == dev && p.out_mode == out_mode &&
-               p.c == c && p.knob_gen == gen;
+               p.c == c && p.knob_gen == gen && p.dst4 == dst4;
     });
     if (!pp) {
         pp = cache.claim();
-        pp->w = w; pp->h = h; pp->wo = wo; pp->ho = ho; pp->signed_char = signed_char; pp->device = dev; pp->out_mode = out_mode; pp->c = c; pp->knob_gen = gen;
+        pp->w = w; pp->h = h; pp->wo = wo; pp->ho = ho; pp->signed_char = signed_char; pp->device = dev; pp->out_mode = out_mode; pp->c = c; pp->knob_gen = gen; pp->dst4 = dst4;
         const int rc = build_resize_pipe_plan(*pp);
         if (rc < 0) return rc;
         cache.commit();
@@ -573,8 +620,10 @@ int vacv::try_launch_resize_pipe_u8c3(const uint8_t* src, void* dst, int images,
     if (total > 0x7fffffffLL - 4096) return 0;
     g.total_tiles = (int)total;
     const int grid = (int)std::min<long long>(total, (long long)plan.sms * plan.per_sm);
+    int tx = plan.quad_tx;
     void* args[] = {(void*)&src, (void*)&dst, (void*)&g, (void*)&mean, (void*)&stddev};
-    const cudaError_t e = cudaLaunchKernel(plan.kern, dim3(grid), dim3(plan.threads), args, plan.smem, s);
+    void* quad_args[] = {(void*)&src, (void*)&dst, (void*)&g, (void*)&tx};
+    const cudaError_t e = cudaLaunchKernel(plan.kern, dim3(grid), dim3(plan.threads), tx > 0 ? quad_args : args, plan.smem, s);
     if (e != cudaSuccess) return set_error(VACV_ERR_CUDA, "resize: %s", cudaGetErrorString(e));
     return 1;
 }

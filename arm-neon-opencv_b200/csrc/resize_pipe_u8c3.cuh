@@ -122,27 +122,28 @@ resize_linear_u8c3_pipe_kernel(const uint8_t* __restrict__ src, void* __restrict
         sh[j] = (int)(((unsigned)sx * 3u) & 3u) * 8;
     }
 
-    auto issue = [&](int tile, int b) {   // one thread: one bulk copy per run of consecutive source rows
+    // Copy issue by the whole first warp: lane 0 arms the barrier with the tile's byte count; band staging is ONE copy (lane 0),
+    // row-list staging one copy per listed row, lane i issuing the i-th (the rows are not consecutive in memory, and one thread
+    // issuing them one after the other was slower than the tile's arithmetic).
+    auto issue = [&](int tile, int b) {   // called by every lane of warp 0
         const int frame = tile / g.tiles_per_frame;
         if (kBand) {
-            const int dy0 = (tile - frame * g.tiles_per_frame) * g.TH, th = min(g.TH, g.ho - dy0);
-            const int y_first = s_sy[dy0], y_last = s_sy[dy0 + th - 1] + 1;
-            const uint32_t bytes = (uint32_t)(y_last - y_first + 1) * row_bytes;
-            mbar_expect_tx(&full_bar[b], bytes);
-            bulk_g2s(stages + (size_t)b * g.stage_bytes, src + (size_t)frame * g.src_image + (size_t)y_first * row_bytes, bytes, &full_bar[b]);
+            if (lane == 0) {
+                const int dy0 = (tile - frame * g.tiles_per_frame) * g.TH, th = min(g.TH, g.ho - dy0);
+                const int y_first = s_sy[dy0], y_last = s_sy[dy0 + th - 1] + 1;
+                const uint32_t bytes = (uint32_t)(y_last - y_first + 1) * row_bytes;
+                mbar_expect_tx(&full_bar[b], bytes);
+                bulk_g2s(stages + (size_t)b * g.stage_bytes, src + (size_t)frame * g.src_image + (size_t)y_first * row_bytes, bytes, &full_bar[b]);
+            }
             return;
         }
         const int* rows = s_tile + (tile - frame * g.tiles_per_frame) * (1 + 2 * kRpMaxTH) + 1;
-        const int n = rows[-1];
-        mbar_expect_tx(&full_bar[b], (uint32_t)n * row_bytes);
-        const uint8_t* f = src + (size_t)frame * g.src_image;
-        uint8_t* st = stages + (size_t)b * g.stage_bytes;
-        for (int i = 0; i < n;) {
-            int j = i + 1;
-            while (j < n && rows[j] == rows[j - 1] + 1) ++j;
-            bulk_g2s(st + (size_t)i * row_bytes, f + (size_t)rows[i] * row_bytes, (uint32_t)(j - i) * row_bytes, &full_bar[b]);
-            i = j;
-        }
+        const int n = rows[-1];   // <= 2 * kRpMaxTH = 16
+        if (lane == 0) mbar_expect_tx(&full_bar[b], (uint32_t)n * row_bytes);
+        __syncwarp();
+        if (lane < n)
+            bulk_g2s(stages + (size_t)b * g.stage_bytes + (size_t)lane * row_bytes, src + (size_t)frame * g.src_image + (size_t)rows[lane] * row_bytes,
+                     row_bytes, &full_bar[b]);
     };
     // horizontal sums of one source row for this thread's columns
     auto hrow = [&](uint32_t rowaddr, int (&H)[NCOL][3]) {
@@ -159,14 +160,14 @@ resize_linear_u8c3_pipe_kernel(const uint8_t* __restrict__ src, void* __restrict
     };
 
     int tile = blockIdx.x;
-    if (tid == 0 && tile < g.total_tiles) issue(tile, 0);
+    if (tid < 32 && tile < g.total_tiles) issue(tile, 0);
     __syncthreads();
     const int n_last = g.wo - (g.wo & ~31);   // valid pixels in the last, partial warp of a row (0: none partial)
 
     for (int it = 0; tile < g.total_tiles; tile += gridDim.x, ++it) {
         const int b = it & 1;
         const int next = tile + gridDim.x;
-        if (tid == 0 && next < g.total_tiles) issue(next, b ^ 1);   // stage b^1 was released by the sync below
+        if (tid < 32 && next < g.total_tiles) issue(next, b ^ 1);   // stage b^1 was released by the sync below
         mbar_wait(&full_bar[b], (it >> 1) & 1);
         const int frame = tile / g.tiles_per_frame, dy0 = (tile - frame * g.tiles_per_frame) * g.TH;
         const int th = min(g.TH, g.ho - dy0);

@@ -238,6 +238,33 @@ def test_resize_linear_u8_planar_flags(vacv, oracle, sz):
         assert_same(got, want)
 
 
+@pytest.mark.parametrize("signed", [False, True])
+@pytest.mark.parametrize("sz", [((1920, 1080), (640, 360)), ((1920, 1080), (1280, 720)), ((3840, 2160), (1920, 1080)), ((640, 360), (1536, 700)),
+                                ((1280, 720), (1276, 361)), ((960, 540), (320, 180)), ((320, 200), (64, 40)), ((1920, 1080), (384, 360)),
+                                ((640, 480), (632, 479)), ((3840, 1080), (3072, 1000)), ((1920, 1080), (638, 360))])
+def test_resize_linear_u8_planes_default_path(vacv, oracle, sz, signed):
+    """CHW tensors (resized plane by plane, resize.cpp:73-87) on the default dispatch: the persistent TMA pipeline for planes --
+    quads of four adjacent columns per thread with packed 32-bit stores where w_out % 4 == 0 (one and two quads per thread, one to
+    several row groups per CTA, band and row-list staging), the byte-per-lane kernel otherwise -- and the gather kernel for the
+    rest.  Batch of 2 frames x 3 planes; both char signedness rules."""
+    (w, h), (wo, ho) = sz
+    src = u8(27, 2, 3, h, w)
+    flags = vacv.FLAG_SIGNED_CHAR if signed else 0
+    got = host(vacv.resize(dev(src), NCHW, wo, ho, vacv.INTER_LINEAR, flags))
+    for i in range(2):
+        assert_same(got[i], oracle.resize_linear(src[i], w, h, 3, NCHW, wo, ho, signed_char=int(signed)))
+    # a destination that is not 4-byte aligned must take the byte-per-lane path and still be right
+    if wo % 4 == 0 and not signed:
+        import torch
+        buf = torch.empty(2 * 3 * wo * ho + 8, dtype=torch.uint8, device="cuda")
+        dst = buf[1:1 + 2 * 3 * wo * ho]
+        d = dev(src)
+        rc = vacv.lib.vacv_cuda_resize(d.data_ptr(), dst.data_ptr(), 2, w, h, 3, vacv.INT8, NCHW, wo, ho, vacv.INTER_LINEAR, 0,
+                                       torch.cuda.current_stream().cuda_stream)
+        assert rc == 0
+        assert_same(dst.cpu().numpy().reshape(2, 3, ho, wo), got)
+
+
 @pytest.mark.parametrize("path", PATHS)
 @pytest.mark.parametrize("layout", [NHWC, NCHW])
 @pytest.mark.parametrize("sz", LIN_SIZES[:5] + [((2560, 1440), (320, 180))])
