@@ -1,0 +1,361 @@
+// u8 bicubic resize of interleaved BGR at RATIONAL horizontal scales (config 4: 2560 -> 1920 = 4 source pixels per 3 output
+// pixels), third generation of the column walker (resize_cubic3_walkn.cuh).
+//
+// Reference arithmetic: OpenCV 2.4.13 cv::resize(CV_8UC3, INTER_CUBIC) -- the reference's only u8 cubic path
+// (src/cv/resize.cpp:33-36) -- bit for bit, exactly as in the other walkers.
+//
+// What is different, and why.  ncu of resize_cubic3_walkn_kernel<4> (profiles/r2_cubic_walkn_v2_ncu_raw.txt): 65 thread-instructions
+// per output pixel, no pipe above 60 %, issue slots the limiter; more resident warps do not help (register caps of 112 / 104 gave
+// 1.5 %).  Of the 65, the horizontal pass of a column and source row costs 4 LDS + 1 IMAD (tap words at a lane-dependent
+// address), 3 SHF (lane-dependent byte alignment), 6 PRMT (de-interleave) and 6 IDP -- because a thread's columns lie 32 apart,
+// every column fetches and aligns its own 12 bytes.  When w_in : w_out = P : Q the tap pattern repeats every Q output columns
+// and P source pixels, so a thread that owns KP whole periods of ADJACENT columns
+//   * reads its P*KP + 3 source pixels ONCE per source row (8 words for 6 columns instead of 24) -- at a lane stride of 3*P*KP
+//     bytes, which the launcher requires to be a multiple of 4, so the byte alignment inside the words is the same in every lane;
+//   * de-interleaves them once into per-channel words and cuts each column's four taps out with PRMTs whose selectors are
+//     COMPILE-TIME constants (no funnel shifts, no per-column address arithmetic);
+//   * source rows arrive by one cp.async.bulk per warp and row (one lane, mbarrier completion) instead of two LDGSTS per lane;
+//   * NV = 3 * Q * KP output bytes per thread and row are packed in registers and staged as 32-bit words.
+// The 11-bit coefficients stay per-lane registers computed with the reference's own float arithmetic (the rounding of the source
+// coordinate to fp32 makes them NOT exactly periodic), and taps OpenCV clamps onto an edge pixel are folded into the in-range
+// positions; the launcher verifies on the host that every column's taps sit where the compile-time pattern expects them and
+// falls back to the generic walker otherwise.
+#pragma once
+#include <type_traits>
+
+#include "resize_cubic3_walk.cuh"
+
+namespace vacv {
+
+constexpr int kPdRing = 8, kPdAhead = 6;     // ring slots per warp / rows in flight ahead of the one being filtered
+constexpr int kPdStageRows = 2;      // staging buffers per warp (one output row each)
+
+struct PeriodGeom {
+    int w, h, wo, ho;
+    int warp_strips, cta_strips, segs, rows_per_seg;
+    int ring_pitch;                    // bytes per ring row of a warp (multiple of 16)
+    double scale_x, scale_y;
+    size_t src_image, dst_image;       // bytes between images
+    f32x2 one2, negzero2, magic2, negmagic2;   // (1,1), (-0,-0), (1.5*2^23)x2, (-1.5*2^23)x2 -- opaque to ptxas on purpose
+};
+
+namespace pd {
+
+template <int N, int I = 0, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<N, I + 1>(f);
+    }
+}
+__host__ __device__ constexpr int floordiv(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
+// window index of the first tap (source pixel sx - 1) of a thread's column c; the thread's window starts at source pixel P*KP*thread - 1
+__host__ __device__ constexpr int tap0(int P, int Q, int c) { return floordiv((2 * c + 1) * P - Q, 2 * Q); }
+
+// bytes G0 <= G1 <= G2 <= G3 (indices into the byte string of W[]) -> one word, with 0..3 PRMTs whose selectors are immediates
+template <int G0, int G1, int G2, int G3, int N>
+__device__ __forceinline__ uint32_t gather4(const uint32_t (&W)[N]) {
+    constexpr int w0 = G0 >> 2, w1 = G1 >> 2, w2 = G2 >> 2, w3 = G3 >> 2;
+    static_assert(w0 <= w1 && w1 <= w2 && w2 <= w3 && w3 < N, "byte indices must ascend inside W");
+    constexpr int d0 = w0;
+    constexpr int d1 = w1 != d0 ? w1 : w2 != d0 ? w2 : w3 != d0 ? w3 : d0;
+    constexpr int d2 = (w2 != d0 && w2 != d1) ? w2 : (w3 != d0 && w3 != d1) ? w3 : -1;
+    constexpr int d3 = (d2 >= 0 && w3 != d0 && w3 != d1 && w3 != d2) ? w3 : -1;
+    constexpr auto nib1 = [](int G) constexpr { return (G >> 2) == d0 ? (G & 3) : (G >> 2) == d1 ? 4 + (G & 3) : 0; };
+    constexpr unsigned sel1 = nib1(G0) | nib1(G1) << 4 | nib1(G2) << 8 | nib1(G3) << 12;
+    uint32_t r;
+    if constexpr (d1 == d0 && sel1 == 0x3210u) r = W[d0];
+    else r = __byte_perm(W[d0], W[d1], sel1);
+    if constexpr (d2 >= 0) {
+        constexpr auto nib2 = [](int G, int j) constexpr { return (G >> 2) == d2 ? 4 + (G & 3) : j; };
+        constexpr unsigned sel2 = nib2(G0, 0) | nib2(G1, 1) << 4 | nib2(G2, 2) << 8 | nib2(G3, 3) << 12;
+        r = __byte_perm(r, W[d2], sel2);
+    }
+    if constexpr (d3 >= 0) {
+        constexpr auto nib3 = [](int G, int j) constexpr { return (G >> 2) == d3 ? 4 + (G & 3) : j; };
+        constexpr unsigned sel3 = nib3(G0, 0) | nib3(G1, 1) << 4 | nib3(G2, 2) << 8 | nib3(G3, 3) << 12;
+        r = __byte_perm(r, W[d3], sel3);
+    }
+    return r;
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+}  // namespace pd
+
+// Geometry shared by the kernel and the launcher (host checks, shared-memory sizes).
+template <int P, int Q, int KP>
+struct PeriodShape {
+    static constexpr int NCOL = Q * KP;                                  // adjacent output columns per thread
+    static constexpr int NPX = pd::tap0(P, Q, NCOL - 1) + 4;              // source pixels in a thread's window
+    static constexpr int LS = 3 * P * KP;                                // bytes between the windows of neighbouring lanes
+    static constexpr int M0 = 1;                                         // the window starts at byte LS*thread - 3: byte 1 of an aligned word
+    static constexpr int NW = (M0 + 3 * NPX + 3) / 4;                    // window words
+    static constexpr int NPW = (NPX + 3) / 4;                            // words per de-interleaved channel
+    static constexpr int NV = 3 * NCOL;                                  // output bytes per thread and row
+    static constexpr int NP = NV / 2;                                    // packed fp32 pairs
+    static constexpr int kWarpRow = 32 * NV;                             // bytes one warp produces per output row
+    static constexpr int kWarpSpan = 32 * LS;                            // source bytes between the windows of neighbouring warps
+    static constexpr int kLaneOff = 12;                                  // ring offset of lane 0's window word 0 (the ring row starts 16 bytes early)
+    static constexpr int kNeed = (LS * 31 + kLaneOff + 4 * NW + 15) & ~15;   // ring bytes of one source row
+    static_assert(LS % 4 == 0, "lane stride must keep the byte alignment lane-invariant");
+    static_assert(NV % 4 == 2 || NV % 4 == 0, "output bytes per thread must be even");
+    static_assert((32 * NV) % 16 == 0 && (32 * LS) % 16 == 0, "warp spans must stay 16-byte aligned");
+};
+
+template <int P, int Q, int KP, bool kDown, int MAXREG>
+__global__ void __maxnreg__(MAXREG) resize_cubic3_period_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, PeriodGeom g) {
+    using S = PeriodShape<P, Q, KP>;
+    constexpr int NCOL = S::NCOL, NPX = S::NPX, LS = S::LS, M0 = S::M0, NW = S::NW, NPW = S::NPW, NV = S::NV, NP = S::NP;
+    constexpr int kWarpRow = S::kWarpRow;
+    extern __shared__ __align__(16) uint8_t smem[];
+    Walk2Row* rows = reinterpret_cast<Walk2Row*>(smem);                                   // [rows_per_seg + 1]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int rows_bytes = (g.rows_per_seg + 1) * (int)sizeof(Walk2Row);
+    uint8_t* stage = smem + rows_bytes + warp * (kPdStageRows * kWarpRow);
+    uint8_t* ring = smem + rows_bytes + nwarps * (kPdStageRows * kWarpRow) + warp * (kPdRing * g.ring_pitch);
+    const uint32_t bars = (uint32_t)__cvta_generic_to_shared(smem + rows_bytes + nwarps * (kPdStageRows * kWarpRow + kPdRing * g.ring_pitch)) + warp * (kPdRing * 8);
+    const int cta_strip = blockIdx.x % g.cta_strips, seg = blockIdx.x / g.cta_strips;
+    const int wstrip = cta_strip * nwarps + warp;
+    const int pt = wstrip * 32 + lane;                 // this thread's index along x: columns NCOL * pt ..
+    const int dy_begin = seg * g.rows_per_seg, nrows = min(g.ho, dy_begin + g.rows_per_seg) - dy_begin;
+    const uint8_t* img = src + blockIdx.y * g.src_image;
+    uint8_t* out_img = dst + blockIdx.y * g.dst_image;
+    const unsigned row_bytes = (unsigned)g.w * 3, out_row_bytes = (unsigned)g.wo * 3;
+
+    // per output row: vertical weights, and the walk step n (source row t_first + n) that completes it
+    int t_first;
+    {
+        int s, q[4];
+        cubic_cv_coord_scaled(dy_begin, g.h, g.scale_y, false, s, q);
+        t_first = s - 1;
+    }
+    for (int r = tid; r <= nrows; r += blockDim.x) {   // entry nrows = sentinel that never matches
+        Walk2Row e;
+        int s, q[4];
+        cubic_cv_coord_scaled(dy_begin + min(r, nrows - 1), g.h, g.scale_y, false, s, q);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) e.b[2 * j] = e.b[2 * j + 1] = (float)q[j] * (1.f / (2048 * 2048));
+        e.last = r < nrows ? s + 2 - t_first : INT_MAX;
+        e.pad[0] = e.pad[1] = e.pad[2] = 0;
+        rows[r] = e;
+    }
+    if (lane == 0) {
+        for (int i = 0; i < kPdRing; ++i) pd::mbar_init(bars + 8 * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (wstrip >= g.warp_strips) return;               // padding warp of the last CTA strip (no CTA barrier below)
+
+    // x taps: column c's four taps sit at window pixels tap0(c) .. tap0(c) + 3 (verified by the launcher); taps OpenCV clamps onto an
+    // edge pixel have their integer coefficients added up at that pixel's position (identical sums)
+    const bool owner = NCOL * pt < g.wo;               // threads past the last column compute on zero coefficients and store nothing
+    int c01[NCOL], c23[NCOL];
+    pd::static_for<NCOL>([&](auto ic) {
+        constexpr int c = decltype(ic)::value;
+        int s, q[4], xc[4] = {0, 0, 0, 0};
+        cubic_cv_coord_scaled(min(NCOL * pt + c, g.wo - 1), g.w, g.scale_x, true, s, q);
+        const int base = P * KP * pt - 1 + pd::tap0(P, Q, c);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int pos = min(max(s - 1 + j, 0), g.w - 1) - base;   // 0..3
+#pragma unroll
+            for (int t = 0; t < 4; ++t) xc[t] += (owner && pos == t) ? q[j] : 0;
+        }
+        c01[c] = (xc[0] & 0xffff) | (xc[1] << 16);
+        c23[c] = (xc[2] & 0xffff) | (xc[3] << 16);
+    });
+
+    // the warp's bytes of a source row: [span0, span0 + kNeed) clipped to the row; ring byte r <-> source byte span0 + r.
+    // Everything the copy issue needs is warp-uniform; the shuffles tell the compiler so (uniform registers, one UBLKCP per warp).
+    constexpr unsigned kPitch = S::kNeed;              // bytes per ring slot
+    const int span0 = S::kWarpSpan * wstrip - 16;
+    const int lo = max(span0, 0), hi = min(span0 + S::kNeed, (int)row_bytes);
+    const uint32_t copy_bytes = __shfl_sync(0xffffffffu, (uint32_t)(hi - lo), 0);
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+    const uint32_t ring_dst = __shfl_sync(0xffffffffu, ring_s + (uint32_t)(lo - span0), 0);
+    const uint32_t ubars = __shfl_sync(0xffffffffu, bars, 0);
+    const uint32_t win_s = ring_s + (uint32_t)(LS * lane + S::kLaneOff);   // this lane's window word 0 in ring slot 0
+    const uint32_t rows_s = (uint32_t)__cvta_generic_to_shared(rows);
+    const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
+    const f32x2 one2 = g.one2, negzero2 = g.negzero2, magic2 = g.magic2, negmagic2 = g.negmagic2;
+
+    uint32_t entry = rows_s;                           // shared address of the next output row's table entry
+    int next_last;
+    asm volatile("ld.shared.s32 %0, [%1+32];" : "=r"(next_last) : "r"(entry));
+    int n_stop;                                        // last walk step = the last output row's last tap row
+    asm volatile("ld.shared.s32 %0, [%1+32];" : "=r"(n_stop) : "r"(rows_s + (nrows - 1) * (int)sizeof(Walk2Row)));
+    n_stop = __shfl_sync(0xffffffffu, n_stop, 0);
+
+    // ---- source rows: walk step n (row t_first + n, clamped to the image like OpenCV's tap rows) -> ring slot n & 7, one bulk copy
+    //      per warp and row, kPdAhead steps ahead
+    int t_pre = t_first;                               // (unclamped) row of the next copy; its walk step is n_pre
+    int n_pre = 0;
+    const uint8_t* g_pre = img + lo + (size_t)(unsigned)min(max(t_first, 0), g.h - 1) * row_bytes;
+    auto issue = [&](const uint32_t slot) {            // warp-uniform; slot is a literal at every call site
+        if (n_pre <= n_stop) {
+            if (lane == 0) {
+                pd::mbar_expect_tx(ubars + 8 * slot, copy_bytes);
+                pd::bulk_g2s(ring_dst + slot * kPitch, g_pre, copy_bytes, ubars + 8 * slot);
+            }
+            g_pre += (unsigned)t_pre < (unsigned)(g.h - 1) ? row_bytes : 0u;   // rows below 0 / beyond h-1 repeat the edge row
+            ++t_pre;
+        }
+        ++n_pre;
+    };
+    // horizontal pass of the walk step in ring slot `slot`: (value 2i, value 2i+1) of the thread's NV = 3 * NCOL output bytes, exact fp32
+    auto hfilter = [&](const uint32_t slot, uint32_t parity, f32x2 (&H)[NP]) {
+        pd::mbar_wait(ubars + 8 * slot, parity);
+        const uint32_t p = win_s + slot * kPitch;
+        uint32_t W[NW];
+        if constexpr (LS % 8 == 0 && S::kLaneOff % 8 == 4) {   // word 0 alone, then 8-byte aligned pairs
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(W[0]) : "r"(p));
+#pragma unroll
+            for (int i = 1; i + 1 < NW; i += 2) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(W[i]), "=r"(W[i + 1]) : "r"(p + 4 * i));
+            if constexpr ((NW & 1) == 0) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(W[NW - 1]) : "r"(p + 4 * (NW - 1)));
+        } else {
+#pragma unroll
+            for (int i = 0; i < NW; ++i) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(W[i]) : "r"(p + 4 * i));
+        }
+        // de-interleave: channel k, pixels 4i .. 4i+3 of the window (pixels past the window repeat the last one: never used)
+        uint32_t pl[3][NPW];
+        pd::static_for<3>([&](auto ik) {
+            constexpr int k = decltype(ik)::value;
+            pd::static_for<NPW>([&](auto ii) {
+                constexpr int i = decltype(ii)::value;
+                constexpr int j0 = 4 * i, j1 = 4 * i + 1 < NPX ? 4 * i + 1 : NPX - 1, j2 = 4 * i + 2 < NPX ? 4 * i + 2 : NPX - 1, j3 = 4 * i + 3 < NPX ? 4 * i + 3 : NPX - 1;
+                pl[k][i] = pd::gather4<M0 + 3 * j0 + k, M0 + 3 * j1 + k, M0 + 3 * j2 + k, M0 + 3 * j3 + k>(W);
+            });
+        });
+        int hv[NV];
+        pd::static_for<NCOL>([&](auto ic) {
+            constexpr int c = decltype(ic)::value;
+            constexpr int t0 = pd::tap0(P, Q, c);
+            pd::static_for<3>([&](auto ik) {
+                constexpr int k = decltype(ik)::value;
+                const uint32_t taps = pd::gather4<t0, t0 + 1, t0 + 2, t0 + 3>(pl[k]);
+                // sum(tap * coef) on top of the bit pattern of 1.5*2^23 (exact int -> float for |H| < 2^22 after subtracting it)
+                hv[3 * c + k] = dp2a_hi_su(c23[c], taps, dp2a_lo_su(c01[c], taps, 0x4B400000));
+            });
+        });
+#pragma unroll
+        for (int i = 0; i < NP; ++i) H[i] = fma2(pack2i(hv[2 * i], hv[2 * i + 1]), one2, negmagic2);
+    };
+
+    // ---- output: every row is staged in one of two kWarpRow-byte buffers of the warp and leaves at once as lane-contiguous 16-byte
+    //      chunks (one warp-wide store of 512 bytes + the remainder).  A thread's NV bytes start at NV * lane: word aligned in even
+    //      lanes, 2 bytes off in odd lanes (NV % 4 == 2) -- odd lanes store their first two bytes as a half word and the rest shifted by
+    //      16 bits, so that everything else is a 32-bit store.  Threads past the last column stage zeros that are never flushed.
+    constexpr bool kHalf = NV % 4 == 2;
+    constexpr int NWD = NV / 4;                        // full words per thread and row
+    constexpr int kChunks = kWarpRow / 16;             // 16-byte chunks per row of the warp
+    static_assert(kChunks > 32 && kChunks <= 64, "flush: one or two chunks per lane");
+    const bool odd = kHalf && (lane & 1);
+    const int sh16 = odd ? 16 : 0;
+    uint32_t st_w = stage_s + NV * lane + (odd ? 2 : 0);            // the 32-bit stores
+    uint32_t st_h = stage_s + NV * lane + (odd ? 0 : 4 * NWD);      // the 16-bit store
+    uint32_t st_f = stage_s + 16 * lane;                            // this lane's first chunk of the staged row
+    int st_d = kWarpRow;                                            // distance to the other staging buffer
+    const int valid_chunks = min(kWarpRow, (int)out_row_bytes - wstrip * kWarpRow) >> 4;        // chunks of a warp row inside the image row
+    const bool f0 = lane < valid_chunks, f1 = lane + 32 < min(valid_chunks, kChunks);
+    uint8_t* gflush = out_img + (size_t)dy_begin * out_row_bytes + (size_t)wstrip * kWarpRow + 16 * lane;   // this lane's first chunk in global memory
+
+    // vertical pass + store of the NV output bytes from the window (h0 = oldest row)
+    auto emit = [&](const f32x2 (&h0)[NP], const f32x2 (&h1)[NP], const f32x2 (&h2)[NP], const f32x2 (&h3)[NP]) {
+        f32x2 w0, w1, w2, w3;
+        asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "r"(entry));
+        asm volatile("ld.shared.v2.b64 {%0, %1}, [%2+16];" : "=l"(w2), "=l"(w3) : "r"(entry));
+        uint32_t pr[NP + 1];                           // two output bytes each (low half)
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {   // OpenCV's SSE2 body: mulps, addps (one rounding each), cvtps2dq (half-even), packs, packus
+            f32x2 f = fma2(h0[i], w0, negzero2);
+            f = fma2(f, one2, fma2(h1[i], w1, negzero2));
+            f = fma2(f, one2, fma2(h2[i], w2, negzero2));
+            f = fma2(f, one2, fma2(h3[i], w3, negzero2));
+            // |f| < 2^22: adding 1.5*2^23 rounds half-to-even at integer granularity; subtracting its bit pattern and clamping
+            // to [0,255] is one DPX op per value (the intermediate s16 saturation of packs cannot change the result)
+            f = fma2(f, one2, magic2);
+            int lo, hi;
+            unpack2i(f, lo, hi);
+            pr[i] = __byte_perm(__viaddmin_s32_relu(lo, -0x4B400000, 255), __viaddmin_s32_relu(hi, -0x4B400000, 255), 0x0040);
+        }
+        pr[NP] = 0;
+        uint32_t A[NWD + 1];
+#pragma unroll
+        for (int j = 0; j < NWD; ++j) A[j] = __byte_perm(pr[2 * j], pr[2 * j + 1], 0x5410);
+        A[NWD] = pr[2 * NWD];                          // kHalf: the last two bytes
+#pragma unroll
+        for (int j = 0; j < NWD; ++j) {
+            const uint32_t x = kHalf ? __funnelshift_r(A[j], A[j + 1], sh16) : A[j];
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(st_w + 4 * j), "r"(x) : "memory");
+        }
+        if (kHalf) {
+            const uint32_t x = odd ? A[0] : A[NWD];
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(st_h), "h"((unsigned short)x) : "memory");
+        }
+        __syncwarp();                                  // the row is staged; the other buffer's readers passed this point a row ago
+        if (f0) {
+            uint4 v;
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(st_f));
+            st_stream16(gflush, v);
+        }
+        if (f1) {
+            uint4 v;
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+512];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(st_f));
+            st_stream16(gflush + 512, v);
+        }
+        gflush += out_row_bytes;
+        st_w += st_d; st_h += st_d; st_f += st_d;                 // the other buffer
+        st_d = -st_d;
+        entry += (int)sizeof(Walk2Row);
+        asm volatile("ld.shared.s32 %0, [%1+32];" : "=r"(next_last) : "r"(entry));   // sentinel INT_MAX after the last row
+    };
+
+    // ---- the walk: step n -> ring slot n & 7 and window slot n & 3 (compile-time inside the 8x unrolled body); an output row is emitted
+    //      as soon as its last tap row has been filtered.  The first output row completes at step 3.
+    f32x2 H[4][NP];
+    const uint32_t entry_end = rows_s + nrows * (int)sizeof(Walk2Row);
+#define VACV_PD_IC(k) (uint32_t)(k)
+    issue(VACV_PD_IC(0)); issue(VACV_PD_IC(1)); issue(VACV_PD_IC(2)); issue(VACV_PD_IC(3)); issue(VACV_PD_IC(4)); issue(VACV_PD_IC(5));
+    static_assert(kPdAhead == 6 && kPdRing == 8, "the unrolled walk below assumes 6 rows ahead in an 8-slot ring");
+    int n = 0;
+    uint32_t parity = 0;
+#define VACV_PD_STEP(u)                                                                                        \
+    if (entry != entry_end) {                                                                                  \
+        __syncwarp(); /* every lane is done with step n - 2, whose ring slot the next copy overwrites */       \
+        issue(VACV_PD_IC(((u) + 6) & 7));                                                                      \
+        hfilter(VACV_PD_IC(u), parity, H[(u) & 3]);                                                            \
+        if (kDown) { /* scale_y >= 1: consecutive output rows end on different source rows */                  \
+            if (next_last == n) emit(H[((u) + 1) & 3], H[((u) + 2) & 3], H[((u) + 3) & 3], H[(u) & 3]);        \
+        } else {                                                                                               \
+            while (next_last == n) emit(H[((u) + 1) & 3], H[((u) + 2) & 3], H[((u) + 3) & 3], H[(u) & 3]);     \
+        }                                                                                                      \
+        ++n;                                                                                                   \
+    }
+    while (entry != entry_end) {                       // n & 7 == u
+        VACV_PD_STEP(0) VACV_PD_STEP(1) VACV_PD_STEP(2) VACV_PD_STEP(3) VACV_PD_STEP(4) VACV_PD_STEP(5) VACV_PD_STEP(6) VACV_PD_STEP(7)
+        parity ^= 1u;
+    }
+#undef VACV_PD_STEP
+#undef VACV_PD_IC
+}
+
+}  // namespace vacv

@@ -34,8 +34,8 @@ struct WalkNGeom {
     f32x2 one2, negzero2, magic2, negmagic2;   // (1,1), (-0,-0), (1.5*2^23)x2, (-1.5*2^23)x2 -- opaque to ptxas on purpose
 };
 
-template <int NC, bool kDown>
-__global__ void __launch_bounds__(128, NC == 4 ? 4 : 6) resize_cubic3_walkn_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, WalkNGeom g) {
+template <int NC, bool kDown, int MAXREG = (NC == 4 ? 128 : 80), bool kPre = true>
+__global__ void __maxnreg__(MAXREG) resize_cubic3_walkn_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, WalkNGeom g) {
     constexpr int kWarpCols = 32 * NC;
     constexpr int kWarpRow = kWarpCols * 3;            // bytes one warp produces per output row
     constexpr int NP = NC / 2;                         // column pairs (packed fp32 lanes)
@@ -231,9 +231,12 @@ __global__ void __launch_bounds__(128, NC == 4 ? 4 : 6) resize_cubic3_walkn_kern
     const uint32_t entry_end = rows_s + nrows * (int)sizeof(Walk2Row);
     // put rows t .. t + kWnAhead - 1 in flight: tpre runs from t - 0; the ring slot of row r is r & 7
     for (int a = 0; a < kWnAhead; ++a) prefetch();
-    prefetch(); fetch(t);                              // software pipeline: the tap words of row t are always fetched one step early,
-    while ((t & 3) != 0) {                             // so their shared-memory latency hides behind the previous row's vertical pass
+    // kPre: software pipeline -- the tap words of row t are fetched one step early, so their shared-memory latency hides behind the
+    // previous row's vertical pass (16 more live registers); !kPre: fetched right before use, other warps cover the latency
+    if (kPre) { prefetch(); fetch(t); }
+    while ((t & 3) != 0) {
         f32x2 hv[3][NP];                               // leading rows up to the first multiple of 4: no complete window yet
+        if (!kPre) { prefetch(); fetch(t); }
         hfilter(hv);
         const int slot = t & 3;
 #pragma unroll
@@ -245,15 +248,16 @@ __global__ void __launch_bounds__(128, NC == 4 ? 4 : 6) resize_cubic3_walkn_kern
                 if (slot == 3) H[3][k][p] = hv[k][p];
             }
         ++t;
-        prefetch(); fetch(t);
+        if (kPre) { prefetch(); fetch(t); }
     }
     while (entry != entry_end) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {                  // t & 3 == u
+            if (!kPre) { prefetch(); fetch(t); }
             hfilter(H[u]);                             // consumes the tap words of row t
             const bool due = next_last == t;
             ++t;
-            prefetch(); fetch(t);                      // issue row t + kWnAhead, wait for row t, read its tap words
+            if (kPre) { prefetch(); fetch(t); }        // issue row t + kWnAhead, wait for row t, read its tap words
             if (kDown) {                               // scale_y >= 1: consecutive output rows end on different source rows
                 if (due) emit(H[(u + 1) & 3], H[(u + 2) & 3], H[(u + 3) & 3], H[u]);
             } else {

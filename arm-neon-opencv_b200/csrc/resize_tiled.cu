@@ -23,6 +23,7 @@
 #include "resize_cubic3.cuh"
 #include "resize_cubic3_walk.cuh"
 #include "resize_cubic3_walkn.cuh"
+#include "resize_cubic3_period.cuh"
 #include "host_util.cuh"
 #include "vacv_common.cuh"
 
@@ -689,7 +690,7 @@ static bool walkn_rows_strictly_increase(int h, int ho, double scale_y) {
     return down;
 }
 
-template <int NC>
+template <int NC, int MAXREG = (NC == 4 ? 128 : 80), bool kPre = true>
 static int launch_cubic3_walkn_nc(const uint8_t* src, uint8_t* dst, int images, int w, int h, int wo, int ho, cudaStream_t s) {
     WalkNGeom g;
     g.w = w; g.h = h; g.wo = wo; g.ho = ho;
@@ -707,7 +708,7 @@ static int launch_cubic3_walkn_nc(const uint8_t* src, uint8_t* dst, int images, 
     g.cta_strips = (g.warp_strips + warps - 1) / warps;
     g.store16 = (((size_t)wo * 3) % 16 == 0 && ((uintptr_t)dst % 16) == 0) ? 1 : 0;
     g.one2 = 0x3F8000003F800000ull; g.negzero2 = 0x8000000080000000ull; g.magic2 = 0x4B4000004B400000ull; g.negmagic2 = 0xCB400000CB400000ull;
-    const int per_sm = (NC == 4 ? 4 : 6) * 4 / warps;   // resident CTAs per SM at the kernel's register budget
+    const int per_sm = 65536 / (MAXREG * 32 * warps);   // resident CTAs per SM at the kernel's register budget
     const long long want = 8LL * per_sm * current_sm_count();
     const long long per_seg = (long long)g.cta_strips * images;
     long long segs = std::max<long long>(1, std::min<long long>((want + per_seg - 1) / per_seg, (ho + 63) / 64));
@@ -718,7 +719,84 @@ static int launch_cubic3_walkn_nc(const uint8_t* src, uint8_t* dst, int images, 
     g.segs = (ho + rps - 1) / rps;
     const size_t smem = (size_t)(rps + 1) * sizeof(Walk2Row) + (size_t)warps * kWnStageRows * 32 * NC * 3 + (size_t)warps * kWnRing * g.ring_pitch;
     const bool down = walkn_rows_strictly_increase(h, ho, g.scale_y);
-    auto kern = down ? resize_cubic3_walkn_kernel<NC, true> : resize_cubic3_walkn_kernel<NC, false>;
+    auto kern = down ? resize_cubic3_walkn_kernel<NC, true, MAXREG, kPre> : resize_cubic3_walkn_kernel<NC, false, MAXREG, kPre>;
+    if (smem > 48 * 1024) {
+        if (smem > 200 * 1024) return 0;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return set_error(VACV_ERR_CUDA, "resize: %s", cudaGetErrorString(e));
+    }
+    const int first_px = ((wo * 3) & ~7) / 3;
+    for (int i0 = 0; i0 < images; i0 += 65535) {
+        const int n = std::min(images - i0, 65535);
+        dim3 grid(g.cta_strips * g.segs, n);
+        kern<<<grid, 32 * warps, smem, s>>>(src + (size_t)i0 * g.src_image, dst + (size_t)i0 * g.dst_image, g);
+        if (first_px < wo) {
+            const long long items = (long long)n * ho * (wo - first_px);
+            resize_cubic3_tail_kernel<<<(unsigned)((items + 127) / 128), 128, 0, s>>>(src + (size_t)i0 * g.src_image, dst + (size_t)i0 * g.dst_image, w, h, wo, ho,
+                                                                                  g.scale_x, g.scale_y, g.src_image, g.dst_image, first_px, n);
+        }
+    }
+    return 1;
+}
+
+// u8, third generation for rational horizontal scales (resize_cubic3_period.cuh): w : wo = P : Q, a thread owns KP periods of adjacent
+// columns.  Returns 0 (not eligible) unless every column's taps sit where the kernel's compile-time pattern expects them.
+struct PeriodPlan { int w, wo, P, Q, KP; bool ok; };
+template <int P, int Q, int KP>
+static bool period_taps_match(int w, int wo, double scale_x) {
+    using S = PeriodShape<P, Q, KP>;
+    static thread_local PlanCache<PeriodPlan, 8> cache;
+    if (PeriodPlan* p = cache.find([&](const PeriodPlan& q) { return q.w == w && q.wo == wo && q.P == P && q.Q == Q && q.KP == KP; })) return p->ok;
+    bool ok = true;
+    for (int dx = 0; dx < wo && ok; ++dx) {            // the device's own coordinate arithmetic (cubic_cv_coord_scaled, is_x)
+        float f = (float)(((double)dx + 0.5) * scale_x - 0.5);
+        int sx = (int)floorf(f);
+        if (sx < 0) sx = 0;
+        if (sx >= w - 1) sx = w - 1;
+        const int pt = dx / S::NCOL, c = dx - pt * S::NCOL;
+        const int base = P * KP * pt - 1 + pd::tap0(P, Q, c);
+        for (int j = 0; j < 4; ++j) {
+            const int pos = std::min(std::max(sx - 1 + j, 0), w - 1) - base;
+            ok = ok && pos >= 0 && pos <= 3;
+        }
+    }
+    PeriodPlan* p = cache.claim();
+    p->w = w; p->wo = wo; p->P = P; p->Q = Q; p->KP = KP; p->ok = ok;
+    cache.commit();
+    return ok;
+}
+
+template <int P, int Q, int KP, int MAXREG>
+static int launch_cubic3_period(const uint8_t* src, uint8_t* dst, int images, int w, int h, int wo, int ho, cudaStream_t s) {
+    using S = PeriodShape<P, Q, KP>;
+    if ((long long)w * Q != (long long)wo * P || wo % S::NCOL != 0) return 0;
+    if (((size_t)wo * 3) % 16 != 0 || ((uintptr_t)dst % 16) != 0) return 0;      // staged rows leave as aligned 16-byte chunks
+    PeriodGeom g;
+    g.w = w; g.h = h; g.wo = wo; g.ho = ho;
+    g.src_image = (size_t)w * h * 3; g.dst_image = (size_t)wo * ho * 3;
+    g.scale_x = 1. / ((double)wo / (double)w); g.scale_y = 1. / ((double)ho / (double)h);   // OpenCV 2.4
+    if (!period_taps_match<P, Q, KP>(w, wo, g.scale_x)) return 0;
+    g.ring_pitch = S::kNeed;
+    g.warp_strips = (wo + 32 * S::NCOL - 1) / (32 * S::NCOL);
+    int warps = 4, best_pad = INT_MAX;
+    for (int wv = 4; wv >= 2; --wv) {
+        const int pad = (g.warp_strips + wv - 1) / wv * wv - g.warp_strips;
+        if (pad < best_pad) { best_pad = pad; warps = wv; }
+    }
+    g.cta_strips = (g.warp_strips + warps - 1) / warps;
+    g.one2 = 0x3F8000003F800000ull; g.negzero2 = 0x8000000080000000ull; g.magic2 = 0x4B4000004B400000ull; g.negmagic2 = 0xCB400000CB400000ull;
+    const int per_sm = std::max(1, 65536 / (MAXREG * 32 * warps));   // resident CTAs per SM at the kernel's register budget
+    const long long want = 8LL * per_sm * current_sm_count();
+    const long long per_seg = (long long)g.cta_strips * images;
+    long long segs = std::max<long long>(1, std::min<long long>((want + per_seg - 1) / per_seg, (ho + 63) / 64));
+    if (const int v = knob(kKnobWalkSegs)) segs = std::max(1, v);   // tuning knob
+    int rps = (int)((ho + segs - 1) / segs);
+    rps = std::min(kWalkMaxRows, std::max(rps, 1));
+    g.rows_per_seg = rps;
+    g.segs = (ho + rps - 1) / rps;
+    const size_t smem = (size_t)(rps + 1) * sizeof(Walk2Row) + (size_t)warps * (kPdStageRows * S::kWarpRow + kPdRing * g.ring_pitch + kPdRing * 8);
+    const bool down = walkn_rows_strictly_increase(h, ho, g.scale_y);
+    auto kern = down ? resize_cubic3_period_kernel<P, Q, KP, true, MAXREG> : resize_cubic3_period_kernel<P, Q, KP, false, MAXREG>;
     if (smem > 48 * 1024) {
         if (smem > 200 * 1024) return 0;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -744,6 +822,15 @@ static int launch_cubic3_walkn(const uint8_t* src, uint8_t* dst, int images, int
     if ((double)h / ho > 4.0) return 0;                                           // the walk filters every source row in a segment
     const int v = knob(kKnobCubicV);                                              // tuning knob: 0 = automatic, 2 / 4 = columns per thread
     int rc = 0;
+    if (v == 0 || v == 20) rc = launch_cubic3_period<4, 3, 2, 128>(src, dst, images, w, h, wo, ho, s);
+    if (v == 21) rc = launch_cubic3_period<4, 3, 2, 152>(src, dst, images, w, h, wo, ho, s);
+    if (v == 22) rc = launch_cubic3_period<4, 3, 2, 168>(src, dst, images, w, h, wo, ho, s);
+    if (rc != 0) return rc;
+    if (v == 5) rc = launch_cubic3_walkn_nc<4, 112, true>(src, dst, images, w, h, wo, ho, s);   // experiments: register caps, no tap prefetch
+    if (v == 6) rc = launch_cubic3_walkn_nc<4, 112, false>(src, dst, images, w, h, wo, ho, s);
+    if (v == 7) rc = launch_cubic3_walkn_nc<4, 128, false>(src, dst, images, w, h, wo, ho, s);
+    if (v == 8) rc = launch_cubic3_walkn_nc<4, 104, false>(src, dst, images, w, h, wo, ho, s);
+    if (v == 9) rc = launch_cubic3_walkn_nc<4, 96, false>(src, dst, images, w, h, wo, ho, s);
     if (v == 0 || v == 4) rc = launch_cubic3_walkn_nc<4>(src, dst, images, w, h, wo, ho, s);
     if (rc == 0 && v != 1) rc = launch_cubic3_walkn_nc<2>(src, dst, images, w, h, wo, ho, s);
     return rc;
