@@ -141,13 +141,57 @@ __global__ void __maxnreg__(MAXREG) resize_cubic3_period_kernel(const uint8_t* _
     uint8_t* out_img = dst + blockIdx.y * g.dst_image;
     const unsigned row_bytes = (unsigned)g.w * 3, out_row_bytes = (unsigned)g.wo * 3;
 
-    // per output row: vertical weights, and the walk step n (source row t_first + n) that completes it
-    int t_first;
+    // walk steps: step n filters source row t_first + n; the last step is the last output row's last tap row
+    int t_first, n_stop;
     {
-        int s, q[4];
-        cubic_cv_coord_scaled(dy_begin, g.h, g.scale_y, false, s, q);
-        t_first = s - 1;
+        const float f0 = (float)(((double)dy_begin + 0.5) * g.scale_y - 0.5), f1 = (float)(((double)(dy_begin + nrows - 1) + 0.5) * g.scale_y - 0.5);
+        t_first = __shfl_sync(0xffffffffu, (int)floorf(f0) - 1, 0);   // cubic_cv_coord_scaled's row index, without the coefficients
+        n_stop = __shfl_sync(0xffffffffu, (int)floorf(f1) + 2, 0) - t_first;
     }
+    const bool active = wstrip < g.warp_strips;        // false: padding warp of the last CTA strip
+
+    // the warp's bytes of a source row: [span0, span0 + kNeed) clipped to the row; ring byte r <-> source byte span0 + r.
+    // Everything the copy issue needs is warp-uniform; the shuffles tell the compiler so (uniform registers, one UBLKCP per warp).
+    constexpr unsigned kPitch = S::kNeed;              // bytes per ring slot
+    const int span0 = S::kWarpSpan * wstrip - 16;
+    const int lo = __shfl_sync(0xffffffffu, max(span0, 0), 0), hi = __shfl_sync(0xffffffffu, min(span0 + S::kNeed, (int)row_bytes), 0);
+    const uint32_t copy_bytes = (uint32_t)(hi - lo);
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+    const uint32_t ring_dst = __shfl_sync(0xffffffffu, ring_s - (uint32_t)span0, 0) + (uint32_t)lo;
+    const uint32_t ubars = __shfl_sync(0xffffffffu, bars, 0);
+    const uint32_t win_s = ring_s + (uint32_t)(LS * lane + S::kLaneOff);   // this lane's window word 0 in ring slot 0
+    const uint32_t rows_s = (uint32_t)__cvta_generic_to_shared(rows);
+    const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
+    const f32x2 one2 = g.one2, negzero2 = g.negzero2, magic2 = g.magic2, negmagic2 = g.negmagic2;
+
+    // ---- source rows: walk step n (row t_first + n, clamped to the image like OpenCV's tap rows) -> ring slot n & 7, one bulk copy
+    //      per warp and row, kPdAhead steps ahead
+    int t_pre = t_first;                               // (unclamped) row of the next copy; its walk step is n_pre
+    int n_pre = 0;
+    const uint8_t* g_pre = src + blockIdx.y * g.src_image + (unsigned)lo + (size_t)(unsigned)min(max(t_first, 0), g.h - 1) * row_bytes;
+    auto issue = [&](const uint32_t slot) {            // warp-uniform; slot is a literal at every call site
+        if (n_pre <= n_stop) {
+            if (lane == 0) {
+                pd::mbar_expect_tx(ubars + 8 * slot, copy_bytes);
+                pd::bulk_g2s(ring_dst + slot * kPitch, g_pre, copy_bytes, ubars + 8 * slot);
+            }
+            g_pre += (unsigned)t_pre < (unsigned)(g.h - 1) ? row_bytes : 0u;   // rows below 0 / beyond h-1 repeat the edge row
+            ++t_pre;
+        }
+        ++n_pre;
+    };
+    // the first rows go in flight before the tables below are computed (their DRAM latency hides behind that arithmetic)
+    if (active) {
+        if (lane == 0) {
+            for (int i = 0; i < kPdRing; ++i) pd::mbar_init(bars + 8 * i, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        static_assert(kPdAhead == 6 && kPdRing == 8, "the unrolled walk below assumes 6 rows ahead in an 8-slot ring");
+        issue(0); issue(1); issue(2); issue(3); issue(4); issue(5);
+    }
+
+    // per output row: vertical weights, and the walk step that completes it
     for (int r = tid; r <= nrows; r += blockDim.x) {   // entry nrows = sentinel that never matches
         Walk2Row e;
         int s, q[4];
@@ -158,16 +202,9 @@ __global__ void __maxnreg__(MAXREG) resize_cubic3_period_kernel(const uint8_t* _
         e.pad[0] = e.pad[1] = e.pad[2] = 0;
         rows[r] = e;
     }
-    if (lane == 0) {
-        for (int i = 0; i < kPdRing; ++i) pd::mbar_init(bars + 8 * i, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (wstrip >= g.warp_strips) return;               // padding warp of the last CTA strip (no CTA barrier below)
-
     // x taps: column c's four taps sit at window pixels tap0(c) .. tap0(c) + 3 (verified by the launcher); taps OpenCV clamps onto an
     // edge pixel have their integer coefficients added up at that pixel's position (identical sums)
-    const bool owner = NCOL * pt < g.wo;               // threads past the last column compute on zero coefficients and store nothing
+    const bool owner = NCOL * pt < g.wo;               // threads past the last column compute on zero coefficients; their bytes are never flushed
     int c01[NCOL], c23[NCOL];
     pd::static_for<NCOL>([&](auto ic) {
         constexpr int c = decltype(ic)::value;
@@ -183,44 +220,13 @@ __global__ void __maxnreg__(MAXREG) resize_cubic3_period_kernel(const uint8_t* _
         c01[c] = (xc[0] & 0xffff) | (xc[1] << 16);
         c23[c] = (xc[2] & 0xffff) | (xc[3] << 16);
     });
-
-    // the warp's bytes of a source row: [span0, span0 + kNeed) clipped to the row; ring byte r <-> source byte span0 + r.
-    // Everything the copy issue needs is warp-uniform; the shuffles tell the compiler so (uniform registers, one UBLKCP per warp).
-    constexpr unsigned kPitch = S::kNeed;              // bytes per ring slot
-    const int span0 = S::kWarpSpan * wstrip - 16;
-    const int lo = max(span0, 0), hi = min(span0 + S::kNeed, (int)row_bytes);
-    const uint32_t copy_bytes = __shfl_sync(0xffffffffu, (uint32_t)(hi - lo), 0);
-    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
-    const uint32_t ring_dst = __shfl_sync(0xffffffffu, ring_s + (uint32_t)(lo - span0), 0);
-    const uint32_t ubars = __shfl_sync(0xffffffffu, bars, 0);
-    const uint32_t win_s = ring_s + (uint32_t)(LS * lane + S::kLaneOff);   // this lane's window word 0 in ring slot 0
-    const uint32_t rows_s = (uint32_t)__cvta_generic_to_shared(rows);
-    const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
-    const f32x2 one2 = g.one2, negzero2 = g.negzero2, magic2 = g.magic2, negmagic2 = g.negmagic2;
+    __syncthreads();
+    if (!active) return;                               // (no CTA barrier below)
 
     uint32_t entry = rows_s;                           // shared address of the next output row's table entry
     int next_last;
     asm volatile("ld.shared.s32 %0, [%1+32];" : "=r"(next_last) : "r"(entry));
-    int n_stop;                                        // last walk step = the last output row's last tap row
-    asm volatile("ld.shared.s32 %0, [%1+32];" : "=r"(n_stop) : "r"(rows_s + (nrows - 1) * (int)sizeof(Walk2Row)));
-    n_stop = __shfl_sync(0xffffffffu, n_stop, 0);
 
-    // ---- source rows: walk step n (row t_first + n, clamped to the image like OpenCV's tap rows) -> ring slot n & 7, one bulk copy
-    //      per warp and row, kPdAhead steps ahead
-    int t_pre = t_first;                               // (unclamped) row of the next copy; its walk step is n_pre
-    int n_pre = 0;
-    const uint8_t* g_pre = img + lo + (size_t)(unsigned)min(max(t_first, 0), g.h - 1) * row_bytes;
-    auto issue = [&](const uint32_t slot) {            // warp-uniform; slot is a literal at every call site
-        if (n_pre <= n_stop) {
-            if (lane == 0) {
-                pd::mbar_expect_tx(ubars + 8 * slot, copy_bytes);
-                pd::bulk_g2s(ring_dst + slot * kPitch, g_pre, copy_bytes, ubars + 8 * slot);
-            }
-            g_pre += (unsigned)t_pre < (unsigned)(g.h - 1) ? row_bytes : 0u;   // rows below 0 / beyond h-1 repeat the edge row
-            ++t_pre;
-        }
-        ++n_pre;
-    };
     // horizontal pass of the walk step in ring slot `slot`: (value 2i, value 2i+1) of the thread's NV = 3 * NCOL output bytes, exact fp32
     auto hfilter = [&](const uint32_t slot, uint32_t parity, f32x2 (&H)[NP]) {
         pd::mbar_wait(ubars + 8 * slot, parity);
@@ -267,7 +273,7 @@ __global__ void __maxnreg__(MAXREG) resize_cubic3_period_kernel(const uint8_t* _
     constexpr bool kHalf = NV % 4 == 2;
     constexpr int NWD = NV / 4;                        // full words per thread and row
     constexpr int kChunks = kWarpRow / 16;             // 16-byte chunks per row of the warp
-    static_assert(kChunks > 32 && kChunks <= 64, "flush: one or two chunks per lane");
+    static_assert(kChunks <= 64, "flush: one or two chunks per lane");
     const bool odd = kHalf && (lane & 1);
     const int sh16 = odd ? 16 : 0;
     uint32_t st_w = stage_s + NV * lane + (odd ? 2 : 0);            // the 32-bit stores
@@ -275,7 +281,7 @@ __global__ void __maxnreg__(MAXREG) resize_cubic3_period_kernel(const uint8_t* _
     uint32_t st_f = stage_s + 16 * lane;                            // this lane's first chunk of the staged row
     int st_d = kWarpRow;                                            // distance to the other staging buffer
     const int valid_chunks = min(kWarpRow, (int)out_row_bytes - wstrip * kWarpRow) >> 4;        // chunks of a warp row inside the image row
-    const bool f0 = lane < valid_chunks, f1 = lane + 32 < min(valid_chunks, kChunks);
+    const bool f0 = lane < min(valid_chunks, kChunks), f1 = kChunks > 32 && lane + 32 < min(valid_chunks, kChunks);
     uint8_t* gflush = out_img + (size_t)dy_begin * out_row_bytes + (size_t)wstrip * kWarpRow + 16 * lane;   // this lane's first chunk in global memory
 
     // vertical pass + store of the NV output bytes from the window (h0 = oldest row)
@@ -317,7 +323,7 @@ __global__ void __maxnreg__(MAXREG) resize_cubic3_period_kernel(const uint8_t* _
             asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(st_f));
             st_stream16(gflush, v);
         }
-        if (f1) {
+        if (kChunks > 32 && f1) {
             uint4 v;
             asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+512];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(st_f));
             st_stream16(gflush + 512, v);
@@ -334,8 +340,6 @@ __global__ void __maxnreg__(MAXREG) resize_cubic3_period_kernel(const uint8_t* _
     f32x2 H[4][NP];
     const uint32_t entry_end = rows_s + nrows * (int)sizeof(Walk2Row);
 #define VACV_PD_IC(k) (uint32_t)(k)
-    issue(VACV_PD_IC(0)); issue(VACV_PD_IC(1)); issue(VACV_PD_IC(2)); issue(VACV_PD_IC(3)); issue(VACV_PD_IC(4)); issue(VACV_PD_IC(5));
-    static_assert(kPdAhead == 6 && kPdRing == 8, "the unrolled walk below assumes 6 rows ahead in an 8-slot ring");
     int n = 0;
     uint32_t parity = 0;
 #define VACV_PD_STEP(u)                                                                                        \

@@ -822,15 +822,13 @@ static int launch_cubic3_walkn(const uint8_t* src, uint8_t* dst, int images, int
     if ((double)h / ho > 4.0) return 0;                                           // the walk filters every source row in a segment
     const int v = knob(kKnobCubicV);                                              // tuning knob: 0 = automatic, 2 / 4 = columns per thread
     int rc = 0;
-    if (v == 0 || v == 20) rc = launch_cubic3_period<4, 3, 2, 128>(src, dst, images, w, h, wo, ho, s);
-    if (v == 21) rc = launch_cubic3_period<4, 3, 2, 152>(src, dst, images, w, h, wo, ho, s);
-    if (v == 22) rc = launch_cubic3_period<4, 3, 2, 168>(src, dst, images, w, h, wo, ho, s);
+    if (v == 0 || v == 20) {                                                      // rational horizontal scales: periodic walker
+        rc = launch_cubic3_period<4, 3, 2, 168>(src, dst, images, w, h, wo, ho, s);   // 4 : 3 (config 4: 2560 -> 1920)
+        if (rc == 0) rc = launch_cubic3_period<2, 1, 4, 128>(src, dst, images, w, h, wo, ho, s);   // 2 : 1 (3840 -> 1920)
+    }
+    if (v == 21) rc = launch_cubic3_period<4, 3, 2, 128>(src, dst, images, w, h, wo, ho, s);
     if (rc != 0) return rc;
-    if (v == 5) rc = launch_cubic3_walkn_nc<4, 112, true>(src, dst, images, w, h, wo, ho, s);   // experiments: register caps, no tap prefetch
-    if (v == 6) rc = launch_cubic3_walkn_nc<4, 112, false>(src, dst, images, w, h, wo, ho, s);
-    if (v == 7) rc = launch_cubic3_walkn_nc<4, 128, false>(src, dst, images, w, h, wo, ho, s);
-    if (v == 8) rc = launch_cubic3_walkn_nc<4, 104, false>(src, dst, images, w, h, wo, ho, s);
-    if (v == 9) rc = launch_cubic3_walkn_nc<4, 96, false>(src, dst, images, w, h, wo, ho, s);
+    if (v == 6) rc = launch_cubic3_walkn_nc<4, 112, false>(src, dst, images, w, h, wo, ho, s);   // experiment: register cap, no tap prefetch
     if (v == 0 || v == 4) rc = launch_cubic3_walkn_nc<4>(src, dst, images, w, h, wo, ho, s);
     if (rc == 0 && v != 1) rc = launch_cubic3_walkn_nc<2>(src, dst, images, w, h, wo, ho, s);
     return rc;

@@ -315,7 +315,7 @@ def test_resize_cubic_u8(vacv, oracle, c, sz, path):
     assert_same(got, want)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 4])
+@pytest.mark.parametrize("variant", [0, 1, 2, 4, 21])
 @pytest.mark.parametrize("sz", [((1280, 720), (960, 540)), ((1280, 720), (400, 300)), ((1024, 96), (1000, 90)), ((512, 700), (384, 1000)),
                                 ((2048, 64), (1536, 48)), ((768, 300), (1000, 200)), ((256, 256), (129, 255)), ((1920, 1080), (1280, 720))])
 def test_resize_cubic_u8_column_walker_generations(vacv, oracle, sz, variant):
@@ -331,6 +331,28 @@ def test_resize_cubic_u8_column_walker_generations(vacv, oracle, sz, variant):
         vacv.lib.vacv_cuda_set_tuning(b"CUBIC_V", 0)
     for i in range(3):
         assert_same(got[i], oracle.resize_cubic_u8(src[i], w, h, 3, wo, ho))
+
+
+@pytest.mark.parametrize("sz", [((2560, 1440), (1920, 1080)), ((1040, 300), (780, 225)), ((1040, 90), (780, 131)), ((64, 40), (48, 30)),
+                                ((16, 16), (12, 12)), ((32, 9), (24, 20)), ((4096, 40), (3072, 30)), ((1280, 64), (960, 64)),
+                                ((3840, 2160), (1920, 1080)), ((2560, 100), (1280, 77)), ((64, 64), (32, 32)), ((32, 12), (16, 30)),
+                                ((1296, 50), (648, 25))])
+def test_resize_cubic_u8_periodic_walker(vacv, oracle, sz):
+    """u8 bicubic at rational horizontal scales (resize_cubic3_period.cuh: 4 : 3 with six adjacent columns per thread, 2 : 1 with four):
+    full and partial warp strips, a handful of threads per row, the clamped taps at both image edges, up- and down-scaling along y
+    (the walk's two emit rules), several vertical segments, a batch of 3 -- against the oracle's OpenCV-2.4 rule and against the
+    first-generation walker byte for byte."""
+    (w, h), (wo, ho) = sz
+    src = u8(63, 3, h, w, 3)
+    got = host(vacv.resize(dev(src), NHWC, wo, ho, vacv.INTER_CUBIC))
+    for i in range(3):
+        assert_same(got[i], oracle.resize_cubic_u8(src[i], w, h, 3, wo, ho))
+    assert vacv.lib.vacv_cuda_set_tuning(b"CUBIC_V", 1) == 0
+    try:
+        first = host(vacv.resize(dev(src), NHWC, wo, ho, vacv.INTER_CUBIC))
+    finally:
+        vacv.lib.vacv_cuda_set_tuning(b"CUBIC_V", 0)
+    assert_same(got, first)
 
 
 def test_resize_cubic_u8_config4_fixture_vs_bundled_opencv(vacv):
