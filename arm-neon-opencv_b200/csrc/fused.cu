@@ -376,6 +376,14 @@ static int build_pipe_plan(PipePlan& plan) {
     g.y_pitch = y.y_pitch; g.c_pitch = y.c_pitch; g.frame_stride = y.frame_stride; g.c_off = y.c_off; g.c2_off = y.c2_off;
     g.canvas_w = cv.w; g.canvas_h = cv.h; g.x0 = cv.x0; g.y0 = cv.y0; g.bf16 = out_dtype == VACV_BF16 ? 1 : 0;
     const bool planar = y.fmt == kFmtPlanar;
+    // padded surfaces (decoder pools: pitch 2048 for 1920-wide frames).  Default: a band is ONE copy, padding included (7 % more DRAM
+    // reads at pitch 2048).  VACV_PIPE_ROWS=1 stages only the rows' own bytes with one bulk copy per row -- measured slower on B200
+    // (1080p -> 640x640 x256, same box: nv12 p2048 fp32 0.447 vs 0.407 ms, i420 p2048 fp16 0.389 vs 0.309 ms): 25-40 copies of
+    // <= 1920 bytes per tile cost more in the copy engine than the padding costs in DRAM.
+    const int y_row16 = (w + 15) & ~15, c_row16 = ((planar ? w / 2 : w) + 15) & ~15;
+    const bool by_row = (y.y_pitch > y_row16 || y.c_pitch > c_row16) && knob(kKnobPipeRows) != 0;
+    g.sy_pitch = by_row ? y_row16 : y.y_pitch;
+    g.sc_pitch = by_row ? c_row16 : y.c_pitch;
     int best_TH = 0;
     size_t best_smem = 0;
     for (int TH = 8; TH >= 1; --TH) {
@@ -386,8 +394,8 @@ static int build_pipe_plan(PipePlan& plan) {
             yrows = std::max(yrows, y1 - y0 + 1);
             crows = std::max(crows, (y1 >> 1) - (y0 >> 1) + 1);
         }
-        const size_t ystage = ((size_t)yrows * y.y_pitch + 127) & ~(size_t)127;
-        const size_t cband = ((size_t)crows * y.c_pitch + 127) & ~(size_t)127;
+        const size_t ystage = ((size_t)yrows * g.sy_pitch + 127) & ~(size_t)127;
+        const size_t cband = ((size_t)crows * g.sc_pitch + 127) & ~(size_t)127;
         const size_t cstage = planar ? 2 * cband : cband;
         const size_t smem = table_bytes + 2 * (ystage + cstage);
         if (smem + static_bytes <= 113 * 1024 || (TH == 1 && smem + static_bytes <= 226 * 1024)) {   // 2 CTAs / SM

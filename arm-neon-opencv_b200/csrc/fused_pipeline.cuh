@@ -32,6 +32,10 @@ struct PipeGeom {
     int table_bytes;        // bytes of the two row tables at the start of dynamic shared memory (multiple of 128)
     // source layout (dense NV12/NV21: y_pitch = c_pitch = w, c_off = w*h, frame_stride = w*h*3/2)
     int y_pitch, c_pitch;   // bytes per luma row / per chroma row (planar formats: per U or V row)
+    // staged rows: sy_pitch / sc_pitch bytes apart in shared memory.  Equal to the source pitches when a band is one contiguous copy;
+    // with VACV_PIPE_ROWS=1 on padded surfaces (pitch >= row + 16) the row rounded up to 16 bytes -- the band is then copied row by
+    // row and the padding stays in DRAM
+    int sy_pitch, sc_pitch;
     int vstage_off;         // planar formats: byte offset of the V band inside the chroma stage
     size_t frame_stride;    // bytes between frames
     size_t c_off, c2_off;   // byte offset of the chroma plane (semi-planar) / of the U and V planes (planar) inside a frame
@@ -312,6 +316,28 @@ __device__ __forceinline__ void compute_tile_packed(uint32_t ybuf, uint32_t cbuf
     }
 }
 
+// Padded surfaces (pitch >= row + 16: decoder pools), opt-in variant VACV_PIPE_ROWS=1 (measured slower than whole bands, see
+// build_pipe_plan in fused.cu): the band of a tile is copied ROW BY ROW, g.sy_pitch / g.sc_pitch bytes each (the
+// row rounded up to 16 bytes), so the padding stays in DRAM; lane i of the calling warp issues rows i, i + 32, ...  Kept out of line:
+// inlined, it changed the register allocation of the tile loop (fp16 outputs lost 8 %).
+template <int FMT>
+__device__ __noinline__ void issue_band_rows(const PipeGeom& g, const uint8_t* f, uint8_t* st, uint64_t* bar, int y_first, int y_last, int lane) {
+    const int c_first = y_first >> 1, c_last = y_last >> 1;
+    const int yrows = y_last - y_first + 1, crows = c_last - c_first + 1;
+    constexpr int kPlanes = FMT == kFmtPlanar ? 2 : 1;
+    if (lane == 0) mbar_expect_tx(bar, (uint32_t)yrows * g.sy_pitch + (uint32_t)(kPlanes * crows) * g.sc_pitch);
+    __syncwarp();
+    for (int r = lane; r < yrows + kPlanes * crows; r += 32) {
+        if (r < yrows) {
+            bulk_g2s(st + (size_t)r * g.sy_pitch, f + (size_t)(y_first + r) * g.y_pitch, (uint32_t)g.sy_pitch, bar);
+        } else {
+            const int q = r - yrows, second = q >= crows ? 1 : 0, cr = q - second * crows;
+            bulk_g2s(st + g.ystage + (second ? g.vstage_off : 0) + (size_t)cr * g.sc_pitch,
+                     f + (second ? g.c2_off : g.c_off) + (size_t)(c_first + cr) * g.c_pitch, (uint32_t)g.sc_pitch, bar);
+        }
+    }
+}
+
 // kDense: the reference's own layout (tensor.cpp:524: no pitch; chroma right after luma) -- one pitch register, constants folded.
 template <int FMT, typename OutT, int NCOL, bool kDense>
 __global__ void __launch_bounds__(NCOL == 1 ? 640 : kPipeThreads, NCOL <= 2 ? 2 : 1)
@@ -331,6 +357,8 @@ nv_resize_normalize_chw_pipe_kernel(const uint8_t* __restrict__ src, OutT* __res
     const size_t plane_bytes = kDense ? (size_t)g.wo * g.ho * Ops::kElem : (size_t)g.canvas_w * g.canvas_h * Ops::kElem;
     const size_t row_bytes = kDense ? (size_t)g.wo * Ops::kElem : (size_t)g.canvas_w * Ops::kElem;
     const int y_pitch = kDense ? g.w : g.y_pitch, c_pitch = kDense ? g.w : g.c_pitch;
+    const int sy_pitch = kDense ? g.w : g.sy_pitch, sc_pitch = kDense ? g.w : g.sc_pitch;      // row pitches of the staged bands
+    const bool by_row = !kDense && (sy_pitch != y_pitch || sc_pitch != c_pitch);
     const size_t frame_stride = kDense ? (size_t)g.w * g.h * 3 / 2 : g.frame_stride, c_off = kDense ? (size_t)g.w * g.h : g.c_off;
     const uint32_t stages_s = smem_u32(stages), sy_s = smem_u32(s_sy), cy_s = smem_u32(s_cy), lut_s = smem_u32(lut);
 
@@ -372,7 +400,7 @@ nv_resize_normalize_chw_pipe_kernel(const uint8_t* __restrict__ src, OutT* __res
     }
     if (any_right) s_any_right = 1;   // benign race: all writers store 1
 
-    auto issue = [&](int tile, int b) {   // one thread
+    auto issue = [&](int tile, int b) {   // one thread: every band is contiguous in memory -> one copy each
         const int frame = tile / g.tiles_per_frame, dy0 = (tile - frame * g.tiles_per_frame) * g.TH;
         const int th = min(g.TH, g.ho - dy0);
         const int y_first = s_sy[dy0], y_last = s_sy[dy0 + th - 1] + 1;
@@ -385,16 +413,27 @@ nv_resize_normalize_chw_pipe_kernel(const uint8_t* __restrict__ src, OutT* __res
         bulk_g2s(st + g.ystage, f + c_off + (size_t)c_first * c_pitch, cbytes, &full_bar[b]);
         if (FMT == kFmtPlanar) bulk_g2s(st + g.ystage + g.vstage_off, f + g.c2_off + (size_t)c_first * c_pitch, cbytes, &full_bar[b]);
     };
+    auto issue_rows = [&](int tile, int b) {   // padded surface; called by every lane of warp 0
+        const int frame = tile / g.tiles_per_frame, dy0 = (tile - frame * g.tiles_per_frame) * g.TH;
+        const int th = min(g.TH, g.ho - dy0);
+        issue_band_rows<FMT>(g, src + (size_t)frame * frame_stride, stages + (size_t)b * (g.ystage + g.cstage), &full_bar[b], s_sy[dy0], s_sy[dy0 + th - 1] + 1, tid);
+    };
 
     int tile = blockIdx.x;
-    if (tid == 0 && tile < g.total_tiles) issue(tile, 0);
+    if (tile < g.total_tiles) {
+        if (by_row) { if (tid < 32) issue_rows(tile, 0); }
+        else if (tid == 0) issue(tile, 0);
+    }
     __syncthreads();
     const bool right = s_any_right != 0;
 
     for (int it = 0; tile < g.total_tiles; tile += gridDim.x, ++it) {
         const int b = it & 1;
         const int next = tile + gridDim.x;
-        if (tid == 0 && next < g.total_tiles) issue(next, b ^ 1);   // stage b^1 was released by the sync below
+        if (next < g.total_tiles) {   // stage b^1 was released by the sync below
+            if (by_row) { if (tid < 32) issue_rows(next, b ^ 1); }
+            else if (tid == 0) issue(next, b ^ 1);
+        }
         mbar_wait(&full_bar[b], (it >> 1) & 1);
         const int frame = tile / g.tiles_per_frame, dy0 = (tile - frame * g.tiles_per_frame) * g.TH;
         const int th = min(g.TH, g.ho - dy0);
@@ -408,11 +447,11 @@ nv_resize_normalize_chw_pipe_kernel(const uint8_t* __restrict__ src, OutT* __res
         // measured on B200 (bench_ops.py c2 / c2g / c2s): the packed variant wins for 16-bit outputs (issue-bound: 0.312 -> 0.282 ms)
         // and loses for fp32 (0.367 -> 0.384 ms: it moves the blend from the FMA pipe's IMADs onto the already busier ALU pipe)
         if (NCOL % 2 == 0 && sizeof(typename Ops::Lut) == 2) {
-            if (right) compute_tile_packed<FMT, OutT, true, NCOL>(ybuf, cbuf, sy_s, cy_s, lut_s, col, dy0, th, y_pitch, c_pitch, g.vstage_off, out, row_bytes, plane_bytes);
-            else compute_tile_packed<FMT, OutT, false, NCOL>(ybuf, cbuf, sy_s, cy_s, lut_s, col, dy0, th, y_pitch, c_pitch, g.vstage_off, out, row_bytes, plane_bytes);
+            if (right) compute_tile_packed<FMT, OutT, true, NCOL>(ybuf, cbuf, sy_s, cy_s, lut_s, col, dy0, th, sy_pitch, sc_pitch, g.vstage_off, out, row_bytes, plane_bytes);
+            else compute_tile_packed<FMT, OutT, false, NCOL>(ybuf, cbuf, sy_s, cy_s, lut_s, col, dy0, th, sy_pitch, sc_pitch, g.vstage_off, out, row_bytes, plane_bytes);
         } else {
-            if (right) compute_tile<FMT, OutT, true, NCOL>(ybuf, cbuf, sy_s, cy_s, lut_s, col, dy0, th, y_pitch, c_pitch, g.vstage_off, out, row_bytes, plane_bytes);
-            else compute_tile<FMT, OutT, false, NCOL>(ybuf, cbuf, sy_s, cy_s, lut_s, col, dy0, th, y_pitch, c_pitch, g.vstage_off, out, row_bytes, plane_bytes);
+            if (right) compute_tile<FMT, OutT, true, NCOL>(ybuf, cbuf, sy_s, cy_s, lut_s, col, dy0, th, sy_pitch, sc_pitch, g.vstage_off, out, row_bytes, plane_bytes);
+            else compute_tile<FMT, OutT, false, NCOL>(ybuf, cbuf, sy_s, cy_s, lut_s, col, dy0, th, sy_pitch, sc_pitch, g.vstage_off, out, row_bytes, plane_bytes);
         }
         __syncthreads();   // all reads of stage b done -> it may be refilled by the next iteration's issue
     }

@@ -19,6 +19,7 @@ enum Knob {
     kKnobWalk2Sync,        // VACV_WALK2_SYNC           u8 bicubic walker: same
     kKnobCubic3Roll,       // VACV_CUBIC3=roll          shared-memory ring kernel instead of the column walker
     kKnobCubicV,           // VACV_CUBIC_V              u8 bicubic kernel variant (0 = default)
+    kKnobPipeRows,         // VACV_PIPE_ROWS            fused pipeline on padded surfaces: one bulk copy per row instead of whole bands (padding included)
     kKnobCount
 };
 int knob(Knob k);
