@@ -162,7 +162,8 @@ resize_linear_u8c3_pipe_kernel(const uint8_t* __restrict__ src, void* __restrict
     int tile = blockIdx.x;
     if (tid < 32 && tile < g.total_tiles) issue(tile, 0);
     __syncthreads();
-    const int n_last = g.wo - (g.wo & ~31);   // valid pixels in the last, partial warp of a row (0: none partial)
+    // u8 output: all of this warp's column groups are full runs of 32 pixels and every output row starts word-aligned
+    const bool all_fast = (tid & ~31) + (NCOL - 1) * nthr + 32 <= g.wo && ((g.wo * 3) & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 3) == 0;
 
     for (int it = 0; tile < g.total_tiles; tile += gridDim.x, ++it) {
         const int b = it & 1;
@@ -174,70 +175,38 @@ resize_linear_u8c3_pipe_kernel(const uint8_t* __restrict__ src, void* __restrict
         const uint32_t buf = stages_s + b * g.stage_bytes;
         const int y_first = kBand ? lds_s32(sy_s + 4 * dy0) : 0;
         uint8_t* orow = dst + (size_t)frame * g.dst_image + (size_t)dy0 * g.wo * 3;
-        int H0[NCOL][3], H1[NCOL][3];
-        int have = -2;
-        for (int ty = 0; ty < th; ++ty, orow += (size_t)g.wo * 3) {
-            const int sy = lds_s32(sy_s + 4 * (dy0 + ty));
-            const int cy = lds_s32(cy_s + 4 * (dy0 + ty));
-            const int cy0 = (short)(cy & 0xffff), cy1 = cy >> 16;
-            if (kPoint) {  // all weights are (2048, 0) x (2048, 0): (p << 22) >> 22 = p, signed or not
-                const uint32_t upper = buf + (unsigned)lds_s32(slot_s + 4 * (dy0 + ty)) * row_bytes;
-                uint8_t* lbp = reinterpret_cast<uint8_t*>(line);
-#pragma unroll
-                for (int j = 0; j < NCOL; ++j) {
-                    uint32_t w0, w1;
-                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(upper + aw[j]));
-                    asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(upper + aw[j]));
-                    const uint32_t px = __funnelshift_r(w0, w1, sh[j]);
-                    lbp[j * 96 + 3 * lane] = (uint8_t)px; lbp[j * 96 + 3 * lane + 1] = (uint8_t)(px >> 8); lbp[j * 96 + 3 * lane + 2] = (uint8_t)(px >> 16);
-                }
-            } else if (kBand) {   // contiguous band: slot = row - first row; a zero-weight lower row is staged anyway and contributes H1 * 0
-                if (sy == have) {
-#pragma unroll
-                    for (int j = 0; j < NCOL; ++j) { H0[j][0] = H1[j][0]; H0[j][1] = H1[j][1]; H0[j][2] = H1[j][2]; }
-                } else if (sy + 1 != have) {
-                    hrow(buf + (unsigned)(sy - y_first) * row_bytes, H0);
-                }
-                if (sy + 1 != have) {
-                    hrow(buf + (unsigned)(sy + 1 - y_first) * row_bytes, H1);
-                    have = sy + 1;
-                }
-            } else {
-                const uint32_t upper = buf + (unsigned)lds_s32(slot_s + 4 * (dy0 + ty)) * row_bytes;   // staged upper tap row; the lower one follows it
-                // have = source row whose sums H1 holds (-2: none).  All threads walk the same rows: no divergence.
-                if (sy == have) {
-#pragma unroll
-                    for (int j = 0; j < NCOL; ++j) { H0[j][0] = H1[j][0]; H0[j][1] = H1[j][1]; H0[j][2] = H1[j][2]; }
-                    have = -2;
-                } else if (sy + 1 != have || cy1 == 0) {
-                    hrow(upper, H0);
-                }
-                if (cy1 != 0) {
-                    if (sy + 1 != have) { hrow(upper + row_bytes, H1); have = sy + 1; }
-                } else {   // zero-weight lower tap: not staged, contributes H1 * 0
-#pragma unroll
-                    for (int j = 0; j < NCOL; ++j) { H1[j][0] = 0; H1[j][1] = 0; H1[j][2] = 0; }
-                    have = -2;
-                }
-            }
+        // Horizontal sums live in two register sets: Ha holds an EVEN source row, Hb an ODD one (have_a / have_b: which).  An output
+        // row blends row sy (upper) with row sy + 1 (lower), one of each parity; when the next output row starts on the previous lower
+        // row, that row's sums are already where its parity puts them -- nothing is copied (the round-1 loop moved H1 into H0: 8 of
+        // its 63 instructions per pixel were register moves, profiles/r2_lin720_ncu_raw.txt).  All threads walk the same rows.
+        int Ha[NCOL][3] = {}, Hb[NCOL][3] = {};
+        int have_a = -2, have_b = -2;
+        // vertical blend + store of one output row (Hu = sums of the upper tap row, Hl = of the lower one)
+        auto blend_store = [&](const int (&Hu)[NCOL][3], const int (&Hl)[NCOL][3], int cy0, int cy1, int ty, uint8_t* orow) {
             if (OUT == kRpOutU8) {
                 uint8_t* lb = reinterpret_cast<uint8_t*>(line);
                 if (!kPoint) {
 #pragma unroll
                     for (int j = 0; j < NCOL; ++j) {
 #pragma unroll
-                        for (int k = 0; k < 3; ++k) lb[j * 96 + 3 * lane + k] = (uint8_t)((H0[j][k] * cy0 + H1[j][k] * cy1) >> 22);   // resize_naive.cpp:60-65
+                        for (int k = 0; k < 3; ++k) lb[j * 96 + 3 * lane + k] = (uint8_t)((Hu[j][k] * cy0 + Hl[j][k] * cy1) >> 22);   // resize_naive.cpp:60-65
                     }
                 }
                 __syncwarp();
+                if (all_fast) {   // every group of this warp is a full, word-aligned run of 32 pixels: 24 lanes x 4 bytes each
 #pragma unroll
-                for (int j = 0; j < NCOL; ++j) {
-                    const int c0 = (tid & ~31) + j * nthr;             // first column of this warp's j-th group
-                    if (c0 >= g.wo) continue;                          // warp-uniform
-                    uint8_t* o = orow + (size_t)c0 * 3;
-                    const int n = min(32, g.wo - c0);
-                    if (n == 32 && (reinterpret_cast<uintptr_t>(o) & 3) == 0) { if (lane < 24) st_stream4(o + 4 * lane, line[j * 24 + lane]); }
-                    else for (int bb = lane; bb < 3 * n; bb += 32) o[bb] = lb[j * 96 + bb];
+                    for (int j = 0; j < NCOL; ++j)
+                        if (lane < 24) st_stream4(orow + (size_t)((tid & ~31) + j * nthr) * 3 + 4 * lane, line[j * 24 + lane]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < NCOL; ++j) {
+                        const int c0 = (tid & ~31) + j * nthr;             // first column of this warp's j-th group
+                        if (c0 >= g.wo) continue;                          // warp-uniform
+                        uint8_t* o = orow + (size_t)c0 * 3;
+                        const int n = min(32, g.wo - c0);
+                        if (n == 32 && (reinterpret_cast<uintptr_t>(o) & 3) == 0) { if (lane < 24) st_stream4(o + 4 * lane, line[j * 24 + lane]); }
+                        else for (int bb = lane; bb < 3 * n; bb += 32) o[bb] = lb[j * 96 + bb];
+                    }
                 }
                 __syncwarp();
             } else {
@@ -250,7 +219,7 @@ resize_linear_u8c3_pipe_kernel(const uint8_t* __restrict__ src, void* __restrict
                     if (c0 >= g.wo) continue;                          // warp-uniform
                     float r[3];
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) r[k] = lut[k * 256 + (((H0[j][k] * cy0 + H1[j][k] * cy1) >> 22) & 0xff)];
+                    for (int k = 0; k < 3; ++k) r[k] = lut[k * 256 + (((Hu[j][k] * cy0 + Hl[j][k] * cy1) >> 22) & 0xff)];
                     if (OUT == kRpOutF32CHW) {
                         float* o = dstf + (size_t)frame * 3 * plane + prow + col;
                         if (col < g.wo) { st_stream4f(o, r[0]); st_stream4f(o + plane, r[1]); st_stream4f(o + 2 * plane, r[2]); }
@@ -269,10 +238,40 @@ resize_linear_u8c3_pipe_kernel(const uint8_t* __restrict__ src, void* __restrict
                     }
                 }
             }
+        };
+        for (int ty = 0; ty < th; ++ty, orow += (size_t)g.wo * 3) {
+            const int sy = lds_s32(sy_s + 4 * (dy0 + ty));
+            const int cy = lds_s32(cy_s + 4 * (dy0 + ty));
+            const int cy0 = (short)(cy & 0xffff), cy1 = cy >> 16;
+            if (kPoint) {  // all weights are (2048, 0) x (2048, 0): (p << 22) >> 22 = p, signed or not
+                const uint32_t upper = buf + (unsigned)lds_s32(slot_s + 4 * (dy0 + ty)) * row_bytes;
+                uint8_t* lbp = reinterpret_cast<uint8_t*>(line);
+#pragma unroll
+                for (int j = 0; j < NCOL; ++j) {
+                    uint32_t w0, w1;
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(upper + aw[j]));
+                    asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(upper + aw[j]));
+                    const uint32_t px = __funnelshift_r(w0, w1, sh[j]);
+                    lbp[j * 96 + 3 * lane] = (uint8_t)px; lbp[j * 96 + 3 * lane + 1] = (uint8_t)(px >> 8); lbp[j * 96 + 3 * lane + 2] = (uint8_t)(px >> 16);
+                }
+                blend_store(Ha, Hb, cy0, cy1, ty, orow);
+                continue;
+            }
+            // staged address of the upper tap row; the lower one follows it (band: slot = row - first row; row list: the slot table).
+            // A lower tap row of weight 0 is not filtered (row list: not even staged): whatever its register set holds is multiplied by 0.
+            const uint32_t upper = kBand ? buf + (unsigned)(sy - y_first) * row_bytes : buf + (unsigned)lds_s32(slot_s + 4 * (dy0 + ty)) * row_bytes;
+            if ((sy & 1) == 0) {
+                if (have_a != sy) { hrow(upper, Ha); have_a = sy; }
+                if (cy1 != 0 && have_b != sy + 1) { hrow(upper + row_bytes, Hb); have_b = sy + 1; }
+                blend_store(Ha, Hb, cy0, cy1, ty, orow);
+            } else {
+                if (have_b != sy) { hrow(upper, Hb); have_b = sy; }
+                if (cy1 != 0 && have_a != sy + 1) { hrow(upper + row_bytes, Ha); have_a = sy + 1; }
+                blend_store(Hb, Ha, cy0, cy1, ty, orow);
+            }
         }
         __syncthreads();   // all reads of stage b done -> it may be refilled by the next iteration's issue
     }
-    (void)n_last;
 }
 
 }  // namespace vacv
