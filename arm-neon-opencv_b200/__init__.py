@@ -13,7 +13,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvacv_cuda.so")
+LIB_PATH = os.environ.get("VACV_B200_LIB") or os.path.join(_HERE, "libvacv_cuda.so")   # override: A/B runs of two builds on one box
 
 FP32, FP16, INT8, FP64 = 0, 1, 2, 3
 BF16 = 16   # extension: output type of the fused pipeline only

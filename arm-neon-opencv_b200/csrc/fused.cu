@@ -306,26 +306,33 @@ static int host_linear_index(int d, double scale, int n_in) {
     return sx;
 }
 
-template <int FMT, typename OutT, bool kDense = false>
+template <int FMT, typename OutT, bool kDense = false, int RIGHT = -1>
 static const void* pipe_kernel_ncol(int ncol) {
     switch (ncol) {
-        case 1: return (const void*)nv_resize_normalize_chw_pipe_kernel<FMT, OutT, 1, kDense>;
-        case 2: return (const void*)nv_resize_normalize_chw_pipe_kernel<FMT, OutT, 2, kDense>;
-        case 3: return (const void*)nv_resize_normalize_chw_pipe_kernel<FMT, OutT, 3, kDense>;
-        default: return (const void*)nv_resize_normalize_chw_pipe_kernel<FMT, OutT, 4, kDense>;
+        case 1: return (const void*)nv_resize_normalize_chw_pipe_kernel<FMT, OutT, 1, kDense, RIGHT>;
+        case 2: return (const void*)nv_resize_normalize_chw_pipe_kernel<FMT, OutT, 2, kDense, RIGHT>;
+        case 3: return (const void*)nv_resize_normalize_chw_pipe_kernel<FMT, OutT, 3, kDense, RIGHT>;
+        default: return (const void*)nv_resize_normalize_chw_pipe_kernel<FMT, OutT, 4, kDense, RIGHT>;
     }
 }
-template <int FMT>
+template <int FMT, int RIGHT>
 static const void* pipe_kernel_pairs(int ncol) {   // fp16 column pairs: even column counts only
-    return ncol <= 2 ? (const void*)nv_resize_normalize_chw_pipe_kernel<FMT, __half2, 2, false>
-                     : (const void*)nv_resize_normalize_chw_pipe_kernel<FMT, __half2, 4, false>;
+    return ncol <= 2 ? (const void*)nv_resize_normalize_chw_pipe_kernel<FMT, __half2, 2, false, RIGHT>
+                     : (const void*)nv_resize_normalize_chw_pipe_kernel<FMT, __half2, 4, false, RIGHT>;
 }
-static const void* pipe_kernel_for(int fmt, bool half_out, bool pairs, bool dense, int ncol) {
-    if (half_out && pairs) return fmt == kFmtVU ? pipe_kernel_pairs<kFmtVU>(ncol) : fmt == kFmtUV ? pipe_kernel_pairs<kFmtUV>(ncol) : pipe_kernel_pairs<kFmtPlanar>(ncol);
-    if (dense && !half_out && fmt != kFmtPlanar)   // the reference's own case keeps its dedicated instantiation
-        return fmt == kFmtVU ? pipe_kernel_ncol<kFmtVU, float, true>(ncol) : pipe_kernel_ncol<kFmtUV, float, true>(ncol);
+static const void* pipe_kernel_for(int fmt, bool half_out, bool pairs, bool dense, int ncol, bool any_right) {
+    if (half_out && pairs) {
+        if (any_right) return fmt == kFmtVU ? pipe_kernel_pairs<kFmtVU, 1>(ncol) : fmt == kFmtUV ? pipe_kernel_pairs<kFmtUV, 1>(ncol) : pipe_kernel_pairs<kFmtPlanar, 1>(ncol);
+        return fmt == kFmtVU ? pipe_kernel_pairs<kFmtVU, 0>(ncol) : fmt == kFmtUV ? pipe_kernel_pairs<kFmtUV, 0>(ncol) : pipe_kernel_pairs<kFmtPlanar, 0>(ncol);
+    }
+    if (dense && !half_out && fmt != kFmtPlanar) {   // the reference's own case keeps its dedicated instantiations: one per tap rule, so
+        // that the path a launch never takes does not shape the register allocation and schedule of the one it does
+        if (any_right) return fmt == kFmtVU ? pipe_kernel_ncol<kFmtVU, float, true, 1>(ncol) : pipe_kernel_ncol<kFmtUV, float, true, 1>(ncol);
+        return fmt == kFmtVU ? pipe_kernel_ncol<kFmtVU, float, true, 0>(ncol) : pipe_kernel_ncol<kFmtUV, float, true, 0>(ncol);
+    }
     if (half_out) return fmt == kFmtVU ? pipe_kernel_ncol<kFmtVU, __half>(ncol) : fmt == kFmtUV ? pipe_kernel_ncol<kFmtUV, __half>(ncol) : pipe_kernel_ncol<kFmtPlanar, __half>(ncol);
-    return fmt == kFmtVU ? pipe_kernel_ncol<kFmtVU, float>(ncol) : fmt == kFmtUV ? pipe_kernel_ncol<kFmtUV, float>(ncol) : pipe_kernel_ncol<kFmtPlanar, float>(ncol);
+    if (any_right) return fmt == kFmtVU ? pipe_kernel_ncol<kFmtVU, float, false, 1>(ncol) : fmt == kFmtUV ? pipe_kernel_ncol<kFmtUV, float, false, 1>(ncol) : pipe_kernel_ncol<kFmtPlanar, float, false, 1>(ncol);
+    return fmt == kFmtVU ? pipe_kernel_ncol<kFmtVU, float, false, 0>(ncol) : fmt == kFmtUV ? pipe_kernel_ncol<kFmtUV, float, false, 0>(ncol) : pipe_kernel_ncol<kFmtPlanar, float, false, 0>(ncol);
 }
 
 // Source description resolved from a vacv_yuv_layout (or the dense NV12/NV21 default).
@@ -431,7 +438,7 @@ static int build_pipe_plan(PipePlan& plan) {
     const int threads = std::min(ncol == 1 ? 640 : kPipeThreads, ((w_out + ncol - 1) / ncol + 31) & ~31);
     const bool dense = y.y_pitch == w && y.c_pitch == w && y.c_off == (size_t)w * h && y.frame_stride == (size_t)w * h * 3 / 2 &&
                        cv.w == w_out && cv.h == h_out;
-    const void* kern = pipe_kernel_for(y.fmt, half_out, pairs, dense, ncol);
+    const void* kern = pipe_kernel_for(y.fmt, half_out, pairs, dense, ncol, any_right);
     // the opt-in limit, not this shape's size: plans of other host threads for the same kernel must stay launchable
     int optin = 0;
     cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, plan.device);

@@ -209,6 +209,70 @@ __device__ __forceinline__ void compute_tile(uint32_t ybuf, uint32_t cbuf, uint3
     }
 }
 
+// Second version of compute_tile: two register sets by source-row parity instead of upper / lower sets.
+template <int FMT, typename OutT, bool kRightTap, int NCOL>
+__device__ __forceinline__ void compute_tile_parity(uint32_t ybuf, uint32_t cbuf, uint32_t tab_sy, uint32_t tab_cy, uint32_t lut,
+                                             const ColState (&col)[NCOL], int dy0, int th, int y_pitch, int c_pitch, int vstage_off,
+                                             char* (&out)[NCOL], size_t row_bytes, size_t plane_bytes) {
+    const int y_first = lds_s32(tab_sy + 4 * dy0), c_first = y_first >> 1;
+    // Horizontal sums live in two register sets: Ha holds an EVEN source row, Hb an ODD one (have_a / have_b: which).  An output row
+    // blends row sy with row sy + 1, one of each parity; when the next output row starts on the previous lower row, that row's sums
+    // already sit where its parity puts them -- nothing is copied.  Used where it measured faster than the first version (compute_tile,
+    // upper / lower sets with a copy when rows are shared) on one box, 1080p -> 640x640 x256, each tap rule in its own kernel:
+    // every launch with right taps (608x608 0.395 -> 0.371 ms, 720p source 0.333 -> 0.317, 416x416 0.244 -> 0.236) and planar
+    // chroma without (I420 0.379 -> 0.365); NV12 without right taps keeps the first version (dense 0.351 vs 0.376, pitch 2048
+    // 0.380 vs 0.387, letterbox 0.381 vs 0.396).
+    int Ha[NCOL][3] = {}, Hb[NCOL][3] = {};
+    ChromaTerms ta[NCOL], tb[NCOL];
+    int have_a = -2, have_b = -2, have_c = -1;
+    auto row = [&](int r, int (&H)[NCOL][3]) {
+        const int cr = r >> 1;
+        if (cr != have_c) {   // all threads walk the same rows: no divergence
+            const uint32_t crow = cbuf + (cr - c_first) * c_pitch;
+#pragma unroll
+            for (int j = 0; j < NCOL; ++j) {
+                ta[j] = terms_at<FMT, kRightTap>(crow + col[j].ca, vstage_off);
+                if (kRightTap) tb[j] = terms_at<FMT, true>(crow + col[j].cb, vstage_off);
+            }
+            have_c = cr;
+        }
+        const uint32_t yrow = ybuf + (r - y_first) * y_pitch;
+#pragma unroll
+        for (int j = 0; j < NCOL; ++j) hrow_cached<kRightTap>(yrow + col[j].yo, col[j], ta[j], tb[j], H[j]);
+    };
+    auto emit = [&](const int (&Hu)[NCOL][3], const int (&Hl)[NCOL][3], int cy0, int cy1) {   // Hu / Hl: sums of the upper / lower tap row
+        constexpr int kCols = OutOps<OutT>::kCols;
+#pragma unroll
+        for (int j = 0; j < NCOL; j += kCols) {
+            char* o = out[j];
+            constexpr int j1 = kCols == 2 ? 1 : 0;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const unsigned v = (unsigned)(Hu[j][k] * cy0 + Hl[j][k] * cy1) >> 22;   // the u8 the unfused chain stores
+                const unsigned v1 = kCols == 2 ? (unsigned)(Hu[j + j1][k] * cy0 + Hl[j + j1][k] * cy1) >> 22 : 0u;
+                OutOps<OutT>::copy(o, lut, k, v, v1);
+                o += plane_bytes;
+            }
+            out[j] += row_bytes;
+        }
+    };
+    for (int ty = 0; ty < th; ++ty) {
+        const int sy = lds_s32(tab_sy + 4 * (dy0 + ty));
+        const int cy = lds_s32(tab_cy + 4 * (dy0 + ty));
+        const int cy0 = cy & 0xffff, cy1 = cy >> 16;   // both in [0, 2048]
+        // a lower tap row of weight 0 is not filtered: whatever its register set holds is multiplied by 0
+        if ((sy & 1) == 0) {
+            if (have_a != sy) { row(sy, Ha); have_a = sy; }
+            if (cy1 != 0 && have_b != sy + 1) { row(sy + 1, Hb); have_b = sy + 1; }
+            emit(Ha, Hb, cy0, cy1);
+        } else {
+            if (have_b != sy) { row(sy, Hb); have_b = sy; }
+            if (cy1 != 0 && have_a != sy + 1) { row(sy + 1, Ha); have_a = sy + 1; }
+            emit(Hb, Ha, cy0, cy1);
+        }
+    }
+}
+
 // Packed variant for an even number of columns per thread: columns are handled in PAIRS on 16-bit lanes.
 //   * add + clamp of a luma sample and a chroma term for two columns = one DPX VIADDMNMX.S16x2.RELU (was two VIADDMNMX),
 //   * the horizontal blend pa*cx0 + pb*cx1 = one IDP.2A on the byte pair (pa, pb) and the packed 16-bit weights (was two
@@ -223,15 +287,16 @@ __device__ __forceinline__ void compute_tile_packed(uint32_t ybuf, uint32_t cbuf
     constexpr int kCols = OutOps<OutT>::kCols;
     const int y_first = lds_s32(tab_sy + 4 * dy0), c_first = y_first >> 1;
     // row state: kRightTap: horizontally blended sums per column; else: clamped bytes of a column pair [p_j 0 p_j+1 0] per channel
-    int H0[kRightTap ? NCOL : 1][3], H1[kRightTap ? NCOL : 1][3];
-    uint32_t R0[kRightTap ? 1 : P][3], R1[kRightTap ? 1 : P][3];
+    // two register sets by source-row parity (see compute_tile): set a holds an even row, set b an odd one
+    int Ha[kRightTap ? NCOL : 1][3] = {}, Hb[kRightTap ? NCOL : 1][3] = {};
+    uint32_t Ra[kRightTap ? 1 : P][3] = {}, Rb[kRightTap ? 1 : P][3] = {};
     uint32_t ta2[P][3], tb2[kRightTap ? P : 1][3];   // chroma terms (ba, -ga, ra) of the pair's two columns, one per 16-bit lane
     uint32_t cxp[kRightTap ? NCOL : 1];
     if (kRightTap) {
 #pragma unroll
         for (int j = 0; j < NCOL; ++j) cxp[j] = (uint32_t)col[j].cx0 | ((uint32_t)col[j].cx1 << 16);
     }
-    int have = -2, have_c = -1;
+    int have_a = -2, have_b = -2, have_c = -1;
     auto pack_terms = [](const ChromaTerms& a, const ChromaTerms& b, uint32_t (&t)[3]) {
         t[0] = __byte_perm((uint32_t)a.ba, (uint32_t)b.ba, 0x5410);
         t[1] = __byte_perm((uint32_t)(-a.ga), (uint32_t)(-b.ga), 0x5410);
@@ -267,25 +332,10 @@ __device__ __forceinline__ void compute_tile_packed(uint32_t ybuf, uint32_t cbuf
             }
         }
     };
-    for (int ty = 0; ty < th; ++ty) {
-        const int sy = lds_s32(tab_sy + 4 * (dy0 + ty));
-        const uint32_t cy = (uint32_t)lds_s32(tab_cy + 4 * (dy0 + ty));   // cy0 | cy1 << 16, both in [0, 2048]
+    // u = upper tap row's set, l = lower tap row's; cy = cy0 | cy1 << 16, both in [0, 2048]
+    auto emit = [&](const int (&Hu)[kRightTap ? NCOL : 1][3], const int (&Hl)[kRightTap ? NCOL : 1][3], const uint32_t (&Ru)[kRightTap ? 1 : P][3],
+                    const uint32_t (&Rl)[kRightTap ? 1 : P][3], uint32_t cy) {
         const int cy0 = cy & 0xffff, cy1 = cy >> 16;
-        if (sy == have) {
-            if (kRightTap) {
-#pragma unroll
-                for (int j = 0; j < NCOL; ++j) { H0[j][0] = H1[j][0]; H0[j][1] = H1[j][1]; H0[j][2] = H1[j][2]; }
-            } else {
-#pragma unroll
-                for (int p = 0; p < P; ++p) { R0[p][0] = R1[p][0]; R0[p][1] = R1[p][1]; R0[p][2] = R1[p][2]; }
-            }
-        } else if (sy + 1 != have) {
-            row(sy, H0, R0);
-        }
-        if (sy + 1 != have) {
-            row(sy + 1, H1, R1);
-            have = sy + 1;
-        }
 #pragma unroll
         for (int p = 0; p < P; ++p) {
             char* o0 = out[2 * p];
@@ -294,10 +344,10 @@ __device__ __forceinline__ void compute_tile_packed(uint32_t ybuf, uint32_t cbuf
             for (int k = 0; k < 3; ++k) {
                 unsigned v0, v1;   // the u8 the unfused chain stores
                 if (kRightTap) {
-                    v0 = (unsigned)(H0[2 * p][k] * cy0 + H1[2 * p][k] * cy1) >> 22;
-                    v1 = (unsigned)(H0[2 * p + 1][k] * cy0 + H1[2 * p + 1][k] * cy1) >> 22;
+                    v0 = (unsigned)(Hu[2 * p][k] * cy0 + Hl[2 * p][k] * cy1) >> 22;
+                    v1 = (unsigned)(Hu[2 * p + 1][k] * cy0 + Hl[2 * p + 1][k] * cy1) >> 22;
                 } else {
-                    const uint32_t m = __byte_perm(R0[p][k], R1[p][k], 0x6240);   // [p0_j p1_j p0_j+1 p1_j+1]
+                    const uint32_t m = __byte_perm(Ru[p][k], Rl[p][k], 0x6240);   // [p0_j p1_j p0_j+1 p1_j+1]
                     v0 = __dp2a_lo(cy, m, 0u) >> 11;
                     v1 = __dp2a_hi(cy, m, 0u) >> 11;
                 }
@@ -312,6 +362,20 @@ __device__ __forceinline__ void compute_tile_packed(uint32_t ybuf, uint32_t cbuf
             }
             out[2 * p] += row_bytes;
             if (kCols != 2) out[2 * p + 1] += row_bytes;
+        }
+    };
+    for (int ty = 0; ty < th; ++ty) {
+        const int sy = lds_s32(tab_sy + 4 * (dy0 + ty));
+        const uint32_t cy = (uint32_t)lds_s32(tab_cy + 4 * (dy0 + ty));
+        const bool lower = (cy >> 16) != 0;           // a lower tap row of weight 0 is not filtered: its set is multiplied by 0
+        if ((sy & 1) == 0) {
+            if (have_a != sy) { row(sy, Ha, Ra); have_a = sy; }
+            if (lower && have_b != sy + 1) { row(sy + 1, Hb, Rb); have_b = sy + 1; }
+            emit(Ha, Hb, Ra, Rb, cy);
+        } else {
+            if (have_b != sy) { row(sy, Hb, Rb); have_b = sy; }
+            if (lower && have_a != sy + 1) { row(sy + 1, Ha, Ra); have_a = sy + 1; }
+            emit(Hb, Ha, Rb, Ra, cy);
         }
     }
 }
@@ -339,7 +403,10 @@ __device__ __noinline__ void issue_band_rows(const PipeGeom& g, const uint8_t* f
 }
 
 // kDense: the reference's own layout (tensor.cpp:524: no pitch; chroma right after luma) -- one pitch register, constants folded.
-template <int FMT, typename OutT, int NCOL, bool kDense>
+// RIGHT: -1 = whether any right tap has weight is found out at run time (both tile loops in the kernel), 0 / 1 = known to the launcher:
+// one tap rule per kernel, so that the loop a launch never takes does not shape the register allocation and schedule of the one it
+// does (config 2, same box: 0.364 -> 0.351 ms).
+template <int FMT, typename OutT, int NCOL, bool kDense, int RIGHT = -1>
 __global__ void __launch_bounds__(NCOL == 1 ? 640 : kPipeThreads, NCOL <= 2 ? 2 : 1)
 nv_resize_normalize_chw_pipe_kernel(const uint8_t* __restrict__ src, OutT* __restrict__ dst, PipeGeom g,
                                     const float* __restrict__ mean, const float* __restrict__ stddev) {
@@ -425,7 +492,7 @@ nv_resize_normalize_chw_pipe_kernel(const uint8_t* __restrict__ src, OutT* __res
         else if (tid == 0) issue(tile, 0);
     }
     __syncthreads();
-    const bool right = s_any_right != 0;
+    const bool right = RIGHT < 0 ? s_any_right != 0 : RIGHT == 1;
 
     for (int it = 0; tile < g.total_tiles; tile += gridDim.x, ++it) {
         const int b = it & 1;
@@ -450,7 +517,8 @@ nv_resize_normalize_chw_pipe_kernel(const uint8_t* __restrict__ src, OutT* __res
             if (right) compute_tile_packed<FMT, OutT, true, NCOL>(ybuf, cbuf, sy_s, cy_s, lut_s, col, dy0, th, sy_pitch, sc_pitch, g.vstage_off, out, row_bytes, plane_bytes);
             else compute_tile_packed<FMT, OutT, false, NCOL>(ybuf, cbuf, sy_s, cy_s, lut_s, col, dy0, th, sy_pitch, sc_pitch, g.vstage_off, out, row_bytes, plane_bytes);
         } else {
-            if (right) compute_tile<FMT, OutT, true, NCOL>(ybuf, cbuf, sy_s, cy_s, lut_s, col, dy0, th, sy_pitch, sc_pitch, g.vstage_off, out, row_bytes, plane_bytes);
+            if (right) compute_tile_parity<FMT, OutT, true, NCOL>(ybuf, cbuf, sy_s, cy_s, lut_s, col, dy0, th, sy_pitch, sc_pitch, g.vstage_off, out, row_bytes, plane_bytes);
+            else if (FMT == kFmtPlanar) compute_tile_parity<FMT, OutT, false, NCOL>(ybuf, cbuf, sy_s, cy_s, lut_s, col, dy0, th, sy_pitch, sc_pitch, g.vstage_off, out, row_bytes, plane_bytes);
             else compute_tile<FMT, OutT, false, NCOL>(ybuf, cbuf, sy_s, cy_s, lut_s, col, dy0, th, sy_pitch, sc_pitch, g.vstage_off, out, row_bytes, plane_bytes);
         }
         __syncthreads();   // all reads of stage b done -> it may be refilled by the next iteration's issue
