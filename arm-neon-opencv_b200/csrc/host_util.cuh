@@ -20,6 +20,7 @@ enum Knob {
     kKnobCubic3Roll,       // VACV_CUBIC3=roll          shared-memory ring kernel instead of the column walker
     kKnobCubicV,           // VACV_CUBIC_V              u8 bicubic kernel variant (0 = default)
     kKnobPipeRows,         // VACV_PIPE_ROWS            fused pipeline on padded surfaces: one bulk copy per row instead of whole bands (padding included)
+    kKnobStreamQpt,        // VACV_STREAM_QPT           16-byte groups per thread of the streaming kernels' grids (0 = default)
     kKnobCount
 };
 int knob(Knob k);

@@ -203,24 +203,38 @@ __global__ void layout_generic_kernel(const T* __restrict__ src, T* __restrict__
 // =====================================================================================================
 // a4 dtype_change (src/common/tensor.cpp:459-502)
 __global__ void __launch_bounds__(256) u8_to_f32_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, size_t n4) {
-    // 4 elements per thread: 32-bit load (128 B / warp), 128-bit store (512 B / warp)
+    // 4 elements per thread and step: 32-bit load (128 B / warp), 128-bit store (512 B / warp); kU independent loads in flight
+    // before the first store (with one load per iteration the loop waits out a DRAM latency per 16 output bytes)
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (; i < n4; i += stride) {
-        uint32_t v = ld_stream4(src + 4 * i);
-        st_stream16f(dst + 4 * i, make_float4((float)(v & 0xff), (float)((v >> 8) & 0xff), (float)((v >> 16) & 0xff),
-                                              (float)(v >> 24)));
+    constexpr int kU = 4;
+    for (; i < n4; i += kU * stride) {
+        uint32_t v[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) v[u] = i + u * stride < n4 ? ld_stream4(src + 4 * (i + u * stride)) : 0u;
+#pragma unroll
+        for (int u = 0; u < kU; ++u)
+            if (i + u * stride < n4)
+                st_stream16f(dst + 4 * (i + u * stride), make_float4((float)(v[u] & 0xff), (float)((v[u] >> 8) & 0xff), (float)((v[u] >> 16) & 0xff),
+                                                                     (float)(v[u] >> 24)));
     }
 }
 __global__ void __launch_bounds__(256) f32_to_u8_kernel(const float* __restrict__ src, uint8_t* __restrict__ dst, size_t n4) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (; i < n4; i += stride) {
-        uint4 r = ld_stream16(src + 4 * i);
-        // static_cast<char>(float) on x86 = cvttss2si then low byte (tensor.cpp:488-492)
-        uint32_t b0 = (uint32_t)(int)__uint_as_float(r.x) & 0xff, b1 = (uint32_t)(int)__uint_as_float(r.y) & 0xff;
-        uint32_t b2 = (uint32_t)(int)__uint_as_float(r.z) & 0xff, b3 = (uint32_t)(int)__uint_as_float(r.w) & 0xff;
-        st_stream4(dst + 4 * i, b0 | (b1 << 8) | (b2 << 16) | (b3 << 24));
+    constexpr int kU = 4;
+    for (; i < n4; i += kU * stride) {
+        uint4 r[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) r[u] = i + u * stride < n4 ? ld_stream16(src + 4 * (i + u * stride)) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            if (i + u * stride >= n4) continue;
+            // static_cast<char>(float) on x86 = cvttss2si then low byte (tensor.cpp:488-492)
+            uint32_t b0 = (uint32_t)(int)__uint_as_float(r[u].x) & 0xff, b1 = (uint32_t)(int)__uint_as_float(r[u].y) & 0xff;
+            uint32_t b2 = (uint32_t)(int)__uint_as_float(r[u].z) & 0xff, b3 = (uint32_t)(int)__uint_as_float(r[u].w) & 0xff;
+            st_stream4(dst + 4 * (i + u * stride), b0 | (b1 << 8) | (b2 << 16) | (b3 << 24));
+        }
     }
 }
 __global__ void dtype_tail_kernel(const void* src, void* dst, size_t begin, size_t n, int to_f32) {
@@ -490,6 +504,15 @@ extern "C" int vacv_cuda_layout_change(const void* src, void* dst, int batch, in
     return check_launch("layout_change");
 }
 
+// CTAs (of 256 threads) for a streaming kernel over n4 16-byte groups: MANY SHORT CTAs.  Round 1 sized these grids as ~16 resident CTAs per
+// SM grid-striding over everything (19 CTAs per 4K frame, 2 432 in all for config 5's apply pass); measured on the same box, u8 HWC
+// normalize 4K x128: 19 CTAs per frame 2.958 ms, 152: 2.660, 1216: 2.509 (6.35 TB/s, 0.97 of the copy peak), 3037: 2.52 -- a grid of two
+// long waves leaves the machine half empty at the end and keeps every CTA of a frame in lockstep on the same DRAM pages.
+static unsigned stream_ctas(size_t n4) {
+    const int qpt = knob(kKnobStreamQpt) > 0 ? knob(kKnobStreamQpt) : 8;   // 16-byte groups per thread (sweep 2..256: 8 is the best or within 1 % of it for every kernel)
+    return (unsigned)std::max<size_t>(1, std::min<size_t>((n4 + (size_t)256 * qpt - 1) / ((size_t)256 * qpt), 0x7fffffff));
+}
+
 extern "C" int vacv_cuda_dtype_change(const void* src, void* dst, size_t n, int from_dtype, int to_dtype, void* stream) {
     VACV_REQUIRE(src && dst, "dtype_change: null pointer");
     VACV_REQUIRE(n > 0, "dtype_change: empty");
@@ -506,8 +529,7 @@ extern "C" int vacv_cuda_dtype_change(const void* src, void* dst, size_t n, int 
     const bool aligned = (((uintptr_t)src | (uintptr_t)dst) & 15) == 0;
     const size_t n4 = aligned ? n / 4 : 0;
     if (n4) {
-        const int sms = current_sm_count();
-        const unsigned blocks = (unsigned)min((size_t)sms * 16, (size_t)ceil_div(n4, 256));
+        const unsigned blocks = stream_ctas(n4);
         if (to_f32) u8_to_f32_kernel<<<blocks, 256, 0, s>>>((const uint8_t*)src, (float*)dst, n4);
         else f32_to_u8_kernel<<<blocks, 256, 0, s>>>((const float*)src, (uint8_t*)dst, n4);
     }
@@ -537,7 +559,7 @@ extern "C" int vacv_cuda_normalize(const void* src, float* dst, int batch, int w
     if (layout == VACV_NHWC && c > 1) {
         if (c > kNormMaxC) return set_error(VACV_ERR_UNSUPPORTED, "normalize: HWC supports c <= %d", kNormMaxC);
         VACV_REQUIRE((g.per_frame % 4) == 0 || batch == 1, "normalize: HWC batch needs w*h*c %% 4 == 0");
-        const unsigned ctas = (unsigned)max(1u, min(ceil_div(g.per_frame / 4, 256 * 8), (unsigned)(sms * 16 / min(batch, sms * 16) + 1)));
+        const unsigned ctas = stream_ctas(g.per_frame / 4);
         for (int f0 = 0; f0 < batch; f0 += 65535) {
             dim3 grid(ctas, min(batch - f0, 65535));
             const void* sp = (const uint8_t*)src + (size_t)f0 * g.per_frame * es;
@@ -551,7 +573,7 @@ extern "C" int vacv_cuda_normalize(const void* src, float* dst, int batch, int w
     } else {
         const long long planes = (long long)batch * c;
         const int chunk = 65535 / c * c;
-        const unsigned ctas = (unsigned)max(1u, min(ceil_div(g.wh / 4 + 1, 256 * 8), (unsigned)(sms * 16 / (unsigned)min(planes, (long long)sms * 16) + 1)));
+        const unsigned ctas = stream_ctas(g.wh / 4 + 1);
         for (long long p0 = 0; p0 < planes; p0 += chunk) {
             dim3 grid(ctas, (unsigned)min((long long)chunk, planes - p0));
             const void* sp = (const uint8_t*)src + (size_t)p0 * g.wh * es;

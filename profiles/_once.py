@@ -29,6 +29,10 @@ elif case == "sums":
     src = B.rand_u8(128, 2160, 3840, 3)
     sums = torch.zeros((1, 3, 2), dtype=torch.int64, device="cuda")
     fn = lambda: vacv.sums_u8(src, vacv.NHWC, False, sums)
+elif case == "normu8":
+    src = B.rand_u8(128, 2160, 3840, 3)
+    out = torch.empty((128, 2160, 3840, 3), dtype=torch.float32, device="cuda")
+    fn = lambda: vacv.normalize(src, vacv.NHWC, mean, std, out=out)
 elif case == "dtype":
     src = B.rand_u8(128, 1080, 1920, 3)
     fn = lambda: vacv.dtype_change(src, vacv.FP32)
