@@ -115,8 +115,12 @@ struct PeriodShape {
     static constexpr int kWarpRow = 32 * NV;                             // bytes one warp produces per output row
     static constexpr int kWarpSpan = 32 * LS;                            // source bytes between the windows of neighbouring warps
     static constexpr int kLaneOff = 12;                                  // ring offset of lane 0's window word 0 (the ring row starts 16 bytes early)
-    static constexpr int kNeed = (LS * 31 + kLaneOff + 4 * NW + 15) & ~15;   // ring bytes of one source row
-    static_assert(LS % 4 == 0, "lane stride must keep the byte alignment lane-invariant");
+    // LS % 4 == 2 (3 : 2 with two periods per thread: 18 bytes): the window of an odd lane starts two bytes later inside its word; odd
+    // lanes read from the word before and every lane funnel-shifts its NW + 1 words by 0 or 16 bits -- after that the alignment is
+    // lane-invariant again
+    static constexpr bool kRealign = LS % 4 != 0;
+    static constexpr int kNeed = (LS * 31 + kLaneOff + 4 * (NW + (kRealign ? 1 : 0)) + 15) & ~15;   // ring bytes of one source row
+    static_assert(LS % 2 == 0, "lane stride must be even");
     static_assert(NV % 4 == 2 || NV % 4 == 0, "output bytes per thread must be even");
     static_assert((32 * NV) % 16 == 0 && (32 * LS) % 16 == 0, "warp spans must stay 16-byte aligned");
 };
@@ -159,7 +163,9 @@ __global__ void __maxnreg__(MAXREG) resize_cubic3_period_kernel(const uint8_t* _
     const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
     const uint32_t ring_dst = __shfl_sync(0xffffffffu, ring_s - (uint32_t)span0, 0) + (uint32_t)lo;
     const uint32_t ubars = __shfl_sync(0xffffffffu, bars, 0);
-    const uint32_t win_s = ring_s + (uint32_t)(LS * lane + S::kLaneOff);   // this lane's window word 0 in ring slot 0
+    // this lane's window word 0 in ring slot 0 (kRealign: odd lanes start at the word before, see PeriodShape)
+    const int realign_sh = S::kRealign && (lane & 1) ? 16 : 0;
+    const uint32_t win_s = ring_s + (uint32_t)(LS * lane + S::kLaneOff - (S::kRealign && (lane & 1) ? 2 : 0));
     const uint32_t rows_s = (uint32_t)__cvta_generic_to_shared(rows);
     const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
     const f32x2 one2 = g.one2, negzero2 = g.negzero2, magic2 = g.magic2, negmagic2 = g.negmagic2;
@@ -232,7 +238,13 @@ __global__ void __maxnreg__(MAXREG) resize_cubic3_period_kernel(const uint8_t* _
         pd::mbar_wait(ubars + 8 * slot, parity);
         const uint32_t p = win_s + slot * kPitch;
         uint32_t W[NW];
-        if constexpr (LS % 8 == 0 && S::kLaneOff % 8 == 4) {   // word 0 alone, then 8-byte aligned pairs
+        if constexpr (S::kRealign) {                   // NW + 1 words from the (lane-dependent) aligned address, shifted into place
+            uint32_t X[NW + 1];
+#pragma unroll
+            for (int i = 0; i <= NW; ++i) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(X[i]) : "r"(p + 4 * i));
+#pragma unroll
+            for (int i = 0; i < NW; ++i) W[i] = __funnelshift_r(X[i], X[i + 1], realign_sh);
+        } else if constexpr (LS % 8 == 0 && S::kLaneOff % 8 == 4) {   // word 0 alone, then 8-byte aligned pairs
             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(W[0]) : "r"(p));
 #pragma unroll
             for (int i = 1; i + 1 < NW; i += 2) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(W[i]), "=r"(W[i + 1]) : "r"(p + 4 * i));

@@ -825,8 +825,9 @@ static int launch_cubic3_walkn(const uint8_t* src, uint8_t* dst, int images, int
     if (v == 0 || v == 20) {                                                      // rational horizontal scales: periodic walker
         rc = launch_cubic3_period<4, 3, 2, 168>(src, dst, images, w, h, wo, ho, s);   // 4 : 3 (config 4: 2560 -> 1920)
         if (rc == 0) rc = launch_cubic3_period<2, 1, 4, 128>(src, dst, images, w, h, wo, ho, s);   // 2 : 1 (3840 -> 1920)
+        if (rc == 0) rc = launch_cubic3_period<3, 2, 2, 128>(src, dst, images, w, h, wo, ho, s);   // 3 : 2 (1920 -> 1280)
     }
-    if (v == 21) rc = launch_cubic3_period<4, 3, 2, 128>(src, dst, images, w, h, wo, ho, s);
+    if (v == 21) rc = launch_cubic3_period<4, 3, 2, 128>(src, dst, images, w, h, wo, ho, s);   // experiment: 128 registers, 16 warps per SM
     if (rc != 0) return rc;
     if (v == 6) rc = launch_cubic3_walkn_nc<4, 112, false>(src, dst, images, w, h, wo, ho, s);   // experiment: register cap, no tap prefetch
     if (v == 0 || v == 4) rc = launch_cubic3_walkn_nc<4>(src, dst, images, w, h, wo, ho, s);

@@ -170,7 +170,11 @@ def c4(iters):   # resize INTER_CUBIC u8 2560x1440 -> 1920x1080, batch 128
         report(f"   same, {name}", ms, b * 1920 * 1080, b * (2560 * 1440 * 3 + 1920 * 1080 * 3))
     big = rand_u8(64, 1080, 1920, 3)
     ms, _ = timeit(lambda: vacv.resize(big, vacv.NHWC, 1280, 720, vacv.INTER_CUBIC), iters)
-    report("   resize cubic u8 hwc 1920x1080->1280x720 x64", ms, 64 * 1280 * 720, 64 * (1920 * 1080 * 3 + 1280 * 720 * 3))
+    report("   resize cubic u8 hwc 1920x1080->1280x720 x64", ms, 64 * 1280 * 720, 64 * (1920 * 1080 * 3 + 1280 * 720 * 3), "3 : 2, periodic walker with realignment")
+    uhd = rand_u8(32, 2160, 3840, 3)
+    ms, _ = timeit(lambda: vacv.resize(uhd, vacv.NHWC, 1920, 1080, vacv.INTER_CUBIC), iters)
+    report("   resize cubic u8 hwc 3840x2160->1920x1080 x32", ms, 32 * 1920 * 1080, 32 * (3840 * 2160 * 3 + 1920 * 1080 * 3), "2 : 1, periodic walker")
+    del uhd
     srcf = src[:32].to(torch.float32)
     ms, _ = timeit(lambda: vacv.resize(srcf, vacv.NHWC, 1920, 1080, vacv.INTER_CUBIC), iters)
     report("   resize cubic f32 hwc 2560x1440->1920x1080 x32", ms, 32 * 1920 * 1080, 32 * 4 * (2560 * 1440 * 3 + 1920 * 1080 * 3))

@@ -12,7 +12,7 @@ import vacv_b200 as vacv  # noqa: E402
 from bench_ops import rand_u8, timeit  # noqa: E402
 
 variants = [tuple(int(x) for x in a.split(":")) for a in sys.argv[1:]] or [(0,)]   # CUBIC_V[:WALK_SEGS]
-shapes = [((2560, 1440), (1920, 1080), 128), ((1920, 1080), (1280, 720), 64), ((1920, 1080), (1000, 700), 32)][:int(os.environ.get("C4_SHAPES", "3"))]
+shapes = [((2560, 1440), (1920, 1080), 128), ((1920, 1080), (1280, 720), 64), ((1920, 1080), (1000, 700), 32), ((3840, 2160), (1920, 1080), 32)][:int(os.environ.get("C4_SHAPES", "4"))]
 for (w, h), (wo, ho), b in shapes:
     src = rand_u8(b, h, w, 3)
     vacv.lib.vacv_cuda_set_tuning(b"CUBIC_V", 1)

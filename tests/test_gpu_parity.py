@@ -336,9 +336,11 @@ def test_resize_cubic_u8_column_walker_generations(vacv, oracle, sz, variant):
 @pytest.mark.parametrize("sz", [((2560, 1440), (1920, 1080)), ((1040, 300), (780, 225)), ((1040, 90), (780, 131)), ((64, 40), (48, 30)),
                                 ((16, 16), (12, 12)), ((32, 9), (24, 20)), ((4096, 40), (3072, 30)), ((1280, 64), (960, 64)),
                                 ((3840, 2160), (1920, 1080)), ((2560, 100), (1280, 77)), ((64, 64), (32, 32)), ((32, 12), (16, 30)),
-                                ((1296, 50), (648, 25))])
+                                ((1296, 50), (648, 25)), ((1920, 1080), (1280, 720)), ((96, 40), (64, 30)), ((1536, 100), (1024, 77)),
+                                ((48, 9), (32, 20)), ((3072, 24), (2048, 16))])
 def test_resize_cubic_u8_periodic_walker(vacv, oracle, sz):
-    """u8 bicubic at rational horizontal scales (resize_cubic3_period.cuh: 4 : 3 with six adjacent columns per thread, 2 : 1 with four):
+    """u8 bicubic at rational horizontal scales (resize_cubic3_period.cuh: 4 : 3 with six adjacent columns per thread, 2 : 1 and 3 : 2 with four -- the latter with the
+    per-lane realignment stage):
     full and partial warp strips, a handful of threads per row, the clamped taps at both image edges, up- and down-scaling along y
     (the walk's two emit rules), several vertical segments, a batch of 3 -- against the oracle's OpenCV-2.4 rule and against the
     first-generation walker byte for byte."""
