@@ -829,7 +829,6 @@ static int launch_cubic3_walkn(const uint8_t* src, uint8_t* dst, int images, int
     }
     if (v == 21) rc = launch_cubic3_period<4, 3, 2, 128>(src, dst, images, w, h, wo, ho, s);   // experiment: 128 registers, 16 warps per SM
     if (rc != 0) return rc;
-    if (v == 6) rc = launch_cubic3_walkn_nc<4, 112, false>(src, dst, images, w, h, wo, ho, s);   // experiment: register cap, no tap prefetch
     if (v == 0 || v == 4) rc = launch_cubic3_walkn_nc<4>(src, dst, images, w, h, wo, ho, s);
     if (rc == 0 && v != 1) rc = launch_cubic3_walkn_nc<2>(src, dst, images, w, h, wo, ho, s);
     return rc;

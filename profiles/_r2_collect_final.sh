@@ -12,7 +12,7 @@ python bench_ops.py --workload ops2 --iters 30 --json gpurun_out/r2z_bench_ops.j
 python bench_ops.py --workload pcie --iters 20 --json gpurun_out/r2z_pcie.jsonl 2>&1 | tail -2 >> gpurun_out/r2z_bench_ops.txt
 cat gpurun_out/r2z_bench_ops.txt
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2z_launches_bench.csv python bench.py --steps 2 --warmup 3 --no-cpu --no-ceiling > gpurun_out/r2z_ncu_launch.log 2>&1
-for kc in "pipe_kernel:c2:fused_head" "period:c4:cubic_period_head" "u8c1_quad:linchw:linchw_quad" "u8c3_pipe:lin720:lin720_head" "u8c3_pipe:c1:c1_point_head"; do
+for kc in ${NCU_CASES:-"pipe_kernel:c2:fused_head" "period:c4:cubic_period_head" "u8c1_quad:linchw:linchw_quad" "u8c3_pipe:lin720:lin720_head" "u8c3_pipe:c1:c1_point_head" "normalize_u8_hwc:normu8:normalize_u8_head" "u8_to_f32:dtype:u8_to_f32_head"}; do
   k=${kc%%:*}; rest=${kc#*:}; c=${rest%%:*}; name=${rest#*:}
   timeout 300 ncu --set full --clock-control none --import-source on -k regex:$k -s 2 -c 1 -o gpurun_out/r2z_$name -f python profiles/_once.py $c > gpurun_out/r2z_ncu_$name.log 2>&1; tail -1 gpurun_out/r2z_ncu_$name.log | cut -c1-150
 done
