@@ -125,7 +125,7 @@ struct PeriodShape {
     static_assert((32 * NV) % 16 == 0 && (32 * LS) % 16 == 0, "warp spans must stay 16-byte aligned");
 };
 
-template <int P, int Q, int KP, bool kDown, int MAXREG>
+template <int P, int Q, int KP, bool kDown, int MAXREG, bool kVStat = false>
 __global__ void __maxnreg__(MAXREG) resize_cubic3_period_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, PeriodGeom g) {
     using S = PeriodShape<P, Q, KP>;
     constexpr int NCOL = S::NCOL, NPX = S::NPX, LS = S::LS, M0 = S::M0, NW = S::NW, NPW = S::NPW, NV = S::NV, NP = S::NP;
@@ -234,10 +234,10 @@ __global__ void __maxnreg__(MAXREG) resize_cubic3_period_kernel(const uint8_t* _
     asm volatile("ld.shared.s32 %0, [%1+32];" : "=r"(next_last) : "r"(entry));
 
     // horizontal pass of the walk step in ring slot `slot`: (value 2i, value 2i+1) of the thread's NV = 3 * NCOL output bytes, exact fp32
-    auto hfilter = [&](const uint32_t slot, uint32_t parity, f32x2 (&H)[NP]) {
+    // hload: wait for the row in ring slot `slot` and read this lane's window words; hcompute: the arithmetic on them
+    auto hload = [&](const uint32_t slot, uint32_t parity, uint32_t (&W)[NW]) {
         pd::mbar_wait(ubars + 8 * slot, parity);
         const uint32_t p = win_s + slot * kPitch;
-        uint32_t W[NW];
         if constexpr (S::kRealign) {                   // NW + 1 words from the (lane-dependent) aligned address, shifted into place
             uint32_t X[NW + 1];
 #pragma unroll
@@ -253,6 +253,8 @@ __global__ void __maxnreg__(MAXREG) resize_cubic3_period_kernel(const uint8_t* _
 #pragma unroll
             for (int i = 0; i < NW; ++i) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(W[i]) : "r"(p + 4 * i));
         }
+    };
+    auto hcompute = [&](const uint32_t (&W)[NW], f32x2 (&H)[NP]) {
         // de-interleave: channel k, pixels 4i .. 4i+3 of the window (pixels past the window repeat the last one: never used)
         uint32_t pl[3][NPW];
         pd::static_for<3>([&](auto ik) {
@@ -276,6 +278,11 @@ __global__ void __maxnreg__(MAXREG) resize_cubic3_period_kernel(const uint8_t* _
         });
 #pragma unroll
         for (int i = 0; i < NP; ++i) H[i] = fma2(pack2i(hv[2 * i], hv[2 * i + 1]), one2, negmagic2);
+    };
+    auto hfilter = [&](const uint32_t slot, uint32_t parity, f32x2 (&H)[NP]) {
+        uint32_t W[NW];
+        hload(slot, parity, W);
+        hcompute(W, H);
     };
 
     // ---- output: every row is staged in one of two kWarpRow-byte buffers of the warp and leaves at once as lane-contiguous 16-byte
@@ -366,9 +373,42 @@ __global__ void __maxnreg__(MAXREG) resize_cubic3_period_kernel(const uint8_t* _
         }                                                                                                      \
         ++n;                                                                                                   \
     }
-    while (entry != entry_end) {                       // n & 7 == u
-        VACV_PD_STEP(0) VACV_PD_STEP(1) VACV_PD_STEP(2) VACV_PD_STEP(3) VACV_PD_STEP(4) VACV_PD_STEP(5) VACV_PD_STEP(6) VACV_PD_STEP(7)
-        parity ^= 1u;
+    if (!kVStat) {
+        while (entry != entry_end) {                   // n & 7 == u
+            VACV_PD_STEP(0) VACV_PD_STEP(1) VACV_PD_STEP(2) VACV_PD_STEP(3) VACV_PD_STEP(4) VACV_PD_STEP(5) VACV_PD_STEP(6) VACV_PD_STEP(7)
+            parity ^= 1u;
+        }
+    } else {
+        // kVStat (the launcher verified it): output row r of the segment completes at step 3 + r + r / 3 -- the 4 : 3 pattern, every step
+        // with n & 3 != 2 completes one row.  The row completed at step n - 1 is blended and stored DURING step n, after that step's
+        // window words were requested and in the same basic block as its horizontal pass: the FFMA2 chain of one and the PRMT / IDP
+        // work of the other are independent, and no data-dependent branch separates them any more.
+        // slots at step n (u = n & 7): rows n-4 .. n-1 live in window slots u & 3, (u+1) & 3, (u+2) & 3, (u+3) & 3; row n goes to u & 3
+#define VACV_PD_STEP_S(u, EMITPREV)                                                                            \
+        if (n <= n_stop) {                                                                                     \
+            __syncwarp();                                                                                      \
+            issue(VACV_PD_IC(((u) + 6) & 7));                                                                  \
+            uint32_t W[NW];                                                                                    \
+            hload(VACV_PD_IC(u), parity, W);                                                                   \
+            if (EMITPREV) emit(H[(u) & 3], H[((u) + 1) & 3], H[((u) + 2) & 3], H[((u) + 3) & 3]);             \
+            hcompute(W, H[(u) & 3]);                                                                           \
+            ++n;                                                                                               \
+        }
+        VACV_PD_STEP_S(0, false) VACV_PD_STEP_S(1, false) VACV_PD_STEP_S(2, false) VACV_PD_STEP_S(3, false)   // rows 0 .. 3 of the walk
+        while (n <= n_stop) {                          // enters with n & 7 == 4; a step emits the previous step's row unless (n - 1) & 3 == 2
+            VACV_PD_STEP_S(4, true) VACV_PD_STEP_S(5, true) VACV_PD_STEP_S(6, true) VACV_PD_STEP_S(7, false)
+            parity ^= 1u;
+            VACV_PD_STEP_S(0, true) VACV_PD_STEP_S(1, true) VACV_PD_STEP_S(2, true) VACV_PD_STEP_S(3, false)
+        }
+        // the row completed by the last step (n_stop & 3 != 2 by construction); n == n_stop + 1 here
+        {
+            const int u = n & 3;
+            if (u == 0) emit(H[0], H[1], H[2], H[3]);
+            else if (u == 1) emit(H[1], H[2], H[3], H[0]);
+            else if (u == 2) emit(H[2], H[3], H[0], H[1]);
+            else emit(H[3], H[0], H[1], H[2]);
+        }
+#undef VACV_PD_STEP_S
     }
 #undef VACV_PD_STEP
 #undef VACV_PD_IC

@@ -766,6 +766,24 @@ static bool period_taps_match(int w, int wo, double scale_x) {
     return ok;
 }
 
+// kVStat's precondition, checked with the device's own arithmetic: in every segment of rps output rows, row r completes at walk step
+// 3 + r + r / 3 (steps counted from the segment's first tap row).
+struct PeriodRowsPlan { int h, ho, rps; bool ok; };
+static bool period_rows_match_4to3(int h, int ho, int rps, double scale_y) {
+    static thread_local PlanCache<PeriodRowsPlan, 8> cache;
+    if (PeriodRowsPlan* p = cache.find([&](const PeriodRowsPlan& q) { return q.h == h && q.ho == ho && q.rps == rps; })) return p->ok;
+    auto row_index = [&](int d) { return (int)floorf((float)(((double)d + 0.5) * scale_y - 0.5)); };
+    bool ok = true;
+    for (int d0 = 0; d0 < ho && ok; d0 += rps) {
+        const int t_first = row_index(d0) - 1, nrows = std::min(rps, ho - d0);
+        for (int r = 0; r < nrows && ok; ++r) ok = row_index(d0 + r) + 2 - t_first == 3 + r + r / 3;
+    }
+    PeriodRowsPlan* p = cache.claim();
+    p->h = h; p->ho = ho; p->rps = rps; p->ok = ok;
+    cache.commit();
+    return ok;
+}
+
 template <int P, int Q, int KP, int MAXREG>
 static int launch_cubic3_period(const uint8_t* src, uint8_t* dst, int images, int w, int h, int wo, int ho, cudaStream_t s) {
     using S = PeriodShape<P, Q, KP>;
@@ -792,11 +810,17 @@ static int launch_cubic3_period(const uint8_t* src, uint8_t* dst, int images, in
     if (const int v = knob(kKnobWalkSegs)) segs = std::max(1, v);   // tuning knob
     int rps = (int)((ho + segs - 1) / segs);
     rps = std::min(kWalkMaxRows, std::max(rps, 1));
+    // vertical 4 : 3 as well (config 4): segments of whole periods (3 output rows), so that every segment sees the same emit pattern
+    // -- output row r of a segment completes at walk step 3 + r + r / 3 -- which the kernel's kVStat variant has compiled in
+    bool vstat = (long long)h * 3 == (long long)ho * 4 && knob(kKnobCubicV) != 22;
+    if (vstat) rps = std::min(kWalkMaxRows / 3 * 3, (rps + 2) / 3 * 3);
     g.rows_per_seg = rps;
     g.segs = (ho + rps - 1) / rps;
+    if (vstat) vstat = period_rows_match_4to3(h, ho, rps, g.scale_y);
     const size_t smem = (size_t)(rps + 1) * sizeof(Walk2Row) + (size_t)warps * (kPdStageRows * S::kWarpRow + kPdRing * g.ring_pitch + kPdRing * 8);
     const bool down = walkn_rows_strictly_increase(h, ho, g.scale_y);
-    auto kern = down ? resize_cubic3_period_kernel<P, Q, KP, true, MAXREG> : resize_cubic3_period_kernel<P, Q, KP, false, MAXREG>;
+    auto kern = down ? (vstat ? resize_cubic3_period_kernel<P, Q, KP, true, MAXREG, true> : resize_cubic3_period_kernel<P, Q, KP, true, MAXREG>)
+                     : resize_cubic3_period_kernel<P, Q, KP, false, MAXREG>;
     if (smem > 48 * 1024) {
         if (smem > 200 * 1024) return 0;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -822,7 +846,7 @@ static int launch_cubic3_walkn(const uint8_t* src, uint8_t* dst, int images, int
     if ((double)h / ho > 4.0) return 0;                                           // the walk filters every source row in a segment
     const int v = knob(kKnobCubicV);                                              // tuning knob: 0 = automatic, 2 / 4 = columns per thread
     int rc = 0;
-    if (v == 0 || v == 20) {                                                      // rational horizontal scales: periodic walker
+    if (v == 0 || v == 20 || v == 22) {                                           // rational horizontal scales: periodic walker (22: without the compiled-in vertical pattern)
         rc = launch_cubic3_period<4, 3, 2, 168>(src, dst, images, w, h, wo, ho, s);   // 4 : 3 (config 4: 2560 -> 1920)
         if (rc == 0) rc = launch_cubic3_period<2, 1, 4, 128>(src, dst, images, w, h, wo, ho, s);   // 2 : 1 (3840 -> 1920)
         if (rc == 0) rc = launch_cubic3_period<3, 2, 2, 128>(src, dst, images, w, h, wo, ho, s);   // 3 : 2 (1920 -> 1280)
