@@ -430,8 +430,10 @@ static int build_pipe_plan(PipePlan& plan) {
             any_right = (int)(x + (x >= 0.f ? 0.5f : -0.5f)) != 0;
         }
     }
+    // Columns per thread: as few as cover the row.  (Round 1 gave launches with right taps 4 columns per thread up to 768 columns; with one
+    // tap rule per kernel and the parity register sets 2 columns measure faster again -- 1080p -> 608x608 0.371 -> 0.358 ms, 720p ->
+    // 640x640 0.317 -> 0.313, 1080p -> 416x416 0.234 -> 0.230, same box.)
     int ncol = (w_out + kPipeThreads - 1) / kPipeThreads;
-    if (any_right && w_out <= 4 * 192) ncol = 4;
     if (const int v = knob(kKnobPipeNcol)) { if (v >= 1 && v <= kPipeMaxCols && (w_out + v - 1) / v <= (v == 1 ? 640 : kPipeThreads)) ncol = v; }   // tuning knob
     const bool pairs = half_out && (w_out % 2) == 0 && (cv.w % 2) == 0 && (cv.x0 % 2) == 0 && plan.pairs_ok;   // 16-bit outputs: 32-bit stores of column pairs
     if (pairs) ncol = ncol <= 2 ? 2 : 4;
