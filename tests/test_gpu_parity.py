@@ -166,6 +166,34 @@ def test_dtype_change(vacv, oracle):
         vacv.dtype_change(dev(np.zeros(8, np.float16)), vacv.FP32)
 
 
+@pytest.mark.parametrize("qpt", [1, 3, 8, 1000])
+def test_streaming_kernels_any_grid(vacv, oracle, qpt):
+    """The streaming kernels (dtype_change, normalize u8 / fp32, HWC and planes) give every thread STREAM_QPT 16-byte groups of work
+    (8 by default); the results must not depend on the grid that follows from it -- one group per thread, a handful of CTAs for the
+    whole frame, sizes that are not multiples of anything."""
+    assert vacv.lib.vacv_cuda_set_tuning(b"STREAM_QPT", qpt) == 0
+    try:
+        for n in [176 * 144 * 3, 1920 * 1080 * 3, 4 * 1001, 20]:
+            src = u8(4, n)
+            assert_same(host(vacv.dtype_change(dev(src), vacv.FP32)), oracle.u8_to_f32(src))
+            g = (rng(5).random(n, dtype=np.float32) * 255.999).astype(np.float32)
+            assert_same(host(vacv.dtype_change(dev(g), vacv.INT8)), oracle.f32_to_u8(g))
+        for (w, h) in [(640, 360), (333, 212), (1920, 1080)]:
+            img = u8(17, 2, h, w, 3)
+            got = host(vacv.normalize(dev(img), NHWC, dev(MEAN), dev(STD)))
+            for i in range(2):
+                assert_same(got[i], oracle.normalize(img[i], w * h, 3, NHWC, MEAN, STD))
+            planes = np.ascontiguousarray(img.transpose(0, 3, 1, 2))
+            gotp = host(vacv.normalize(dev(planes), NCHW, dev(MEAN), dev(STD)))
+            for i in range(2):
+                assert_same(gotp[i], oracle.normalize(planes[i], w * h, 3, NCHW, MEAN, STD))
+            f = img.astype(np.float32)
+            gotf = host(vacv.normalize(dev(f), NHWC, dev(MEAN), dev(STD)))
+            assert_same(gotf[0], oracle.normalize(f[0], w * h, 3, NHWC, MEAN, STD))
+    finally:
+        vacv.lib.vacv_cuda_set_tuning(b"STREAM_QPT", 0)
+
+
 # ------------------------------------------------------------------ a5-a7 bilinear
 LIN_SIZES = [((64, 48), (20, 16)), ((64, 48), (200, 111)), ((1920, 1080), (640, 360)), ((1920, 1080), (640, 640)),
              ((333, 211), (500, 300)), ((2, 2), (7, 5)), ((640, 360), (639, 359)), ((2560, 1440), (320, 180))]
