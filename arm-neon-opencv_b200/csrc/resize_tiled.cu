@@ -24,6 +24,7 @@
 #include "resize_cubic3_walk.cuh"
 #include "resize_cubic3_walkn.cuh"
 #include "resize_cubic3_period.cuh"
+#include "resize_cubic_f32_period.cuh"
 #include "host_util.cuh"
 #include "vacv_common.cuh"
 
@@ -840,6 +841,96 @@ static int launch_cubic3_period(const uint8_t* src, uint8_t* dst, int images, in
     return 1;
 }
 
+// fp32 planes at rational horizontal scales (resize_cubic_f32_period.cuh).  Host twin of cubic_naive_scaled (resize_coeffs.cuh; same
+// IEEE operations: this file is built with contraction off on both sides) for the launcher's checks.
+static void host_cubic_naive(int d, int n_in, double scale, int& ofs, float (&a)[4]) {
+    float fx = (float)(((double)d + 0.5) * scale - 0.5);
+    int sx = (int)floorf(fx);
+    fx -= (float)sx;
+    const float A = -0.75f;
+    const float fx0 = fx + 1, fx1 = fx, fx2 = 1 - fx;
+    a[0] = A * fx0 * fx0 * fx0 - 5 * A * fx0 * fx0 + 8 * A * fx0 - 4 * A;
+    a[1] = (A + 2) * fx1 * fx1 * fx1 - (A + 3) * fx1 * fx1 + 1;
+    a[2] = (A + 2) * fx2 * fx2 * fx2 - (A + 3) * fx2 * fx2 + 1;
+    a[3] = 1.f - a[0] - a[1] - a[2];
+    if (sx <= -1) { sx = 1; a[0] = 1.f - a[3]; a[1] = a[3]; a[2] = 0.f; a[3] = 0.f; }
+    if (sx == 0) { sx = 1; a[0] = a[0] + a[1]; a[1] = a[2]; a[2] = a[3]; a[3] = 0.f; }
+    if (sx == n_in - 2) { sx = n_in - 3; a[3] = a[2] + a[3]; a[2] = a[1]; a[1] = a[0]; a[0] = 0.f; }
+    if (sx >= n_in - 1) { sx = n_in - 3; a[3] = 1.f - a[0]; a[2] = a[0]; a[1] = 0.f; a[0] = 0.f; }
+    ofs = sx;
+}
+struct PeriodF32Plan { int w, wo, h, ho, P, Q, KP; bool ok, down; };
+template <int P, int Q, int KP>
+static const PeriodF32Plan* period_f32_plan(int w, int h, int wo, int ho, double scale_x, double scale_y) {
+    using S = PeriodF32Shape<P, Q, KP>;
+    static thread_local PlanCache<PeriodF32Plan, 8> cache;
+    if (PeriodF32Plan* p = cache.find([&](const PeriodF32Plan& q) { return q.w == w && q.wo == wo && q.h == h && q.ho == ho && q.P == P && q.Q == Q && q.KP == KP; }))
+        return p;
+    bool ok = true;
+    for (int dx = 0; dx < wo && ok; ++dx) {            // every tap with a non-zero coefficient inside the column's compile-time window
+        int ofs; float a[4];
+        host_cubic_naive(dx, w, scale_x, ofs, a);
+        const int pt = dx / S::NCOL, c = dx - pt * S::NCOL;
+        const int base = P * KP * pt - 1 + pd::tap0(P, Q, c);
+        for (int j = 0; j < 4; ++j) {
+            const int pos = ofs - 1 + j - base;
+            if (a[j] != 0.f) ok = ok && pos >= 0 && pos <= 3;
+        }
+    }
+    bool down = true;                                  // kDown's precondition: every output row ends on a later source row
+    int prev = INT_MIN;
+    for (int d = 0; d < ho && down; ++d) {
+        int ofs; float a[4];
+        host_cubic_naive(d, h, scale_y, ofs, a);
+        down = ofs > prev;
+        prev = ofs;
+    }
+    PeriodF32Plan* p = cache.claim();
+    p->w = w; p->wo = wo; p->h = h; p->ho = ho; p->P = P; p->Q = Q; p->KP = KP; p->ok = ok; p->down = down;
+    cache.commit();
+    return p;
+}
+template <int P, int Q, int KP>
+static int launch_cubic_f32_period(const float* src, float* dst, int images, int w, int h, int wo, int ho, cudaStream_t s) {
+    using S = PeriodF32Shape<P, Q, KP>;
+    if ((long long)w * Q != (long long)wo * P || wo % S::NCOL != 0 || (w % 4) != 0 || (wo % 4) != 0) return 0;
+    if (((uintptr_t)src % 16) != 0 || ((uintptr_t)dst % 16) != 0) return 0;
+    if (w < 4 || h < 4 || (size_t)w * h * 4 >= 0xffffffffull || (size_t)wo * ho * 4 >= 0xffffffffull || (double)h / ho > 4.0) return 0;
+    PeriodF32Geom g;
+    g.w = w; g.h = h; g.wo = wo; g.ho = ho;
+    g.src_image = (size_t)w * h; g.dst_image = (size_t)wo * ho;
+    g.scale_x = (double)w / (double)wo; g.scale_y = (double)h / (double)ho;      // resize_naive.cpp:144
+    const PeriodF32Plan* plan = period_f32_plan<P, Q, KP>(w, h, wo, ho, g.scale_x, g.scale_y);
+    if (!plan->ok) return 0;
+    g.warp_strips = (wo + 32 * S::NCOL - 1) / (32 * S::NCOL);
+    int warps = 4, best_pad = INT_MAX;
+    for (int wv = 4; wv >= 1; --wv) {
+        const int pad = (g.warp_strips + wv - 1) / wv * wv - g.warp_strips;
+        if (pad < best_pad) { best_pad = pad; warps = wv; }
+    }
+    g.cta_strips = (g.warp_strips + warps - 1) / warps;
+    const long long want = 8LL * 16 * current_sm_count();
+    const long long per_seg = (long long)g.cta_strips * images;
+    long long segs = std::max<long long>(1, std::min<long long>((want + per_seg - 1) / per_seg, (ho + 31) / 32));
+    if (const int v = knob(kKnobWalkSegs)) segs = std::max(1, v);   // tuning knob
+    int rps = (int)((ho + segs - 1) / segs);
+    rps = std::min(kWalkMaxRows, std::max(rps, 1));
+    g.rows_per_seg = rps;
+    g.segs = (ho + rps - 1) / rps;
+    const size_t smem = (size_t)(rps + 1) * sizeof(WalkRow) + (size_t)warps * (kPdRing * S::kNeed + kPdRing * 8);
+    auto kern = plan->down ? resize_cubic_f32_period_kernel<P, Q, KP, true> : resize_cubic_f32_period_kernel<P, Q, KP, false>;
+    if (smem > 48 * 1024) {
+        if (smem > 200 * 1024) return 0;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return set_error(VACV_ERR_CUDA, "resize: %s", cudaGetErrorString(e));
+    }
+    for (int i0 = 0; i0 < images; i0 += 65535) {
+        dim3 grid(g.cta_strips * g.segs, std::min(images - i0, 65535));
+        kern<<<grid, 32 * warps, smem, s>>>(src + (size_t)i0 * g.src_image, dst + (size_t)i0 * g.dst_image, g);
+    }
+    return 1;
+}
+
 static int launch_cubic3_walkn(const uint8_t* src, uint8_t* dst, int images, int w, int h, int wo, int ho, cudaStream_t s) {
     if (((size_t)w * 3) % 16 != 0 || ((uintptr_t)src % 16) != 0) return 0;     // the cp.async ring copies aligned 16-byte chunks
     if (w < 4 || h < 4 || (size_t)w * h * 3 >= 0xffffffffull || (size_t)wo * ho * 3 >= 0xffffffffull) return 0;
@@ -892,7 +983,14 @@ int try_launch_resize_tiled(int kind, const void* src, void* dst, int images, in
         if (rc != 0) return rc;
     }
     if (c == 1 && kind == kCubF32) {   // planes of a CHW tensor
-        const int rc = launch_cubic_walk_f32<1>((const float*)src, (float*)dst, images, w, h, wo, ho, s);
+        int rc = 0;
+        if (knob(kKnobCubicV) != 1) {   // rational horizontal scales: periodic walker (CUBIC_V=1: the one-column walker everywhere)
+            rc = launch_cubic_f32_period<3, 2, 4>((const float*)src, (float*)dst, images, w, h, wo, ho, s);          // 3 : 2 (1920 -> 1280)
+            if (rc == 0) rc = launch_cubic_f32_period<4, 3, 4>((const float*)src, (float*)dst, images, w, h, wo, ho, s);   // 4 : 3 (2560 -> 1920)
+            // (2 : 1 stays on the one-column walker: its lanes are 8 bytes apart there already, 4.0 - 4.7 TB/s; the periodic form measured the same)
+            if (rc != 0) return rc;
+        }
+        rc = launch_cubic_walk_f32<1>((const float*)src, (float*)dst, images, w, h, wo, ho, s);
         if (rc != 0) return rc;
     }
     const int es = (kind == kLinF32 || kind == kCubF32) ? 4 : 1;

@@ -339,7 +339,15 @@ def ops2(iters):   # shapes off the headline path: planar layouts, fp32 gathers,
     ms, _ = timeit(lambda: vacv.resize(bgr, vacv.NHWC, 1280, 720), iters)
     report("op2 resize linear u8 hwc 1080p->1280x720 x64", ms, b * 1280 * 720, b * (1920 * 1080 * 3 + 1280 * 720 * 3))
     ms, _ = timeit(lambda: vacv.resize(chw, vacv.NCHW, 1280, 720, vacv.INTER_CUBIC) if False else vacv.resize(fchw, vacv.NCHW, 1280, 720, vacv.INTER_CUBIC), iters)
-    report("op2 resize cubic f32 chw 1080p->1280x720 x16", ms, 16 * 1280 * 720, 16 * 4 * (1920 * 1080 * 3 + 1280 * 720 * 3))
+    report("op2 resize cubic f32 chw 1080p->1280x720 x16", ms, 16 * 1280 * 720, 16 * 4 * (1920 * 1080 * 3 + 1280 * 720 * 3), "3 : 2, periodic walker")
+    vacv.lib.vacv_cuda_set_tuning(b"CUBIC_V", 1)   # A/B: the one-column walker
+    ms, _ = timeit(lambda: vacv.resize(fchw, vacv.NCHW, 1280, 720, vacv.INTER_CUBIC), iters)
+    vacv.lib.vacv_cuda_set_tuning(b"CUBIC_V", 0)
+    report("   same, one-column walker (CUBIC_V=1)", ms, 16 * 1280 * 720, 16 * 4 * (1920 * 1080 * 3 + 1280 * 720 * 3))
+    qhd = rand_u8(8, 3, 1440, 2560).to(torch.float32)
+    ms, _ = timeit(lambda: vacv.resize(qhd, vacv.NCHW, 1920, 1080, vacv.INTER_CUBIC), iters)
+    report("op2 resize cubic f32 chw 2560x1440->1920x1080 x8", ms, 8 * 1920 * 1080, 8 * 4 * 3 * (2560 * 1440 + 1920 * 1080), "4 : 3, periodic walker")
+    del qhd
     ms, _ = timeit(lambda: vacv.normalize(chw, vacv.NCHW, mean, std), iters)
     report("op2 normalize u8 chw 1080p x64", ms, b * 1920 * 1080, b * 1920 * 1080 * 15)
     ms, _ = timeit(lambda: vacv.crop(chw, vacv.NCHW, 321, 181, 1280, 720), iters)
