@@ -1,8 +1,8 @@
-// fp32 bicubic resize of single planes (CHW tensors are resized plane by plane) at RATIONAL horizontal scales: the periodic form of
-// the column walker (resize_cubic3_walk.cuh), as resize_cubic3_period.cuh is for u8 BGR.
+// fp32 bicubic resize at RATIONAL horizontal scales -- C = 1: single planes (CHW tensors are resized plane by plane), C = 3: interleaved
+// BGR -- the periodic form of the column walker (resize_cubic3_walk.cuh), as resize_cubic3_period.cuh is for u8 BGR.
 //
-// Reference arithmetic: resize_naive_inter_cubic_fp32_one_channel (src/cv/resize_naive.cpp:368-529; coefficients and border folding
-// :130-185, horizontal / vertical accumulation order :230 / :345), fp32 with one rounding per operation (built --fmad=false).
+// Reference arithmetic: resize_naive_inter_cubic_fp32_one_channel / _three_channel (src/cv/resize_naive.cpp:368-529 / :187-366;
+// coefficients and border folding :130-185, horizontal / vertical accumulation order :230 / :345), fp32 with one rounding per operation (built --fmad=false).
 //
 // Why.  ncu of resize_cubic3_walk_f32_kernel<1> at 1080p -> 1280x720 (profiles/r2_cubic_f32_chw_ncu_raw.txt): the shared-memory data
 // pipe at 87 % of its wavefront peak, short-scoreboard the top stall -- one column per thread reads its four taps with four LDS.32
@@ -28,36 +28,43 @@ struct PeriodF32Geom {
     size_t src_image, dst_image;       // floats between planes
 };
 
-template <int P, int Q, int KP>
+template <int C, int P, int Q, int KP>
 struct PeriodF32Shape {
     static constexpr int NCOL = Q * KP;                                  // adjacent output columns per thread
-    static constexpr int NPX = pd::tap0(P, Q, NCOL - 1) + 4;              // source floats in a thread's window
-    static constexpr int LS = 4 * P * KP;                                // bytes between the windows of neighbouring lanes
+    static constexpr int NPX = pd::tap0(P, Q, NCOL - 1) + 4;              // source pixels in a thread's window
+    static constexpr int NWF = C * NPX;                                  // ... as floats
+    static constexpr int NV = C * NCOL;                                  // output floats per thread and row
+    static constexpr int LS = 4 * C * P * KP;                            // bytes between the windows of neighbouring lanes
     static constexpr int kWarpSpan = 32 * LS;                            // source bytes between the windows of neighbouring warps
-    static constexpr int kLaneOff = 12;                                  // ring offset of lane 0's window float 0 (source float P*KP*thread - 1; the ring row starts 16 bytes early)
-    static constexpr int kNeed = (LS * 31 + kLaneOff + 4 * (NPX + 1) + 15) & ~15;   // ring bytes of one source row (the 64-bit loads may read one float past the window)
-    static_assert(NCOL % 4 == 0, "a thread's results leave as 16-byte stores");
-    static_assert(LS % 8 == 0, "window floats 1.. are read as 64-bit words");
+    static constexpr int kLaneOff = 16 - 4 * C;                          // ring offset of lane 0's window float 0 (source pixel P*KP*thread - 1; the ring row starts 16 bytes early)
+    static constexpr int kNeed = (LS * 31 + kLaneOff + 4 * (NWF + 1) + 15) & ~15;   // ring bytes of one source row (the 64-bit loads may read one float past the window)
+    static constexpr bool kDirect = NV % 4 == 0;                         // results leave as 16-byte stores straight from registers, else through a staged row
+    static constexpr int kWarpRow = 32 * NV * 4;                         // bytes one warp produces per output row
+    static_assert(C >= 1 && C <= 3, "window float 0 must lie inside the 16 bytes before the warp's span");
+    static_assert(LS % 8 == 0 && kLaneOff % 8 == 4, "window float 0 is read alone, floats 1.. as 64-bit words");
+    static_assert(kWarpRow % 16 == 0 && kWarpRow / 16 <= 96, "flush: up to three 16-byte chunks per lane");
 };
 
-template <int P, int Q, int KP, bool kDown>
+template <int C, int P, int Q, int KP, bool kDown>
 __global__ void __launch_bounds__(128) resize_cubic_f32_period_kernel(const float* __restrict__ src, float* __restrict__ dst, PeriodF32Geom g) {
-    using S = PeriodF32Shape<P, Q, KP>;
-    constexpr int NCOL = S::NCOL, NPX = S::NPX, LS = S::LS;
+    using S = PeriodF32Shape<C, P, Q, KP>;
+    constexpr int NCOL = S::NCOL, NWF = S::NWF, NV = S::NV, LS = S::LS, kWarpRow = S::kWarpRow;
     constexpr unsigned kPitch = S::kNeed;
     extern __shared__ __align__(16) uint8_t smem[];
     WalkRow* rows = reinterpret_cast<WalkRow*>(smem);                                     // [rows_per_seg + 1]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int rows_bytes = (g.rows_per_seg + 1) * (int)sizeof(WalkRow);
+    constexpr int kStage = S::kDirect ? 0 : 2 * kWarpRow;              // two staging buffers per warp (one output row each)
     uint8_t* ring = smem + rows_bytes + warp * (kPdRing * kPitch);
-    const uint32_t bars = (uint32_t)__cvta_generic_to_shared(smem + rows_bytes + nwarps * (kPdRing * kPitch)) + warp * (kPdRing * 8);
+    uint8_t* stage = smem + rows_bytes + nwarps * (kPdRing * kPitch) + warp * kStage;
+    const uint32_t bars = (uint32_t)__cvta_generic_to_shared(smem + rows_bytes + nwarps * (kPdRing * kPitch + kStage)) + warp * (kPdRing * 8);
     const int cta_strip = blockIdx.x % g.cta_strips, seg = blockIdx.x / g.cta_strips;
     const int wstrip = cta_strip * nwarps + warp;
     const int pt = wstrip * 32 + lane;                 // this thread's index along x: columns NCOL * pt ..
     const int dy_begin = seg * g.rows_per_seg, nrows = min(g.ho, dy_begin + g.rows_per_seg) - dy_begin;
     const uint8_t* img = reinterpret_cast<const uint8_t*>(src + blockIdx.y * g.src_image);
     float* out_img = dst + blockIdx.y * g.dst_image;
-    const unsigned row_bytes = (unsigned)g.w * 4u;
+    const unsigned row_bytes = (unsigned)g.w * 4u * C;
     const bool active = wstrip < g.warp_strips;        // false: padding warp of the last CTA strip
 
     // walk steps: step n filters source row t_first + n; the last step is the last output row's last tap row (ofs + 2)
@@ -142,39 +149,65 @@ __global__ void __launch_bounds__(128) resize_cubic_f32_period_kernel(const floa
     int next_last;
     asm volatile("ld.shared.s32 %0, [%1+16];" : "=r"(next_last) : "r"(entry));
 
-    // horizontal pass of the walk step in ring slot `slot`: window floats -> the NCOL sums, resize_naive.cpp:230 order
-    auto hfilter = [&](const uint32_t slot, uint32_t parity, float (&H)[NCOL]) {
+    // horizontal pass of the walk step in ring slot `slot`: window floats -> the NV sums (value C*c + k), resize_naive.cpp:230 order
+    auto hfilter = [&](const uint32_t slot, uint32_t parity, float (&H)[NV]) {
         pd::mbar_wait(ubars + 8 * slot, parity);
         const uint32_t p = win_s + slot * kPitch;
-        float W[NPX + 1];
+        float W[NWF + 1];
         asm volatile("ld.shared.f32 %0, [%1];" : "=f"(W[0]) : "r"(p));
 #pragma unroll
-        for (int i = 1; i + 1 <= NPX; i += 2) asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(W[i]), "=f"(W[i + 1]) : "r"(p + 4 * i));
+        for (int i = 1; i + 1 <= NWF; i += 2) asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(W[i]), "=f"(W[i + 1]) : "r"(p + 4 * i));
         pd::static_for<NCOL>([&](auto ic) {
             constexpr int c = decltype(ic)::value;
             constexpr int t0 = pd::tap0(P, Q, c);
-            H[c] = W[t0] * xa[c][0] + W[t0 + 1] * xa[c][1] + W[t0 + 2] * xa[c][2] + W[t0 + 3] * xa[c][3];
+#pragma unroll
+            for (int k = 0; k < C; ++k)
+                H[C * c + k] = W[C * t0 + k] * xa[c][0] + W[C * (t0 + 1) + k] * xa[c][1] + W[C * (t0 + 2) + k] * xa[c][2] + W[C * (t0 + 3) + k] * xa[c][3];
         });
     };
-    // vertical pass (resize_naive.cpp:345 order) + store: NCOL adjacent floats per thread, 16-byte stores from registers
-    float* orow = out_img + (size_t)dy_begin * g.wo + (size_t)NCOL * pt;
-    auto emit = [&](const float (&h0)[NCOL], const float (&h1)[NCOL], const float (&h2)[NCOL], const float (&h3)[NCOL]) {
+    // vertical pass (resize_naive.cpp:345 order) + store: NV adjacent floats per thread -- 16-byte stores straight from registers when NV
+    // is a multiple of 4, else staged in one of two buffers of the warp and flushed at once as lane-contiguous 16-byte chunks
+    float* orow = out_img + ((size_t)dy_begin * g.wo + (size_t)NCOL * pt) * C;
+    const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
+    uint32_t st_w = stage_s + 4 * NV * lane, st_f = stage_s + 16 * lane;
+    int st_d = kWarpRow;
+    constexpr int kChunks = kWarpRow / 16;
+    const int valid_chunks = min(kWarpRow, (int)((unsigned)g.wo * 4u * C) - wstrip * kWarpRow) >> 4;   // chunks of a warp row inside the image row
+    uint8_t* gflush = reinterpret_cast<uint8_t*>(out_img + ((size_t)dy_begin * g.wo) * C) + (size_t)wstrip * kWarpRow + 16 * lane;
+    auto emit = [&](const float (&h0)[NV], const float (&h1)[NV], const float (&h2)[NV], const float (&h3)[NV]) {
         float4 bw;
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bw.x), "=f"(bw.y), "=f"(bw.z), "=f"(bw.w) : "r"(entry));
-        float o[NCOL];
+        float o[NV];
 #pragma unroll
-        for (int c = 0; c < NCOL; ++c) o[c] = h0[c] * bw.x + h1[c] * bw.y + h2[c] * bw.z + h3[c] * bw.w;
-        if (owner) {
+        for (int v = 0; v < NV; ++v) o[v] = h0[v] * bw.x + h1[v] * bw.y + h2[v] * bw.z + h3[v] * bw.w;
+        if (S::kDirect) {
+            if (owner) {
 #pragma unroll
-            for (int q = 0; q < NCOL / 4; ++q) st_stream16f(orow + 4 * q, make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]));
+                for (int q = 0; q < NV / 4; ++q) st_stream16f(orow + 4 * q, make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]));
+            }
+            orow += (size_t)g.wo * C;
+        } else {                                       // threads past the last column stage zeros that are never flushed
+#pragma unroll
+            for (int v = 0; v < NV; ++v) asm volatile("st.shared.f32 [%0], %1;" ::"r"(st_w + 4 * v), "f"(o[v]) : "memory");
+            __syncwarp();                              // the row is staged; the other buffer's readers passed this point a row ago
+#pragma unroll
+            for (int q = 0; q < (kChunks + 31) / 32; ++q) {
+                if (lane + 32 * q < min(valid_chunks, kChunks)) {
+                    uint4 v;
+                    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(st_f + 512 * q));
+                    st_stream16(gflush + 512 * q, v);
+                }
+            }
+            gflush += (size_t)g.wo * 4u * C;
+            st_w += st_d; st_f += st_d;
+            st_d = -st_d;
         }
-        orow += g.wo;
         entry += (int)sizeof(WalkRow);
         asm volatile("ld.shared.s32 %0, [%1+16];" : "=r"(next_last) : "r"(entry));   // sentinel INT_MAX after the last row
     };
 
     // ---- the walk: step n -> ring slot n & 7 and window slot n & 3 (compile-time inside the 8x unrolled body)
-    float H[4][NCOL];
+    float H[4][NV];
     const uint32_t entry_end = rows_s + nrows * (int)sizeof(WalkRow);
     int n = 0;
     uint32_t parity = 0;

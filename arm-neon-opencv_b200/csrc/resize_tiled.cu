@@ -862,7 +862,7 @@ static void host_cubic_naive(int d, int n_in, double scale, int& ofs, float (&a)
 struct PeriodF32Plan { int w, wo, h, ho, P, Q, KP; bool ok, down; };
 template <int P, int Q, int KP>
 static const PeriodF32Plan* period_f32_plan(int w, int h, int wo, int ho, double scale_x, double scale_y) {
-    using S = PeriodF32Shape<P, Q, KP>;
+    using S = PeriodF32Shape<1, P, Q, KP>;             // the tap pattern does not depend on the channel count
     static thread_local PlanCache<PeriodF32Plan, 8> cache;
     if (PeriodF32Plan* p = cache.find([&](const PeriodF32Plan& q) { return q.w == w && q.wo == wo && q.h == h && q.ho == ho && q.P == P && q.Q == Q && q.KP == KP; }))
         return p;
@@ -890,15 +890,15 @@ static const PeriodF32Plan* period_f32_plan(int w, int h, int wo, int ho, double
     cache.commit();
     return p;
 }
-template <int P, int Q, int KP>
+template <int C, int P, int Q, int KP>
 static int launch_cubic_f32_period(const float* src, float* dst, int images, int w, int h, int wo, int ho, cudaStream_t s) {
-    using S = PeriodF32Shape<P, Q, KP>;
-    if ((long long)w * Q != (long long)wo * P || wo % S::NCOL != 0 || (w % 4) != 0 || (wo % 4) != 0) return 0;
-    if (((uintptr_t)src % 16) != 0 || ((uintptr_t)dst % 16) != 0) return 0;
-    if (w < 4 || h < 4 || (size_t)w * h * 4 >= 0xffffffffull || (size_t)wo * ho * 4 >= 0xffffffffull || (double)h / ho > 4.0) return 0;
+    using S = PeriodF32Shape<C, P, Q, KP>;
+    if ((long long)w * Q != (long long)wo * P || wo % S::NCOL != 0 || ((w * C) % 4) != 0 || ((wo * C) % 4) != 0) return 0;   // rows are whole 16-byte chunks
+    if (((uintptr_t)src % 16) != 0 || ((uintptr_t)dst % 16) != 0 || ((size_t)w * h * C) % 4 != 0 || ((size_t)wo * ho * C) % 4 != 0) return 0;
+    if (w < 4 || h < 4 || (size_t)w * h * 4 * C >= 0xffffffffull || (size_t)wo * ho * 4 * C >= 0xffffffffull || (double)h / ho > 4.0) return 0;
     PeriodF32Geom g;
     g.w = w; g.h = h; g.wo = wo; g.ho = ho;
-    g.src_image = (size_t)w * h; g.dst_image = (size_t)wo * ho;
+    g.src_image = (size_t)w * h * C; g.dst_image = (size_t)wo * ho * C;
     g.scale_x = (double)w / (double)wo; g.scale_y = (double)h / (double)ho;      // resize_naive.cpp:144
     const PeriodF32Plan* plan = period_f32_plan<P, Q, KP>(w, h, wo, ho, g.scale_x, g.scale_y);
     if (!plan->ok) return 0;
@@ -917,8 +917,8 @@ static int launch_cubic_f32_period(const float* src, float* dst, int images, int
     rps = std::min(kWalkMaxRows, std::max(rps, 1));
     g.rows_per_seg = rps;
     g.segs = (ho + rps - 1) / rps;
-    const size_t smem = (size_t)(rps + 1) * sizeof(WalkRow) + (size_t)warps * (kPdRing * S::kNeed + kPdRing * 8);
-    auto kern = plan->down ? resize_cubic_f32_period_kernel<P, Q, KP, true> : resize_cubic_f32_period_kernel<P, Q, KP, false>;
+    const size_t smem = (size_t)(rps + 1) * sizeof(WalkRow) + (size_t)warps * (kPdRing * S::kNeed + (S::kDirect ? 0 : 2 * S::kWarpRow) + kPdRing * 8);
+    auto kern = plan->down ? resize_cubic_f32_period_kernel<C, P, Q, KP, true> : resize_cubic_f32_period_kernel<C, P, Q, KP, false>;
     if (smem > 48 * 1024) {
         if (smem > 200 * 1024) return 0;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -975,6 +975,11 @@ int try_launch_resize_tiled(int kind, const void* src, void* dst, int images, in
         if (rc != 0) return rc;
         if (kind == kCubU8 && !roll) rc = launch_cubic3_walk2((const uint8_t*)src, (uint8_t*)dst, images, w, h, wo, ho, s);   // CUBIC_V=1: first generation
         if (rc != 0) return rc;
+        if (kind == kCubF32 && !roll && knob(kKnobCubicV) != 1) {   // rational horizontal scales: periodic walker for interleaved fp32
+            rc = launch_cubic_f32_period<3, 4, 3, 1>((const float*)src, (float*)dst, images, w, h, wo, ho, s);          // 4 : 3 (2560 -> 1920)
+            if (rc == 0) rc = launch_cubic_f32_period<3, 3, 2, 2>((const float*)src, (float*)dst, images, w, h, wo, ho, s);   // 3 : 2 (1920 -> 1280)
+            if (rc != 0) return rc;
+        }
         if (kind == kCubF32 && !roll) rc = launch_cubic_walk_f32<3>((const float*)src, (float*)dst, images, w, h, wo, ho, s);
         if (rc != 0) return rc;
         rc = kind == kCubU8 ? launch_cubic3_rolling<true>(src, dst, images, w, h, wo, ho, s) : launch_cubic3_rolling<false>(src, dst, images, w, h, wo, ho, s);
@@ -985,8 +990,8 @@ int try_launch_resize_tiled(int kind, const void* src, void* dst, int images, in
     if (c == 1 && kind == kCubF32) {   // planes of a CHW tensor
         int rc = 0;
         if (knob(kKnobCubicV) != 1) {   // rational horizontal scales: periodic walker (CUBIC_V=1: the one-column walker everywhere)
-            rc = launch_cubic_f32_period<3, 2, 4>((const float*)src, (float*)dst, images, w, h, wo, ho, s);          // 3 : 2 (1920 -> 1280)
-            if (rc == 0) rc = launch_cubic_f32_period<4, 3, 4>((const float*)src, (float*)dst, images, w, h, wo, ho, s);   // 4 : 3 (2560 -> 1920)
+            rc = launch_cubic_f32_period<1, 3, 2, 4>((const float*)src, (float*)dst, images, w, h, wo, ho, s);          // 3 : 2 (1920 -> 1280)
+            if (rc == 0) rc = launch_cubic_f32_period<1, 4, 3, 4>((const float*)src, (float*)dst, images, w, h, wo, ho, s);   // 4 : 3 (2560 -> 1920)
             // (2 : 1 stays on the one-column walker: its lanes are 8 bytes apart there already, 4.0 - 4.7 TB/s; the periodic form measured the same)
             if (rc != 0) return rc;
         }

@@ -330,19 +330,21 @@ def test_resize_cubic_f32(vacv, oracle, layout, sz, path):
 @pytest.mark.parametrize("sz", [((1920, 1080), (1280, 720)), ((96, 40), (64, 30)), ((48, 9), (32, 20)), ((1536, 33), (1024, 77)), ((12, 12), (8, 8)),
                                 ((2560, 360), (1920, 270)), ((64, 64), (48, 48)), ((1024, 20), (768, 50)), ((16, 16), (12, 12)),
                                 ((3840, 540), (1920, 270)), ((64, 17), (32, 40)), ((8, 8), (4, 4)), ((1296, 50), (648, 25))])
-def test_resize_cubic_f32_planes_periodic_walker(vacv, oracle, sz):
-    """fp32 bicubic on planes at rational horizontal scales (resize_cubic_f32_period.cuh: 3 : 2 with eight adjacent columns per
-    thread, 4 : 3 with twelve; the 2 : 1 shapes take the one-column walker): full and partial warp strips, a handful of threads per row, the reference's border folding at both
-    image edges (taps that move onto other window positions), up- and down-scaling along y, a batch of 2 x 3 planes -- against the
-    oracle (resize_naive.cpp:368-529) and against the one-column walker bit for bit."""
+@pytest.mark.parametrize("layout", [NCHW, NHWC])
+def test_resize_cubic_f32_planes_periodic_walker(vacv, oracle, sz, layout):
+    """fp32 bicubic at rational horizontal scales (resize_cubic_f32_period.cuh; planes: 3 : 2 with eight adjacent columns per thread,
+    4 : 3 with twelve; interleaved BGR: 4 : 3 with three -- staged stores -- and 3 : 2 with four; the 2 : 1 shapes take the one-column
+    walker): full and partial warp strips, a handful of threads per row, the reference's border folding at both image edges (taps that
+    move onto other window positions), up- and down-scaling along y, a batch of 2 -- against the oracle (resize_naive.cpp:187-529) and
+    against the one-column walker bit for bit."""
     (w, h), (wo, ho) = sz
-    src = f32(71, 2, 3, h, w)
-    got = host(vacv.resize(dev(src), NCHW, wo, ho, vacv.INTER_CUBIC))
+    src = f32(71, 2, 3, h, w) if layout == NCHW else f32(71, 2, h, w, 3)
+    got = host(vacv.resize(dev(src), layout, wo, ho, vacv.INTER_CUBIC))
     for i in range(2):
-        assert_same(got[i], oracle.resize_cubic_f32(src[i], w, h, 3, NCHW, wo, ho))
+        assert_same(got[i], oracle.resize_cubic_f32(src[i], w, h, 3, layout, wo, ho))
     assert vacv.lib.vacv_cuda_set_tuning(b"CUBIC_V", 1) == 0
     try:
-        first = host(vacv.resize(dev(src), NCHW, wo, ho, vacv.INTER_CUBIC))
+        first = host(vacv.resize(dev(src), layout, wo, ho, vacv.INTER_CUBIC))
     finally:
         vacv.lib.vacv_cuda_set_tuning(b"CUBIC_V", 0)
     assert_same(got, first)
