@@ -21,6 +21,7 @@ enum Knob {
     kKnobCubicV,           // VACV_CUBIC_V              u8 bicubic kernel variant (0 = default)
     kKnobPipeRows,         // VACV_PIPE_ROWS            fused pipeline on padded surfaces: one bulk copy per row instead of whole bands (padding included)
     kKnobStreamQpt,        // VACV_STREAM_QPT           16-byte groups per thread of the streaming kernels' grids (0 = default)
+    kKnobWarpV,            // VACV_WARP_V               u8 BGR warp_affine: 1 = first-generation flat-order gather kernel (0 = automatic: column-owning pack kernel where eligible)
     kKnobCount
 };
 int knob(Knob k);

@@ -291,6 +291,7 @@ __global__ void __launch_bounds__(256) warp_affine_u8c1_kernel(const uint8_t* __
 }  // namespace vacv
 
 #include "tma_host.cuh"
+#include "warp_pack_u8c3.cuh"     // column-owning form of the u8 BGR gather kernel (64-bit tap loads, shuffle-packed stores)
 #include "warp_staged_u8c3.cuh"   // TMA-staged variant of the 3-channel kernel (uses Taps / warp_taps_fast / kWarpOut*)
 
 using namespace vacv;
@@ -389,6 +390,21 @@ extern "C" int vacv_cuda_warp_affine(const void* frames, int n_frames, int w, in
             if (flags & VACV_FLAG_SIGNED_CHAR)
                 return launch_staged<kWarpOutU8, true>(*maps, (const uint8_t*)frames, frame_idx, minv, dst, w, h, n_crops, w_out, h_out, nullptr, nullptr, s);
             return launch_staged<kWarpOutU8, false>(*maps, (const uint8_t*)frames, frame_idx, minv, dst, w, h, n_crops, w_out, h_out, nullptr, nullptr, s);
+        }
+    }
+    if (dtype == VACV_INT8 && c == 3 && layout == VACV_NHWC && words_ok && knob(kKnobWarpV) != 1 && (w % 8) == 0 && ((uintptr_t)frames % 8) == 0 &&
+        (w_out % 4) == 0 && w_out <= 256 && ((uintptr_t)dst % 4) == 0 && n_crops <= 0x7fffffff / 6) {
+        // pack kernel: a CTA is `rows` whole output rows wide; taken when its last warp is not mostly idle
+        const int rows = 256 / w_out, threads = (rows * w_out + 31) & ~31;
+        if (rows * w_out * 100 >= threads * 85) {
+            const int bands = ceil_div(h_out, (4096 + w_out - 1) / w_out);
+            const int rows_per_cta = (ceil_div(h_out, bands) + rows - 1) / rows * rows;
+            dim3 grid(n_crops, ceil_div(h_out, rows_per_cta));
+            if (flags & VACV_FLAG_SIGNED_CHAR)
+                warp_affine_u8c3_pack_kernel<true><<<grid, threads, 0, s>>>((const uint8_t*)frames, frame_idx, minv, (uint8_t*)dst, w, h, w_out, h_out, g.frame_elems, rows, rows_per_cta, 0);
+            else
+                warp_affine_u8c3_pack_kernel<false><<<grid, threads, 0, s>>>((const uint8_t*)frames, frame_idx, minv, (uint8_t*)dst, w, h, w_out, h_out, g.frame_elems, rows, rows_per_cta, 0);
+            return check_launch("warp_affine");
         }
     }
     if (dtype == VACV_INT8 && c == 3 && layout == VACV_NHWC && words_ok) {

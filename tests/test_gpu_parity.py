@@ -562,6 +562,45 @@ def test_warp_affine_staged_many_tiles_per_cta(vacv, oracle):
         assert_same(host(a[i]), oracle.warp_affine(host(frames[idx[i]]), w, h, 3, NHWC, wo, ho, minv[i]))
 
 
+PACK_CASES = [
+    # (w, h, wo, ho): frames with rows of whole 8-byte words, output widths that are multiples of 4 -> the column-owning pack kernel
+    (320, 200, 112, 112),    # two output rows per pass, 7 whole warps
+    (320, 200, 100, 57),     # 200 threads in 7 warps (padding lanes), odd row count (half-filled last pass)
+    (1280, 720, 240, 240),   # one row per pass, 16 padding lanes
+    (336, 64, 64, 40),       # four rows per pass
+    (640, 368, 28, 9),       # nine rows per pass, one band
+    (328, 200, 112, 112),    # rows of 984 bytes: whole 8-byte words, but no 16-byte rows (no tensor map)
+]
+
+
+@pytest.mark.parametrize("case", range(len(PACK_CASES)))
+def test_warp_affine_u8_pack_kernel(vacv, oracle, case):
+    """u8 BGR warp_affine, column-owning kernel (64-bit tap loads, shuffle-packed stores): oracle, first-generation gather kernel
+    (VACV_WARP_V=1) and signed-char compat on crops that leave the frame on every side."""
+    w, h, wo, ho = PACK_CASES[case]
+    nf, n = 3, 10
+    frames = u8(70 + case, nf, h, w, 3)
+    r = np.random.default_rng(700 + case)
+    fwd = [_similarity(r.uniform(0.3, 1.4), r.uniform(-40, 40), r.uniform(0, w), r.uniform(0, h), wo, ho) for _ in range(n - 2)]
+    fwd += [[1, 0, 0, 0, 1, 0], [0.5, 0, 0, 0, 0.5, 0]]   # identity (every tap on a pixel centre), exact half scale
+    minv = np.array([vacv.invert_affine(m) for m in fwd], np.float32)
+    idx = (np.arange(n) % nf).astype(np.int32)
+    got = host(vacv.warp_affine(dev(frames), NHWC, dev(minv), wo, ho, dev(idx)))
+    got_sc = host(vacv.warp_affine(dev(frames), NHWC, dev(minv), wo, ho, dev(idx), vacv.FLAG_SIGNED_CHAR))
+    assert vacv.lib.vacv_cuda_set_tuning(b"WARP_V", 1) == 0
+    try:
+        first = host(vacv.warp_affine(dev(frames), NHWC, dev(minv), wo, ho, dev(idx)))
+        first_sc = host(vacv.warp_affine(dev(frames), NHWC, dev(minv), wo, ho, dev(idx), vacv.FLAG_SIGNED_CHAR))
+    finally:
+        vacv.lib.vacv_cuda_set_tuning(b"WARP_V", 0)
+    assert_same(got, first)
+    assert_same(got_sc, first_sc)
+    for i in range(n):
+        assert_same(got[i], oracle.warp_affine(frames[idx[i]], w, h, 3, NHWC, wo, ho, minv[i]))
+    for i in (0, n - 1):
+        assert_same(got_sc[i], oracle.warp_affine(frames[idx[i]], w, h, 3, NHWC, wo, ho, minv[i], signed_char=1))
+
+
 def test_warp_affine_grey_and_planar_batches(vacv, oracle):
     """Single-channel frames and CHW frames (c planes, one matrix) through the word-granular single-channel kernel."""
     w, h, wo, ho, nf, n = 320, 200, 112, 100, 3, 9
