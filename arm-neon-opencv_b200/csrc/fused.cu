@@ -19,8 +19,11 @@
 #include "host_util.cuh"
 #include "vacv_common.cuh"
 #include "fused_pipeline.cuh"
+#include "tma_host.cuh"
 #include "gather_u8c3.cuh"
+#include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <type_traits>
 #include <cstdlib>
 #include <vector>
@@ -306,13 +309,13 @@ static int host_linear_index(int d, double scale, int n_in) {
     return sx;
 }
 
-template <int FMT, typename OutT, bool kDense = false, int RIGHT = -1>
+template <int FMT, typename OutT, bool kDense = false, int RIGHT = -1, bool kMaps = false>
 static const void* pipe_kernel_ncol(int ncol) {
     switch (ncol) {
-        case 1: return (const void*)nv_resize_normalize_chw_pipe_kernel<FMT, OutT, 1, kDense, RIGHT>;
-        case 2: return (const void*)nv_resize_normalize_chw_pipe_kernel<FMT, OutT, 2, kDense, RIGHT>;
-        case 3: return (const void*)nv_resize_normalize_chw_pipe_kernel<FMT, OutT, 3, kDense, RIGHT>;
-        default: return (const void*)nv_resize_normalize_chw_pipe_kernel<FMT, OutT, 4, kDense, RIGHT>;
+        case 1: return (const void*)nv_resize_normalize_chw_pipe_kernel<FMT, OutT, 1, kDense, RIGHT, kMaps>;
+        case 2: return (const void*)nv_resize_normalize_chw_pipe_kernel<FMT, OutT, 2, kDense, RIGHT, kMaps>;
+        case 3: return (const void*)nv_resize_normalize_chw_pipe_kernel<FMT, OutT, 3, kDense, RIGHT, kMaps>;
+        default: return (const void*)nv_resize_normalize_chw_pipe_kernel<FMT, OutT, 4, kDense, RIGHT, kMaps>;
     }
 }
 template <int FMT, int RIGHT>
@@ -320,7 +323,11 @@ static const void* pipe_kernel_pairs(int ncol) {   // fp16 column pairs: even co
     return ncol <= 2 ? (const void*)nv_resize_normalize_chw_pipe_kernel<FMT, __half2, 2, false, RIGHT>
                      : (const void*)nv_resize_normalize_chw_pipe_kernel<FMT, __half2, 4, false, RIGHT>;
 }
-static const void* pipe_kernel_for(int fmt, bool half_out, bool pairs, bool dense, int ncol, bool any_right) {
+static const void* pipe_kernel_for(int fmt, bool half_out, bool pairs, bool dense, int ncol, bool any_right, bool dense_maps) {
+    if (dense_maps) {   // padded NV12 / NV21 surfaces through tensor maps, fp32 planes without letterbox: the dense tile loops
+        if (any_right) return fmt == kFmtVU ? pipe_kernel_ncol<kFmtVU, float, true, 1, true>(ncol) : pipe_kernel_ncol<kFmtUV, float, true, 1, true>(ncol);
+        return fmt == kFmtVU ? pipe_kernel_ncol<kFmtVU, float, true, 0, true>(ncol) : pipe_kernel_ncol<kFmtUV, float, true, 0, true>(ncol);
+    }
     if (half_out && pairs) {
         if (any_right) return fmt == kFmtVU ? pipe_kernel_pairs<kFmtVU, 1>(ncol) : fmt == kFmtUV ? pipe_kernel_pairs<kFmtUV, 1>(ncol) : pipe_kernel_pairs<kFmtPlanar, 1>(ncol);
         return fmt == kFmtVU ? pipe_kernel_pairs<kFmtVU, 0>(ncol) : fmt == kFmtUV ? pipe_kernel_pairs<kFmtUV, 0>(ncol) : pipe_kernel_pairs<kFmtPlanar, 0>(ncol);
@@ -353,6 +360,8 @@ struct PipePlan {
     YuvSource y; int w_out, h_out, out_dtype; Canvas cv; bool pairs_ok; int device, knob_gen;
     // plan
     bool eligible; PipeGeom g; const void* kern; int threads, per_sm, sms; size_t smem;
+    // padded surfaces through tensor maps (g.tile_maps): the maps bind the surface pool's address and are re-encoded when it changes
+    PipeMaps maps; const void* maps_src; int maps_batch;
 };
 
 static bool same_key(const PipePlan& p, const YuvSource& y, int w_out, int h_out, int out_dtype, const Canvas& cv, bool pairs_ok, int device) {
@@ -387,29 +396,54 @@ static int build_pipe_plan(PipePlan& plan) {
     // reads at pitch 2048).  VACV_PIPE_ROWS=1 stages only the rows' own bytes with one bulk copy per row -- measured slower on B200
     // (1080p -> 640x640 x256, same box: nv12 p2048 fp32 0.447 vs 0.407 ms, i420 p2048 fp16 0.389 vs 0.309 ms): 25-40 copies of
     // <= 1920 bytes per tile cost more in the copy engine than the padding costs in DRAM.
+    // Round 2, default: one tensor-map box per band and plane (rows' own bytes only, ONE copy per plane): needs rows of whole 16-byte
+    // chunks, <= 256 8-byte elements per box row and at most kPipeMapHeights distinct band heights; otherwise whole bands.
+    // VACV_PIPE_ROWS=2 forces whole bands (A/B).
     const int y_row16 = (w + 15) & ~15, c_row16 = ((planar ? w / 2 : w) + 15) & ~15;
-    const bool by_row = (y.y_pitch > y_row16 || y.c_pitch > c_row16) && knob(kKnobPipeRows) != 0;
-    g.sy_pitch = by_row ? y_row16 : y.y_pitch;
-    g.sc_pitch = by_row ? c_row16 : y.c_pitch;
+    const bool padded = y.y_pitch > y_row16 || y.c_pitch > c_row16;
+    const bool by_row = padded && knob(kKnobPipeRows) == 1;
+    bool by_map = padded && knob(kKnobPipeRows) == 0 && (w % 16) == 0 && (!planar || (w % 32) == 0) && w <= 2048 && encode_tiled_fn() != nullptr;
     int best_TH = 0;
     size_t best_smem = 0;
-    for (int TH = 8; TH >= 1; --TH) {
-        int yrows = 0, crows = 0;
-        for (int d0 = 0; d0 < h_out; d0 += TH) {
-            const int d1 = std::min(d0 + TH, h_out) - 1;
-            const int y0 = sy[d0], y1 = sy[d1] + 1;
-            yrows = std::max(yrows, y1 - y0 + 1);
-            crows = std::max(crows, (y1 >> 1) - (y0 >> 1) + 1);
+    for (int attempt = 0; attempt < 2 && !best_TH; ++attempt) {
+        g.sy_pitch = by_row || by_map ? y_row16 : y.y_pitch;
+        g.sc_pitch = by_row || by_map ? c_row16 : y.c_pitch;
+        for (int TH = 8; TH >= 1; --TH) {
+            int yrows = 0, crows = 0;
+            for (int d0 = 0; d0 < h_out; d0 += TH) {
+                const int d1 = std::min(d0 + TH, h_out) - 1;
+                const int y0 = sy[d0], y1 = sy[d1] + 1;
+                yrows = std::max(yrows, y1 - y0 + 1);
+                crows = std::max(crows, (y1 >> 1) - (y0 >> 1) + 1);
+            }
+            const size_t ystage = ((size_t)yrows * g.sy_pitch + 127) & ~(size_t)127;
+            const size_t cband = ((size_t)crows * g.sc_pitch + 127) & ~(size_t)127;
+            const size_t cstage = planar ? 2 * cband : cband;
+            const size_t smem = table_bytes + 2 * (ystage + cstage);
+            if (smem + static_bytes <= 113 * 1024 || (TH == 1 && smem + static_bytes <= 226 * 1024)) {   // 2 CTAs / SM
+                best_TH = TH; best_smem = smem; g.ystage = (int)ystage; g.cstage = (int)cstage; g.vstage_off = (int)cband;
+                break;
+            }
         }
-        const size_t ystage = ((size_t)yrows * g.sy_pitch + 127) & ~(size_t)127;
-        const size_t cband = ((size_t)crows * g.sc_pitch + 127) & ~(size_t)127;
-        const size_t cstage = planar ? 2 * cband : cband;
-        const size_t smem = table_bytes + 2 * (ystage + cstage);
-        if (smem + static_bytes <= 113 * 1024 || (TH == 1 && smem + static_bytes <= 226 * 1024)) {   // 2 CTAs / SM
-            best_TH = TH; best_smem = smem; g.ystage = (int)ystage; g.cstage = (int)cstage; g.vstage_off = (int)cband;
-            break;
+        if (!by_map) break;
+        if (best_TH) {   // the band heights that occur with this tile height: one tensor map each
+            std::memset(&plan.maps, 0, sizeof(plan.maps));
+            int ny = 0, nc = 0;
+            bool fits = true;
+            for (int d0 = 0; d0 < h_out && fits; d0 += best_TH) {
+                const int d1 = std::min(d0 + best_TH, h_out) - 1;
+                const int y0 = sy[d0], y1 = sy[d1] + 1;
+                const int yr = y1 - y0 + 1, cr = (y1 >> 1) - (y0 >> 1) + 1;
+                if (std::find(plan.maps.yh, plan.maps.yh + ny, yr) == plan.maps.yh + ny) { if (ny < kPipeMapHeights) plan.maps.yh[ny++] = yr; else fits = false; }
+                if (std::find(plan.maps.ch, plan.maps.ch + nc, cr) == plan.maps.ch + nc) { if (nc < kPipeMapHeights) plan.maps.ch[nc++] = cr; else fits = false; }
+            }
+            if (fits) break;
         }
+        by_map = false;   // second attempt: whole bands, padding included
+        best_TH = 0;
     }
+    g.tile_maps = by_map ? 1 : 0;
+    plan.maps_src = nullptr;
     if (!best_TH) return 0;
     g.TH = best_TH;
     g.tiles_per_frame = (h_out + best_TH - 1) / best_TH;
@@ -440,7 +474,8 @@ static int build_pipe_plan(PipePlan& plan) {
     const int threads = std::min(ncol == 1 ? 640 : kPipeThreads, ((w_out + ncol - 1) / ncol + 31) & ~31);
     const bool dense = y.y_pitch == w && y.c_pitch == w && y.c_off == (size_t)w * h && y.frame_stride == (size_t)w * h * 3 / 2 &&
                        cv.w == w_out && cv.h == h_out;
-    const void* kern = pipe_kernel_for(y.fmt, half_out, pairs, dense, ncol, any_right);
+    const bool dense_maps = by_map && !half_out && !planar && cv.w == w_out && cv.h == h_out && g.sy_pitch == w && g.sc_pitch == w;
+    const void* kern = pipe_kernel_for(y.fmt, half_out, pairs, dense, ncol, any_right, dense_maps);
     // the opt-in limit, not this shape's size: plans of other host threads for the same kernel must stay launchable
     int optin = 0;
     cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, plan.device);
@@ -484,7 +519,25 @@ static int try_launch_pipe(const uint8_t* src, void* dst, int out_dtype, int bat
     if (total > 0x7fffffffLL - 4096) return 0;
     g.total_tiles = (int)total;
     const int grid = (int)std::min<long long>(total, (long long)plan.sms * plan.per_sm);
-    void* args[] = {(void*)&src, (void*)&dst, (void*)&g, (void*)&mean, (void*)&stddev};
+    if (g.tile_maps && (pp->maps_src != src || pp->maps_batch != batch)) {   // (re-)encode the maps for this surface pool: frames are the third dimension
+        const YuvSource& ys = plan.y;
+        const bool planar = ys.fmt == kFmtPlanar;
+        const cuuint64_t frames = (cuuint64_t)batch;
+        const int cw8 = (planar ? ys.w / 2 : ys.w) / 8, chh = (ys.h + 1) / 2;
+        bool ok = true;
+        for (int k = 0; k < kPipeMapHeights && ok; ++k) {
+            if (pp->maps.yh[k])
+                ok = encode_map_3d(&pp->maps.y[k], CU_TENSOR_MAP_DATA_TYPE_UINT64, src, ys.w / 8, ys.h, frames, ys.y_pitch, ys.frame_stride, ys.w / 8, pp->maps.yh[k], 1);
+            if (ok && pp->maps.ch[k]) {
+                ok = encode_map_3d(&pp->maps.c[k], CU_TENSOR_MAP_DATA_TYPE_UINT64, src + ys.c_off, cw8, chh, frames, ys.c_pitch, ys.frame_stride, cw8, pp->maps.ch[k], 1);
+                if (ok && planar)
+                    ok = encode_map_3d(&pp->maps.c2[k], CU_TENSOR_MAP_DATA_TYPE_UINT64, src + ys.c2_off, cw8, chh, frames, ys.c_pitch, ys.frame_stride, cw8, pp->maps.ch[k], 1);
+            }
+        }
+        if (!ok) return set_error(VACV_ERR_CUDA, "nv_resize_normalize_chw: cuTensorMapEncodeTiled failed");
+        pp->maps_src = src; pp->maps_batch = batch;
+    }
+    void* args[] = {(void*)&src, (void*)&dst, (void*)&g, (void*)&mean, (void*)&stddev, (void*)&pp->maps};
     const cudaError_t e = cudaLaunchKernel(plan.kern, dim3(grid), dim3(plan.threads), args, plan.smem, s);
     if (e != cudaSuccess) return set_error(VACV_ERR_CUDA, "nv_resize_normalize_chw: %s", cudaGetErrorString(e));
     return 1;

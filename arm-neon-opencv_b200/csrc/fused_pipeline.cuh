@@ -13,6 +13,7 @@
 //           cached per chroma row (two luma rows share one), H of the lower row is carried to the next output row
 //           when it starts there.  out = table[c][(H0*cy0 + H1*cy1) >> 22], stored 128 B / warp / plane, streaming.
 #pragma once
+#include <cuda.h>   // CUtensorMap (type only; the encoder is resolved at run time, tma_host.cuh)
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -43,6 +44,17 @@ struct PipeGeom {
     // letterbox canvas = result and x0 = y0 = 0
     int canvas_w, canvas_h, x0, y0;
     int bf16;               // 16-bit outputs: table holds bfloat16 instead of half
+    int tile_maps;          // padded surfaces staged through tensor maps (PipeMaps below)
+};
+
+// Padded decoder surfaces (pitch >= row + 16), default since round 2: a tile's luma / chroma band is ONE tensor-map box of
+// [band rows] x [w bytes] (cp.async.bulk.tensor, SASS UTMALDG) -- only the rows' own bytes leave DRAM and land densely in the stage,
+// one copy per plane like the dense path.  A box has a fixed row count, so there is one map per band height that occurs (the
+// heights of a linear scale take two or three values); frames are the third tensor dimension.
+constexpr int kPipeMapHeights = 4;
+struct PipeMaps {
+    CUtensorMap y[kPipeMapHeights], c[kPipeMapHeights], c2[kPipeMapHeights];   // luma, chroma (or U), V -- one per band height
+    int yh[kPipeMapHeights], ch[kPipeMapHeights];                               // the band heights (unused slots 0)
 };
 
 enum { kFmtVU = 0, kFmtUV = 1, kFmtPlanar = 2 };   // interleaved chroma V-first (NV21), U-first (NV12), separate U and V planes (I420 / YV12)
@@ -69,6 +81,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
                  "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void pipe_tma_load_3d(uint32_t smem_dst, const void* tmap, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_dst), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
 }
 
 // ---- explicit shared-window accesses (32-bit addresses: no generic->shared conversion in the inner loop)
@@ -402,14 +419,36 @@ __device__ __noinline__ void issue_band_rows(const PipeGeom& g, const uint8_t* f
     }
 }
 
+// Padded surfaces, default: the band of a tile is one tensor-map box per plane (PipeMaps), only the rows' own bytes leave DRAM.
+// Out of line for the same reason as issue_band_rows.
+template <int FMT>
+__device__ __noinline__ void issue_band_maps(const PipeMaps* maps, uint32_t st, int ystage, int vstage_off, int sy_pitch, int sc_pitch,
+                                             uint64_t* bar, int y_first, int y_last, int frame) {
+    const int c_first = y_first >> 1, c_last = y_last >> 1;
+    const int yrows = y_last - y_first + 1, crows = c_last - c_first + 1;
+    int ky = 0, kc = 0;
+#pragma unroll
+    for (int k = 1; k < kPipeMapHeights; ++k) {
+        if (maps->yh[k] == yrows) ky = k;
+        if (maps->ch[k] == crows) kc = k;
+    }
+    mbar_expect_tx(bar, (uint32_t)yrows * sy_pitch + (uint32_t)((FMT == kFmtPlanar ? 2 : 1) * crows) * sc_pitch);
+    pipe_tma_load_3d(st, &maps->y[ky], 0, y_first, frame, bar);
+    pipe_tma_load_3d(st + ystage, &maps->c[kc], 0, c_first, frame, bar);
+    if (FMT == kFmtPlanar) pipe_tma_load_3d(st + ystage + vstage_off, &maps->c2[kc], 0, c_first, frame, bar);
+}
+
 // kDense: the reference's own layout (tensor.cpp:524: no pitch; chroma right after luma) -- one pitch register, constants folded.
 // RIGHT: -1 = whether any right tap has weight is found out at run time (both tile loops in the kernel), 0 / 1 = known to the launcher:
 // one tap rule per kernel, so that the loop a launch never takes does not shape the register allocation and schedule of the one it
 // does (config 2, same box: 0.364 -> 0.351 ms).
-template <int FMT, typename OutT, int NCOL, bool kDense, int RIGHT = -1>
+// kMaps (with kDense): the SOURCE is a padded surface staged through tensor maps -- the stage then looks exactly like the dense case
+// (rows w bytes apart), so the dense tile loops and output addressing apply; only the copy issue differs.
+template <int FMT, typename OutT, int NCOL, bool kDense, int RIGHT = -1, bool kMaps = false>
 __global__ void __launch_bounds__(NCOL == 1 ? 640 : kPipeThreads, NCOL <= 2 ? 2 : 1)
 nv_resize_normalize_chw_pipe_kernel(const uint8_t* __restrict__ src, OutT* __restrict__ dst, PipeGeom g,
-                                    const float* __restrict__ mean, const float* __restrict__ stddev) {
+                                    const float* __restrict__ mean, const float* __restrict__ stddev,
+                                    const __grid_constant__ PipeMaps maps) {
     extern __shared__ __align__(128) uint8_t dyn_smem[];     // [s_sy: ho][s_cy: ho][pad] 2 x (ystage + cstage)
     typedef OutOps<OutT> Ops;
     static_assert(NCOL % Ops::kCols == 0, "column pairs need an even column count");
@@ -425,7 +464,8 @@ nv_resize_normalize_chw_pipe_kernel(const uint8_t* __restrict__ src, OutT* __res
     const size_t row_bytes = kDense ? (size_t)g.wo * Ops::kElem : (size_t)g.canvas_w * Ops::kElem;
     const int y_pitch = kDense ? g.w : g.y_pitch, c_pitch = kDense ? g.w : g.c_pitch;
     const int sy_pitch = kDense ? g.w : g.sy_pitch, sc_pitch = kDense ? g.w : g.sc_pitch;      // row pitches of the staged bands
-    const bool by_row = !kDense && (sy_pitch != y_pitch || sc_pitch != c_pitch);
+    const bool by_map = kDense ? kMaps : g.tile_maps != 0;
+    const bool by_row = !kDense && !by_map && (sy_pitch != y_pitch || sc_pitch != c_pitch);
     const size_t frame_stride = kDense ? (size_t)g.w * g.h * 3 / 2 : g.frame_stride, c_off = kDense ? (size_t)g.w * g.h : g.c_off;
     const uint32_t stages_s = smem_u32(stages), sy_s = smem_u32(s_sy), cy_s = smem_u32(s_cy), lut_s = smem_u32(lut);
 
@@ -480,6 +520,12 @@ nv_resize_normalize_chw_pipe_kernel(const uint8_t* __restrict__ src, OutT* __res
         bulk_g2s(st + g.ystage, f + c_off + (size_t)c_first * c_pitch, cbytes, &full_bar[b]);
         if (FMT == kFmtPlanar) bulk_g2s(st + g.ystage + g.vstage_off, f + g.c2_off + (size_t)c_first * c_pitch, cbytes, &full_bar[b]);
     };
+    auto issue_maps = [&](int tile, int b) {   // padded surface, one thread
+        const int frame = tile / g.tiles_per_frame, dy0 = (tile - frame * g.tiles_per_frame) * g.TH;
+        const int th = min(g.TH, g.ho - dy0);
+        issue_band_maps<FMT>(&maps, stages_s + (uint32_t)b * (g.ystage + g.cstage), g.ystage, g.vstage_off, sy_pitch, sc_pitch, &full_bar[b],
+                             s_sy[dy0], s_sy[dy0 + th - 1] + 1, frame);
+    };
     auto issue_rows = [&](int tile, int b) {   // padded surface; called by every lane of warp 0
         const int frame = tile / g.tiles_per_frame, dy0 = (tile - frame * g.tiles_per_frame) * g.TH;
         const int th = min(g.TH, g.ho - dy0);
@@ -489,6 +535,7 @@ nv_resize_normalize_chw_pipe_kernel(const uint8_t* __restrict__ src, OutT* __res
     int tile = blockIdx.x;
     if (tile < g.total_tiles) {
         if (by_row) { if (tid < 32) issue_rows(tile, 0); }
+        else if (by_map) { if (tid == 0) issue_maps(tile, 0); }
         else if (tid == 0) issue(tile, 0);
     }
     __syncthreads();
@@ -499,6 +546,7 @@ nv_resize_normalize_chw_pipe_kernel(const uint8_t* __restrict__ src, OutT* __res
         const int next = tile + gridDim.x;
         if (next < g.total_tiles) {   // stage b^1 was released by the sync below
             if (by_row) { if (tid < 32) issue_rows(next, b ^ 1); }
+            else if (by_map) { if (tid == 0) issue_maps(next, b ^ 1); }
             else if (tid == 0) issue(next, b ^ 1);
         }
         mbar_wait(&full_bar[b], (it >> 1) & 1);

@@ -96,12 +96,13 @@ def c2_surfaces(iters):
         ms, _ = timeit(lambda: vacv.yuv_resize_normalize_chw(src, fmt, w, h, wo, ho, mean, std, y_pitch=yp, c_pitch=cp, batch=b,
                                                              half=half, out=out), iters)
         report(f"c2s fused {name} 1080p->640x640 x{b}", ms, b * wo * ho, b * (w * h * 3 // 2 + wo * ho * (6 if half else 12)))
-        if yp != w:   # A/B: one bulk copy per row (no padding bytes read) instead of one per band
-            vacv.lib.vacv_cuda_set_tuning(b"PIPE_ROWS", 1)
-            ms, _ = timeit(lambda: vacv.yuv_resize_normalize_chw(src, fmt, w, h, wo, ho, mean, std, y_pitch=yp, c_pitch=cp, batch=b,
-                                                                 half=half, out=out), iters)
-            vacv.lib.vacv_cuda_set_tuning(b"PIPE_ROWS", 0)
-            report("   same, one bulk copy per row, padding not read (PIPE_ROWS=1)", ms, b * wo * ho, b * (w * h * 3 // 2 + wo * ho * (6 if half else 12)))
+        if yp != w:   # A/B of the three staging forms on padded surfaces: tensor-map boxes (default), one bulk copy per row, whole bands
+            for mode, what in ((1, "one bulk copy per row, padding not read (PIPE_ROWS=1)"), (2, "whole bands, padding read (PIPE_ROWS=2, the round-1 path)")):
+                vacv.lib.vacv_cuda_set_tuning(b"PIPE_ROWS", mode)
+                ms, _ = timeit(lambda: vacv.yuv_resize_normalize_chw(src, fmt, w, h, wo, ho, mean, std, y_pitch=yp, c_pitch=cp, batch=b,
+                                                                     half=half, out=out), iters)
+                vacv.lib.vacv_cuda_set_tuning(b"PIPE_ROWS", 0)
+                report(f"   same, {what}", ms, b * wo * ho, b * (w * h * 3 // 2 + wo * ho * (6 if half else 12)))
     src = rand_u8(b * w * h * 3 // 2)
     for name, dt, tdt, eb in [("f32", vacv.FP32, torch.float32, 4), ("bf16", vacv.BF16, torch.bfloat16, 2)]:
         out = torch.empty((b, 3, ho, wo), dtype=tdt, device="cuda")

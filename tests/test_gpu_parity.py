@@ -753,14 +753,15 @@ def test_fused_pipeline_yuv_surfaces(vacv, oracle, fmt, half, w, h, yp, cp, wo, 
         assert_same(got, want.astype(np.float16))    # fp16 = the exact fp32 result rounded to nearest even
     else:
         assert_same(got, want)
-    if y_pitch != w:   # padded surfaces: the opt-in variant that copies row by row (VACV_PIPE_ROWS) must give the same bytes
-        assert vacv.lib.vacv_cuda_set_tuning(b"PIPE_ROWS", 1) == 0
-        try:
-            rows = host(vacv.yuv_resize_normalize_chw(dev(buf), fmt, w, h, wo, ho, dev(MEAN), dev(STD), y_pitch=y_pitch,
-                                                      c_pitch=c_pitch, frame_stride=stride, batch=b, half=half))
-        finally:
-            vacv.lib.vacv_cuda_set_tuning(b"PIPE_ROWS", 0)
-        assert_same(rows, got)
+    if y_pitch != w:   # padded surfaces: tensor-map boxes by default (where eligible); one bulk copy per row (VACV_PIPE_ROWS=1) and
+        for mode in (1, 2):   # whole bands with their padding (VACV_PIPE_ROWS=2, the round-1 path) must give the same bytes
+            assert vacv.lib.vacv_cuda_set_tuning(b"PIPE_ROWS", mode) == 0
+            try:
+                other = host(vacv.yuv_resize_normalize_chw(dev(buf), fmt, w, h, wo, ho, dev(MEAN), dev(STD), y_pitch=y_pitch,
+                                                           c_pitch=c_pitch, frame_stride=stride, batch=b, half=half))
+            finally:
+                vacv.lib.vacv_cuda_set_tuning(b"PIPE_ROWS", 0)
+            assert_same(other, got)
 
 
 def _bf16_round(x):
