@@ -22,6 +22,7 @@ enum Knob {
     kKnobPipeRows,         // VACV_PIPE_ROWS            fused pipeline on padded surfaces: one bulk copy per row instead of whole bands (padding included)
     kKnobStreamQpt,        // VACV_STREAM_QPT           16-byte groups per thread of the streaming kernels' grids (0 = default)
     kKnobWarpV,            // VACV_WARP_V               u8 BGR warp_affine: 1 = first-generation flat-order gather kernel (0 = automatic: column-owning pack kernel where eligible)
+    kKnobLinearV,          // VACV_LINEAR_V             u8 BGR bilinear: 1 = rational scales stay on the persistent pipeline (0 = automatic: periodic walker where eligible)
     kKnobCount
 };
 int knob(Knob k);

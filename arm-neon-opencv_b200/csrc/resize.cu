@@ -674,6 +674,9 @@ extern "C" int vacv_cuda_resize(const void* src, void* dst, int batch, int w, in
         uint8_t* dp = (uint8_t*)dst + (size_t)i0 * g.dst_image * es;
         const bool c3_words = g.c == 3 && (((size_t)w * h * 3) % 4) == 0 && ((uintptr_t)src % 4) == 0 && (size_t)w * h * 3 < 0xfffffff0ull;
         if (!cubic && dtype == VACV_INT8 && c3_words && !(flags & (VACV_FLAG_NEON_RULE | VACV_FLAG_DIRECT_GATHER)) && !knob(kKnobNoRpipe)) {
+            const int rcp = try_launch_resize_linear3_period(sp, dp, ni, w, h, w_out, h_out, (flags & VACV_FLAG_SIGNED_CHAR) != 0, s);   // rational scales
+            if (rcp < 0) return rcp;
+            if (rcp > 0) continue;
             const int rc = try_launch_resize_pipe_u8c3(sp, dp, ni, w, h, w_out, h_out, (flags & VACV_FLAG_SIGNED_CHAR) != 0, kRpOutU8, nullptr, nullptr, s);
             if (rc < 0) return rc;
             if (rc > 0) continue;

@@ -18,6 +18,10 @@ int check_launch(const char* what);
 int try_launch_resize_pipe_u8c3(const uint8_t* src, void* dst, int images, int w, int h, int wo, int ho, bool signed_char, int out_mode,
                                 const float* mean, const float* stddev, cudaStream_t s, int c = 3);   // c = 1: single planes (u8 output only)
 
+// resize_linear_period.cu: periodic walker for u8 BGR bilinear at rational horizontal scales (resize_linear3_period.cuh).
+// Returns 1 = launched, 0 = shape not eligible, < 0 = error.
+int try_launch_resize_linear3_period(const uint8_t* src, uint8_t* dst, int images, int w, int h, int wo, int ho, bool signed_char, cudaStream_t s);
+
 #define VACV_REQUIRE(cond, ...)                                                 \
     do {                                                                        \
         if (!(cond)) return ::vacv::set_error(VACV_ERR_INVALID_ARG, __VA_ARGS__); \

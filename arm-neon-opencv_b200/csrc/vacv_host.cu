@@ -22,7 +22,7 @@ static std::atomic<int> g_knobs[kKnobCount];
 static std::atomic<int> g_knob_gen{0};
 static std::once_flag g_knob_once;
 static const char* const kKnobNames[kKnobCount] = {"PIPE_NCOL", "RPIPE_NCOL", "WARP_GATHER", "NO_RPIPE", "RESIZE_NORMALIZE_GATHER",
-                                                    "WALK_SEGS", "WALK_SYNC", "WALK2_SYNC", "CUBIC3", "CUBIC_V", "PIPE_ROWS", "STREAM_QPT", "WARP_V"};
+                                                    "WALK_SEGS", "WALK_SYNC", "WALK2_SYNC", "CUBIC3", "CUBIC_V", "PIPE_ROWS", "STREAM_QPT", "WARP_V", "LINEAR_V"};
 static void init_knobs() {
     for (int k = 0; k < kKnobCount; ++k) {
         char name[64];

@@ -232,6 +232,42 @@ def test_resize_linear_u8_default_path(vacv, oracle, sz, signed):
         assert_same(got[i], oracle.resize_linear(src[i], w, h, 3, NHWC, wo, ho, signed_char=int(signed)))
 
 
+LINEAR_PERIOD_CASES = [
+    # rational horizontal scales the periodic walker takes (3:2 / 4:3 / 2:1, rows of whole 16-byte chunks); any vertical scale <= 2
+    ((192, 96), (128, 64)),      # 3:2, one partly filled warp strip
+    ((480, 100), (320, 77)),     # 3:2, two strips (the second with 8 owning lanes), generic vertical scale
+    ((1920, 270), (1280, 180)),  # 3:2, five strips
+    ((1920, 100), (1280, 200)),  # 3:2, vertical up-scaling (several output rows per walk step)
+    ((384, 64), (256, 64)),      # 3:2, vertical scale 1 (the last two rows share a source row)
+    ((384, 128), (256, 64)),     # 3:2, vertical 2:1 (the limit: every source row still used)
+    ((384, 700), (256, 600)),    # 3:2, more than one vertical segment per column strip
+    ((128, 60), (96, 45)),       # 4:3 both ways
+    ((2560, 90), (1920, 77)),    # 4:3, five strips
+    ((128, 50), (64, 25)),       # 2:1 both ways
+    ((3840, 64), (1920, 40)),    # 2:1, fifteen strips
+]
+
+
+@pytest.mark.parametrize("signed", [False, True])
+@pytest.mark.parametrize("case", range(len(LINEAR_PERIOD_CASES)))
+def test_resize_linear_u8_periodic_walker(vacv, oracle, case, signed):
+    """u8 BGR bilinear at rational horizontal scales: the periodic walker (adjacent columns per thread, compile-time tap positions,
+    bulk-copy ring) against the oracle and against the persistent pipeline (VACV_LINEAR_V=1), both char signedness rules."""
+    (w, h), (wo, ho) = LINEAR_PERIOD_CASES[case]
+    b = 3
+    src = u8(60 + case, b, h, w, 3)
+    flags = vacv.FLAG_SIGNED_CHAR if signed else 0
+    got = host(vacv.resize(dev(src), NHWC, wo, ho, vacv.INTER_LINEAR, flags))
+    assert vacv.lib.vacv_cuda_set_tuning(b"LINEAR_V", 1) == 0
+    try:
+        pipe = host(vacv.resize(dev(src), NHWC, wo, ho, vacv.INTER_LINEAR, flags))
+    finally:
+        vacv.lib.vacv_cuda_set_tuning(b"LINEAR_V", 0)
+    assert_same(got, pipe)
+    for i in range(b):
+        assert_same(got[i], oracle.resize_linear(src[i], w, h, 3, NHWC, wo, ho, signed_char=int(signed)))
+
+
 def test_resize_linear_u8_config1_fixture_vs_reference(vacv):
     img = load_fixture("universe1920x1080")
     if img is None or not ref_available():
