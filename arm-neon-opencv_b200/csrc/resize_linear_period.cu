@@ -98,7 +98,8 @@ template <bool kSigned>
 int launch_any(const uint8_t* src, uint8_t* dst, int images, int w, int h, int wo, int ho, cudaStream_t s) {
     int rc = launch_linear3_period<3, 2, 4, kSigned>(src, dst, images, w, h, wo, ho, s);            // 3 : 2 (1920 -> 1280): 8 columns per thread
     if (rc == 0) rc = launch_linear3_period<4, 3, 4, kSigned>(src, dst, images, w, h, wo, ho, s);   // 4 : 3 (2560 -> 1920): 12 columns
-    if (rc == 0) rc = launch_linear3_period<2, 1, 4, kSigned>(src, dst, images, w, h, wo, ho, s);   // 2 : 1 (3840 -> 1920): 4 columns
+    if (rc == 0 && knob(kKnobLinearV) != 2) rc = launch_linear3_period<2, 1, 8, kSigned>(src, dst, images, w, h, wo, ho, s);   // 2 : 1 (3840 -> 1920): 8 columns
+    if (rc == 0) rc = launch_linear3_period<2, 1, 4, kSigned>(src, dst, images, w, h, wo, ho, s);   // 2 : 1, widths that are not multiples of 8 columns (LINEAR_V=2: always): 4 columns
     return rc;
 }
 

@@ -27,18 +27,28 @@ PEAK, _ = measured_peak()
 RESULTS = []
 
 
+GATE_CYCLES = 400_000   # ~0.2 ms of torch.cuda._sleep ahead of every sample
+INNER = 4               # back-to-back launches per sample
+
+
 def timeit(fn, iters, warmup=5):
+    """Median / min DEVICE time of one call of fn, in ms.  A sample = INNER back-to-back calls between two CUDA events on the launching
+    stream, queued while the GPU still spins in a gate kernel -- so the events bracket the launches' execution only.  (Until round 2
+    a sample was one call issued to an idle GPU: the host's 10-25 us between recording the first event and the launch were inside
+    every figure, which matters for the operators that take 0.05-0.15 ms.)"""
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
     times = []
     for _ in range(iters):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda._sleep(GATE_CYCLES)
         e0.record()
-        fn()
+        for _ in range(INNER):
+            fn()
         e1.record()
         e1.synchronize()
-        times.append(e0.elapsed_time(e1))
+        times.append(e0.elapsed_time(e1) / INNER)
     return statistics.median(times), min(times)
 
 
