@@ -22,8 +22,11 @@ __device__ __forceinline__ uint2 ldg_u64(const uint8_t* p) {
     return __ldg(reinterpret_cast<const uint2*>(p));
 }
 
-// grid = (crops, bands); blockDim.x = rows * wo (rows = output rows per pass)
-template <bool kSigned>
+// grid = (crops, bands); blockDim.x = rows * wo rounded up to whole warps (rows = output rows per pass).  Branch-free: a pixel
+// outside the frame or the band loads from offset 0 and its result is discarded.  U = passes per loop iteration, the tap loads of U
+// pixels of a thread issued before the first blend: U = 2 measured no faster than U = 1 (0.223 vs 0.220 ms on config 3's shape) --
+// long-scoreboard is the top stall, but what bounds the kernel is the L1 data pipe (75 % of its wavefront peak), not load latency.
+template <bool kSigned, int U>
 __global__ void __launch_bounds__(256) warp_affine_u8c3_pack_kernel(const uint8_t* __restrict__ frames, const int* __restrict__ frame_idx,
                                                                      const float* __restrict__ minv, uint8_t* __restrict__ dst,
                                                                      int w, int h, int wo, int ho, size_t frame_bytes,
@@ -46,46 +49,55 @@ __global__ void __launch_bounds__(256) warp_affine_u8c3_pack_kernel(const uint8_
     const size_t o_step = (size_t)rows * wo * 3;   // blockDim.x may hold padding lanes
     float fdy = (float)(y0 + ty);
     const float frows = (float)rows;
-    for (int yb = y0; yb < y1; yb += rows, fdy += frows, o += o_step) {   // CTA-uniform loop: the shuffle below needs whole warps
-        const bool valid = ty < rows && yb + ty < y1;   // ty >= rows: padding lanes of the last warp
-        uint32_t lo = 0;
-        float fx = (ax + m1 * fdy) + m2;
-        float fy = (ay + m4 * fdy) + m5;
-        const float flx = floorf(fx), fly = floorf(fy);
-        const int sx = (int)flx, sy = (int)fly;
-        if (valid && !(sy < 0 || sy >= hm1 || sx < 0 || sx >= wm1)) {
+    const bool live = ty < rows;                   // false: padding lanes of the last warp
+    for (int yb = y0; yb < y1; yb += U * rows) {   // CTA-uniform loop: the shuffle below needs whole warps
+        bool valid[U], in[U];
+        uint32_t cx[U], q0[U], q1[U];
+        unsigned r[U];
+        uint2 t0[U], u0[U], t1[U], u1[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            valid[u] = live && yb + u * rows + ty < y1;
+            float fx = (ax + m1 * fdy) + m2;
+            float fy = (ay + m4 * fdy) + m5;
+            fdy += frows;
+            const float flx = floorf(fx), fly = floorf(fy);
+            const int sx = (int)flx, sy = (int)fly;
+            in[u] = valid[u] && !(sy < 0 || sy >= hm1 || sx < 0 || sx >= wm1);
             fx -= flx;
             fy -= fly;
             // SATURATE_CAST_SHORT of values in [0, 2048] (macro.h:25-30) == trunc(x + 0.5f); see warp_taps_fast
             const int cx0 = (int)((1.f - fx) * 2048.f + 0.5f), cy0 = (int)((1.f - fy) * 2048.f + 0.5f);
-            const uint32_t cx = (uint32_t)cx0 | ((uint32_t)(2048 - cx0) << 16);
-            const int cy0q = cy0 << 2, cy1q = 8192 - cy0q;   // 4 * cy: 255 * 2048 * 8192 < 2^32, the result is byte 3 of the sum
-            const unsigned a = ((unsigned)sy * (unsigned)w + (unsigned)sx) * 3u;
-            const unsigned r = a & 7u;
+            cx[u] = (uint32_t)cx0 | ((uint32_t)(2048 - cx0) << 16);
+            q0[u] = (uint32_t)(cy0 << 2);          // 4 * cy: 255 * 2048 * 8192 < 2^32, the result is byte 3 of the sum
+            q1[u] = 8192u - q0[u];
+            const unsigned a = in[u] ? ((unsigned)sy * (unsigned)w + (unsigned)sx) * 3u : 0u;
+            r[u] = a & 7u;
             const uint8_t* p = img + (a & ~7u);
-            const uint2 t0 = ldg_u64(p), u0 = ldg_u64(p + row);
-            uint2 t1 = make_uint2(0u, 0u), u1 = make_uint2(0u, 0u);
-            if (r > 2u) { t1 = ldg_u64(p + 8); u1 = ldg_u64(p + row + 8); }
-            const bool hiw = r >= 4u;
-            const unsigned sh = r * 8u;   // funnel shifts use the amount mod 32
-            uint32_t b0, b1, c0, c1;
-            {
-                const uint32_t x0 = hiw ? t0.y : t0.x, x1 = hiw ? t1.x : t0.y, x2 = hiw ? t1.y : t1.x;
-                b0 = __funnelshift_r(x0, x1, sh); b1 = __funnelshift_r(x1, x2, sh);
-                const uint32_t z0 = hiw ? u0.y : u0.x, z1 = hiw ? u1.x : u0.y, z2 = hiw ? u1.y : u1.x;
-                c0 = __funnelshift_r(z0, z1, sh); c1 = __funnelshift_r(z1, z2, sh);
-            }
-            int Ht[3], Hb[3];
-            hsum_u8c3<kSigned>(b0, b1, cx, Ht);   // p00*cx0 + p01*cx1
-            hsum_u8c3<kSigned>(c0, c1, cx, Hb);   // p10*cx0 + p11*cx1
-            // warp_affine_naive.cpp:50-54 regrouped row-wise, times 4: bits 22..29 of the reference's sum are byte 3 here
-            const uint32_t q0 = (uint32_t)cy0q, q1 = (uint32_t)cy1q;   // unsigned: the signed-char sums wrap mod 2^32 by design
-            const uint32_t s0 = (uint32_t)Ht[0] * q0 + (uint32_t)Hb[0] * q1, s1 = (uint32_t)Ht[1] * q0 + (uint32_t)Hb[1] * q1,
-                           s2 = (uint32_t)Ht[2] * q0 + (uint32_t)Hb[2] * q1;
-            lo = __byte_perm(__byte_perm(s0, s1, 0x0730), s2, 0x7210);   // [. v0 v1 v2]
+            t0[u] = ldg_u64(p); u0[u] = ldg_u64(p + row);
+            t1[u] = make_uint2(0u, 0u); u1[u] = make_uint2(0u, 0u);
+            if (r[u] > 2u) { t1[u] = ldg_u64(p + 8); u1[u] = ldg_u64(p + row + 8); }
         }
-        const uint32_t nxt = __shfl_down_sync(0xffffffffu, lo, 1);
-        if (valid && j != 3) st_stream4(o, __byte_perm(lo, nxt, sel));
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const bool hiw = r[u] >= 4u;
+            const unsigned sh = r[u] * 8u;   // funnel shifts use the amount mod 32
+            const uint32_t x0 = hiw ? t0[u].y : t0[u].x, x1 = hiw ? t1[u].x : t0[u].y, x2 = hiw ? t1[u].y : t1[u].x;
+            const uint32_t b0 = __funnelshift_r(x0, x1, sh), b1 = __funnelshift_r(x1, x2, sh);
+            const uint32_t z0 = hiw ? u0[u].y : u0[u].x, z1 = hiw ? u1[u].x : u0[u].y, z2 = hiw ? u1[u].y : u1[u].x;
+            const uint32_t c0 = __funnelshift_r(z0, z1, sh), c1 = __funnelshift_r(z1, z2, sh);
+            int Ht[3], Hb[3];
+            hsum_u8c3<kSigned>(b0, b1, cx[u], Ht);   // p00*cx0 + p01*cx1
+            hsum_u8c3<kSigned>(c0, c1, cx[u], Hb);   // p10*cx0 + p11*cx1
+            // warp_affine_naive.cpp:50-54 regrouped row-wise, times 4: bits 22..29 of the reference's sum are byte 3 here
+            // (unsigned arithmetic: the signed-char sums wrap mod 2^32 by design)
+            const uint32_t s0 = (uint32_t)Ht[0] * q0[u] + (uint32_t)Hb[0] * q1[u], s1 = (uint32_t)Ht[1] * q0[u] + (uint32_t)Hb[1] * q1[u],
+                           s2 = (uint32_t)Ht[2] * q0[u] + (uint32_t)Hb[2] * q1[u];
+            const uint32_t lo = in[u] ? __byte_perm(__byte_perm(s0, s1, 0x0730), s2, 0x7210) : 0u;   // [. v0 v1 v2]; outside the frame: 0 (App. C-5)
+            const uint32_t nxt = __shfl_down_sync(0xffffffffu, lo, 1);
+            if (valid[u] && j != 3) st_stream4(o, __byte_perm(lo, nxt, sel));
+            o += o_step;
+        }
     }
 }
 

@@ -163,10 +163,11 @@ def c3(iters):   # warp_affine face crops: 4096 x (1280x720 -> 112x112 fp32 norm
     report("   same, direct gather kernel (WARP_GATHER=1)", ms, n * wo * wo, n * (roi + wo * wo * 12))
     ms, _ = timeit(lambda: vacv.warp_affine(frames, vacv.NHWC, minv, wo, wo, idx), iters)
     report("   warp_affine u8 1280x720->112x112 x4096", ms, n * wo * wo, n * (roi + wo * wo * 3))
-    vacv.lib.vacv_cuda_set_tuning(b"WARP_V", 1)    # A/B: the first-generation flat-order gather kernel
-    ms, _ = timeit(lambda: vacv.warp_affine(frames, vacv.NHWC, minv, wo, wo, idx), iters)
-    vacv.lib.vacv_cuda_set_tuning(b"WARP_V", 0)
-    report("   warp_affine u8, first-generation gather kernel (WARP_V=1)", ms, n * wo * wo, n * (roi + wo * wo * 3))
+    for v, what in ((2, "pack kernel with two pixels per thread in flight (WARP_V=2)"), (1, "first-generation gather kernel (WARP_V=1)")):   # A/B
+        vacv.lib.vacv_cuda_set_tuning(b"WARP_V", v)
+        ms, _ = timeit(lambda: vacv.warp_affine(frames, vacv.NHWC, minv, wo, wo, idx), iters)
+        vacv.lib.vacv_cuda_set_tuning(b"WARP_V", 0)
+        report(f"   warp_affine u8, {what}", ms, n * wo * wo, n * (roi + wo * wo * 3))
     ms, _ = timeit(lambda: vacv.warp_affine(frames, vacv.NHWC, minv, wo, wo, idx, vacv.FLAG_TILED), iters)
     report("   warp_affine u8 (TMA-staged kernel, opt-in) x4096", ms, n * wo * wo, n * (roi + wo * wo * 3))
     ms, _ = timeit(lambda: vacv.warp_affine_normalize(frames, minv, wo, wo, mean, std, idx, out_layout=vacv.NCHW), iters)

@@ -623,14 +623,15 @@ def test_warp_affine_u8_pack_kernel(vacv, oracle, case):
     idx = (np.arange(n) % nf).astype(np.int32)
     got = host(vacv.warp_affine(dev(frames), NHWC, dev(minv), wo, ho, dev(idx)))
     got_sc = host(vacv.warp_affine(dev(frames), NHWC, dev(minv), wo, ho, dev(idx), vacv.FLAG_SIGNED_CHAR))
-    assert vacv.lib.vacv_cuda_set_tuning(b"WARP_V", 1) == 0
-    try:
-        first = host(vacv.warp_affine(dev(frames), NHWC, dev(minv), wo, ho, dev(idx)))
-        first_sc = host(vacv.warp_affine(dev(frames), NHWC, dev(minv), wo, ho, dev(idx), vacv.FLAG_SIGNED_CHAR))
-    finally:
-        vacv.lib.vacv_cuda_set_tuning(b"WARP_V", 0)
-    assert_same(got, first)
-    assert_same(got_sc, first_sc)
+    for variant in (1, 2):   # 1: first-generation gather kernel; 2: pack kernel with two pixels per thread in flight (default: one)
+        assert vacv.lib.vacv_cuda_set_tuning(b"WARP_V", variant) == 0
+        try:
+            other = host(vacv.warp_affine(dev(frames), NHWC, dev(minv), wo, ho, dev(idx)))
+            other_sc = host(vacv.warp_affine(dev(frames), NHWC, dev(minv), wo, ho, dev(idx), vacv.FLAG_SIGNED_CHAR))
+        finally:
+            vacv.lib.vacv_cuda_set_tuning(b"WARP_V", 0)
+        assert_same(got, other)
+        assert_same(got_sc, other_sc)
     for i in range(n):
         assert_same(got[i], oracle.warp_affine(frames[idx[i]], w, h, 3, NHWC, wo, ho, minv[i]))
     for i in (0, n - 1):
