@@ -401,20 +401,23 @@ __device__ __forceinline__ void compute_tile_packed(uint32_t ybuf, uint32_t cbuf
 // build_pipe_plan in fused.cu): the band of a tile is copied ROW BY ROW, g.sy_pitch / g.sc_pitch bytes each (the
 // row rounded up to 16 bytes), so the padding stays in DRAM; lane i of the calling warp issues rows i, i + 32, ...  Kept out of line:
 // inlined, it changed the register allocation of the tile loop (fp16 outputs lost 8 %).
+// (Its arguments are scalars on purpose: a `const PipeGeom&` made every kernel that can reach this call keep a copy of the
+// geometry in local memory -- 112 bytes of stack in all non-dense instantiations.)
 template <int FMT>
-__device__ __noinline__ void issue_band_rows(const PipeGeom& g, const uint8_t* f, uint8_t* st, uint64_t* bar, int y_first, int y_last, int lane) {
+__device__ __noinline__ void issue_band_rows(int sy_pitch, int sc_pitch, int y_pitch, int c_pitch, int ystage, int vstage_off, size_t c_off, size_t c2_off,
+                                             const uint8_t* f, uint8_t* st, uint64_t* bar, int y_first, int y_last, int lane) {
     const int c_first = y_first >> 1, c_last = y_last >> 1;
     const int yrows = y_last - y_first + 1, crows = c_last - c_first + 1;
     constexpr int kPlanes = FMT == kFmtPlanar ? 2 : 1;
-    if (lane == 0) mbar_expect_tx(bar, (uint32_t)yrows * g.sy_pitch + (uint32_t)(kPlanes * crows) * g.sc_pitch);
+    if (lane == 0) mbar_expect_tx(bar, (uint32_t)yrows * sy_pitch + (uint32_t)(kPlanes * crows) * sc_pitch);
     __syncwarp();
     for (int r = lane; r < yrows + kPlanes * crows; r += 32) {
         if (r < yrows) {
-            bulk_g2s(st + (size_t)r * g.sy_pitch, f + (size_t)(y_first + r) * g.y_pitch, (uint32_t)g.sy_pitch, bar);
+            bulk_g2s(st + (size_t)r * sy_pitch, f + (size_t)(y_first + r) * y_pitch, (uint32_t)sy_pitch, bar);
         } else {
             const int q = r - yrows, second = q >= crows ? 1 : 0, cr = q - second * crows;
-            bulk_g2s(st + g.ystage + (second ? g.vstage_off : 0) + (size_t)cr * g.sc_pitch,
-                     f + (second ? g.c2_off : g.c_off) + (size_t)(c_first + cr) * g.c_pitch, (uint32_t)g.sc_pitch, bar);
+            bulk_g2s(st + ystage + (second ? vstage_off : 0) + (size_t)cr * sc_pitch,
+                     f + (second ? c2_off : c_off) + (size_t)(c_first + cr) * c_pitch, (uint32_t)sc_pitch, bar);
         }
     }
 }
@@ -529,7 +532,8 @@ nv_resize_normalize_chw_pipe_kernel(const uint8_t* __restrict__ src, OutT* __res
     auto issue_rows = [&](int tile, int b) {   // padded surface; called by every lane of warp 0
         const int frame = tile / g.tiles_per_frame, dy0 = (tile - frame * g.tiles_per_frame) * g.TH;
         const int th = min(g.TH, g.ho - dy0);
-        issue_band_rows<FMT>(g, src + (size_t)frame * frame_stride, stages + (size_t)b * (g.ystage + g.cstage), &full_bar[b], s_sy[dy0], s_sy[dy0 + th - 1] + 1, tid);
+        issue_band_rows<FMT>(sy_pitch, sc_pitch, y_pitch, c_pitch, g.ystage, g.vstage_off, c_off, g.c2_off, src + (size_t)frame * frame_stride,
+                             stages + (size_t)b * (g.ystage + g.cstage), &full_bar[b], s_sy[dy0], s_sy[dy0 + th - 1] + 1, tid);
     };
 
     int tile = blockIdx.x;
