@@ -966,6 +966,62 @@ def test_full_size_config3_4096_crops_sampled_vs_oracle(vacv, oracle):
         assert_same(host(out[i]), want)
 
 
+def test_full_size_u8_warp_pack_kernel_4096_crops(vacv, oracle):
+    """Config 3's crops with u8 output at full size: the column-owning pack kernel equals the first-generation gather kernel on every
+    crop (device-side comparison) and the oracle on sampled crops."""
+    w, h, wo, ho, nf, n = 1280, 720, 112, 112, 64, 4096
+    frames = _gpu_rand_u8(13, nf, h, w, 3)
+    minv = np.array([vacv.invert_affine(m) for m in random_face_matrices(n, w, h, wo, 17)], np.float32)
+    idx = (np.arange(n) % nf).astype(np.int32)
+    out = vacv.warp_affine(frames, NHWC, dev(minv), wo, ho, dev(idx))
+    assert vacv.lib.vacv_cuda_set_tuning(b"WARP_V", 1) == 0
+    try:
+        first = vacv.warp_affine(frames, NHWC, dev(minv), wo, ho, dev(idx))
+    finally:
+        vacv.lib.vacv_cuda_set_tuning(b"WARP_V", 0)
+    assert torch.equal(out, first)
+    for i in (0, 1234, 4095):
+        assert_same(host(out[i]), oracle.warp_affine(host(frames[idx[i]]), w, h, 3, NHWC, wo, ho, minv[i]))
+
+
+@pytest.mark.parametrize("sz", [((1920, 1080), (1280, 720), 64), ((2560, 1440), (1920, 1080), 32), ((3840, 2160), (1920, 1080), 16)])
+def test_full_size_u8_bilinear_periodic_walker(vacv, oracle, sz):
+    """bench_ops' rational-scale bilinear shapes at full size: the periodic walker equals the persistent pipeline on the whole batch
+    (device-side comparison), one frame equals the oracle, and the batch equals frame-by-frame processing."""
+    (w, h), (wo, ho), b = sz
+    src = _gpu_rand_u8(14, b, h, w, 3)
+    out = vacv.resize(src, NHWC, wo, ho)
+    assert vacv.lib.vacv_cuda_set_tuning(b"LINEAR_V", 1) == 0
+    try:
+        pipe = vacv.resize(src, NHWC, wo, ho)
+    finally:
+        vacv.lib.vacv_cuda_set_tuning(b"LINEAR_V", 0)
+    assert torch.equal(out, pipe)
+    assert_same(host(out[b - 1]), oracle.resize_linear(host(src[b - 1]), w, h, 3, NHWC, wo, ho))
+    assert torch.equal(out[3], vacv.resize(src[3:4], NHWC, wo, ho)[0])
+
+
+def test_full_size_config2_padded_surfaces_three_staging_forms(vacv):
+    """Config 2 on 256 pitch-2048 NV12 surfaces: tensor-map boxes (default), whole bands with their padding and per-row copies give the
+    same bytes, and those equal the dense path on the same frames re-packed without padding."""
+    w, h, wo, ho, b, pitch = 1920, 1080, 640, 640, 256, 2048
+    dense = _gpu_rand_u8(15, b, h * 3 // 2, w)
+    padded = torch.zeros((b, h * 3 // 2, pitch), dtype=torch.uint8, device="cuda")
+    padded[:, :, :w] = dense
+    padded[:, :, w:] = 0xA5   # the padding must never reach the result
+    mean, std = dev(MEAN), dev(STD)
+    want = vacv.nv_resize_normalize_chw(dense.reshape(b, -1), w, h, wo, ho, mean, std, False)   # v_first = False: NV12
+    outs = []
+    for mode in (0, 2, 1):
+        assert vacv.lib.vacv_cuda_set_tuning(b"PIPE_ROWS", mode) == 0
+        try:
+            outs.append(vacv.yuv_resize_normalize_chw(padded.reshape(-1), vacv.YUV_NV12, w, h, wo, ho, mean, std, y_pitch=pitch, c_pitch=pitch, batch=b))
+        finally:
+            vacv.lib.vacv_cuda_set_tuning(b"PIPE_ROWS", 0)
+    for o in outs:
+        assert torch.equal(o, want)
+
+
 def test_full_size_config4_batch128_properties(vacv, oracle):
     """BASELINE config 4 at its full size (128 x 2560x1440 -> 1920x1080 u8 bicubic): one frame against the oracle (OpenCV-2.4
     rule), and the batch result is independent of the batch position (the same frame replicated gives identical outputs)."""
