@@ -403,6 +403,11 @@ extern "C" int vacv_cuda_warp_affine(const void* frames, int n_frames, int w, in
             const bool sc = (flags & VACV_FLAG_SIGNED_CHAR) != 0;
             // one pixel per thread and pass; two (U = 2, tap loads of both in flight together) measured the same to 1.5 % slower -- the
             // kernel is bound by L1 wavefronts, not by load latency -- and stay as the A/B variant VACV_WARP_V=2
+            if (knob(kKnobWarpV) == 3) {   // A/B: 32-bit tap loads
+                auto k3 = sc ? warp_affine_u8c3_pack_kernel<true, 1, false> : warp_affine_u8c3_pack_kernel<false, 1, false>;
+                k3<<<grid, threads, 0, s>>>((const uint8_t*)frames, frame_idx, minv, (uint8_t*)dst, w, h, w_out, h_out, g.frame_elems, rows, rows_per_cta, 0);
+                return check_launch("warp_affine");
+            }
             auto kern = knob(kKnobWarpV) == 2 ? (sc ? warp_affine_u8c3_pack_kernel<true, 2> : warp_affine_u8c3_pack_kernel<false, 2>)
                                               : (sc ? warp_affine_u8c3_pack_kernel<true, 1> : warp_affine_u8c3_pack_kernel<false, 1>);
             kern<<<grid, threads, 0, s>>>((const uint8_t*)frames, frame_idx, minv, (uint8_t*)dst, w, h, w_out, h_out, g.frame_elems, rows, rows_per_cta, 0);

@@ -26,7 +26,7 @@ __device__ __forceinline__ uint2 ldg_u64(const uint8_t* p) {
 // outside the frame or the band loads from offset 0 and its result is discarded.  U = passes per loop iteration, the tap loads of U
 // pixels of a thread issued before the first blend: U = 2 measured no faster than U = 1 (0.223 vs 0.220 ms on config 3's shape) --
 // long-scoreboard is the top stall, but what bounds the kernel is the L1 data pipe (75 % of its wavefront peak), not load latency.
-template <bool kSigned, int U>
+template <bool kSigned, int U, bool kWide = true>
 __global__ void __launch_bounds__(256) warp_affine_u8c3_pack_kernel(const uint8_t* __restrict__ frames, const int* __restrict__ frame_idx,
                                                                      const float* __restrict__ minv, uint8_t* __restrict__ dst,
                                                                      int w, int h, int wo, int ho, size_t frame_bytes,
@@ -72,20 +72,27 @@ __global__ void __launch_bounds__(256) warp_affine_u8c3_pack_kernel(const uint8_
             q0[u] = (uint32_t)(cy0 << 2);          // 4 * cy: 255 * 2048 * 8192 < 2^32, the result is byte 3 of the sum
             q1[u] = 8192u - q0[u];
             const unsigned a = in[u] ? ((unsigned)sy * (unsigned)w + (unsigned)sx) * 3u : 0u;
-            r[u] = a & 7u;
-            const uint8_t* p = img + (a & ~7u);
-            t0[u] = ldg_u64(p); u0[u] = ldg_u64(p + row);
-            t1[u] = make_uint2(0u, 0u); u1[u] = make_uint2(0u, 0u);
-            if (r[u] > 2u) { t1[u] = ldg_u64(p + 8); u1[u] = ldg_u64(p + row + 8); }
+            if (kWide) {
+                r[u] = a & 7u;
+                const uint8_t* p = img + (a & ~7u);
+                t0[u] = ldg_u64(p); u0[u] = ldg_u64(p + row);
+                t1[u] = make_uint2(0u, 0u); u1[u] = make_uint2(0u, 0u);
+                if (r[u] > 2u) { t1[u] = ldg_u64(p + 8); u1[u] = ldg_u64(p + row + 8); }
+            } else {   // 32-bit tap loads (linear_taps_u8c3): t0 / u0 hold the funnel-shifted words directly
+                r[u] = 0u;
+                linear_taps_u8c3(img, a, t0[u].x, t0[u].y);
+                linear_taps_u8c3(img, a + row, u0[u].x, u0[u].y);
+                t1[u] = make_uint2(0u, 0u); u1[u] = make_uint2(0u, 0u);
+            }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const bool hiw = r[u] >= 4u;
             const unsigned sh = r[u] * 8u;   // funnel shifts use the amount mod 32
             const uint32_t x0 = hiw ? t0[u].y : t0[u].x, x1 = hiw ? t1[u].x : t0[u].y, x2 = hiw ? t1[u].y : t1[u].x;
-            const uint32_t b0 = __funnelshift_r(x0, x1, sh), b1 = __funnelshift_r(x1, x2, sh);
+            const uint32_t b0 = kWide ? __funnelshift_r(x0, x1, sh) : t0[u].x, b1 = kWide ? __funnelshift_r(x1, x2, sh) : t0[u].y;
             const uint32_t z0 = hiw ? u0[u].y : u0[u].x, z1 = hiw ? u1[u].x : u0[u].y, z2 = hiw ? u1[u].y : u1[u].x;
-            const uint32_t c0 = __funnelshift_r(z0, z1, sh), c1 = __funnelshift_r(z1, z2, sh);
+            const uint32_t c0 = kWide ? __funnelshift_r(z0, z1, sh) : u0[u].x, c1 = kWide ? __funnelshift_r(z1, z2, sh) : u0[u].y;
             int Ht[3], Hb[3];
             hsum_u8c3<kSigned>(b0, b1, cx[u], Ht);   // p00*cx0 + p01*cx1
             hsum_u8c3<kSigned>(c0, c1, cx[u], Hb);   // p10*cx0 + p11*cx1
