@@ -57,7 +57,8 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-TRAFFIC_PROFILE = "r2_fused_head_ncu_raw.txt" if os.path.exists(os.path.join(ROOT, "profiles", "r2_fused_head_ncu_raw.txt")) else "r1_fused_v3_ncu_raw.txt"
+TRAFFIC_PROFILE = next((f for f in ("r2f_fused_head_ncu_raw.txt", "r2_fused_head_ncu_raw.txt") if os.path.exists(os.path.join(ROOT, "profiles", f))),
+                       "r1_fused_v3_ncu_raw.txt")   # the newest ncu --set full capture of the headline kernel
 
 
 def ncu_traffic_bytes():
