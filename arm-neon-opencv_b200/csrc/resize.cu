@@ -689,6 +689,9 @@ extern "C" int vacv_cuda_resize(const void* src, void* dst, int batch, int w, in
             else resize_linear_u8c3_kernel<false, false><<<grid, block, 0, s>>>(sp, dp, g);
         } else if (!cubic && dtype == VACV_INT8 && g.c == 1 && (((size_t)w * h) % 4) == 0 && ((uintptr_t)src % 4) == 0 && (size_t)w * h < 0xfffffff0ull) {
             if (!(flags & (VACV_FLAG_NEON_RULE | VACV_FLAG_DIRECT_GATHER)) && !knob(kKnobNoRpipe)) {   // persistent TMA pipeline for planes
+                const int rcp = try_launch_resize_linear1_period(sp, dp, ni, w, h, w_out, h_out, (flags & VACV_FLAG_SIGNED_CHAR) != 0, s);   // rational scales
+                if (rcp < 0) return rcp;
+                if (rcp > 0) continue;
                 const int rc = try_launch_resize_pipe_u8c3(sp, dp, ni, w, h, w_out, h_out, (flags & VACV_FLAG_SIGNED_CHAR) != 0, kRpOutU8, nullptr, nullptr, s, 1);
                 if (rc < 0) return rc;
                 if (rc > 0) continue;

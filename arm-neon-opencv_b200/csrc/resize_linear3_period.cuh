@@ -34,18 +34,20 @@ struct LinPeriodGeom {
 
 struct LinRow { int cy0q, cy1q, last, pad; };   // 4 * cy0, 4 * cy1, walk step that completes the row
 
-template <int P, int Q, int KP>
+// C = 3: interleaved BGR; C = 1: one plane of a CHW tensor (resized plane by plane, resize.cpp:73-87) or a grey image
+template <int P, int Q, int KP, int C = 3>
 struct LinPeriodShape {
     static constexpr int NCOL = Q * KP;          // adjacent output columns per thread
     static constexpr int NPX = P * KP;           // source pixels in a thread's window = its own period pixels
-    static constexpr int LS = 3 * NPX;           // window bytes = bytes between the windows of neighbouring lanes
+    static constexpr int LS = C * NPX;           // window bytes = bytes between the windows of neighbouring lanes
     static constexpr int NW = LS / 4;            // window words
-    static constexpr int NV = 3 * NCOL;          // output bytes per thread and row
+    static constexpr int NV = C * NCOL;          // output bytes per thread and row
     static constexpr int kWarpRow = 32 * NV;     // bytes one warp produces per output row
     static constexpr int kWarpSpan = 32 * LS;    // source bytes of a warp per row = ring slot size
     static_assert(P > Q, "down-scaling only: both taps of every column inside the thread's own pixels");
     static_assert(LS % 4 == 0 && NV % 4 == 0, "windows and output runs are whole words");
     static_assert(pd::tap0(P, Q, NCOL - 1) + 1 < NPX, "last column's right tap inside the window");
+    static_assert(C == 3 || (C == 1 && NCOL % 2 == 0), "planes: columns are filtered in pairs");
 };
 
 // bytes B0..B3 of the window (any order, inside two neighbouring words) -> one word with ONE PRMT whose selector is an immediate
@@ -59,9 +61,9 @@ __device__ __forceinline__ uint32_t lin_pick(const uint32_t (&W)[N]) {
     return __byte_perm(W[w0], W[w1], sel);
 }
 
-template <int P, int Q, int KP, bool kSigned, bool kDown>
+template <int P, int Q, int KP, bool kSigned, bool kDown, int C = 3>
 __global__ void __launch_bounds__(128) resize_linear3_period_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, LinPeriodGeom g) {
-    using S = LinPeriodShape<P, Q, KP>;
+    using S = LinPeriodShape<P, Q, KP, C>;
     constexpr int NCOL = S::NCOL, LS = S::LS, NW = S::NW, NV = S::NV, kWarpRow = S::kWarpRow;
     constexpr unsigned kPitch = S::kWarpSpan;             // bytes per ring slot
     extern __shared__ __align__(16) uint8_t smem[];
@@ -76,7 +78,7 @@ __global__ void __launch_bounds__(128) resize_linear3_period_kernel(const uint8_
     const int pt = wstrip * 32 + lane;                 // this thread's index along x: columns NCOL * pt ..
     const int dy_begin = seg * g.rows_per_seg, nrows = min(g.ho, dy_begin + g.rows_per_seg) - dy_begin;
     uint8_t* out_img = dst + blockIdx.y * g.dst_image;
-    const unsigned row_bytes = (unsigned)g.w * 3, out_row_bytes = (unsigned)g.wo * 3;
+    const unsigned row_bytes = (unsigned)g.w * C, out_row_bytes = (unsigned)g.wo * C;
 
     // walk steps: step n filters source row t_first + n; the last step is the last output row's lower tap row (all inside the image:
     // linear_coord clamps the index to [0, h - 2])
@@ -156,20 +158,37 @@ __global__ void __launch_bounds__(128) resize_linear3_period_kernel(const uint8_
     auto hfilter = [&](const uint32_t slot, uint32_t parity, int (&H)[NV]) {
         pd::mbar_wait(ubars + 8 * slot, parity);
         const uint32_t p = win_s + slot * kPitch;
+        // 32-bit loads.  Lane strides of 32 / 48 / 24 bytes (planes 4:3 and 2:1, BGR 4:3 and 2:1, planes 3:2) make them 8- / 4- / 2-way
+        // bank conflicts, which 128- / 64-bit loads would avoid -- measured: planes unchanged (0.095 / 0.100 / 0.164 ms either way), BGR
+        // 4:3 0.097 -> 0.096 ms, BGR 2:1 0.087 -> 0.128 ms (the PRMTs then wait for whole vectors): the shared-memory pipe is not what
+        // bounds these kernels, 32-bit loads stay.
         uint32_t W[NW];
 #pragma unroll
         for (int i = 0; i < NW; ++i) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(W[i]) : "r"(p + 4 * i));
-        pd::static_for<NCOL>([&](auto ic) {
-            constexpr int c = decltype(ic)::value;
-            constexpr int a = 3 * pd::tap0(P, Q, c);   // first byte of the left tap
-            const uint32_t bg = lin_pick<a, a + 3, a + 1, a + 4>(W);   // [L.b R.b L.g R.g]
-            const uint32_t rr = lin_pick<a + 2, a + 5, a + 2, a + 5>(W);   // [L.r R.r  .   . ]
-            if (kSigned) {
-                H[3 * c] = __dp2a_lo((int)cx[c], (int)bg, 0); H[3 * c + 1] = __dp2a_hi((int)cx[c], (int)bg, 0); H[3 * c + 2] = __dp2a_lo((int)cx[c], (int)rr, 0);
-            } else {
-                H[3 * c] = (int)__dp2a_lo(cx[c], bg, 0u); H[3 * c + 1] = (int)__dp2a_hi(cx[c], bg, 0u); H[3 * c + 2] = (int)__dp2a_lo(cx[c], rr, 0u);
-            }
-        });
+        if constexpr (C == 3) {
+            pd::static_for<NCOL>([&](auto ic) {
+                constexpr int c = decltype(ic)::value;
+                constexpr int a = 3 * pd::tap0(P, Q, c);   // first byte of the left tap
+                const uint32_t bg = lin_pick<a, a + 3, a + 1, a + 4>(W);   // [L.b R.b L.g R.g]
+                const uint32_t rr = lin_pick<a + 2, a + 5, a + 2, a + 5>(W);   // [L.r R.r  .   . ]
+                if (kSigned) {
+                    H[3 * c] = __dp2a_lo((int)cx[c], (int)bg, 0); H[3 * c + 1] = __dp2a_hi((int)cx[c], (int)bg, 0); H[3 * c + 2] = __dp2a_lo((int)cx[c], (int)rr, 0);
+                } else {
+                    H[3 * c] = (int)__dp2a_lo(cx[c], bg, 0u); H[3 * c + 1] = (int)__dp2a_hi(cx[c], bg, 0u); H[3 * c + 2] = (int)__dp2a_lo(cx[c], rr, 0u);
+                }
+            });
+        } else {   // planes: one PRMT per column PAIR ([L R] of both columns lie within four consecutive bytes), one IDP.2A per column
+            pd::static_for<NCOL / 2>([&](auto ic) {
+                constexpr int c = 2 * decltype(ic)::value;
+                constexpr int a = pd::tap0(P, Q, c), b = pd::tap0(P, Q, c + 1);
+                const uint32_t lr = lin_pick<a, a + 1, b, b + 1>(W);   // [L0 R0 L1 R1]
+                if (kSigned) {
+                    H[c] = __dp2a_lo((int)cx[c], (int)lr, 0); H[c + 1] = __dp2a_hi((int)cx[c + 1], (int)lr, 0);
+                } else {
+                    H[c] = (int)__dp2a_lo(cx[c], lr, 0u); H[c + 1] = (int)__dp2a_hi(cx[c + 1], lr, 0u);
+                }
+            });
+        }
     };
 
     // ---- output: every row is staged in one of two kWarpRow-byte buffers of the warp and leaves at once as lane-contiguous 16-byte

@@ -43,16 +43,16 @@ const LinPeriodPlan* lin_period_plan(int w, int h, int wo, int ho, double scale_
     return p;
 }
 
-template <int P, int Q, int KP, bool kSigned>
+template <int P, int Q, int KP, bool kSigned, int C = 3>
 int launch_linear3_period(const uint8_t* src, uint8_t* dst, int images, int w, int h, int wo, int ho, cudaStream_t s) {
-    using S = LinPeriodShape<P, Q, KP>;
+    using S = LinPeriodShape<P, Q, KP, C>;
     if ((long long)w * Q != (long long)wo * P || wo % S::NCOL != 0) return 0;
     // bulk copies and the staged flush move aligned 16-byte chunks
-    if (((size_t)wo * 3) % 16 != 0 || ((size_t)w * 3) % 16 != 0 || ((uintptr_t)dst % 16) != 0 || ((uintptr_t)src % 16) != 0) return 0;
+    if (((size_t)wo * C) % 16 != 0 || ((size_t)w * C) % 16 != 0 || ((uintptr_t)dst % 16) != 0 || ((uintptr_t)src % 16) != 0) return 0;
     if (h > 2 * ho || h < 2 || ho < 1) return 0;   // the walk filters every source row between a segment's first and last tap row
     LinPeriodGeom g;
     g.w = w; g.h = h; g.wo = wo; g.ho = ho;
-    g.src_image = (size_t)w * h * 3; g.dst_image = (size_t)wo * ho * 3;
+    g.src_image = (size_t)w * h * C; g.dst_image = (size_t)wo * ho * C;
     g.scale_x = (double)((float)w / (float)wo); g.scale_y = (double)((float)h / (float)ho);   // resize_naive.cpp:14-15: fp32 scales
     const LinPeriodPlan* plan = lin_period_plan<P, Q, KP>(w, h, wo, ho, g.scale_x, g.scale_y);
     if (!plan->ok) return 0;
@@ -73,13 +73,13 @@ int launch_linear3_period(const uint8_t* src, uint8_t* dst, int images, int w, i
     g.rows_per_seg = rps;
     g.segs = (ho + rps - 1) / rps;
     const size_t smem = (size_t)(rps + 1) * sizeof(LinRow) + warps * per_warp;
-    auto kern = plan->down ? resize_linear3_period_kernel<P, Q, KP, kSigned, true> : resize_linear3_period_kernel<P, Q, KP, kSigned, false>;
+    auto kern = plan->down ? resize_linear3_period_kernel<P, Q, KP, kSigned, true, C> : resize_linear3_period_kernel<P, Q, KP, kSigned, false, C>;
     if (smem > 48 * 1024) {
         if (smem > 200 * 1024) return 0;
         static thread_local unsigned long long attr_devices = 0;   // opt-in per device (the maximum, so any later shape fits)
         const int device = current_device();
         if (device >= 64 || !((attr_devices >> device) & 1)) {
-            for (auto k : {resize_linear3_period_kernel<P, Q, KP, kSigned, true>, resize_linear3_period_kernel<P, Q, KP, kSigned, false>}) {
+            for (auto k : {resize_linear3_period_kernel<P, Q, KP, kSigned, true, C>, resize_linear3_period_kernel<P, Q, KP, kSigned, false, C>}) {
                 cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
                 if (e != cudaSuccess) return set_error(VACV_ERR_CUDA, "resize: %s", cudaGetErrorString(e));
             }
@@ -103,7 +103,21 @@ int launch_any(const uint8_t* src, uint8_t* dst, int images, int w, int h, int w
     return rc;
 }
 
+// planes (CHW tensors plane by plane, grey images): more periods per thread so that a warp's bulk copy of a source row stays >= 768 bytes
+template <bool kSigned>
+int launch_any_planes(const uint8_t* src, uint8_t* dst, int planes, int w, int h, int wo, int ho, cudaStream_t s) {
+    int rc = launch_linear3_period<3, 2, 8, kSigned, 1>(src, dst, planes, w, h, wo, ho, s);            // 3 : 2: 16 columns per thread
+    if (rc == 0) rc = launch_linear3_period<4, 3, 8, kSigned, 1>(src, dst, planes, w, h, wo, ho, s);   // 4 : 3: 24 columns
+    if (rc == 0) rc = launch_linear3_period<2, 1, 16, kSigned, 1>(src, dst, planes, w, h, wo, ho, s);  // 2 : 1: 16 columns
+    return rc;
+}
+
 }  // namespace
+
+int vacv::try_launch_resize_linear1_period(const uint8_t* src, uint8_t* dst, int planes, int w, int h, int wo, int ho, bool signed_char, cudaStream_t s) {
+    if (knob(kKnobLinearV) == 1) return 0;
+    return signed_char ? launch_any_planes<true>(src, dst, planes, w, h, wo, ho, s) : launch_any_planes<false>(src, dst, planes, w, h, wo, ho, s);
+}
 
 // 1 = launched, 0 = shape not eligible (the caller goes on to the persistent pipeline), < 0 = error
 int vacv::try_launch_resize_linear3_period(const uint8_t* src, uint8_t* dst, int images, int w, int h, int wo, int ho, bool signed_char, cudaStream_t s) {

@@ -21,6 +21,7 @@ int try_launch_resize_pipe_u8c3(const uint8_t* src, void* dst, int images, int w
 // resize_linear_period.cu: periodic walker for u8 BGR bilinear at rational horizontal scales (resize_linear3_period.cuh).
 // Returns 1 = launched, 0 = shape not eligible, < 0 = error.
 int try_launch_resize_linear3_period(const uint8_t* src, uint8_t* dst, int images, int w, int h, int wo, int ho, bool signed_char, cudaStream_t s);
+int try_launch_resize_linear1_period(const uint8_t* src, uint8_t* dst, int planes, int w, int h, int wo, int ho, bool signed_char, cudaStream_t s);   // single planes
 
 #define VACV_REQUIRE(cond, ...)                                                 \
     do {                                                                        \

@@ -348,6 +348,15 @@ def ops2(iters):   # shapes off the headline path: planar layouts, fp32 gathers,
     mean, std = stats()
     ms, _ = timeit(lambda: vacv.resize(chw, vacv.NCHW, 640, 360), iters)
     report("op2 resize linear u8 chw 1080p->640x360 x64", ms, b * 640 * 360, b * (1920 * 1080 * 3 * 2 // 3 + 640 * 360 * 3), "2 of 3 rows touched")
+    for (w, h, wo, ho, n, what) in ((1920, 1080, 1280, 720, 64, "3 : 2"), (2560, 1440, 1920, 1080, 32, "4 : 3"), (3840, 2160, 1920, 1080, 16, "2 : 1")):
+        planes = chw if w == 1920 else rand_u8(n, 3, h, w)
+        for v in (0, 1):
+            vacv.lib.vacv_cuda_set_tuning(b"LINEAR_V", v)
+            ms, _ = timeit(lambda: vacv.resize(planes, vacv.NCHW, wo, ho), iters)
+            vacv.lib.vacv_cuda_set_tuning(b"LINEAR_V", 0)
+            report(f"op2 resize linear u8 chw {w}x{h}->{wo}x{ho} x{n}" if v == 0 else "   same, planes pipeline / gather kernel (LINEAR_V=1)", ms, n * wo * ho,
+                   n * 3 * (w * h + wo * ho), f"{what}, periodic walker on planes" if v == 0 else "")
+        del planes
     ms, _ = timeit(lambda: vacv.resize(f, vacv.NHWC, 640, 360), iters)
     report("op2 resize linear f32 hwc 1080p->640x360 x16", ms, 16 * 640 * 360, 16 * 4 * (1920 * 1080 * 3 * 2 // 3 + 640 * 360 * 3), "2 of 3 rows touched")
     ms, _ = timeit(lambda: vacv.resize(f, vacv.NHWC, 1280, 720), iters)

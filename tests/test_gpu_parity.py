@@ -268,6 +268,42 @@ def test_resize_linear_u8_periodic_walker(vacv, oracle, case, signed):
         assert_same(got[i], oracle.resize_linear(src[i], w, h, 3, NHWC, wo, ho, signed_char=int(signed)))
 
 
+LINEAR_PERIOD_PLANE_CASES = [
+    # CHW tensors (plane by plane) at rational horizontal scales: rows of whole 16-byte chunks on both sides
+    ((384, 96), (256, 64)),       # 3:2, half a warp strip
+    ((1920, 270), (1280, 180)),   # 3:2, 2.5 strips
+    ((1920, 100), (1280, 200)),   # 3:2, vertical up-scaling
+    ((768, 64), (512, 64)),       # 3:2, vertical scale 1
+    ((768, 700), (512, 600)),     # 3:2, several vertical segments
+    ((256, 60), (192, 45)),       # 4:3 both ways (24 columns per thread: wo must be a multiple of 48)
+    ((2560, 90), (1920, 77)),     # 4:3, wide planes (no pipeline kernel takes 1920 columns)
+    ((128, 50), (64, 25)),        # 2:1 both ways
+    ((3840, 64), (1920, 40)),     # 2:1, wide planes
+]
+
+
+@pytest.mark.parametrize("signed", [False, True])
+@pytest.mark.parametrize("case", range(len(LINEAR_PERIOD_PLANE_CASES)))
+def test_resize_linear_u8_planes_periodic_walker(vacv, oracle, case, signed):
+    """CHW u8 bilinear at rational horizontal scales: the periodic walker with one channel (16 / 24 adjacent columns per thread, one
+    PRMT per column pair) against the oracle and against the persistent planes pipeline / gather kernel (VACV_LINEAR_V=1)."""
+    (w, h), (wo, ho) = LINEAR_PERIOD_PLANE_CASES[case]
+    src = u8(80 + case, 2, 3, h, w)
+    flags = vacv.FLAG_SIGNED_CHAR if signed else 0
+    got = host(vacv.resize(dev(src), NCHW, wo, ho, vacv.INTER_LINEAR, flags))
+    assert vacv.lib.vacv_cuda_set_tuning(b"LINEAR_V", 1) == 0
+    try:
+        pipe = host(vacv.resize(dev(src), NCHW, wo, ho, vacv.INTER_LINEAR, flags))
+    finally:
+        vacv.lib.vacv_cuda_set_tuning(b"LINEAR_V", 0)
+    assert_same(got, pipe)
+    for i in range(2):
+        assert_same(got[i], oracle.resize_linear(src[i], w, h, 3, NCHW, wo, ho, signed_char=int(signed)))
+    grey = np.ascontiguousarray(src[:, :1].transpose(0, 2, 3, 1))   # [2, h, w, 1]: single-channel HWC takes the same kernel
+    got_g = host(vacv.resize(dev(grey), NHWC, wo, ho, vacv.INTER_LINEAR, flags))
+    assert_same(got_g[1, :, :, 0], got[1, 0])
+
+
 def test_resize_linear_u8_config1_fixture_vs_reference(vacv):
     img = load_fixture("universe1920x1080")
     if img is None or not ref_available():
