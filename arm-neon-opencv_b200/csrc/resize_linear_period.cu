@@ -67,8 +67,12 @@ int launch_linear3_period(const uint8_t* src, uint8_t* dst, int images, int w, i
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(16 / warps * 4, (200 * 1024) / (per_warp * warps + 2048)));   // resident CTAs per SM (shared memory / warps)
     const long long want = 6LL * per_sm * sm_count(current_device());
     const long long per_seg = (long long)g.cta_strips * images;
-    const long long segs = std::max<long long>(1, std::min<long long>((want + per_seg - 1) / per_seg, (ho + 31) / 32));
+    // about six waves of CTAs, but segments of at least 8 output rows (a segment re-reads one or two source rows and pays the table
+    // prologue).  Sweep of segments per strip on B200 (profiles/_lin_segs.py): one 1080p frame per call 0.0151 ms at >= 32 rows per
+    // segment (46 CTAs), 0.0069 at 5 rows; 16 4K frames 0.0878 -> 0.0837 ms; large batches are within 5 % from 11 to 45 rows.
+    const long long segs = std::max<long long>(1, std::min<long long>((want + per_seg - 1) / per_seg, (ho + 7) / 8));
     int rps = (int)((ho + segs - 1) / segs);
+    if (const int v = knob(kKnobWalkSegs)) rps = (ho + std::max(1, v) - 1) / std::max(1, v);   // tuning knob: vertical segments per column strip
     rps = std::min(512, std::max(rps, 1));
     g.rows_per_seg = rps;
     g.segs = (ho + rps - 1) / rps;
