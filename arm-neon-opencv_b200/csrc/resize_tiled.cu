@@ -584,6 +584,14 @@ static int launch_cubic3_rolling(const void* src, void* dst, int images, int w, 
 
 // Column-walking bicubic for fp32 images, C = 3 interleaved or C = 1 planes (resize_cubic3_walk.cuh).  1 = launched, 0 = shape
 // not eligible.
+// Most vertical segments a column strip is cut into: segments of >= 32 output rows when the batch already supplies CTAs (a segment
+// re-reads its first tap rows and pays the table prologue), >= 8 rows for small batches, which need the CTAs more -- one 1440p frame per
+// call: u8 bicubic 0.0315 -> 0.0130 ms, four frames 0.043 -> 0.034, 16 frames best at 32 rows (profiles/_cubic_segs.py).
+static inline long long seg_cap(int ho, long long per_seg) {
+    const int min_rows = per_seg >= 32 ? 32 : 8;
+    return (ho + min_rows - 1) / min_rows;
+}
+
 template <int C>
 static int launch_cubic_walk_f32(const float* src, float* dst, int images, int w, int h, int wo, int ho, cudaStream_t s) {
     constexpr int PX = 4 * C;
@@ -597,7 +605,7 @@ static int launch_cubic_walk_f32(const float* src, float* dst, int images, int w
     g.store16 = (((size_t)wo * PX) % 16 == 0 && ((uintptr_t)dst % 16) == 0) ? 1 : 0;
     const long long want = 8LL * 8 * current_sm_count();
     const long long per_seg = (long long)g.strips * images;
-    long long segs = std::max<long long>(1, std::min<long long>((want + per_seg - 1) / per_seg, (ho + 63) / 64));
+    long long segs = std::max<long long>(1, std::min<long long>((want + per_seg - 1) / per_seg, seg_cap(ho, per_seg)));
     if (const int v = knob(kKnobWalkSegs)) segs = std::max(1, v);   // tuning knob
     int rps = (int)((ho + segs - 1) / segs);
     rps = std::min(kWalkMaxRows, std::max(rps, 1));
@@ -637,7 +645,7 @@ static int launch_cubic3_walk2(const uint8_t* src, uint8_t* dst, int images, int
     g.one2 = 0x3F8000003F800000ull; g.negzero2 = 0x8000000080000000ull; g.magic2 = 0x4B4000004B400000ull; g.negmagic2 = 0xCB400000CB400000ull;
     const long long want = 8LL * 6 * current_sm_count();
     const long long per_seg = (long long)g.strips * images;
-    long long segs = std::max<long long>(1, std::min<long long>((want + per_seg - 1) / per_seg, (ho + 63) / 64));
+    long long segs = std::max<long long>(1, std::min<long long>((want + per_seg - 1) / per_seg, seg_cap(ho, per_seg)));
     if (const int v = knob(kKnobWalkSegs)) segs = std::max(1, v);   // tuning knob
     int rps = (int)((ho + segs - 1) / segs);
     rps = std::min(kWalkMaxRows, std::max(rps, 1));
@@ -712,7 +720,7 @@ static int launch_cubic3_walkn_nc(const uint8_t* src, uint8_t* dst, int images, 
     const int per_sm = 65536 / (MAXREG * 32 * warps);   // resident CTAs per SM at the kernel's register budget
     const long long want = 8LL * per_sm * current_sm_count();
     const long long per_seg = (long long)g.cta_strips * images;
-    long long segs = std::max<long long>(1, std::min<long long>((want + per_seg - 1) / per_seg, (ho + 63) / 64));
+    long long segs = std::max<long long>(1, std::min<long long>((want + per_seg - 1) / per_seg, seg_cap(ho, per_seg)));
     if (const int v = knob(kKnobWalkSegs)) segs = std::max(1, v);   // tuning knob
     int rps = (int)((ho + segs - 1) / segs);
     rps = std::min(kWalkMaxRows, std::max(rps, 1));
@@ -807,7 +815,7 @@ static int launch_cubic3_period(const uint8_t* src, uint8_t* dst, int images, in
     const int per_sm = std::max(1, 65536 / (MAXREG * 32 * warps));   // resident CTAs per SM at the kernel's register budget
     const long long want = 8LL * per_sm * current_sm_count();
     const long long per_seg = (long long)g.cta_strips * images;
-    long long segs = std::max<long long>(1, std::min<long long>((want + per_seg - 1) / per_seg, (ho + 63) / 64));
+    long long segs = std::max<long long>(1, std::min<long long>((want + per_seg - 1) / per_seg, seg_cap(ho, per_seg)));
     if (const int v = knob(kKnobWalkSegs)) segs = std::max(1, v);   // tuning knob
     int rps = (int)((ho + segs - 1) / segs);
     rps = std::min(kWalkMaxRows, std::max(rps, 1));
@@ -911,7 +919,7 @@ static int launch_cubic_f32_period(const float* src, float* dst, int images, int
     g.cta_strips = (g.warp_strips + warps - 1) / warps;
     const long long want = 8LL * 16 * current_sm_count();
     const long long per_seg = (long long)g.cta_strips * images;
-    long long segs = std::max<long long>(1, std::min<long long>((want + per_seg - 1) / per_seg, (ho + 31) / 32));
+    long long segs = std::max<long long>(1, std::min<long long>((want + per_seg - 1) / per_seg, seg_cap(ho, per_seg)));
     if (const int v = knob(kKnobWalkSegs)) segs = std::max(1, v);   // tuning knob
     int rps = (int)((ho + segs - 1) / segs);
     rps = std::min(kWalkMaxRows, std::max(rps, 1));
