@@ -64,7 +64,7 @@ int launch_linear3_period(const uint8_t* src, uint8_t* dst, int images, int w, i
     }
     g.cta_strips = (g.warp_strips + warps - 1) / warps;
     const size_t per_warp = (size_t)kPdStageRows * S::kWarpRow + (size_t)kPdRing * S::kWarpSpan + kPdRing * 8;
-    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(16 / warps * 4, (200 * 1024) / (per_warp * warps + 2048)));   // resident CTAs per SM (shared memory / warps)
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(64 / warps, (200 * 1024) / (per_warp * warps + 2048)));   // resident CTAs per SM: warp slots, shared memory (4 - 6 in practice)
     const long long want = 6LL * per_sm * sm_count(current_device());
     const long long per_seg = (long long)g.cta_strips * images;
     // about six waves of CTAs, but segments of at least 8 output rows (a segment re-reads one or two source rows and pays the table

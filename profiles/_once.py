@@ -47,6 +47,12 @@ elif case == "c3u8":
 elif case == "lin720":
     src = B.rand_u8(64, 1080, 1920, 3)
     fn = lambda: vacv.resize(src, vacv.NHWC, 1280, 720)
+elif case == "linchw720":   # planes walker, 3 : 2
+    src = B.rand_u8(64, 3, 1080, 1920)
+    fn = lambda: vacv.resize(src, vacv.NCHW, 1280, 720)
+elif case == "linchw4k":    # planes walker, 2 : 1
+    src = B.rand_u8(16, 3, 2160, 3840)
+    fn = lambda: vacv.resize(src, vacv.NCHW, 1920, 1080)
 elif case == "linchw":
     src = B.rand_u8(64, 3, 1080, 1920)
     fn = lambda: vacv.resize(src, vacv.NCHW, 640, 360)
