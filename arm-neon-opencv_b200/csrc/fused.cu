@@ -361,7 +361,10 @@ struct PipePlan {
     // plan
     bool eligible; PipeGeom g; const void* kern; int threads, per_sm, sms; size_t smem;
     // padded surfaces through tensor maps (g.tile_maps): the maps bind the surface pool's address and are re-encoded when it changes
-    PipeMaps maps; const void* maps_src; int maps_batch;
+    // (a decoder pool rotates through a few surface buffers: kMapSlots encoded sets are kept, replaced round-robin)
+    static constexpr int kMapSlots = 4;
+    PipeMaps maps;                                   // the band heights; tensor maps of slot 0 when encoded
+    PipeMaps map_slots[kMapSlots]; const void* maps_src[kMapSlots]; int maps_batch[kMapSlots]; int maps_next;
 };
 
 static bool same_key(const PipePlan& p, const YuvSource& y, int w_out, int h_out, int out_dtype, const Canvas& cv, bool pairs_ok, int device) {
@@ -443,7 +446,8 @@ static int build_pipe_plan(PipePlan& plan) {
         best_TH = 0;
     }
     g.tile_maps = by_map ? 1 : 0;
-    plan.maps_src = nullptr;
+    for (int i = 0; i < PipePlan::kMapSlots; ++i) { plan.maps_src[i] = nullptr; plan.maps_batch[i] = 0; }
+    plan.maps_next = 0;
     if (!best_TH) return 0;
     g.TH = best_TH;
     g.tiles_per_frame = (h_out + best_TH - 1) / best_TH;
@@ -519,25 +523,37 @@ static int try_launch_pipe(const uint8_t* src, void* dst, int out_dtype, int bat
     if (total > 0x7fffffffLL - 4096) return 0;
     g.total_tiles = (int)total;
     const int grid = (int)std::min<long long>(total, (long long)plan.sms * plan.per_sm);
-    if (g.tile_maps && (pp->maps_src != src || pp->maps_batch != batch)) {   // (re-)encode the maps for this surface pool: frames are the third dimension
-        const YuvSource& ys = plan.y;
-        const bool planar = ys.fmt == kFmtPlanar;
-        const cuuint64_t frames = (cuuint64_t)batch;
-        const int cw8 = (planar ? ys.w / 2 : ys.w) / 8, chh = (ys.h + 1) / 2;
-        bool ok = true;
-        for (int k = 0; k < kPipeMapHeights && ok; ++k) {
-            if (pp->maps.yh[k])
-                ok = encode_map_3d(&pp->maps.y[k], CU_TENSOR_MAP_DATA_TYPE_UINT64, src, ys.w / 8, ys.h, frames, ys.y_pitch, ys.frame_stride, ys.w / 8, pp->maps.yh[k], 1);
-            if (ok && pp->maps.ch[k]) {
-                ok = encode_map_3d(&pp->maps.c[k], CU_TENSOR_MAP_DATA_TYPE_UINT64, src + ys.c_off, cw8, chh, frames, ys.c_pitch, ys.frame_stride, cw8, pp->maps.ch[k], 1);
-                if (ok && planar)
-                    ok = encode_map_3d(&pp->maps.c2[k], CU_TENSOR_MAP_DATA_TYPE_UINT64, src + ys.c2_off, cw8, chh, frames, ys.c_pitch, ys.frame_stride, cw8, pp->maps.ch[k], 1);
+    const PipeMaps* maps = &pp->maps;   // plans without tensor maps pass the (unused) height table
+    if (g.tile_maps) {   // the encoded maps of this surface pool (frames are the third dimension), or encode them into the next slot
+        int slot = -1;
+        for (int i = 0; i < PipePlan::kMapSlots; ++i)
+            if (pp->maps_src[i] == src && pp->maps_batch[i] == batch) slot = i;
+        if (slot < 0) {
+            slot = pp->maps_next;
+            pp->maps_next = (pp->maps_next + 1) % PipePlan::kMapSlots;
+            PipeMaps& m = pp->map_slots[slot];
+            m = pp->maps;
+            pp->maps_src[slot] = nullptr;
+            const YuvSource& ys = plan.y;
+            const bool planar = ys.fmt == kFmtPlanar;
+            const cuuint64_t frames = (cuuint64_t)batch;
+            const int cw8 = (planar ? ys.w / 2 : ys.w) / 8, chh = (ys.h + 1) / 2;
+            bool ok = true;
+            for (int k = 0; k < kPipeMapHeights && ok; ++k) {
+                if (m.yh[k])
+                    ok = encode_map_3d(&m.y[k], CU_TENSOR_MAP_DATA_TYPE_UINT64, src, ys.w / 8, ys.h, frames, ys.y_pitch, ys.frame_stride, ys.w / 8, m.yh[k], 1);
+                if (ok && m.ch[k]) {
+                    ok = encode_map_3d(&m.c[k], CU_TENSOR_MAP_DATA_TYPE_UINT64, src + ys.c_off, cw8, chh, frames, ys.c_pitch, ys.frame_stride, cw8, m.ch[k], 1);
+                    if (ok && planar)
+                        ok = encode_map_3d(&m.c2[k], CU_TENSOR_MAP_DATA_TYPE_UINT64, src + ys.c2_off, cw8, chh, frames, ys.c_pitch, ys.frame_stride, cw8, m.ch[k], 1);
+                }
             }
+            if (!ok) return set_error(VACV_ERR_CUDA, "nv_resize_normalize_chw: cuTensorMapEncodeTiled failed");
+            pp->maps_src[slot] = src; pp->maps_batch[slot] = batch;
         }
-        if (!ok) return set_error(VACV_ERR_CUDA, "nv_resize_normalize_chw: cuTensorMapEncodeTiled failed");
-        pp->maps_src = src; pp->maps_batch = batch;
+        maps = &pp->map_slots[slot];
     }
-    void* args[] = {(void*)&src, (void*)&dst, (void*)&g, (void*)&mean, (void*)&stddev, (void*)&pp->maps};
+    void* args[] = {(void*)&src, (void*)&dst, (void*)&g, (void*)&mean, (void*)&stddev, (void*)maps};
     const cudaError_t e = cudaLaunchKernel(plan.kern, dim3(grid), dim3(plan.threads), args, plan.smem, s);
     if (e != cudaSuccess) return set_error(VACV_ERR_CUDA, "nv_resize_normalize_chw: %s", cudaGetErrorString(e));
     return 1;

@@ -1037,6 +1037,27 @@ def test_full_size_u8_bilinear_periodic_walker(vacv, oracle, sz):
     assert torch.equal(out[3], vacv.resize(src[3:4], NHWC, wo, ho)[0])
 
 
+def test_fused_pipeline_padded_surfaces_rotating_pools(vacv):
+    """Tensor-map staging binds the maps to a surface pool's address: a caller that rotates through more pools than the plan keeps
+    encoded (4) must get every pool's own pixels, in any order and with changing batch sizes."""
+    w, h, wo, ho, pitch = 1280, 720, 416, 416, 1536
+    mean, std = dev(MEAN), dev(STD)
+    pools, wants = [], []
+    for i in range(6):
+        b = 1 + i % 3
+        dense = _gpu_rand_u8(200 + i, b, h * 3 // 2, w)
+        padded = torch.full((b, h * 3 // 2, pitch), 0x5A, dtype=torch.uint8, device="cuda")
+        padded[:, :, :w] = dense
+        pools.append((padded, b))
+        wants.append(vacv.nv_resize_normalize_chw(dense.reshape(b, -1), w, h, wo, ho, mean, std, False))
+    for i in (0, 1, 2, 3, 4, 5, 0, 3, 5, 1, 4, 2, 2, 0):
+        padded, b = pools[i]
+        got = vacv.yuv_resize_normalize_chw(padded.reshape(-1), vacv.YUV_NV12, w, h, wo, ho, mean, std, y_pitch=pitch, c_pitch=pitch, batch=b)
+        assert torch.equal(got, wants[i])
+    got = vacv.yuv_resize_normalize_chw(pools[2][0].reshape(-1), vacv.YUV_NV12, w, h, wo, ho, mean, std, y_pitch=pitch, c_pitch=pitch, batch=1)
+    assert torch.equal(got[0], wants[2][0])   # same pool, smaller batch: the maps' frame extent follows
+
+
 def test_full_size_config2_padded_surfaces_three_staging_forms(vacv):
     """Config 2 on 256 pitch-2048 NV12 surfaces: tensor-map boxes (default), whole bands with their padding and per-row copies give the
     same bytes, and those equal the dense path on the same frames re-packed without padding."""
