@@ -49,7 +49,9 @@ int launch_linear3_period(const uint8_t* src, uint8_t* dst, int images, int w, i
     if ((long long)w * Q != (long long)wo * P || wo % S::NCOL != 0) return 0;
     // bulk copies and the staged flush move aligned 16-byte chunks
     if (((size_t)wo * C) % 16 != 0 || ((size_t)w * C) % 16 != 0 || ((uintptr_t)dst % 16) != 0 || ((uintptr_t)src % 16) != 0) return 0;
-    if (h > 2 * ho || h < 2 || ho < 1) return 0;   // the walk filters every source row between a segment's first and last tap row
+    // the walk filters every source row between a segment's first and last tap row: up to a vertical ratio of 3 (where one row in three
+    // is copied without being used) that is still faster than the gather kernel (1080p -> 768x432: see profiles/r2f_bench_ops.txt)
+    if (h > 3 * ho || h < 2 || ho < 1) return 0;
     LinPeriodGeom g;
     g.w = w; g.h = h; g.wo = wo; g.ho = ho;
     g.src_image = (size_t)w * h * C; g.dst_image = (size_t)wo * ho * C;
@@ -102,6 +104,8 @@ template <bool kSigned>
 int launch_any(const uint8_t* src, uint8_t* dst, int images, int w, int h, int wo, int ho, cudaStream_t s) {
     int rc = launch_linear3_period<3, 2, 4, kSigned>(src, dst, images, w, h, wo, ho, s);            // 3 : 2 (1920 -> 1280): 8 columns per thread
     if (rc == 0) rc = launch_linear3_period<4, 3, 4, kSigned>(src, dst, images, w, h, wo, ho, s);   // 4 : 3 (2560 -> 1920): 12 columns
+    if (rc == 0) rc = launch_linear3_period<5, 2, 4, kSigned>(src, dst, images, w, h, wo, ho, s);   // 5 : 2 (1920 -> 768, 1280 -> 512): 8 columns
+    if (rc == 0) rc = launch_linear3_period<5, 3, 4, kSigned>(src, dst, images, w, h, wo, ho, s);   // 5 : 3 (1920 -> 1152, 1280 -> 768): 12 columns
     if (rc == 0 && knob(kKnobLinearV) != 2) rc = launch_linear3_period<2, 1, 8, kSigned>(src, dst, images, w, h, wo, ho, s);   // 2 : 1 (3840 -> 1920): 8 columns
     if (rc == 0) rc = launch_linear3_period<2, 1, 4, kSigned>(src, dst, images, w, h, wo, ho, s);   // 2 : 1, widths that are not multiples of 8 columns (LINEAR_V=2: always): 4 columns
     return rc;
@@ -113,6 +117,8 @@ int launch_any_planes(const uint8_t* src, uint8_t* dst, int planes, int w, int h
     int rc = launch_linear3_period<3, 2, 8, kSigned, 1>(src, dst, planes, w, h, wo, ho, s);            // 3 : 2: 16 columns per thread
     if (rc == 0) rc = launch_linear3_period<4, 3, 8, kSigned, 1>(src, dst, planes, w, h, wo, ho, s);   // 4 : 3: 24 columns
     if (rc == 0) rc = launch_linear3_period<2, 1, 16, kSigned, 1>(src, dst, planes, w, h, wo, ho, s);  // 2 : 1: 16 columns
+    if (rc == 0) rc = launch_linear3_period<5, 2, 8, kSigned, 1>(src, dst, planes, w, h, wo, ho, s);   // 5 : 2: 16 columns
+    if (rc == 0) rc = launch_linear3_period<5, 3, 8, kSigned, 1>(src, dst, planes, w, h, wo, ho, s);   // 5 : 3: 24 columns
     return rc;
 }
 

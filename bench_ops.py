@@ -367,15 +367,17 @@ def ops2(iters):   # shapes off the headline path: planar layouts, fp32 gathers,
     ms, _ = timeit(lambda: vacv.resize(bgr, vacv.NHWC, 1280, 720), iters)
     vacv.lib.vacv_cuda_set_tuning(b"LINEAR_V", 0)
     report("   same, persistent pipeline (LINEAR_V=1)", ms, b * 1280 * 720, b * (1920 * 1080 * 3 + 1280 * 720 * 3))
-    for (w, h, wo, ho, n, what) in ((2560, 1440, 1920, 1080, 32, "4 : 3"), (3840, 2160, 1920, 1080, 16, "2 : 1")):
-        big = rand_u8(n, h, w, 3)
+    for (w, h, wo, ho, n, what) in ((2560, 1440, 1920, 1080, 32, "4 : 3"), (3840, 2160, 1920, 1080, 16, "2 : 1"), (1920, 1080, 768, 432, 64, "5 : 2"),
+                                    (1920, 1080, 1152, 648, 64, "5 : 3")):
+        big = bgr if w == 1920 else rand_u8(n, h, w, 3)
         for v in (0, 1):
             vacv.lib.vacv_cuda_set_tuning(b"LINEAR_V", v)
             ms, _ = timeit(lambda: vacv.resize(big, vacv.NHWC, wo, ho), iters)
             vacv.lib.vacv_cuda_set_tuning(b"LINEAR_V", 0)
             report(f"op2 resize linear u8 hwc {w}x{h}->{wo}x{ho} x{n}" if v == 0 else "   same, persistent pipeline (LINEAR_V=1)", ms, n * wo * ho,
                    n * (w * h * 3 + wo * ho * 3), f"{what}, periodic walker" if v == 0 else "")
-        del big
+        if big is not bgr:
+            del big
     ms, _ = timeit(lambda: vacv.resize(chw, vacv.NCHW, 1280, 720, vacv.INTER_CUBIC) if False else vacv.resize(fchw, vacv.NCHW, 1280, 720, vacv.INTER_CUBIC), iters)
     report("op2 resize cubic f32 chw 1080p->1280x720 x16", ms, 16 * 1280 * 720, 16 * 4 * (1920 * 1080 * 3 + 1280 * 720 * 3), "3 : 2, periodic walker")
     vacv.lib.vacv_cuda_set_tuning(b"CUBIC_V", 1)   # A/B: the one-column walker

@@ -245,6 +245,11 @@ LINEAR_PERIOD_CASES = [
     ((2560, 90), (1920, 77)),    # 4:3, five strips
     ((128, 50), (64, 25)),       # 2:1 both ways
     ((3840, 64), (1920, 40)),    # 2:1, fifteen strips
+    ((640, 100), (256, 40)),     # 5:2 both ways (vertical ratio 2.5: one source row in five is walked without being used)
+    ((1920, 270), (768, 108)),   # 5:2, three strips
+    ((320, 90), (192, 54)),      # 5:3 both ways
+    ((1920, 100), (1152, 60)),   # 5:3, three strips
+    ((384, 180), (256, 60)),     # 3:2 with vertical 3:1 (the limit of the walk)
 ]
 
 
@@ -279,6 +284,8 @@ LINEAR_PERIOD_PLANE_CASES = [
     ((2560, 90), (1920, 77)),     # 4:3, wide planes (no pipeline kernel takes 1920 columns)
     ((128, 50), (64, 25)),        # 2:1 both ways
     ((3840, 64), (1920, 40)),     # 2:1, wide planes
+    ((640, 100), (256, 40)),      # 5:2 both ways
+    ((1920, 90), (1152, 54)),     # 5:3 both ways, 1.5 strips
 ]
 
 
