@@ -67,12 +67,18 @@ int launch_linear3_period(const uint8_t* src, uint8_t* dst, int images, int w, i
     g.cta_strips = (g.warp_strips + warps - 1) / warps;
     const size_t per_warp = (size_t)kPdStageRows * S::kWarpRow + (size_t)kPdRing * S::kWarpSpan + kPdRing * 8;
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(64 / warps, (200 * 1024) / (per_warp * warps + 2048)));   // resident CTAs per SM: warp slots, shared memory (4 - 6 in practice)
-    const long long want = 6LL * per_sm * sm_count(current_device());
+    // waves of CTAs to aim for and the shortest segment, by measurement (profiles/_lin_segs.py): BGR is best at ~12 waves of short segments
+    // (1080p -> 720p x64: 0.088 ms at 11 rows per segment, 0.092 at 22, 0.102 at 45), planes -- two to three times the columns per thread,
+    // hence a heavier prologue -- at ~4 waves of >= 16 rows (CHW 1080p -> 720p x64: 0.093 ms at 45 rows, 0.105 at 11)
+    // (planes at 2 : 1 -- four source bytes per output byte, waiting on its row copies -- behave like BGR: 16 4K frames 0.147 ms at 18 rows,
+    // 0.103 at 8)
+    constexpr bool kShort = C == 3 || (P == 2 && Q == 1);
+    constexpr int kWaves = kShort ? 12 : 4, kMinRows = kShort ? 8 : 16;
+    const long long want = (long long)kWaves * per_sm * sm_count(current_device());
     const long long per_seg = (long long)g.cta_strips * images;
-    // about six waves of CTAs, but segments of at least 8 output rows (a segment re-reads one or two source rows and pays the table
-    // prologue).  Sweep of segments per strip on B200 (profiles/_lin_segs.py): one 1080p frame per call 0.0151 ms at >= 32 rows per
+    // a segment re-reads one or two source rows and pays the table prologue, but small batches need the CTAs.  Sweep of segments per strip on B200 (profiles/_lin_segs.py): one 1080p frame per call 0.0151 ms at >= 32 rows per
     // segment (46 CTAs), 0.0069 at 5 rows; 16 4K frames 0.0878 -> 0.0837 ms; large batches are within 5 % from 11 to 45 rows.
-    const long long segs = std::max<long long>(1, std::min<long long>((want + per_seg - 1) / per_seg, (ho + 7) / 8));
+    const long long segs = std::max<long long>(1, std::min<long long>((want + per_seg - 1) / per_seg, (ho + kMinRows - 1) / kMinRows));
     int rps = (int)((ho + segs - 1) / segs);
     if (const int v = knob(kKnobWalkSegs)) rps = (ho + std::max(1, v) - 1) / std::max(1, v);   // tuning knob: vertical segments per column strip
     rps = std::min(512, std::max(rps, 1));
