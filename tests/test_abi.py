@@ -90,6 +90,18 @@ def test_argument_validation_without_gpu():
     assert vacv.lib.vacv_cuda_resize(p, p, 1, 8, 8, 3, vacv.INT8, vacv.NHWC, 4, 4, 0, 0, None) == -2   # INTER_NEAREST
 
 
+def test_tuning_switches_without_gpu():
+    """vacv_cuda_set_tuning is host-only: every switch DESIGN.md lists is known by name, unknown names are rejected, and a switch can be
+    set back (the kernels never read the environment on the call path)."""
+    import vacv_b200 as vacv
+    for name in (b"PIPE_NCOL", b"RPIPE_NCOL", b"WARP_GATHER", b"NO_RPIPE", b"RESIZE_NORMALIZE_GATHER", b"WALK_SEGS", b"WALK_SYNC", b"WALK2_SYNC",
+                 b"CUBIC3", b"CUBIC_V", b"PIPE_ROWS", b"STREAM_QPT", b"WARP_V", b"LINEAR_V"):
+        assert vacv.lib.vacv_cuda_set_tuning(name, 1) == 0, name
+        assert vacv.lib.vacv_cuda_set_tuning(name, 0) == 0, name
+    assert vacv.lib.vacv_cuda_set_tuning(b"NO_SUCH_SWITCH", 1) == -1
+    assert b"unknown" in vacv.lib.vacv_cuda_last_error()
+
+
 def test_host_matrix_helpers_match_oracle(oracle):
     import vacv_b200 as vacv
     m = [0.849158, 0.012257, -474.827, -0.01225, 0.849158, -379.18]   # test_warp_affine.cpp:31-32
